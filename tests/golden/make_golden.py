@@ -1,0 +1,172 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference (/root/reference, CPU fp32) on
+the seeded synthetic weights/inputs of video_llava_seg_b200.synth, and at the same time pins the
+oracle restatement (oracle/sam2_path.py) against it.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+What is patched on the reference side (and why):
+  * `SAM2Base.forward_image` / `load_video_frames`: the image encoder is outside the hot path, so
+    the reference predictor is fed the synthetic backbone features directly.
+  * `sam2.utils.misc.get_connected_components`: the reference ships no build recipe for sam2._C
+    and its kernel has no CPU path, so hole filling would be silently skipped
+    (utils/misc.py:321-336).  The C restatement oracle/cc_oracle.c stands in for it.
+Everything else (memory attention, decoder, memory encoder, tracking logic) is reference code.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+from oracle import cc as cc_oracle  # noqa: E402
+from oracle import ref_import, sam2_path as O  # noqa: E402
+from video_llava_seg_b200 import synth  # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def maxdiff(a, b):
+    return (a.float() - b.float()).abs().max().item()
+
+
+def load_synth_weights(model, sd):
+    ref_sd = model.state_dict()
+    hot = {k: v for k, v in ref_sd.items() if not k.startswith("image_encoder.")}
+    assert set(hot) == set(sd), (set(hot) ^ set(sd))
+    for k, v in hot.items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("image_encoder.") for k in missing)
+
+
+def module_cases(model, sd):
+    g = torch.Generator().manual_seed(1234)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    out = {}
+    # ---- memory attention: 16x16 query grid, 2 memory frames + 2 pointers (8 tokens), B=2
+    nq, b = 256, 2
+    nk = 2 * nq + 8
+    curr, curr_pos = rn(nq, b, 256) * 0.5, rn(nq, b, 256) * 0.5
+    mem, mem_pos = rn(nk, b, 64) * 0.5, rn(nk, b, 64) * 0.5
+    ref = model.memory_attention(curr=[curr], curr_pos=[curr_pos], memory=mem, memory_pos=mem_pos,
+                                 num_obj_ptr_tokens=8)
+    ora = O.memory_attention(sd, curr, mem, curr_pos, mem_pos, 8)
+    print("memory_attention oracle-vs-ref", maxdiff(ref, ora))
+    assert maxdiff(ref, ora) < 2e-5
+    out["memattn_out"] = ref.numpy()
+    # ---- mask decoder, video flavour (multimask, repeat_image=False) and LLaVA flavour
+    emb = rn(2, 256, 64, 64) * 0.5
+    s0, s1 = rn(2, 32, 256, 256) * 0.3, rn(2, 64, 128, 128) * 0.3
+    sparse = rn(2, 2, 256)
+    dense = model.sam_prompt_encoder.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(2, -1, 64, 64)
+    pe = model.sam_prompt_encoder.get_dense_pe()
+    assert maxdiff(pe, O.dense_pe(sd)) < 1e-6
+    ref = model.sam_mask_decoder(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse,
+                                 dense_prompt_embeddings=dense, multimask_output=True, repeat_image=False,
+                                 high_res_features=[s0, s1])
+    ora = O.mask_decoder(sd, emb, pe, sparse, dense, True, False, [s0, s1])
+    d = [maxdiff(r, o) for r, o in zip(ref, ora)]
+    print("mask_decoder(video) oracle-vs-ref", d)
+    assert max(d) < 5e-5
+    out["dec_video_masks_s4"] = ref[0][:, :, ::4, ::4].numpy()
+    out["dec_video_iou"], out["dec_video_tok"], out["dec_video_obj"] = (x.numpy() for x in ref[1:])
+    seg = rn(3, 1, 256)
+    dense3 = dense[:1].expand(3, -1, -1, -1)
+    ref = model.sam_mask_decoder(image_embeddings=emb[:1], image_pe=pe, sparse_prompt_embeddings=seg,
+                                 dense_prompt_embeddings=dense3, multimask_output=False, repeat_image=True,
+                                 high_res_features=[s0[:1], s1[:1]])
+    ora = O.mask_decoder(sd, emb[:1], pe, seg, dense3, False, True, [s0[:1], s1[:1]])
+    d = [maxdiff(r, o) for r, o in zip(ref, ora)]
+    print("mask_decoder(llava) oracle-vs-ref", d)
+    assert max(d) < 5e-5
+    out["dec_llava_masks_s4"] = ref[0][:, :, ::4, ::4].numpy()
+    out["dec_llava_iou"] = ref[1].numpy()
+    # ---- memory encoder, full size, B=2
+    pix = rn(2, 256, 64, 64) * 0.5
+    msk = torch.sigmoid(rn(2, 1, 1024, 1024) * 3) * 20 - 10
+    ref = model.memory_encoder(pix, msk, skip_mask_sigmoid=True)
+    ora = O.memory_encoder(sd, pix, msk, True)
+    print("memory_encoder oracle-vs-ref", maxdiff(ref["vision_features"], ora["vision_features"]),
+          maxdiff(ref["vision_pos_enc"][0], ora["vision_pos_enc"][0]))
+    assert maxdiff(ref["vision_features"], ora["vision_features"]) < 5e-5
+    assert maxdiff(ref["vision_pos_enc"][0], ora["vision_pos_enc"][0]) < 1e-6
+    out["memenc_feat_s2"] = ref["vision_features"][:, :, ::2, ::2].numpy()
+    out["memenc_pos0"] = ref["vision_pos_enc"][0][0].numpy()
+    np.savez_compressed(os.path.join(OUT, "modules.npz"), **out)
+
+
+def run_reference_clip(model, clip, batch, num_frames):
+    import sam2.sam2_video_predictor as vp
+    import sam2.utils.misc as misc
+
+    misc.get_connected_components = lambda m: cc_oracle.cc_label(m)
+    vp.fill_holes_in_mask_scores.__globals__["get_connected_components"] = misc.get_connected_components
+    imgs = torch.arange(num_frames, dtype=torch.float32).view(-1, 1, 1, 1).expand(-1, 3, 1, 1).contiguous()
+    vp.load_video_frames = lambda **kw: (imgs, 1024, 1024)
+
+    def forward_image(img):
+        t = int(img.flatten()[0].item())
+        f = clip.frame(t, 1)
+        feat = f["vision_feat"].permute(1, 2, 0).reshape(1, 256, 64, 64)
+        pos = f["vision_pos"].permute(1, 2, 0).reshape(1, 256, 64, 64)
+        return {"backbone_fpn": [f["feat_s0"], f["feat_s1"], feat],
+                "vision_pos_enc": [torch.zeros(1, 1, 256, 256), torch.zeros(1, 1, 128, 128), pos]}
+
+    model.forward_image = forward_image
+    state = model.init_state(video_path="synthetic")
+    prompt = clip.point_prompt(batch)
+    for o in range(batch):
+        model.add_new_points_or_box(state, frame_idx=0, obj_id=o + 1,
+                                    points=prompt["point_coords"][o].tolist(), labels=[1])
+    per_frame = []
+    for fi, obj_ids, video_res in model.propagate_in_video(state):
+        key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
+        o = state["output_dict"][key][fi]
+        per_frame.append(dict(pred_masks=o["pred_masks"].clone(), obj_ptr=o["obj_ptr"].clone(),
+                              object_score_logits=o["object_score_logits"].clone(),
+                              maskmem_features=o["maskmem_features"].clone(), video_res=video_res.clone()))
+    return per_frame
+
+
+def clip_case(model, sd, name, seed, num_frames, batch):
+    clip = synth.SyntheticClip(seed, num_frames)
+    ref = run_reference_clip(model, clip, batch, num_frames)
+    ora = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, batch), clip.point_prompt(batch), num_frames,
+                      cc=cc_oracle.cc_label)
+    out = {}
+    for t, (r, o) in enumerate(zip(ref, ora)):
+        d_mask = maxdiff(r["pred_masks"], o["pred_masks"])
+        d_ptr = maxdiff(r["obj_ptr"], o["obj_ptr"])
+        d_mem = maxdiff(r["maskmem_features"], o["maskmem_features"])
+        fg = (r["pred_masks"] > 0).float().mean().item()
+        print(f"{name} t={t} oracle-vs-ref mask {d_mask:.2e} ptr {d_ptr:.2e} mem {d_mem:.2e} | "
+              f"obj {r['object_score_logits'].flatten().tolist()} fg {fg:.4f} "
+              f"range [{r['pred_masks'].min():.2f},{r['pred_masks'].max():.2f}]")
+        assert d_mask < 2e-3 and d_ptr < 1e-3, "oracle drifted from the reference"
+        out[f"mask_s2_{t}"] = r["pred_masks"][:, :, ::2, ::2].numpy()
+        out[f"maskbits_{t}"] = np.packbits((r["pred_masks"] > 0).numpy().reshape(batch, -1), axis=1)
+        out[f"obj_ptr_{t}"] = r["obj_ptr"].numpy()
+        out[f"obj_score_{t}"] = r["object_score_logits"].numpy()
+        out[f"mem_s4_{t}"] = r["maskmem_features"].float()[:, :, ::4, ::4].numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+
+
+def main():
+    assert ref_import.available(), "needs /root/reference (build container only)"
+    torch.set_num_threads(os.cpu_count())
+    sd = synth.init_state_dict(0)
+    model = ref_import.build_video_predictor("t", with_image_encoder=True)
+    load_synth_weights(model, sd)
+    with torch.inference_mode():
+        module_cases(model, sd)
+        clip_case(model, sd, "clip_b1_t8", seed=1, num_frames=8, batch=1)
+        clip_case(model, sd, "clip_b2_t4", seed=2, num_frames=4, batch=2)
+    print("golden vectors written to", OUT)
+
+
+if __name__ == "__main__":
+    main()
