@@ -1,0 +1,143 @@
+"""GPU parity tests of the building-block kernels, called through the C ABI (libvls_b200.so):
+tcgen05 GEMM epilogues and d=256 flash attention against torch fp32 math on the same bf16-rounded
+inputs (tolerances stated per test), connected components bit-exact against the C oracle."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev(vls_lib):
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+def _rand(shape, dev, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dev)
+
+
+@pytest.mark.parametrize("M,N,K,B", [(128, 64, 64, 1), (4096, 256, 256, 1), (300, 200, 192, 2), (4096, 2048, 256, 1),
+                                     (4096, 256, 2048, 1), (256, 28736, 64, 1), (1000, 384, 256, 3)])
+def test_gemm_plain(dev, M, N, K, B):
+    from video_llava_seg_b200 import ops
+
+    a = _rand((B, M, K), dev, 1).bfloat16()
+    w = _rand((N, K), dev, 2, 1.0 / math.sqrt(K)).bfloat16()
+    ldc = (N + 7) // 8 * 8
+    outbuf = torch.zeros((B, M, ldc), device=dev, dtype=torch.float32)
+    out = ops.gemm(a, w, out=outbuf[:, :, :N])
+    ref = a.float() @ w.float().t()
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), err
+
+
+def test_gemm_epilogues(dev):
+    from video_llava_seg_b200 import ops
+
+    M, N, K = 1024, 256, 256
+    a = _rand((M, K), dev, 3).bfloat16()
+    w = _rand((N, K), dev, 4, 1.0 / 16).bfloat16()
+    bias = _rand((N,), dev, 5)
+    res = _rand((M, N), dev, 6)
+    # bias + relu + residual, f32 out
+    out = ops.gemm(a, w, bias=bias, act="relu", residual=res, out_dtype=torch.float32)
+    ref = torch.relu(a.float() @ w.float().t() + bias) + res
+    assert (out - ref).abs().max().item() < 5e-3
+    # gelu, bf16 out
+    out = ops.gemm(a, w, bias=bias, act="gelu", out_dtype=torch.bfloat16)
+    ref = torch.nn.functional.gelu(a.float() @ w.float().t() + bias)
+    assert (out.float() - ref).abs().max().item() < 3e-2
+    # per-row bias (used for V^T = Wv X^T)
+    brow = _rand((M,), dev, 7)
+    out = ops.gemm(a, w, bias=brow, bias_mode=2, out_dtype=torch.float32)
+    ref = a.float() @ w.float().t() + brow[:, None]
+    assert (out - ref).abs().max().item() < 5e-3
+
+
+def test_gemm_rope(dev):
+    """RoPE epilogue == apply_rotary_enc (position_encoding.py:195-222) on the projected tensor."""
+    from oracle import sam2_path as O
+    from video_llava_seg_b200 import ops
+
+    side, K = 16, 64
+    nq = side * side
+    M = 2 * nq + 8  # two repeated memory frames + 8 un-rotated pointer tokens
+    a = _rand((M, K), dev, 8).bfloat16()
+    w = _rand((256, K), dev, 9, 1.0 / 8).bfloat16()
+    bias = _rand((256,), dev, 10, 0.1)
+    cos, sin = O.axial_rope_table(side, side)
+    out = ops.gemm(a, w, bias=bias, rope=(cos.to(dev).contiguous(), sin.to(dev).contiguous()), rope_rows=2 * nq,
+                   out_dtype=torch.float32)
+    y = (a.float() @ w.float().t() + bias).cpu()
+    ref = torch.cat([O.apply_rope(y[None, None, : 2 * nq], cos.repeat(2, 1), sin.repeat(2, 1))[0, 0], y[2 * nq:]], 0)
+    assert (out.cpu() - ref).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 256, 520, 1), (2, 256, 1000, 2), (1, 4096, 4096, 0),
+                                            (1, 4096, 28736, 0), (1, 4096, 28700, 4)])
+def test_attention_d256(dev, B, Nq, Nk, splits):
+    """vs softmax(QK^T/16)V in fp32 on the same bf16 inputs; P is rounded to bf16 inside the kernel
+    (as flash-attention does), so the tolerance is 2e-2 on outputs of magnitude ~1."""
+    from video_llava_seg_b200 import ops
+
+    q = _rand((B, Nq, 256), dev, 11).bfloat16()
+    k = _rand((B, Nk, 256), dev, 12).bfloat16()
+    v = _rand((B, Nk, 256), dev, 13).bfloat16()
+    ld = (Nk + 63) // 64 * 64
+    vt = torch.zeros((B, 256, ld), device=dev, dtype=torch.bfloat16)
+    vt[:, :, :Nk] = v.transpose(1, 2)
+    out = ops.attention_d256(q, k, vt[:, :, :Nk] if ld == Nk else vt, splits=splits)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+
+
+@pytest.mark.parametrize("shape,density", [((1, 1, 256, 256), 0.5), ((8, 1, 256, 256), 0.62), ((3, 1, 64, 96), 0.4),
+                                           ((2, 1, 2, 2), 0.5), ((1, 1, 250, 130), 0.55), ((2, 1, 512, 384), 0.6),
+                                           ((1, 1, 1024, 1024), 0.58), ((4, 1, 256, 256), 0.0), ((4, 1, 256, 256), 1.0)])
+def test_cc_bit_exact(dev, shape, density):
+    from oracle import cc as cc_oracle
+    from video_llava_seg_b200.utils.misc import get_connected_components
+
+    g = torch.Generator().manual_seed(hash(shape) % 1000 + int(density * 100))
+    m = torch.rand(shape, generator=g) < density
+    labels, counts = get_connected_components(m.to(dev))
+    rl, rc = cc_oracle.cc_label(m)
+    assert torch.equal(labels.cpu(), rl)
+    assert torch.equal(counts.cpu(), rc)
+
+
+def test_cc_structured_and_errors(dev):
+    from oracle import cc as cc_oracle
+    from video_llava_seg_b200.utils.misc import fill_holes_in_mask_scores, get_connected_components
+
+    m = torch.zeros(2, 1, 256, 256, dtype=torch.bool)
+    m[0, 0, 10:200, 20:220] = True
+    m[0, 0, 50:60, 50:60] = False          # a hole (background component) inside
+    m[0, 0, ::7, :] ^= True                 # stripes
+    m[1, 0] = torch.arange(256).view(1, -1).expand(256, -1) % 3 == 0  # thin vertical lines
+    for t in (m, ~m):
+        labels, counts = get_connected_components(t.to(dev))
+        rl, rc = cc_oracle.cc_label(t)
+        assert torch.equal(labels.cpu(), rl) and torch.equal(counts.cpu(), rc)
+    with pytest.raises(RuntimeError):
+        get_connected_components(torch.zeros(1, 1, 5, 4, dtype=torch.bool, device=dev))
+    with pytest.raises(RuntimeError):
+        get_connected_components(torch.zeros(1, 1, 4, 4, dtype=torch.bool))  # CPU tensor
+    assert get_connected_components(torch.zeros(0, 1, 4, 4, dtype=torch.bool, device=dev))[0].shape == (0, 1, 4, 4)
+    # fused hole filling == reference recipe on top of the oracle labels (utils/misc.py:322-325)
+    from oracle import sam2_path as O
+    g = torch.Generator().manual_seed(5)
+    for shape in ((3, 1, 256, 256), (1, 1, 512, 512)):
+        s = torch.randn(shape, generator=g)
+        s = torch.nn.functional.avg_pool2d(s, 5, 1, 2) * 3
+        got = fill_holes_in_mask_scores(s.to(dev), 8)
+        ref = O.fill_holes_in_mask_scores(s, 8, cc=cc_oracle.cc_label)
+        assert torch.equal(got.cpu(), ref)
+        assert (got.cpu() != s).any()

@@ -1,0 +1,84 @@
+"""ctypes binding of libvls_b200.so (C ABI: include/vls_b200.h).
+
+The library is the product: if it is missing or a call fails this module RAISES -- there is no
+eager/PyTorch/CPU fallback anywhere on the path (the reference instead swallows a missing
+`sam2._C` and silently skips hole filling, sam2/utils/misc.py:321-336).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvls_b200.so")
+_lib = None
+
+c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
+                                            ctypes.c_size_t)
+
+
+class GemmDesc(ctypes.Structure):
+    _fields_ = [
+        ("A", c_void_p), ("lda", c_ll), ("a_bstride", c_ll),
+        ("W", c_void_p), ("ldw", c_ll), ("w_bstride", c_ll),
+        ("M", c_int), ("N", c_int), ("K", c_int), ("batch", c_int),
+        ("bias", c_void_p), ("bias_mode", c_int),
+        ("act", c_int),
+        ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("rope_period", c_int), ("rope_rows", c_int),
+        ("residual", c_void_p), ("ld_res", c_ll), ("res_bstride", c_ll),
+        ("C", c_void_p), ("c_bf16", c_int), ("ldc", c_ll), ("c_bstride", c_ll),
+    ]
+
+
+def _declare(lib):
+    lib.vls_last_error.restype = ctypes.c_char_p
+    lib.vls_abi_version.restype = c_int
+    lib.vls_cc_workspace_bytes.restype = c_size_t
+    lib.vls_cc_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vls_cc_label.restype = c_int
+    lib.vls_cc_label.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vls_fill_holes_workspace_bytes.restype = c_size_t
+    lib.vls_fill_holes_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vls_fill_holes.restype = c_int
+    lib.vls_fill_holes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_size_t, c_void_p]
+    lib.vls_gemm_bf16.restype = c_int
+    lib.vls_gemm_bf16.argtypes = [ctypes.POINTER(GemmDesc), c_void_p]
+    lib.vls_attention_workspace_bytes.restype = c_size_t
+    lib.vls_attention_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.vls_attention_d256.restype = c_int
+    lib.vls_attention_d256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
+                                       c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t, c_void_p]
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raise loudly if the CUDA extension is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: the sm_100a CUDA extension is the only implementation of this path "
+                "(no CPU fallback). Build it with `python -m video_llava_seg_b200.build`.")
+        handle = ctypes.CDLL(LIB_PATH)
+        _declare(handle)
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().vls_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"libvls_b200 {what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("inputs must be a CUDA tensor")  # connected_components.cu:215

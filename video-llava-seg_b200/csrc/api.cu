@@ -1,0 +1,63 @@
+// extern "C" entry points of libvls_b200.so (declared in include/vls_b200.h).
+#include "vls_b200.h"
+
+#include "kernels.h"
+
+using namespace vls;
+
+extern "C" {
+
+const char* vls_last_error(void) { return last_error(); }
+int vls_abi_version(void) { return 1; }
+
+size_t vls_cc_workspace_bytes(int n, int h, int w) { return cc_workspace_bytes(n, h, w, false); }
+int vls_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* workspace,
+                 size_t workspace_bytes, vls_stream_t stream) {
+  return launch_cc_label(img, n, h, w, labels, counts, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+size_t vls_fill_holes_workspace_bytes(int n, int h, int w) { return cc_workspace_bytes(n, h, w, true); }
+int vls_fill_holes(float* scores, int n, int h, int w, int max_area, float fill_value, void* workspace,
+                   size_t workspace_bytes, vls_stream_t stream) {
+  return launch_fill_holes(scores, n, h, w, max_area, fill_value, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int vls_gemm_bf16(const vls_gemm_desc* d, vls_stream_t stream) {
+  VLS_REQUIRE(d != nullptr, "gemm: null descriptor");
+  GemmArgs a;
+  a.A = d->A; a.lda = d->lda; a.a_bstride = d->a_bstride;
+  a.W = d->W; a.ldw = d->ldw; a.w_bstride = d->w_bstride;
+  a.M = d->M; a.N = d->N; a.K = d->K; a.batch = d->batch;
+  a.bias = d->bias; a.bias_mode = d->bias_mode; a.act = d->act;
+  a.rope_cos = d->rope_cos; a.rope_sin = d->rope_sin; a.rope_period = d->rope_period; a.rope_rows = d->rope_rows;
+  a.residual = d->residual; a.ld_res = d->ld_res; a.res_bstride = d->res_bstride;
+  a.C = d->C; a.c_bf16 = d->c_bf16; a.ldc = d->ldc; a.c_bstride = d->c_bstride;
+  return launch_gemm(a, (cudaStream_t)stream);
+}
+
+size_t vls_attention_workspace_bytes(int B, int Nq, int Nk, int splits) {
+  if (splits <= 0) splits = attn_pick_splits(B, Nq, Nk);
+  return attn_workspace_bytes(B, Nq, splits);
+}
+
+int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
+                       long long k_bstride, const void* Vt, long long ldvt, long long vt_bstride, int B, int Nq, int Nk,
+                       float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
+                       size_t workspace_bytes, vls_stream_t stream) {
+  if (splits <= 0) splits = attn_pick_splits(B, Nq, Nk);
+  AttnArgs a;
+  a.Q = Q; a.ldq = ldq; a.q_bstride = q_bstride;
+  a.K = K; a.ldk = ldk; a.k_bstride = k_bstride;
+  a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = vt_bstride;
+  a.B = B; a.Nq = Nq; a.Nk = Nk; a.scale = scale; a.splits = splits;
+  a.O = O; a.ldo = ldo; a.o_bstride = o_bstride;
+  if (splits > 1) {
+    const size_t need = attn_workspace_bytes(B, Nq, splits);
+    VLS_REQUIRE(workspace && workspace_bytes >= need, "attention: workspace too small (%zu < %zu)", workspace_bytes,
+                need);
+    a.part_o = reinterpret_cast<float*>(workspace);
+    a.part_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)B * splits * Nq * 256 * 4));
+  }
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+}  // extern "C"

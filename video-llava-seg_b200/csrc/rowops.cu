@@ -1,0 +1,285 @@
+// Bandwidth kernels around the GEMMs: LayerNorm over 256 channels (warp per row, 128-bit loads),
+// layout/precision preparation (seq-first / NCHW -> batch-major token rows, bf16 rounding, fused
+// "a + alpha*b"), and the small token-side linears of the mask decoder (warp per output).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace vls {
+
+namespace {
+
+__device__ __forceinline__ float ld_any(const void* p, long long i, int is_bf16) {
+  return is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(p)[i]) : reinterpret_cast<const float*>(p)[i];
+}
+
+// ------------------------------------------------------------------ LayerNorm, C = 256
+// x: f32 rows [B][T][256] contiguous. One warp per row, lane owns channels [8*lane, 8*lane+8).
+__global__ void ln256_kernel(const float* __restrict__ x, int B, int T, const float* __restrict__ w,
+                             const float* __restrict__ bsh, float eps, int gelu, float* __restrict__ out_f32,
+                             long long f_sb, long long f_st, bf16* __restrict__ out_bf16, long long h_sb,
+                             long long h_st) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= (long long)B * T) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(row / T), t = (int)(row % T);
+  const float4* src = reinterpret_cast<const float4*>(x + row * 256 + lane * 8);
+  const float4 a = src[0], c = src[1];
+  float v[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += v[i];
+  const float mean = warp_sum(s) * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] -= mean;
+    q += v[i] * v[i];
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + eps);
+  const float4 w0 = reinterpret_cast<const float4*>(w + lane * 8)[0], w1 = reinterpret_cast<const float4*>(w + lane * 8)[1];
+  const float4 b0 = reinterpret_cast<const float4*>(bsh + lane * 8)[0], b1 = reinterpret_cast<const float4*>(bsh + lane * 8)[1];
+  const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+  const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = v[i] * rstd * ww[i] + bb[i];
+    if (gelu) v[i] = gelu_erf(v[i]);
+  }
+  if (out_f32) {
+    float4* o = reinterpret_cast<float4*>(out_f32 + b * f_sb + t * f_st + lane * 8);
+    o[0] = make_float4(v[0], v[1], v[2], v[3]);
+    o[1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  if (out_bf16) {
+    *reinterpret_cast<uint4*>(out_bf16 + b * h_sb + t * h_st + lane * 8) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
+// ------------------------------------------------------------------ out[b][t][c] = a + alpha * p
+// a, p: element (t, b, c) at  t*s_t + b*s_b + c  (f32 or bf16); C % 4 == 0.  out rows contiguous.
+__global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long long a_st, long long a_sb,
+                                 const void* __restrict__ p, int p_bf16, long long p_st, long long p_sb, float alpha,
+                                 int B, int T, int C, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total4 = (long long)B * T * C / 4;
+  if (i4 >= total4) return;
+  const long long e = i4 * 4;
+  const int c = (int)(e % C);
+  const long long bt = e / C;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    v[i] = ld_any(a, t * a_st + b * a_sb + c + i, a_bf16);
+    if (p) v[i] += alpha * ld_any(p, t * p_st + b * p_sb + c + i, p_bf16);
+  }
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = make_float4(v[0], v[1], v[2], v[3]);
+  if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+// ------------------------------------------------------------------ NCHW (+ optional addend) -> token rows
+// in element (b, c, y, x) at b*sb + c*sc + y*sh + x*sw (any of them may be 0 for expanded views).
+struct Strides4 { long long sb, sc, sh, sw; };
+__global__ void nchw_to_rows_kernel(const void* __restrict__ in, int in_bf16, Strides4 si, const void* __restrict__ add,
+                                    int add_bf16, Strides4 sa, int C, int H, int W, float* __restrict__ out_f32,
+                                    bf16* __restrict__ out_bf16) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int T = H * W;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    float v = 0.f;
+    if (c < C && t < T) {
+      const int y = t / W, x = t % W;
+      v = ld_any(in, b * si.sb + c * si.sc + y * si.sh + x * si.sw, in_bf16);
+      if (add) v += ld_any(add, b * sa.sb + c * sa.sc + y * sa.sh + x * sa.sw, add_bf16);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    if (t < T && c < C) {
+      const float v = tile[threadIdx.x][i];
+      const long long o = ((long long)b * T + t) * C + c;
+      if (out_f32) out_f32[o] = v;
+      if (out_bf16) out_bf16[o] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ token rows -> NCHW f32/bf16 (+ gated channel vector)
+// out[b][c][t] = in[b][t][c] + gate[b] * vec[c]
+__global__ void rows_to_nchw_kernel(const float* __restrict__ in, int C, int T, const float* __restrict__ gate,
+                                    const float* __restrict__ vec, float* __restrict__ out_f32,
+                                    bf16* __restrict__ out_bf16) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z;
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int t = t0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (t < T && c < C) ? in[((long long)b * T + t) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const float g = gate ? gate[b] : 0.f;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, t = t0 + threadIdx.x;
+    if (t < T && c < C) {
+      const float v = tile[threadIdx.x][i] + (vec ? g * vec[c] : 0.f);
+      const long long o = ((long long)b * C + c) * T + t;
+      if (out_f32) out_f32[o] = v;
+      if (out_bf16) out_bf16[o] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ small linear (token side)
+// out[g][r][n] = act( sum_k (x[g][r][k] + xadd[g][r][k]) * W[g][n][k] + bias[g][n] ) + res[g][r][n]
+// one warp per output element; x f32, W bf16. K % 8 == 0.
+struct SmallLin {
+  const float* x; long long x_sg, x_sr;
+  const float* xadd; long long xa_sg, xa_sr;
+  const bf16* W; long long w_sg;
+  const float* bias; long long b_sg;
+  const float* res; long long r_sg, r_sr;
+  float* out; long long o_sg, o_sr;
+  int G, R, N, K, act;  // act: 0 none, 1 relu, 3 sigmoid
+};
+__global__ void small_linear_kernel(const SmallLin p) {
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long total = (long long)p.G * p.R * p.N;
+  if (gw >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int n = (int)(gw % p.N);
+  const int r = (int)((gw / p.N) % p.R);
+  const int g = (int)(gw / ((long long)p.N * p.R));
+  const float* x = p.x + g * p.x_sg + r * p.x_sr;
+  const float* xa = p.xadd ? p.xadd + g * p.xa_sg + r * p.xa_sr : nullptr;
+  const bf16* w = p.W + g * p.w_sg + (long long)n * p.K;
+  float acc = 0.f;
+  for (int k = lane * 8; k < p.K; k += 256) {
+    const uint4 wv = *reinterpret_cast<const uint4*>(w + k);
+    const float4 x0 = *reinterpret_cast<const float4*>(x + k), x1 = *reinterpret_cast<const float4*>(x + k + 4);
+    float xv[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    if (xa) {
+      const float4 a0 = *reinterpret_cast<const float4*>(xa + k), a1 = *reinterpret_cast<const float4*>(xa + k + 4);
+      xv[0] += a0.x; xv[1] += a0.y; xv[2] += a0.z; xv[3] += a0.w;
+      xv[4] += a1.x; xv[5] += a1.y; xv[6] += a1.z; xv[7] += a1.w;
+    }
+    const uint32_t wu[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const __nv_bfloat162 w2 = *reinterpret_cast<const __nv_bfloat162*>(&wu[i]);
+      acc += xv[2 * i] * __low2float(w2) + xv[2 * i + 1] * __high2float(w2);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    if (p.bias) acc += p.bias[g * p.b_sg + n];
+    if (p.act == 1) acc = fmaxf(acc, 0.f);
+    if (p.act == 3) acc = 1.0f / (1.0f + __expf(-acc));
+    if (p.res) acc += p.res[g * p.r_sg + r * p.r_sr + n];
+    p.out[g * p.o_sg + r * p.o_sr + n] = acc;
+  }
+}
+
+// LayerNorm over 256 for a handful of token rows (f32 in/out), optional residual-free in-place.
+__global__ void ln256_small_kernel(const float* __restrict__ x, long long x_sr, int rows, const float* __restrict__ w,
+                                   const float* __restrict__ b, float eps, float* __restrict__ out, long long o_sr) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int lane = threadIdx.x & 31;
+  float v[8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] = x[row * x_sr + lane + 32 * i];
+    s += v[i];
+  }
+  const float mean = warp_sum(s) * (1.0f / 256.0f);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    v[i] -= mean;
+    q += v[i] * v[i];
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / 256.0f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) out[row * o_sr + lane + 32 * i] = v[i] * rstd * w[lane + 32 * i] + b[lane + 32 * i];
+}
+
+}  // namespace
+
+int launch_ln256(const float* x, int B, int T, const float* w, const float* b, float eps, int gelu, float* out_f32,
+                 long long f_sb, long long f_st, void* out_bf16, long long h_sb, long long h_st, cudaStream_t stream) {
+  const long long rows = (long long)B * T;
+  if (rows == 0) return 0;
+  const int wpb = 8;
+  ln256_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
+      x, B, T, w, b, eps, gelu, out_f32, f_sb, f_st, reinterpret_cast<bf16*>(out_bf16), h_sb, h_st);
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
+                     long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
+                     cudaStream_t stream) {
+  VLS_REQUIRE(C % 4 == 0, "axpy_rows: C must be a multiple of 4");
+  const long long total4 = (long long)B * T * C / 4;
+  if (total4 == 0) return 0;
+  axpy_rows_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
+      a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], const void* add, int add_bf16,
+                        const long long sa[4], int B, int C, int H, int W, float* out_f32, void* out_bf16,
+                        cudaStream_t stream) {
+  Strides4 s1{si[0], si[1], si[2], si[3]};
+  Strides4 s2{0, 0, 0, 0};
+  if (add) s2 = Strides4{sa[0], sa[1], sa[2], sa[3]};
+  dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), blk(32, 8);
+  nchw_to_rows_kernel<<<grid, blk, 0, stream>>>(in, in_bf16, s1, add, add_bf16, s2, C, H, W, out_f32,
+                                               reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rows_to_nchw(const float* in, int B, int C, int T, const float* gate, const float* vec, float* out_f32,
+                        void* out_bf16, cudaStream_t stream) {
+  dim3 grid((T + 31) / 32, (C + 31) / 32, B), blk(32, 8);
+  rows_to_nchw_kernel<<<grid, blk, 0, stream>>>(in, C, T, gate, vec, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream) {
+  VLS_REQUIRE(a.K % 8 == 0, "small_linear: K must be a multiple of 8");
+  SmallLin p;
+  p.x = a.x; p.x_sg = a.x_sg; p.x_sr = a.x_sr;
+  p.xadd = a.xadd; p.xa_sg = a.xa_sg; p.xa_sr = a.xa_sr;
+  p.W = reinterpret_cast<const bf16*>(a.W); p.w_sg = a.w_sg;
+  p.bias = a.bias; p.b_sg = a.b_sg;
+  p.res = a.res; p.r_sg = a.r_sg; p.r_sr = a.r_sr;
+  p.out = a.out; p.o_sg = a.o_sg; p.o_sr = a.o_sr;
+  p.G = a.G; p.R = a.R; p.N = a.N; p.K = a.K; p.act = a.act;
+  const long long total = (long long)a.G * a.R * a.N;
+  if (total == 0) return 0;
+  const int wpb = 8;
+  small_linear_kernel<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w, const float* b, float eps, float* out,
+                       long long o_sr, cudaStream_t stream) {
+  if (rows == 0) return 0;
+  ln256_small_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, x_sr, rows, w, b, eps, out, o_sr);
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace vls

@@ -1,0 +1,66 @@
+"""Thin Python wrappers over the building-block entry points of libvls_b200.so (used by the host
+modules and by the parity tests).  Everything here launches hand-written sm_100a kernels."""
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, lib, ptr, stream
+
+ACT = {None: 0, "none": 0, "relu": 1, "gelu": 2}
+
+
+def gemm(a, w, bias=None, bias_mode=1, act=None, rope=None, rope_rows=0, residual=None, out=None,
+         out_dtype=torch.bfloat16):
+    """C[b,m,n] = act(A[b,m,:] . W[n,:] + bias) (+ residual).
+
+    a: bf16 [M,K] or [B,M,K] (last dim contiguous); w: bf16 [N,K] or [B,N,K];
+    rope: (cos, sin) f32 [P,128] tables -> rotates column pairs of rows m < rope_rows at position m % P.
+    """
+    _lib.require_cuda(a, w)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    a3 = a if a.dim() == 3 else a.unsqueeze(0)
+    w3 = w if w.dim() == 3 else w.unsqueeze(0)
+    B, M, K = a3.shape
+    N = w3.shape[1]
+    assert w3.shape[2] == K and a3.stride(2) == 1 and w3.stride(2) == 1
+    if out is None:
+        out = torch.empty((B, M, N), device=a.device, dtype=out_dtype)
+    o3 = out if out.dim() == 3 else out.unsqueeze(0)
+    assert o3.stride(2) == 1 and o3.shape == (B, M, N)
+    d = GemmDesc()
+    d.A, d.lda, d.a_bstride = ptr(a3), a3.stride(1), a3.stride(0)
+    d.W, d.ldw, d.w_bstride = ptr(w3), w3.stride(1), (w3.stride(0) if w3.shape[0] > 1 else 0)
+    d.M, d.N, d.K, d.batch = M, N, K, B
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        d.bias, d.bias_mode = ptr(bias), bias_mode
+    d.act = ACT[act]
+    if rope is not None:
+        cos, sin = rope
+        assert cos.dtype == torch.float32 and cos.shape[1] == 128 and cos.is_contiguous() and sin.is_contiguous()
+        d.rope_cos, d.rope_sin, d.rope_period, d.rope_rows = ptr(cos), ptr(sin), cos.shape[0], rope_rows
+    if residual is not None:
+        r3 = residual if residual.dim() == 3 else residual.unsqueeze(0)
+        assert r3.dtype == torch.float32 and r3.stride(2) == 1
+        d.residual, d.ld_res, d.res_bstride = ptr(r3), r3.stride(1), (r3.stride(0) if r3.shape[0] > 1 else 0)
+    d.C, d.c_bf16, d.ldc, d.c_bstride = ptr(o3), int(o3.dtype == torch.bfloat16), o3.stride(1), o3.stride(0)
+    check(lib().vls_gemm_bf16(d, stream()), "vls_gemm_bf16")
+    return out if a.dim() == 3 else out.reshape(M, N) if out.dim() == 3 else out
+
+
+def attention_d256(q, k, vt, scale=None, splits=0, out=None):
+    """softmax(q k^T * scale) v for one head of dim 256.  q [B,Nq,256], k [B,Nk,256], vt [B,256,>=Nk]
+    (V transposed, row stride a multiple of 8), all bf16 with unit inner stride."""
+    _lib.require_cuda(q, k, vt)
+    B, Nq, D = q.shape
+    Nk = k.shape[1]
+    assert D == 256 and k.shape[2] == 256 and vt.shape[1] == 256 and vt.shape[2] >= Nk
+    assert q.stride(2) == 1 and k.stride(2) == 1 and vt.stride(2) == 1
+    if out is None:
+        out = torch.empty((B, Nq, 256), device=q.device, dtype=torch.bfloat16)
+    scale = float(scale) if scale is not None else 1.0 / 16.0
+    nbytes = lib().vls_attention_workspace_bytes(B, Nq, Nk, splits)
+    ws = torch.empty(max(nbytes, 1), device=q.device, dtype=torch.uint8)
+    check(lib().vls_attention_d256(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(vt),
+                                   vt.stride(1), vt.stride(0), B, Nq, Nk, scale, splits, ptr(out), out.stride(1),
+                                   out.stride(0), ptr(ws), nbytes, stream()), "vls_attention_d256")
+    return out
