@@ -67,6 +67,124 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
                        float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
                        size_t workspace_bytes, vls_stream_t stream);
 
+/* ---- module-level entry points ---------------------------------------------------------------
+ * dtype codes for activations handed over by the host: */
+#define VLS_F32 0
+#define VLS_BF16 1
+
+/* Memory attention (memory_attention.py:119-169). All weights bf16 [out][in] row-major (nn.Linear
+ * layout) and biases / LayerNorm affines f32, packed once by the host.  d_model 256, kv_in 64, FFN 2048,
+ * one head of 256 (sam2.1 YAMLs :26-58). */
+typedef struct vls_mem_attn_layer {
+  const void* sa_qk_w; const float* sa_qk_b;  /* [512,256] = [q_proj; k_proj] of self_attn */
+  const void* sa_v_w;  const float* sa_v_b;   /* [256,256] */
+  const void* sa_o_w;  const float* sa_o_b;   /* [256,256] */
+  const void* ca_q_w;  const float* ca_q_b;   /* [256,256] cross_attn_image.q_proj */
+  const void* ca_k_w;  const float* ca_k_b;   /* [256,64] */
+  const void* ca_v_w;  const float* ca_v_b;   /* [256,64] */
+  const void* ca_o_w;  const float* ca_o_b;   /* [256,256] */
+  const void* l1_w;    const float* l1_b;     /* [2048,256] */
+  const void* l2_w;    const float* l2_b;     /* [256,2048] */
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
+} vls_mem_attn_layer;
+typedef struct vls_mem_attn_weights {
+  int num_layers;                 /* <= 8 */
+  vls_mem_attn_layer layers[8];
+  const float *norm_w, *norm_b;
+  const float *rope_cos, *rope_sin; /* f32 [Nq][128]: axial table for a sqrt(Nq) x sqrt(Nq) grid */
+  int rope_len;                   /* must equal Nq */
+} vls_mem_attn_weights;
+/* curr/curr_pos: element (t,b,c) at t*st + b*sb + c, c < 256 (seq-first [Nq,B,256] -> st=B*256, sb=256);
+ * memory/memory_pos likewise with 64 channels; the last num_obj_ptr_tokens keys are not rotated.
+ * out uses the same addressing.  curr_pos may be NULL (pos_enc_at_input off). */
+size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk);
+int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+                         long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
+                         const void* memory, int mem_dtype, long long mem_st, long long mem_sb, const void* memory_pos,
+                         int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
+                         int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
+                         void* workspace, size_t workspace_bytes, vls_stream_t stream);
+
+/* Mask decoder (sam/mask_decoder.py:110-245 + sam/transformer.py:90-286). */
+typedef struct vls_attn_w {
+  const void* q_w; const float* q_b; const void* k_w; const float* k_b;
+  const void* v_w; const float* v_b; const void* o_w; const float* o_b;
+} vls_attn_w;
+typedef struct vls_dec_layer {
+  vls_attn_w self_attn;        /* 256 -> 256, 8 heads */
+  vls_attn_w t2i;              /* q_w [128,256] (tokens), o_w [256,128]; k/v live in img_w */
+  vls_attn_w i2t;              /* k_w, v_w [128,256] (tokens), o_w [256,128]; q lives in img_w */
+  const void* img_w; const float* img_b;  /* [384,256] = [t2i.k; t2i.v; i2t.q], bias [384] */
+  const float* img_pe_add;     /* f32 [T][384] = [image_pe . t2i.k^T | 0 | image_pe . i2t.q^T] */
+  const void* mlp1_w; const float* mlp1_b; const void* mlp2_w; const float* mlp2_b;
+  const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b, *n4_w, *n4_b;
+} vls_dec_layer;
+typedef struct vls_mask_decoder_weights {
+  vls_dec_layer layers[2];
+  vls_attn_w final_t2i;        /* q_w [128,256], o_w [256,128] */
+  const void* final_img_w; const float* final_img_b;  /* [256,256] = [k; v] */
+  const float* final_pe_add;   /* f32 [T][256] = [image_pe . k^T | 0] */
+  const float *nf_w, *nf_b;
+  const float* out_tokens;     /* f32 [6][256]: obj_score, iou, mask x4 */
+  const void* up1_w; const float* up1_b;   /* bf16 [(dy*2+dx)*64+co][ci], f32 [256] (bias tiled x4) */
+  const float *up_ln_w, *up_ln_b;          /* [64] */
+  const float* up2_w; const float* up2_b;  /* f32 [4 pos][64 ci][32 co], [32] */
+  const void* hyper_w[3]; const float* hyper_b[3]; /* 4 MLPs batched: [4][256][256] x2, [4][32][256] */
+  const void* iou_w[3];   const float* iou_b[3];   /* [256,256] x2, [4,256] */
+  const void* obj_w[3];   const float* obj_b[3];   /* [256,256] x2, [1,256] */
+  int iou_sigmoid;
+} vls_mask_decoder_weights;
+/* image_embeddings / dense: NCHW views given by 4 element strides (b,c,y,x); a 0 batch stride
+ * implements repeat_image / expand().  sparse: f32 [B][Ns][256].  feat_s0 [B or 1][32][4H][4W],
+ * feat_s1 [B or 1][64][2H][2W] (batch stride 0 when shared).  Outputs (all f32): masks [B][4][4H][4W],
+ * iou [B][4], tokens_out [B][4][256], obj_logits [B]. */
+size_t vls_mask_decoder_workspace_bytes(int B, int Ns, int H, int W);
+int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* image_embeddings, int emb_dtype,
+                             const long long emb_strides[4], const void* dense, int dense_dtype,
+                             const long long dense_strides[4], const float* sparse, const void* feat_s0, int s0_dtype,
+                             long long s0_bstride, const void* feat_s1, int s1_dtype, long long s1_bstride, int B, int Ns,
+                             int H, int W, float* masks, float* iou, float* tokens_out, float* obj_logits,
+                             void* workspace, size_t workspace_bytes, vls_stream_t stream);
+
+/* Post-decoder glue of SAM2Base._forward_sam_heads (sam2_base.py:359-403). */
+typedef struct vls_obj_ptr_weights {
+  const void* w[3]; const float* b[3];  /* obj_ptr_proj MLP 256-256-256-256 */
+  const float* no_obj_ptr;              /* f32 [256] */
+} vls_obj_ptr_weights;
+int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                       const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                       int* best_idx, float* is_obj, void* workspace, size_t workspace_bytes, vls_stream_t stream);
+
+/* Memory encoder (memory_encoder.py:158-181). */
+typedef struct vls_cx_block {
+  const float *dw_w, *dw_b;    /* f32 [49][256], [256] */
+  const float *ln_w, *ln_b;
+  const void* pw1_w; const float* pw1_b;  /* [1024,256] */
+  const void* pw2_w; const float* pw2_b;  /* [256,1024], gamma folded into both */
+} vls_cx_block;
+typedef struct vls_mem_encoder_weights {
+  const float *c1_w, *c1_b, *ln1_w, *ln1_b;   /* f32 [4][9] */
+  const float *c2_w, *c2_b, *ln2_w, *ln2_b;   /* f32 [9][4][16] */
+  const float *c3_w, *c3_b, *ln3_w, *ln3_b;   /* f32 [9][16][64] */
+  const void* c4_w; const float *c4_b, *ln4_w, *ln4_b;  /* bf16 [256][9*64] (tap-major), f32 */
+  const void* c5_w; const float* c5_b;        /* bf16 [256][256] */
+  const void* pix_w; const float* pix_b;      /* bf16 [256][256] */
+  vls_cx_block cx[2];
+  const void* out_w; const float* out_b;      /* bf16 [64][256] */
+  const float* no_obj_embed;                  /* f32 [64] or NULL */
+} vls_mem_encoder_weights;
+/* pix_feat: pix_layout 0 = NCHW view with strides[4] = (b,c,y,x); 1 = token rows, element (t,b,c) at
+ * t*strides[0] + b*strides[1] + c.   mask_mode: 0 high-res mask [B][16H][16W] used as is, 1 = sigmoid of
+ * it, 2 = LOW-res logits [B][4H][4W] -> sigmoid(bilinear x4)*scale+bias, 3 = (bilinear x4 > 0)*scale+bias.
+ * occluded_gate: f32 [B] = (1 - is_obj) or NULL.  Outputs (either may be NULL): out_nchw [B][64][H*W]
+ * (out_dtype), out_rows bf16 [B][H*W][64]. */
+size_t vls_mem_encoder_workspace_bytes(int B, int H, int W);
+int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_feat, int pix_dtype, int pix_layout,
+                            const long long pix_strides[4], const float* mask, int mask_mode, float sig_scale,
+                            float sig_bias, const float* occluded_gate, int B, int H, int W, void* out_nchw,
+                            int out_dtype, void* out_rows_bf16, void* workspace, size_t workspace_bytes,
+                            vls_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

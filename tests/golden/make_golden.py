@@ -25,6 +25,7 @@ os.environ.setdefault("TQDM_DISABLE", "1")
 from oracle import cc as cc_oracle  # noqa: E402
 from oracle import ref_import, sam2_path as O  # noqa: E402
 from video_llava_seg_b200 import synth  # noqa: E402
+from tests import golden_cases  # noqa: E402
 
 OUT = os.path.dirname(os.path.abspath(__file__))
 
@@ -44,14 +45,9 @@ def load_synth_weights(model, sd):
 
 
 def module_cases(model, sd):
-    g = torch.Generator().manual_seed(1234)
-    rn = lambda *s: torch.randn(*s, generator=g)
+    gi = golden_cases.module_inputs()
     out = {}
-    # ---- memory attention: 16x16 query grid, 2 memory frames + 2 pointers (8 tokens), B=2
-    nq, b = 256, 2
-    nk = 2 * nq + 8
-    curr, curr_pos = rn(nq, b, 256) * 0.5, rn(nq, b, 256) * 0.5
-    mem, mem_pos = rn(nk, b, 64) * 0.5, rn(nk, b, 64) * 0.5
+    curr, curr_pos, mem, mem_pos = gi["curr"], gi["curr_pos"], gi["mem"], gi["mem_pos"]
     ref = model.memory_attention(curr=[curr], curr_pos=[curr_pos], memory=mem, memory_pos=mem_pos,
                                  num_obj_ptr_tokens=8)
     ora = O.memory_attention(sd, curr, mem, curr_pos, mem_pos, 8)
@@ -59,9 +55,7 @@ def module_cases(model, sd):
     assert maxdiff(ref, ora) < 2e-5
     out["memattn_out"] = ref.numpy()
     # ---- mask decoder, video flavour (multimask, repeat_image=False) and LLaVA flavour
-    emb = rn(2, 256, 64, 64) * 0.5
-    s0, s1 = rn(2, 32, 256, 256) * 0.3, rn(2, 64, 128, 128) * 0.3
-    sparse = rn(2, 2, 256)
+    emb, s0, s1, sparse = gi["emb"], gi["s0"], gi["s1"], gi["sparse"]
     dense = model.sam_prompt_encoder.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(2, -1, 64, 64)
     pe = model.sam_prompt_encoder.get_dense_pe()
     assert maxdiff(pe, O.dense_pe(sd)) < 1e-6
@@ -74,7 +68,7 @@ def module_cases(model, sd):
     assert max(d) < 5e-5
     out["dec_video_masks_s4"] = ref[0][:, :, ::4, ::4].numpy()
     out["dec_video_iou"], out["dec_video_tok"], out["dec_video_obj"] = (x.numpy() for x in ref[1:])
-    seg = rn(3, 1, 256)
+    seg = gi["seg"]
     dense3 = dense[:1].expand(3, -1, -1, -1)
     ref = model.sam_mask_decoder(image_embeddings=emb[:1], image_pe=pe, sparse_prompt_embeddings=seg,
                                  dense_prompt_embeddings=dense3, multimask_output=False, repeat_image=True,
@@ -86,8 +80,7 @@ def module_cases(model, sd):
     out["dec_llava_masks_s4"] = ref[0][:, :, ::4, ::4].numpy()
     out["dec_llava_iou"] = ref[1].numpy()
     # ---- memory encoder, full size, B=2
-    pix = rn(2, 256, 64, 64) * 0.5
-    msk = torch.sigmoid(rn(2, 1, 1024, 1024) * 3) * 20 - 10
+    pix, msk = gi["pix"], gi["msk"]
     ref = model.memory_encoder(pix, msk, skip_mask_sigmoid=True)
     ora = O.memory_encoder(sd, pix, msk, True)
     print("memory_encoder oracle-vs-ref", maxdiff(ref["vision_features"], ora["vision_features"]),

@@ -15,6 +15,10 @@ _lib = None
 
 c_void_p, c_int, c_ll, c_float, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float,
                                             ctypes.c_size_t)
+VLS_F32, VLS_BF16 = 0, 1
+VLS_DTYPE = {torch.float32: VLS_F32, torch.bfloat16: VLS_BF16}
+LL4 = c_ll * 4
+LLP = ctypes.POINTER(c_ll)
 
 
 class GemmDesc(ctypes.Structure):
@@ -50,6 +54,30 @@ def _declare(lib):
                                        c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t, c_void_p]
 
 
+def _declare_modules(lib):
+    lib.vls_mem_attn_workspace_bytes.restype = c_size_t
+    lib.vls_mem_attn_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vls_mem_attn_forward.restype = c_int
+    lib.vls_mem_attn_forward.argtypes = [c_void_p, c_void_p, c_int, c_ll, c_ll, c_void_p, c_int, c_ll, c_ll, c_void_p,
+                                         c_int, c_ll, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_int, c_int,
+                                         c_void_p, c_int, c_ll, c_ll, c_void_p, c_size_t, c_void_p]
+    lib.vls_mask_decoder_workspace_bytes.restype = c_size_t
+    lib.vls_mask_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.vls_mask_decoder_forward.restype = c_int
+    lib.vls_mask_decoder_forward.argtypes = [c_void_p, c_void_p, c_int, LLP, c_void_p, c_int, LLP, c_void_p, c_void_p,
+                                             c_int, c_ll, c_void_p, c_int, c_ll, c_int, c_int, c_int, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vls_sam_heads_post.restype = c_int
+    lib.vls_sam_heads_post.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vls_mem_encoder_workspace_bytes.restype = c_size_t
+    lib.vls_mem_encoder_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.vls_mem_encoder_forward.restype = c_int
+    lib.vls_mem_encoder_forward.argtypes = [c_void_p, c_void_p, c_int, c_int, LLP, c_void_p, c_int, c_float, c_float,
+                                            c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p,
+                                            c_size_t, c_void_p]
+
+
 def lib():
     """Load (once) and return the ctypes handle; raise loudly if the CUDA extension is missing."""
     global _lib
@@ -60,6 +88,7 @@ def lib():
                 "(no CPU fallback). Build it with `python -m video_llava_seg_b200.build`.")
         handle = ctypes.CDLL(LIB_PATH)
         _declare(handle)
+        _declare_modules(handle)
         _lib = handle
     return _lib
 

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libvls_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-I", INCLUDE, "-I", CSRC]
 
 

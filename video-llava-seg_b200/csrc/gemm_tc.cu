@@ -32,7 +32,7 @@ struct Epi {
   void* C;
   int c_bf16;
   long long ldc, c_bstride;
-  int w_batched;
+  int w_batched, a_batched;
 };
 
 template <int BN>
@@ -87,7 +87,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem + s * STAGE_BYTES;
-        tma_load_3d(sa, &tmA, &full[s], kb * BK, m0, bz);
+        tma_load_3d(sa, &tmA, &full[s], kb * BK, m0, e.a_batched ? bz : 0);
         tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BK, n0, wz);
       }
     }
@@ -198,7 +198,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN>
 int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
-  VLS_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a.batch, a.lda, a.a_bstride, BM));
+  const bool a_batched = a.a_bstride != 0 && a.batch > 1;
+  VLS_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, a.a_bstride, BM));
   const bool w_batched = a.w_bstride != 0 && a.batch > 1;
   VLS_TRY(make_tmap_bf16(&tmB, a.W, a.K, a.N, w_batched ? a.batch : 1, a.ldw, a.w_bstride, BN));
   Epi e;
@@ -209,6 +210,7 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   e.residual = a.residual; e.ld_res = a.ld_res; e.res_bstride = a.res_bstride;
   e.C = a.C; e.c_bf16 = a.c_bf16; e.ldc = a.ldc; e.c_bstride = a.c_bstride;
   e.w_batched = w_batched ? 1 : 0;
+  e.a_batched = a_batched ? 1 : 0;
   static bool attr_set = false;
   if (!attr_set) {
     VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));

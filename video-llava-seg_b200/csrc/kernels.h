@@ -57,4 +57,65 @@ int launch_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, in
 int launch_fill_holes(float* scores, int n, int h, int w, int max_area, float fill_value, void* ws, size_t ws_bytes,
                       cudaStream_t stream);
 
+// ---------------------------------------------------------------- row / layout kernels (rowops.cu)
+// LayerNorm over 256 channels of f32 rows [B][T][256]; writes f32 and/or bf16 at b*sb + t*st.
+int launch_ln256(const float* x, int B, int T, const float* w, const float* b, float eps, int gelu, float* out_f32,
+                 long long f_sb, long long f_st, void* out_bf16, long long h_sb, long long h_st, cudaStream_t stream);
+// out[b][t][c] = a(t,b,c) + alpha * p(t,b,c); inputs f32/bf16 at t*st + b*sb + c; outputs contiguous rows.
+int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
+                     long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
+                     cudaStream_t stream);
+// NCHW view (strides sb,sc,sh,sw; zeros allowed) (+ addend) -> rows [B][H*W][C] f32 and/or bf16.
+int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], const void* add, int add_bf16,
+                        const long long sa[4], int B, int C, int H, int W, float* out_f32, void* out_bf16,
+                        cudaStream_t stream);
+// rows [B][T][C] f32 -> NCHW [B][C][T] (+ gate[b]*vec[c]) f32 and/or bf16.
+int launch_rows_to_nchw(const float* in, int B, int C, int T, const float* gate, const float* vec, float* out_f32,
+                        void* out_bf16, cudaStream_t stream);
+struct SmallLinArgs {
+  const float* x = nullptr; long long x_sg = 0, x_sr = 0;
+  const float* xadd = nullptr; long long xa_sg = 0, xa_sr = 0;
+  const void* W = nullptr; long long w_sg = 0;          // bf16 [G][N][K]
+  const float* bias = nullptr; long long b_sg = 0;
+  const float* res = nullptr; long long r_sg = 0, r_sr = 0;
+  float* out = nullptr; long long o_sg = 0, o_sr = 0;
+  int G = 1, R = 0, N = 0, K = 0, act = 0;              // act: 0 none, 1 relu, 3 sigmoid
+};
+int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream);
+int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w, const float* b, float eps, float* out,
+                       long long o_sr, cudaStream_t stream);
+
+int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse, int Ns, int B, float* tok_a, float* tok_b,
+                        cudaStream_t stream);
+int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gate, const float* vec, void* out,
+                          cudaStream_t stream);
+int launch_gather_rows(const float* src, long long sg, long long sr, int G, int R, int n, float* dst, cudaStream_t stream);
+
+// ---------------------------------------------------------------- mask decoder kernels (decoder.cu)
+int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, int Nt, float* out, cudaStream_t stream);
+int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_sb, int koff, int voff, int B, int Nt,
+                    int T, float* out, cudaStream_t stream);
+int launch_i2t_attn(const void* qrows, long long ld, long long q_sb, int qoff, const float* ktok, const float* vtok, int B,
+                    int Nt, int T, void* out, cudaStream_t stream);
+int launch_up1_post(const void* g, const void* feat, int feat_bf16, long long feat_sb, int B, int h, int w,
+                    const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream);
+int launch_up2_masks(const void* u, const float* w2t, const float* bias, const void* feat, int feat_bf16,
+                     long long feat_sb, const float* hyper, int B, int M, int h2, int w2, float* masks,
+                     cudaStream_t stream);
+int launch_select_best(const float* masks, const float* iou, const float* tokens, const float* obj_logits, int B, int M,
+                       int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
+                       cudaStream_t stream);
+int launch_gate_ptr(float* ptr, const float* is_obj, const float* no_obj_ptr, int B, cudaStream_t stream);
+
+// ---------------------------------------------------------------- memory encoder kernels (memenc.cu)
+int launch_mds1(const float* src, int mode, int B, int H, int W, int factor, float scale, float bias_v, const float* wgt,
+                const float* cb, const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream);
+int launch_mds2(const void* in, int B, int H, int W, const float* wgt, const float* cb, const float* lnw, const float* lnb,
+                float eps, void* out, cudaStream_t stream);
+int launch_mds3(const void* in, int B, int H, int W, const float* wgt, const float* cb, const float* lnw, const float* lnb,
+                float eps, void* out, cudaStream_t stream);
+int launch_im2col3x3s2(const void* in, int B, int H, int W, int C, void* out, cudaStream_t stream);
+int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
+                      const float* lnb, float eps, void* out, cudaStream_t stream);
+
 }  // namespace vls

@@ -1,0 +1,437 @@
+// Module-level entry points: each one sequences the kernels of one reference module on the caller's
+// stream using a caller-provided workspace (no allocation, no synchronisation).
+#include "vls_b200.h"
+
+#include "kernels.h"
+
+using namespace vls;
+
+namespace {
+
+constexpr int C = 256;      // d_model / transformer_dim
+constexpr int CM = 64;      // mem_dim
+constexpr int FFN = 2048;
+constexpr float LN_EPS = 1e-5f;   // nn.LayerNorm default
+constexpr float LN2D_EPS = 1e-6f; // LayerNorm2d (sam2_utils.py:141-153)
+
+inline long long rup(long long x, long long m) { return (x + m - 1) / m * m; }
+
+GemmArgs lin(const void* A, long long lda, long long a_bs, const void* W, int M, int N, int K, int batch, const float* bias,
+             void* Cout, int c_bf16, long long ldc, long long c_bs) {
+  GemmArgs g;
+  g.A = A; g.lda = lda; g.a_bstride = a_bs;
+  g.W = W; g.ldw = K; g.w_bstride = 0;
+  g.M = M; g.N = N; g.K = K; g.batch = batch;
+  g.bias = bias; g.bias_mode = bias ? 1 : 0;
+  g.C = Cout; g.c_bf16 = c_bf16; g.ldc = ldc; g.c_bstride = c_bs;
+  return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+// ================================================================== memory attention
+size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) {
+  const long long ldv = rup(Nq > Nk ? Nq : Nk, 64);
+  size_t n = 0;
+  n += align256((size_t)B * Nq * C * 4);        // x
+  n += align256((size_t)B * Nq * C * 2);        // t
+  n += align256((size_t)B * Nq * 2 * C * 2);    // qk
+  n += 2 * align256((size_t)B * Nk * CM * 2);   // mem, mempos
+  n += align256((size_t)B * Nk * C * 2);        // kc
+  n += align256((size_t)B * C * ldv * 2);       // vt
+  n += align256((size_t)B * Nq * C * 2);        // ao
+  n += align256((size_t)B * Nq * FFN * 2);      // h
+  const int s1 = attn_pick_splits(B, Nq, Nq), s2 = attn_pick_splits(B, Nq, Nk);
+  const size_t a1 = attn_workspace_bytes(B, Nq, s1), a2 = attn_workspace_bytes(B, Nq, s2);
+  n += align256(a1 > a2 ? a1 : a2);
+  return n + 4096;
+}
+
+int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+                         long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
+                         const void* memory, int mem_dtype, long long mem_st, long long mem_sb, const void* memory_pos,
+                         int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
+                         int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
+                         void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  VLS_REQUIRE(w && curr && memory && out, "mem_attn: null argument");
+  VLS_REQUIRE(w->num_layers >= 1 && w->num_layers <= 8, "mem_attn: num_layers out of range");
+  VLS_REQUIRE(B >= 1 && Nq >= 1 && Nk >= 1, "mem_attn: bad shape");
+  VLS_REQUIRE(num_obj_ptr_tokens >= 0 && num_obj_ptr_tokens <= Nk, "mem_attn: bad num_obj_ptr_tokens");
+  VLS_REQUIRE(w->rope_cos && w->rope_sin && w->rope_len == Nq, "mem_attn: RoPE table length %d != Nq %d", w->rope_len, Nq);
+  VLS_REQUIRE((Nk - num_obj_ptr_tokens) % Nq == 0, "mem_attn: rotated keys (%d) must be a multiple of Nq (%d)",
+              Nk - num_obj_ptr_tokens, Nq);  // rope_k_repeat (sam/transformer.py:329-338)
+  VLS_REQUIRE(workspace && workspace_bytes >= vls_mem_attn_workspace_bytes(B, Nq, Nk), "mem_attn: workspace too small");
+  Workspace ws(workspace, workspace_bytes);
+  const long long ldv = rup(Nq > Nk ? Nq : Nk, 64);
+  float* x = (float*)ws.take((size_t)B * Nq * C * 4);
+  void* t = ws.take((size_t)B * Nq * C * 2);
+  char* qk = (char*)ws.take((size_t)B * Nq * 2 * C * 2);
+  void* mem = ws.take((size_t)B * Nk * CM * 2);
+  void* mempos = ws.take((size_t)B * Nk * CM * 2);
+  void* kc = ws.take((size_t)B * Nk * C * 2);
+  void* vt = ws.take((size_t)B * C * ldv * 2);
+  void* ao = ws.take((size_t)B * Nq * C * 2);
+  void* h = ws.take((size_t)B * Nq * FFN * 2);
+  const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits(B, Nq, Nk);
+  const size_t a1 = attn_workspace_bytes(B, Nq, s_self), a2 = attn_workspace_bytes(B, Nq, s_cross);
+  char* aws = (char*)ws.take(a1 > a2 ? a1 : a2);
+  VLS_REQUIRE(x && t && qk && mem && mempos && kc && vt && ao && h && (aws || (a1 == 0 && a2 == 0)),
+              "mem_attn: workspace carve failed");
+
+  // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
+  VLS_TRY(launch_axpy_rows(curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, 0.1f, B, Nq, C, x,
+                           nullptr, st));
+  VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, st));
+  VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
+                           memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, st));
+
+  auto attention = [&](const void* K, long long ldk, long long k_bs, int nk, int splits) -> int {
+    AttnArgs a;
+    a.Q = qk; a.ldq = 2 * C; a.q_bstride = (long long)Nq * 2 * C;
+    a.K = K; a.ldk = ldk; a.k_bstride = k_bs;
+    a.Vt = vt; a.ldvt = ldv; a.vt_bstride = (long long)C * ldv;
+    a.B = B; a.Nq = Nq; a.Nk = nk; a.scale = 0.0625f; a.splits = splits;
+    a.O = ao; a.ldo = C; a.o_bstride = (long long)Nq * C;
+    if (splits > 1) {
+      a.part_o = (float*)aws;
+      a.part_ml = (float*)(aws + align256((size_t)B * splits * Nq * 256 * 4));
+    }
+    return launch_attention(a, st);
+  };
+
+  for (int l = 0; l < w->num_layers; ++l) {
+    const vls_mem_attn_layer& L = w->layers[l];
+    // ---- self attention (memory_attention.py:58-64): q = k = v = LN1(x); RoPE on q and k
+    VLS_TRY(launch_ln256(x, B, Nq, L.n1_w, L.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    {
+      GemmArgs g = lin(t, C, (long long)Nq * C, L.sa_qk_w, Nq, 2 * C, C, B, L.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
+      g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
+      VLS_TRY(launch_gemm(g, st));
+      GemmArgs v;  // V^T[c][t] = sum_k Wv[c][k] * t[t][k] + bv[c]
+      v.A = L.sa_v_w; v.lda = C; v.a_bstride = 0;
+      v.W = t; v.ldw = C; v.w_bstride = (long long)Nq * C;
+      v.M = C; v.N = Nq; v.K = C; v.batch = B;
+      v.bias = L.sa_v_b; v.bias_mode = 2;
+      v.C = vt; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
+      VLS_TRY(launch_gemm(v, st));
+    }
+    VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, Nq, s_self));
+    {
+      GemmArgs g = lin(ao, C, (long long)Nq * C, L.sa_o_w, Nq, C, C, B, L.sa_o_b, x, 0, C, (long long)Nq * C);
+      g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
+      VLS_TRY(launch_gemm(g, st));
+    }
+    // ---- cross attention to the memory bank (memory_attention.py:66-81)
+    VLS_TRY(launch_ln256(x, B, Nq, L.n2_w, L.n2_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    {
+      GemmArgs g = lin(t, C, (long long)Nq * C, L.ca_q_w, Nq, C, C, B, L.ca_q_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
+      g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
+      VLS_TRY(launch_gemm(g, st));
+      GemmArgs k = lin(mempos, CM, (long long)Nk * CM, L.ca_k_w, Nk, C, CM, B, L.ca_k_b, kc, 1, C, (long long)Nk * C);
+      k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
+      VLS_TRY(launch_gemm(k, st));
+      GemmArgs v;
+      v.A = L.ca_v_w; v.lda = CM; v.a_bstride = 0;
+      v.W = mem; v.ldw = CM; v.w_bstride = (long long)Nk * CM;
+      v.M = C; v.N = Nk; v.K = CM; v.batch = B;
+      v.bias = L.ca_v_b; v.bias_mode = 2;
+      v.C = vt; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
+      VLS_TRY(launch_gemm(v, st));
+    }
+    VLS_TRY(attention(kc, C, (long long)Nk * C, Nk, s_cross));
+    {
+      GemmArgs g = lin(ao, C, (long long)Nq * C, L.ca_o_w, Nq, C, C, B, L.ca_o_b, x, 0, C, (long long)Nq * C);
+      g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
+      VLS_TRY(launch_gemm(g, st));
+    }
+    // ---- FFN (memory_attention.py:95-98)
+    VLS_TRY(launch_ln256(x, B, Nq, L.n3_w, L.n3_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    {
+      GemmArgs g = lin(t, C, (long long)Nq * C, L.l1_w, Nq, FFN, C, B, L.l1_b, h, 1, FFN, (long long)Nq * FFN);
+      g.act = 1;
+      VLS_TRY(launch_gemm(g, st));
+      GemmArgs g2 = lin(h, FFN, (long long)Nq * FFN, L.l2_w, Nq, C, FFN, B, L.l2_b, x, 0, C, (long long)Nq * C);
+      g2.residual = x; g2.ld_res = C; g2.res_bstride = (long long)Nq * C;
+      VLS_TRY(launch_gemm(g2, st));
+    }
+  }
+  if (out_dtype == VLS_BF16)
+    return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, nullptr, 0, 0, out, out_sb, out_st, st);
+  return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, (float*)out, out_sb, out_st, nullptr, 0, 0, st);
+}
+
+// ================================================================== mask decoder
+static size_t dec_token_floats(int B, int Nt) {
+  // tokens0, queries, q, k, v, a (256 each) + qt/kt/vt/at (128 each) + mlp hidden (2048) + heads scratch
+  return (size_t)B * Nt * (6 * 256 + 4 * 128 + 2048) + (size_t)B * (4 * 256 * 2 + 4 * 32 + 2 * 256 * 2) + 1024;
+}
+
+size_t vls_mask_decoder_workspace_bytes(int B, int Ns, int H, int W) {
+  const size_t T = (size_t)H * W;
+  const int Nt = 6 + Ns;
+  size_t n = 0;
+  n += align256(B * T * C * 4);       // keys f32
+  n += align256(B * T * C * 2);       // keys bf16
+  n += align256(B * T * 384 * 2);     // fused image-side projections
+  n += align256(B * T * 128 * 2);     // i2t attention output
+  n += align256(B * T * C * 4);       // f32 scratch (pre-LN keys / upscaling GEMM)
+  n += align256(B * 4 * T * 64 * 2);  // upscaled stage-1 rows
+  n += align256(dec_token_floats(B, Nt) * 4);
+  return n + 4096;
+}
+
+int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* image_embeddings, int emb_dtype,
+                             const long long emb_strides[4], const void* dense, int dense_dtype,
+                             const long long dense_strides[4], const float* sparse, const void* feat_s0, int s0_dtype,
+                             long long s0_bstride, const void* feat_s1, int s1_dtype, long long s1_bstride, int B, int Ns,
+                             int H, int W, float* masks, float* iou, float* tokens_out, float* obj_logits,
+                             void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  VLS_REQUIRE(w && image_embeddings && feat_s0 && feat_s1 && masks && iou && tokens_out && obj_logits,
+              "mask_decoder: null argument");
+  VLS_REQUIRE(B >= 1 && Ns >= 0 && (Ns == 0 || sparse), "mask_decoder: bad prompt arguments");
+  VLS_REQUIRE(workspace && workspace_bytes >= vls_mask_decoder_workspace_bytes(B, Ns, H, W),
+              "mask_decoder: workspace too small");
+  const int T = H * W, Nt = 6 + Ns, R = B * Nt;
+  VLS_REQUIRE(Nt <= 32, "mask_decoder: at most 26 sparse prompt tokens are supported (got %d)", Ns);
+  Workspace ws(workspace, workspace_bytes);
+  float* keys = (float*)ws.take((size_t)B * T * C * 4);
+  void* keys_h = ws.take((size_t)B * T * C * 2);
+  void* kvq = ws.take((size_t)B * T * 384 * 2);
+  void* ai = ws.take((size_t)B * T * 128 * 2);
+  float* scratch = (float*)ws.take((size_t)B * T * C * 4);
+  void* up1 = ws.take((size_t)B * 4 * T * 64 * 2);
+  float* tk = (float*)ws.take(dec_token_floats(B, Nt) * 4);
+  VLS_REQUIRE(keys && keys_h && kvq && ai && scratch && up1 && tk, "mask_decoder: workspace carve failed");
+  float* tokens0 = tk;               tk += (size_t)R * 256;
+  float* queries = tk;               tk += (size_t)R * 256;
+  float* q = tk;                     tk += (size_t)R * 256;
+  float* k = tk;                     tk += (size_t)R * 256;
+  float* v = tk;                     tk += (size_t)R * 256;
+  float* a = tk;                     tk += (size_t)R * 256;
+  float* qt = tk;                    tk += (size_t)R * 128;
+  float* kt = tk;                    tk += (size_t)R * 128;
+  float* vt = tk;                    tk += (size_t)R * 128;
+  float* at = tk;                    tk += (size_t)R * 128;
+  float* hid = tk;                   tk += (size_t)R * 2048;
+  float* hy1 = tk;                   tk += (size_t)B * 4 * 256;
+  float* hy2 = tk;                   tk += (size_t)B * 4 * 256;
+  float* hyper = tk;                 tk += (size_t)B * 4 * 32;
+  float* hd1 = tk;                   tk += (size_t)B * 256 * 2;
+  float* hd2 = tk;                   tk += (size_t)B * 256 * 2;
+
+  // tokens = [obj_score, iou, mask x4, sparse...] (mask_decoder.py:179-197); queries = tokens
+  VLS_TRY(launch_build_tokens(w->out_tokens, 6, sparse, Ns, B, tokens0, queries, st));
+  // keys = image_embeddings (+ repeat) + dense, NCHW -> token rows (mask_decoder.py:200-205)
+  VLS_TRY(launch_nchw_to_rows(image_embeddings, emb_dtype, emb_strides, dense, dense_dtype, dense_strides, B, C, H, W, keys,
+                              keys_h, st));
+
+  auto tok_lin = [&](const float* x, const float* xadd, int K, const void* Wt, const float* bias, int N, int act,
+                     const float* res, float* out) -> int {
+    SmallLinArgs s;
+    s.x = x; s.x_sr = K; s.xadd = xadd; s.xa_sr = K;
+    s.W = Wt; s.bias = bias; s.res = res; s.r_sr = N; s.out = out; s.o_sr = N;
+    s.G = 1; s.R = R; s.N = N; s.K = K; s.act = act;
+    return launch_small_linear(s, st);
+  };
+  auto t2i = [&](const vls_attn_w& A, const void* rows, long long ld, const float* nw, const float* nb) -> int {
+    VLS_TRY(tok_lin(queries, tokens0, 256, A.q_w, A.q_b, 128, 0, nullptr, qt));
+    VLS_TRY(launch_t2i_attn(qt, rows, ld, (long long)T * ld, 0, 128, B, Nt, T, at, st));
+    VLS_TRY(tok_lin(at, nullptr, 128, A.o_w, A.o_b, 256, 0, queries, a));
+    return launch_ln256_small(a, 256, R, nw, nb, LN_EPS, queries, 256, st);
+  };
+
+  for (int l = 0; l < 2; ++l) {
+    const vls_dec_layer& L = w->layers[l];
+    // -- token self attention (sam/transformer.py:183-191); layer 0 drops the PE and the residual
+    const float* pe = l == 0 ? nullptr : tokens0;
+    VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.q_w, L.self_attn.q_b, 256, 0, nullptr, q));
+    VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.k_w, L.self_attn.k_b, 256, 0, nullptr, k));
+    VLS_TRY(tok_lin(queries, nullptr, 256, L.self_attn.v_w, L.self_attn.v_b, 256, 0, nullptr, v));
+    VLS_TRY(launch_tok_self_attn(q, k, v, B, Nt, a, st));
+    VLS_TRY(tok_lin(a, nullptr, 256, L.self_attn.o_w, L.self_attn.o_b, 256, 0, l == 0 ? nullptr : queries, q));
+    VLS_TRY(launch_ln256_small(q, 256, R, L.n1_w, L.n1_b, LN_EPS, queries, 256, st));
+    // -- image-side projections for this layer in one GEMM: [K_t2i | V_t2i | Q_i2t], PE folded in as a residual
+    {
+      GemmArgs g = lin(keys_h, C, (long long)T * C, L.img_w, T, 384, C, B, L.img_b, kvq, 1, 384, (long long)T * 384);
+      g.residual = L.img_pe_add; g.ld_res = 384; g.res_bstride = 0;
+      VLS_TRY(launch_gemm(g, st));
+    }
+    // -- tokens -> image cross attention (:193-198)
+    VLS_TRY(t2i(L.t2i, kvq, 384, L.n2_w, L.n2_b));
+    // -- token MLP (:200-203)
+    VLS_TRY(tok_lin(queries, nullptr, 256, L.mlp1_w, L.mlp1_b, 2048, 1, nullptr, hid));
+    VLS_TRY(tok_lin(hid, nullptr, 2048, L.mlp2_w, L.mlp2_b, 256, 0, queries, a));
+    VLS_TRY(launch_ln256_small(a, 256, R, L.n3_w, L.n3_b, LN_EPS, queries, 256, st));
+    // -- image -> tokens cross attention (:205-210)
+    VLS_TRY(tok_lin(queries, tokens0, 256, L.i2t.k_w, L.i2t.k_b, 128, 0, nullptr, kt));
+    VLS_TRY(tok_lin(queries, nullptr, 256, L.i2t.v_w, L.i2t.v_b, 128, 0, nullptr, vt));
+    VLS_TRY(launch_i2t_attn(kvq, 384, (long long)T * 384, 256, kt, vt, B, Nt, T, ai, st));
+    {
+      GemmArgs g = lin(ai, 128, (long long)T * 128, L.i2t.o_w, T, C, 128, B, L.i2t.o_b, scratch, 0, C, (long long)T * C);
+      g.residual = keys; g.ld_res = C; g.res_bstride = (long long)T * C;
+      VLS_TRY(launch_gemm(g, st));
+    }
+    VLS_TRY(launch_ln256(scratch, B, T, L.n4_w, L.n4_b, LN_EPS, 0, keys, (long long)T * C, C, keys_h, (long long)T * C, C, st));
+  }
+  // -- final tokens -> image attention (sam/transformer.py:127-132)
+  {
+    GemmArgs g = lin(keys_h, C, (long long)T * C, w->final_img_w, T, 256, C, B, w->final_img_b, kvq, 1, 256, (long long)T * 256);
+    g.residual = w->final_pe_add; g.ld_res = 256; g.res_bstride = 0;
+    VLS_TRY(launch_gemm(g, st));
+  }
+  VLS_TRY(t2i(w->final_t2i, kvq, 256, w->nf_w, w->nf_b));
+  // queries == hs: [0]=obj score token, [1]=iou token, [2..5]=mask tokens (mask_decoder.py:213-215)
+
+  // -- upscaling (mask_decoder.py:218-225): ConvT(256->64) as a GEMM, + feat_s1, LN2d, GELU
+  {
+    GemmArgs g = lin(keys_h, C, (long long)T * C, w->up1_w, T, 256, C, B, w->up1_b, scratch, 0, 256, (long long)T * 256);
+    VLS_TRY(launch_gemm(g, st));
+  }
+  VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, st));
+  // -- hyper-network MLPs on the 4 mask tokens, batched over tokens (mask_decoder.py:227-232)
+  {
+    SmallLinArgs s;
+    s.G = 4; s.R = B; s.K = 256; s.N = 256; s.act = 1;
+    s.x = queries + 2 * 256; s.x_sg = 256; s.x_sr = (long long)Nt * 256;
+    s.W = w->hyper_w[0]; s.w_sg = 256 * 256; s.bias = w->hyper_b[0]; s.b_sg = 256;
+    s.out = hy1; s.o_sg = (long long)B * 256; s.o_sr = 256;
+    VLS_TRY(launch_small_linear(s, st));
+    s.x = hy1; s.x_sg = (long long)B * 256; s.x_sr = 256;
+    s.W = w->hyper_w[1]; s.bias = w->hyper_b[1]; s.out = hy2;
+    VLS_TRY(launch_small_linear(s, st));
+    s.x = hy2; s.N = 32; s.act = 0;
+    s.W = w->hyper_w[2]; s.w_sg = 32 * 256; s.bias = w->hyper_b[2]; s.b_sg = 32;
+    s.out = hyper; s.o_sg = 32; s.o_sr = 4 * 32;
+    VLS_TRY(launch_small_linear(s, st));
+  }
+  // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234)
+  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, st));
+  // -- IoU head on hs[:,1] and object-score head on hs[:,0] (mask_decoder.py:237-240)
+  for (int head = 0; head < 2; ++head) {
+    const void* const* Wt = head == 0 ? w->iou_w : w->obj_w;
+    const float* const* bs = head == 0 ? w->iou_b : w->obj_b;
+    SmallLinArgs s;
+    s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
+    s.x = queries + (head == 0 ? 256 : 0); s.x_sr = (long long)Nt * 256;
+    s.W = Wt[0]; s.bias = bs[0]; s.out = hd1; s.o_sr = 256;
+    VLS_TRY(launch_small_linear(s, st));
+    s.x = hd1; s.x_sr = 256; s.W = Wt[1]; s.bias = bs[1]; s.out = hd2;
+    VLS_TRY(launch_small_linear(s, st));
+    s.x = hd2; s.W = Wt[2]; s.bias = bs[2];
+    if (head == 0) { s.N = 4; s.act = w->iou_sigmoid ? 3 : 0; s.out = iou; s.o_sr = 4; }
+    else { s.N = 1; s.act = 0; s.out = obj_logits; s.o_sr = 1; }
+    VLS_TRY(launch_small_linear(s, st));
+  }
+  // -- mask tokens out
+  return launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st);
+}
+
+// ================================================================== post-decoder glue
+int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                       const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                       int* best_idx, float* is_obj, void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  VLS_REQUIRE(w && masks && iou && tokens && obj_logits && low_res_masks && obj_ptr && best_idx && is_obj,
+              "sam_heads_post: null argument");
+  VLS_REQUIRE(workspace && workspace_bytes >= (size_t)B * 256 * 3 * 4, "sam_heads_post: workspace too small");
+  float* tok = (float*)workspace;
+  float* h1 = tok + (size_t)B * 256;
+  float* h2 = h1 + (size_t)B * 256;
+  VLS_TRY(launch_select_best(masks, iou, tokens, obj_logits, B, 4, multimask, HW, low_res_masks, tok, best_idx, is_obj, st));
+  SmallLinArgs s;
+  s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
+  s.x = tok; s.x_sr = 256; s.W = w->w[0]; s.bias = w->b[0]; s.out = h1; s.o_sr = 256;
+  VLS_TRY(launch_small_linear(s, st));
+  s.x = h1; s.W = w->w[1]; s.bias = w->b[1]; s.out = h2;
+  VLS_TRY(launch_small_linear(s, st));
+  s.x = h2; s.W = w->w[2]; s.bias = w->b[2]; s.out = obj_ptr; s.act = 0;
+  VLS_TRY(launch_small_linear(s, st));
+  return launch_gate_ptr(obj_ptr, is_obj, w->no_obj_ptr, B, st);
+}
+
+// ================================================================== memory encoder
+size_t vls_mem_encoder_workspace_bytes(int B, int H, int W) {
+  const size_t T = (size_t)H * W;
+  size_t n = 0;
+  n += align256(B * 64 * T * 4 * 2);    // stage 1 rows (8H x 8W x 4)
+  n += align256(B * 16 * T * 16 * 2);   // stage 2 rows (4H x 4W x 16)
+  n += align256(B * 4 * T * 64 * 2);    // stage 3 rows (2H x 2W x 64)
+  n += align256(B * T * 576 * 2);       // im2col
+  n += 2 * align256(B * T * C * 4);     // f32 scratch + x
+  n += 2 * align256(B * T * C * 2);     // bf16 t, pix rows
+  n += align256(B * T * 1024 * 2);      // CXBlock hidden
+  n += align256(B * T * 64 * 4);        // out rows f32
+  return n + 4096;
+}
+
+int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_feat, int pix_dtype, int pix_layout,
+                            const long long pix_strides[4], const float* mask, int mask_mode, float sig_scale,
+                            float sig_bias, const float* occluded_gate, int B, int H, int W, void* out_nchw,
+                            int out_dtype, void* out_rows_bf16, void* workspace, size_t workspace_bytes,
+                            vls_stream_t stream_) {
+  cudaStream_t st = (cudaStream_t)stream_;
+  VLS_REQUIRE(w && pix_feat && mask && (out_nchw || out_rows_bf16), "mem_encoder: null argument");
+  VLS_REQUIRE(mask_mode >= 0 && mask_mode <= 3, "mem_encoder: bad mask_mode");
+  VLS_REQUIRE(workspace && workspace_bytes >= vls_mem_encoder_workspace_bytes(B, H, W), "mem_encoder: workspace too small");
+  const int T = H * W;
+  Workspace ws(workspace, workspace_bytes);
+  void* m1 = ws.take((size_t)B * 64 * T * 4 * 2);
+  void* m2 = ws.take((size_t)B * 16 * T * 16 * 2);
+  void* m3 = ws.take((size_t)B * 4 * T * 64 * 2);
+  void* col = ws.take((size_t)B * T * 576 * 2);
+  float* scratch = (float*)ws.take((size_t)B * T * C * 4);
+  float* x = (float*)ws.take((size_t)B * T * C * 4);
+  void* t = ws.take((size_t)B * T * C * 2);
+  void* pix = ws.take((size_t)B * T * C * 2);
+  void* hid = ws.take((size_t)B * T * 1024 * 2);
+  float* orow = (float*)ws.take((size_t)B * T * 64 * 4);
+  VLS_REQUIRE(m1 && m2 && m3 && col && scratch && x && t && pix && hid && orow, "mem_encoder: workspace carve failed");
+
+  // mask down-sampler (memory_encoder.py:17-58): 3x (conv3x3 s2 + LN2d + GELU) on CUDA cores, the 4th as im2col + GEMM
+  VLS_TRY(launch_mds1(mask, mask_mode, B, 16 * H, 16 * W, mask_mode >= 2 ? 4 : 1, sig_scale, sig_bias, w->c1_w, w->c1_b,
+                      w->ln1_w, w->ln1_b, LN2D_EPS, m1, st));
+  VLS_TRY(launch_mds2(m1, B, 8 * H, 8 * W, w->c2_w, w->c2_b, w->ln2_w, w->ln2_b, LN2D_EPS, m2, st));
+  VLS_TRY(launch_mds3(m2, B, 4 * H, 4 * W, w->c3_w, w->c3_b, w->ln3_w, w->ln3_b, LN2D_EPS, m3, st));
+  VLS_TRY(launch_im2col3x3s2(m3, B, 2 * H, 2 * W, 64, col, st));
+  VLS_TRY(launch_gemm(lin(col, 576, (long long)T * 576, w->c4_w, T, C, 576, B, w->c4_b, scratch, 0, C, (long long)T * C), st));
+  VLS_TRY(launch_ln256(scratch, B, T, w->ln4_w, w->ln4_b, LN2D_EPS, 1, nullptr, 0, 0, t, (long long)T * C, C, st));
+  VLS_TRY(launch_gemm(lin(t, C, (long long)T * C, w->c5_w, T, C, C, B, w->c5_b, scratch, 0, C, (long long)T * C), st));
+  // x = pix_feat_proj(pix_feat) + mask features (memory_encoder.py:174-175)
+  if (pix_layout == 0) {
+    VLS_TRY(launch_nchw_to_rows(pix_feat, pix_dtype, pix_strides, nullptr, 0, nullptr, B, C, H, W, nullptr, pix, st));
+  } else {
+    VLS_TRY(launch_axpy_rows(pix_feat, pix_dtype, pix_strides[0], pix_strides[1], nullptr, 0, 0, 0, 0.f, B, T, C, nullptr,
+                             pix, st));
+  }
+  {
+    GemmArgs g = lin(pix, C, (long long)T * C, w->pix_w, T, C, C, B, w->pix_b, x, 0, C, (long long)T * C);
+    g.residual = scratch; g.ld_res = C; g.res_bstride = (long long)T * C;
+    VLS_TRY(launch_gemm(g, st));
+  }
+  // fuser: 2 x CXBlock (memory_encoder.py:103-117); gamma is folded into pw2
+  for (int i = 0; i < 2; ++i) {
+    const vls_cx_block& cx = w->cx[i];
+    VLS_TRY(launch_dwconv7_ln(x, B, H, W, cx.dw_w, cx.dw_b, cx.ln_w, cx.ln_b, LN2D_EPS, t, st));
+    GemmArgs g1 = lin(t, C, (long long)T * C, cx.pw1_w, T, 1024, C, B, cx.pw1_b, hid, 1, 1024, (long long)T * 1024);
+    g1.act = 2;
+    VLS_TRY(launch_gemm(g1, st));
+    GemmArgs g2 = lin(hid, 1024, (long long)T * 1024, cx.pw2_w, T, C, 1024, B, cx.pw2_b, x, 0, C, (long long)T * C);
+    g2.residual = x; g2.ld_res = C; g2.res_bstride = (long long)T * C;
+    VLS_TRY(launch_gemm(g2, st));
+  }
+  // out_proj 256 -> 64 (memory_encoder.py:177) (+ occlusion embedding, sam2_base.py:716-722)
+  VLS_TRY(launch_axpy_rows(x, 0, C, (long long)T * C, nullptr, 0, 0, 0, 0.f, B, T, C, nullptr, t, st));
+  VLS_TRY(launch_gemm(lin(t, C, (long long)T * C, w->out_w, T, 64, C, B, w->out_b, orow, 0, 64, (long long)T * 64), st));
+  const float* gate = (occluded_gate && w->no_obj_embed) ? occluded_gate : nullptr;
+  if (out_nchw)
+    VLS_TRY(launch_rows_to_nchw(orow, B, 64, T, gate, w->no_obj_embed, out_dtype == VLS_F32 ? (float*)out_nchw : nullptr,
+                                out_dtype == VLS_BF16 ? out_nchw : nullptr, st));
+  if (out_rows_bf16) VLS_TRY(launch_rows_gate_cast(orow, B, T, 64, gate, w->no_obj_embed, out_rows_bf16, st));
+  return 0;
+}
+
+}  // extern "C"

@@ -210,7 +210,62 @@ __global__ void ln256_small_kernel(const float* __restrict__ x, long long x_sr, 
   for (int i = 0; i < 8; ++i) out[row * o_sr + lane + 32 * i] = v[i] * rstd * w[lane + 32 * i] + b[lane + 32 * i];
 }
 
+// tokens[b][i][:] = i < n_out ? out_tokens[i][:] : sparse[b][i - n_out][:]      (mask_decoder.py:179-197)
+__global__ void build_tokens_kernel(const float* __restrict__ out_tokens, int n_out, const float* __restrict__ sparse,
+                                    int Ns, int B, float* __restrict__ tok_a, float* __restrict__ tok_b) {
+  const int Nt = n_out + Ns;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * Nt * 256) return;
+  const int c = i & 255, r = (i >> 8) % Nt, b = i / (Nt * 256);
+  const float v = r < n_out ? out_tokens[r * 256 + c] : sparse[((long long)b * Ns + (r - n_out)) * 256 + c];
+  tok_a[i] = v;
+  tok_b[i] = v;
+}
+
+// out_bf16[b][t][c] = in[b][t][c] + gate[b] * vec[c]
+__global__ void rows_gate_cast_kernel(const float* __restrict__ in, int B, int T, int C, const float* __restrict__ gate,
+                                      const float* __restrict__ vec, bf16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)B * T * C) return;
+  const int c = (int)(i % C), b = (int)(i / ((long long)T * C));
+  out[i] = __float2bfloat16_rn(in[i] + ((gate && vec) ? gate[b] * vec[c] : 0.f));
+}
+
+// dst[g][r][:n] = src[g*sg + r*sr + :n]
+__global__ void gather_rows_kernel(const float* __restrict__ src, long long sg, long long sr, int G, int R, int n,
+                                   float* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * R * n) return;
+  const int c = i % n, r = (i / n) % R, g = i / (n * R);
+  dst[i] = src[g * sg + r * sr + c];
+}
+
 }  // namespace
+
+int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse, int Ns, int B, float* tok_a, float* tok_b,
+                        cudaStream_t stream) {
+  const int total = B * (n_out + Ns) * 256;
+  build_tokens_kernel<<<(total + 255) / 256, 256, 0, stream>>>(out_tokens, n_out, sparse, Ns, B, tok_a, tok_b);
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gate, const float* vec, void* out,
+                          cudaStream_t stream) {
+  const long long total = (long long)B * T * C;
+  rows_gate_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, B, T, C, gate, vec,
+                                                                             reinterpret_cast<bf16*>(out));
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_gather_rows(const float* src, long long sg, long long sr, int G, int R, int n, float* dst, cudaStream_t stream) {
+  const int total = G * R * n;
+  if (total == 0) return 0;
+  gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, sg, sr, G, R, n, dst);
+  VLS_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int launch_ln256(const float* x, int B, int T, const float* w, const float* b, float eps, int gelu, float* out_f32,
                  long long f_sb, long long f_st, void* out_bf16, long long h_sb, long long h_st, cudaStream_t stream) {
