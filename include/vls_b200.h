@@ -27,6 +27,9 @@ extern "C" {
 #endif
 
 typedef void* vls_stream_t; /* cudaStream_t */
+/* dtype codes for activations handed over by the host */
+#define VLS_F32 0
+#define VLS_BF16 1
 
 const char* vls_last_error(void);
 int vls_abi_version(void);
@@ -67,10 +70,24 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
                        float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
                        size_t workspace_bytes, vls_stream_t stream);
 
+/* Bilinear resize of n f32 images [h,w] -> [H,W], align_corners=False, no antialiasing
+ * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */
+int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, vls_stream_t stream);
+
+/* out[r][:n] = act(x[r][:k] . W[n][k]^T + bias), x/out f32, W bf16 row-major, k % 8 == 0;
+ * act: 0 none, 1 ReLU, 3 sigmoid.  Warp-per-output kernel for the handful-of-rows linears
+ * (object-pointer projections, sam2_base.py:393,633). */
+int vls_linear_f32(const float* x, long long ldx, const void* w_bf16, const float* bias, int rows, int n, int k, int act,
+                   float* out, long long ldo, vls_stream_t stream);
+
+/* out[b][t][c] = a(t,b,c) + alpha * p(t,b,c), inputs f32/bf16 addressed as t*st + b*sb + c (strides may
+ * be 0 to broadcast), output contiguous rows [B][T][C] in f32 or bf16.  C % 4 == 0.  Used for the
+ * no-memory embedding add (sam2_base.py:653) and layout/precision conversion. */
+int vls_axpy_rows(const void* a, int a_dtype, long long a_st, long long a_sb, const void* p, int p_dtype, long long p_st,
+                  long long p_sb, float alpha, int B, int T, int C, void* out, int out_dtype, vls_stream_t stream);
+
 /* ---- module-level entry points ---------------------------------------------------------------
  * dtype codes for activations handed over by the host: */
-#define VLS_F32 0
-#define VLS_BF16 1
 
 /* Memory attention (memory_attention.py:119-169). All weights bf16 [out][in] row-major (nn.Linear
  * layout) and biases / LayerNorm affines f32, packed once by the host.  d_model 256, kv_in 64, FFN 2048,
@@ -174,8 +191,9 @@ typedef struct vls_mem_encoder_weights {
   const float* no_obj_embed;                  /* f32 [64] or NULL */
 } vls_mem_encoder_weights;
 /* pix_feat: pix_layout 0 = NCHW view with strides[4] = (b,c,y,x); 1 = token rows, element (t,b,c) at
- * t*strides[0] + b*strides[1] + c.   mask_mode: 0 high-res mask [B][16H][16W] used as is, 1 = sigmoid of
- * it, 2 = LOW-res logits [B][4H][4W] -> sigmoid(bilinear x4)*scale+bias, 3 = (bilinear x4 > 0)*scale+bias.
+ * t*strides[0] + b*strides[1] + c.   mask_mode: 0 high-res mask [B][16H][16W] used as is, 1 = sigmoid(it)*scale+bias,
+ * 4 = (it > 0)*scale+bias, 2 = LOW-res logits [B][4H][4W] -> sigmoid(bilinear x4)*scale+bias,
+ * 3 = (bilinear x4 > 0)*scale+bias.
  * occluded_gate: f32 [B] = (1 - is_obj) or NULL.  Outputs (either may be NULL): out_nchw [B][64][H*W]
  * (out_dtype), out_rows bf16 [B][H*W][64]. */
 size_t vls_mem_encoder_workspace_bytes(int B, int H, int W);

@@ -98,6 +98,14 @@ def run_reference_clip(model, clip, batch, num_frames):
 
     misc.get_connected_components = lambda m: cc_oracle.cc_label(m)
     vp.fill_holes_in_mask_scores.__globals__["get_connected_components"] = misc.get_connected_components
+    prefill = []  # mask logits as they enter hole filling, in call order (B calls for the prompt frame, then 1/frame)
+    orig_fill = misc.fill_holes_in_mask_scores
+
+    def recording_fill(mask, max_area):
+        prefill.append(mask.clone())
+        return orig_fill(mask, max_area)
+
+    vp.fill_holes_in_mask_scores = recording_fill
     imgs = torch.arange(num_frames, dtype=torch.float32).view(-1, 1, 1, 1).expand(-1, 3, 1, 1).contiguous()
     vp.load_video_frames = lambda **kw: (imgs, 1024, 1024)
 
@@ -122,6 +130,11 @@ def run_reference_clip(model, clip, batch, num_frames):
         per_frame.append(dict(pred_masks=o["pred_masks"].clone(), obj_ptr=o["obj_ptr"].clone(),
                               object_score_logits=o["object_score_logits"].clone(),
                               maskmem_features=o["maskmem_features"].clone(), video_res=video_res.clone()))
+    vp.fill_holes_in_mask_scores = orig_fill
+    pre = [torch.cat(prefill[:batch], 0)] + prefill[batch:]
+    assert len(pre) == len(per_frame)
+    for o, p in zip(per_frame, pre):
+        o["pred_masks_prefill"] = p
     return per_frame
 
 
@@ -141,6 +154,7 @@ def clip_case(model, sd, name, seed, num_frames, batch):
               f"range [{r['pred_masks'].min():.2f},{r['pred_masks'].max():.2f}]")
         assert d_mask < 2e-3 and d_ptr < 1e-3, "oracle drifted from the reference"
         out[f"mask_s2_{t}"] = r["pred_masks"][:, :, ::2, ::2].numpy()
+        out[f"prefill_s2_{t}"] = r["pred_masks_prefill"][:, :, ::2, ::2].numpy()
         out[f"maskbits_{t}"] = np.packbits((r["pred_masks"] > 0).numpy().reshape(batch, -1), axis=1)
         out[f"obj_ptr_{t}"] = r["obj_ptr"].numpy()
         out[f"obj_score_{t}"] = r["object_score_logits"].numpy()

@@ -55,6 +55,14 @@ def _declare(lib):
 
 
 def _declare_modules(lib):
+    lib.vls_resize_bilinear.restype = c_int
+    lib.vls_resize_bilinear.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.vls_axpy_rows.restype = c_int
+    lib.vls_axpy_rows.argtypes = [c_void_p, c_int, c_ll, c_ll, c_void_p, c_int, c_ll, c_ll, c_float, c_int, c_int, c_int,
+                                  c_void_p, c_int, c_void_p]
+    lib.vls_linear_f32.restype = c_int
+    lib.vls_linear_f32.argtypes = [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
+                                   c_void_p]
     lib.vls_mem_attn_workspace_bytes.restype = c_size_t
     lib.vls_mem_attn_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vls_mem_attn_forward.restype = c_int

@@ -49,3 +49,40 @@ def load_prefixed(module, sd, prefix):
     sub = {k[len(prefix):]: v for k, v in sd.items() if k.startswith(prefix)}
     module.load_state_dict(sub, strict=True)
     return module
+
+
+SAM21_MODEL_KWARGS = dict(  # sam2/configs/sam2.1/sam2.1_hiera_*.yaml:84-116 (identical for t/s/b+/l)
+    num_maskmem=7, image_size=1024, sigmoid_scale_for_mem_enc=20.0, sigmoid_bias_for_mem_enc=-10.0,
+    use_mask_input_as_output_without_sam=True, directly_add_no_mem_embed=True, no_obj_embed_spatial=True,
+    use_high_res_features_in_sam=True, multimask_output_in_sam=True, iou_prediction_use_sigmoid=True,
+    use_obj_ptrs_in_encoder=True, add_tpos_enc_to_obj_ptrs=True, proj_tpos_enc_in_obj_ptrs=True,
+    use_signed_tpos_enc_to_obj_ptrs=True, only_obj_ptrs_in_the_past_for_eval=True, pred_obj_scores=True,
+    pred_obj_scores_mlp=True, fixed_no_obj_ptr=True, multimask_output_for_tracking=True,
+    use_multimask_token_for_obj_ptr=True, multimask_min_pt_num=0, multimask_max_pt_num=1,
+    use_mlp_for_obj_ptr_proj=True, compile_image_encoder=False)
+
+
+def build_sam2_video_predictor(image_encoder=None, state_dict=None, device="cuda", apply_postprocessing=True, **overrides):
+    """Counterpart of sam2/build_sam.py:79-118.  `image_encoder` is any module returning the reference's
+    {"backbone_fpn", "vision_pos_enc"} dict (the Hiera + FPN encoder is outside this package; None when frames
+    come with precomputed features).  `state_dict`: reference checkpoint["model"] (image_encoder.* keys are
+    forwarded to the encoder if given, otherwise ignored)."""
+    from .sam2_video_predictor import SAM2VideoPredictor
+
+    kw = dict(SAM21_MODEL_KWARGS)
+    if apply_postprocessing:  # build_sam.py:93-102
+        kw.update(binarize_mask_from_pts_for_mem_enc=True, fill_hole_area=8,
+                  sam_mask_decoder_extra_args=dict(dynamic_multimask_via_stability=True,
+                                                   dynamic_multimask_stability_delta=0.05,
+                                                   dynamic_multimask_stability_thresh=0.98))
+    kw.update(overrides)
+    model = SAM2VideoPredictor(image_encoder=image_encoder, memory_attention=build_memory_attention(),
+                               memory_encoder=build_memory_encoder(), **kw)
+    if state_dict is not None:
+        own = model.state_dict()
+        sd = {k: v for k, v in state_dict.items() if k in own}
+        missing = [k for k in own if k not in sd]
+        if missing:
+            raise RuntimeError(f"checkpoint is missing hot-path keys, e.g. {missing[:5]}")
+        model.load_state_dict(sd, strict=True)
+    return model.to(device).eval()

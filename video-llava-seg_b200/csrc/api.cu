@@ -60,4 +60,26 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
   return launch_attention(a, (cudaStream_t)stream);
 }
 
+int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, vls_stream_t stream) {
+  VLS_REQUIRE(n == 0 || (in && out), "resize: null pointer");
+  return launch_resize_bilinear(in, n, h, w, out, H, W, (cudaStream_t)stream);
+}
+
+int vls_linear_f32(const float* x, long long ldx, const void* w_bf16, const float* bias, int rows, int n, int k, int act,
+                   float* out, long long ldo, vls_stream_t stream) {
+  VLS_REQUIRE(x && w_bf16 && out, "linear: null pointer");
+  SmallLinArgs s;
+  s.x = x; s.x_sr = ldx; s.W = w_bf16; s.bias = bias; s.out = out; s.o_sr = ldo;
+  s.G = 1; s.R = rows; s.N = n; s.K = k; s.act = act;
+  return launch_small_linear(s, (cudaStream_t)stream);
+}
+
+int vls_axpy_rows(const void* a, int a_dtype, long long a_st, long long a_sb, const void* p, int p_dtype, long long p_st,
+                  long long p_sb, float alpha, int B, int T, int C, void* out, int out_dtype, vls_stream_t stream) {
+  VLS_REQUIRE(a && out, "axpy_rows: null pointer");
+  return launch_axpy_rows(a, a_dtype, a_st, a_sb, p, p_dtype, p_st, p_sb, alpha, B, T, C,
+                          out_dtype == VLS_F32 ? (float*)out : nullptr, out_dtype == VLS_BF16 ? out : nullptr,
+                          (cudaStream_t)stream);
+}
+
 }  // extern "C"

@@ -118,4 +118,7 @@ int launch_im2col3x3s2(const void* in, int B, int H, int W, int C, void* out, cu
 int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
                       const float* lnb, float eps, void* out, cudaStream_t stream);
 
+// ---------------------------------------------------------------- resize (resize.cu)
+int launch_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, cudaStream_t stream);
+
 }  // namespace vls

@@ -22,7 +22,8 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ lo, int h, int
 
 // ------------------------------------------------------------------ stage 1: 1 -> 4 channels, HxW -> H/2 x W/2
 // mode 0: src is the high-res mask, used as is        (MemoryEncoder.forward skip_mask_sigmoid=True)
-// mode 1: src is the high-res mask, sigmoid applied   (skip_mask_sigmoid=False)
+// mode 1: src is the high-res mask, sigmoid(src)*scale + bias   (skip_mask_sigmoid=False: scale 1, bias 0)
+// mode 4: src is the high-res mask, (src > 0)*scale + bias
 // mode 2: src is the LOW-res logit map [h/F], value = sigmoid(bilinear)*scale + bias   (sam2_base.py:703-708)
 // mode 3: src is the LOW-res logit map, value = (bilinear > 0)*scale + bias            (sam2_base.py:698-700)
 __global__ void __launch_bounds__(256)
@@ -34,7 +35,8 @@ mds1_kernel(const float* __restrict__ src, int mode, int H, int W, int factor, f
   const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
   const int OH = H >> 1, OW = W >> 1;
   const int lh = H / factor, lw = W / factor;
-  const float* s = src + (long long)b * (mode >= 2 ? (long long)lh * lw : (long long)H * W);
+  const bool low = (mode == 2 || mode == 3);
+  const float* s = src + (long long)b * (low ? (long long)lh * lw : (long long)H * W);
   const float inv_f = 1.0f / factor;
   for (int i = threadIdx.x; i < 33 * 33; i += 256) {
     const int ty = i / 33, tx = i % 33;
@@ -42,7 +44,8 @@ mds1_kernel(const float* __restrict__ src, int mode, int H, int W, int factor, f
     float v = 0.f;
     if (Y >= 0 && Y < H && X >= 0 && X < W) {
       if (mode == 0) v = s[(long long)Y * W + X];
-      else if (mode == 1) v = 1.f / (1.f + expf(-s[(long long)Y * W + X]));
+      else if (mode == 1) v = 1.f / (1.f + expf(-s[(long long)Y * W + X])) * scale + bias_v;
+      else if (mode == 4) v = (s[(long long)Y * W + X] > 0.f ? 1.f : 0.f) * scale + bias_v;
       else {
         const float hr = bilerp(s, lh, lw, Y, X, inv_f);
         v = (mode == 2 ? 1.f / (1.f + expf(-hr)) : (hr > 0.f ? 1.f : 0.f)) * scale + bias_v;

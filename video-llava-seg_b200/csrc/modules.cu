@@ -375,7 +375,7 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
                             vls_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
   VLS_REQUIRE(w && pix_feat && mask && (out_nchw || out_rows_bf16), "mem_encoder: null argument");
-  VLS_REQUIRE(mask_mode >= 0 && mask_mode <= 3, "mem_encoder: bad mask_mode");
+  VLS_REQUIRE(mask_mode >= 0 && mask_mode <= 4, "mem_encoder: bad mask_mode");
   VLS_REQUIRE(workspace && workspace_bytes >= vls_mem_encoder_workspace_bytes(B, H, W), "mem_encoder: workspace too small");
   const int T = H * W;
   Workspace ws(workspace, workspace_bytes);
@@ -392,7 +392,7 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
   VLS_REQUIRE(m1 && m2 && m3 && col && scratch && x && t && pix && hid && orow, "mem_encoder: workspace carve failed");
 
   // mask down-sampler (memory_encoder.py:17-58): 3x (conv3x3 s2 + LN2d + GELU) on CUDA cores, the 4th as im2col + GEMM
-  VLS_TRY(launch_mds1(mask, mask_mode, B, 16 * H, 16 * W, mask_mode >= 2 ? 4 : 1, sig_scale, sig_bias, w->c1_w, w->c1_b,
+  VLS_TRY(launch_mds1(mask, mask_mode, B, 16 * H, 16 * W, (mask_mode == 2 || mask_mode == 3) ? 4 : 1, sig_scale, sig_bias, w->c1_w, w->c1_b,
                       w->ln1_w, w->ln1_b, LN2D_EPS, m1, st));
   VLS_TRY(launch_mds2(m1, B, 8 * H, 8 * W, w->c2_w, w->c2_b, w->ln2_w, w->ln2_b, LN2D_EPS, m2, st));
   VLS_TRY(launch_mds3(m2, B, 4 * H, 4 * W, w->c3_w, w->c3_b, w->ln3_w, w->ln3_b, LN2D_EPS, m3, st));

@@ -1,0 +1,35 @@
+"""Precomputed backbone features as a `video_path` for SAM2VideoPredictor.init_state: the image encoder
+(Hiera + FPN) is outside the hot path, so clips can be handed over as the tensors forward_image would return."""
+import torch
+
+
+class FeatureClip:
+    """Wraps `frame(t) -> {"vision_feat" [HW,1,256], "vision_pos" [HW,1,256], "feat_s0" [1,32,4H,4W],
+    "feat_s1" [1,64,2H,2W]}` (e.g. synth.SyntheticClip.frame).  With `pinned=True` frames are staged in pinned
+    host memory and copied to the device inside `frame_features` (the end-to-end path of bench.py); otherwise
+    they are uploaded once and stay resident in HBM."""
+
+    def __init__(self, frame_fn, num_frames, video_height=1024, video_width=1024, feat=64, resident_device=None,
+                 pinned=False):
+        self.num_frames, self.video_height, self.video_width, self.feat = num_frames, video_height, video_width, feat
+        self._frames = []
+        self.h2d_bytes_per_frame = 0
+        for t in range(num_frames):
+            f = frame_fn(t)
+            d = {k: v[:, :1].contiguous() if k.startswith("vision") else v[:1].contiguous() for k, v in f.items()}
+            if resident_device is not None:
+                d = {k: v.to(resident_device) for k, v in d.items()}
+            elif pinned:
+                d = {k: v.pin_memory() for k, v in d.items()}
+            self._frames.append(d)
+        if self._frames:
+            self.h2d_bytes_per_frame = sum(v.numel() * v.element_size() for v in self._frames[0].values())
+
+    def frame_features(self, t, device):
+        d = {k: v.to(device, non_blocking=True) for k, v in self._frames[t].items()}
+        s = self.feat
+        feat = d["vision_feat"].permute(1, 2, 0).reshape(1, 256, s, s)
+        pos = d["vision_pos"].permute(1, 2, 0).reshape(1, 256, s, s)
+        z0 = torch.zeros(1, 1, 4 * s, 4 * s, device=device)
+        z1 = torch.zeros(1, 1, 2 * s, 2 * s, device=device)
+        return {"backbone_fpn": [d["feat_s0"], d["feat_s1"], feat], "vision_pos_enc": [z0, z1, pos]}

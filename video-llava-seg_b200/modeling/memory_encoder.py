@@ -63,54 +63,49 @@ class MemoryEncoder(PackedModule):
         self.position_encoding = position_encoding
         self.out_proj = nn.Conv2d(in_dim, out_dim, kernel_size=1)
 
-    def _pack(self, dev):
-        if self._packed is None:
-            self._packed = _pack.pack_mem_encoder(self._flat_sd(), "", dev)
-        return self._packed[0]
+    def _encode(self, pix_nchw, pix_rows, mask, mode, scale, bias, gate, no_obj_embed, want_rows, out_dtype):
+        """One C call for the whole module.  Exactly one of pix_nchw [B,256,H,W] / pix_rows [HW,B,256] is given;
+        mask is [B,1,16H,16W] (modes 0/1/4) or the low-res logits [B,1,4H,4W] (modes 2/3)."""
+        require_cuda(mask)
+        dev = mask.device
+        if pix_nchw is not None:
+            pix = pix_nchw.to(dev)
+            B, _, H, W = pix.shape
+            layout, ps = 0, LL4(pix.stride(0), pix.stride(1), pix.stride(2), pix.stride(3))
+        else:
+            pix = pix_rows if pix_rows.stride(2) == 1 else pix_rows.contiguous()
+            T, B, _ = pix.shape
+            H = W = int(round(math.sqrt(T)))
+            layout, ps = 1, LL4(pix.stride(0), pix.stride(1), 0, 0)
+        f = 4 if mode in (2, 3) else 16
+        assert mask.shape == (B, 1, f * H, f * W), f"mask must be [B,1,{f}H,{f}W], got {tuple(mask.shape)}"
+        if self._packed is None or (no_obj_embed is not None and not self._packed[0].no_obj_embed):
+            self._packed = _pack.pack_mem_encoder(self._flat_sd(), "", dev, no_obj_embed)
+        w = self._packed[0]
+        m = mask.float().contiguous()
+        out = torch.empty((B, 64, H, W), device=dev, dtype=out_dtype)
+        rows = torch.empty((B, H * W, 64), device=dev, dtype=torch.bfloat16) if want_rows else None
+        nbytes = lib().vls_mem_encoder_workspace_bytes(B, H, W)
+        ws = self._workspace(nbytes, dev)
+        check(lib().vls_mem_encoder_forward(
+            ctypes_ref(w), ptr(pix), dtype_code(pix), layout, ps, ptr(m), int(mode), float(scale), float(bias),
+            ptr(gate), B, H, W, ptr(out), dtype_code(out), ptr(rows), ptr(ws), ws.numel(), stream()),
+            "vls_mem_encoder_forward")
+        return out, rows
 
     def forward(self, pix_feat, masks, skip_mask_sigmoid=False):
         """pix_feat [B,256,H,W], masks [B,1,16H,16W] -> {"vision_features": [B,64,H,W], "vision_pos_enc": [[B,64,H,W]]}
         (memory_encoder.py:158-181)."""
-        require_cuda(masks)
-        dev = masks.device
-        pix_feat = pix_feat.to(dev)
-        B, C, H, W = pix_feat.shape
-        assert masks.shape == (B, 1, 16 * H, 16 * W), "mask must be 16x the feature resolution"
-        w = self._pack(dev)
-        m = masks.float().contiguous()
-        ps = LL4(pix_feat.stride(0), pix_feat.stride(1), pix_feat.stride(2), pix_feat.stride(3))
-        out = torch.empty((B, 64, H, W), device=dev, dtype=pix_feat.dtype)
-        nbytes = lib().vls_mem_encoder_workspace_bytes(B, H, W)
-        ws = self._workspace(nbytes, dev)
-        check(lib().vls_mem_encoder_forward(
-            ctypes_ref(w), ptr(pix_feat), dtype_code(pix_feat), 0, ps, ptr(m), 0 if skip_mask_sigmoid else 1, 1.0, 0.0,
-            None, B, H, W, ptr(out), dtype_code(out), None, ptr(ws), ws.numel(), stream()), "vls_mem_encoder_forward")
+        out, _ = self._encode(pix_feat, None, masks, 0 if skip_mask_sigmoid else 1, 1.0, 0.0, None, None, False,
+                              pix_feat.dtype)
         pos = self.position_encoding(out).to(out.dtype)
         return {"vision_features": out, "vision_pos_enc": [pos]}
 
     def encode_from_low_res(self, vision_feat_rows, low_res_logits, binarize, sigmoid_scale, sigmoid_bias,
                             occluded_gate=None, no_obj_embed=None, want_rows=True):
         """Fast path used by the predictor (replaces sam2_base.py:372-378 + :676-724): takes the [B,1,4H,4W]
-        low-res logits and fuses the x4 bilinear up-sampling, sigmoid*scale+bias (or binarisation) into the first
+        low-res logits and fuses the x4 bilinear up-sampling and sigmoid*scale+bias (or binarisation) into the first
         convolution, so the [B,1,1024,1024] f32 mask never exists.  vision_feat_rows: [HW,B,256] seq-first.
         Returns (features NCHW bf16 [B,64,H,W], features rows bf16 [B,HW,64] or None)."""
-        require_cuda(vision_feat_rows, low_res_logits)
-        dev = low_res_logits.device
-        T, B, C = vision_feat_rows.shape
-        H = W = int(round(math.sqrt(T)))
-        assert low_res_logits.shape == (B, 1, 4 * H, 4 * W)
-        if self._packed is None or (no_obj_embed is not None and not self._packed[0].no_obj_embed):
-            self._packed = _pack.pack_mem_encoder(self._flat_sd(), "", dev, no_obj_embed)
-        w = self._packed[0]
-        vf = vision_feat_rows if vision_feat_rows.stride(2) == 1 else vision_feat_rows.contiguous()
-        ps = LL4(vf.stride(0), vf.stride(1), 0, 0)
-        lo = low_res_logits.float().contiguous()
-        out = torch.empty((B, 64, H, W), device=dev, dtype=torch.bfloat16)
-        rows = torch.empty((B, T, 64), device=dev, dtype=torch.bfloat16) if want_rows else None
-        nbytes = lib().vls_mem_encoder_workspace_bytes(B, H, W)
-        ws = self._workspace(nbytes, dev)
-        check(lib().vls_mem_encoder_forward(
-            ctypes_ref(w), ptr(vf), dtype_code(vf), 1, ps, ptr(lo), 3 if binarize else 2, float(sigmoid_scale),
-            float(sigmoid_bias), ptr(occluded_gate), B, H, W, ptr(out), 1, ptr(rows), ptr(ws), ws.numel(), stream()),
-            "vls_mem_encoder_forward")
-        return out, rows
+        return self._encode(None, vision_feat_rows, low_res_logits, 3 if binarize else 2, sigmoid_scale, sigmoid_bias,
+                            occluded_gate, no_obj_embed, want_rows, torch.bfloat16)

@@ -31,7 +31,7 @@ class PromptEncoder(nn.Module):
     def get_dense_pe(self):
         """[1, embed_dim, h, w]; cached so the decoder's PE-dependent constants are packed only once."""
         g = self.pe_layer.positional_encoding_gaussian_matrix
-        key = (g.data_ptr(), g._version)
+        key = (g.data_ptr(), g.device)
         if self._dense_pe is None or self._dense_pe[0] != key:
             self._dense_pe = (key, self.pe_layer(self.image_embedding_size).unsqueeze(0))
         return self._dense_pe[1]

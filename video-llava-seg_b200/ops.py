@@ -64,3 +64,41 @@ def attention_d256(q, k, vt, scale=None, splits=0, out=None):
                                    vt.stride(1), vt.stride(0), B, Nq, Nk, scale, splits, ptr(out), out.stride(1),
                                    out.stride(0), ptr(ws), nbytes, stream()), "vls_attention_d256")
     return out
+
+
+def resize_bilinear(x, size):
+    """F.interpolate(x, size, mode="bilinear", align_corners=False) for f32 [N,C,h,w]."""
+    _lib.require_cuda(x)
+    x = x.float().contiguous()
+    n, c, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((n, c, H, W), device=x.device, dtype=torch.float32)
+    check(lib().vls_resize_bilinear(ptr(x), n * c, h, w, ptr(out), H, W, stream()), "vls_resize_bilinear")
+    return out
+
+
+def linear_f32(x, w_bf16, bias=None, act=None):
+    """Small-row linear: x f32 [R,K], w bf16 [N,K] -> f32 [R,N]."""
+    _lib.require_cuda(x, w_bf16)
+    x = x.float().contiguous()
+    R, K = x.shape
+    N = w_bf16.shape[0]
+    assert w_bf16.dtype == torch.bfloat16 and w_bf16.is_contiguous() and w_bf16.shape[1] == K
+    out = torch.empty((R, N), device=x.device, dtype=torch.float32)
+    code = {None: 0, "none": 0, "relu": 1, "sigmoid": 3}[act]
+    check(lib().vls_linear_f32(ptr(x), K, ptr(w_bf16), ptr(bias), R, N, K, code, ptr(out), N, stream()),
+          "vls_linear_f32")
+    return out
+
+
+def add_rowvec(x, vec):
+    """x [T,B,C] (f32/bf16, unit channel stride) + vec [..., C] broadcast -> f32 [T,B,C] (seq-first view)."""
+    _lib.require_cuda(x, vec)
+    if x.stride(2) != 1:
+        x = x.contiguous()
+    T, B, C = x.shape
+    v = vec.reshape(-1).float().contiguous()
+    out = torch.empty((B, T, C), device=x.device, dtype=torch.float32)
+    check(lib().vls_axpy_rows(ptr(x), _lib.VLS_DTYPE[x.dtype], x.stride(0), x.stride(1), ptr(v), 0, 0, 0, 1.0, B, T, C,
+                              ptr(out), 0, stream()), "vls_axpy_rows")
+    return out.transpose(0, 1)

@@ -37,3 +37,39 @@ def fill_holes_in_mask_scores(mask, max_area):
     ws = torch.empty(max(nbytes, 1), device=out.device, dtype=torch.uint8)
     check(lib().vls_fill_holes(ptr(out), n, h, w, int(max_area), 0.1, ptr(ws), nbytes, stream()), "vls_fill_holes")
     return out
+
+
+def load_video_frames(video_path, image_size, offload_video_to_cpu, img_mean=(0.485, 0.456, 0.406),
+                      img_std=(0.229, 0.224, 0.225), async_loading_frames=False, compute_device=torch.device("cuda")):
+    """Frames -> ([T,3,S,S] normalised f32, video_height, video_width); host-side IO next to the hot path
+    (sam2/utils/misc.py:172-309).  Accepts a JPEG folder (frames named by integer index, as the reference
+    requires) or an already-normalised [T,3,H,W] tensor.  MP4 decoding needs `decord`, which this image lacks."""
+    import os
+
+    if isinstance(video_path, torch.Tensor):
+        t = video_path
+        assert t.dim() == 4 and t.shape[1] == 3, "expected a [T,3,H,W] tensor of normalised frames"
+        h, w = int(t.shape[-2]), int(t.shape[-1])
+        if (h, w) != (image_size, image_size):
+            t = torch.nn.functional.interpolate(t.float(), size=(image_size, image_size), mode="bilinear",
+                                                align_corners=False, antialias=True)
+        return (t if offload_video_to_cpu else t.to(compute_device)), h, w
+    if isinstance(video_path, str) and os.path.isdir(video_path):
+        import numpy as np
+        from PIL import Image
+
+        names = [p for p in os.listdir(video_path) if os.path.splitext(p)[-1].lower() in (".jpg", ".jpeg")]
+        names.sort(key=lambda p: int(os.path.splitext(p)[0]))
+        if not names:
+            raise RuntimeError(f"no images found in {video_path}")
+        mean = torch.tensor(img_mean, dtype=torch.float32)[:, None, None]
+        std = torch.tensor(img_std, dtype=torch.float32)[:, None, None]
+        frames, h, w = [], None, None
+        for n in names:
+            im = Image.open(os.path.join(video_path, n))
+            w, h = im.size
+            a = np.array(im.convert("RGB").resize((image_size, image_size)))
+            frames.append((torch.from_numpy(a).permute(2, 0, 1).float() / 255.0 - mean) / std)
+        images = torch.stack(frames, 0)
+        return (images if offload_video_to_cpu else images.to(compute_device)), h, w
+    raise NotImplementedError("Only JPEG folders and frame tensors are supported (MP4 needs decord)")
