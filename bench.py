@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- propagated frames/s of the SAM 2.1 mask-propagation hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W     # CPU arm: oracle port of the reference path
+
+Workload = BASELINE.json configs[1]: Hiera-B+ propagation at 1024^2 (64x64 tokens), 7-frame memory bank +
+16 object pointers (Nk = 28 736), 1 object per GPU, synthetic clip, random-init weights.  The image encoder is
+outside the hot path: clips are given as backbone features.  One step = one propagated frame in steady state
+(the bank is filled during an untimed 17-frame ramp).  N > 1: one process per GPU (torchrun), one clip per rank,
+no collective on the data path ("scaling": "weak"); NCCL only for the barrier / max-over-ranks of the time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("TQDM_DISABLE", "1")
+
+METRIC = "propagated frames/sec (SAM2.1 Hiera-B+ hot path, 1024^2, 7-frame memory bank, 1 object per GPU)"
+UNIT = "frames/s"
+WORKLOAD = "configs[1]: SAM2.1 Hiera-B+ propagation, 64x64 tokens, 7 memories + 16 pointers (Nk=28736), 1 object, synthetic"
+RAMP = 17  # prompt frame + 16 propagated frames: full memory bank and 16 pointers afterwards
+NQ, NK_STEADY, D = 4096, 7 * 4096 + 64, 256
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return dict(tflops=float(j.get("bf16_tflops_sustained", j.get("bf16_tflops", 1400.0))), hbm=float(j["hbm_gbs"]),
+                    source="measured (MEASURED_PEAKS.json, sustained bf16)")
+    return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)]
+        self.proc, self.thread = None, None
+
+    def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+def make_clip(seed, num_frames):
+    from video_llava_seg_b200 import synth
+
+    return synth.SyntheticClip(seed, num_frames)
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from video_llava_seg_b200 import _lib, build_sam, synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py measures the sm_100a kernels: a CUDA device is required (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.lib()
+    K, W = args.steps, max(args.warmup, 3)
+    T = max(RAMP + W + K + 1, RAMP + 9)  # the roofline pass needs RAMP + 8 frames
+    predictor = build_sam.build_sam2_video_predictor(None, synth.init_state_dict(0), dev)
+    clip = make_clip(100 + rank, T)
+    frames = [clip.frame(t, 1) for t in range(T)]
+    prompt = clip.point_prompt(1)["point_coords"][0].tolist()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def timed_pass(source, d2h):
+        """Ramp + warm-up untimed, then K steps each bracketed by CUDA events, L2 flushed between steps."""
+        state = predictor.init_state(source)
+        predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
+        gen = predictor.propagate_in_video(state)
+        for _ in range(RAMP + W):
+            _, _, m = next(gen)
+            if d2h:
+                (m > 0).to(torch.uint8).cpu()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        launches0 = lib.vls_launch_count()
+        out_bytes = 0
+        with ClockSampler(local) as clocks:
+            for i in range(K):
+                flush.zero_()
+                starts[i].record()
+                _, _, m = next(gen)
+                if d2h:
+                    host = (m > 0).to(torch.uint8).cpu()   # result read back every step
+                    out_bytes = host.numel()
+                stops[i].record()
+            torch.cuda.synchronize()
+        launches = lib.vls_launch_count() - launches0
+        ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+        if world > 1:
+            dist.barrier()
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        gen.close()
+        return ms, launches, clocks.summary(), out_bytes
+
+    # (1) device-resident inputs: kernel + host-orchestration throughput
+    resident = FeatureClip(lambda t: frames[t], T, resident_device=dev)
+    ms, launches, clocks, _ = timed_pass(resident, d2h=False)
+    value = world * K / (ms / 1e3)
+    # (2) end to end through the public API with host buffers: H2D of each frame's features, D2H of the mask
+    pinned = FeatureClip(lambda t: frames[t], T, pinned=True)
+    ms_e2e, _, _, out_bytes = timed_pass(pinned, d2h=True)
+    e2e = world * K / (ms_e2e / 1e3)
+    line = {
+        "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic backbone features + seeded random-init weights",
+        "config": {"workload": WORKLOAD, "objects_per_gpu": 1, "clips_per_gpu": 1, "ramp_frames": RAMP,
+                   "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
+                   "parallelism": f"{world} independent replica(s), sharded by clip, no collective on the path"},
+        "clocks": clocks, "gpu_launches": int(launches),
+        "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes_per_frame),
+                "d2h_bytes_per_step": int(out_bytes)},
+    }
+    if rank == 0:
+        line["roofline"] = roofline(predictor, resident, prompt, lib, torch)
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(steps=2)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def roofline(predictor, source, prompt, lib, torch):
+    """Dominant kernel = attn_fwd_kernel on the memory cross-attention (4 launches / frame).  Algorithmic FLOPs per
+    launch = 4 * Nq * Nk * d (QK^T + PV, 2 flops/MAC); duration = CUDA events around each launch on its stream."""
+    import ctypes
+
+    state = predictor.init_state(source)
+    predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
+    gen = predictor.propagate_in_video(state)
+    for _ in range(RAMP + 2):
+        next(gen)
+    torch.cuda.synchronize()
+    lib.vls_prof_enable(1)
+    for _ in range(6):
+        next(gen)
+    torch.cuda.synchronize()
+    lib.vls_prof_enable(0)
+    gen.close()
+    cnt, tot = ctypes.c_int(0), ctypes.c_double(0.0)
+    lib.vls_prof_collect(0, ctypes.byref(cnt), ctypes.byref(tot))
+    cnt_s, tot_s = ctypes.c_int(0), ctypes.c_double(0.0)
+    lib.vls_prof_collect(1, ctypes.byref(cnt_s), ctypes.byref(tot_s))
+    pk = peaks()
+    flops = 4.0 * NQ * NK_STEADY * D
+    avg_ms = tot.value / max(cnt.value, 1)
+    achieved = flops / (avg_ms * 1e-3) / 1e12 if avg_ms > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "attn_cross_dram_bytes.json")
+    if os.path.exists(prof):
+        traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+    return {"bound": "tensor", "kernel": "attn_fwd_kernel (memory cross-attention, Nq=4096, Nk=28736, d=256)",
+            "achieved": round(achieved, 2), "peak": pk["tflops"], "unit": "TFLOP/s", "frac": round(achieved / pk["tflops"], 4),
+            "traffic": traffic, "peak_source": pk["source"], "launches_timed": cnt.value,
+            "avg_launch_ms": round(avg_ms, 4), "flops_per_launch": flops,
+            "self_attn_avg_launch_ms": round(tot_s.value / max(cnt_s.value, 1), 4)}
+
+
+# ------------------------------------------------------------------------------------------ CPU arm (oracle port)
+def _oracle_steady_state(num_frames_total):
+    """A full memory bank for the CPU path without tracking 16 frames on the CPU: 7 memories from the oracle's
+    own memory encoder on synthetic masks + 16 seeded pointers (same shapes/dtypes the predictor would hold)."""
+    import torch
+
+    from oracle import sam2_path as O
+    from video_llava_seg_b200 import synth
+
+    sd = synth.init_state_dict(0)
+    clip = make_clip(100, num_frames_total)
+    g = torch.Generator().manual_seed(9)
+    out = {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
+    pos = O.sine_pe_2d(64, 64, 64)[None]
+    for t in range(RAMP):
+        e = dict(obj_ptr=torch.randn(1, 256, generator=g) * 0.5, maskmem_features=None, maskmem_pos_enc=[pos])
+        if t == 0 or t >= RAMP - 6:
+            f = clip.frame(t, 1)
+            mask = torch.sigmoid(torch.randn(1, 1, 1024, 1024, generator=g)) * 20 - 10
+            pix = f["vision_feat"].permute(1, 2, 0).reshape(1, 256, 64, 64)
+            e["maskmem_features"] = O.memory_encoder(sd, pix, mask, True)["vision_features"].to(torch.bfloat16)
+        (out["cond_frame_outputs"] if t == 0 else out["non_cond_frame_outputs"])[t] = e
+    return sd, clip, out
+
+
+def cpu_steps(steps, warmup=0):
+    import torch
+
+    from oracle import cc as cc_oracle
+    from oracle import sam2_path as O
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    T = RAMP + warmup + steps + 1
+    sd, clip, bank = _oracle_steady_state(T)
+    times = []
+    with torch.inference_mode():
+        for i in range(warmup + steps):
+            t = RAMP + i
+            feats = clip.frame(t, 1)
+            t0 = time.perf_counter()
+            o = O.track_step(sd, O.Cfg, t, False, feats, None, bank, T, run_mem_encoder=True)
+            pm = O.fill_holes_in_mask_scores(o["pred_masks"], O.Cfg.fill_hole_area, cc_oracle.cc_label)
+            dt = time.perf_counter() - t0
+            bank["non_cond_frame_outputs"][t] = dict(
+                maskmem_features=o["maskmem_features"].to(torch.bfloat16), maskmem_pos_enc=o["maskmem_pos_enc"],
+                pred_masks=pm, obj_ptr=o["obj_ptr"], object_score_logits=o["object_score_logits"])
+            if i >= warmup:
+                times.append(dt)
+    return times, torch.get_num_threads()
+
+
+def cpu_baseline(steps):
+    times, cores = cpu_steps(steps)
+    return {"value": round(len(times) / sum(times), 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{len(times)} steady-state frames (Nk=28736, 1 object) of oracle/sam2_path.py track_step + hole "
+                      f"filling, torch CPU fp32, {cores} threads"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    times, cores = cpu_steps(K, min(W, 1))
+    total = sum(times)
+    value = len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(value, 4), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+        "steps": len(times), "warmup": min(W, 1), "ms_per_step": round(total / len(times) * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic backbone features + seeded random-init weights",
+        "config": {"workload": WORKLOAD, "note": "reference path on the host CPU (oracle port of the unmodified PyTorch "
+                   "modules; the Python reference itself cannot travel to this box); each step = one steady-state frame"},
+        "cpu_baseline": {"value": round(value, 4), "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{len(times)} steady-state frames, torch CPU fp32, {cores} threads"},
+        "e2e": {"value": round(value, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -33,6 +33,13 @@ typedef void* vls_stream_t; /* cudaStream_t */
 
 const char* vls_last_error(void);
 int vls_abi_version(void);
+/* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
+long long vls_launch_count(void);
+/* Optional live kernel timing: when enabled, the attention launcher brackets its kernel with CUDA events
+ * on the launching stream; vls_prof_collect(slot) synchronises them and returns count / total ms and clears
+ * the slot.  slot 0 = memory cross-attention launches (Nk > Nq), slot 1 = self-attention launches. */
+void vls_prof_enable(int on);
+int vls_prof_collect(int slot, int* count, double* total_ms);
 
 /* ---- connected components ------------------------------------------------------------------
  * img: uint8 [n,1,h,w] (non-zero = foreground), h and w even (else error, as the reference

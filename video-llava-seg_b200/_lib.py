@@ -37,6 +37,11 @@ class GemmDesc(ctypes.Structure):
 def _declare(lib):
     lib.vls_last_error.restype = ctypes.c_char_p
     lib.vls_abi_version.restype = c_int
+    lib.vls_launch_count.restype = c_ll
+    lib.vls_prof_enable.restype = None
+    lib.vls_prof_enable.argtypes = [c_int]
+    lib.vls_prof_collect.restype = c_int
+    lib.vls_prof_collect.argtypes = [c_int, ctypes.POINTER(c_int), ctypes.POINTER(ctypes.c_double)]
     lib.vls_cc_workspace_bytes.restype = c_size_t
     lib.vls_cc_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vls_cc_label.restype = c_int

@@ -9,6 +9,12 @@ extern "C" {
 
 const char* vls_last_error(void) { return last_error(); }
 int vls_abi_version(void) { return 1; }
+long long vls_launch_count(void) { return launch_count(); }
+void vls_prof_enable(int on) { prof_set(on != 0); }
+int vls_prof_collect(int slot, int* count, double* total_ms) {
+  VLS_REQUIRE(slot >= 0 && slot < PROF_SLOTS && count && total_ms, "prof_collect: bad arguments");
+  return prof_collect(slot, count, total_ms);
+}
 
 size_t vls_cc_workspace_bytes(int n, int h, int w) { return cc_workspace_bytes(n, h, w, false); }
 int vls_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* workspace,

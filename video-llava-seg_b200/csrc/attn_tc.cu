@@ -330,14 +330,17 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.Nq + BM - 1) / BM, a.splits, a.B);
+  const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
+  prof_begin(slot, stream);
   attn_fwd_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
-  VLS_CUDA(cudaGetLastError());
+  prof_end(slot, stream);
+  VLS_POST_LAUNCH(1);
   if (a.splits > 1) {
     const long long rows = (long long)a.B * a.Nq;
     const int wpb = 8;
     attn_combine_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
         a.part_o, a.part_ml, a.B, a.Nq, a.splits, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride);
-    VLS_CUDA(cudaGetLastError());
+    VLS_POST_LAUNCH(1);
   }
   return 0;
 }

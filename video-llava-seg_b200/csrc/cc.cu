@@ -336,7 +336,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     }
     cc_small_kernel<FILL><<<n, CC_THREADS, small_smem(h, w), stream>>>(img, h, w, labels, counts, scores, max_area,
                                                                         fill_value);
-    VLS_CUDA(cudaGetLastError());
+    VLS_POST_LAUNCH(1);
     return 0;
   }
   const size_t px = (size_t)n * h * w;
@@ -351,7 +351,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   cc_g_merge<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, scores);
   cc_g_compress_count<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, area, scores);
   cc_g_final<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, area, counts, scores, max_area, fill_value);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(4);
   return 0;
 }
 

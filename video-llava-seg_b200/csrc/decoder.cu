@@ -314,7 +314,7 @@ __global__ void gate_ptr_kernel(float* __restrict__ ptr, const float* __restrict
 int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, int Nt, float* out, cudaStream_t stream) {
   VLS_REQUIRE(Nt >= 1 && Nt <= 32, "decoder: between 1 and 32 tokens are supported (got %d)", Nt);
   tok_self_attn_kernel<<<dim3(8, B), 128, 0, stream>>>(q, k, v, Nt, out);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -322,7 +322,7 @@ int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_s
                     int T, float* out, cudaStream_t stream) {
   t2i_attn_kernel<<<dim3(Nt, 8, B), 256, 0, stream>>>(q, reinterpret_cast<const bf16*>(kv), ld, kv_sb, koff, voff, Nt, T,
                                                       out);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -331,7 +331,7 @@ int launch_i2t_attn(const void* qrows, long long ld, long long q_sb, int qoff, c
   const size_t smem = (size_t)Nt * 128 * 2 * sizeof(float);
   i2t_attn_kernel<<<dim3((T * 8 + 255) / 256, B), 256, smem, stream>>>(reinterpret_cast<const bf16*>(qrows), ld, q_sb, qoff,
                                                                        ktok, vtok, Nt, T, reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -340,7 +340,7 @@ int launch_up1_post(const void* g, const void* feat, int feat_bf16, long long fe
   up1_post_kernel<<<dim3((2 * w + 31) / 32, 2 * h, B), 256, 0, stream>>>(reinterpret_cast<const float*>(g), feat, feat_bf16,
                                                                          feat_sb, h, w, lnw, lnb, eps,
                                                                          reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -356,7 +356,7 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
   }
   up2_masks_kernel<4><<<dim3((w2 + 31) / 32, h2, B), 128, smem, stream>>>(reinterpret_cast<const bf16*>(u), w2t, bias, feat,
                                                                           feat_bf16, feat_sb, hyper, h2, w2, masks);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -366,13 +366,13 @@ int launch_select_best(const float* masks, const float* iou, const float* tokens
   VLS_REQUIRE(HW % 4 == 0, "select_best: H*W must be a multiple of 4");
   select_best_kernel<<<dim3(16, B), 256, 0, stream>>>(masks, iou, tokens, obj_logits, M, multimask, HW, low_res, tok_sel,
                                                       best_idx, is_obj, -1024.0f);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_gate_ptr(float* ptr, const float* is_obj, const float* no_obj_ptr, int B, cudaStream_t stream) {
   gate_ptr_kernel<<<(B * 256 + 255) / 256, 256, 0, stream>>>(ptr, is_obj, no_obj_ptr, B);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 

@@ -218,7 +218,7 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
   gemm_tn_kernel<BN><<<grid, THREADS, smem_bytes<BN>(), stream>>>(tmA, tmB, e);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 

@@ -2,8 +2,11 @@
 
 #include <cudaTypedefs.h>
 
+#include <atomic>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 namespace vls {
 
@@ -16,6 +19,49 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+struct ProfSlot {
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+  cudaEvent_t open = nullptr;
+};
+static bool g_prof = false;
+static ProfSlot g_slots[PROF_SLOTS];
+bool prof_enabled() { return g_prof; }
+void prof_set(bool on) { g_prof = on; }
+void prof_begin(int slot, cudaStream_t stream) {
+  if (!g_prof) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  g_slots[slot].open = e;
+}
+void prof_end(int slot, cudaStream_t stream) {
+  if (!g_prof || !g_slots[slot].open) return;
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, stream);
+  g_slots[slot].ev.emplace_back(g_slots[slot].open, e);
+  g_slots[slot].open = nullptr;
+}
+int prof_collect(int slot, int* count, double* total_ms) {
+  *count = 0;
+  *total_ms = 0.0;
+  for (auto& pr : g_slots[slot].ev) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+      *count += 1;
+      *total_ms += ms;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  g_slots[slot].ev.clear();
+  return 0;
+}
 
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;

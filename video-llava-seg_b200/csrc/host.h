@@ -22,6 +22,24 @@ const char* last_error();
     }                                                                                           \
   } while (0)
 
+// Every kernel launch site reports itself (bench.py's `gpu_launches`) and checks the launch status.
+void count_launches(int n);
+long long launch_count();
+#define VLS_POST_LAUNCH(n)               \
+  do {                                   \
+    vls::count_launches(n);              \
+    VLS_CUDA(cudaGetLastError());        \
+  } while (0)
+
+// Optional per-kernel device timing (CUDA events on the launching stream), off by default.
+// Used by bench.py to measure the dominant kernel's average launch duration live.
+bool prof_enabled();
+void prof_begin(int slot, cudaStream_t stream);
+void prof_end(int slot, cudaStream_t stream);
+enum { PROF_ATTN_CROSS = 0, PROF_ATTN_SELF = 1, PROF_SLOTS = 8 };
+void prof_set(bool on);
+int prof_collect(int slot, int* count, double* total_ms);
+
 #define VLS_REQUIRE(cond, ...)      \
   do {                              \
     if (!(cond)) {                  \

@@ -301,7 +301,7 @@ int launch_mds1(const float* src, int mode, int B, int H, int W, int factor, flo
   mds1_kernel<<<dim3((W / 2 + 15) / 16, (H / 2 + 15) / 16, B), 256, 0, stream>>>(src, mode, H, W, factor, scale, bias_v, wgt,
                                                                                  cb, lnw, lnb, eps,
                                                                                  reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -310,7 +310,7 @@ int launch_mds2(const void* in, int B, int H, int W, const float* wgt, const flo
   mds2_kernel<<<dim3((W / 2 + 31) / 32, (H / 2 + 7) / 8, B), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), H, W, wgt,
                                                                                cb, lnw, lnb, eps,
                                                                                reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -320,7 +320,7 @@ int launch_mds3(const void* in, int B, int H, int W, const float* wgt, const flo
   mds3_kernel<<<dim3((W / 2 + 15) / 16, (H / 2 + 3) / 4, B), 256, smem, stream>>>(reinterpret_cast<const bf16*>(in), H, W,
                                                                                   wgt, cb, lnw, lnb, eps,
                                                                                   reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -329,7 +329,7 @@ int launch_im2col3x3s2(const void* in, int B, int H, int W, int C, void* out, cu
   const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
   im2col3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), B, H, W, C,
                                                                           reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -337,7 +337,7 @@ int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, con
                       const float* lnb, float eps, void* out, cudaStream_t stream) {
   dwconv7_ln_kernel<<<dim3((W + 7) / 8, H, B), 256, 0, stream>>>(x, H, W, wgt, cb, lnw, lnb, eps,
                                                                 reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 

@@ -42,7 +42,7 @@ int launch_resize_bilinear(const float* in, int n, int h, int w, float* out, int
   const long long total = (long long)n * H * ((W + 3) / 4);
   resize_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, h, w, out, H, W, (float)h / H,
                                                                               (float)w / W);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 

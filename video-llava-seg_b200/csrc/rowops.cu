@@ -246,7 +246,7 @@ int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse,
                         cudaStream_t stream) {
   const int total = B * (n_out + Ns) * 256;
   build_tokens_kernel<<<(total + 255) / 256, 256, 0, stream>>>(out_tokens, n_out, sparse, Ns, B, tok_a, tok_b);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -255,7 +255,7 @@ int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gat
   const long long total = (long long)B * T * C;
   rows_gate_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, B, T, C, gate, vec,
                                                                              reinterpret_cast<bf16*>(out));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -263,7 +263,7 @@ int launch_gather_rows(const float* src, long long sg, long long sr, int G, int 
   const int total = G * R * n;
   if (total == 0) return 0;
   gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, sg, sr, G, R, n, dst);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -274,7 +274,7 @@ int launch_ln256(const float* x, int B, int T, const float* w, const float* b, f
   const int wpb = 8;
   ln256_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
       x, B, T, w, b, eps, gelu, out_f32, f_sb, f_st, reinterpret_cast<bf16*>(out_bf16), h_sb, h_st);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -286,7 +286,7 @@ int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, 
   if (total4 == 0) return 0;
   axpy_rows_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
       a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -299,7 +299,7 @@ int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], cons
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), blk(32, 8);
   nchw_to_rows_kernel<<<grid, blk, 0, stream>>>(in, in_bf16, s1, add, add_bf16, s2, C, H, W, out_f32,
                                                reinterpret_cast<bf16*>(out_bf16));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -307,7 +307,7 @@ int launch_rows_to_nchw(const float* in, int B, int C, int T, const float* gate,
                         void* out_bf16, cudaStream_t stream) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), blk(32, 8);
   rows_to_nchw_kernel<<<grid, blk, 0, stream>>>(in, C, T, gate, vec, out_f32, reinterpret_cast<bf16*>(out_bf16));
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -325,7 +325,7 @@ int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream) {
   if (total == 0) return 0;
   const int wpb = 8;
   small_linear_kernel<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 
@@ -333,7 +333,7 @@ int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w,
                        long long o_sr, cudaStream_t stream) {
   if (rows == 0) return 0;
   ln256_small_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, x_sr, rows, w, b, eps, out, o_sr);
-  VLS_CUDA(cudaGetLastError());
+  VLS_POST_LAUNCH(1);
   return 0;
 }
 

@@ -13,10 +13,14 @@ class FeatureClip:
                  pinned=False):
         self.num_frames, self.video_height, self.video_width, self.feat = num_frames, video_height, video_width, feat
         self._frames = []
+        self._pos = None  # the neck's sine position encoding is a per-clip constant: uploaded once, not per frame
         self.h2d_bytes_per_frame = 0
         for t in range(num_frames):
             f = frame_fn(t)
             d = {k: v[:, :1].contiguous() if k.startswith("vision") else v[:1].contiguous() for k, v in f.items()}
+            pos = d.pop("vision_pos")
+            if self._pos is None:
+                self._pos = pos
             if resident_device is not None:
                 d = {k: v.to(resident_device) for k, v in d.items()}
             elif pinned:
@@ -27,6 +31,9 @@ class FeatureClip:
 
     def frame_features(self, t, device):
         d = {k: v.to(device, non_blocking=True) for k, v in self._frames[t].items()}
+        if self._pos.device != torch.device(device):
+            self._pos = self._pos.to(device)
+        d["vision_pos"] = self._pos
         s = self.feat
         feat = d["vision_feat"].permute(1, 2, 0).reshape(1, 256, s, s)
         pos = d["vision_pos"].permute(1, 2, 0).reshape(1, 256, s, s)
