@@ -94,6 +94,7 @@ def run_ours(args):
 
     from video_llava_seg_b200 import _lib, build_sam, synth
     from video_llava_seg_b200.features import FeatureClip
+    from video_llava_seg_b200.shard import aggregate_throughput
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -143,20 +144,16 @@ def run_ours(args):
         ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
         if world > 1:
             dist.barrier()
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
+        fps, ms, _ = aggregate_throughput(K, ms, dev)   # sum of frames over ranks / max-over-ranks device time
         gen.close()
-        return ms, launches, clocks.summary(), out_bytes
+        return fps, ms, launches, clocks.summary(), out_bytes
 
     # (1) device-resident inputs: kernel + host-orchestration throughput
     resident = FeatureClip(lambda t: frames[t], T, resident_device=dev)
-    ms, launches, clocks, _ = timed_pass(resident, d2h=False)
-    value = world * K / (ms / 1e3)
+    value, ms, launches, clocks, _ = timed_pass(resident, d2h=False)
     # (2) end to end through the public API with host buffers: H2D of each frame's features, D2H of the mask
     pinned = FeatureClip(lambda t: frames[t], T, pinned=True)
-    ms_e2e, _, _, out_bytes = timed_pass(pinned, d2h=True)
-    e2e = world * K / (ms_e2e / 1e3)
+    e2e, _, _, _, out_bytes = timed_pass(pinned, d2h=True)
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

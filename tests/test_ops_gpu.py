@@ -141,3 +141,24 @@ def test_cc_structured_and_errors(dev):
         ref = O.fill_holes_in_mask_scores(s, 8, cc=cc_oracle.cc_label)
         assert torch.equal(got.cpu(), ref)
         assert (got.cpu() != s).any()
+
+
+def test_cc_matches_reference_kernel(dev):
+    """Pin: the reference's own connected_components.cu (compiled unmodified into oracle/_ref/ in the build
+    container by oracle/build_ref.py) against our kernel and the C oracle, on the same masks."""
+    from oracle import build_ref
+    from oracle import cc as cc_oracle
+    from video_llava_seg_b200.utils.misc import get_connected_components
+
+    ref = build_ref.load_ref()
+    if ref is None:
+        pytest.skip("oracle/_ref/ref_cc.so was not built (needs /root/reference in the build container)")
+    g = torch.Generator().manual_seed(11)
+    for shape, dens in (((4, 1, 256, 256), 0.58), ((2, 1, 64, 96), 0.45), ((1, 1, 512, 384), 0.6)):
+        m = (torch.rand(shape, generator=g) < dens)
+        rl, rc = ref.get_connected_componnets(m.to(torch.uint8).to(dev))
+        ours_l, ours_c = get_connected_components(m.to(dev))
+        torch.cuda.synchronize()
+        assert torch.equal(ours_l, rl) and torch.equal(ours_c, rc)
+        ol, oc = cc_oracle.cc_label(m)
+        assert torch.equal(ol, rl.cpu()) and torch.equal(oc, rc.cpu())
