@@ -150,6 +150,14 @@ def run_ours(args):
 
     # (1) device-resident inputs: kernel + host-orchestration throughput
     resident = FeatureClip(lambda t: frames[t], T, resident_device=dev)
+    # one untimed pass over the whole clip first: the predictor keeps every frame's outputs (as the reference
+    # does), so a fresh process would otherwise time cudaMalloc growth of the caching allocator, not the path
+    warm = predictor.init_state(resident)
+    predictor.add_new_points_or_box(warm, 0, 1, points=prompt, labels=[1])
+    for _ in predictor.propagate_in_video(warm):
+        pass
+    del warm
+    torch.cuda.synchronize()
     value, ms, launches, clocks, _ = timed_pass(resident, d2h=False)
     # (2) end to end through the public API with host buffers: H2D of each frame's features, D2H of the mask
     pinned = FeatureClip(lambda t: frames[t], T, pinned=True)

@@ -104,8 +104,6 @@ typedef struct vls_mem_attn_layer {
   const void* sa_v_w;  const float* sa_v_b;   /* [256,256] */
   const void* sa_o_w;  const float* sa_o_b;   /* [256,256] */
   const void* ca_q_w;  const float* ca_q_b;   /* [256,256] cross_attn_image.q_proj */
-  const void* ca_k_w;  const float* ca_k_b;   /* [256,64] */
-  const void* ca_v_w;  const float* ca_v_b;   /* [256,64] */
   const void* ca_o_w;  const float* ca_o_b;   /* [256,256] */
   const void* l1_w;    const float* l1_b;     /* [2048,256] */
   const void* l2_w;    const float* l2_b;     /* [256,2048] */
@@ -115,6 +113,10 @@ typedef struct vls_mem_attn_weights {
   int num_layers;                 /* <= 8 */
   vls_mem_attn_layer layers[8];
   const float *norm_w, *norm_b;
+  /* cross_attn_image.k_proj / v_proj of all layers stacked, so the memory bank is projected for every
+   * layer in one launch: bf16 [num_layers][256][64], f32 [num_layers][256] */
+  const void* ca_k_w_all; const float* ca_k_b_all;
+  const void* ca_v_w_all; const float* ca_v_b_all;
   const float *rope_cos, *rope_sin; /* f32 [Nq][128]: axial table for a sqrt(Nq) x sqrt(Nq) grid */
   int rope_len;                   /* must equal Nq */
 } vls_mem_attn_weights;
@@ -170,14 +172,17 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
                              int H, int W, float* masks, float* iou, float* tokens_out, float* obj_logits,
                              void* workspace, size_t workspace_bytes, vls_stream_t stream);
 
-/* Post-decoder glue of SAM2Base._forward_sam_heads (sam2_base.py:359-403). */
+/* Post-decoder glue of SAM2Base._forward_sam_heads (sam2_base.py:359-403).  masks [B][4][HW], iou [B][4],
+ * tokens [B][4][256], obj_logits [B] (all f32).  Outputs: low_res_masks [B][HW] (best-IoU mask, -1024 where the
+ * object is absent), obj_ptr [B][256], best_idx [B], is_obj [B] and occluded [B] = 1 - is_obj (f32). */
 typedef struct vls_obj_ptr_weights {
   const void* w[3]; const float* b[3];  /* obj_ptr_proj MLP 256-256-256-256 */
   const float* no_obj_ptr;              /* f32 [256] */
 } vls_obj_ptr_weights;
 int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
                        const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
-                       int* best_idx, float* is_obj, void* workspace, size_t workspace_bytes, vls_stream_t stream);
+                       int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                       vls_stream_t stream);
 
 /* Memory encoder (memory_encoder.py:158-181). */
 typedef struct vls_cx_block {

@@ -128,8 +128,8 @@ def test_ctypes_structs_match_header_sizes():
     from video_llava_seg_b200 import _pack
 
     P, I = ctypes.sizeof(ctypes.c_void_p), ctypes.sizeof(ctypes.c_int)
-    assert ctypes.sizeof(_pack.MemAttnLayer) == 24 * P
-    assert ctypes.sizeof(_pack.MemAttnWeights) == P + 8 * 24 * P + 4 * P + P  # ints padded to pointer alignment
+    assert ctypes.sizeof(_pack.MemAttnLayer) == 20 * P
+    assert ctypes.sizeof(_pack.MemAttnWeights) == P + 8 * 20 * P + 8 * P + P  # ints padded to pointer alignment
     assert ctypes.sizeof(_pack.AttnW) == 8 * P
     assert ctypes.sizeof(_pack.DecLayer) == 3 * 8 * P + 15 * P
     assert ctypes.sizeof(_pack.CxBlock) == 8 * P

@@ -82,7 +82,7 @@ def _declare_modules(lib):
                                              c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vls_sam_heads_post.restype = c_int
     lib.vls_sam_heads_post.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
-                                       c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
     lib.vls_mem_encoder_workspace_bytes.restype = c_size_t
     lib.vls_mem_encoder_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vls_mem_encoder_forward.restype = c_int

@@ -271,7 +271,8 @@ up2_masks_kernel(const bf16* __restrict__ u, const float* __restrict__ w2t, cons
 __global__ void select_best_kernel(const float* __restrict__ masks, const float* __restrict__ iou,
                                    const float* __restrict__ tokens, const float* __restrict__ obj_logits, int M,
                                    int multimask, int HW, float* __restrict__ low_res, float* __restrict__ tok_sel,
-                                   int* __restrict__ best_idx, float* __restrict__ is_obj_out, float no_obj_score) {
+                                   int* __restrict__ best_idx, float* __restrict__ is_obj_out,
+                                   float* __restrict__ occluded_out, float no_obj_score) {
   const int b = blockIdx.y;
   int best = 0;
   if (multimask) {
@@ -296,6 +297,7 @@ __global__ void select_best_kernel(const float* __restrict__ masks, const float*
     if (threadIdx.x == 0) {
       best_idx[b] = best;
       is_obj_out[b] = is_obj ? 1.f : 0.f;
+      occluded_out[b] = is_obj ? 0.f : 1.f;
     }
   }
 }
@@ -362,10 +364,10 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
 
 int launch_select_best(const float* masks, const float* iou, const float* tokens, const float* obj_logits, int B, int M,
                        int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
-                       cudaStream_t stream) {
+                       float* occluded, cudaStream_t stream) {
   VLS_REQUIRE(HW % 4 == 0, "select_best: H*W must be a multiple of 4");
   select_best_kernel<<<dim3(16, B), 256, 0, stream>>>(masks, iou, tokens, obj_logits, M, multimask, HW, low_res, tok_sel,
-                                                      best_idx, is_obj, -1024.0f);
+                                                      best_idx, is_obj, occluded, -1024.0f);
   VLS_POST_LAUNCH(1);
   return 0;
 }

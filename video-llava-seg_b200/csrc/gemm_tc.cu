@@ -3,10 +3,13 @@
 //
 //   C[b][m][n] = epi( sum_k A[b][m][k] * W[n][k] )      A, W: bf16, K-major;  accumulate f32 in TMEM
 //
-// One CTA computes a 128 x BN tile.  Warp 0 = TMA producer (4-stage mbarrier ring, 128B-swizzled
-// [128 x 64] / [BN x 64] boxes), warp 1 = single-thread tcgen05.mma issuer + TMEM owner,
-// warps 2-5 = epilogue (each warp drains its 32-lane TMEM quarter with tcgen05.ld 32x32b.x32 and
-// applies bias / ReLU / GELU / RoPE / residual before the store).
+// One CTA computes a 128 x BN tile.  Warp 0 = TMA producer (6/8-stage mbarrier ring = 192 KB of
+// 128B-swizzled [128 x 64] / [BN x 64] boxes in flight), warp 1 = single-thread tcgen05.mma issuer +
+// TMEM owner, warps 2-5 = epilogue: each warp drains its 32-lane TMEM quarter (tcgen05.ld 32x32b.x32)
+// into an f32 staging tile that reuses the idle operand ring, then the 128 epilogue threads sweep the
+// tile row-wise so that bias / ReLU / GELU / RoPE-table / residual reads and the stores are all
+// coalesced 128-bit accesses.  blockIdx.z indexes (object, layer) batches with independent
+// div/mod maps per operand, so e.g. the memory K/V projections of all 4 layers are one launch.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -16,14 +19,25 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int STAGES = 4;
 constexpr int THREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN>
+struct Cfg {
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = BN == 64 ? 8 : 6;              // 192 KB of operand ring either way
+  static constexpr int PITCH = BN + 4;                          // f32 staging pitch (16 B aligned, conflict-free)
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
+  static_assert(BM * PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
+};
 
 struct Epi {
   int M, N, K;
   const float* bias;
   int bias_mode, act;
+  long long bias_bstride;
+  int bias_div, bias_mod;
   const float* rope_cos;
   const float* rope_sin;
   int rope_period, rope_rows;
@@ -32,19 +46,16 @@ struct Epi {
   void* C;
   int c_bf16;
   long long ldc, c_bstride;
-  int w_batched, a_batched;
+  int a_div, a_mod, w_div, w_mod;   // operand batch index = (blockIdx.z / div) % mod
 };
-
-template <int BN>
-constexpr int smem_bytes() {
-  return STAGES * (A_BYTES + BN * BK * 2) + 128 + 1024;
-}
 
 template <int BN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Epi e) {
-  constexpr int B_BYTES = BN * BK * 2;
-  constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  using C_ = Cfg<BN>;
+  constexpr int STAGES = C_::STAGES;
+  constexpr int STAGE_BYTES = C_::STAGE_BYTES;
+  constexpr int PITCH = C_::PITCH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
@@ -80,14 +91,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     if (lane == 0) {
-      const int wz = e.w_batched ? bz : 0;
+      const int az = (bz / e.a_div) % e.a_mod;
+      const int wz = (bz / e.w_div) % e.w_mod;
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* sa = smem + s * STAGE_BYTES;
-        tma_load_3d(sa, &tmA, &full[s], kb * BK, m0, e.a_batched ? bz : 0);
+        tma_load_3d(sa, &tmA, &full[s], kb * BK, m0, az);
         tma_load_3d(sa + A_BYTES, &tmB, &full[s], kb * BK, n0, wz);
       }
     }
@@ -110,84 +122,71 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       umma_commit(acc_full);
     }
   } else {
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
-    const bool row_ok = row < e.M;
-    mbar_wait(acc_full, 0);
+    // ---- epilogue: TMEM -> registers -> f32 staging tile in the (now idle) operand ring -> coalesced pass
+    const int q = warp & 3;          // TMEM lane quarter of this warp
+    const int et = threadIdx.x - 64; // 0..127
+    float* stage = reinterpret_cast<float*>(smem);
+    mbar_wait(acc_full, 0);          // all MMAs done => every TMA load has landed and been consumed
     tc_fence_after();
-    const float bias_row = (e.bias_mode == 2 && row_ok) ? e.bias[row] : 0.0f;
-    const bool do_rope = e.rope_cos != nullptr && row < e.rope_rows;
-    const int pos = do_rope ? (row % e.rope_period) : 0;
-    const float* res_row = e.residual ? e.residual + (long long)bz * e.res_bstride + (long long)row * e.ld_res : nullptr;
+    {
+      float* srow = stage + (q * 32 + lane) * PITCH;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld32(tmem + (uint32_t(q * 32) << 16) + c * 32, r);
-      tc_wait_ld();
-      const int col0 = n0 + c * 32;
-      if (!row_ok || col0 >= e.N) continue;
-      float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem + (uint32_t(q * 32) << 16) + c * 32, r);
+        tc_wait_ld();
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(srow + c * 32 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");  // the four epilogue warps only
+    constexpr int CG = BN / 4;            // float4 column groups per row
+    constexpr int RPP = 128 / CG;         // rows handled per pass by the 128 epilogue threads
+    const int cg = et % CG;
+    const int col = n0 + cg * 4;
+    const bool col_ok = col < e.N;        // N % 4 == 0 is required by the launcher
+    const float* bias = e.bias ? e.bias + (long long)((bz / e.bias_div) % e.bias_mod) * e.bias_bstride : nullptr;
+    float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias_mode == 1 && col_ok) bcol = *reinterpret_cast<const float4*>(bias + col);
+    const int pair0 = (col & 255) >> 1;
+#pragma unroll 2
+    for (int r0 = 0; r0 < BM; r0 += RPP) {
+      const int rl = r0 + et / CG;
+      const int row = m0 + rl;
+      if (row >= e.M || !col_ok) continue;
+      float4 v = *reinterpret_cast<const float4*>(stage + rl * PITCH + cg * 4);
       if (e.bias_mode == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < e.N) v[j] += __ldg(e.bias + col0 + j);
+        v.x += bcol.x; v.y += bcol.y; v.z += bcol.z; v.w += bcol.w;
       } else if (e.bias_mode == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] += bias_row;
+        const float b = __ldg(bias + row);
+        v.x += b; v.y += b; v.z += b; v.w += b;
       }
       if (e.act == 1) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
       } else if (e.act == 2) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
       }
-      if (do_rope) {
-        const int pair0 = (col0 & 255) >> 1;
-        const float* cs = e.rope_cos + (long long)pos * 128 + pair0;
-        const float* sn = e.rope_sin + (long long)pos * 128 + pair0;
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const float co = __ldg(cs + j), si = __ldg(sn + j);
-          const float a = v[2 * j], b = v[2 * j + 1];
-          v[2 * j] = a * co - b * si;
-          v[2 * j + 1] = a * si + b * co;
-        }
+      if (e.rope_cos != nullptr && row < e.rope_rows) {
+        const long long t = (long long)(row % e.rope_period) * 128 + pair0;
+        const float2 co = *reinterpret_cast<const float2*>(e.rope_cos + t);
+        const float2 si = *reinterpret_cast<const float2*>(e.rope_sin + t);
+        const float a0 = v.x, b0 = v.y, a1 = v.z, b1 = v.w;
+        v.x = a0 * co.x - b0 * si.x; v.y = a0 * si.x + b0 * co.x;
+        v.z = a1 * co.y - b1 * si.y; v.w = a1 * si.y + b1 * co.y;
       }
-      if (res_row) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < e.N) v[j] += res_row[col0 + j];
+      if (e.residual) {
+        const float4 rr = *reinterpret_cast<const float4*>(e.residual + (long long)bz * e.res_bstride +
+                                                           (long long)row * e.ld_res + col);
+        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
       }
-      const long long off = (long long)bz * e.c_bstride + (long long)row * e.ldc + col0;
-      const bool full_chunk = col0 + 32 <= e.N;
-      if (e.c_bf16) {
-        bf16* out = reinterpret_cast<bf16*>(e.C) + off;
-        if (full_chunk && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-          uint4* o4 = reinterpret_cast<uint4*>(out);
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            o4[j] = make_uint4(pack_bf16x2(v[8 * j], v[8 * j + 1]), pack_bf16x2(v[8 * j + 2], v[8 * j + 3]),
-                               pack_bf16x2(v[8 * j + 4], v[8 * j + 5]), pack_bf16x2(v[8 * j + 6], v[8 * j + 7]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < e.N) out[j] = __float2bfloat16_rn(v[j]);
-        }
-      } else {
-        float* out = reinterpret_cast<float*>(e.C) + off;
-        if (full_chunk && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
-          float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < e.N) out[j] = v[j];
-        }
-      }
+      const long long off = (long long)bz * e.c_bstride + (long long)row * e.ldc + col;
+      if (e.c_bf16)
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+      else
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + off) = v;
     }
   }
   tc_fence_before();
@@ -198,38 +197,44 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 template <int BN>
 int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   CUtensorMap tmA, tmB;
-  const bool a_batched = a.a_bstride != 0 && a.batch > 1;
-  VLS_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a_batched ? a.batch : 1, a.lda, a.a_bstride, BM));
-  const bool w_batched = a.w_bstride != 0 && a.batch > 1;
-  VLS_TRY(make_tmap_bf16(&tmB, a.W, a.K, a.N, w_batched ? a.batch : 1, a.ldw, a.w_bstride, BN));
+  VLS_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a.a_batches, a.lda, a.a_bstride, BM));
+  VLS_TRY(make_tmap_bf16(&tmB, a.W, a.K, a.N, a.w_batches, a.ldw, a.w_bstride, BN));
   Epi e;
   e.M = a.M; e.N = a.N; e.K = a.K;
   e.bias = a.bias; e.bias_mode = a.bias ? a.bias_mode : 0; e.act = a.act;
+  e.bias_bstride = a.bias_bstride; e.bias_div = a.bias_div > 0 ? a.bias_div : 1; e.bias_mod = a.bias_batches > 0 ? a.bias_batches : 1;
   e.rope_cos = a.rope_cos; e.rope_sin = a.rope_sin; e.rope_period = a.rope_period > 0 ? a.rope_period : 1;
   e.rope_rows = a.rope_rows;
   e.residual = a.residual; e.ld_res = a.ld_res; e.res_bstride = a.res_bstride;
   e.C = a.C; e.c_bf16 = a.c_bf16; e.ldc = a.ldc; e.c_bstride = a.c_bstride;
-  e.w_batched = w_batched ? 1 : 0;
-  e.a_batched = a_batched ? 1 : 0;
+  e.a_div = a.a_div; e.a_mod = a.a_batches; e.w_div = a.w_div; e.w_mod = a.w_batches;
   static bool attr_set = false;
   if (!attr_set) {
-    VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BN>()));
+    VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
     attr_set = true;
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
-  gemm_tn_kernel<BN><<<grid, THREADS, smem_bytes<BN>(), stream>>>(tmA, tmB, e);
+  gemm_tn_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, e);
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 }  // namespace
 
-int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
+int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
+  GemmArgs a = a_in;
   VLS_REQUIRE(a.A && a.W && a.C, "gemm: null operand");
   VLS_REQUIRE(a.M > 0 && a.N > 0 && a.K > 0 && a.batch > 0, "gemm: bad shape M=%d N=%d K=%d batch=%d", a.M, a.N,
               a.K, a.batch);
   VLS_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
+  VLS_REQUIRE(a.N % 4 == 0 && a.ldc % 4 == 0, "gemm: N and ldc must be multiples of 4");
+  VLS_REQUIRE(!a.residual || a.ld_res % 4 == 0, "gemm: ld_res must be a multiple of 4");
   VLS_REQUIRE(!a.rope_cos || (a.rope_sin && a.rope_period > 0), "gemm: incomplete RoPE arguments");
+  // default batch indexing: operand batch = blockIdx.z when it has a batch stride, else shared
+  if (a.a_batches <= 0) { a.a_batches = (a.a_bstride != 0 && a.batch > 1) ? a.batch : 1; a.a_div = 1; }
+  if (a.w_batches <= 0) { a.w_batches = (a.w_bstride != 0 && a.batch > 1) ? a.batch : 1; a.w_div = 1; }
+  if (a.a_div <= 0) a.a_div = 1;
+  if (a.w_div <= 0) a.w_div = 1;
   const long long tiles128 = (long long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
   if (tiles128 < 120 || a.N <= 64) return launch_bn<64>(a, stream);
   return launch_bn<128>(a, stream);

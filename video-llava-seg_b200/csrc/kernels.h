@@ -16,8 +16,11 @@ struct GemmArgs {
   const void* W = nullptr;   // bf16 [batch or 1][N][ldw]
   long long ldw = 0, w_bstride = 0;  // w_bstride == 0 -> shared across the batch
   int M = 0, N = 0, K = 0, batch = 1;
+  // optional explicit batch maps: operand batch index = (blockIdx.z / div) % batches  (0 = derive from strides)
+  int a_batches = 0, a_div = 1, w_batches = 0, w_div = 1;
   const float* bias = nullptr;
   int bias_mode = 0;         // 0 none, 1 per output column (n), 2 per output row (m)
+  long long bias_bstride = 0; int bias_batches = 0, bias_div = 1;  // bias + ((z / div) % batches) * stride
   int act = 0;               // 0 none, 1 ReLU, 2 GELU(erf)
   const float* rope_cos = nullptr;  // [rope_period][128]; rotates column pairs inside every 256-column block
   const float* rope_sin = nullptr;
@@ -104,7 +107,7 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
                      cudaStream_t stream);
 int launch_select_best(const float* masks, const float* iou, const float* tokens, const float* obj_logits, int B, int M,
                        int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
-                       cudaStream_t stream);
+                       float* occluded, cudaStream_t stream);
 int launch_gate_ptr(float* ptr, const float* is_obj, const float* no_obj_ptr, int B, cudaStream_t stream);
 
 // ---------------------------------------------------------------- memory encoder kernels (memenc.cu)

@@ -32,22 +32,25 @@ GemmArgs lin(const void* A, long long lda, long long a_bs, const void* W, int M,
 extern "C" {
 
 // ================================================================== memory attention
-size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) {
-  const long long ldv = rup(Nq > Nk ? Nq : Nk, 64);
+static size_t mem_attn_ws(int B, int Nq, int Nk, int L) {
+  const long long ldv = rup(Nk, 64), ldvs = rup(Nq, 64);
   size_t n = 0;
-  n += align256((size_t)B * Nq * C * 4);        // x
-  n += align256((size_t)B * Nq * C * 2);        // t
-  n += align256((size_t)B * Nq * 2 * C * 2);    // qk
-  n += 2 * align256((size_t)B * Nk * CM * 2);   // mem, mempos
-  n += align256((size_t)B * Nk * C * 2);        // kc
-  n += align256((size_t)B * C * ldv * 2);       // vt
-  n += align256((size_t)B * Nq * C * 2);        // ao
-  n += align256((size_t)B * Nq * FFN * 2);      // h
+  n += align256((size_t)B * Nq * C * 4);            // x
+  n += align256((size_t)B * Nq * C * 2);            // t
+  n += align256((size_t)B * Nq * 2 * C * 2);        // qk
+  n += 2 * align256((size_t)B * Nk * CM * 2);       // mem, mempos
+  n += align256((size_t)L * B * Nk * C * 2);        // rotated cross-attention keys of every layer
+  n += align256((size_t)L * B * C * ldv * 2);       // transposed cross-attention values of every layer
+  n += align256((size_t)B * C * ldvs * 2);          // transposed self-attention values
+  n += align256((size_t)B * Nq * C * 2);            // ao
+  n += align256((size_t)B * Nq * FFN * 2);          // h
   const int s1 = attn_pick_splits(B, Nq, Nq), s2 = attn_pick_splits(B, Nq, Nk);
   const size_t a1 = attn_workspace_bytes(B, Nq, s1), a2 = attn_workspace_bytes(B, Nq, s2);
   n += align256(a1 > a2 ? a1 : a2);
   return n + 4096;
 }
+
+size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) { return mem_attn_ws(B, Nq, Nk, 8); }
 
 int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
                          long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
@@ -63,22 +66,25 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   VLS_REQUIRE(w->rope_cos && w->rope_sin && w->rope_len == Nq, "mem_attn: RoPE table length %d != Nq %d", w->rope_len, Nq);
   VLS_REQUIRE((Nk - num_obj_ptr_tokens) % Nq == 0, "mem_attn: rotated keys (%d) must be a multiple of Nq (%d)",
               Nk - num_obj_ptr_tokens, Nq);  // rope_k_repeat (sam/transformer.py:329-338)
-  VLS_REQUIRE(workspace && workspace_bytes >= vls_mem_attn_workspace_bytes(B, Nq, Nk), "mem_attn: workspace too small");
+  const int L = w->num_layers;
+  VLS_REQUIRE(workspace && workspace_bytes >= mem_attn_ws(B, Nq, Nk, L), "mem_attn: workspace too small");
+  VLS_REQUIRE(w->ca_k_w_all && w->ca_k_b_all && w->ca_v_w_all && w->ca_v_b_all, "mem_attn: stacked K/V weights missing");
   Workspace ws(workspace, workspace_bytes);
-  const long long ldv = rup(Nq > Nk ? Nq : Nk, 64);
+  const long long ldv = rup(Nk, 64), ldvs = rup(Nq, 64);
   float* x = (float*)ws.take((size_t)B * Nq * C * 4);
   void* t = ws.take((size_t)B * Nq * C * 2);
   char* qk = (char*)ws.take((size_t)B * Nq * 2 * C * 2);
   void* mem = ws.take((size_t)B * Nk * CM * 2);
   void* mempos = ws.take((size_t)B * Nk * CM * 2);
-  void* kc = ws.take((size_t)B * Nk * C * 2);
-  void* vt = ws.take((size_t)B * C * ldv * 2);
+  char* kc_all = (char*)ws.take((size_t)L * B * Nk * C * 2);
+  char* vt_all = (char*)ws.take((size_t)L * B * C * ldv * 2);
+  void* vts = ws.take((size_t)B * C * ldvs * 2);
   void* ao = ws.take((size_t)B * Nq * C * 2);
   void* h = ws.take((size_t)B * Nq * FFN * 2);
   const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits(B, Nq, Nk);
   const size_t a1 = attn_workspace_bytes(B, Nq, s_self), a2 = attn_workspace_bytes(B, Nq, s_cross);
   char* aws = (char*)ws.take(a1 > a2 ? a1 : a2);
-  VLS_REQUIRE(x && t && qk && mem && mempos && kc && vt && ao && h && (aws || (a1 == 0 && a2 == 0)),
+  VLS_REQUIRE(x && t && qk && mem && mempos && kc_all && vt_all && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
               "mem_attn: workspace carve failed");
 
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
@@ -88,11 +94,32 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
                            memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, st));
 
-  auto attention = [&](const void* K, long long ldk, long long k_bs, int nk, int splits) -> int {
+  // memory K / V^T projections of ALL layers in two launches (they do not depend on x): batch index z = l*B + b.
+  //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated);   V_l^T = Wv_l mem^T + bv_l
+  {
+    GemmArgs k;
+    k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
+    k.W = w->ca_k_w_all; k.ldw = CM; k.w_bstride = (long long)C * CM; k.w_batches = L; k.w_div = B;
+    k.M = Nk; k.N = C; k.K = CM; k.batch = L * B;
+    k.bias = w->ca_k_b_all; k.bias_mode = 1; k.bias_bstride = C; k.bias_batches = L; k.bias_div = B;
+    k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
+    k.C = kc_all; k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
+    VLS_TRY(launch_gemm(k, st));
+    GemmArgs v;
+    v.A = w->ca_v_w_all; v.lda = CM; v.a_bstride = (long long)C * CM; v.a_batches = L; v.a_div = B;
+    v.W = mem; v.ldw = CM; v.w_bstride = (long long)Nk * CM; v.w_batches = B; v.w_div = 1;
+    v.M = C; v.N = Nk; v.K = CM; v.batch = L * B;
+    v.bias = w->ca_v_b_all; v.bias_mode = 2; v.bias_bstride = C; v.bias_batches = L; v.bias_div = B;
+    v.C = vt_all; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
+    VLS_TRY(launch_gemm(v, st));
+  }
+
+  auto attention = [&](const void* K, long long ldk, long long k_bs, const void* Vt, long long ldvt, int nk,
+                       int splits) -> int {
     AttnArgs a;
     a.Q = qk; a.ldq = 2 * C; a.q_bstride = (long long)Nq * 2 * C;
     a.K = K; a.ldk = ldk; a.k_bstride = k_bs;
-    a.Vt = vt; a.ldvt = ldv; a.vt_bstride = (long long)C * ldv;
+    a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = (long long)C * ldvt;
     a.B = B; a.Nq = Nq; a.Nk = nk; a.scale = 0.0625f; a.splits = splits;
     a.O = ao; a.ldo = C; a.o_bstride = (long long)Nq * C;
     if (splits > 1) {
@@ -102,58 +129,49 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     return launch_attention(a, st);
   };
 
-  for (int l = 0; l < w->num_layers; ++l) {
-    const vls_mem_attn_layer& L = w->layers[l];
+  for (int l = 0; l < L; ++l) {
+    const vls_mem_attn_layer& Lw = w->layers[l];
     // ---- self attention (memory_attention.py:58-64): q = k = v = LN1(x); RoPE on q and k
-    VLS_TRY(launch_ln256(x, B, Nq, L.n1_w, L.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    VLS_TRY(launch_ln256(x, B, Nq, Lw.n1_w, Lw.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
-      GemmArgs g = lin(t, C, (long long)Nq * C, L.sa_qk_w, Nq, 2 * C, C, B, L.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
+      GemmArgs g = lin(t, C, (long long)Nq * C, Lw.sa_qk_w, Nq, 2 * C, C, B, Lw.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
       VLS_TRY(launch_gemm(g, st));
       GemmArgs v;  // V^T[c][t] = sum_k Wv[c][k] * t[t][k] + bv[c]
-      v.A = L.sa_v_w; v.lda = C; v.a_bstride = 0;
+      v.A = Lw.sa_v_w; v.lda = C; v.a_bstride = 0;
       v.W = t; v.ldw = C; v.w_bstride = (long long)Nq * C;
       v.M = C; v.N = Nq; v.K = C; v.batch = B;
-      v.bias = L.sa_v_b; v.bias_mode = 2;
-      v.C = vt; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
+      v.bias = Lw.sa_v_b; v.bias_mode = 2;
+      v.C = vts; v.c_bf16 = 1; v.ldc = ldvs; v.c_bstride = (long long)C * ldvs;
       VLS_TRY(launch_gemm(v, st));
     }
-    VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, Nq, s_self));
+    VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, Nq, s_self));
     {
-      GemmArgs g = lin(ao, C, (long long)Nq * C, L.sa_o_w, Nq, C, C, B, L.sa_o_b, x, 0, C, (long long)Nq * C);
+      GemmArgs g = lin(ao, C, (long long)Nq * C, Lw.sa_o_w, Nq, C, C, B, Lw.sa_o_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
       VLS_TRY(launch_gemm(g, st));
     }
     // ---- cross attention to the memory bank (memory_attention.py:66-81)
-    VLS_TRY(launch_ln256(x, B, Nq, L.n2_w, L.n2_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    VLS_TRY(launch_ln256(x, B, Nq, Lw.n2_w, Lw.n2_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
-      GemmArgs g = lin(t, C, (long long)Nq * C, L.ca_q_w, Nq, C, C, B, L.ca_q_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
+      GemmArgs g = lin(t, C, (long long)Nq * C, Lw.ca_q_w, Nq, C, C, B, Lw.ca_q_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
       VLS_TRY(launch_gemm(g, st));
-      GemmArgs k = lin(mempos, CM, (long long)Nk * CM, L.ca_k_w, Nk, C, CM, B, L.ca_k_b, kc, 1, C, (long long)Nk * C);
-      k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
-      VLS_TRY(launch_gemm(k, st));
-      GemmArgs v;
-      v.A = L.ca_v_w; v.lda = CM; v.a_bstride = 0;
-      v.W = mem; v.ldw = CM; v.w_bstride = (long long)Nk * CM;
-      v.M = C; v.N = Nk; v.K = CM; v.batch = B;
-      v.bias = L.ca_v_b; v.bias_mode = 2;
-      v.C = vt; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
-      VLS_TRY(launch_gemm(v, st));
     }
-    VLS_TRY(attention(kc, C, (long long)Nk * C, Nk, s_cross));
+    VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, vt_all + (size_t)l * B * C * ldv * 2, ldv, Nk,
+                      s_cross));
     {
-      GemmArgs g = lin(ao, C, (long long)Nq * C, L.ca_o_w, Nq, C, C, B, L.ca_o_b, x, 0, C, (long long)Nq * C);
+      GemmArgs g = lin(ao, C, (long long)Nq * C, Lw.ca_o_w, Nq, C, C, B, Lw.ca_o_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
       VLS_TRY(launch_gemm(g, st));
     }
     // ---- FFN (memory_attention.py:95-98)
-    VLS_TRY(launch_ln256(x, B, Nq, L.n3_w, L.n3_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    VLS_TRY(launch_ln256(x, B, Nq, Lw.n3_w, Lw.n3_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
-      GemmArgs g = lin(t, C, (long long)Nq * C, L.l1_w, Nq, FFN, C, B, L.l1_b, h, 1, FFN, (long long)Nq * FFN);
+      GemmArgs g = lin(t, C, (long long)Nq * C, Lw.l1_w, Nq, FFN, C, B, Lw.l1_b, h, 1, FFN, (long long)Nq * FFN);
       g.act = 1;
       VLS_TRY(launch_gemm(g, st));
-      GemmArgs g2 = lin(h, FFN, (long long)Nq * FFN, L.l2_w, Nq, C, FFN, B, L.l2_b, x, 0, C, (long long)Nq * C);
+      GemmArgs g2 = lin(h, FFN, (long long)Nq * FFN, Lw.l2_w, Nq, C, FFN, B, Lw.l2_b, x, 0, C, (long long)Nq * C);
       g2.residual = x; g2.ld_res = C; g2.res_bstride = (long long)Nq * C;
       VLS_TRY(launch_gemm(g2, st));
     }
@@ -333,15 +351,17 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
 // ================================================================== post-decoder glue
 int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
                        const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
-                       int* best_idx, float* is_obj, void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+                       int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                       vls_stream_t stream_) {
   cudaStream_t st = (cudaStream_t)stream_;
-  VLS_REQUIRE(w && masks && iou && tokens && obj_logits && low_res_masks && obj_ptr && best_idx && is_obj,
+  VLS_REQUIRE(w && masks && iou && tokens && obj_logits && low_res_masks && obj_ptr && best_idx && is_obj && occluded,
               "sam_heads_post: null argument");
   VLS_REQUIRE(workspace && workspace_bytes >= (size_t)B * 256 * 3 * 4, "sam_heads_post: workspace too small");
   float* tok = (float*)workspace;
   float* h1 = tok + (size_t)B * 256;
   float* h2 = h1 + (size_t)B * 256;
-  VLS_TRY(launch_select_best(masks, iou, tokens, obj_logits, B, 4, multimask, HW, low_res_masks, tok, best_idx, is_obj, st));
+  VLS_TRY(launch_select_best(masks, iou, tokens, obj_logits, B, 4, multimask, HW, low_res_masks, tok, best_idx, is_obj,
+                             occluded, st));
   SmallLinArgs s;
   s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
   s.x = tok; s.x_sr = 256; s.W = w->w[0]; s.bias = w->b[0]; s.out = h1; s.o_sr = 256;

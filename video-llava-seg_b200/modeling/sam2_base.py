@@ -146,18 +146,25 @@ class SAM2Base(nn.Module):
 
     def _ptr_pos_rows(self, dist_key, num_frames):
         """Temporal encoding of pointers at the given signed frame distances -> [P*4, 64] f32
-        (sam2_base.py:628-643).  Cached per distance tuple (steady state reuses one entry)."""
+        (sam2_base.py:628-643).  Each distance's rows are a weight constant, computed once (sine PE + the
+        obj_ptr_tpos_proj linear through vls_linear_f32) and cached; the nearest-15 block repeats every frame."""
         c = self._constants()
-        key = (dist_key, num_frames)
-        if key not in c["ptr_pos"]:
-            if len(c["ptr_pos"]) > 512:
-                c["ptr_pos"].clear()
-            t_diff_max = min(num_frames, self.max_obj_ptrs_in_encoder) - 1
-            pos = torch.tensor(dist_key, device=c["device"], dtype=torch.float32) / t_diff_max
-            pe = get_1d_sine_pe(pos, dim=self.hidden_dim)
-            rows = ops.linear_f32(pe, c["tpos_w"], c["tpos_b"])                  # [P, 64]
-            c["ptr_pos"][key] = rows.repeat_interleave(self.hidden_dim // self.mem_dim, dim=0).contiguous()
-        return c["ptr_pos"][key]
+        t_diff_max = min(num_frames, self.max_obj_ptrs_in_encoder) - 1
+        table = c["ptr_pos"].setdefault(t_diff_max, {})
+        missing = [d for d in dist_key if d not in table]
+        if missing:
+            pos = torch.tensor(missing, device=c["device"], dtype=torch.float32) / t_diff_max
+            rows = ops.linear_f32(get_1d_sine_pe(pos, dim=self.hidden_dim), c["tpos_w"], c["tpos_b"])   # [n, 64]
+            rep = self.hidden_dim // self.mem_dim
+            for i, d in enumerate(missing):
+                table[d] = rows[i:i + 1].expand(rep, -1)
+        tail_key = ("tail", t_diff_max, dist_key[1:])
+        if tail_key not in c["ptr_pos"]:
+            if len(c["ptr_pos"]) > 256:
+                c["ptr_pos"] = {t_diff_max: table}
+            c["ptr_pos"][tail_key] = torch.cat([table[d] for d in dist_key[1:]], 0) if len(dist_key) > 1 else None
+        tail = c["ptr_pos"][tail_key]
+        return table[dist_key[0]] if tail is None else torch.cat([table[dist_key[0]], tail], 0)
 
     # ------------------------------------------------------------------ image features (out of the hot path)
     def forward_image(self, img_batch):
@@ -188,7 +195,7 @@ class SAM2Base(nn.Module):
         if point_inputs is not None:
             coords, labels = point_inputs["point_coords"], point_inputs["point_labels"]
             assert coords.size(0) == B and labels.size(0) == B
-        else:
+        elif mask_inputs is not None:
             coords = torch.zeros(B, 1, 2, device=dev)
             labels = -torch.ones(B, 1, dtype=torch.int32, device=dev)
         if mask_inputs is not None:
@@ -217,10 +224,11 @@ class SAM2Base(nn.Module):
         obj_ptr = torch.empty((B, self.hidden_dim), device=dev, dtype=torch.float32)
         best = torch.empty((B,), device=dev, dtype=torch.int32)
         is_obj = torch.empty((B,), device=dev, dtype=torch.float32)
+        occluded = torch.empty((B,), device=dev, dtype=torch.float32)
         ws = torch.empty((B * 256 * 3 * 4,), device=dev, dtype=torch.uint8)
         check(lib().vls_sam_heads_post(ctypes_ref(c["ptr_w"]), ptr(masks4), ptr(iou4), ptr(tok4), ptr(obj_logits), B,
                                        int(bool(multimask_output)), hw, ptr(low), ptr(obj_ptr), ptr(best), ptr(is_obj),
-                                       ptr(ws), ws.numel(), stream()), "vls_sam_heads_post")
+                                       ptr(occluded), ptr(ws), ws.numel(), stream()), "vls_sam_heads_post")
         if multimask_output:
             low_multi, ious = masks4[:, 1:], iou4[:, 1:]
         else:
@@ -231,7 +239,7 @@ class SAM2Base(nn.Module):
             high_multi = ops.resize_bilinear(gated, (self.image_size, self.image_size))
             high = ops.resize_bilinear(low, (self.image_size, self.image_size))
             low_multi = gated
-        self._last_is_obj = is_obj
+        self._last_gate = (obj_logits, occluded)
         return low_multi, high_multi, ious, low, high, obj_ptr, obj_logits
 
     def _use_mask_as_output(self, backbone_features, high_res_features, mask_inputs):
@@ -349,8 +357,12 @@ class SAM2Base(nn.Module):
         return feats, [pos]
 
     def _occluded_gate(self, object_score_logits):
+        """(1 - is_obj) per object for the occlusion embedding (sam2_base.py:716-722)."""
         if self.no_obj_embed_spatial is None:
             return None
+        last = getattr(self, "_last_gate", None)
+        if last is not None and last[0] is object_score_logits:
+            return last[1]            # produced by the heads-post kernel of this very frame
         return (object_score_logits.reshape(-1) <= 0).float().contiguous()
 
     def _encode_new_memory_low_res(self, current_vision_feats, low_res_masks, object_score_logits, is_mask_from_pts):
