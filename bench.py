@@ -40,13 +40,14 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons.  Started before the ramp (nvidia-smi needs ~100 ms to start) and
+    summarised over the samples whose wall-clock time falls inside the timed window [mark_start, mark_stop]."""
 
     def __init__(self, index):
-        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.samples, self.max_mhz, self.t0, self.t1 = [], None, None, None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)]
+        self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)]
         self.proc, self.thread = None, None
 
     def _read(self):
@@ -54,11 +55,10 @@ class ClockSampler:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             try:
-                self.samples.append(float(f[0]))
+                mhz = float(f[0])
                 self.max_mhz = float(f[1])
-                for n, v in zip(names, f[2:6]):
-                    if v.lower().startswith("active"):
-                        self.reasons.add(n)
+                active = [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]
+                self.samples.append((time.perf_counter(), mhz, active))
             except (ValueError, IndexError):
                 pass
 
@@ -71,14 +71,27 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def mark_start(self):
+        self.t0 = time.perf_counter()
+
+    def mark_stop(self):
+        self.t1 = time.perf_counter()
+
     def __exit__(self, *a):
         if self.proc is not None:
+            time.sleep(0.05)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
-        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons)}
+        t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
+        win = [s for s in self.samples if t0 - 0.02 <= s[0] <= t1 + 0.04]
+        scope = "timed window"
+        if not win:  # window shorter than the sampling period: fall back to the loaded ramp just before it
+            win, scope = [s for s in self.samples if s[0] <= t1 + 0.04][-10:], "ramp + timed window"
+        reasons = sorted({r for s in win for r in s[2]})
+        return {"sm_mhz": statistics.median([s[1] for s in win]) if win else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(win), "scope": scope}
 
 
 def make_clip(seed, num_frames):
@@ -116,21 +129,22 @@ def run_ours(args):
 
     def timed_pass(source, d2h):
         """Ramp + warm-up untimed, then K steps each bracketed by CUDA events, L2 flushed between steps."""
-        state = predictor.init_state(source)
-        predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
-        gen = predictor.propagate_in_video(state)
-        for _ in range(RAMP + W):
-            _, _, m = next(gen)
-            if d2h:
-                (m > 0).to(torch.uint8).cpu()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-        launches0 = lib.vls_launch_count()
-        out_bytes = 0
         with ClockSampler(local) as clocks:
+            state = predictor.init_state(source)
+            predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
+            gen = predictor.propagate_in_video(state)
+            for _ in range(RAMP + W):
+                _, _, m = next(gen)
+                if d2h:
+                    (m > 0).to(torch.uint8).cpu()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+            stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+            launches0 = lib.vls_launch_count()
+            out_bytes = 0
+            clocks.mark_start()
             for i in range(K):
                 flush.zero_()
                 starts[i].record()
@@ -140,6 +154,7 @@ def run_ours(args):
                     out_bytes = host.numel()
                 stops[i].record()
             torch.cuda.synchronize()
+            clocks.mark_stop()
         launches = lib.vls_launch_count() - launches0
         ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
         if world > 1:

@@ -22,14 +22,18 @@ constexpr int BK = 64;
 constexpr int THREADS = 192;
 constexpr int A_BYTES = BM * BK * 2;
 
-template <int BN>
+template <int BN, int STAGES_>
 struct Cfg {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES = BN == 64 ? 8 : 6;              // 192 KB of operand ring either way
+  static constexpr int STAGES = STAGES_;                        // = K blocks for short K, 8/6 for long K
   static constexpr int PITCH = BN + 4;                          // f32 staging pitch (16 B aligned, conflict-free)
-  static constexpr int SMEM = STAGES * STAGE_BYTES + 256 + 1024;
-  static_assert(BM * PITCH * 4 <= STAGES * STAGE_BYTES, "epilogue staging must fit in the operand ring");
+  static constexpr int RING = STAGES * STAGE_BYTES;
+  static constexpr int STAGING = BM * PITCH * 4;                // epilogue tile, aliases the idle operand ring
+  static constexpr int SMEM = (RING > STAGING ? RING : STAGING) + 256 + 1024;
+  // resident CTAs per SM (smem-limited, capped at 3): one CTA's epilogue overlaps the others' loads/MMAs
+  static constexpr int MINB = (232448 / SMEM) >= 3 ? 3 : ((232448 / SMEM) >= 2 ? 2 : 1);
+  static constexpr int G = MINB >= 3 ? 4 : 8;                   // rows whose global loads are batched per thread
 };
 
 struct Epi {
@@ -49,16 +53,16 @@ struct Epi {
   int a_div, a_mod, w_div, w_mod;   // operand batch index = (blockIdx.z / div) % mod
 };
 
-template <int BN>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int BN, int STAGES_>
+__global__ void __launch_bounds__(THREADS, Cfg<BN, STAGES_>::MINB)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Epi e) {
-  using C_ = Cfg<BN>;
+  using C_ = Cfg<BN, STAGES_>;
   constexpr int STAGES = C_::STAGES;
   constexpr int STAGE_BYTES = C_::STAGE_BYTES;
   constexpr int PITCH = C_::PITCH;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (C_::RING > C_::STAGING ? C_::RING : C_::STAGING));
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
@@ -152,41 +156,59 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4 bcol = make_float4(0.f, 0.f, 0.f, 0.f);
     if (e.bias_mode == 1 && col_ok) bcol = *reinterpret_cast<const float4*>(bias + col);
     const int pair0 = (col & 255) >> 1;
-#pragma unroll 2
-    for (int r0 = 0; r0 < BM; r0 += RPP) {
-      const int rl = r0 + et / CG;
-      const int row = m0 + rl;
-      if (row >= e.M || !col_ok) continue;
-      float4 v = *reinterpret_cast<const float4*>(stage + rl * PITCH + cg * 4);
-      if (e.bias_mode == 1) {
-        v.x += bcol.x; v.y += bcol.y; v.z += bcol.z; v.w += bcol.w;
-      } else if (e.bias_mode == 2) {
-        const float b = __ldg(bias + row);
-        v.x += b; v.y += b; v.z += b; v.w += b;
+    const bool rope = e.rope_cos != nullptr;
+    const float* res = e.residual ? e.residual + (long long)bz * e.res_bstride + col : nullptr;
+    constexpr int G = C_::G;  // rows per thread whose global loads are issued together (memory-level parallelism)
+#pragma unroll 1
+    for (int r0 = 0; r0 < BM; r0 += RPP * G) {
+      float4 v[G], rr[G];
+      float2 co[G], si[G];
+      float brow[G];
+      bool ok[G], rot[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int rl = r0 + g * RPP + et / CG;
+        const int row = m0 + rl;
+        ok[g] = col_ok && row < e.M;
+        rot[g] = rope && ok[g] && row < e.rope_rows;
+        v[g] = *reinterpret_cast<const float4*>(stage + rl * PITCH + cg * 4);
+        if (rot[g]) {
+          const long long t = (long long)(row % e.rope_period) * 128 + pair0;
+          co[g] = *reinterpret_cast<const float2*>(e.rope_cos + t);
+          si[g] = *reinterpret_cast<const float2*>(e.rope_sin + t);
+        }
+        if (res && ok[g]) rr[g] = *reinterpret_cast<const float4*>(res + (long long)row * e.ld_res);
+        brow[g] = (e.bias_mode == 2 && ok[g]) ? __ldg(bias + row) : 0.f;
       }
-      if (e.act == 1) {
-        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-      } else if (e.act == 2) {
-        v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        if (!ok[g]) continue;
+        const int row = m0 + r0 + g * RPP + et / CG;
+        float4 x = v[g];
+        if (e.bias_mode == 1) {
+          x.x += bcol.x; x.y += bcol.y; x.z += bcol.z; x.w += bcol.w;
+        } else if (e.bias_mode == 2) {
+          x.x += brow[g]; x.y += brow[g]; x.z += brow[g]; x.w += brow[g];
+        }
+        if (e.act == 1) {
+          x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+        } else if (e.act == 2) {
+          x.x = gelu_erf(x.x); x.y = gelu_erf(x.y); x.z = gelu_erf(x.z); x.w = gelu_erf(x.w);
+        }
+        if (rot[g]) {
+          const float a0 = x.x, b0 = x.y, a1 = x.z, b1 = x.w;
+          x.x = a0 * co[g].x - b0 * si[g].x; x.y = a0 * si[g].x + b0 * co[g].x;
+          x.z = a1 * co[g].y - b1 * si[g].y; x.w = a1 * si[g].y + b1 * co[g].y;
+        }
+        if (res) {
+          x.x += rr[g].x; x.y += rr[g].y; x.z += rr[g].z; x.w += rr[g].w;
+        }
+        const long long off = (long long)bz * e.c_bstride + (long long)row * e.ldc + col;
+        if (e.c_bf16)
+          *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + off) = make_uint2(pack_bf16x2(x.x, x.y), pack_bf16x2(x.z, x.w));
+        else
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + off) = x;
       }
-      if (e.rope_cos != nullptr && row < e.rope_rows) {
-        const long long t = (long long)(row % e.rope_period) * 128 + pair0;
-        const float2 co = *reinterpret_cast<const float2*>(e.rope_cos + t);
-        const float2 si = *reinterpret_cast<const float2*>(e.rope_sin + t);
-        const float a0 = v.x, b0 = v.y, a1 = v.z, b1 = v.w;
-        v.x = a0 * co.x - b0 * si.x; v.y = a0 * si.x + b0 * co.x;
-        v.z = a1 * co.y - b1 * si.y; v.w = a1 * si.y + b1 * co.y;
-      }
-      if (e.residual) {
-        const float4 rr = *reinterpret_cast<const float4*>(e.residual + (long long)bz * e.res_bstride +
-                                                           (long long)row * e.ld_res + col);
-        v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-      }
-      const long long off = (long long)bz * e.c_bstride + (long long)row * e.ldc + col;
-      if (e.c_bf16)
-        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(e.C) + off) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-      else
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.C) + off) = v;
     }
   }
   tc_fence_before();
@@ -194,8 +216,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) tmem_dealloc(tmem, BN);
 }
 
-template <int BN>
-int launch_bn(const GemmArgs& a, cudaStream_t stream) {
+template <int BN, int STAGES_>
+int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
+  using C_ = Cfg<BN, STAGES_>;
   CUtensorMap tmA, tmB;
   VLS_TRY(make_tmap_bf16(&tmA, a.A, a.K, a.M, a.a_batches, a.lda, a.a_bstride, BM));
   VLS_TRY(make_tmap_bf16(&tmB, a.W, a.K, a.N, a.w_batches, a.ldw, a.w_bstride, BN));
@@ -210,13 +233,26 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   e.a_div = a.a_div; e.a_mod = a.a_batches; e.w_div = a.w_div; e.w_mod = a.w_batches;
   static bool attr_set = false;
   if (!attr_set) {
-    VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::SMEM));
+    VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
     attr_set = true;
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
-  gemm_tn_kernel<BN><<<grid, THREADS, Cfg<BN>::SMEM, stream>>>(tmA, tmB, e);
+  gemm_tn_kernel<BN, STAGES_><<<grid, THREADS, C_::SMEM, stream>>>(tmA, tmB, e);
   VLS_POST_LAUNCH(1);
   return 0;
+}
+
+template <int BN>
+int launch_bn(const GemmArgs& a, cudaStream_t stream) {
+  // short K: ring = exactly the K blocks (1/2/4 stages) so 2-3 CTAs stay resident per SM and one CTA's epilogue
+  // overlaps the others' main loops; long K: 192 KB of loads in flight to cover the L2->smem latency
+  const int kblocks = (a.K + BK - 1) / BK;
+  const long long ctas = (long long)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * a.batch;
+  if (kblocks <= 1) return launch_cfg<BN, 1>(a, stream);
+  // multi-wave grids with short K are epilogue-bound: a 2-stage ring keeps 3 CTAs resident per SM
+  if (kblocks <= 2 || (kblocks <= 4 && ctas > 2 * 148)) return launch_cfg<BN, 2>(a, stream);
+  if (kblocks <= 4) return launch_cfg<BN, 4>(a, stream);
+  return launch_cfg<BN, BN == 64 ? 8 : 6>(a, stream);
 }
 
 }  // namespace
