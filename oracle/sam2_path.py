@@ -347,12 +347,17 @@ class Cfg:
 def forward_sam_heads(sd, cfg, pix_feat, high_res, point_inputs, multimask_output):
     """SAM2Base._forward_sam_heads (sam2_base.py:257-413), mask_inputs=None path."""
     bsz = pix_feat.size(0)
-    if point_inputs is not None:
-        coords, labels = point_inputs["point_coords"], point_inputs["point_labels"]
+    if point_inputs is not None and "prompt_embedding" in point_inputs:
+        # [SEG]-token prompt (SURVEY.md section 8 f-1): what the reference predictor computes when
+        # sam_prompt_encoder.forward is patched to return this sparse embedding (+ the no-mask dense embedding)
+        sparse = point_inputs["prompt_embedding"]
     else:
-        coords = torch.zeros(bsz, 1, 2)
-        labels = -torch.ones(bsz, 1, dtype=torch.int32)
-    sparse = prompt_points(sd, coords, labels, cfg.image_size)
+        if point_inputs is not None:
+            coords, labels = point_inputs["point_coords"], point_inputs["point_labels"]
+        else:
+            coords = torch.zeros(bsz, 1, 2)
+            labels = -torch.ones(bsz, 1, dtype=torch.int32)
+        sparse = prompt_points(sd, coords, labels, cfg.image_size)
     dense = dense_no_mask(sd, bsz, cfg.feat)
     low, ious, tokens, obj_logits = mask_decoder(sd, pix_feat, dense_pe(sd, cfg.feat), sparse, dense,
                                                  multimask_output, False, high_res)
@@ -446,8 +451,11 @@ def track_step(sd, cfg, frame_idx, is_init_cond_frame, feats, point_inputs, outp
         mem, mem_pos, n_ptr = memory_bank(sd, cfg, frame_idx, output_dict, num_frames)
         pix = memory_attention(sd, vf, mem, vp, mem_pos, n_ptr)
         pix = pix.permute(1, 2, 0).reshape(bsz, cfg.hidden, cfg.feat, cfg.feat)
-    num_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
-    multimask = 0 <= num_pts <= 1  # _use_multimask (sam2_base.py:879-887) with YAML :109-113
+    if point_inputs is not None and "prompt_embedding" in point_inputs:
+        multimask = False  # single-mask decode, as the LLaVA head does (llava/model/seg_head/sam2.py:111)
+    else:
+        num_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
+        multimask = 0 <= num_pts <= 1  # _use_multimask (sam2_base.py:879-887) with YAML :109-113
     out = forward_sam_heads(sd, cfg, pix, [feats["feat_s0"], feats["feat_s1"]], point_inputs, multimask)
     cur = dict(pred_masks=out["low_res_masks"], pred_masks_high_res=out["high_res_masks"],
                obj_ptr=out["obj_ptr"], object_score_logits=out["object_score_logits"], ious=out["ious"],

@@ -117,3 +117,64 @@ def test_api_errors(predictor):
     predictor.add_new_points_or_box(state, 2, 7, box=[200.0, 400.0, 420.0, 620.0])
     rev = [f for f, _, _ in predictor.propagate_in_video(state, reverse=True)]
     assert rev == [2, 1, 0]
+
+
+def test_seg_embedding_prompt_then_propagation(predictor):
+    """BASELINE config 4 / SURVEY f-1: a [SEG]-style sparse prompt embedding on frame 0, then propagation.
+    Checked live against the oracle with the same embedding (3 frames)."""
+    from oracle import cc as cc_oracle
+    from oracle import sam2_path as O
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    sd = synth.init_state_dict(0)
+    T = 3
+    clip = synth.SyntheticClip(9, T)
+    emb = torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(21))
+    state = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+    fi, ids, m = predictor.add_new_prompt_embedding(state, 0, 5, emb[0])
+    assert fi == 0 and ids == [5] and m.shape == (1, 1, 1024, 1024)
+    got = {}
+    for fi, ids, _ in predictor.propagate_in_video(state):
+        key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
+        got[fi] = state["output_dict"][key][fi]["pred_masks"].float().cpu()
+    with torch.inference_mode():
+        ref = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, 1), {"prompt_embedding": emb}, T, cc=cc_oracle.cc_label)
+    for t in range(T):
+        a, b = got[t] > 0, ref[t]["pred_masks"] > 0
+        iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
+        d = (got[t] - ref[t]["pred_masks"]).abs()
+        one_sided = (got[t] == 0.1) ^ (ref[t]["pred_masks"] == 0.1)
+        print(f"seg-embedding t={t}: IoU {iou:.5f} max logit err (non-fill) {d[~one_sided].max():.3e}")
+        assert iou >= 0.995 and d[~one_sided].max() < 1e-2
+    with pytest.raises(ValueError):
+        predictor.add_new_prompt_embedding(state, 0, 5, torch.zeros(3))
+
+
+def test_llava_seg_head_per_frame_decode(predictor):
+    """SegmentationHeadSAM2 flavour (llava/model/seg_head/sam2.py:49-131): per-frame decode of N objects x Q queries
+    with repeat_image=True, max over queries -- against the oracle decoder."""
+    from oracle import sam2_path as O
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.llava_seg_head import SegmentationHeadSAM2
+
+    sd = synth.init_state_dict(0)
+    g = torch.Generator().manual_seed(31)
+    head = SegmentationHeadSAM2(n_token_dims=512, n_seg_queries=2, sam2_model=predictor).to("cuda:0")
+    with torch.no_grad():
+        head.proj_token.weight.copy_(torch.randn(512, 512, generator=g) * 0.05)
+        head.proj_token.bias.copy_(torch.randn(512, generator=g) * 0.05)
+    head._w = None
+    T, M = 2, 3
+    feats = torch.randn(T, 256, 64, 64, generator=g) * 0.5
+    s0, s1 = torch.randn(T, 32, 256, 256, generator=g) * 0.3, torch.randn(T, 64, 128, 128, generator=g) * 0.3
+    tok = torch.randn(M, 512, generator=g)
+    got = head.decode(feats.cuda(), (s0.cuda(), s1.cuda()), tok.cuda()).cpu()
+    assert got.shape == (M, T, 256, 256)
+    w, b = head.proj_token.weight.detach().cpu().to(torch.bfloat16).float(), head.proj_token.bias.detach().cpu()
+    sparse = (tok @ w.t() + b).reshape(M * 2, 1, 256)
+    for t in range(T):
+        ref = O.mask_decoder(sd, feats[t:t + 1] + sd["no_mem_embed"].reshape(1, 256, 1, 1), O.dense_pe(sd), sparse,
+                             O.dense_no_mask(sd, M * 2), False, True, [s0[t:t + 1], s1[t:t + 1]])[0]
+        ref = ref.reshape(M, 2, 256, 256).max(1).values
+        assert (got[:, t] - ref).abs().max() < 1e-2

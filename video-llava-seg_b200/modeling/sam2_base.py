@@ -192,7 +192,9 @@ class SAM2Base(nn.Module):
         B = backbone_features.size(0)
         dev = backbone_features.device
         require_cuda(backbone_features)
-        if point_inputs is not None:
+        if point_inputs is not None and "prompt_embedding" in point_inputs:
+            assert point_inputs["prompt_embedding"].size(0) == B
+        elif point_inputs is not None:
             coords, labels = point_inputs["point_coords"], point_inputs["point_labels"]
             assert coords.size(0) == B and labels.size(0) == B
         elif mask_inputs is not None:
@@ -207,7 +209,12 @@ class SAM2Base(nn.Module):
                 mask_prompt = mask_inputs
         else:
             mask_prompt = None
-        if point_inputs is None and mask_prompt is None:
+        if point_inputs is not None and "prompt_embedding" in point_inputs:
+            # [SEG]-token prompt: the projected LLM hidden state is the sparse prompt (llava sam2.py:75-88)
+            pe = self.sam_prompt_encoder
+            sparse = point_inputs["prompt_embedding"].to(dev).float()
+            dense = pe.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(B, -1, *pe.image_embedding_size)
+        elif point_inputs is None and mask_prompt is None:
             # no prompt on propagated frames: two `not_a_point` tokens + `no_mask` dense embedding are
             # weight constants (prompt_encoder.py:87-96,178-180) -- skip the per-frame prompt-encoder ops
             pe = self.sam_prompt_encoder
@@ -421,6 +428,8 @@ class SAM2Base(nn.Module):
 
     def _use_multimask(self, is_init_cond_frame, point_inputs):
         """sam2_base.py:879-887."""
+        if point_inputs is not None and "prompt_embedding" in point_inputs:
+            return False  # embedding prompts decode a single mask, like the LLaVA seg head (llava sam2.py:111)
         num_pts = 0 if point_inputs is None else point_inputs["point_labels"].size(1)
         return (self.multimask_output_in_sam and (is_init_cond_frame or self.multimask_output_for_tracking)
                 and (self.multimask_min_pt_num <= num_pts <= self.multimask_max_pt_num))

@@ -97,7 +97,7 @@ class SAM2VideoPredictor(SAM2Base):
         is_cond = is_init or self.add_all_frames_to_correct_as_cond
         key = "cond_frame_outputs" if is_cond else "non_cond_frame_outputs"
         prev_logits = None
-        if point_inputs is not None:
+        if point_inputs is not None and "prompt_embedding" not in point_inputs:
             prev = obj_tmp[key].get(frame_idx) or obj_out["cond_frame_outputs"].get(frame_idx) \
                 or obj_out["non_cond_frame_outputs"].get(frame_idx)
             if prev is not None and prev["pred_masks"] is not None:
@@ -145,6 +145,24 @@ class SAM2VideoPredictor(SAM2Base):
         per_frame = st["point_inputs_per_obj"][obj_idx]
         point_inputs = _concat_points(None if clear_old_points else per_frame.get(frame_idx, None), points, labels)
         per_frame[frame_idx] = point_inputs
+        st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
+        return self._prompt_frame(st, frame_idx, obj_idx, point_inputs, None)
+
+    @torch.inference_mode()
+    def add_new_prompt_embedding(self, inference_state, frame_idx, obj_id, sparse_embedding):
+        """Prompt an object with a sparse prompt EMBEDDING instead of clicks: `sparse_embedding` [Ns,256] or
+        [1,Ns,256], e.g. the projected `[SEG]` hidden state of the LLM (llava/model/seg_head/sam2.py:75-88).  The
+        frame becomes a conditioning frame exactly as with add_new_points_or_box; propagate_in_video then tracks
+        the object (BASELINE config 4: "[SEG] prompt -> decoder + propagation")."""
+        st = inference_state
+        obj_idx = self._obj_id_to_idx(st, obj_id)
+        e = torch.as_tensor(sparse_embedding, dtype=torch.float32)
+        if e.dim() == 2:
+            e = e.unsqueeze(0)
+        if e.dim() != 3 or e.shape[0] != 1 or e.shape[2] != self.hidden_dim:
+            raise ValueError(f"sparse_embedding must be [Ns,{self.hidden_dim}] or [1,Ns,{self.hidden_dim}]")
+        point_inputs = {"prompt_embedding": e.to(st["device"])}
+        st["point_inputs_per_obj"][obj_idx][frame_idx] = point_inputs
         st["mask_inputs_per_obj"][obj_idx].pop(frame_idx, None)
         return self._prompt_frame(st, frame_idx, obj_idx, point_inputs, None)
 
