@@ -93,6 +93,14 @@ int vls_linear_f32(const float* x, long long ldx, const void* w_bf16, const floa
 int vls_axpy_rows(const void* a, int a_dtype, long long a_st, long long a_sb, const void* p, int p_dtype, long long p_st,
                   long long p_sb, float alpha, int B, int T, int C, void* out, int out_dtype, vls_stream_t stream);
 
+/* CXBlock front half (memory_encoder.py:103-105): depth-wise 7x7 conv (pad 3) + LayerNorm2d over 256 channels.
+ * x f32 NHWC [B][H*W][256], dw_w f32 [49][256], out bf16 [B][H*W][256].  Exported for parity / roofline tests. */
+int vls_dwconv7_ln(const float* x, int B, int H, int W, const float* dw_w, const float* dw_b, const float* ln_w,
+                   const float* ln_b, float eps, void* out_bf16, vls_stream_t stream);
+/* LayerNorm over 256 channels of f32 rows -> bf16 rows (optional GELU). */
+int vls_layernorm256(const float* x, long long rows, const float* w, const float* b, float eps, int gelu, void* out_bf16,
+                     vls_stream_t stream);
+
 /* ---- module-level entry points ---------------------------------------------------------------
  * dtype codes for activations handed over by the host: */
 

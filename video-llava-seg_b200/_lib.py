@@ -62,6 +62,11 @@ def _declare(lib):
 def _declare_modules(lib):
     lib.vls_resize_bilinear.restype = c_int
     lib.vls_resize_bilinear.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
+    lib.vls_dwconv7_ln.restype = c_int
+    lib.vls_dwconv7_ln.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                   c_void_p]
+    lib.vls_layernorm256.restype = c_int
+    lib.vls_layernorm256.argtypes = [c_void_p, c_ll, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p]
     lib.vls_axpy_rows.restype = c_int
     lib.vls_axpy_rows.argtypes = [c_void_p, c_int, c_ll, c_ll, c_void_p, c_int, c_ll, c_ll, c_float, c_int, c_int, c_int,
                                   c_void_p, c_int, c_void_p]

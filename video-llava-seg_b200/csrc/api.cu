@@ -88,4 +88,16 @@ int vls_axpy_rows(const void* a, int a_dtype, long long a_st, long long a_sb, co
                           (cudaStream_t)stream);
 }
 
+int vls_dwconv7_ln(const float* x, int B, int H, int W, const float* dw_w, const float* dw_b, const float* ln_w,
+                   const float* ln_b, float eps, void* out_bf16, vls_stream_t stream) {
+  VLS_REQUIRE(x && dw_w && dw_b && ln_w && ln_b && out_bf16, "dwconv7_ln: null pointer");
+  return launch_dwconv7_ln(x, B, H, W, dw_w, dw_b, ln_w, ln_b, eps, out_bf16, (cudaStream_t)stream);
+}
+
+int vls_layernorm256(const float* x, long long rows, const float* w, const float* b, float eps, int gelu, void* out_bf16,
+                     vls_stream_t stream) {
+  VLS_REQUIRE(x && w && b && out_bf16 && rows >= 0 && rows < (1ll << 31), "layernorm256: bad arguments");
+  return launch_ln256(x, 1, (int)rows, w, b, eps, gelu, nullptr, 0, 0, out_bf16, 0, 256, (cudaStream_t)stream);
+}
+
 }  // extern "C"

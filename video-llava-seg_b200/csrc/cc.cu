@@ -16,8 +16,8 @@
 //   D. path compression + area: __match_any_sync / __reduce_add_sync aggregate lanes sharing a
 //      root so a large component costs one smem atomic per warp-row, not one per block
 //   E. 128-bit stores of labels and areas (or, for hole filling, sparse in-place stores of 0.1)
-// Generic path (any even H, W): same union-find in global memory (labels array is the forest, as in
-// the reference), batched over N, four launches.
+// Larger images: 64 x 128 pixel tiles labelled in shared memory the same way, tile-border unions in global
+// memory (the labels array is the forest, as in the reference), batched over N, four launches.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -213,62 +213,112 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   }
 }
 
-// ------------------------------------------------------------------ generic (global memory) path
-// The forest lives in labels[] at each block's top-left pixel (as in the reference); area
-// accumulators live in a zeroed workspace indexed by the same pixel index.
-template <bool FILL>
-__global__ void cc_g_init(const void* img_all, int H, int W, int32_t* forest_all, const float* scores_all) {
-  const int BW = W >> 1, BH = H >> 1;
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
-  if (bx >= BW || by >= BH) return;
-  const size_t off = (size_t)blockIdx.z * H * W;
-  const int idx = 2 * by * W + 2 * bx;
-  forest_all[off + idx] = idx;
-}
+// ------------------------------------------------------------------ tiled path (images larger than 256 x 256)
+// Tile = 64 x 128 pixels = 32 x 64 blocks, labelled entirely in shared memory with the same warp-level
+// run merge as the small path; only tile-border blocks take part in global atomicMin unions.
+//   cc_t_label   : occupancy (also cached as 1 byte / block for the later passes), local union-find,
+//                  forest[block's top-left pixel] = GLOBAL pixel index of the local root
+//   cc_t_border  : unions across tile borders (top row: up / up-left / up-right; left column: left / up-left;
+//                  right column: up-right)
+//   cc_t_count   : global find + path compression, area[root] += popcount (warp-aggregated atomics)
+//   cc_t_final   : 8-byte stores of labels / areas (or sparse in-place fill of small holes)
+constexpr int TBH = 32, TBW = 64, T_THREADS = 256;
 
 template <bool FILL>
-__device__ __forceinline__ uint32_t occ_g(const void* img_all, const float* scores_all, size_t off, int H, int W, int by,
-                                          int bx) {
+__global__ void __launch_bounds__(T_THREADS)
+cc_t_label(const void* img_all, const float* scores_all, int H, int W, int32_t* forest_all, uint8_t* occ_all) {
+  __shared__ int lab[TBH * TBW];
+  __shared__ uint8_t occ[TBH * TBW];
+  const int BH = H >> 1, BW = W >> 1;
+  const size_t off = (size_t)blockIdx.z * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + off);
-  return load_occ<FILL>(img, H, W, by, bx, 0.f);
+  const int by0 = blockIdx.y * TBH, bx0 = blockIdx.x * TBW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = T_THREADS / 32;
+  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
+    const int by = by0 + i / TBW, bx = bx0 + i % TBW;
+    const uint32_t o = (by < BH && bx < BW) ? load_occ<FILL>(img, H, W, by, bx, 0.f) : 0u;
+    occ[i] = (uint8_t)o;
+    if (by < BH && bx < BW) occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx] = (uint8_t)o;
+  }
+  __syncthreads();
+  constexpr int CH = TBW / 32;
+  for (int t = warp; t < TBH * CH; t += nwarps) {
+    const int ly = t / CH, c0 = (t % CH) << 5, lx = c0 + lane, li = ly * TBW + lx;
+    const uint32_t me = occ[li], left = lx > 0 ? occ[li - 1] : 0u;
+    const uint32_t hm = __ballot_sync(0xffffffffu, conn_left(me, left));
+    const uint32_t stops = (~hm | 1u) & (0xffffffffu >> (31 - lane));
+    lab[li] = ly * TBW + c0 + (31 - __clz(stops));
+  }
+  __syncthreads();
+  for (int t = warp; t < TBH * CH; t += nwarps) {
+    const int ly = t / CH, c0 = (t % CH) << 5, lx = c0 + lane, li = ly * TBW + lx;
+    const uint32_t me = occ[li], left = lx > 0 ? occ[li - 1] : 0u;
+    const bool h = conn_left(me, left);
+    uint32_t up = 0, ul = 0, ur = 0;
+    if (ly > 0) {
+      up = occ[li - TBW];
+      if (lx > 0) ul = occ[li - TBW - 1];
+      if (lx + 1 < TBW) ur = occ[li - TBW + 1];
+    }
+    const bool cu = conn_up(me, up);
+    const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
+    const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
+    const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
+    const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
+    if (lane == 0 && h) uf_union(lab, li, li - 1);
+    if (cu && !cu_redundant) uf_union(lab, li, li - TBW);
+    if (cul) uf_union(lab, li, li - TBW - 1);
+    if (cur) uf_union(lab, li, li - TBW + 1);
+  }
+  __syncthreads();
+  int32_t* forest = forest_all + off;
+  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
+    const int by = by0 + i / TBW, bx = bx0 + i % TBW;
+    if (by >= BH || bx >= BW) continue;
+    const int r = occ[i] ? uf_find(lab, i) : i;
+    forest[(2 * by) * W + 2 * bx] = (2 * (by0 + r / TBW)) * W + 2 * (bx0 + r % TBW);
+  }
 }
 
-template <bool FILL>
-__global__ void cc_g_merge(const void* img_all, int H, int W, int32_t* forest_all, const float* scores_all) {
-  const int BW = W >> 1, BH = H >> 1;
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
-  if (bx >= BW || by >= BH) return;
-  const size_t off = (size_t)blockIdx.z * H * W;
-  int32_t* forest = forest_all + off;
-  const uint32_t me = occ_g<FILL>(img_all, scores_all, off, H, W, by, bx);
+__global__ void cc_t_border(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all) {
+  const int BH = H >> 1, BW = W >> 1;
+  const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
+  const int per_tile = TBW + 2 * TBH;  // top row, left column, right column
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)tiles_x * tiles_y * per_tile) return;
+  const int tile = (int)(id / per_tile), k = (int)(id % per_tile);
+  const int ty = tile / tiles_x, tx = tile % tiles_x;
+  int ly, lx, kind;  // kind 0: top row, 1: left column, 2: right column
+  if (k < TBW) { ly = 0; lx = k; kind = 0; }
+  else if (k < TBW + TBH) { ly = k - TBW; lx = 0; kind = 1; }
+  else { ly = k - TBW - TBH; lx = TBW - 1; kind = 2; }
+  const int by = ty * TBH + ly, bx = tx * TBW + lx;
+  if (by >= BH || bx >= BW) return;
+  const uint8_t* occ = occ_all + (size_t)blockIdx.z * BH * BW;
+  int32_t* forest = forest_all + (size_t)blockIdx.z * H * W;
+  const uint32_t me = occ[(size_t)by * BW + bx];
   if (!me) return;
   const int idx = 2 * by * W + 2 * bx;
-  const uint32_t left = bx > 0 ? occ_g<FILL>(img_all, scores_all, off, H, W, by, bx - 1) : 0u;
-  uint32_t up = 0, ul = 0, ur = 0;
-  if (by > 0) {
-    up = occ_g<FILL>(img_all, scores_all, off, H, W, by - 1, bx);
-    if (bx > 0) ul = occ_g<FILL>(img_all, scores_all, off, H, W, by - 1, bx - 1);
-    if (bx + 1 < BW) ur = occ_g<FILL>(img_all, scores_all, off, H, W, by - 1, bx + 1);
+  auto at = [&](int y, int x) -> uint32_t { return (y >= 0 && x >= 0 && x < BW) ? occ[(size_t)y * BW + x] : 0u; };
+  if (kind == 0 && by > 0) {
+    if (conn_up(me, at(by - 1, bx))) uf_union(forest, idx, idx - 2 * W);
+    if (conn_upleft(me, at(by - 1, bx - 1))) uf_union(forest, idx, idx - 2 * W - 2);
+    if (conn_upright(me, at(by - 1, bx + 1))) uf_union(forest, idx, idx - 2 * W + 2);
+  } else if (kind == 1 && bx > 0) {
+    if (conn_left(me, at(by, bx - 1))) uf_union(forest, idx, idx - 2);
+    if (ly > 0 && conn_upleft(me, at(by - 1, bx - 1))) uf_union(forest, idx, idx - 2 * W - 2);
+  } else if (kind == 2 && ly > 0) {
+    if (conn_upright(me, at(by - 1, bx + 1))) uf_union(forest, idx, idx - 2 * W + 2);
   }
-  const bool cu = conn_up(me, up);
-  if (conn_left(me, left)) uf_union(forest, idx, idx - 2);
-  if (cu) uf_union(forest, idx, idx - 2 * W);
-  if (conn_upleft(me, ul) && !(cu && conn_left(up, ul))) uf_union(forest, idx, idx - 2 * W - 2);
-  if (conn_upright(me, ur) && !(cu && conn_left(ur, up))) uf_union(forest, idx, idx - 2 * W + 2);
 }
 
-template <bool FILL>
-__global__ void cc_g_compress_count(const void* img_all, int H, int W, int32_t* forest_all, int32_t* area_all,
-                                    const float* scores_all) {
+__global__ void cc_t_count(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all, int32_t* area_all) {
   const int BW = W >> 1, BH = H >> 1;
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   const bool in = bx < BW && by < BH;
   const size_t off = (size_t)blockIdx.z * H * W;
-  const uint32_t me = in ? occ_g<FILL>(img_all, scores_all, off, H, W, by, bx) : 0u;
+  const uint32_t me = in ? occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx] : 0u;
   int root = -1 - (int)(threadIdx.x & 31);
   if (me) {
     const int idx = 2 * by * W + 2 * bx;
@@ -281,14 +331,14 @@ __global__ void cc_g_compress_count(const void* img_all, int H, int W, int32_t* 
 }
 
 template <bool FILL>
-__global__ void cc_g_final(const void* img_all, int H, int W, int32_t* labels_all, const int32_t* area_all,
-                           int32_t* counts_all, float* scores_all, int max_area, float fill_value) {
+__global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* labels_all,
+                           const int32_t* __restrict__ area_all, int32_t* counts_all, float* scores_all, int max_area,
+                           float fill_value) {
   const int BW = W >> 1, BH = H >> 1;
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x;
-  const int by = blockIdx.y;
+  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= BW || by >= BH) return;
   const size_t off = (size_t)blockIdx.z * H * W;
-  const uint32_t me = occ_g<FILL>(img_all, scores_all, off, H, W, by, bx);
+  const uint32_t me = occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx];
   const int idx = 2 * by * W + 2 * bx;
   int root = 0, n = 0;
   if (me) {
@@ -340,17 +390,21 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     return 0;
   }
   const size_t px = (size_t)n * h * w;
-  const size_t need = FILL ? 2 * px * 4 : px * 4;
+  const size_t blocks = px / 4;
+  const size_t need = (FILL ? 2 * px * 4 : px * 4) + blocks;
   VLS_REQUIRE(ws != nullptr && ws_bytes >= need, "cc: workspace too small (%zu < %zu)", ws_bytes, need);
   int32_t* area = reinterpret_cast<int32_t*>(ws);
   int32_t* forest = FILL ? area + px : labels;
+  uint8_t* occ = reinterpret_cast<uint8_t*>(area + (FILL ? 2 * px : px));
   VLS_CUDA(cudaMemsetAsync(area, 0, px * 4, stream));
-  dim3 blk(128, 1, 1);
-  dim3 grd((w / 2 + 127) / 128, h / 2, n);
-  cc_g_init<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, scores);
-  cc_g_merge<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, scores);
-  cc_g_compress_count<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, area, scores);
-  cc_g_final<FILL><<<grd, blk, 0, stream>>>(img, h, w, forest, area, counts, scores, max_area, fill_value);
+  const int BH = h / 2, BW = w / 2;
+  const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
+  cc_t_label<FILL><<<dim3(tiles_x, tiles_y, n), T_THREADS, 0, stream>>>(img, scores, h, w, forest, occ);
+  const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
+  cc_t_border<<<dim3((unsigned)((border + 255) / 256), 1, n), 256, 0, stream>>>(occ, h, w, forest);
+  dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, n);
+  cc_t_count<<<grd, blk, 0, stream>>>(occ, h, w, forest, area);
+  cc_t_final<FILL><<<grd, blk, 0, stream>>>(occ, h, w, forest, area, counts, scores, max_area, fill_value);
   VLS_POST_LAUNCH(4);
   return 0;
 }
@@ -359,7 +413,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
 
 size_t cc_workspace_bytes(int n, int h, int w, bool fill) {
   if (n <= 0 || h <= 0 || w <= 0 || small_ok(h, w)) return 0;
-  return (size_t)n * h * w * 4 * (fill ? 2 : 1);
+  return (size_t)n * h * w * 4 * (fill ? 2 : 1) + (size_t)n * h * w / 4;
 }
 
 int launch_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* ws,
