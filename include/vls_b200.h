@@ -35,6 +35,12 @@ const char* vls_last_error(void);
 int vls_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 long long vls_launch_count(void);
+/* Performance knobs (results are identical for every setting).  "attn_cluster": 1 = each CTA of the attention
+ * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each. */
+int vls_set_tuning(const char* key, int value);
+/* Developer aid: when non-NULL, CTA (0,0,0) of every attention launch writes clock64() stamps of its producer /
+ * MMA / softmax roles for the first 64 key tiles into this device buffer of 3*64*8 int64 (tools/trace_attention.py). */
+void vls_attention_trace(long long* device_buffer);
 /* Optional live kernel timing: when enabled, the attention launcher brackets its kernel with CUDA events
  * on the launching stream; vls_prof_collect(slot) synchronises them and returns count / total ms and clears
  * the slot.  slot 0 = memory cross-attention launches (Nk > Nq), slot 1 = self-attention launches. */

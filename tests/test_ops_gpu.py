@@ -162,3 +162,27 @@ def test_cc_matches_reference_kernel(dev):
         assert torch.equal(ours_l, rl) and torch.equal(ours_c, rc)
         ol, oc = cc_oracle.cc_label(m)
         assert torch.equal(ol, rl.cpu()) and torch.equal(oc, rc.cpu())
+
+
+@pytest.mark.parametrize("Nq,Nk,cluster", [(4096, 28736, 1), (4096, 4096, 1), (4096, 28736, 2)])
+def test_attention_is_bitwise_deterministic(dev, vls_lib, Nq, Nk, cluster):
+    """Race detector for the TMEM / mbarrier pipeline: same inputs and KV splits must give bit-identical outputs
+    run after run, also with a cold L2 and other kernels interleaved (this caught a P/S aliasing hazard in r1)."""
+    from video_llava_seg_b200 import ops
+
+    vls_lib.vls_set_tuning(b"attn_cluster", cluster)
+    try:
+        q = _rand((1, Nq, 256), dev, 41).bfloat16()
+        k = _rand((1, Nk, 256), dev, 42).bfloat16()
+        vt = _rand((1, 256, Nk), dev, 43).bfloat16()
+        flush = torch.empty(300 << 20, dtype=torch.uint8, device=dev)
+        base = ops.attention_d256(q, k, vt).clone()
+        for it in range(120):
+            if it % 3 == 0:
+                flush.zero_()
+            if it % 7 == 0:
+                (q.float() @ k.float().transpose(1, 2)).sum()
+            out = ops.attention_d256(q, k, vt)
+            assert torch.equal(out, base), f"run {it} differs from run 0"
+    finally:
+        vls_lib.vls_set_tuning(b"attn_cluster", 1)

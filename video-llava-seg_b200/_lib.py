@@ -38,6 +38,10 @@ def _declare(lib):
     lib.vls_last_error.restype = ctypes.c_char_p
     lib.vls_abi_version.restype = c_int
     lib.vls_launch_count.restype = c_ll
+    lib.vls_attention_trace.restype = None
+    lib.vls_attention_trace.argtypes = [c_void_p]
+    lib.vls_set_tuning.restype = c_int
+    lib.vls_set_tuning.argtypes = [ctypes.c_char_p, c_int]
     lib.vls_prof_enable.restype = None
     lib.vls_prof_enable.argtypes = [c_int]
     lib.vls_prof_collect.restype = c_int

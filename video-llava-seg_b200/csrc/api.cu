@@ -1,6 +1,8 @@
 // extern "C" entry points of libvls_b200.so (declared in include/vls_b200.h).
 #include "vls_b200.h"
 
+#include <string>
+
 #include "kernels.h"
 
 using namespace vls;
@@ -10,6 +12,17 @@ extern "C" {
 const char* vls_last_error(void) { return last_error(); }
 int vls_abi_version(void) { return 1; }
 long long vls_launch_count(void) { return launch_count(); }
+void vls_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
+int vls_set_tuning(const char* key, int value) {
+  VLS_REQUIRE(key != nullptr, "set_tuning: null key");
+  if (std::string(key) == "attn_cluster") {
+    VLS_REQUIRE(value == 1 || value == 2, "attn_cluster must be 1 or 2");
+    g_attn_cluster = value;
+    return 0;
+  }
+  set_error("set_tuning: unknown key '%s'", key);
+  return 1;
+}
 void vls_prof_enable(int on) { prof_set(on != 0); }
 int vls_prof_collect(int slot, int* count, double* total_ms) {
   VLS_REQUIRE(slot >= 0 && slot < PROF_SLOTS && count && total_ms, "prof_collect: bad arguments");

@@ -2,14 +2,20 @@
 // Nq = 4096 queries, Nk up to 7*4096 + 64 keys (sam/transformer.py:311-360 after projection;
 // RoPE is already applied to Q/K by the projection GEMM epilogue).
 //
-// CTA = one 128-query tile x one KV split.  Warp 0: TMA producer (Q once; K / V^T tiles of 64 keys,
-// 2 stages each, 128B swizzle).  Warp 1: single-thread tcgen05.mma issuer:
-//      S_j = Q K_j^T   (SS, M128 N64 K16 x16)  -> TMEM S[j&1]
-//      O  += P_j V_j   (TS, A = bf16 P_j in TMEM aliasing S[j&1], B = V^T tile, M128 N256 K16 x4)
-// S_{j+1} is issued before P_j is waited on, so the tensor pipe overlaps the softmax of tile j.
-// Warps 2-5: softmax, one thread per query row (no shuffles), running max kept in the log2 domain
-// and only refreshed when it grows by more than 8 (lazy rescale of O in TMEM), exp2 with the
-// 1/sqrt(d)*log2(e) scale folded in, P written back to TMEM as packed bf16.
+// CTA = one 128-query tile x one KV split; CTAs run as CLUSTERS OF 2 (adjacent query tiles, same KV range):
+// each CTA TMA-loads half of every K / V^T tile and MULTICASTS it to both, halving the L2->SM operand traffic
+// (the r1 ncu capture showed 941 MB / launch = 6.4 TB/s of L2 reads with private loads).
+//   warp 0   : TMA producer (Q once; K / V^T tiles of 128 keys, 128B swizzle, optionally multicast)
+//   warp 1   : single-thread tcgen05.mma issuer
+//                S_j = Q K_j^T   (SS, M128 N128 K16 x16: an in-kernel clock64 trace showed that N=64 MMAs issue at
+//                                 half rate, ~67 cycles each, so tiles are 128 keys)  -> TMEM S[j&1] (2 x 128 columns)
+//                O  += P_j V_j   (TS, A = bf16 P_j in TMEM aliasing S[j&1], B = V^T tile, M128 N256 K16 x8)
+//              S_{j+1} is issued before P_j is waited on, so the tensor pipe overlaps the softmax of tile j;
+//              operand stages are released with a commit multicast to BOTH CTAs' empty barriers
+//   warps 2-9: softmax, 256 threads = 2 threads per query row (columns 0-63 / 64-127 of the tile; the row max is
+//              exchanged through shared memory), running max in the log2 domain, refreshed only when it grows by
+//              more than 8 (lazy rescale of each thread's half of O in TMEM), exp2 with the 1/sqrt(d)*log2(e)
+//              scale folded in, P written back to TMEM as packed bf16.
 // With KV splits, partial (O, m, l) go to a workspace and attn_combine_kernel merges them.
 #include "common.cuh"
 #include "kernels.h"
@@ -19,18 +25,21 @@ namespace vls {
 namespace {
 
 constexpr int BM = 128;
-constexpr int BN = 64;
+constexpr int BN = 128;          // keys per tile: S = Q K^T runs as M128 N128 K16 MMAs (N=64 issues at half rate)
 constexpr int D = 256;
-constexpr int KV_STAGES = 2;
+constexpr int KV_STAGES = 1;     // Q 64 KB + K tile 64 KB + V^T tile 64 KB; K(j+1) streams in under softmax(j) + PV(j)
 constexpr int Q_BYTES = BM * D * 2;
 constexpr int K_BYTES = BN * D * 2;
 constexpr int V_BYTES = D * BN * 2;
-constexpr int THREADS = 192;
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + 256 + 1024;
+constexpr int THREADS = 352;           // K-producer warp + MMA warp + 8 softmax warps + V-producer warp
+constexpr int SOFTMAX_THREADS = 256;
+constexpr int XCHG_BYTES = 3 * 2 * BM * 4;  // row-max exchange [tile parity][half][row] + row-sum exchange [half][row]
+constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCHG_BYTES + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0;
-constexpr uint32_t TM_S = 256;
+constexpr uint32_t TM_S = 256;   // 2 x 128 columns (f32 scores, overwritten in place by packed bf16 P)
 constexpr float RESCALE_THRESHOLD = 8.0f;
+constexpr uint16_t PAIR_MASK = 0x3;
 
 struct AttnParams {
   int Nq, Nk, splits;
@@ -39,29 +48,41 @@ struct AttnParams {
   long long ldo, o_bstride;
   float* part_o;
   float* part_ml;
+  long long* trace;  // optional dev trace: [role 0..2][tile][8] clock64 stamps of CTA (0,0,0) (vls_attention_trace)
 };
 
+#define VLS_TRACE(role, tile, slot)                                                                         \
+  do {                                                                                                      \
+    if (p.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (tile) < 64)                    \
+      p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64();                                             \
+  } while (0)
+
+template <int CL>  // CTAs per cluster (1: private loads, 2: each CTA multicasts half of every K / V^T tile)
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
+  // the dynamic smem base has the same offset in both CTAs of the pair, so this alignment is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + Q_BYTES;
   uint8_t* sV = sK + KV_STAGES * K_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + KV_STAGES * V_BYTES);
+  float* xchg = reinterpret_cast<float*>(sV + KV_STAGES * V_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + XCHG_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
-  uint64_t* k_empty = bars + 3;
-  uint64_t* v_full = bars + 5;
-  uint64_t* v_empty = bars + 7;
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_ready = bars + 11;
-  uint64_t* pv_done = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  uint64_t* k_empty = bars + 4;
+  uint64_t* v_full = bars + 7;
+  uint64_t* v_empty = bars + 10;
+  uint64_t* s_full = bars + 13;
+  uint64_t* p_ready = bars + 15;
+  uint64_t* pv_done = bars + 17;
+  uint64_t* o_done = bars + 18;   // single phase: all PV MMAs of this CTA have completed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
   const int q0 = blockIdx.x * BM;
   const int split = blockIdx.y;
   const int bz = blockIdx.z;
@@ -72,15 +93,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < KV_STAGES; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], CL);  // released by the MMA commits of every CTA of the cluster
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], CL);
+    }
+    for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_ready[s], 128);
+      mbar_init(&p_ready[s], SOFTMAX_THREADS);
     }
     mbar_init(pv_done, 1);
+    mbar_init(o_done, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -92,6 +116,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peer's barriers must be initialised before any multicast can signal them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -101,17 +126,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
       for (int kp = 0; kp < 4; ++kp) tma_load_3d(sQ + kp * (BM * 128), &tmQ, q_full, kp * 64, q0, bz);
       for (int j = 0; j < n; ++j) {
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
         const int kv0 = (t0 + j) * BN;
         mbar_wait(&k_empty[st], ph ^ 1);
+        VLS_TRACE(0, j, 0);
         mbar_expect_tx(&k_full[st], K_BYTES);
+        if (CL > 1) {
+          // K tile: this CTA fetches key rows [rank*64, rank*64+64) of each 64-channel panel for both CTAs
 #pragma unroll
-        for (int kp = 0; kp < 4; ++kp)
-          tma_load_3d(sK + st * K_BYTES + kp * (BN * 128), &tmK, &k_full[st], kp * 64, kv0, bz);
+          for (int kp = 0; kp < 4; ++kp)
+            tma_load_3d_mc(sK + st * K_BYTES + kp * (BN * 128) + rank * (64 * 128), &tmK, &k_full[st], kp * 64,
+                           kv0 + (int)rank * 64, bz, PAIR_MASK);
+        } else {
+#pragma unroll
+          for (int kp = 0; kp < 4; ++kp)
+            tma_load_3d(sK + st * K_BYTES + kp * (BN * 128), &tmK, &k_full[st], kp * 64, kv0, bz);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // V^T producer on its own warp: with one stage per operand an in-order K,V,K,V producer would hold K(j+1)
+    // back until PV(j-1) has released the V buffer
+    if (lane == 0) {
+      for (int j = 0; j < n; ++j) {
+        const int st = j % KV_STAGES;
+        const uint32_t ph = (j / KV_STAGES) & 1;
+        const int kv0 = (t0 + j) * BN;
         mbar_wait(&v_empty[st], ph ^ 1);
+        VLS_TRACE(0, j, 1);
         mbar_expect_tx(&v_full[st], V_BYTES);
-        tma_load_3d(sV + st * V_BYTES, &tmV, &v_full[st], kv0, 0, bz);
+        // V^T tile = two 64-key panels of [256 channels x 128 B]
+#pragma unroll
+        for (int vp = 0; vp < 2; ++vp) {
+          if (CL > 1)  // this CTA fetches channel rows [rank*128, rank*128+128) of each panel for both CTAs
+            tma_load_3d_mc(sV + st * V_BYTES + vp * (D * 128) + rank * (128 * 128), &tmV, &v_full[st], kv0 + vp * 64,
+                           (int)rank * 128, bz, PAIR_MASK);
+          else
+            tma_load_3d(sV + st * V_BYTES + vp * (D * 128), &tmV, &v_full[st], kv0 + vp * 64, 0, bz);
+        }
       }
     }
   } else if (warp == 1) {
@@ -121,8 +174,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t q_addr = smem_u32(sQ);
       mbar_wait(q_full, 0);
       auto issue_s = [&](int j) {
-        const int st = j & 1;
-        mbar_wait(&k_full[st], (j >> 1) & 1);
+        const int st = j % KV_STAGES;
+        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
+        VLS_TRACE(1, j, 0);
         tc_fence_after();
         const uint32_t k_addr = smem_u32(sK + st * K_BYTES);
         const uint32_t d_s = tmem + TM_S + uint32_t(j & 1) * BN;
@@ -133,56 +187,72 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, qd + 2 * kk, kd + 2 * kk, idesc_s, (kp | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(&k_empty[st]);
+        if (CL > 1) umma_commit_mc(&k_empty[st], PAIR_MASK); else umma_commit(&k_empty[st]);
         umma_commit(&s_full[j & 1]);
+        VLS_TRACE(1, j, 1);
       };
       issue_s(0);
       for (int j = 0; j < n; ++j) {
         if (j + 1 < n) issue_s(j + 1);
-        const int st = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        mbar_wait(&p_ready[st], ph);
-        mbar_wait(&v_full[st], ph);
+        const int st = j % KV_STAGES;
+        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+        VLS_TRACE(1, j, 2);
+        mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
+        VLS_TRACE(1, j, 3);
         tc_fence_after();
-        const uint64_t vd = make_desc_sw128(smem_u32(sV + st * V_BYTES));
+        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
         const uint32_t a_p = tmem + TM_S + uint32_t(j & 1) * BN;
 #pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks)
-          umma_ts(tmem + TM_O, a_p + ks * 8, vd + 2 * ks, idesc_pv, (j | ks) != 0 ? 1u : 0u);
-        umma_commit(&v_empty[st]);
+        for (int ks = 0; ks < BN / 16; ++ks) {
+          const uint64_t vd = make_desc_sw128(v_addr + (ks >> 2) * (D * 128));
+          umma_ts(tmem + TM_O, a_p + ks * 8, vd + 2 * (ks & 3), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+        }
+        if (CL > 1) umma_commit_mc(&v_empty[st], PAIR_MASK); else umma_commit(&v_empty[st]);
         umma_commit(pv_done);
+        VLS_TRACE(1, j, 4);
       }
+      umma_commit(o_done);
     }
-  } else {
-    const int q = warp & 3;
-    const int row = q0 + q * 32 + lane;
+  } else if (warp < 10) {
+    const int q = warp & 3;            // TMEM lane quarter (two warps share each quarter)
+    const int half = (warp - 2) >> 2;  // 0: columns 0-31 of the S tile / 0-127 of O, 1: the other halves
+    const int rl = q * 32 + lane;      // row inside the tile
+    const int row = q0 + rl;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
     float m_used = -INFINITY;
     float l = 0.0f;
     for (int j = 0; j < n; ++j) {
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 0);
       tc_fence_after();
       uint32_t r[64];
-      tmem_ld32(tmem + lane_off + TM_S + b * BN, r);
-      tmem_ld32(tmem + lane_off + TM_S + b * BN + 32, r + 32);
+      tmem_ld32(tmem + lane_off + TM_S + b * BN + half * 64, r);
+      tmem_ld32(tmem + lane_off + TM_S + b * BN + half * 64 + 32, r + 32);
       tc_wait_ld();
-      const int kv0 = (t0 + j) * BN;
-      const int valid = p.Nk - kv0;  // >= 1
+      const int kv0 = (t0 + j) * BN + half * 64;
+      const int valid = p.Nk - kv0;  // may be <= 0 for the upper half of the last tile
       float mx = -INFINITY;
+      if (valid < 64) {  // only the last key tile of the sequence is ragged
 #pragma unroll
-      for (int i = 0; i < 64; ++i) {
-        float s = __uint_as_float(r[i]);
-        if (i >= valid) s = -INFINITY;
-        r[i] = __float_as_uint(s);
-        mx = fmaxf(mx, s);
+        for (int i = 0; i < 64; ++i)
+          if (i >= valid) r[i] = 0xff800000u;  // -inf
       }
+#pragma unroll
+      for (int i = 0; i < 64; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+      // both threads of a row need the max over all 128 columns
+      float* xb = xchg + b * (2 * BM);
+      xb[half * BM + rl] = mx;
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 1);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 2);
+      mx = fmaxf(mx, xb[(half ^ 1) * BM + rl]);
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       const bool need = m_new > m_used + RESCALE_THRESHOLD;
       if (__any_sync(0xffffffffu, need)) {
         float alpha = 1.0f;
         if (need) {
-          alpha = exp2f(m_used - m_new);
+          alpha = ex2_approx(m_used - m_new);
           m_used = m_new;
         }
         l *= alpha;
@@ -190,13 +260,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < D / 32; ++c) {
+          for (int c = 0; c < 4; ++c) {
             uint32_t o[32];
-            tmem_ld32(tmem + lane_off + TM_O + c * 32, o);
+            tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem + lane_off + TM_O + c * 32, o);
+            tmem_st32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
           }
           tc_wait_st();
         }
@@ -204,28 +274,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       uint32_t pk[32];
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float p0 = exp2f(__uint_as_float(r[2 * i]) * p.scale_log2 - m_used);
-        const float p1 = exp2f(__uint_as_float(r[2 * i + 1]) * p.scale_log2 - m_used);
+        const float x0 = __uint_as_float(r[2 * i]) * p.scale_log2 - m_used;
+        const float x1 = __uint_as_float(r[2 * i + 1]) * p.scale_log2 - m_used;
+        const float p0 = ex2_approx(x0), p1 = ex2_approx(x1);
         l += p0 + p1;
         pk[i] = pack_bf16x2(p0, p1);
       }
-      tmem_st32(tmem + lane_off + TM_S + b * BN, pk);
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 3);
+      tmem_st32(tmem + lane_off + TM_S + b * BN + half * 32, pk);
       tc_wait_st();
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 4);
       tc_fence_before();
       mbar_arrive(&p_ready[b]);
+      if (threadIdx.x == 64) VLS_TRACE(2, j, 5);
     }
     if (n > 0) {
-      mbar_wait(pv_done, (n - 1) & 1);
+      // NOT pv_done: its parity can alias here.  A softmax thread only knows that S_{n-1} has completed, i.e. that
+      // PV_{n-3} has, so pv_done may be one OR two phases behind and a parity wait for phase n-1 would pass in the
+      // latter case (caught by the bitwise-determinism test: O read before the last two PVs had landed).  The
+      // per-tile rescale wait above is safe: S_j complete => PV_{j-2} complete => at most one phase behind.
+      mbar_wait(o_done, 0);
       tc_fence_after();
     }
+    // total row sum = sum of the two halves (same m_used on both)
+    float* lx = xchg + 2 * (2 * BM);  // separate region: a partner may still be reading the last tile's max
+    lx[half * BM + rl] = l;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    l += lx[(half ^ 1) * BM + rl];
     const bool row_ok = row < p.Nq;
     if (p.splits == 1) {
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-      bf16* out = p.O + (long long)bz * p.o_bstride + (long long)row * p.ldo;
+      bf16* out = p.O + (long long)bz * p.o_bstride + (long long)row * p.ldo + half * 128;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t o[32];
-        tmem_ld32(tmem + lane_off + TM_O + c * 32, o);
+        tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
         tc_wait_ld();
         if (row_ok) {
           uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
@@ -239,11 +322,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     } else {
       const long long prow = ((long long)bz * p.splits + split) * p.Nq + row;
-      float* po = p.part_o + prow * D;
+      float* po = p.part_o + prow * D + half * 128;
 #pragma unroll 1
-      for (int c = 0; c < D / 32; ++c) {
+      for (int c = 0; c < 4; ++c) {
         uint32_t o[32];
-        tmem_ld32(tmem + lane_off + TM_O + c * 32, o);
+        tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
         tc_wait_ld();
         if (row_ok) {
           float4* o4 = reinterpret_cast<float4*>(po + c * 32);
@@ -253,7 +336,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                                 __uint_as_float(o[4 * i + 3]));
         }
       }
-      if (row_ok) {
+      if (row_ok && half == 0) {
         p.part_ml[prow * 2] = m_used;
         p.part_ml[prow * 2 + 1] = l;
       }
@@ -261,6 +344,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // do not exit while the peer may still multicast into this CTA
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
@@ -293,6 +377,9 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
 
 }  // namespace
 
+long long* g_attn_trace = nullptr;  // dev-only timeline buffer (3*64*8 int64), see tools/trace_attention.py
+int g_attn_cluster = 1;  // 1: private K/V loads; 2: pairs of query tiles multicast K/V (vls_set_tuning "attn_cluster")
+
 size_t attn_workspace_bytes(int B, int Nq, int splits) {
   if (splits <= 1) return 0;
   return align256((size_t)B * splits * Nq * D * 4) + align256((size_t)B * splits * Nq * 2 * 4);
@@ -315,24 +402,37 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   const int nt = (a.Nk + BN - 1) / BN;
   VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
   VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
+  const int qtiles = (a.Nq + BM - 1) / BM;
+  const int cl = (qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
   CUtensorMap tmQ, tmK, tmV;
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
-  VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, BN));
-  VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, D, a.B, a.ldvt, a.vt_bstride, D));
+  VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, cl > 1 ? BN / 2 : BN));
+  VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, D, a.B, a.ldvt, a.vt_bstride, cl > 1 ? D / 2 : D));
   AttnParams p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.splits = a.splits;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.O = reinterpret_cast<bf16*>(a.O); p.ldo = a.ldo; p.o_bstride = a.o_bstride;
   p.part_o = a.part_o; p.part_ml = a.part_ml;
+  p.trace = g_attn_trace;
   static bool attr_set = false;
   if (!attr_set) {
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  dim3 grid((a.Nq + BM - 1) / BM, a.splits, a.B);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(qtiles, a.splits, a.B);
+  cfg.blockDim = dim3(THREADS);
+  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
   const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
   prof_begin(slot, stream);
-  attn_fwd_kernel<<<grid, THREADS, SMEM_BYTES, stream>>>(tmQ, tmK, tmV, p);
+  if (cl > 1) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2>, tmQ, tmK, tmV, p));
+  else VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1>, tmQ, tmK, tmV, p));
   prof_end(slot, stream);
   VLS_POST_LAUNCH(1);
   if (a.splits > 1) {

@@ -49,6 +49,8 @@ struct AttnArgs {
   float* part_o = nullptr;   // workspace when splits > 1: f32 [B][splits][Nq][256]
   float* part_ml = nullptr;  // f32 [B][splits][Nq][2] (running max in log2 domain, sum)
 };
+extern int g_attn_cluster;
+extern long long* g_attn_trace;
 size_t attn_workspace_bytes(int B, int Nq, int splits);
 int attn_pick_splits(int B, int Nq, int Nk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
