@@ -183,7 +183,8 @@ def run_ours(args):
         "dtype": "bf16", "data": "synthetic backbone features + seeded random-init weights",
         "config": {"workload": WORKLOAD, "objects_per_gpu": 1, "clips_per_gpu": 1, "ramp_frames": RAMP,
                    "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
-                   "parallelism": f"{world} independent replica(s), sharded by clip, no collective on the path"},
+                   "parallelism": f"{world} independent replica(s), sharded by clip, no collective on the path",
+                   "execution": "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes_per_frame),
                 "d2h_bytes_per_step": int(out_bytes)},
@@ -203,6 +204,7 @@ def roofline(predictor, source, prompt, lib, torch):
     launch = 4 * Nq * Nk * d (QK^T + PV, 2 flops/MAC); duration = CUDA events around each launch on its stream."""
     import ctypes
 
+    predictor.use_cuda_graph = False   # the same kernels, launched eagerly so that each launch can be bracketed by events
     state = predictor.init_state(source)
     predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
     gen = predictor.propagate_in_video(state)
@@ -215,6 +217,7 @@ def roofline(predictor, source, prompt, lib, torch):
     torch.cuda.synchronize()
     lib.vls_prof_enable(0)
     gen.close()
+    predictor.use_cuda_graph = True
     cnt, tot = ctypes.c_int(0), ctypes.c_double(0.0)
     lib.vls_prof_collect(0, ctypes.byref(cnt), ctypes.byref(tot))
     cnt_s, tot_s = ctypes.c_int(0), ctypes.c_double(0.0)

@@ -35,6 +35,9 @@ const char* vls_last_error(void);
 int vls_abi_version(void);
 /* Number of kernels this library has launched in the calling process (bench.py's `gpu_launches`). */
 long long vls_launch_count(void);
+/* A CUDA graph that captured n of this library's launches reports each replay here, so the counter keeps
+ * meaning "kernels of this library executed" (bench.py's `gpu_launches`). */
+void vls_launch_count_add(long long n);
 /* Performance knobs (results are identical for every setting).  "attn_cluster": 1 = each CTA of the attention
  * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each. */
 int vls_set_tuning(const char* key, int value);

@@ -11,8 +11,14 @@ T = 60
 clip = synth.SyntheticClip(100, T)
 frames = [clip.frame(t, 1) for t in range(T)]
 src = FeatureClip(lambda t: frames[t], T, resident_device=dev)
-for mode in ("nosync", "sync", "nosync"):
-    state = predictor.init_state(src)
+pinned = FeatureClip(lambda t: frames[t], T, pinned=True)
+for mode in ("nosync", "sync", "nosync", "pinned-sync", "pinned-sync-eager"):
+    if mode.startswith("pinned"):
+        src_use = pinned
+        predictor.use_cuda_graph = not mode.endswith("eager")
+    else:
+        src_use = src
+    state = predictor.init_state(src_use)
     predictor.add_new_points_or_box(state, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
     gen = predictor.propagate_in_video(state)
     for _ in range(20):
@@ -26,7 +32,7 @@ for mode in ("nosync", "sync", "nosync"):
     for _ in range(n):
         t0 = time.perf_counter()
         next(gen)
-        if mode == "sync":
+        if "sync" in mode and mode != "nosync":
             torch.cuda.synchronize()
         cpu.append(time.perf_counter() - t0)
     e1.record()

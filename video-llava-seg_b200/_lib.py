@@ -38,6 +38,8 @@ def _declare(lib):
     lib.vls_last_error.restype = ctypes.c_char_p
     lib.vls_abi_version.restype = c_int
     lib.vls_launch_count.restype = c_ll
+    lib.vls_launch_count_add.restype = None
+    lib.vls_launch_count_add.argtypes = [c_ll]
     lib.vls_attention_trace.restype = None
     lib.vls_attention_trace.argtypes = [c_void_p]
     lib.vls_set_tuning.restype = c_int

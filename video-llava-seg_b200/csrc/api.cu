@@ -12,6 +12,7 @@ extern "C" {
 const char* vls_last_error(void) { return last_error(); }
 int vls_abi_version(void) { return 1; }
 long long vls_launch_count(void) { return launch_count(); }
+void vls_launch_count_add(long long n) { count_launches((int)n); }
 void vls_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 int vls_set_tuning(const char* key, int value) {
   VLS_REQUIRE(key != nullptr, "set_tuning: null key");

@@ -6,13 +6,16 @@ import torch
 class FeatureClip:
     """Wraps `frame(t) -> {"vision_feat" [HW,1,256], "vision_pos" [HW,1,256], "feat_s0" [1,32,4H,4W],
     "feat_s1" [1,64,2H,2W]}` (e.g. synth.SyntheticClip.frame).  With `pinned=True` frames are staged in pinned
-    host memory and copied to the device inside `frame_features` (the end-to-end path of bench.py); otherwise
-    they are uploaded once and stay resident in HBM."""
+    host memory and copied to the device inside `frame_features`, double-buffered on a copy stream so that frame
+    t+1 crosses PCIe while frame t is tracked (the end-to-end path of bench.py); otherwise they are uploaded once
+    and stay resident in HBM."""
 
     def __init__(self, frame_fn, num_frames, video_height=1024, video_width=1024, feat=64, resident_device=None,
                  pinned=False):
         self.num_frames, self.video_height, self.video_width, self.feat = num_frames, video_height, video_width, feat
         self._frames = []
+        self._pinned, self._copy_stream, self._zeros = bool(pinned and resident_device is None), None, None
+        self._staging = self._ready = self._consumed = None
         self._pos = None  # the neck's sine position encoding is a per-clip constant: uploaded once, not per frame
         self.h2d_bytes_per_frame = 0
         for t in range(num_frames):
@@ -29,14 +32,49 @@ class FeatureClip:
         if self._frames:
             self.h2d_bytes_per_frame = sum(v.numel() * v.element_size() for v in self._frames[0].values())
 
+    def _issue_h2d(self, t, device):
+        """Enqueue the host->device copy of frame t on the copy stream into staging set t % 2."""
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=device)
+            self._staging = [None, None]
+            self._ready = [None, None]
+            self._consumed = [None, None]
+        s = t % 2
+        if self._staging[s] is None:
+            self._staging[s] = {k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in self._frames[t].items()}
+        cs = self._copy_stream
+        if self._consumed[s] is not None:
+            cs.wait_event(self._consumed[s])           # the previous user of this staging set must be done
+        with torch.cuda.stream(cs):
+            for k, v in self._frames[t].items():
+                self._staging[s][k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._ready[s] = (t, ev)
+
     def frame_features(self, t, device):
-        d = {k: v.to(device, non_blocking=True) for k, v in self._frames[t].items()}
+        if self._pinned:
+            # double-buffered prefetch: frame t+1 crosses PCIe on a copy stream while frame t is being tracked
+            main = torch.cuda.current_stream(device)
+            if self._copy_stream is None or self._ready[t % 2] is None or self._ready[t % 2][0] != t:
+                self._issue_h2d(t, device)
+            prev = (t - 1) % 2
+            if self._consumed is not None and self._staging[prev] is not None:
+                ev = torch.cuda.Event()
+                ev.record(main)                          # everything that read the other set has been enqueued by now
+                self._consumed[prev] = ev
+            main.wait_event(self._ready[t % 2][1])
+            if t + 1 < self.num_frames:
+                self._issue_h2d(t + 1, device)
+            d = dict(self._staging[t % 2])
+        else:
+            d = {k: v.to(device, non_blocking=True) for k, v in self._frames[t].items()}
         if self._pos.device != torch.device(device):
             self._pos = self._pos.to(device)
         d["vision_pos"] = self._pos
         s = self.feat
         feat = d["vision_feat"].permute(1, 2, 0).reshape(1, 256, s, s)
         pos = d["vision_pos"].permute(1, 2, 0).reshape(1, 256, s, s)
-        z0 = torch.zeros(1, 1, 4 * s, 4 * s, device=device)
-        z1 = torch.zeros(1, 1, 2 * s, 2 * s, device=device)
-        return {"backbone_fpn": [d["feat_s0"], d["feat_s1"], feat], "vision_pos_enc": [z0, z1, pos]}
+        if self._zeros is None or self._zeros[0].device != torch.device(device):
+            self._zeros = (torch.zeros(1, 1, 4 * s, 4 * s, device=device), torch.zeros(1, 1, 2 * s, 2 * s, device=device))
+        return {"backbone_fpn": [d["feat_s0"], d["feat_s1"], feat], "vision_pos_enc": [self._zeros[0], self._zeros[1], pos]}

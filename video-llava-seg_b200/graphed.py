@@ -1,0 +1,189 @@
+"""Steady-state propagation as ONE CUDA-graph replay per frame.
+
+Once the memory bank is full (1 conditioning frame + 6 previous frames + 16 object pointers) every
+propagated frame runs the same kernel sequence on the same shapes.  `SteadyStateGraph` keeps the bank in
+device-resident static buffers laid out in the reference's key order (sam2_base.py:533-568,599-646):
+
+    bank_mem [B, 7*HW + 16*4, 64] bf16 = [cond | t-6 ... t-1 | ptr(cond), ptr(t-1) ... ptr(t-15)]
+    bank_pos [    7*HW + 16*4, 64] f32 = maskmem_pos_enc + tpos per slot | pointer temporal encodings
+
+so the positional rows are constants (only the conditioning pointer's distance changes: 4 rows per frame),
+captures {memory attention -> mask decoder -> SAM-heads glue -> fused memory encoder -> hole filling ->
+video-resolution resize -> bank shift} into a torch.cuda.CUDAGraph, and replays it.  Per frame the host only
+copies the frame's backbone features into the static inputs, patches 4 positional rows, launches the graph and
+clones the outputs it must retain -- ~10 stream operations instead of ~190 kernel launches.
+
+Results are those of the eager path (same kernels, same key order); the eager path remains the general one
+(ragged bank during the ramp, prompts, reverse tracking, CPU offload, several conditioning frames).
+"""
+import torch
+
+from . import _lib, ops
+from .modeling.sam2_utils import get_1d_sine_pe
+from .utils.misc import fill_holes_in_mask_scores
+
+
+class SteadyStateGraph:
+    def __init__(self, model, state, frame_idx, batch_size):
+        self.model, self.B = model, batch_size
+        self.dev = state["device"]
+        self.num_frames = state["num_frames"]
+        self.hw = (state["video_height"], state["video_width"])
+        m = model
+        self.HW = m.sam_image_embedding_size ** 2
+        self.n_mem = m.num_maskmem                       # 7
+        self.n_ptr = min(self.num_frames, m.max_obj_ptrs_in_encoder)   # 16
+        self.k = m.hidden_dim // m.mem_dim               # 4 tokens per pointer
+        self.Nk = self.n_mem * self.HW + self.n_ptr * self.k
+        self.cond_idx = next(iter(state["output_dict"]["cond_frame_outputs"]))
+        self.graph = None
+        self.next_frame = None
+        self._build_static(state, frame_idx)
+
+    # ------------------------------------------------------------------ eligibility
+    @staticmethod
+    def eligible(model, state, frame_idx, batch_size, reverse):
+        if reverse or not getattr(model, "use_cuda_graph", True) or state["offload_state_to_cpu"]:
+            return False
+        if model.memory_temporal_stride_for_eval != 1 or model.max_cond_frames_in_attn != -1 or model.non_overlap_masks \
+                or model.non_overlap_masks_for_mem_enc or model.num_maskmem != 7 or model.training:
+            return False
+        out = state["output_dict"]
+        if len(out["cond_frame_outputs"]) != 1:
+            return False
+        cond = next(iter(out["cond_frame_outputs"]))
+        n_ptr = min(state["num_frames"], model.max_obj_ptrs_in_encoder)
+        if frame_idx - cond < n_ptr or n_ptr < model.num_maskmem:
+            return False
+        non = out["non_cond_frame_outputs"]
+        for d in range(1, n_ptr):
+            o = non.get(frame_idx - d)
+            if o is None or o["obj_ptr"].shape[0] != batch_size:
+                return False
+            if d < model.num_maskmem and (o.get("maskmem_rows") is None and o.get("maskmem_features") is None):
+                return False
+        return True
+
+    # ------------------------------------------------------------------ static buffers
+    def _build_static(self, state, frame_idx):
+        m, B, dev, HW = self.model, self.B, self.dev, self.HW
+        c = m._constants()
+        out = state["output_dict"]
+        cond = out["cond_frame_outputs"][self.cond_idx]
+        non = out["non_cond_frame_outputs"]
+        self.bank_mem = torch.empty((B, self.Nk, m.mem_dim), device=dev, dtype=torch.bfloat16)
+        self.bank_pos = torch.empty((self.Nk, m.mem_dim), device=dev, dtype=torch.float32)
+        self.shift_tmp = torch.empty((B, (self.n_mem - 2) * HW, m.mem_dim), device=dev, dtype=torch.bfloat16)
+        self.ptr_tmp = torch.empty((B, (self.n_ptr - 2) * self.k, m.mem_dim), device=dev, dtype=torch.bfloat16)
+        # memories: conditioning frame (t_pos 0), then t-6 ... t-1 (t_pos 1..6)   (sam2_base.py:533-568)
+        self.bank_mem[:, :HW] = m._mem_rows(cond).to(dev)
+        self.bank_pos[:HW] = c["mem_pos_rows"][0]
+        for t_pos in range(1, self.n_mem):
+            t_rel = self.n_mem - t_pos
+            self.bank_mem[:, t_pos * HW:(t_pos + 1) * HW] = m._mem_rows(non[frame_idx - t_rel]).to(dev)
+            self.bank_pos[t_pos * HW:(t_pos + 1) * HW] = c["mem_pos_rows"][t_pos]
+        # pointers: conditioning frame, then t-1 ... t-15, 4 tokens of 64 each   (sam2_base.py:599-646)
+        self.ptr_off = self.n_mem * HW
+        ptrs = [cond["obj_ptr"]] + [non[frame_idx - d]["obj_ptr"] for d in range(1, self.n_ptr)]
+        self.bank_mem[:, self.ptr_off:] = torch.stack(ptrs, 1).reshape(B, self.n_ptr * self.k, m.mem_dim).to(torch.bfloat16)
+        # pointer temporal encodings for every possible distance: one table, rows repeated x4
+        t_diff_max = self.n_ptr - 1
+        dist = torch.arange(self.num_frames + 1, device=dev, dtype=torch.float32) / t_diff_max
+        table = ops.linear_f32(get_1d_sine_pe(dist, dim=m.hidden_dim), c["tpos_w"], c["tpos_b"])       # [T+1, 64]
+        self.ptr_pos_table = table.repeat_interleave(self.k, dim=0).reshape(self.num_frames + 1, self.k, m.mem_dim)
+        for d in range(1, self.n_ptr):
+            self.bank_pos[self.ptr_off + d * self.k: self.ptr_off + (d + 1) * self.k] = self.ptr_pos_table[d]
+        # static inputs: same strides as the tensors the feature source hands out
+        _, bo, _, _, _ = m._get_image_feature(state, frame_idx, 1)
+        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
+        self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in fpn[-3:])
+        self.in_pos = torch.empty_like(pe[-1])
+        self._pos_src = None
+        self.next_frame = frame_idx
+
+    def _load_inputs(self, state, frame_idx):
+        _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx, 1)
+        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
+        self.in_s0.copy_(fpn[-3], non_blocking=True)
+        self.in_s1.copy_(fpn[-2], non_blocking=True)
+        self.in_feat.copy_(fpn[-1], non_blocking=True)
+        if self._pos_src is None or self._pos_src != (pe[-1].data_ptr(), pe[-1].shape):
+            self.in_pos.copy_(pe[-1], non_blocking=True)   # the neck's sine encoding is normally one constant tensor
+            self._pos_src = (pe[-1].data_ptr(), pe[-1].shape)
+        d = frame_idx - self.cond_idx                      # only the conditioning pointer's distance changes
+        self.bank_pos[self.ptr_off: self.ptr_off + self.k].copy_(self.ptr_pos_table[min(d, self.num_frames)], non_blocking=True)
+
+    # ------------------------------------------------------------------ the captured step
+    def _step(self):
+        m, B, HW = self.model, self.B, self.HW
+        s = m.sam_image_embedding_size
+        vf = self.in_feat.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+        vp = self.in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+        pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=self.bank_mem.transpose(0, 1),
+                                 memory_pos=self.bank_pos[None].expand(B, -1, -1).transpose(0, 1),
+                                 num_obj_ptr_tokens=self.n_ptr * self.k)
+        pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
+        high = [self.in_s0.expand(B, -1, -1, -1), self.in_s1.expand(B, -1, -1, -1)]
+        _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
+            pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False)
+        nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
+        pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
+        video = pred if tuple(pred.shape[-2:]) == self.hw else ops.resize_bilinear(pred, self.hw)
+        # bank shift for the next frame: memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
+        n, k, po = self.n_mem, self.k, self.ptr_off
+        self.shift_tmp.copy_(self.bank_mem[:, 2 * HW: n * HW])
+        self.bank_mem[:, HW:(n - 1) * HW].copy_(self.shift_tmp)
+        self.bank_mem[:, (n - 1) * HW: n * HW].copy_(rows)
+        self.ptr_tmp.copy_(self.bank_mem[:, po + k: po + (self.n_ptr - 1) * k])
+        self.bank_mem[:, po + 2 * k:].copy_(self.ptr_tmp)
+        self.bank_mem[:, po + k: po + 2 * k].copy_(obj_ptr.reshape(B, k, m.mem_dim))
+        return pred, obj_ptr, obj_logits, nchw, rows, video
+
+    def _capture(self):
+        keep = (self.bank_mem.clone(), self.bank_pos.clone())
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                              # warm every lazily-built buffer before capturing
+                self._step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.lib().vls_launch_count()
+        with torch.cuda.graph(self.graph):
+            self.outputs = self._step()
+        self.launches_per_replay = _lib.lib().vls_launch_count() - before   # library kernels inside the graph
+        self.bank_mem.copy_(keep[0])                        # the warm-up runs shifted the bank: restore it
+        self.bank_pos.copy_(keep[1])
+        # the graph has baked in the addresses of the modules' workspaces, packed weights and constants:
+        # hold references so they outlive any later re-allocation, and remember their identity
+        self._keepalive = self._signature_objects()
+        self._sig = tuple(id(o) for o in self._keepalive)
+
+    def _signature_objects(self):
+        m = self.model
+        return [m.memory_attention._ws, m.memory_attention._packed, m.sam_mask_decoder._ws, m.sam_mask_decoder._packed,
+                m.memory_encoder._ws, m.memory_encoder._packed, m._consts]
+
+    def valid(self):
+        """False once weights were re-packed / moved (the captured pointers would be stale)."""
+        return self.graph is None or self._sig == tuple(id(o) for o in self._signature_objects())
+
+    # ------------------------------------------------------------------ per frame
+    def run(self, state, frame_idx):
+        """One propagated frame.  Returns the compact state entry and the video-resolution logits."""
+        assert frame_idx == self.next_frame, "graphed propagation must advance frame by frame"
+        self._load_inputs(state, frame_idx)
+        if self.graph is None:
+            self._capture()
+            self._load_inputs(state, frame_idx)
+        self.graph.replay()
+        _lib.lib().vls_launch_count_add(self.launches_per_replay)
+        pred, obj_ptr, obj_logits, nchw, rows, video = self.outputs
+        self.next_frame = frame_idx + 1
+        compact = {
+            "maskmem_features": nchw.clone(), "maskmem_rows": rows.clone(),
+            "maskmem_pos_enc": self.model._get_maskmem_pos_enc(state, {"maskmem_pos_enc": [
+                self.model._constants()["maskmem_pos"].expand(self.B, -1, -1, -1)]}),
+            "pred_masks": pred.clone(), "obj_ptr": obj_ptr.clone(), "object_score_logits": obj_logits.clone(),
+        }
+        return compact, video.clone()

@@ -14,6 +14,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
+from .graphed import SteadyStateGraph
 from .modeling.sam2_base import NO_OBJ_SCORE, SAM2Base
 from .utils.misc import fill_holes_in_mask_scores, load_video_frames
 
@@ -38,6 +39,8 @@ class SAM2VideoPredictor(SAM2Base):
         self.clear_non_cond_mem_around_input = clear_non_cond_mem_around_input
         self.clear_non_cond_mem_for_multi_obj = clear_non_cond_mem_for_multi_obj
         self.add_all_frames_to_correct_as_cond = add_all_frames_to_correct_as_cond
+        # replay the steady-state frame as one CUDA graph (graphed.py); set to False to force the eager path
+        self.use_cuda_graph = True
 
     # ------------------------------------------------------------------ session
     @torch.inference_mode()
@@ -64,6 +67,7 @@ class SAM2VideoPredictor(SAM2Base):
         st["output_dict_per_obj"], st["temp_output_dict_per_obj"] = {}, {}
         st["consolidated_frame_inds"] = {"cond_frame_outputs": set(), "non_cond_frame_outputs": set()}
         st["tracking_has_started"], st["frames_already_tracked"] = False, {}
+        st["steady_graph"] = None
         self._get_image_feature(st, frame_idx=0, batch_size=1)  # warm up / cache frame 0, as the reference does
         return st
 
@@ -91,6 +95,7 @@ class SAM2VideoPredictor(SAM2Base):
     # ------------------------------------------------------------------ prompts
     def _prompt_frame(self, st, frame_idx, obj_idx, point_inputs, mask_inputs):
         """Shared tail of add_new_points_or_box / add_new_mask (sam2_video_predictor.py:250-314,355-402)."""
+        st["steady_graph"] = None  # new prompts change the memory bank
         is_init = frame_idx not in st["frames_already_tracked"]
         reverse = False if is_init else st["frames_already_tracked"][frame_idx]["reverse"]
         obj_out, obj_tmp = st["output_dict_per_obj"][obj_idx], st["temp_output_dict_per_obj"][obj_idx]
@@ -317,13 +322,23 @@ class SAM2VideoPredictor(SAM2Base):
                 pred = cur["pred_masks"]
             else:
                 key = "non_cond_frame_outputs"
-                cur, pred = self._run_single_frame_inference(
-                    inference_state=st, output_dict=out_all, frame_idx=f, batch_size=B, is_init_cond_frame=False,
-                    point_inputs=None, mask_inputs=None, reverse=reverse, run_mem_encoder=True)
+                g = st.get("steady_graph")
+                if g is not None and (g.next_frame != f or g.B != B or not g.valid()):
+                    g = st["steady_graph"] = None
+                if g is None and SteadyStateGraph.eligible(self, st, f, B, reverse):
+                    g = st["steady_graph"] = SteadyStateGraph(self, st, f, B)
+                if g is not None:   # full memory bank: one CUDA-graph replay per frame
+                    cur, video_res = g.run(st, f)
+                    pred = None
+                else:
+                    cur, pred = self._run_single_frame_inference(
+                        inference_state=st, output_dict=out_all, frame_idx=f, batch_size=B, is_init_cond_frame=False,
+                        point_inputs=None, mask_inputs=None, reverse=reverse, run_mem_encoder=True)
                 out_all[key][f] = cur
             self._add_output_per_object(st, f, cur, key)
             st["frames_already_tracked"][f] = {"reverse": reverse}
-            _, video_res = self._get_orig_video_res_output(st, pred)
+            if pred is not None:
+                _, video_res = self._get_orig_video_res_output(st, pred)
             yield f, obj_ids, video_res
 
     def _add_output_per_object(self, st, frame_idx, cur, key):
@@ -383,6 +398,7 @@ class SAM2VideoPredictor(SAM2Base):
             st[k].clear()
 
     def _reset_tracking_results(self, st):
+        st["steady_graph"] = None
         for k in ("point_inputs_per_obj", "mask_inputs_per_obj"):
             for v in st[k].values():
                 v.clear()
