@@ -39,15 +39,40 @@ def peaks():
     return dict(tflops=1400.0, hbm=6650.0, source="fallback (B200_PROFILING.md)")
 
 
+NVML_SAMPLER = r"""
+import sys, time
+import pynvml as N
+N.nvmlInit()
+h = N.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+bits = (("hw_slowdown", N.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", N.nvmlClocksThrottleReasonHwThermalSlowdown),
+        ("sw_thermal_slowdown", N.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", N.nvmlClocksThrottleReasonSwPowerCap))
+while True:
+    mhz = N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)
+    r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+    f = ["Active" if r & b else "Not Active" for _, b in bits]
+    print(f"{time.time()!r}, {mhz}, {mx}, " + ", ".join(f), flush=True)
+    time.sleep(0.004)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons.  Started before the ramp (nvidia-smi needs ~100 ms to start) and
-    summarised over the samples whose wall-clock time falls inside the timed window [mark_start, mark_stop]."""
+    """SM clock / throttle reasons sampled DURING the timed window by a separate process (NVML through pynvml, one
+    light query every ~4 ms; `nvidia-smi -lms` as the fallback).  A child process, not a thread: a Python sampler
+    thread would contend for the GIL with the loop that enqueues the frames, and a polling `nvidia-smi` takes driver
+    locks for milliseconds, which showed up as 3-20 ms stalls of individual timed steps."""
 
     def __init__(self, index):
         self.samples, self.max_mhz, self.t0, self.t1 = [], None, None, None
         q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
-        self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)]
+        try:
+            import pynvml  # noqa: F401
+
+            self.cmd, self.stamped = [sys.executable, "-c", NVML_SAMPLER, str(index)], True
+        except ImportError:
+            self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)]
+            self.stamped = False
         self.proc, self.thread = None, None
 
     def _read(self):
@@ -55,40 +80,53 @@ class ClockSampler:
         for line in self.proc.stdout:
             f = [x.strip() for x in line.split(",")]
             try:
+                stamp = float(f.pop(0)) if self.stamped else time.time()
                 mhz = float(f[0])
                 self.max_mhz = float(f[1])
                 active = [n for n, v in zip(names, f[2:6]) if v.lower().startswith("active")]
-                self.samples.append((time.perf_counter(), mhz, active))
+                self.samples.append((stamp, mhz, active))
             except (ValueError, IndexError):
                 pass
 
-    def __enter__(self):
+    def start(self, ready_timeout=15.0):
+        """Spawn the sampler once per process and wait for its first sample: nvmlInit / nvidia-smi start-up holds
+        driver locks for 0.1-1 s on a fresh box and must not overlap a timed window."""
         try:
             self.proc = subprocess.Popen(self.cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
+            t_end = time.time() + ready_timeout
+            while not self.samples and time.time() < t_end and self.proc.poll() is None:
+                time.sleep(0.01)
         except OSError:
             self.proc = None
         return self
 
-    def mark_start(self):
-        self.t0 = time.perf_counter()
-
-    def mark_stop(self):
-        self.t1 = time.perf_counter()
-
-    def __exit__(self, *a):
+    def stop(self):
         if self.proc is not None:
-            time.sleep(0.05)
             self.proc.terminate()
             self.thread.join(timeout=2)
+            self.proc = None
+
+    def __enter__(self):
+        return self
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
+
+    def __exit__(self, *a):
+        time.sleep(0.02)      # let the last in-window samples arrive
 
     def summary(self):
         t0, t1 = self.t0 or 0.0, self.t1 or float("inf")
-        win = [s for s in self.samples if t0 - 0.02 <= s[0] <= t1 + 0.04]
+        m0, m1 = (0.0, 0.0) if self.stamped else (0.02, 0.04)   # nvidia-smi lines are stamped on arrival
+        win = [s for s in self.samples if t0 - m0 <= s[0] <= t1 + m1]
         scope = "timed window"
         if not win:  # window shorter than the sampling period: fall back to the loaded ramp just before it
-            win, scope = [s for s in self.samples if s[0] <= t1 + 0.04][-10:], "ramp + timed window"
+            win, scope = [s for s in self.samples if s[0] <= t1 + m1][-10:], "ramp + timed window"
         reasons = sorted({r for s in win for r in s[2]})
         return {"sm_mhz": statistics.median([s[1] for s in win]) if win else None, "sm_max_mhz": self.max_mhz,
                 "reasons": reasons, "samples": len(win), "scope": scope}
@@ -119,6 +157,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.lib()
+    sampler = ClockSampler(local).start()
     K, W = args.steps, max(args.warmup, 3)
     T = max(RAMP + W + K + 1, RAMP + 9)  # the roofline pass needs RAMP + 8 frames
     predictor = build_sam.build_sam2_video_predictor(None, synth.init_state_dict(0), dev)
@@ -128,15 +167,29 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def timed_pass(source, d2h):
-        """Ramp + warm-up untimed, then K steps each bracketed by CUDA events, L2 flushed between steps."""
-        with ClockSampler(local) as clocks:
+        """Ramp + warm-up untimed, then K steps each bracketed by CUDA events, L2 flushed between steps.
+        With d2h the binarised video-resolution mask of EVERY step is read back into pinned host memory inside the
+        step's events; the consumer is software-pipelined by one frame (it waits for frame t-1's mask after frame t
+        has been enqueued), as a streaming client of propagate_in_video would be."""
+        import gc
+
+        host = [torch.empty((1, 1, 1024, 1024), dtype=torch.uint8).pin_memory() for _ in range(2)] if d2h else None
+        done = [torch.cuda.Event(), torch.cuda.Event()]
+        checksum = 0
+
+        def read_back(m, slot):
+            host[slot].copy_((m > 0).to(torch.uint8), non_blocking=True)
+            done[slot].record()
+
+        with sampler as clocks:
             state = predictor.init_state(source)
             predictor.add_new_points_or_box(state, 0, 1, points=prompt, labels=[1])
             gen = predictor.propagate_in_video(state)
-            for _ in range(RAMP + W):
+            for j in range(RAMP + W):
                 _, _, m = next(gen)
                 if d2h:
-                    (m > 0).to(torch.uint8).cpu()
+                    read_back(m, j % 2)
+                    done[j % 2].synchronize()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
@@ -144,19 +197,28 @@ def run_ours(args):
             stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
             launches0 = lib.vls_launch_count()
             out_bytes = 0
+            gc.collect()
+            gc.disable()          # a generation-2 collection inside a 2 ms step is host noise, not the path
             clocks.mark_start()
             for i in range(K):
                 flush.zero_()
                 starts[i].record()
                 _, _, m = next(gen)
                 if d2h:
-                    host = (m > 0).to(torch.uint8).cpu()   # result read back every step
-                    out_bytes = host.numel()
+                    read_back(m, i % 2)                      # result of step i -> pinned host memory, inside its events
+                    out_bytes = host[i % 2].numel()
                 stops[i].record()
+                if d2h and i > 0:
+                    done[(i - 1) % 2].synchronize()          # consume step i-1's mask on the host
+                    checksum += int(host[(i - 1) % 2][0, 0, 0, 0])
             torch.cuda.synchronize()
             clocks.mark_stop()
+            gc.enable()
         launches = lib.vls_launch_count() - launches0
-        ms = sum(s.elapsed_time(e) for s, e in zip(starts, stops))
+        per_step = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+        ms = sum(per_step)
+        if os.environ.get("VLS_BENCH_DEBUG"):
+            print(f"[bench debug] d2h={d2h} per-step ms: {[round(x, 3) for x in per_step]}", file=sys.stderr, flush=True)
         if world > 1:
             dist.barrier()
         fps, ms, _ = aggregate_throughput(K, ms, dev)   # sum of frames over ranks / max-over-ranks device time
@@ -177,6 +239,7 @@ def run_ours(args):
     # (2) end to end through the public API with host buffers: H2D of each frame's features, D2H of the mask
     pinned = FeatureClip(lambda t: frames[t], T, pinned=True)
     e2e, _, _, _, out_bytes = timed_pass(pinned, d2h=True)
+    sampler.stop()
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -3,7 +3,8 @@
  *
  * Conventions (all entry points):
  *   - plain pointers and sizes only; every buffer is CALLER-OWNED DEVICE memory unless stated
- *   - work is enqueued on `stream` (a cudaStream_t); no allocation, no synchronisation inside
+ *   - work is enqueued on `stream` (a cudaStream_t); no allocation, no host synchronisation inside
+ *     (vls_mem_attn_forward forks one internal side stream with event fork/join; it is graph-capturable)
  *   - return 0 on success; non-zero on error, with a message in vls_last_error() (thread-local)
  *   - no CPU fallback: without a CUDA device the calls fail, they never compute on the host
  *

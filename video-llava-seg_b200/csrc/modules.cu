@@ -96,6 +96,21 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
 
   // memory K / V^T projections of ALL layers in two launches (they do not depend on x): batch index z = l*B + b.
   //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated);   V_l^T = Wv_l mem^T + bv_l
+  // They run on a forked side stream (event fork/join, capturable into CUDA graphs) so that they overlap layer 0's
+  // LayerNorm -> q/k/v projection -> self-attention -> out-projection chain, whose kernels fill < 1 wave of SMs.
+  static cudaStream_t side_stream = nullptr;
+  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  static const bool overlap = !(getenv("VLS_NO_SIDE_STREAM") && getenv("VLS_NO_SIDE_STREAM")[0] == '1');
+  if (overlap && !side_stream) {
+    VLS_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
+    VLS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    VLS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+  }
+  cudaStream_t side = overlap ? side_stream : st;
+  if (overlap) {
+    VLS_CUDA(cudaEventRecord(ev_fork, st));
+    VLS_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
+  }
   {
     GemmArgs k;
     k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
@@ -104,15 +119,17 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     k.bias = w->ca_k_b_all; k.bias_mode = 1; k.bias_bstride = C; k.bias_batches = L; k.bias_div = B;
     k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
     k.C = kc_all; k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
-    VLS_TRY(launch_gemm(k, st));
+    VLS_TRY(launch_gemm(k, side));
     GemmArgs v;
     v.A = w->ca_v_w_all; v.lda = CM; v.a_bstride = (long long)C * CM; v.a_batches = L; v.a_div = B;
     v.W = mem; v.ldw = CM; v.w_bstride = (long long)Nk * CM; v.w_batches = B; v.w_div = 1;
     v.M = C; v.N = Nk; v.K = CM; v.batch = L * B;
     v.bias = w->ca_v_b_all; v.bias_mode = 2; v.bias_bstride = C; v.bias_batches = L; v.bias_div = B;
     v.C = vt_all; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
-    VLS_TRY(launch_gemm(v, st));
+    VLS_TRY(launch_gemm(v, side));
   }
+  if (overlap) VLS_CUDA(cudaEventRecord(ev_join, side));
+  bool joined = !overlap;
 
   auto attention = [&](const void* K, long long ldk, long long k_bs, const void* Vt, long long ldvt, int nk,
                        int splits) -> int {
@@ -157,6 +174,10 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.ca_q_w, Nq, C, C, B, Lw.ca_q_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
       VLS_TRY(launch_gemm(g, st));
+    }
+    if (!joined) {
+      VLS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+      joined = true;
     }
     VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, vt_all + (size_t)l * B * C * ldv * 2, ldv, Nk,
                       s_cross));

@@ -16,6 +16,8 @@ clones the outputs it must retain -- ~10 stream operations instead of ~190 kerne
 Results are those of the eager path (same kernels, same key order); the eager path remains the general one
 (ragged bank during the ramp, prompts, reverse tracking, CPU offload, several conditioning frames).
 """
+import os
+
 import torch
 
 from . import _lib, ops
@@ -38,6 +40,7 @@ class SteadyStateGraph:
         self.cond_idx = next(iter(state["output_dict"]["cond_frame_outputs"]))
         self.graph = None
         self.next_frame = None
+        self._side = torch.cuda.Stream(device=self.dev)
         self._build_static(state, frame_idx)
 
     # ------------------------------------------------------------------ eligibility
@@ -126,9 +129,16 @@ class SteadyStateGraph:
         high = [self.in_s0.expand(B, -1, -1, -1), self.in_s1.expand(B, -1, -1, -1)]
         _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
             pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False)
+        # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
+        # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side if os.environ.get("VLS_NO_SIDE_STREAM", "0") != "1" else main
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
+            video = pred if tuple(pred.shape[-2:]) == self.hw else ops.resize_bilinear(pred, self.hw)
         nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
-        pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
-        video = pred if tuple(pred.shape[-2:]) == self.hw else ops.resize_bilinear(pred, self.hw)
+        main.wait_stream(side)
         # bank shift for the next frame: memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
         n, k, po = self.n_mem, self.k, self.ptr_off
         self.shift_tmp.copy_(self.bank_mem[:, 2 * HW: n * HW])
