@@ -113,6 +113,42 @@ def test_cc_bit_exact(dev, shape, density):
     assert torch.equal(counts.cpu(), rc)
 
 
+def _blobby(n, h, w, seed, thr=0.0):
+    g = torch.Generator().manual_seed(seed)
+    z = torch.randn(n, 1, max(h // 8, 1), max(w // 8, 1), generator=g)
+    z = torch.nn.functional.interpolate(z, size=(h, w), mode="bilinear", align_corners=False)
+    return (z + 0.15 * torch.randn(n, 1, h, w, generator=g)) > thr
+
+
+@pytest.mark.parametrize("shape", [(32, 1, 256, 256), (6, 1, 32, 1024), (5, 1, 1024, 32), (3, 1, 128, 512), (2, 1, 48, 80)])
+def test_cc_blobby_large_components(dev, shape):
+    """Mask-like inputs (few large components with ragged borders + speckle): long union-find chains, many
+    concurrent unions on the same roots.  Repeated, because a lock-free race would be timing dependent."""
+    from oracle import cc as cc_oracle
+    from video_llava_seg_b200.utils.misc import get_connected_components
+
+    for rep in range(3):
+        m = _blobby(shape[0], shape[2], shape[3], 7 * rep + shape[2])
+        rl, rc = cc_oracle.cc_label(m)
+        md = m.to(dev)
+        for _ in range(3):
+            labels, counts = get_connected_components(md)
+            assert torch.equal(labels.cpu(), rl) and torch.equal(counts.cpu(), rc)
+    # a view whose base address is not 16-byte aligned takes the scalar load path: same result
+    buf = torch.zeros(shape[2] * shape[3] + 3, dtype=torch.uint8, device=dev)
+    m1 = _blobby(1, shape[2], shape[3], 99)
+    view = buf[3:].view(1, 1, shape[2], shape[3])
+    view.copy_(m1.to(dev))
+    from video_llava_seg_b200 import _lib
+    from video_llava_seg_b200._lib import check, ptr, stream
+
+    labels = torch.empty((1, 1, shape[2], shape[3]), dtype=torch.int32, device=dev)
+    counts = torch.empty_like(labels)
+    check(_lib.lib().vls_cc_label(ptr(view), 1, shape[2], shape[3], ptr(labels), ptr(counts), None, 0, stream()))
+    rl, rc = cc_oracle.cc_label(m1)
+    assert torch.equal(labels.cpu(), rl) and torch.equal(counts.cpu(), rc)
+
+
 def test_cc_structured_and_errors(dev):
     from oracle import cc as cc_oracle
     from video_llava_seg_b200.utils.misc import fill_holes_in_mask_scores, get_connected_components

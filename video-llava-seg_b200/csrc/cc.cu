@@ -7,15 +7,18 @@
 // always the minimum index, so   label(pixel) = 1 + min over its component of ((r&~1)*W + (c&~1))
 // and count(pixel) = component area; background pixels get 0 / 0.
 //
-// Small path (one CTA per image, (H/2)*(W/2) <= 16384 blocks): everything lives in shared memory.
-//   A. each lane derives its block's 4-bit occupancy straight from global memory (16-bit loads)
-//   B. warp-level run merge: a warp walks a row of blocks, __ballot_sync of "connected to the left
-//      block" turns horizontal runs into star trees without a single atomic
-//   C. vertical / diagonal unions (atomicMin union-find in smem), pruned when the previous lane of
-//      the same run already linked to a horizontally connected upper block
-//   D. path compression + area: __match_any_sync / __reduce_add_sync aggregate lanes sharing a
-//      root so a large component costs one smem atomic per warp-row, not one per block
-//   E. 128-bit stores of labels and areas (or, for hole filling, sparse in-place stores of 0.1)
+// Small path (one CTA of 512 threads per image, (H/2)*(W/2) <= 16384 blocks, two CTAs per SM): everything lives in
+// 5 bytes of shared memory per block (a union-find word that doubles as the area counter + an occupancy byte).
+//   A. occupancy of every 2x2 block straight from global memory with 128-bit loads (16 pixels x 2 rows per thread)
+//   B. region labelling: a warp walks its band of rows of one 32-block column strip top-down, keeping the previous
+//      row's labels in registers; a horizontal run (found with __ballot_sync) inherits the smallest label of the upper
+//      blocks it touches (warp reductions / segmented min-scan) or starts a new label.  No atomics unless a run joins
+//      two differently named components.  Run areas are summed per label in registers and parked on the label's word.
+//   C. seams between regions (band seams inside a strip, strip seams one lane per row) with lock-free atomicMin
+//      min-root unions + path compression; area parked on a node travels with the link
+//   D. the few blocks that ever started a label are flattened onto their roots (the only loop-y finds)
+//   E. block -> label -> root -> area with plain loads; 128-bit streaming stores of labels and areas
+//      (or, for hole filling, sparse in-place stores of 0.1)
 // Larger images: 64 x 128 pixel tiles labelled in shared memory the same way, tile-border unions in global
 // memory (the labels array is the forest, as in the reference), batched over N, four launches.
 #include "common.cuh"
@@ -25,8 +28,11 @@ namespace vls {
 
 namespace {
 
-constexpr int CC_THREADS = 1024;
+constexpr int CC_THREADS = 512;
 constexpr int CC_MAX_BLOCKS = 16384;
+constexpr int CC_IDX_BITS = 14;                       // block index < 16384; bits 14.. of a ROOT's word hold its area
+constexpr int CC_IDX_MASK = (1 << CC_IDX_BITS) - 1;
+constexpr uint32_t CC_NAME = 0x10u;                   // occupancy byte, bit 4: the block started a new label in phase B
 
 __device__ __forceinline__ int uf_find(const volatile int* s, int n) {
   int p = s[n];
@@ -37,23 +43,76 @@ __device__ __forceinline__ int uf_find(const volatile int* s, int n) {
   return n;
 }
 
+// Every node on the path n -> ... -> r gets parent r.  r is an ancestor of n and parents are always smaller than
+// their children, so the walk ends at r; atomicMin keeps "parent only ever moves to a smaller member of the set".
+__device__ __forceinline__ void uf_compress(int* s, int n, int r) {
+  while (n > r) {
+    const int p = reinterpret_cast<const volatile int*>(s)[n];
+    if (p == n) break;
+    if (p > r) atomicMin(s + n, r);
+    n = p;
+  }
+}
+
+// min-root union (lock-free, atomicMin on roots) followed by path compression of both sides
 __device__ __forceinline__ void uf_union(int* s, int a, int b) {
-  bool done;
-  do {
-    a = uf_find(s, a);
-    b = uf_find(s, b);
-    if (a < b) {
-      const int old = atomicMin(s + b, a);
-      done = (old == b);
-      b = old;
-    } else if (b < a) {
-      const int old = atomicMin(s + a, b);
-      done = (old == a);
-      a = old;
-    } else {
-      done = true;
+  int ra = uf_find(s, a), rb = uf_find(s, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      const int t = ra;
+      ra = rb;
+      rb = t;
     }
-  } while (!done);
+    const int old = atomicMin(s + ra, rb);  // ra > rb
+    if (old == ra) break;
+    ra = uf_find(s, old);                   // ra had been linked meanwhile: carry on from its parent
+    rb = uf_find(s, rb);
+  }
+  const int r = ra < rb ? ra : rb;
+  uf_compress(s, a, r);
+  uf_compress(s, b, r);
+}
+
+// ---- area-carrying variant for the shared-memory kernel: a word is parent | area << 14.  Areas are parked on NAME
+// blocks (phase B) and travel with the links: atomicMin returns the old word, whose area part is re-added to the new
+// parent.  Area left on a name that is no longer a root is collected when the names are flattened (phase D).
+__device__ __forceinline__ int ufa_find(const volatile int* s, int n) {
+  int p = s[n] & CC_IDX_MASK;
+  while (p != n) {
+    n = p;
+    p = s[n] & CC_IDX_MASK;
+  }
+  return n;
+}
+__device__ __forceinline__ void ufa_move_area(int* s, int old_word, int to) {
+  const uint32_t a = (uint32_t)old_word >> CC_IDX_BITS;
+  if (a) atomicAdd(s + to, (int)(a << CC_IDX_BITS));
+}
+__device__ __forceinline__ void ufa_compress(int* s, int n, int r) {
+  while (n > r) {
+    const int p = reinterpret_cast<const volatile int*>(s)[n] & CC_IDX_MASK;
+    if (p == n) break;
+    if (p > r) ufa_move_area(s, atomicMin(s + n, r), r);
+    n = p;
+  }
+}
+__device__ __forceinline__ void ufa_union(int* s, int a, int b) {
+  int ra = ufa_find(s, a), rb = ufa_find(s, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      const int t = ra;
+      ra = rb;
+      rb = t;
+    }
+    const int old = atomicMin(s + ra, rb);  // ra > rb: the word becomes rb (any area bits made it larger than rb)
+    ufa_move_area(s, old, rb);
+    if ((old & CC_IDX_MASK) == ra) break;
+    ra = ufa_find(s, old & CC_IDX_MASK);
+    rb = ufa_find(s, rb);
+  }
+  const int r = ra < rb ? ra : rb;
+  ufa_compress(s, a, r);
+  ufa_compress(s, b, r);
 }
 
 // occupancy bits: 0 = top-left, 1 = top-right, 2 = bottom-left, 3 = bottom-right
@@ -66,103 +125,265 @@ template <bool FILL>
 __device__ __forceinline__ uint32_t load_occ(const void* img, int H, int W, int by, int bx, float) {
   const int r = 2 * by, c = 2 * bx;
   if (FILL) {  // foreground of the hole search = (score <= 0)   (utils/misc.py:322)
-    const float* f = reinterpret_cast<const float*>(img);
-    const float2 t = *reinterpret_cast<const float2*>(f + (size_t)r * W + c);
-    const float2 b = *reinterpret_cast<const float2*>(f + (size_t)(r + 1) * W + c);
-    return (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
+    const float* t = reinterpret_cast<const float*>(img) + (size_t)r * W + c;   // scalar loads: any 4-byte aligned base
+    const float* b = t + W;
+    return (t[0] <= 0.f ? 1u : 0u) | (t[1] <= 0.f ? 2u : 0u) | (b[0] <= 0.f ? 4u : 0u) | (b[1] <= 0.f ? 8u : 0u);
   } else {
-    const uint8_t* u = reinterpret_cast<const uint8_t*>(img);
-    const uint16_t t = *reinterpret_cast<const uint16_t*>(u + (size_t)r * W + c);
-    const uint16_t b = *reinterpret_cast<const uint16_t*>(u + (size_t)(r + 1) * W + c);
-    return ((t & 0xFF) ? 1u : 0u) | ((t >> 8) ? 2u : 0u) | ((b & 0xFF) ? 4u : 0u) | ((b >> 8) ? 8u : 0u);
+    const uint8_t* t = reinterpret_cast<const uint8_t*>(img) + (size_t)r * W + c;  // byte loads: any base address
+    const uint8_t* b = t + W;
+    return (t[0] ? 1u : 0u) | (t[1] ? 2u : 0u) | (b[0] ? 4u : 0u) | (b[1] ? 8u : 0u);
   }
 }
 
+// 4 top + 4 bottom uint8 pixels -> the occupancy bytes of 2 blocks (low 16 bits of the result)
+__device__ __forceinline__ uint32_t occ2_from_u8(uint32_t top, uint32_t bot) {
+  const uint32_t x = (__vcmpne4(top, 0u) & 0x01010101u) | ((__vcmpne4(bot, 0u) & 0x01010101u) << 2);
+  const uint32_t a = (x & 0x5u) | ((x >> 7) & 0xAu);
+  const uint32_t b = ((x >> 16) & 0x5u) | ((x >> 23) & 0xAu);
+  return a | (b << 8);
+}
+
+// One warp-row = 32 consecutive blocks of one block row.  Neighbour occupancies come from two byte loads per lane
+// plus shuffles; only the edge lanes read the adjacent chunk.
+struct RowOcc {
+  uint32_t me, left, up, ul, ur;
+};
+__device__ __forceinline__ RowOcc row_occ(const uint8_t* occ, int BW, int by, int bx, int bi, bool in, int lane) {
+  RowOcc o;
+  o.me = in ? occ[bi] : 0u;
+  o.up = (in && by > 0) ? occ[bi - BW] : 0u;
+  o.left = __shfl_up_sync(0xffffffffu, o.me, 1);
+  o.ul = __shfl_up_sync(0xffffffffu, o.up, 1);
+  o.ur = __shfl_down_sync(0xffffffffu, o.up, 1);
+  if (lane == 0) {
+    o.left = (in && bx > 0) ? occ[bi - 1] : 0u;
+    o.ul = (in && bx > 0 && by > 0) ? occ[bi - BW - 1] : 0u;
+  }
+  if (lane == 31) o.ur = (in && bx + 1 < BW && by > 0) ? occ[bi - BW + 1] : 0u;
+  return o;
+}
+
 // FILL=false: img uint8 -> labels/counts int32.   FILL=true: scores f32 updated in place.
+// Shared memory: one int32 per block (union-find parent; a root's word additionally carries area << 14 once the
+// areas are accumulated) + one occupancy byte per block = 5 B/block, 80 KB at 256 x 256 -> two CTAs per SM, so one
+// image's loads/stores overlap the other's union-find.
 template <bool FILL>
-__global__ void __launch_bounds__(CC_THREADS, 1)
+__global__ void __launch_bounds__(CC_THREADS, 2)
 cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t* counts_all, float* scores_all,
-                int max_area, float fill_value) {
+                int max_area, float fill_value, int vec) {
   extern __shared__ int cc_smem[];
   const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
   int* lab = cc_smem;
-  int* cnt = cc_smem + nb;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + 2 * nb);
+  uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + nb);
   const size_t img_off = (size_t)blockIdx.x * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = CC_THREADS / 32;
   const int chunks = (BW + 31) >> 5;
+  // warp-row tasks in column-strip-major order; each warp owns a contiguous band of rows of one strip and walks it
+  // top-down, which (with path compression) keeps the union-find chains a few hops long
+  const int ntask = BH * chunks, per = (ntask + nwarps - 1) / nwarps;
+  const int t_begin = warp * per, t_end = min(ntask, t_begin + per);
 
+#ifdef CC_TRACE
+  long long tr[6];
+  tr[0] = clock64();
+#define CC_MARK(i) tr[i] = clock64()
+#else
+#define CC_MARK(i)
+#endif
   // A. occupancy
+  if (vec) {
+    if (FILL) {  // 2 x float4 -> 2 blocks
+      const float* f = reinterpret_cast<const float*>(img);
+      const int upr = W >> 2, units = BH * upr;
+#pragma unroll 4
+      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
+        const int by = u / upr, k = u - by * upr;
+        const float4 t = *reinterpret_cast<const float4*>(f + (size_t)(2 * by) * W + 4 * k);
+        const float4 b = *reinterpret_cast<const float4*>(f + (size_t)(2 * by + 1) * W + 4 * k);
+        const uint32_t o0 = (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
+        const uint32_t o1 = (t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u);
+        *reinterpret_cast<uint16_t*>(occ + by * BW + 2 * k) = (uint16_t)(o0 | (o1 << 8));
+      }
+    } else {     // 2 x 16 pixels -> 8 blocks
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
+      const int upr = W >> 4, units = BH * upr;
+#pragma unroll 2
+      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
+        const int by = u / upr, k = u - by * upr;
+        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 16 * k);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 16 * k);
+        uint2 o;
+        o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
+        o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
+        *reinterpret_cast<uint2*>(occ + by * BW + 8 * k) = o;
+      }
+    }
+  } else {
+    for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
+  }
+  __syncthreads();
+  CC_MARK(1);
+  // B. region labelling.  A region = this warp's band of rows within one 32-block column strip, walked top-down with
+  //    the previous row's labels kept in REGISTERS: a run takes the smallest label among the upper blocks it touches
+  //    (segmented min-scan over the run's lanes) or becomes a new root; shared memory sees one store per block.
+  //    Only a run that touches two differently named upper components costs a union-find operation.
+  {
+    constexpr int INF = 0x7fffffff;
+    uint32_t up_me = 0u;
+    int up_lab = INF, acc_name = -1, acc_sum = 0;
+    int chunk = t_begin / BH, by = t_begin - chunk * BH;
+    for (int t = t_begin; t < t_end; ++t, ++by) {
+      if (by == BH) {
+        by = 0;
+        ++chunk;
+      }
+      if (by == 0) {
+        up_me = 0u;
+        up_lab = INF;
+      }
+      const int c0 = chunk << 5, bx = c0 + lane;
+      const bool in = bx < BW;
+      const int bi = by * BW + bx;
+      const uint32_t me = in ? occ[bi] : 0u;
+      uint32_t left = __shfl_up_sync(0xffffffffu, me, 1);
+      uint32_t ulo = __shfl_up_sync(0xffffffffu, up_me, 1), uro = __shfl_down_sync(0xffffffffu, up_me, 1);
+      const int ull = __shfl_up_sync(0xffffffffu, up_lab, 1), url = __shfl_down_sync(0xffffffffu, up_lab, 1);
+      if (lane == 0) left = 0u, ulo = 0u;
+      if (lane == 31) uro = 0u;
+      const int ca = conn_up(me, up_me) ? up_lab : INF, cb = conn_upleft(me, ulo) ? ull : INF,
+                cc = conn_upright(me, uro) ? url : INF;
+      const int cand = min(ca, min(cb, cc));
+      const uint32_t hm = __ballot_sync(0xffffffffu, conn_left(me, left));
+      const uint32_t stops = ~hm | 1u;
+      const int head = 31 - __clz(stops & (0xffffffffu >> (31 - lane)));
+      const uint32_t above = stops & ~(0xffffffffu >> (31 - lane));
+      // smallest candidate of the run.  Usually every candidate in the 32-block row carries the same name (one
+      // component passes through): two warp reductions + a ballot.  Otherwise a segmented min-scan over the runs.
+      const int mn = __reduce_min_sync(0xffffffffu, cand);
+      const int mx = __reduce_max_sync(0xffffffffu, cand == INF ? -1 : cand);
+      int runmin;
+      if (mx == -1 || mx == mn) {
+        const uint32_t run = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << head) - 1u);
+        runmin = (__ballot_sync(0xffffffffu, cand != INF) & run) ? mn : INF;
+      } else {
+        int x = cand;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const int v = __shfl_up_sync(0xffffffffu, x, d);
+          if (lane - d >= head) x = min(x, v);
+        }
+        runmin = __shfl_sync(0xffffffffu, x, above ? __ffs(above) - 2 : 31);
+      }
+      int label = INF;
+      if (me) {
+        label = (runmin == INF) ? (by * BW + c0 + head) : runmin;
+        lab[bi] = label;
+        if (runmin == INF && head == lane) occ[bi] = (uint8_t)(me | CC_NAME);   // this block is a NAME: a tree node others point to
+      }
+      // area of every run goes to its label's word; the runs of this row that share the first run's label are summed
+      // with one warp reduction and carried in registers from row to row (one atomic per label change, not per run)
+      {
+        const uint32_t run = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << lane) - 1u);
+        const uint32_t b0 = __ballot_sync(0xffffffffu, me & 1u), b1 = __ballot_sync(0xffffffffu, me & 2u);
+        const uint32_t b2 = __ballot_sync(0xffffffffu, me & 4u), b3 = __ballot_sync(0xffffffffu, me & 8u);
+        const bool is_head = me && head == lane;
+        const int area = __popc(b0 & run) + __popc(b1 & run) + __popc(b2 & run) + __popc(b3 & run);
+        const uint32_t heads = __ballot_sync(0xffffffffu, is_head);
+        if (heads) {
+          const int n0 = __shfl_sync(0xffffffffu, label, __ffs(heads) - 1);
+          const int total = __reduce_add_sync(0xffffffffu, (is_head && label == n0) ? area : 0);
+          if (n0 == acc_name) {
+            acc_sum += total;
+          } else {
+            __syncwarp();
+            if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
+            acc_name = n0;
+            acc_sum = total;
+          }
+          if (is_head && label != n0) atomicAdd(lab + label, area << CC_IDX_BITS);
+        }
+      }
+      // rare: a run joining differently named components (every candidate of every lane, not just the lane's minimum)
+      if (ca != INF && ca != runmin) ufa_union(lab, ca, runmin);
+      if (cb != INF && cb != runmin && cb != ca) ufa_union(lab, cb, runmin);
+      if (cc != INF && cc != runmin && cc != ca && cc != cb) ufa_union(lab, cc, runmin);
+      up_me = me;
+      up_lab = label;
+    }
+    __syncwarp();
+    if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
+  }
+  __syncthreads();
+  CC_MARK(2);
+  // C. seams between regions (generic lock-free unions; every region is already labelled)
+  //    C1: the first row of each band against the last row of the band above, inside the strip
+  if (t_begin < t_end) {
+    const int chunk = t_begin / BH, by = t_begin - chunk * BH;
+    if (by > 0) {
+      const int c0 = chunk << 5, bx = c0 + lane;
+      const bool in = bx < BW;
+      const int bi = by * BW + bx;
+      const uint32_t me = in ? occ[bi] : 0u, up = in ? occ[bi - BW] : 0u;
+      uint32_t left = __shfl_up_sync(0xffffffffu, me, 1);
+      uint32_t ul = __shfl_up_sync(0xffffffffu, up, 1), ur = __shfl_down_sync(0xffffffffu, up, 1);
+      if (lane == 0) left = 0u, ul = 0u;
+      if (lane == 31) ur = 0u;
+      const bool h = conn_left(me, left);
+      const bool cu = conn_up(me, up);
+      const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
+      const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
+      const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
+      const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
+      if (cu && !cu_redundant) ufa_union(lab, bi, bi - BW);
+      if (cul) ufa_union(lab, bi, bi - BW - 1);
+      if (cur) ufa_union(lab, bi, bi - BW + 1);
+    }
+  }
+  //    C2: strip seams, one lane per row: left edge block of a strip with its left / upper-left neighbour, and the right
+  //    edge block of the strip before it with its upper-right neighbour
+  {
+    const int rg = (BH + 31) >> 5, ns = (chunks - 1) * rg;
+    for (int u = warp; u < ns; u += nwarps) {
+      const int sb = 1 + u / rg, by = ((u - (sb - 1) * rg) << 5) + lane;
+      if (by < BH) {
+        const int bi = by * BW + (sb << 5);
+        const uint32_t me = occ[bi], lf = occ[bi - 1];
+        if (conn_left(me, lf)) ufa_union(lab, bi, bi - 1);
+        if (by > 0) {
+          const uint32_t up = occ[bi - BW], ul = occ[bi - BW - 1];
+          const bool across = conn_left(up, ul);
+          if (conn_upleft(me, ul) && !(conn_up(me, up) && across)) ufa_union(lab, bi, bi - BW - 1);
+          if (conn_upright(lf, up) && !(conn_up(lf, ul) && across)) ufa_union(lab, bi - 1, bi - BW);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  CC_MARK(3);
+  // D. every parent pointer written so far targets a NAME block (a run that started a new label): flatten the names
+  //    (the only loop-y finds left, a few per region) and hand the area parked on a name to its root.  Afterwards
+  //    block -> name -> root is two plain loads and a root's word is root | area << 14.
   for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) {
-    occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
-    cnt[bi] = 0;
-  }
-  __syncthreads();
-  // B. horizontal runs -> star trees
-  for (int t = warp; t < BH * chunks; t += nwarps) {
-    const int by = t / chunks, c0 = (t % chunks) << 5, bx = c0 + lane;
-    const bool in = bx < BW;
-    const int bi = by * BW + bx;
-    const uint32_t me = in ? occ[bi] : 0u;
-    const uint32_t left = (in && bx > 0) ? occ[bi - 1] : 0u;
-    const bool h = conn_left(me, left);
-    const uint32_t hm = __ballot_sync(0xffffffffu, h);
-    if (in) {
-      const uint32_t stops = (~hm | 1u) & (0xffffffffu >> (31 - lane));
-      lab[bi] = by * BW + c0 + (31 - __clz(stops));
+    if (occ[bi] & CC_NAME) {
+      const int root = ufa_find(lab, bi);
+      if (root != bi) {
+        ufa_move_area(lab, lab[bi], root);
+        lab[bi] = root;
+      }
     }
   }
   __syncthreads();
-  // C. unions: chunk seams, up, up-left, up-right
-  for (int t = warp; t < BH * chunks; t += nwarps) {
-    const int by = t / chunks, c0 = (t % chunks) << 5, bx = c0 + lane;
-    const bool in = bx < BW;
-    const int bi = by * BW + bx;
-    const uint32_t me = in ? occ[bi] : 0u;
-    const uint32_t left = (in && bx > 0) ? occ[bi - 1] : 0u;
-    const bool h = conn_left(me, left);
-    uint32_t up = 0, ul = 0, ur = 0;
-    if (in && by > 0) {
-      up = occ[bi - BW];
-      if (bx > 0) ul = occ[bi - BW - 1];
-      if (bx + 1 < BW) ur = occ[bi - BW + 1];
-    }
-    const bool cu = conn_up(me, up);
-    const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
-    const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
-    const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
-    const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
-    if (lane == 0 && h) uf_union(lab, bi, bi - 1);
-    if (cu && !cu_redundant) uf_union(lab, bi, bi - BW);
-    if (cul) uf_union(lab, bi, bi - BW - 1);
-    if (cur) uf_union(lab, bi, bi - BW + 1);
-  }
-  __syncthreads();
-  // D. compression + areas
-  for (int t = warp; t < BH * chunks; t += nwarps) {
-    const int by = t / chunks, c0 = (t % chunks) << 5, bx = c0 + lane;
-    const bool in = bx < BW;
-    const int bi = by * BW + bx;
-    const uint32_t me = in ? occ[bi] : 0u;
-    int root = -1 - lane;  // unique negative key for empty lanes
-    if (me) {
-      root = uf_find(lab, bi);
-      lab[bi] = root;  // benign race: concurrent finds still see a valid ancestor
-    }
-    const uint32_t peers = __match_any_sync(0xffffffffu, root);
-    const int area = __reduce_add_sync(peers, (int)__popc(me));
-    if (me && lane == (__ffs(peers) - 1)) atomicAdd(cnt + root, area);
-  }
-  __syncthreads();
+  CC_MARK(4);
   // E. outputs
   if (FILL) {
     float* sc = scores_all + img_off;
     for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) {
       const uint32_t me = occ[bi];
       if (!me) continue;
-      if (cnt[lab[bi]] > max_area) continue;
+      const int rt = lab[lab[bi] & CC_IDX_MASK] & CC_IDX_MASK;
+      if ((int)((uint32_t)lab[rt] >> CC_IDX_BITS) > max_area) continue;
       const int r = 2 * (bi / BW), c = 2 * (bi % BW);
       if (me & 1u) sc[(size_t)r * W + c] = fill_value;
       if (me & 2u) sc[(size_t)r * W + c + 1] = fill_value;
@@ -173,27 +394,34 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
     int32_t* labels = labels_all + img_off;
     int32_t* counts = counts_all + img_off;
     if ((W & 3) == 0) {
-      const int quads = (H * W) >> 2, qpr = W >> 2;
-      for (int qd = threadIdx.x; qd < quads; qd += CC_THREADS) {
-        const int r = qd / qpr, c = (qd % qpr) << 2;
+      // root block index -> label value needs root / BW: multiply-high by ceil(2^32 / BW) is exact for root < 2^14
+      const uint32_t magic = BW > 1 ? (uint32_t)((0x100000000ull + BW - 1) / BW) : 0u;
+      const int segs = (W + 127) >> 7;
+#pragma unroll 2
+      for (int task = warp; task < H * segs; task += nwarps) {
+        const int r = task / segs, c = ((task - r * segs) << 7) + (lane << 2);
+        if (c >= W) continue;
         const int b0 = (r >> 1) * BW + (c >> 1);
         const int sh = (r & 1) << 1;
-        const uint32_t o0 = occ[b0] >> sh, o1 = occ[b0 + 1] >> sh;
+        const uint32_t oo = *reinterpret_cast<const uint16_t*>(occ + b0);
+        const uint32_t o0 = (oo & 0xFFu) >> sh, o1 = (oo >> 8) >> sh;
         int l0 = 0, l1 = 0, n0 = 0, n1 = 0;
         if (o0 & 3u) {
-          const int rt = lab[b0];
-          l0 = (rt / BW) * 2 * W + (rt % BW) * 2 + 1;
-          n0 = cnt[rt];
+          const int rt = lab[lab[b0] & CC_IDX_MASK] & CC_IDX_MASK;
+          const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
+          l0 = q * 2 * W + (rt - q * BW) * 2 + 1;
+          n0 = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
         }
         if (o1 & 3u) {
-          const int rt = lab[b0 + 1];
-          l1 = (rt / BW) * 2 * W + (rt % BW) * 2 + 1;
-          n1 = cnt[rt];
+          const int rt = lab[lab[b0 + 1] & CC_IDX_MASK] & CC_IDX_MASK;
+          const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
+          l1 = q * 2 * W + (rt - q * BW) * 2 + 1;
+          n1 = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
         }
         const int4 lv = make_int4((o0 & 1u) ? l0 : 0, (o0 & 2u) ? l0 : 0, (o1 & 1u) ? l1 : 0, (o1 & 2u) ? l1 : 0);
         const int4 cv = make_int4((o0 & 1u) ? n0 : 0, (o0 & 2u) ? n0 : 0, (o1 & 1u) ? n1 : 0, (o1 & 2u) ? n1 : 0);
-        *reinterpret_cast<int4*>(labels + (size_t)r * W + c) = lv;
-        *reinterpret_cast<int4*>(counts + (size_t)r * W + c) = cv;
+        __stcs(reinterpret_cast<int4*>(labels + (size_t)r * W + c), lv);
+        __stcs(reinterpret_cast<int4*>(counts + (size_t)r * W + c), cv);
       }
     } else {
       for (int px = threadIdx.x; px < H * W; px += CC_THREADS) {
@@ -202,15 +430,22 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
         const bool fg = (occ[b0] >> (((r & 1) << 1) | (c & 1))) & 1u;
         int l = 0, n = 0;
         if (fg) {
-          const int rt = lab[b0];
+          const int rt = lab[lab[b0] & CC_IDX_MASK] & CC_IDX_MASK;
           l = (rt / BW) * 2 * W + (rt % BW) * 2 + 1;
-          n = cnt[rt];
+          n = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
         }
         labels[px] = l;
         counts[px] = n;
       }
     }
   }
+#ifdef CC_TRACE
+  __syncthreads();
+  CC_MARK(5);
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    printf("cc_small<%d> cta %d: A %lld B %lld C %lld D %lld E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
+           tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4]);
+#endif
 }
 
 // ------------------------------------------------------------------ tiled path (images larger than 256 x 256)
@@ -367,7 +602,7 @@ __global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, in
 bool small_ok(int h, int w) { return (h / 2) * (w / 2) <= CC_MAX_BLOCKS; }
 size_t small_smem(int h, int w) {
   const size_t nb = (size_t)(h / 2) * (w / 2);
-  return nb * 9;
+  return (nb * 5 + 15) & ~(size_t)15;
 }
 
 template <bool FILL>
@@ -381,11 +616,14 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     static bool attr[2] = {false, false};
     if (!attr[FILL]) {
       VLS_CUDA(cudaFuncSetAttribute(cc_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    CC_MAX_BLOCKS * 9));
+                                    CC_MAX_BLOCKS * 5));
       attr[FILL] = true;
     }
+    // 128-bit loads need 16-byte aligned rows: W % 16 (uint8) / W % 4 (f32) and an aligned base
+    const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0)
+                         : ((w % 16) == 0 && ((uintptr_t)img % 16) == 0);
     cc_small_kernel<FILL><<<n, CC_THREADS, small_smem(h, w), stream>>>(img, h, w, labels, counts, scores, max_area,
-                                                                        fill_value);
+                                                                        fill_value, vec);
     VLS_POST_LAUNCH(1);
     return 0;
   }
