@@ -52,13 +52,13 @@ while True:
     r = N.nvmlDeviceGetCurrentClocksThrottleReasons(h)
     f = ["Active" if r & b else "Not Active" for _, b in bits]
     print(f"{time.time()!r}, {mhz}, {mx}, " + ", ".join(f), flush=True)
-    time.sleep(0.004)
+    time.sleep(float(sys.argv[2]))
 """
 
 
 class ClockSampler:
     """SM clock / throttle reasons sampled DURING the timed window by a separate process (NVML through pynvml, one
-    light query every ~4 ms; `nvidia-smi -lms` as the fallback).  A child process, not a thread: a Python sampler
+    light query every 25 ms -- at 4 ms the queries themselves stalled about one 16 MB H2D step per run by 6-20 ms; `nvidia-smi -lms` as the fallback).  A child process, not a thread: a Python sampler
     thread would contend for the GIL with the loop that enqueues the frames, and a polling `nvidia-smi` takes driver
     locks for milliseconds, which showed up as 3-20 ms stalls of individual timed steps."""
 
@@ -69,7 +69,7 @@ class ClockSampler:
         try:
             import pynvml  # noqa: F401
 
-            self.cmd, self.stamped = [sys.executable, "-c", NVML_SAMPLER, str(index)], True
+            self.cmd, self.stamped = [sys.executable, "-c", NVML_SAMPLER, str(index), os.environ.get("VLS_BENCH_SAMPLE_S", "0.025")], True
         except ImportError:
             self.cmd = ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(index)]
             self.stamped = False
@@ -177,9 +177,11 @@ def run_ours(args):
         done = [torch.cuda.Event(), torch.cuda.Event()]
         checksum = 0
 
-        def read_back(m, slot):
-            host[slot].copy_((m > 0).to(torch.uint8), non_blocking=True)
+        def read_back(m, slot):   # with d2h the predictor runs in output_mode "binary": m is already the uint8 mask
+            host[slot].copy_(m, non_blocking=True)
             done[slot].record()
+
+        predictor.output_mode = "binary" if d2h else "logits"
 
         with sampler as clocks:
             state = predictor.init_state(source)
@@ -214,6 +216,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             clocks.mark_stop()
             gc.enable()
+            predictor.output_mode = "logits"
         launches = lib.vls_launch_count() - launches0
         per_step = [s.elapsed_time(e) for s, e in zip(starts, stops)]
         ms = sum(per_step)
@@ -247,7 +250,8 @@ def run_ours(args):
         "config": {"workload": WORKLOAD, "objects_per_gpu": 1, "clips_per_gpu": 1, "ramp_frames": RAMP,
                    "l2": "flushed between timed steps (256 MiB memset, outside the per-step events)",
                    "parallelism": f"{world} independent replica(s), sharded by clip, no collective on the path",
-                   "execution": "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay"},
+                   "execution": "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay",
+                   "e2e_path": "pinned host features -> double-buffered H2D -> propagate_in_video(output_mode='binary': fused resize+threshold) -> uint8 mask D2H into pinned memory every step, consumer pipelined by one frame"},
         "clocks": clocks, "gpu_launches": int(launches),
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes_per_frame),
                 "d2h_bytes_per_step": int(out_bytes)},
@@ -383,7 +387,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

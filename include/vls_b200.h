@@ -91,6 +91,13 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
  * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */
 int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, vls_stream_t stream);
 
+/* Fused output stage: the same bilinear resize followed by `> thresh`, without materialising the f32 [H,W] logits
+ * (sam2_video_predictor.py:404-424 + the caller's threshold, e.g. llava/inference/utils.py:71-85).
+ * out_u8  : [n][H][W] uint8 0/1, or NULL.   out_bits: [n][H][ceil(W/8)] bytes, first pixel = most significant bit
+ * (numpy.packbits order), or NULL.  At least one output must be given.  Bit-identical to (vls_resize_bilinear > thresh). */
+int vls_resize_binarize(const float* in, int n, int h, int w, int H, int W, float thresh, uint8_t* out_u8, uint8_t* out_bits,
+                        vls_stream_t stream);
+
 /* out[r][:n] = act(x[r][:k] . W[n][k]^T + bias), x/out f32, W bf16 row-major, k % 8 == 0;
  * act: 0 none, 1 ReLU, 3 sigmoid.  Warp-per-output kernel for the handful-of-rows linears
  * (object-pointer projections, sam2_base.py:393,633). */

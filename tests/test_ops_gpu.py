@@ -179,6 +179,26 @@ def test_cc_structured_and_errors(dev):
         assert (got.cpu() != s).any()
 
 
+@pytest.mark.parametrize("shape,size", [((3, 1, 256, 256), (1024, 1024)), ((2, 2, 64, 48), (100, 77)), ((1, 1, 256, 256), (720, 1284))])
+def test_resize_binarize_matches_interpolate(dev, shape, size):
+    """Fused output stage: (bilinear(x) > t) as bytes and as packed bits == torch's interpolate + threshold, except on
+    pixels whose interpolated logit is within float rounding of the threshold (none expected at these seeds)."""
+    from video_llava_seg_b200 import ops
+
+    x = _rand(shape, dev, 77) * 3
+    ref = torch.nn.functional.interpolate(x, size=size, mode="bilinear", align_corners=False)
+    ours = ops.resize_bilinear(x, size)
+    for t in (0.0, 0.5):
+        u8 = ops.resize_binarize(x, size, t)
+        bits = ops.resize_binarize(x, size, t, packed=True)
+        assert u8.dtype == torch.uint8 and u8.shape == ref.shape
+        assert torch.equal(u8, (ours > t).to(torch.uint8)), "must agree bit for bit with the unfused kernels"
+        unsure = (ref - t).abs() < 1e-5
+        assert ((u8 == (ref > t).to(torch.uint8)) | unsure).all()
+        import numpy as np
+        assert torch.equal(bits.cpu(), torch.from_numpy(np.packbits(u8.cpu().numpy(), axis=-1)))
+
+
 def test_cc_matches_reference_kernel(dev):
     """Pin: the reference's own connected_components.cu (compiled unmodified into oracle/_ref/ in the build
     container by oracle/build_ref.py) against our kernel and the C oracle, on the same masks."""

@@ -93,6 +93,53 @@ def test_propagation_matches_reference(predictor, name, seed, T, B):
     print(f"{name} worst: {worst}")
 
 
+def test_remove_object_keeps_the_other_track(predictor):
+    """remove_object (sam2_video_predictor.py:1042-1153): after dropping object 1 of a two-object session the
+    remaining object's stored frames are the reference's object-2 rows, re-propagation reproduces the reference's
+    object-2 track (objects are independent: non_overlap_masks is off), and the id maps are re-packed."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    gold = np.load(os.path.join(GOLD, "clip_b2_t4.npz"))
+    T = 4
+    clip = synth.SyntheticClip(2, T)
+    state = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+    prompt = clip.point_prompt(2)
+    for o in range(2):
+        predictor.add_new_points_or_box(state, 0, o + 1, points=prompt["point_coords"][o].tolist(), labels=[1])
+    for _ in predictor.propagate_in_video(state):
+        pass
+    with pytest.raises(RuntimeError):
+        predictor.remove_object(state, 77, strict=True)
+    assert predictor.remove_object(state, 77) == ([1, 2], [])
+    ids, updated = predictor.remove_object(state, 1)
+    assert ids == [2] and state["obj_id_to_idx"] == {2: 0} and state["obj_idx_to_id"] == {0: 2}
+    assert [f for f, _ in updated] == [0] and updated[0][1].shape == (1, 1, 1024, 1024)
+    assert set(state["output_dict_per_obj"]) == {0} and set(state["point_inputs_per_obj"]) == {0}
+
+    def check(t, out):
+        ref_bits = np.unpackbits(gold[f"maskbits_{t}"], axis=1).reshape(2, 1, 256, 256).astype(bool)[1:2]
+        got = out["pred_masks"].float().cpu()
+        assert got.shape == (1, 1, 256, 256) and out["obj_ptr"].shape == (1, 256)
+        assert out["maskmem_features"].shape[0] == 1 and out["object_score_logits"].shape == (1, 1)
+        iou = (ref_bits & (got > 0).numpy()).sum() / max((ref_bits | (got > 0).numpy()).sum(), 1)
+        assert iou >= 0.995, (t, iou)
+        assert (out["obj_ptr"].cpu() - torch.from_numpy(gold[f"obj_ptr_{t}"])[1:2]).abs().max().item() < 5e-2
+
+    for t in range(T):       # sliced storage
+        check(t, state["output_dict"]["cond_frame_outputs" if t == 0 else "non_cond_frame_outputs"][t])
+    seen = []
+    for fi, ids, video_res in predictor.propagate_in_video(state):   # re-propagation with one object
+        assert ids == [2] and video_res.shape == (1, 1, 1024, 1024)
+        seen.append(fi)
+        check(fi, state["output_dict"]["cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"][fi])
+    assert seen == list(range(T))
+    ids, updated = predictor.remove_object(state, 2)                  # last object: the session is reset
+    assert ids == [] and updated == [] and not state["output_dict"]["cond_frame_outputs"]
+    with pytest.raises(RuntimeError):
+        type(predictor).from_pretrained("facebook/sam2.1-hiera-base-plus")
+
+
 def test_api_errors(predictor):
     from video_llava_seg_b200 import synth
     from video_llava_seg_b200.features import FeatureClip
@@ -220,3 +267,43 @@ def test_cuda_graph_steady_state_matches_eager(predictor):
                 assert d.max() < tol, (t, name, d.max().item())
         if t < 16:
             assert torch.equal(eager[t][0], graphed[t][0]), "ramp frames take the same eager path"
+
+
+@pytest.mark.parametrize("mode", ["binary", "bits"])
+def test_fused_binary_output_stage(predictor, mode):
+    """f-3: output_mode 'binary' / 'bits' (fused up-sampling + threshold, f32 video-resolution logits never written)
+    must equal (video_res_logits > 0) of the default mode bit for bit, on the eager and on the CUDA-graph frames."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 20
+    clip = synth.SyntheticClip(13, T)
+    src = FeatureClip(lambda t: clip.frame(t, 1), T, video_height=720, video_width=1284, resident_device="cuda:0")
+    point = clip.point_prompt(1)["point_coords"][0].tolist()
+
+    def run(m):
+        predictor.output_mode = m
+        st = predictor.init_state(src)
+        _, _, first = predictor.add_new_points_or_box(st, 0, 1, points=point, labels=[1], normalize_coords=False)
+        outs = [v.cpu() for _, _, v in predictor.propagate_in_video(st)]
+        return first.cpu(), outs, st
+
+    try:
+        ref_first, ref, _ = run("logits")
+        got_first, got, st = run(mode)
+    finally:
+        predictor.output_mode = "logits"
+    assert st["steady_graph"] is not None and st["steady_graph"].graph is not None, "the graph path was not taken"
+    assert ref[0].shape == (1, 1, 720, 1284) and ref[0].dtype == torch.float32
+    for r, g in [(ref_first, got_first)] + list(zip(ref, got)):
+        want = (r > 0).to(torch.uint8)
+        if mode == "bits":
+            assert g.shape == (1, 1, 720, (1284 + 7) // 8) and g.dtype == torch.uint8
+            want = torch.from_numpy(np.packbits(want.numpy(), axis=-1))
+        assert torch.equal(g, want)
+    with pytest.raises(ValueError):
+        predictor.output_mode = "rle"
+        try:
+            predictor.add_new_points_or_box(predictor.init_state(src), 0, 1, points=point, labels=[1], normalize_coords=False)
+        finally:
+            predictor.output_mode = "logits"

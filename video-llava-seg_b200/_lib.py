@@ -66,6 +66,8 @@ def _declare(lib):
 
 
 def _declare_modules(lib):
+    lib.vls_resize_binarize.restype = c_int
+    lib.vls_resize_binarize.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.vls_resize_bilinear.restype = c_int
     lib.vls_resize_bilinear.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
     lib.vls_dwconv7_ln.restype = c_int

@@ -80,6 +80,12 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
   return launch_attention(a, (cudaStream_t)stream);
 }
 
+int vls_resize_binarize(const float* in, int n, int h, int w, int H, int W, float thresh, uint8_t* out_u8, uint8_t* out_bits,
+                        vls_stream_t stream) {
+  VLS_REQUIRE(n == 0 || in, "resize_binarize: null pointer");
+  return launch_resize_binarize(in, n, h, w, H, W, thresh, out_u8, out_bits, (cudaStream_t)stream);
+}
+
 int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, vls_stream_t stream) {
   VLS_REQUIRE(n == 0 || (in && out), "resize: null pointer");
   return launch_resize_bilinear(in, n, h, w, out, H, W, (cudaStream_t)stream);

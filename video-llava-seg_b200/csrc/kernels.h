@@ -125,5 +125,7 @@ int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, con
 
 // ---------------------------------------------------------------- resize (resize.cu)
 int launch_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, cudaStream_t stream);
+int launch_resize_binarize(const float* in, int n, int h, int w, int H, int W, float thresh, uint8_t* out_u8,
+                           uint8_t* out_bits, cudaStream_t stream);
 
 }  // namespace vls

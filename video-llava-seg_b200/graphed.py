@@ -38,6 +38,7 @@ class SteadyStateGraph:
         self.k = m.hidden_dim // m.mem_dim               # 4 tokens per pointer
         self.Nk = self.n_mem * self.HW + self.n_ptr * self.k
         self.cond_idx = next(iter(state["output_dict"]["cond_frame_outputs"]))
+        self.output_mode = model.output_mode
         self.graph = None
         self.next_frame = None
         self._side = torch.cuda.Stream(device=self.dev)
@@ -136,7 +137,7 @@ class SteadyStateGraph:
         side.wait_stream(main)
         with torch.cuda.stream(side):
             pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
-            video = pred if tuple(pred.shape[-2:]) == self.hw else ops.resize_bilinear(pred, self.hw)
+            video = m._video_res_output(pred, self.hw)
         nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
         main.wait_stream(side)
         # bank shift for the next frame: memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
@@ -176,6 +177,8 @@ class SteadyStateGraph:
 
     def valid(self):
         """False once weights were re-packed / moved (the captured pointers would be stale)."""
+        if self.output_mode != self.model.output_mode:
+            return False                                   # the output stage is part of the captured graph
         return self.graph is None or self._sig == tuple(id(o) for o in self._signature_objects())
 
     # ------------------------------------------------------------------ per frame

@@ -77,6 +77,20 @@ def resize_bilinear(x, size):
     return out
 
 
+def resize_binarize(x, size, thresh=0.0, packed=False):
+    """(F.interpolate(x, size, mode="bilinear", align_corners=False) > thresh) in one pass for f32 [N,C,h,w], without
+    the f32 full-resolution intermediate.  Returns uint8 [N,C,H,W] (0/1), or with packed=True the numpy.packbits
+    layout uint8 [N,C,H,ceil(W/8)] (first pixel = most significant bit)."""
+    _lib.require_cuda(x)
+    x = x.float().contiguous()
+    n, c, h, w = x.shape
+    H, W = int(size[0]), int(size[1])
+    out = torch.empty((n, c, H, (W + 7) // 8 if packed else W), device=x.device, dtype=torch.uint8)
+    check(lib().vls_resize_binarize(ptr(x), n * c, h, w, H, W, float(thresh), None if packed else ptr(out),
+                                    ptr(out) if packed else None, stream()), "vls_resize_binarize")
+    return out
+
+
 def linear_f32(x, w_bf16, bias=None, act=None):
     """Small-row linear: x f32 [R,K], w bf16 [N,K] -> f32 [R,N]."""
     _lib.require_cuda(x, w_bf16)

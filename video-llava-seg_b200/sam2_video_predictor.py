@@ -41,6 +41,12 @@ class SAM2VideoPredictor(SAM2Base):
         self.add_all_frames_to_correct_as_cond = add_all_frames_to_correct_as_cond
         # replay the steady-state frame as one CUDA graph (graphed.py); set to False to force the eager path
         self.use_cuda_graph = True
+        # what propagate_in_video / add_new_* yield as `video_res_masks`:
+        #   "logits" f32 [B,1,Hv,Wv] scores, as the reference (sam2_video_predictor.py:404-424)
+        #   "binary" uint8 0/1 [B,1,Hv,Wv] = (scores > 0), "bits" the same bit-packed [B,1,Hv,ceil(Wv/8)] (np.packbits
+        #   order): the fused resize+threshold output stage; the f32 video-resolution logits are
+        #   never written.  Not available with non_overlap_masks (which needs the scores of every object).
+        self.output_mode = "logits"
 
     # ------------------------------------------------------------------ session
     @torch.inference_mode()
@@ -194,10 +200,19 @@ class SAM2VideoPredictor(SAM2Base):
         """Resize scores to the video resolution (sam2_video_predictor.py:404-424) with the resize kernel."""
         any_res_masks = any_res_masks.to(st["device"], non_blocking=True)
         hw = (st["video_height"], st["video_width"])
-        video_res = any_res_masks if tuple(any_res_masks.shape[-2:]) == hw else ops.resize_bilinear(any_res_masks, hw)
+        return any_res_masks, self._video_res_output(any_res_masks, hw)
+
+    def _video_res_output(self, masks, hw):
+        if self.output_mode != "logits":
+            if self.output_mode not in ("binary", "bits"):
+                raise ValueError(f"output_mode must be 'logits', 'binary' or 'bits', got {self.output_mode!r}")
+            if self.non_overlap_masks:
+                raise ValueError("output_mode='binary'/'bits' cannot be combined with non_overlap_masks")
+            return ops.resize_binarize(masks, hw, 0.0, packed=self.output_mode == "bits")
+        video_res = masks if tuple(masks.shape[-2:]) == hw else ops.resize_bilinear(masks, hw)
         if self.non_overlap_masks:
             video_res = self._apply_non_overlapping_constraints(video_res)
-        return any_res_masks, video_res
+        return video_res
 
     def _consolidate_temp_output_across_obj(self, st, frame_idx, is_cond, run_mem_encoder,
                                             consolidate_at_video_res=False):
@@ -388,6 +403,64 @@ class SAM2VideoPredictor(SAM2Base):
                                                        consolidate_at_video_res=True)
         _, video_res = self._get_orig_video_res_output(st, out["pred_masks_video_res"])
         return frame_idx, st["obj_ids"], video_res
+
+    @classmethod
+    def from_pretrained(cls, model_id, **kwargs):
+        """sam2_video_predictor.py:33-43 downloads a checkpoint from the Hugging Face hub; this package is offline
+        by design: build with build_sam.build_sam2_video_predictor(config, state_dict_or_checkpoint_path)."""
+        raise RuntimeError(f"from_pretrained({model_id!r}) needs network access; load a local checkpoint with "
+                           "video_llava_seg_b200.build_sam.build_sam2_video_predictor instead")
+
+    @torch.inference_mode()
+    def remove_object(self, inference_state, obj_id, strict=False, need_output=True):
+        """Drop one tracked object (sam2_video_predictor.py:1042-1153): its prompts are cleared (which may demote
+        conditioning frames), the object indices are re-packed, and every stored frame keeps only the remaining
+        objects' rows.  Returns (remaining obj_ids, [(frame_idx, video_res_masks)] for the frames it had inputs on)."""
+        st = inference_state
+        rm = st["obj_id_to_idx"].get(obj_id)
+        updated = []
+        if rm is None:
+            if strict:
+                raise RuntimeError(f"Cannot remove object id {obj_id} as it doesn't exist. "
+                                   f"All existing object ids: {st['obj_ids']}.")
+            return st["obj_ids"], updated
+        if len(st["obj_id_to_idx"]) == 1:
+            self.reset_state(st)
+            return st["obj_ids"], updated
+        st["steady_graph"] = None                     # the captured graph is specialised on the object count
+        input_frames = set(st["point_inputs_per_obj"][rm]) | set(st["mask_inputs_per_obj"][rm])
+        for f in input_frames:
+            self.clear_all_prompts_in_frame(st, f, obj_id, need_output=False)
+        old_ids = list(st["obj_ids"])
+        keep = [i for i in range(len(old_ids)) if i != rm]
+        new_ids = [old_ids[i] for i in keep]
+        remap = {old: new for new, old in enumerate(keep)}
+        st["obj_id_to_idx"] = {oid: i for i, oid in enumerate(new_ids)}
+        st["obj_idx_to_id"] = {i: oid for i, oid in enumerate(new_ids)}
+        st["obj_ids"] = new_ids
+        for name in ("point_inputs_per_obj", "mask_inputs_per_obj", "output_dict_per_obj", "temp_output_dict_per_obj"):
+            box = st[name]
+            moved = {remap[k]: v for k, v in box.items() if k in remap}
+            box.clear()
+            box.update(moved)
+        for key in ("cond_frame_outputs", "non_cond_frame_outputs"):
+            for f, out in st["output_dict"][key].items():
+                for field in ("maskmem_features", "maskmem_rows", "pred_masks", "obj_ptr", "object_score_logits"):
+                    if out.get(field) is not None:
+                        out[field] = out[field][keep]
+                if out.get("maskmem_pos_enc") is not None:
+                    out["maskmem_pos_enc"] = self._get_maskmem_pos_enc(st, {"maskmem_pos_enc": [
+                        x[keep] if x.shape[0] == len(old_ids) else x for x in out["maskmem_pos_enc"]]})
+                self._add_output_per_object(st, f, out, key)
+        if need_output:
+            tmp_all = st["temp_output_dict_per_obj"]
+            for f in sorted(input_frames):
+                is_cond = any(f in t["cond_frame_outputs"] for t in tmp_all.values())
+                out = self._consolidate_temp_output_across_obj(st, f, is_cond=is_cond, run_mem_encoder=False,
+                                                               consolidate_at_video_res=True)
+                _, video_res = self._get_orig_video_res_output(st, out["pred_masks_video_res"])
+                updated.append((f, video_res))
+        return st["obj_ids"], updated
 
     @torch.inference_mode()
     def reset_state(self, inference_state):
