@@ -40,7 +40,10 @@ long long vls_launch_count(void);
  * meaning "kernels of this library executed" (bench.py's `gpu_launches`). */
 void vls_launch_count_add(long long n);
 /* Performance knobs (results are identical for every setting).  "attn_cluster": 1 = each CTA of the attention
- * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each. */
+ * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each.
+ * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
+ * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
+ * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
 int vls_set_tuning(const char* key, int value);
 /* Developer aid: when non-NULL, CTA (0,0,0) of every attention launch writes clock64() stamps of its producer /
  * MMA / softmax roles for the first 64 key tiles into this device buffer of 3*64*8 int64 (tools/trace_attention.py). */

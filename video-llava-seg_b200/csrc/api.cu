@@ -21,6 +21,10 @@ int vls_set_tuning(const char* key, int value) {
     g_attn_cluster = value;
     return 0;
   }
+  if (std::string(key) == "pdl") {   // programmatic dependent launch on/off (host.h)
+    pdl_set(value != 0);
+    return 0;
+  }
   set_error("set_tuning: unknown key '%s'", key);
   return 1;
 }

@@ -119,6 +119,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (CL > 1) cluster_sync_all();  // the peer's barriers must be initialised before any multicast can signal them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_enter();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -351,6 +352,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 // Merge KV-split partials: one warp per query row, lane owns 8 channels.
 __global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
                                     int splits, bf16* __restrict__ O, long long ldo, long long o_bstride) {
+  pdl_enter();
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (gw >= (long long)B * Nq) return;
   const int lane = threadIdx.x & 31;
@@ -425,10 +427,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
   prof_begin(slot, stream);
   if (cl > 1) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2>, tmQ, tmK, tmV, p));
@@ -438,8 +442,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (a.splits > 1) {
     const long long rows = (long long)a.B * a.Nq;
     const int wpb = 8;
-    attn_combine_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-        a.part_o, a.part_ml, a.B, a.Nq, a.splits, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride);
+    VLS_CUDA(launch_k(attn_combine_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream,  a.part_o, a.part_ml, a.B, a.Nq, a.splits, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
     VLS_POST_LAUNCH(1);
   }
   return 0;

@@ -171,6 +171,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(CC_THREADS, 2)
 cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t* counts_all, float* scores_all,
                 int max_area, float fill_value, int vec) {
+  pdl_enter();
   extern __shared__ int cc_smem[];
   const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
   int* lab = cc_smem;
@@ -462,6 +463,7 @@ constexpr int TBH = 32, TBW = 64, T_THREADS = 256;
 template <bool FILL>
 __global__ void __launch_bounds__(T_THREADS)
 cc_t_label(const void* img_all, const float* scores_all, int H, int W, int32_t* forest_all, uint8_t* occ_all) {
+  pdl_enter();
   __shared__ int lab[TBH * TBW];
   __shared__ uint8_t occ[TBH * TBW];
   const int BH = H >> 1, BW = W >> 1;
@@ -517,6 +519,7 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int32_t* 
 }
 
 __global__ void cc_t_border(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all) {
+  pdl_enter();
   const int BH = H >> 1, BW = W >> 1;
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
   const int per_tile = TBW + 2 * TBH;  // top row, left column, right column
@@ -549,6 +552,7 @@ __global__ void cc_t_border(const uint8_t* __restrict__ occ_all, int H, int W, i
 }
 
 __global__ void cc_t_count(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all, int32_t* area_all) {
+  pdl_enter();
   const int BW = W >> 1, BH = H >> 1;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   const bool in = bx < BW && by < BH;
@@ -569,6 +573,7 @@ template <bool FILL>
 __global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* labels_all,
                            const int32_t* __restrict__ area_all, int32_t* counts_all, float* scores_all, int max_area,
                            float fill_value) {
+  pdl_enter();
   const int BW = W >> 1, BH = H >> 1;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= BW || by >= BH) return;
@@ -622,8 +627,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     // 128-bit loads need 16-byte aligned rows: W % 16 (uint8) / W % 4 (f32) and an aligned base
     const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0)
                          : ((w % 16) == 0 && ((uintptr_t)img % 16) == 0);
-    cc_small_kernel<FILL><<<n, CC_THREADS, small_smem(h, w), stream>>>(img, h, w, labels, counts, scores, max_area,
-                                                                        fill_value, vec);
+    VLS_CUDA(launch_k(cc_small_kernel<FILL>, dim3(n), dim3(CC_THREADS), small_smem(h, w), stream, img, h, w, labels, counts, scores, max_area, fill_value, vec));
     VLS_POST_LAUNCH(1);
     return 0;
   }
@@ -637,12 +641,12 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   VLS_CUDA(cudaMemsetAsync(area, 0, px * 4, stream));
   const int BH = h / 2, BW = w / 2;
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
-  cc_t_label<FILL><<<dim3(tiles_x, tiles_y, n), T_THREADS, 0, stream>>>(img, scores, h, w, forest, occ);
+  VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(dim3(tiles_x, tiles_y, n)), dim3(T_THREADS), 0, stream, img, scores, h, w, forest, occ));
   const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
-  cc_t_border<<<dim3((unsigned)((border + 255) / 256), 1, n), 256, 0, stream>>>(occ, h, w, forest);
+  VLS_CUDA(launch_k(cc_t_border, dim3(dim3((unsigned)((border + 255) / 256), 1, n)), dim3(256), 0, stream, occ, h, w, forest));
   dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, n);
-  cc_t_count<<<grd, blk, 0, stream>>>(occ, h, w, forest, area);
-  cc_t_final<FILL><<<grd, blk, 0, stream>>>(occ, h, w, forest, area, counts, scores, max_area, fill_value);
+  VLS_CUDA(launch_k(cc_t_count, dim3(grd), dim3(blk), 0, stream, occ, h, w, forest, area));
+  VLS_CUDA(launch_k(cc_t_final<FILL>, dim3(grd), dim3(blk), 0, stream, occ, h, w, forest, area, counts, scores, max_area, fill_value));
   VLS_POST_LAUNCH(4);
   return 0;
 }

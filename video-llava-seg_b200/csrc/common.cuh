@@ -21,6 +21,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 }
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31; }
 
+// First statement of EVERY kernel (see launch_k in host.h): block until the grids this launch depends on have completed
+// and their writes are visible, then let the next launch in the stream be scheduled behind this one.  Both are no-ops
+// for a launch without the programmatic-serialisation attribute.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

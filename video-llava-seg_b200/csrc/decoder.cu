@@ -14,6 +14,7 @@ namespace {
 // q,k,v: f32 [B][Nt][256]; out f32 [B][Nt][256].  block = (head, b), one warp per query row.
 __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k,
                                      const float* __restrict__ v, int Nt, float* __restrict__ out) {
+  pdl_enter();
   const int h = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
@@ -45,6 +46,7 @@ __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* _
 __global__ void __launch_bounds__(256)
 t2i_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, long long ld, long long kv_sb, int koff,
                 int voff, int Nt, int T, float* __restrict__ out) {
+  pdl_enter();
   const int i = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ float red[8][18];
@@ -110,6 +112,7 @@ t2i_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, long l
 __global__ void __launch_bounds__(256)
 i2t_attn_kernel(const bf16* __restrict__ qrows, long long ld, long long q_sb, int qoff, const float* __restrict__ ktok,
                 const float* __restrict__ vtok, int Nt, int T, bf16* __restrict__ out) {
+  pdl_enter();
   extern __shared__ float sm_i2t[];
   float* sk = sm_i2t;
   float* sv = sm_i2t + Nt * 128;
@@ -161,6 +164,7 @@ i2t_attn_kernel(const bf16* __restrict__ qrows, long long ld, long long q_sb, in
 __global__ void __launch_bounds__(256)
 up1_post_kernel(const float* __restrict__ g, const void* __restrict__ feat, int feat_bf16, long long feat_sb, int h, int w,
                 const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
+  pdl_enter();
   __shared__ float tile[64][33];
   const int b = blockIdx.z, Y = blockIdx.y, X0 = blockIdx.x * 32;
   const int W2 = 2 * w, H2 = 2 * h;
@@ -204,6 +208,7 @@ __global__ void __launch_bounds__(128)
 up2_masks_kernel(const bf16* __restrict__ u, const float* __restrict__ w2t, const float* __restrict__ bias,
                  const void* __restrict__ feat, int feat_bf16, long long feat_sb, const float* __restrict__ hyper, int h2,
                  int w2, float* __restrict__ masks) {
+  pdl_enter();
   extern __shared__ float sm_up2[];
   float* sw = sm_up2;                 // [4 pos][64 ci][32 co]
   float* su = sw + 4 * 32 * 64;       // [64 ci][33]
@@ -273,6 +278,7 @@ __global__ void select_best_kernel(const float* __restrict__ masks, const float*
                                    int multimask, int HW, float* __restrict__ low_res, float* __restrict__ tok_sel,
                                    int* __restrict__ best_idx, float* __restrict__ is_obj_out,
                                    float* __restrict__ occluded_out, float no_obj_score) {
+  pdl_enter();
   const int b = blockIdx.y;
   int best = 0;
   if (multimask) {
@@ -305,6 +311,7 @@ __global__ void select_best_kernel(const float* __restrict__ masks, const float*
 // obj_ptr = is_obj ? ptr : no_obj_ptr   (sam2_base.py:394-403 with fixed_no_obj_ptr, hard gate)
 __global__ void gate_ptr_kernel(float* __restrict__ ptr, const float* __restrict__ is_obj,
                                 const float* __restrict__ no_obj_ptr, int B) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * 256) return;
   const float lam = is_obj[i / 256];
@@ -315,15 +322,14 @@ __global__ void gate_ptr_kernel(float* __restrict__ ptr, const float* __restrict
 
 int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, int Nt, float* out, cudaStream_t stream) {
   VLS_REQUIRE(Nt >= 1 && Nt <= 32, "decoder: between 1 and 32 tokens are supported (got %d)", Nt);
-  tok_self_attn_kernel<<<dim3(8, B), 128, 0, stream>>>(q, k, v, Nt, out);
+  VLS_CUDA(launch_k(tok_self_attn_kernel, dim3(dim3(8, B)), dim3(128), 0, stream, q, k, v, Nt, out));
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_sb, int koff, int voff, int B, int Nt,
                     int T, float* out, cudaStream_t stream) {
-  t2i_attn_kernel<<<dim3(Nt, 8, B), 256, 0, stream>>>(q, reinterpret_cast<const bf16*>(kv), ld, kv_sb, koff, voff, Nt, T,
-                                                      out);
+  VLS_CUDA(launch_k(t2i_attn_kernel, dim3(dim3(Nt, 8, B)), dim3(256), 0, stream, q, reinterpret_cast<const bf16*>(kv), ld, kv_sb, koff, voff, Nt, T, out));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -331,17 +337,14 @@ int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_s
 int launch_i2t_attn(const void* qrows, long long ld, long long q_sb, int qoff, const float* ktok, const float* vtok, int B,
                     int Nt, int T, void* out, cudaStream_t stream) {
   const size_t smem = (size_t)Nt * 128 * 2 * sizeof(float);
-  i2t_attn_kernel<<<dim3((T * 8 + 255) / 256, B), 256, smem, stream>>>(reinterpret_cast<const bf16*>(qrows), ld, q_sb, qoff,
-                                                                       ktok, vtok, Nt, T, reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(i2t_attn_kernel, dim3(dim3((T * 8 + 255) / 256, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(qrows), ld, q_sb, qoff, ktok, vtok, Nt, T, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_up1_post(const void* g, const void* feat, int feat_bf16, long long feat_sb, int B, int h, int w,
                     const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream) {
-  up1_post_kernel<<<dim3((2 * w + 31) / 32, 2 * h, B), 256, 0, stream>>>(reinterpret_cast<const float*>(g), feat, feat_bf16,
-                                                                         feat_sb, h, w, lnw, lnb, eps,
-                                                                         reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(up1_post_kernel, dim3(dim3((2 * w + 31) / 32, 2 * h, B)), dim3(256), 0, stream, reinterpret_cast<const float*>(g), feat, feat_bf16, feat_sb, h, w, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -356,8 +359,7 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
     VLS_CUDA(cudaFuncSetAttribute(up2_masks_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  up2_masks_kernel<4><<<dim3((w2 + 31) / 32, h2, B), 128, smem, stream>>>(reinterpret_cast<const bf16*>(u), w2t, bias, feat,
-                                                                          feat_bf16, feat_sb, hyper, h2, w2, masks);
+  VLS_CUDA(launch_k(up2_masks_kernel<4>, dim3(dim3((w2 + 31) / 32, h2, B)), dim3(128), smem, stream, reinterpret_cast<const bf16*>(u), w2t, bias, feat, feat_bf16, feat_sb, hyper, h2, w2, masks));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -366,14 +368,13 @@ int launch_select_best(const float* masks, const float* iou, const float* tokens
                        int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
                        float* occluded, cudaStream_t stream) {
   VLS_REQUIRE(HW % 4 == 0, "select_best: H*W must be a multiple of 4");
-  select_best_kernel<<<dim3(16, B), 256, 0, stream>>>(masks, iou, tokens, obj_logits, M, multimask, HW, low_res, tok_sel,
-                                                      best_idx, is_obj, occluded, -1024.0f);
+  VLS_CUDA(launch_k(select_best_kernel, dim3(dim3(16, B)), dim3(256), 0, stream, masks, iou, tokens, obj_logits, M, multimask, HW, low_res, tok_sel, best_idx, is_obj, occluded, -1024.0f));
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_gate_ptr(float* ptr, const float* is_obj, const float* no_obj_ptr, int B, cudaStream_t stream) {
-  gate_ptr_kernel<<<(B * 256 + 255) / 256, 256, 0, stream>>>(ptr, is_obj, no_obj_ptr, B);
+  VLS_CUDA(launch_k(gate_ptr_kernel, dim3((B * 256 + 255) / 256), dim3(256), 0, stream, ptr, is_obj, no_obj_ptr, B));
   VLS_POST_LAUNCH(1);
   return 0;
 }

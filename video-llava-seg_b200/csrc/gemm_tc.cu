@@ -92,6 +92,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_enter();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
     if (lane == 0) {
@@ -237,7 +238,7 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
     attr_set = true;
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
-  gemm_tn_kernel<BN, STAGES_><<<grid, THREADS, C_::SMEM, stream>>>(tmA, tmB, e);
+  VLS_CUDA(launch_k(gemm_tn_kernel<BN, STAGES_>, dim3(grid), dim3(THREADS), C_::SMEM, stream, tmA, tmB, e));
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -3,6 +3,7 @@
 #include <cudaTypedefs.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -23,6 +24,16 @@ const char* last_error() { return g_err; }
 static std::atomic<long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("VLS_PDL");
+    g_pdl = (e && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl == 1;
+}
+void pdl_set(bool on) { g_pdl = on ? 1 : 0; }
 
 struct ProfSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;

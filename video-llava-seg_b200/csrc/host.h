@@ -6,6 +6,7 @@
 #include <stdint.h>
 
 #include <cstdarg>
+#include <utility>
 #include <cstdio>
 
 namespace vls {
@@ -30,6 +31,32 @@ long long launch_count();
     vls::count_launches(n);              \
     VLS_CUDA(cudaGetLastError());        \
   } while (0)
+
+// Programmatic dependent launch (PDL): every kernel of the library starts with griddepcontrol.wait (pdl_enter() in
+// common.cuh), so a launch may be released as soon as all CTAs of the previous kernel in the stream have STARTED; the
+// dependent grid's launch latency, CTA scheduling and parameter/descriptor fetch then overlap the previous grid's tail,
+// and its CTAs block at the wait until that grid has completed and flushed.  The per-frame path is a chain of ~190
+// mostly 3-25 us kernels.  Captured into CUDA graphs as programmatic edges.  MEASURED (B200, r1, whole frame as one graph
+// replay): 1.7245 ms/frame with PDL vs 1.6988 ms without -- graph replay already hides the launch gaps, what remains
+// is each small kernel's own ramp/drain -- so it is OFF by default; VLS_PDL=1 or vls_set_tuning("pdl", 1) enables it
+// (useful for the eager, un-graphed path).
+bool pdl_enabled();
+void pdl_set(bool on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // Optional per-kernel device timing (CUDA events on the launching stream), off by default.
 // Used by bench.py to measure the dominant kernel's average launch duration live.

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(256)
 mds1_kernel(const float* __restrict__ src, int mode, int H, int W, int factor, float scale, float bias_v,
             const float* __restrict__ wgt /*[4][9]*/, const float* __restrict__ cb, const float* __restrict__ lnw,
             const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
+  pdl_enter();
   __shared__ float tile[33][34];
   const int b = blockIdx.z;
   const int oy0 = blockIdx.y * 16, ox0 = blockIdx.x * 16;
@@ -87,6 +88,7 @@ mds1_kernel(const float* __restrict__ src, int mode, int H, int W, int factor, f
 __global__ void __launch_bounds__(256)
 mds2_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__ wgt, const float* __restrict__ cb,
             const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
+  pdl_enter();
   __shared__ float sw[9 * 4 * 16];
   for (int i = threadIdx.x; i < 9 * 4 * 16; i += 256) sw[i] = wgt[i];
   __syncthreads();
@@ -142,6 +144,7 @@ mds2_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__
 __global__ void __launch_bounds__(256)
 mds3_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__ wgt, const float* __restrict__ cb,
             const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
+  pdl_enter();
   extern __shared__ float sw3[];
   for (int i = threadIdx.x; i < 9 * 16 * 64; i += 256) sw3[i] = wgt[i];
   __syncthreads();
@@ -213,6 +216,7 @@ mds3_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__
 // ------------------------------------------------------------------ im2col for the 64 -> 256, 3x3/s2 convolution
 // in NHWC bf16 [B][H*W][C]; out bf16 [B][(H/2)*(W/2)][9*C], column (ky*3+kx)*C + ci. One uint4 (8 ch) per thread.
 __global__ void im2col3x3s2_kernel(const bf16* __restrict__ in, int B, int H, int W, int C, bf16* __restrict__ out) {
+  pdl_enter();
   const int OH = H >> 1, OW = W >> 1, c8 = C >> 3;
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)B * OH * OW * 9 * c8;
@@ -234,6 +238,7 @@ __global__ void im2col3x3s2_kernel(const bf16* __restrict__ in, int B, int H, in
 __global__ void __launch_bounds__(256)
 dwconv7_ln_kernel(const float* __restrict__ x, int H, int W, const float* __restrict__ wgt, const float* __restrict__ cb,
                   const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
+  pdl_enter();
   __shared__ float red[8][2][8];
   const int c = threadIdx.x, lane = c & 31, warp = c >> 5;
   const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 8;
@@ -298,18 +303,14 @@ dwconv7_ln_kernel(const float* __restrict__ x, int H, int W, const float* __rest
 int launch_mds1(const float* src, int mode, int B, int H, int W, int factor, float scale, float bias_v, const float* wgt,
                 const float* cb, const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream) {
   VLS_REQUIRE(H % 2 == 0 && W % 2 == 0 && factor >= 1 && H % factor == 0 && W % factor == 0, "mds1: bad shape");
-  mds1_kernel<<<dim3((W / 2 + 15) / 16, (H / 2 + 15) / 16, B), 256, 0, stream>>>(src, mode, H, W, factor, scale, bias_v, wgt,
-                                                                                 cb, lnw, lnb, eps,
-                                                                                 reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(mds1_kernel, dim3(dim3((W / 2 + 15) / 16, (H / 2 + 15) / 16, B)), dim3(256), 0, stream, src, mode, H, W, factor, scale, bias_v, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_mds2(const void* in, int B, int H, int W, const float* wgt, const float* cb, const float* lnw, const float* lnb,
                 float eps, void* out, cudaStream_t stream) {
-  mds2_kernel<<<dim3((W / 2 + 31) / 32, (H / 2 + 7) / 8, B), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), H, W, wgt,
-                                                                               cb, lnw, lnb, eps,
-                                                                               reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(mds2_kernel, dim3(dim3((W / 2 + 31) / 32, (H / 2 + 7) / 8, B)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(in), H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -317,9 +318,7 @@ int launch_mds2(const void* in, int B, int H, int W, const float* wgt, const flo
 int launch_mds3(const void* in, int B, int H, int W, const float* wgt, const float* cb, const float* lnw, const float* lnb,
                 float eps, void* out, cudaStream_t stream) {
   const int smem = 9 * 16 * 64 * 4;
-  mds3_kernel<<<dim3((W / 2 + 15) / 16, (H / 2 + 3) / 4, B), 256, smem, stream>>>(reinterpret_cast<const bf16*>(in), H, W,
-                                                                                  wgt, cb, lnw, lnb, eps,
-                                                                                  reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(mds3_kernel, dim3(dim3((W / 2 + 15) / 16, (H / 2 + 3) / 4, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(in), H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -327,16 +326,14 @@ int launch_mds3(const void* in, int B, int H, int W, const float* wgt, const flo
 int launch_im2col3x3s2(const void* in, int B, int H, int W, int C, void* out, cudaStream_t stream) {
   VLS_REQUIRE(C % 8 == 0, "im2col: C must be a multiple of 8");
   const long long total = (long long)B * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col3x3s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(reinterpret_cast<const bf16*>(in), B, H, W, C,
-                                                                          reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(im2col3x3s2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, reinterpret_cast<const bf16*>(in), B, H, W, C, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
 
 int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
                       const float* lnb, float eps, void* out, cudaStream_t stream) {
-  dwconv7_ln_kernel<<<dim3((W + 7) / 8, H, B), 256, 0, stream>>>(x, H, W, wgt, cb, lnw, lnb, eps,
-                                                                reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(dwconv7_ln_kernel, dim3(dim3((W + 7) / 8, H, B)), dim3(256), 0, stream, x, H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -21,6 +21,7 @@ __device__ __forceinline__ float bilerp(const float* __restrict__ src, int h, in
 // (np.packbits order: first pixel = most significant bit).  One thread per 8 consecutive output pixels.
 __global__ void resize_binarize_kernel(const float* __restrict__ in, int n, int h, int w, int H, int W, float sy, float sx,
                                        float thresh, uint8_t* __restrict__ out_u8, uint8_t* __restrict__ out_bits) {
+  pdl_enter();
   const int W8 = (W + 7) >> 3;
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= (long long)n * H * W8) return;
@@ -54,6 +55,7 @@ __global__ void resize_binarize_kernel(const float* __restrict__ in, int n, int 
 
 __global__ void resize_bilinear_kernel(const float* __restrict__ in, int n, int h, int w, float* __restrict__ out, int H,
                                        int W, float sy, float sx) {
+  pdl_enter();
   const int W4 = (W + 3) >> 2;
   const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= (long long)n * H * W4) return;
@@ -79,8 +81,7 @@ int launch_resize_bilinear(const float* in, int n, int h, int w, float* out, int
   VLS_REQUIRE(n >= 0 && h > 0 && w > 0 && H > 0 && W > 0, "resize: bad shape");
   if (n == 0) return 0;
   const long long total = (long long)n * H * ((W + 3) / 4);
-  resize_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, h, w, out, H, W, (float)h / H,
-                                                                              (float)w / W);
+  VLS_CUDA(launch_k(resize_bilinear_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, in, n, h, w, out, H, W, (float)h / H, (float)w / W));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -91,8 +92,7 @@ int launch_resize_binarize(const float* in, int n, int h, int w, int H, int W, f
   VLS_REQUIRE(out_u8 || out_bits, "resize_binarize: no output requested");
   if (n == 0) return 0;
   const long long total = (long long)n * H * ((W + 7) / 8);
-  resize_binarize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, n, h, w, H, W, (float)h / H, (float)w / W,
-                                                                              thresh, out_u8, out_bits);
+  VLS_CUDA(launch_k(resize_binarize_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, in, n, h, w, H, W, (float)h / H, (float)w / W, thresh, out_u8, out_bits));
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -18,6 +18,7 @@ __global__ void ln256_kernel(const float* __restrict__ x, int B, int T, const fl
                              const float* __restrict__ bsh, float eps, int gelu, float* __restrict__ out_f32,
                              long long f_sb, long long f_st, bf16* __restrict__ out_bf16, long long h_sb,
                              long long h_st) {
+  pdl_enter();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= (long long)B * T) return;
   const int lane = threadIdx.x & 31;
@@ -61,6 +62,7 @@ __global__ void ln256_kernel(const float* __restrict__ x, int B, int T, const fl
 __global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long long a_st, long long a_sb,
                                  const void* __restrict__ p, int p_bf16, long long p_st, long long p_sb, float alpha,
                                  int B, int T, int C, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+  pdl_enter();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total4 = (long long)B * T * C / 4;
   if (i4 >= total4) return;
@@ -84,6 +86,7 @@ struct Strides4 { long long sb, sc, sh, sw; };
 __global__ void nchw_to_rows_kernel(const void* __restrict__ in, int in_bf16, Strides4 si, const void* __restrict__ add,
                                     int add_bf16, Strides4 sa, int C, int H, int W, float* __restrict__ out_f32,
                                     bf16* __restrict__ out_bf16) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -115,6 +118,7 @@ __global__ void nchw_to_rows_kernel(const void* __restrict__ in, int in_bf16, St
 __global__ void rows_to_nchw_kernel(const float* __restrict__ in, int C, int T, const float* __restrict__ gate,
                                     const float* __restrict__ vec, float* __restrict__ out_f32,
                                     bf16* __restrict__ out_bf16) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -148,6 +152,7 @@ struct SmallLin {
   int G, R, N, K, act;  // act: 0 none, 1 relu, 3 sigmoid
 };
 __global__ void small_linear_kernel(const SmallLin p) {
+  pdl_enter();
   const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const long long total = (long long)p.G * p.R * p.N;
   if (gw >= total) return;
@@ -188,6 +193,7 @@ __global__ void small_linear_kernel(const SmallLin p) {
 // LayerNorm over 256 for a handful of token rows (f32 in/out), optional residual-free in-place.
 __global__ void ln256_small_kernel(const float* __restrict__ x, long long x_sr, int rows, const float* __restrict__ w,
                                    const float* __restrict__ b, float eps, float* __restrict__ out, long long o_sr) {
+  pdl_enter();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
@@ -213,6 +219,7 @@ __global__ void ln256_small_kernel(const float* __restrict__ x, long long x_sr, 
 // tokens[b][i][:] = i < n_out ? out_tokens[i][:] : sparse[b][i - n_out][:]      (mask_decoder.py:179-197)
 __global__ void build_tokens_kernel(const float* __restrict__ out_tokens, int n_out, const float* __restrict__ sparse,
                                     int Ns, int B, float* __restrict__ tok_a, float* __restrict__ tok_b) {
+  pdl_enter();
   const int Nt = n_out + Ns;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * Nt * 256) return;
@@ -225,6 +232,7 @@ __global__ void build_tokens_kernel(const float* __restrict__ out_tokens, int n_
 // out_bf16[b][t][c] = in[b][t][c] + gate[b] * vec[c]
 __global__ void rows_gate_cast_kernel(const float* __restrict__ in, int B, int T, int C, const float* __restrict__ gate,
                                       const float* __restrict__ vec, bf16* __restrict__ out) {
+  pdl_enter();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)B * T * C) return;
   const int c = (int)(i % C), b = (int)(i / ((long long)T * C));
@@ -234,6 +242,7 @@ __global__ void rows_gate_cast_kernel(const float* __restrict__ in, int B, int T
 // dst[g][r][:n] = src[g*sg + r*sr + :n]
 __global__ void gather_rows_kernel(const float* __restrict__ src, long long sg, long long sr, int G, int R, int n,
                                    float* __restrict__ dst) {
+  pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= G * R * n) return;
   const int c = i % n, r = (i / n) % R, g = i / (n * R);
@@ -245,7 +254,7 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, long long sg, 
 int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse, int Ns, int B, float* tok_a, float* tok_b,
                         cudaStream_t stream) {
   const int total = B * (n_out + Ns) * 256;
-  build_tokens_kernel<<<(total + 255) / 256, 256, 0, stream>>>(out_tokens, n_out, sparse, Ns, B, tok_a, tok_b);
+  VLS_CUDA(launch_k(build_tokens_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, out_tokens, n_out, sparse, Ns, B, tok_a, tok_b));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -253,8 +262,7 @@ int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse,
 int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gate, const float* vec, void* out,
                           cudaStream_t stream) {
   const long long total = (long long)B * T * C;
-  rows_gate_cast_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(in, B, T, C, gate, vec,
-                                                                             reinterpret_cast<bf16*>(out));
+  VLS_CUDA(launch_k(rows_gate_cast_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream, in, B, T, C, gate, vec, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -262,7 +270,7 @@ int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gat
 int launch_gather_rows(const float* src, long long sg, long long sr, int G, int R, int n, float* dst, cudaStream_t stream) {
   const int total = G * R * n;
   if (total == 0) return 0;
-  gather_rows_kernel<<<(total + 255) / 256, 256, 0, stream>>>(src, sg, sr, G, R, n, dst);
+  VLS_CUDA(launch_k(gather_rows_kernel, dim3((total + 255) / 256), dim3(256), 0, stream, src, sg, sr, G, R, n, dst));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -272,8 +280,7 @@ int launch_ln256(const float* x, int B, int T, const float* w, const float* b, f
   const long long rows = (long long)B * T;
   if (rows == 0) return 0;
   const int wpb = 8;
-  ln256_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, stream>>>(
-      x, B, T, w, b, eps, gelu, out_f32, f_sb, f_st, reinterpret_cast<bf16*>(out_bf16), h_sb, h_st);
+  VLS_CUDA(launch_k(ln256_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream,  x, B, T, w, b, eps, gelu, out_f32, f_sb, f_st, reinterpret_cast<bf16*>(out_bf16), h_sb, h_st));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -284,8 +291,7 @@ int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, 
   VLS_REQUIRE(C % 4 == 0, "axpy_rows: C must be a multiple of 4");
   const long long total4 = (long long)B * T * C / 4;
   if (total4 == 0) return 0;
-  axpy_rows_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, stream>>>(
-      a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(launch_k(axpy_rows_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,  a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -297,8 +303,7 @@ int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], cons
   Strides4 s2{0, 0, 0, 0};
   if (add) s2 = Strides4{sa[0], sa[1], sa[2], sa[3]};
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), blk(32, 8);
-  nchw_to_rows_kernel<<<grid, blk, 0, stream>>>(in, in_bf16, s1, add, add_bf16, s2, C, H, W, out_f32,
-                                               reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(launch_k(nchw_to_rows_kernel, dim3(grid), dim3(blk), 0, stream, in, in_bf16, s1, add, add_bf16, s2, C, H, W, out_f32, reinterpret_cast<bf16*>(out_bf16)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -306,7 +311,7 @@ int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], cons
 int launch_rows_to_nchw(const float* in, int B, int C, int T, const float* gate, const float* vec, float* out_f32,
                         void* out_bf16, cudaStream_t stream) {
   dim3 grid((T + 31) / 32, (C + 31) / 32, B), blk(32, 8);
-  rows_to_nchw_kernel<<<grid, blk, 0, stream>>>(in, C, T, gate, vec, out_f32, reinterpret_cast<bf16*>(out_bf16));
+  VLS_CUDA(launch_k(rows_to_nchw_kernel, dim3(grid), dim3(blk), 0, stream, in, C, T, gate, vec, out_f32, reinterpret_cast<bf16*>(out_bf16)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -324,7 +329,7 @@ int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream) {
   const long long total = (long long)a.G * a.R * a.N;
   if (total == 0) return 0;
   const int wpb = 8;
-  small_linear_kernel<<<(unsigned)((total + wpb - 1) / wpb), wpb * 32, 0, stream>>>(p);
+  VLS_CUDA(launch_k(small_linear_kernel, dim3((unsigned)((total + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, p));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -332,7 +337,7 @@ int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream) {
 int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w, const float* b, float eps, float* out,
                        long long o_sr, cudaStream_t stream) {
   if (rows == 0) return 0;
-  ln256_small_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(x, x_sr, rows, w, b, eps, out, o_sr);
+  VLS_CUDA(launch_k(ln256_small_kernel, dim3((rows + 3) / 4), dim3(128), 0, stream, x, x_sr, rows, w, b, eps, out, o_sr));
   VLS_POST_LAUNCH(1);
   return 0;
 }
