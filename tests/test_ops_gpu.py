@@ -199,6 +199,27 @@ def test_resize_binarize_matches_interpolate(dev, shape, size):
         assert torch.equal(bits.cpu(), torch.from_numpy(np.packbits(u8.cpu().numpy(), axis=-1)))
 
 
+@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 20, 12), (24, 64, 64), (40, 30, 22)])
+def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W):
+    """CXBlock head (memory_encoder.py:86-93): depth-wise 7x7 conv (pad 3) + LayerNorm2d(eps 1e-6) on NHWC rows, f32 in,
+    bf16 out.  Small batches take the per-row kernel, large ones the FFMA2 column-strip kernel (odd sizes exercise the
+    halo / ragged strips of both)."""
+    from video_llava_seg_b200._lib import check, ptr, stream
+
+    x = _rand((B, H * W, 256), dev, 3)
+    w = _rand((256, 1, 7, 7), dev, 4) * 0.2
+    cb, lw, lb = _rand((256,), dev, 5) * 0.1, 1 + 0.1 * _rand((256,), dev, 6), 0.1 * _rand((256,), dev, 7)
+    out = torch.empty((B, H * W, 256), dtype=torch.bfloat16, device=dev)
+    wt = w.reshape(256, 49).t().contiguous()
+    check(vls_lib.vls_dwconv7_ln(ptr(x), B, H, W, ptr(wt), ptr(cb), ptr(lw), ptr(lb), 1e-6, ptr(out), stream()))
+    nchw = x.view(B, H, W, 256).permute(0, 3, 1, 2)
+    y = torch.nn.functional.conv2d(nchw, w, cb, padding=3, groups=256).permute(0, 2, 3, 1)
+    ref = torch.nn.functional.layer_norm(y, (256,), lw, lb, 1e-6).reshape(B, H * W, 256)
+    err = (out.float() - ref).abs().max().item()
+    assert err < 3e-2, err                       # bf16 output rounding of O(1) values
+    assert (out.float() - ref).abs().mean().item() < 3e-3
+
+
 def test_cc_matches_reference_kernel(dev):
     """Pin: the reference's own connected_components.cu (compiled unmodified into oracle/_ref/ in the build
     container by oracle/build_ref.py) against our kernel and the C oracle, on the same masks."""

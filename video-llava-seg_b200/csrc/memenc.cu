@@ -331,9 +331,159 @@ int launch_im2col3x3s2(const void* in, int B, int H, int W, int C, void* out, cu
   return 0;
 }
 
+// ---- v2: column-strip sliding window with packed FP32 FMAs.
+// The op is 49 FMA per 6 bytes: above the FP32 machine balance of plain FFMA, so the kernel is written for the FMA
+// pipe first: a thread owns a channel PAIR and every multiply-add is one fma.rn.f32x2 (FFMA2: two FMAs per issue slot).
+// CTA = 128 threads = 256 channels; it walks a strip of 4 pixel columns down R output rows.  Each input row is loaded
+// ONCE (10 x LDG.64 per thread, 256 B per warp and pixel) and scattered into the seven output rows it contributes to;
+// the partial output rows live in registers and rotate statically (row loop unrolled by 8, two input rows per step so
+// that one LDS.64 of a depth-wise weight feeds 8 FFMA2).  The LayerNorm statistics of two finished rows (2 x 4 pixels x
+// {sum, sum of squares}) are reduced with a 16-shuffle butterfly transpose instead of 80 plain shuffles, one
+// __syncthreads per two output rows.  Depth-wise weights sit in shared memory as [tap][channel pair].
+constexpr int DW_TX = 4;
+
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                     rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
+__global__ void __launch_bounds__(128)
+dwconv7_ln_strip_kernel(const float* __restrict__ x, int H, int W, int R, const float* __restrict__ wgt,
+                        const float* __restrict__ cb, const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                        bf16* __restrict__ out) {
+  pdl_enter();
+  extern __shared__ float2 dw_smem[];
+  float2* sw = dw_smem;                                            // [49][128]
+  float* red = reinterpret_cast<float*>(dw_smem + 49 * 128);       // [2 parity][4 warps][16]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, y0 = blockIdx.y * R, x0 = blockIdx.x * DW_TX;
+  for (int i = tid; i < 49 * 128; i += 128) sw[i] = *reinterpret_cast<const float2*>(wgt + (i >> 7) * 256 + 2 * (i & 127));
+  const float2 bias = *reinterpret_cast<const float2*>(cb + 2 * tid);
+  const float2 g = *reinterpret_cast<const float2*>(lnw + 2 * tid), be = *reinterpret_cast<const float2*>(lnb + 2 * tid);
+  const float* xb = x + (long long)b * H * W * 256 + 2 * tid;
+  bf16* ob = out + (long long)b * H * W * 256 + 2 * tid;
+  __syncthreads();
+  // eight partial output rows in registers (slot = output row mod 8 relative to the strip); every step consumes TWO
+  // input rows per weight fetch: one LDS.64 feeds 8 FFMA2
+  float2 acc[8][DW_TX];
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int j = 0; j < DW_TX; ++j) acc[s][j] = bias;
+  const int y_last = min(y0 + R, H) - 1;          // last output row of this CTA
+  int parity = 0;
+  for (int base = y0 - 3; base <= y_last + 3; base += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const int yi = base + k;                     // input rows yi, yi + 1
+      if (yi > y_last + 3) break;
+      float2 row[2][DW_TX + 6];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const bool yok = yi + r >= 0 && yi + r < H;
+#pragma unroll
+        for (int i = 0; i < DW_TX + 6; ++i) {
+          const int X = x0 + i - 3;
+          row[r][i] = (yok && X >= 0 && X < W) ? *reinterpret_cast<const float2*>(xb + ((long long)(yi + r) * W + X) * 256)
+                                               : make_float2(0.f, 0.f);
+        }
+      }
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) {             // input row yi+r, tap row dy -> output row yi + r + 3 - dy
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+          const float2 w2 = sw[(dy * 7 + dx) * 128 + tid];
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int slot = (k + r + 3 - dy + 8) % 8;
+#pragma unroll
+            for (int j = 0; j < DW_TX; ++j) acc[slot][j] = ffma2(w2, row[r][j + dx], acc[slot][j]);
+          }
+        }
+      }
+      // output rows yi - 3 and yi - 2 are complete: slots (k + 5) % 8 and (k + 6) % 8
+      const int yo = yi - 3;
+      const int sa = (k + 5) % 8, sb = (k + 6) % 8;
+      if (yo + 1 >= y0 && yo <= y_last) {
+        // LayerNorm over the 256 channels of 2 rows x 4 pixels: 16 quantities, butterfly transpose-reduce (16 shuffles)
+        float q[16];
+#pragma unroll
+        for (int j = 0; j < DW_TX; ++j) {
+          const float2 v = acc[sa][j], u = acc[sb][j];
+          q[j] = v.x + v.y;
+          q[4 + j] = v.x * v.x + v.y * v.y;
+          q[8 + j] = u.x + u.y;
+          q[12 + j] = u.x * u.x + u.y * u.y;
+        }
+#pragma unroll
+        for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+          const bool hi = lane & bit;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = hi ? q[i] : q[i + half], keep = hi ? q[i + half] : q[i];
+            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+        q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+        // lane (pairs of lanes) now holds quantity index lane >> 1 summed over the warp
+        if ((lane & 1) == 0) red[(parity * 4 + warp) * 16 + (lane >> 1)] = q[0];
+        __syncthreads();
+        const float4* rp = reinterpret_cast<const float4*>(red + parity * 64);
+        float4 t[4] = {rp[0], rp[1], rp[2], rp[3]};
+#pragma unroll
+        for (int w = 1; w < 4; ++w)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 a = rp[4 * w + c];
+            t[c].x += a.x; t[c].y += a.y; t[c].z += a.z; t[c].w += a.w;
+          }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int yr = yo + r;
+          if (yr < y0 || yr > y_last) continue;
+          const float sum[4] = {t[2 * r].x, t[2 * r].y, t[2 * r].z, t[2 * r].w};
+          const float sq[4] = {t[2 * r + 1].x, t[2 * r + 1].y, t[2 * r + 1].z, t[2 * r + 1].w};
+#pragma unroll
+          for (int j = 0; j < DW_TX; ++j) {
+            const float mean = sum[j] * (1.f / 256.f);
+            const float var = fmaxf(sq[j] * (1.f / 256.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            const int X = x0 + j;
+            if (X < W) {
+              const float2 v = r == 0 ? acc[sa][j] : acc[sb][j];
+              *reinterpret_cast<uint32_t*>(ob + ((long long)yr * W + X) * 256) =
+                  pack_bf16x2((v.x - mean) * rstd * g.x + be.x, (v.y - mean) * rstd * g.y + be.y);
+            }
+          }
+        }
+        parity ^= 1;
+      }
+#pragma unroll
+      for (int j = 0; j < DW_TX; ++j) acc[sa][j] = acc[sb][j] = bias;   // these slots start output rows yi + 5, yi + 6
+    }
+  }
+}
+
 int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
                       const float* lnb, float eps, void* out, cudaStream_t stream) {
-  VLS_CUDA(launch_k(dwconv7_ln_kernel, dim3(dim3((W + 7) / 8, H, B)), dim3(256), 0, stream, x, H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
+  // few images: one CTA per 8 pixels of a row (512 CTAs at B=1, latency matters); many images: the FFMA2 column-strip
+  // kernel, strips of R rows chosen so that the grid is at least ~4 waves of 148 SMs x 4 CTAs
+  const long long strips = (long long)((W + DW_TX - 1) / DW_TX) * B;
+  if (strips * ((H + 15) / 16) < 1184) {
+    VLS_CUDA(launch_k(dwconv7_ln_kernel, dim3((W + 7) / 8, H, B), dim3(256), 0, stream, x, H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
+  } else {
+    int R = H;
+    while (R > 16 && strips * ((H + R - 1) / R) < 2368) R = (R + 1) / 2;
+    const size_t smem = 49 * 128 * sizeof(float2) + 2 * 4 * 16 * sizeof(float);
+    static bool attr = false;
+    if (!attr) {
+      VLS_CUDA(cudaFuncSetAttribute(dwconv7_ln_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    VLS_CUDA(launch_k(dwconv7_ln_strip_kernel, dim3((W + DW_TX - 1) / DW_TX, (H + R - 1) / R, B), dim3(128), smem, stream, x, H, W, R, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
+  }
   VLS_POST_LAUNCH(1);
   return 0;
 }
