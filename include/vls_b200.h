@@ -94,6 +94,17 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
  * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */
 int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H, int W, vls_stream_t stream);
 
+/* Device-resident memory bank of the steady-state tracker (replaces the per-frame flatten/permute/cat of
+ * sam2_base.py:533-646).  bank: bf16 [B][n_mem*HW + n_ptr*tokens_per_ptr][64] in the reference's
+ * key order [cond | t-6 .. t-1 | ptr(cond), ptr(t-1) .. ptr(t-(n_ptr-1))].  Advances it one frame in place, in one
+ * launch: memory slots 1..n_mem-2 <- 2..n_mem-1, slot n_mem-1 <- new_rows (bf16 [B][HW][64]); pointer slots
+ * 2..n_ptr-1 <- 1..n_ptr-2, slot 1 <- new_ptr (f32 [B][tokens_per_ptr*64]).  Slot 0 of both (conditioning frame) stays. */
+int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,
+                   const float* new_ptr, vls_stream_t stream);
+/* n <= 8 device-to-device copies in one launch (src[i] -> dst[i], bytes[i] % 16 == 0, 16-byte aligned): the per-frame
+ * snapshots of the outputs a replayed CUDA graph leaves in its static buffers. */
+int vls_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, vls_stream_t stream);
+
 /* Fused output stage: the same bilinear resize followed by `> thresh`, without materialising the f32 [H,W] logits
  * (sam2_video_predictor.py:404-424 + the caller's threshold, e.g. llava/inference/utils.py:71-85).
  * out_u8  : [n][H][W] uint8 0/1, or NULL.   out_bits: [n][H][ceil(W/8)] bytes, first pixel = most significant bit

@@ -138,7 +138,7 @@ def run_reference_clip(model, clip, batch, num_frames):
     return per_frame
 
 
-def clip_case(model, sd, name, seed, num_frames, batch):
+def clip_case(model, sd, name, seed, num_frames, batch, sub=2):
     clip = synth.SyntheticClip(seed, num_frames)
     ref = run_reference_clip(model, clip, batch, num_frames)
     ora = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, batch), clip.point_prompt(batch), num_frames,
@@ -153,8 +153,8 @@ def clip_case(model, sd, name, seed, num_frames, batch):
               f"obj {r['object_score_logits'].flatten().tolist()} fg {fg:.4f} "
               f"range [{r['pred_masks'].min():.2f},{r['pred_masks'].max():.2f}]")
         assert d_mask < 2e-3 and d_ptr < 1e-3, "oracle drifted from the reference"
-        out[f"mask_s2_{t}"] = r["pred_masks"][:, :, ::2, ::2].numpy()
-        out[f"prefill_s2_{t}"] = r["pred_masks_prefill"][:, :, ::2, ::2].numpy()
+        out[f"mask_s{sub}_{t}"] = r["pred_masks"][:, :, ::sub, ::sub].numpy()
+        out[f"prefill_s{sub}_{t}"] = r["pred_masks_prefill"][:, :, ::sub, ::sub].numpy()
         out[f"maskbits_{t}"] = np.packbits((r["pred_masks"] > 0).numpy().reshape(batch, -1), axis=1)
         out[f"obj_ptr_{t}"] = r["obj_ptr"].numpy()
         out[f"obj_score_{t}"] = r["object_score_logits"].numpy()
@@ -169,9 +169,15 @@ def main():
     model = ref_import.build_video_predictor("t", with_image_encoder=True)
     load_synth_weights(model, sd)
     with torch.inference_mode():
-        module_cases(model, sd)
-        clip_case(model, sd, "clip_b1_t8", seed=1, num_frames=8, batch=1)
-        clip_case(model, sd, "clip_b2_t4", seed=2, num_frames=4, batch=2)
+        only = sys.argv[1:]                       # optional: names of the cases to (re)generate
+        if not only or "modules" in only:
+            module_cases(model, sd)
+        for name, kw in (("clip_b1_t8", dict(seed=1, num_frames=8, batch=1)),
+                         ("clip_b2_t4", dict(seed=2, num_frames=4, batch=2)),
+                         # BASELINE configs[2]: 8 objects tracked jointly (batched memory bank / object pointers)
+                         ("clip_b8_t3", dict(seed=3, num_frames=3, batch=8, sub=4))):
+            if not only or name in only:
+                clip_case(model, sd, name, **kw)
     print("golden vectors written to", OUT)
 
 

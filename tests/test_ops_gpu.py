@@ -220,6 +220,29 @@ def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W):
     assert (out.float() - ref).abs().mean().item() < 3e-3
 
 
+@pytest.mark.parametrize("B,HW,n_mem,n_ptr,k", [(1, 4096, 7, 16, 4), (3, 64, 7, 16, 4), (2, 8, 3, 2, 4)])
+def test_bank_shift_and_clone_many(dev, B, HW, n_mem, n_ptr, k):
+    """Device memory bank: the one-launch in-place age shift equals the slice copies it replaces (exact, bf16 moves +
+    one f32->bf16 rounding of the new pointer), and clone_many equals Tensor.clone()."""
+    from video_llava_seg_b200 import ops
+
+    Nk = n_mem * HW + n_ptr * k
+    bank = _rand((B, Nk, 64), dev, 21).bfloat16()
+    rows = _rand((B, HW, 64), dev, 22).bfloat16()
+    new_ptr = _rand((B, k * 64), dev, 23)
+    want = bank.clone()
+    po = n_mem * HW
+    want[:, HW:(n_mem - 1) * HW] = bank[:, 2 * HW:n_mem * HW]
+    want[:, (n_mem - 1) * HW:n_mem * HW] = rows
+    want[:, po + 2 * k:] = bank[:, po + k:po + (n_ptr - 1) * k]
+    want[:, po + k:po + 2 * k] = new_ptr.reshape(B, k, 64).bfloat16()
+    ops.bank_shift(bank, HW, n_mem, n_ptr, k, rows, new_ptr)
+    assert torch.equal(bank, want)
+    src = [rows, new_ptr, bank[:, :HW], torch.arange(5, device=dev), _rand((B, 1, 16, 16), dev, 24)]
+    out = ops.clone_many(src)
+    assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(src, out))
+
+
 def test_cc_matches_reference_kernel(dev):
     """Pin: the reference's own connected_components.cu (compiled unmodified into oracle/_ref/ in the build
     container by oracle/build_ref.py) against our kernel and the C oracle, on the same masks."""

@@ -52,22 +52,24 @@ def _run(predictor, seed, num_frames, batch):
     return [tuple(f) + (p,) for f, p in zip(frames, pre)]
 
 
-@pytest.mark.parametrize("name,seed,T,B", [("clip_b1_t8", 1, 8, 1), ("clip_b2_t4", 2, 4, 2)])
+@pytest.mark.parametrize("name,seed,T,B", [("clip_b1_t8", 1, 8, 1), ("clip_b2_t4", 2, 4, 2), ("clip_b8_t3", 3, 3, 8)])
 def test_propagation_matches_reference(predictor, name, seed, T, B):
+    """clip_b8_t3 is BASELINE configs[2]'s shape: 8 objects tracked jointly (batched bank, pointers, decoder)."""
     gold = np.load(os.path.join(GOLD, name + ".npz"))
+    sub = 4 if "mask_s4_0" in gold.files else 2          # spatial sub-sampling of the stored reference logits
     frames = _run(predictor, seed, T, B)
     assert [f[0] for f in frames] == list(range(T))
     worst = dict(err=0.0, iou=1.0, flips=0.0)
     for t, out, video_res, prefill in frames:
         # (1) raw decoder logits (before hole filling): north-star bound 1e-2 abs
-        err = (prefill.float().cpu()[:, :, ::2, ::2] - torch.from_numpy(gold[f"prefill_s2_{t}"])).abs().max().item()
+        err = (prefill.float().cpu()[:, :, ::sub, ::sub] - torch.from_numpy(gold[f"prefill_s{sub}_{t}"])).abs().max().item()
         # (2) stored (hole-filled) logits: binarised IoU >= 0.995; filling is a discrete decision on pixels whose
         #     logit is within noise of 0, so a few pixels may differ by the fill value 0.1 -- bound their share
         pm = out["pred_masks"].float().cpu()
-        ref_post = torch.from_numpy(gold[f"mask_s2_{t}"])
-        d = (pm[:, :, ::2, ::2] - ref_post).abs()
+        ref_post = torch.from_numpy(gold[f"mask_s{sub}_{t}"])
+        d = (pm[:, :, ::sub, ::sub] - ref_post).abs()
         flips = (d > 1e-2).float().mean().item()
-        one_sided_fill = (pm[:, :, ::2, ::2] == 0.1) ^ (ref_post == 0.1)
+        one_sided_fill = (pm[:, :, ::sub, ::sub] == 0.1) ^ (ref_post == 0.1)
         assert ((d <= 1e-2) | one_sided_fill).all(), "post-fill differences must be pixels filled on one side only"
         ref_bits = np.unpackbits(gold[f"maskbits_{t}"], axis=1).reshape(B, 1, 256, 256).astype(bool)
         got_bits = (pm > 0).numpy()

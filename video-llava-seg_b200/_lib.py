@@ -66,6 +66,10 @@ def _declare(lib):
 
 
 def _declare_modules(lib):
+    lib.vls_bank_shift.restype = c_int
+    lib.vls_bank_shift.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]
+    lib.vls_multi_copy.restype = c_int
+    lib.vls_multi_copy.argtypes = [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_size_t), c_int, c_void_p]
     lib.vls_resize_binarize.restype = c_int
     lib.vls_resize_binarize.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_void_p]
     lib.vls_resize_bilinear.restype = c_int

@@ -84,6 +84,15 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
   return launch_attention(a, (cudaStream_t)stream);
 }
 
+int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,
+                   const float* new_ptr, vls_stream_t stream) {
+  return launch_bank_shift(bank, B, HW, n_mem, n_ptr, tokens_per_ptr, new_rows, new_ptr, (cudaStream_t)stream);
+}
+int vls_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, vls_stream_t stream) {
+  VLS_REQUIRE(n == 0 || (src && dst && bytes), "multi_copy: null argument");
+  return launch_multi_copy(src, dst, bytes, n, (cudaStream_t)stream);
+}
+
 int vls_resize_binarize(const float* in, int n, int h, int w, int H, int W, float thresh, uint8_t* out_u8, uint8_t* out_bits,
                         vls_stream_t stream) {
   VLS_REQUIRE(n == 0 || in, "resize_binarize: null pointer");

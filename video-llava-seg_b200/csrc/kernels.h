@@ -94,6 +94,9 @@ int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse,
                         cudaStream_t stream);
 int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gate, const float* vec, void* out,
                           cudaStream_t stream);
+int launch_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int k, const void* new_rows, const float* new_ptr,
+                      cudaStream_t stream);
+int launch_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, cudaStream_t stream);
 int launch_gather_rows(const float* src, long long sg, long long sr, int G, int R, int n, float* dst, cudaStream_t stream);
 
 // ---------------------------------------------------------------- mask decoder kernels (decoder.cu)

@@ -249,7 +249,96 @@ __global__ void gather_rows_kernel(const float* __restrict__ src, long long sg, 
   dst[i] = src[g * sg + r * sr + c];
 }
 
+// ------------------------------------------------------------------ device memory bank (graphed.py, sam2_base.py:533-646)
+// bank [B][n_mem*HW + n_ptr*k][64] bf16 in key order [cond | t-6 .. t-1 | ptr(cond), ptr(t-1) .. ptr(t-(n_ptr-1))].
+// Advance one frame IN PLACE: memories 1..n_mem-2 <- 2..n_mem-1, memory n_mem-1 <- new_rows; pointers 2..n_ptr-1 <-
+// 1..n_ptr-2, pointer 1 <- new_ptr (f32 -> bf16).  A thread owns one 16-byte column of a memory slot (or one element
+// pair of a pointer slot) and walks the chain of slots itself, so every element is read before the same thread
+// overwrites it: no staging buffer, no grid barrier, one launch instead of six copy nodes.
+__global__ void bank_shift_kernel(bf16* __restrict__ bank, int B, int HW, int n_mem, int n_ptr, int k,
+                                  const bf16* __restrict__ new_rows, const float* __restrict__ new_ptr) {
+  pdl_enter();
+  const long long slot_vec = (long long)HW * 64 / 8;            // uint4 vectors per memory slot
+  const long long Nk = (long long)n_mem * HW + (long long)n_ptr * k;
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ptr_vec = k * 64 / 8;                                // uint4 vectors per pointer slot
+  if (id < (long long)B * slot_vec) {
+    const int b = (int)(id / slot_vec);
+    const long long off = id % slot_vec;
+    uint4* base = reinterpret_cast<uint4*>(bank + (long long)b * Nk * 64) + off;
+    uint4 v[8];                                  // all loads first (independent, in flight together), then the stores
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (j + 1 < n_mem) v[j] = base[(j + 1) * slot_vec];
+    const uint4 fresh = reinterpret_cast<const uint4*>(new_rows + (long long)b * HW * 64)[off];
+#pragma unroll
+    for (int j = 1; j < 8; ++j)
+      if (j + 1 < n_mem) base[j * slot_vec] = v[j];
+    base[(long long)(n_mem - 1) * slot_vec] = fresh;
+  } else if (id < (long long)B * slot_vec + (long long)B * ptr_vec) {
+    const long long pid = id - (long long)B * slot_vec;
+    const int b = (int)(pid / ptr_vec), off = (int)(pid % ptr_vec);
+    uint4* base = reinterpret_cast<uint4*>(bank + ((long long)b * Nk + (long long)n_mem * HW) * 64) + off;
+    for (int j = n_ptr - 1; j >= 2; --j) base[j * ptr_vec] = base[(j - 1) * ptr_vec];
+    const float* src = new_ptr + (long long)b * k * 64 + off * 8;
+    uint4 v;
+    v.x = pack_bf16x2(src[0], src[1]); v.y = pack_bf16x2(src[2], src[3]);
+    v.z = pack_bf16x2(src[4], src[5]); v.w = pack_bf16x2(src[6], src[7]);
+    base[ptr_vec] = v;
+  }
+}
+
+// up to 8 device-to-device copies in one launch (per-frame snapshots of the graph's static outputs)
+struct MultiCopy {
+  const uint4* src[8];
+  uint4* dst[8];
+  long long vecs[8];     // 16-byte vectors per copy
+  long long first[9];    // prefix sums of vecs
+};
+__global__ void multi_copy_kernel(const MultiCopy m, int n) {
+  pdl_enter();
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= m.first[n]) return;
+  int c = 0;
+#pragma unroll
+  for (int i = 1; i < 8; ++i) c += (i < n && id >= m.first[i]) ? 1 : 0;
+  m.dst[c][id - m.first[c]] = m.src[c][id - m.first[c]];
+}
+
 }  // namespace
+
+int launch_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int k, const void* new_rows, const float* new_ptr,
+                      cudaStream_t stream) {
+  VLS_REQUIRE(bank && new_rows && new_ptr, "bank_shift: null argument");
+  VLS_REQUIRE(B >= 1 && HW >= 1 && n_mem >= 2 && n_mem <= 9 && n_ptr >= 2 && k >= 1 && (HW * 64) % 8 == 0, "bank_shift: bad shape");
+  const long long total = (long long)B * HW * 8 + (long long)B * k * 8;
+  VLS_CUDA(launch_k(bank_shift_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, stream,
+                    reinterpret_cast<bf16*>(bank), B, HW, n_mem, n_ptr, k, reinterpret_cast<const bf16*>(new_rows), new_ptr));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+int launch_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, cudaStream_t stream) {
+  VLS_REQUIRE(n >= 0 && n <= 8, "multi_copy: between 0 and 8 copies per launch");
+  if (n == 0) return 0;
+  MultiCopy m;
+  m.first[0] = 0;
+  for (int i = 0; i < 8; ++i) {
+    m.src[i] = nullptr; m.dst[i] = nullptr; m.vecs[i] = 0;
+    if (i < n) {
+      VLS_REQUIRE(src[i] && dst[i] && bytes[i] % 16 == 0 && ((uintptr_t)src[i] % 16) == 0 && ((uintptr_t)dst[i] % 16) == 0,
+                  "multi_copy: copy %d must be 16-byte aligned and a multiple of 16 bytes", i);
+      m.src[i] = reinterpret_cast<const uint4*>(src[i]);
+      m.dst[i] = reinterpret_cast<uint4*>(dst[i]);
+      m.vecs[i] = (long long)(bytes[i] / 16);
+    }
+    m.first[i + 1] = m.first[i] + m.vecs[i];
+  }
+  if (m.first[n] == 0) return 0;
+  VLS_CUDA(launch_k(multi_copy_kernel, dim3((unsigned)((m.first[n] + 255) / 256)), dim3(256), 0, stream, m, n));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
 
 int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse, int Ns, int B, float* tok_a, float* tok_b,
                         cudaStream_t stream) {

@@ -77,8 +77,6 @@ class SteadyStateGraph:
         non = out["non_cond_frame_outputs"]
         self.bank_mem = torch.empty((B, self.Nk, m.mem_dim), device=dev, dtype=torch.bfloat16)
         self.bank_pos = torch.empty((self.Nk, m.mem_dim), device=dev, dtype=torch.float32)
-        self.shift_tmp = torch.empty((B, (self.n_mem - 2) * HW, m.mem_dim), device=dev, dtype=torch.bfloat16)
-        self.ptr_tmp = torch.empty((B, (self.n_ptr - 2) * self.k, m.mem_dim), device=dev, dtype=torch.bfloat16)
         # memories: conditioning frame (t_pos 0), then t-6 ... t-1 (t_pos 1..6)   (sam2_base.py:533-568)
         self.bank_mem[:, :HW] = m._mem_rows(cond).to(dev)
         self.bank_pos[:HW] = c["mem_pos_rows"][0]
@@ -140,14 +138,8 @@ class SteadyStateGraph:
             video = m._video_res_output(pred, self.hw)
         nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
         main.wait_stream(side)
-        # bank shift for the next frame: memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
-        n, k, po = self.n_mem, self.k, self.ptr_off
-        self.shift_tmp.copy_(self.bank_mem[:, 2 * HW: n * HW])
-        self.bank_mem[:, HW:(n - 1) * HW].copy_(self.shift_tmp)
-        self.bank_mem[:, (n - 1) * HW: n * HW].copy_(rows)
-        self.ptr_tmp.copy_(self.bank_mem[:, po + k: po + (self.n_ptr - 1) * k])
-        self.bank_mem[:, po + 2 * k:].copy_(self.ptr_tmp)
-        self.bank_mem[:, po + k: po + 2 * k].copy_(obj_ptr.reshape(B, k, m.mem_dim))
+        # bank shift for the next frame (one launch, in place): memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
+        ops.bank_shift(self.bank_mem, HW, self.n_mem, self.n_ptr, self.k, rows.contiguous(), obj_ptr.float().contiguous())
         return pred, obj_ptr, obj_logits, nchw, rows, video
 
     def _capture(self):
@@ -193,10 +185,12 @@ class SteadyStateGraph:
         _lib.lib().vls_launch_count_add(self.launches_per_replay)
         pred, obj_ptr, obj_logits, nchw, rows, video = self.outputs
         self.next_frame = frame_idx + 1
+        # snapshots of the static outputs the session must retain: one launch for all six copies
+        nchw_c, rows_c, pred_c, ptr_c, logit_c, video_c = ops.clone_many([nchw, rows, pred, obj_ptr, obj_logits, video])
         compact = {
-            "maskmem_features": nchw.clone(), "maskmem_rows": rows.clone(),
+            "maskmem_features": nchw_c, "maskmem_rows": rows_c,
             "maskmem_pos_enc": self.model._get_maskmem_pos_enc(state, {"maskmem_pos_enc": [
                 self.model._constants()["maskmem_pos"].expand(self.B, -1, -1, -1)]}),
-            "pred_masks": pred.clone(), "obj_ptr": obj_ptr.clone(), "object_score_logits": obj_logits.clone(),
+            "pred_masks": pred_c, "obj_ptr": ptr_c, "object_score_logits": logit_c,
         }
-        return compact, video.clone()
+        return compact, video_c

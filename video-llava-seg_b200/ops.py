@@ -77,6 +77,37 @@ def resize_bilinear(x, size):
     return out
 
 
+def bank_shift(bank, hw, n_mem, n_ptr, tokens_per_ptr, new_rows, new_ptr):
+    """Advance the device memory bank [B, n_mem*hw + n_ptr*tokens_per_ptr, 64] (bf16, reference key order) by one frame
+    in place: see vls_bank_shift."""
+    _lib.require_cuda(bank, new_rows, new_ptr)
+    assert bank.dtype == torch.bfloat16 and bank.is_contiguous() and bank.shape[1] == n_mem * hw + n_ptr * tokens_per_ptr
+    assert new_rows.dtype == torch.bfloat16 and new_rows.is_contiguous() and new_ptr.dtype == torch.float32 and new_ptr.is_contiguous()
+    check(lib().vls_bank_shift(ptr(bank), bank.shape[0], hw, n_mem, n_ptr, tokens_per_ptr, ptr(new_rows), ptr(new_ptr),
+                               stream()), "vls_bank_shift")
+
+
+def clone_many(tensors):
+    """[t.clone() for t in tensors] with ONE kernel launch (vls_multi_copy) for up to 8 contiguous CUDA tensors whose
+    byte sizes are multiples of 16; anything else falls back to Tensor.clone()."""
+    import ctypes
+
+    outs = [torch.empty_like(t) for t in tensors]
+    fast = [i for i, t in enumerate(tensors) if t.is_cuda and t.is_contiguous() and (t.numel() * t.element_size()) % 16 == 0
+            and t.data_ptr() % 16 == 0 and outs[i].data_ptr() % 16 == 0 and t.numel() > 0]
+    for i in range(len(tensors)):
+        if i not in fast:
+            outs[i].copy_(tensors[i])
+    for g in range(0, len(fast), 8):
+        grp = fast[g:g + 8]
+        n = len(grp)
+        src = (ctypes.c_void_p * n)(*[tensors[i].data_ptr() for i in grp])
+        dst = (ctypes.c_void_p * n)(*[outs[i].data_ptr() for i in grp])
+        nb = (ctypes.c_size_t * n)(*[tensors[i].numel() * tensors[i].element_size() for i in grp])
+        check(lib().vls_multi_copy(src, dst, nb, n, stream()), "vls_multi_copy")
+    return outs
+
+
 def resize_binarize(x, size, thresh=0.0, packed=False):
     """(F.interpolate(x, size, mode="bilinear", align_corners=False) > thresh) in one pass for f32 [N,C,h,w], without
     the f32 full-resolution intermediate.  Returns uint8 [N,C,H,W] (0/1), or with packed=True the numpy.packbits
