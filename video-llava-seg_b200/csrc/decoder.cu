@@ -230,23 +230,48 @@ up2_masks_kernel(const bf16* __restrict__ u, const float* __restrict__ w2t, cons
   float* sb = sh + M * 32;            // [32]
   const int b = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 32;
   const int H4 = 2 * h2, W4 = 2 * w2;
-  for (int i = threadIdx.x; i < 4 * 32 * 64; i += 128) sw[i] = w2t[i];
+  // all fills are 128-bit and unrolled (they used to be ~110 serialised scalar round trips to L2 per thread)
+#pragma unroll 8
+  for (int i = threadIdx.x; i < 4 * 32 * 64 / 4; i += 128) reinterpret_cast<float4*>(sw)[i] = reinterpret_cast<const float4*>(w2t)[i];
   for (int i = threadIdx.x; i < M * 32; i += 128) sh[i] = hyper[(long long)b * M * 32 + i];
   if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
-  for (int i = threadIdx.x; i < 32 * 64; i += 128) {
-    const int px = i >> 6, ci = i & 63;
+#pragma unroll
+  for (int i = threadIdx.x; i < 32 * 8; i += 128) {            // 32 pixels x 8 vectors of 8 channels
+    const int px = i >> 3, c8 = (i & 7) * 8;
     const int x = x0 + px;
-    su[ci * 33 + px] = x < w2 ? __bfloat162float(u[(((long long)b * h2 + y) * w2 + x) * 64 + ci]) : 0.f;
-  }
-  for (int i = threadIdx.x; i < 2 * 32 * 64; i += 128) {
-    const int X = i & 63, co = (i >> 6) & 31, dy = i >> 11;
-    const int Xg = 2 * x0 + X;
-    float v = 0.f;
-    if (Xg < W4) {
-      const long long idx = (long long)b * feat_sb + ((long long)co * H4 + 2 * y + dy) * W4 + Xg;
-      v = feat_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(feat)[idx]) : reinterpret_cast<const float*>(feat)[idx];
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (x < w2) v = *reinterpret_cast<const uint4*>(u + (((long long)b * h2 + y) * w2 + x) * 64 + c8);
+    const uint32_t vu[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 p2 = *reinterpret_cast<const __nv_bfloat162*>(&vu[j]);
+      su[(c8 + 2 * j) * 33 + px] = __low2float(p2);
+      su[(c8 + 2 * j + 1) * 33 + px] = __high2float(p2);
     }
-    sf[(dy * 32 + co) * 65 + X] = v;
+  }
+  if (!feat_bf16 && (W4 & 3) == 0 && (feat_sb & 3) == 0 && (reinterpret_cast<uintptr_t>(feat) & 15) == 0) {
+#pragma unroll 8
+    for (int i = threadIdx.x; i < 2 * 32 * 16; i += 128) {     // (dy, co) rows of 64 floats = 16 float4
+      const int X = (i & 15) * 4, co = (i >> 4) & 31, dy = i >> 9;
+      const int Xg = 2 * x0 + X;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (Xg < W4)
+        v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(feat) + (long long)b * feat_sb +
+                                             ((long long)co * H4 + 2 * y + dy) * W4 + Xg);
+      float* d = sf + (dy * 32 + co) * 65 + X;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * 32 * 64; i += 128) {
+      const int X = i & 63, co = (i >> 6) & 31, dy = i >> 11;
+      const int Xg = 2 * x0 + X;
+      float v = 0.f;
+      if (Xg < W4) {
+        const long long idx = (long long)b * feat_sb + ((long long)co * H4 + 2 * y + dy) * W4 + Xg;
+        v = feat_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(feat)[idx]) : reinterpret_cast<const float*>(feat)[idx];
+      }
+      sf[(dy * 32 + co) * 65 + X] = v;
+    }
   }
   __syncthreads();
   const int px = threadIdx.x & 31, pos = threadIdx.x >> 5;  // pos = dy*2+dx, warp-uniform

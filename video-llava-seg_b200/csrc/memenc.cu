@@ -146,7 +146,11 @@ mds3_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__
             const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
   pdl_enter();
   extern __shared__ float sw3[];
-  for (int i = threadIdx.x; i < 9 * 16 * 64; i += 256) sw3[i] = wgt[i];
+  // 128-bit fills, unrolled: the kernel is a few short latency chains (weight fill -> tap loads -> FMAs), so every
+  // serialised L2 round trip shows up in its ~45 us
+#pragma unroll 9
+  for (int i = threadIdx.x; i < 9 * 16 * 64 / 4; i += 256)
+    reinterpret_cast<float4*>(sw3)[i] = reinterpret_cast<const float4*>(wgt)[i];
   __syncthreads();
   const int b = blockIdx.z, OH = H >> 1, OW = W >> 1;
   const int q = threadIdx.x & 3;
@@ -157,15 +161,22 @@ mds3_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__
   for (int co = 0; co < 16; ++co) acc[co] = cb[q * 16 + co];
   const bf16* base = in + (long long)b * H * W * 16;
   if (ok) {
+#pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int Y = 2 * oy + ky - 1;
       if (Y < 0 || Y >= H) continue;
+      uint4 rr[3][2];                      // the three taps of this kernel row: six independent 16-byte loads in flight
+#pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         const int X = 2 * ox + kx - 1;
-        if (X < 0 || X >= W) continue;
-        const uint4* ip = reinterpret_cast<const uint4*>(base + ((long long)Y * W + X) * 16);
-        const uint4 r0 = ip[0], r1 = ip[1];
-        const uint32_t ru[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+        const bool in = X >= 0 && X < W;
+        const uint4* ip = reinterpret_cast<const uint4*>(base + ((long long)Y * W + (in ? X : 0)) * 16);
+        rr[kx][0] = in ? ip[0] : make_uint4(0, 0, 0, 0);
+        rr[kx][1] = in ? ip[1] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t ru[8] = {rr[kx][0].x, rr[kx][0].y, rr[kx][0].z, rr[kx][0].w, rr[kx][1].x, rr[kx][1].y, rr[kx][1].z, rr[kx][1].w};
         const float* wp = sw3 + (ky * 3 + kx) * 16 * 64 + q * 16;
 #pragma unroll
         for (int c2 = 0; c2 < 8; ++c2) {
