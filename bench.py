@@ -202,7 +202,10 @@ def run_ours(args):
             gc.collect()
             gc.disable()          # a generation-2 collection inside a 2 ms step is host noise, not the path
             clocks.mark_start()
+            dbg = bool(os.environ.get("VLS_BENCH_DEBUG"))
+            host_ms, seg0 = [], torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
             for i in range(K):
+                t_host = time.perf_counter()
                 flush.zero_()
                 starts[i].record()
                 _, _, m = next(gen)
@@ -213,6 +216,8 @@ def run_ours(args):
                 if d2h and i > 0:
                     done[(i - 1) % 2].synchronize()          # consume step i-1's mask on the host
                     checksum += int(host[(i - 1) % 2][0, 0, 0, 0])
+                if dbg:
+                    host_ms.append(round((time.perf_counter() - t_host) * 1e3, 3))
             torch.cuda.synchronize()
             clocks.mark_stop()
             gc.enable()
@@ -220,8 +225,10 @@ def run_ours(args):
         launches = lib.vls_launch_count() - launches0
         per_step = [s.elapsed_time(e) for s, e in zip(starts, stops)]
         ms = sum(per_step)
-        if os.environ.get("VLS_BENCH_DEBUG"):
+        if dbg:
             print(f"[bench debug] d2h={d2h} per-step ms: {[round(x, 3) for x in per_step]}", file=sys.stderr, flush=True)
+            print(f"[bench debug] d2h={d2h} host ms per iteration: {host_ms}; cudaMalloc segments during the timed loop: "
+                  f"{torch.cuda.memory_stats(dev).get('num_device_alloc', 0) - seg0}", file=sys.stderr, flush=True)
         if world > 1:
             dist.barrier()
         fps, ms, _ = aggregate_throughput(K, ms, dev)   # sum of frames over ranks / max-over-ranks device time

@@ -26,7 +26,10 @@ from .utils.misc import fill_holes_in_mask_scores
 
 
 class SteadyStateGraph:
+    ARENA_FRAMES = 64     # frames of retained outputs allocated at once
+
     def __init__(self, model, state, frame_idx, batch_size):
+        self._arena, self._arena_pos = None, 0
         self.model, self.B = model, batch_size
         self.dev = state["device"]
         self.num_frames = state["num_frames"]
@@ -185,8 +188,18 @@ class SteadyStateGraph:
         _lib.lib().vls_launch_count_add(self.launches_per_replay)
         pred, obj_ptr, obj_logits, nchw, rows, video = self.outputs
         self.next_frame = frame_idx + 1
-        # snapshots of the static outputs the session must retain: one launch for all six copies
-        nchw_c, rows_c, pred_c, ptr_c, logit_c, video_c = ops.clone_many([nchw, rows, pred, obj_ptr, obj_logits, video])
+        # snapshots of the static outputs: one launch for all six copies.  The five tensors the session retains per frame
+        # go into arenas of ARENA_FRAMES frames (views), so the steady state makes no allocator calls that can reach
+        # cudaMalloc (1.3 MB per frame and object from the 2 MB small-block segments = one cudaMalloc every ~1.5 frames,
+        # each a potential multi-millisecond host stall); the yielded video-resolution tensor is a normal allocation
+        # that the caching allocator recycles as soon as the consumer drops it.
+        keep = [nchw, rows, pred, obj_ptr, obj_logits]
+        if self._arena is None or self._arena_pos == self.ARENA_FRAMES:
+            self._arena = [torch.empty((self.ARENA_FRAMES,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in keep]
+            self._arena_pos = 0
+        dst = [a[self._arena_pos] for a in self._arena] + [torch.empty_like(video)]
+        self._arena_pos += 1
+        nchw_c, rows_c, pred_c, ptr_c, logit_c, video_c = ops.copy_many(keep + [video], dst)
         compact = {
             "maskmem_features": nchw_c, "maskmem_rows": rows_c,
             "maskmem_pos_enc": self.model._get_maskmem_pos_enc(state, {"maskmem_pos_enc": [

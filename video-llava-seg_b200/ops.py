@@ -87,25 +87,32 @@ def bank_shift(bank, hw, n_mem, n_ptr, tokens_per_ptr, new_rows, new_ptr):
                                stream()), "vls_bank_shift")
 
 
-def clone_many(tensors):
-    """[t.clone() for t in tensors] with ONE kernel launch (vls_multi_copy) for up to 8 contiguous CUDA tensors whose
-    byte sizes are multiples of 16; anything else falls back to Tensor.clone()."""
+def copy_many(srcs, dsts):
+    """dst.copy_(src) for every pair with ONE kernel launch per 8 pairs (vls_multi_copy) when both sides are contiguous
+    CUDA tensors of equal byte size that is a multiple of 16 (16-byte aligned); other pairs fall back to Tensor.copy_."""
     import ctypes
 
-    outs = [torch.empty_like(t) for t in tensors]
-    fast = [i for i, t in enumerate(tensors) if t.is_cuda and t.is_contiguous() and (t.numel() * t.element_size()) % 16 == 0
-            and t.data_ptr() % 16 == 0 and outs[i].data_ptr() % 16 == 0 and t.numel() > 0]
-    for i in range(len(tensors)):
-        if i not in fast:
-            outs[i].copy_(tensors[i])
+    fast = []
+    for i, (a, b) in enumerate(zip(srcs, dsts)):
+        nb = a.numel() * a.element_size()
+        if (a.is_cuda and b.is_cuda and a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype and nb > 0
+                and nb == b.numel() * b.element_size() and nb % 16 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+            fast.append(i)
+        else:
+            b.copy_(a)
     for g in range(0, len(fast), 8):
         grp = fast[g:g + 8]
         n = len(grp)
-        src = (ctypes.c_void_p * n)(*[tensors[i].data_ptr() for i in grp])
-        dst = (ctypes.c_void_p * n)(*[outs[i].data_ptr() for i in grp])
-        nb = (ctypes.c_size_t * n)(*[tensors[i].numel() * tensors[i].element_size() for i in grp])
+        src = (ctypes.c_void_p * n)(*[srcs[i].data_ptr() for i in grp])
+        dst = (ctypes.c_void_p * n)(*[dsts[i].data_ptr() for i in grp])
+        nb = (ctypes.c_size_t * n)(*[srcs[i].numel() * srcs[i].element_size() for i in grp])
         check(lib().vls_multi_copy(src, dst, nb, n, stream()), "vls_multi_copy")
-    return outs
+    return dsts
+
+
+def clone_many(tensors):
+    """[t.clone() for t in tensors] with one launch (see copy_many)."""
+    return copy_many(tensors, [torch.empty_like(t) for t in tensors])
 
 
 def resize_binarize(x, size, thresh=0.0, packed=False):
