@@ -155,7 +155,11 @@ class SteadyStateGraph:
         torch.cuda.current_stream(self.dev).wait_stream(side)
         self.graph = torch.cuda.CUDAGraph()
         before = _lib.lib().vls_launch_count()
-        with torch.cuda.graph(self.graph):
+        # captured on a HIGH-priority stream: the forked side streams (memory K/V projections = 2 x 1800 CTAs, output
+        # branch) keep the default (lowest) priority, so the block scheduler serves the main chain's small kernels first
+        # instead of queueing them behind the big grids
+        hi = torch.cuda.Stream(device=self.dev, priority=-1)
+        with torch.cuda.graph(self.graph, stream=hi):
             self.outputs = self._step()
         self.launches_per_replay = _lib.lib().vls_launch_count() - before   # library kernels inside the graph
         self.bank_mem.copy_(keep[0])                        # the warm-up runs shifted the bank: restore it
