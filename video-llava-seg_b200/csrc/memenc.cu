@@ -140,88 +140,100 @@ mds2_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__
 }
 
 // ------------------------------------------------------------------ stage 3: 16 -> 64 channels (NHWC bf16)
-// 4 lanes per output pixel, 16 output channels each.  wgt f32 [9 taps][16 ci][64 co] in smem.
+// 4 lanes per output-pixel PAIR, 16 output channels each; every weight vector fetched from shared memory feeds both
+// pixels (the one-pixel version was bound by its 576 LDS.128 per thread).  wgt f32 [9 taps][16 ci][64 co] in smem.
+// CTA = 16 x 8 output pixels.
 __global__ void __launch_bounds__(256)
 mds3_kernel(const bf16* __restrict__ in, int H, int W, const float* __restrict__ wgt, const float* __restrict__ cb,
             const float* __restrict__ lnw, const float* __restrict__ lnb, float eps, bf16* __restrict__ out) {
   pdl_enter();
   extern __shared__ float sw3[];
-  // 128-bit fills, unrolled: the kernel is a few short latency chains (weight fill -> tap loads -> FMAs), so every
-  // serialised L2 round trip shows up in its ~45 us
 #pragma unroll 9
   for (int i = threadIdx.x; i < 9 * 16 * 64 / 4; i += 256)
     reinterpret_cast<float4*>(sw3)[i] = reinterpret_cast<const float4*>(wgt)[i];
   __syncthreads();
   const int b = blockIdx.z, OH = H >> 1, OW = W >> 1;
   const int q = threadIdx.x & 3;
-  const int ox = blockIdx.x * 16 + ((threadIdx.x >> 2) & 15), oy = blockIdx.y * 4 + (threadIdx.x >> 6);
-  const bool ok = ox < OW && oy < OH;
-  float acc[16];
+  const int ox = blockIdx.x * 16 + 2 * ((threadIdx.x >> 2) & 7), oy = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const bool row_ok = oy < OH;
+  float acc[2][16];
 #pragma unroll
-  for (int co = 0; co < 16; ++co) acc[co] = cb[q * 16 + co];
+  for (int co = 0; co < 16; ++co) acc[0][co] = acc[1][co] = cb[q * 16 + co];
   const bf16* base = in + (long long)b * H * W * 16;
-  if (ok) {
-#pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
+  if (row_ok && ox < OW) {
+    // NOT unrolled over the taps: fully unrolled the kernel is ~9 k straight-line instructions per warp (150 KB of code)
+    // and ncu shows it stalled on instruction fetch (stall_no_instruction 5.7 per issue); one tap is ~1 k
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const int ky = tap / 3, kx = tap - 3 * ky;
       const int Y = 2 * oy + ky - 1;
       if (Y < 0 || Y >= H) continue;
-      uint4 rr[3][2];                      // the three taps of this kernel row: six independent 16-byte loads in flight
+      uint4 rr[2][2];                      // the two input columns (one per pixel of the pair) this tap reads
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const int X = 2 * ox + kx - 1;
-        const bool in = X >= 0 && X < W;
-        const uint4* ip = reinterpret_cast<const uint4*>(base + ((long long)Y * W + (in ? X : 0)) * 16);
-        rr[kx][0] = in ? ip[0] : make_uint4(0, 0, 0, 0);
-        rr[kx][1] = in ? ip[1] : make_uint4(0, 0, 0, 0);
+      for (int p = 0; p < 2; ++p) {
+        const int X = 2 * (ox + p) + kx - 1;
+        const bool inb = X >= 0 && X < W;
+        const uint4* ip = reinterpret_cast<const uint4*>(base + ((long long)Y * W + (inb ? X : 0)) * 16);
+        rr[p][0] = inb ? ip[0] : make_uint4(0, 0, 0, 0);
+        rr[p][1] = inb ? ip[1] : make_uint4(0, 0, 0, 0);
       }
+      const float* wp = sw3 + tap * 16 * 64 + q * 16;
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx) {
-        const uint32_t ru[8] = {rr[kx][0].x, rr[kx][0].y, rr[kx][0].z, rr[kx][0].w, rr[kx][1].x, rr[kx][1].y, rr[kx][1].z, rr[kx][1].w};
-        const float* wp = sw3 + (ky * 3 + kx) * 16 * 64 + q * 16;
+      for (int c2 = 0; c2 < 8; ++c2) {
+        const float4* w0 = reinterpret_cast<const float4*>(wp + (2 * c2) * 64);
+        const float4* w1 = reinterpret_cast<const float4*>(wp + (2 * c2 + 1) * 64);
+        float4 wa[4], wd[4];
 #pragma unroll
-        for (int c2 = 0; c2 < 8; ++c2) {
-          const __nv_bfloat162 p = *reinterpret_cast<const __nv_bfloat162*>(&ru[c2]);
-          const float v0 = __low2float(p), v1 = __high2float(p);
-          const float4* w0 = reinterpret_cast<const float4*>(wp + (2 * c2) * 64);
-          const float4* w1 = reinterpret_cast<const float4*>(wp + (2 * c2 + 1) * 64);
+        for (int c4 = 0; c4 < 4; ++c4) {
+          wa[c4] = w0[c4];
+          wd[c4] = w1[c4];
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+          const uint4 lo = rr[p][0], hi = rr[p][1];
+          const uint32_t ru[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          const __nv_bfloat162 pv = *reinterpret_cast<const __nv_bfloat162*>(&ru[c2]);
+          const float v0 = __low2float(pv), v1 = __high2float(pv);
 #pragma unroll
           for (int c4 = 0; c4 < 4; ++c4) {
-            const float4 a = w0[c4], d = w1[c4];
-            acc[4 * c4] += v0 * a.x + v1 * d.x;
-            acc[4 * c4 + 1] += v0 * a.y + v1 * d.y;
-            acc[4 * c4 + 2] += v0 * a.z + v1 * d.z;
-            acc[4 * c4 + 3] += v0 * a.w + v1 * d.w;
+            acc[p][4 * c4] += v0 * wa[c4].x + v1 * wd[c4].x;
+            acc[p][4 * c4 + 1] += v0 * wa[c4].y + v1 * wd[c4].y;
+            acc[p][4 * c4 + 2] += v0 * wa[c4].z + v1 * wd[c4].z;
+            acc[p][4 * c4 + 3] += v0 * wa[c4].w + v1 * wd[c4].w;
           }
         }
       }
     }
   }
-  float s = 0.f;
 #pragma unroll
-  for (int co = 0; co < 16; ++co) s += acc[co];
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  const float mean = s * (1.f / 64.f);
-  float var = 0.f;
+  for (int p = 0; p < 2; ++p) {
+    float s = 0.f;
 #pragma unroll
-  for (int co = 0; co < 16; ++co) {
-    acc[co] -= mean;
-    var += acc[co] * acc[co];
+    for (int co = 0; co < 16; ++co) s += acc[p][co];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const float mean = s * (1.f / 64.f);
+    float var = 0.f;
+#pragma unroll
+    for (int co = 0; co < 16; ++co) {
+      acc[p][co] -= mean;
+      var += acc[p][co] * acc[p][co];
+    }
+    var += __shfl_xor_sync(0xffffffffu, var, 1);
+    var += __shfl_xor_sync(0xffffffffu, var, 2);
+    const float rstd = rsqrtf(var * (1.f / 64.f) + eps);
+    if (!row_ok || ox + p >= OW) continue;
+    uint32_t pk[8];
+#pragma unroll
+    for (int co = 0; co < 8; ++co) {
+      const int c = q * 16 + 2 * co;
+      pk[co] = pack_bf16x2(gelu_erf(acc[p][2 * co] * rstd * lnw[c] + lnb[c]),
+                           gelu_erf(acc[p][2 * co + 1] * rstd * lnw[c + 1] + lnb[c + 1]));
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox + p) * 64 + q * 16);
+    o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+    o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
   }
-  var += __shfl_xor_sync(0xffffffffu, var, 1);
-  var += __shfl_xor_sync(0xffffffffu, var, 2);
-  const float rstd = rsqrtf(var * (1.f / 64.f) + eps);
-  if (!ok) return;
-  uint32_t pk[8];
-#pragma unroll
-  for (int co = 0; co < 8; ++co) {
-    const int c = q * 16 + 2 * co;
-    pk[co] = pack_bf16x2(gelu_erf(acc[2 * co] * rstd * lnw[c] + lnb[c]),
-                         gelu_erf(acc[2 * co + 1] * rstd * lnw[c + 1] + lnb[c + 1]));
-  }
-  uint4* o = reinterpret_cast<uint4*>(out + (((long long)b * OH + oy) * OW + ox) * 64 + q * 16);
-  o[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-  o[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
 }
 
 // ------------------------------------------------------------------ im2col for the 64 -> 256, 3x3/s2 convolution
@@ -329,7 +341,7 @@ int launch_mds2(const void* in, int B, int H, int W, const float* wgt, const flo
 int launch_mds3(const void* in, int B, int H, int W, const float* wgt, const float* cb, const float* lnw, const float* lnb,
                 float eps, void* out, cudaStream_t stream) {
   const int smem = 9 * 16 * 64 * 4;
-  VLS_CUDA(launch_k(mds3_kernel, dim3(dim3((W / 2 + 15) / 16, (H / 2 + 3) / 4, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(in), H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
+  VLS_CUDA(launch_k(mds3_kernel, dim3(dim3((W / 2 + 15) / 16, (H / 2 + 7) / 8, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(in), H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
