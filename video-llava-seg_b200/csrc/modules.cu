@@ -1,5 +1,7 @@
 // Module-level entry points: each one sequences the kernels of one reference module on the caller's
 // stream using a caller-provided workspace (no allocation, no synchronisation).
+#include <cstdlib>
+
 #include "vls_b200.h"
 
 #include "kernels.h"
@@ -25,6 +27,49 @@ GemmArgs lin(const void* A, long long lda, long long a_bs, const void* W, int M,
   g.bias = bias; g.bias_mode = bias ? 1 : 0;
   g.C = Cout; g.c_bf16 = c_bf16; g.ldc = ldc; g.c_bstride = c_bs;
   return g;
+}
+
+// Fork / join of independent kernel chains onto an internal side stream (events only: no host synchronisation, and
+// the pattern is captured into CUDA graphs as parallel branches).  The per-frame path is a chain of small kernels
+// that each fill a fraction of the 148 SMs, so independent sub-chains are run side by side.  VLS_NO_SIDE_STREAM=1
+// keeps everything on the caller's stream.
+struct Fork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+bool overlap_enabled() {
+  static const bool on = !(getenv("VLS_NO_SIDE_STREAM") && getenv("VLS_NO_SIDE_STREAM")[0] == '1');
+  return on;
+}
+int fork_get(int idx, Fork** out) {
+  static Fork forks[4];
+  Fork& f = forks[idx];
+  if (!f.side) {
+    VLS_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
+    VLS_CUDA(cudaEventCreateWithFlags(&f.ev_fork, cudaEventDisableTiming));
+    VLS_CUDA(cudaEventCreateWithFlags(&f.ev_join, cudaEventDisableTiming));
+  }
+  *out = &f;
+  return 0;
+}
+// returns the stream the forked chain must be launched on (the caller's own stream when overlap is disabled)
+int fork_begin(int idx, cudaStream_t main, cudaStream_t* side) {
+  *side = main;
+  if (!overlap_enabled()) return 0;
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  VLS_CUDA(cudaEventRecord(f->ev_fork, main));
+  VLS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+  *side = f->side;
+  return 0;
+}
+int fork_join(int idx, cudaStream_t main) {
+  if (!overlap_enabled()) return 0;
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  VLS_CUDA(cudaEventRecord(f->ev_join, f->side));
+  VLS_CUDA(cudaStreamWaitEvent(main, f->ev_join, 0));
+  return 0;
 }
 
 }  // namespace
@@ -98,19 +143,8 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated);   V_l^T = Wv_l mem^T + bv_l
   // They run on a forked side stream (event fork/join, capturable into CUDA graphs) so that they overlap layer 0's
   // LayerNorm -> q/k/v projection -> self-attention -> out-projection chain, whose kernels fill < 1 wave of SMs.
-  static cudaStream_t side_stream = nullptr;
-  static cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-  static const bool overlap = !(getenv("VLS_NO_SIDE_STREAM") && getenv("VLS_NO_SIDE_STREAM")[0] == '1');
-  if (overlap && !side_stream) {
-    VLS_CUDA(cudaStreamCreateWithFlags(&side_stream, cudaStreamNonBlocking));
-    VLS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    VLS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-  }
-  cudaStream_t side = overlap ? side_stream : st;
-  if (overlap) {
-    VLS_CUDA(cudaEventRecord(ev_fork, st));
-    VLS_CUDA(cudaStreamWaitEvent(side, ev_fork, 0));
-  }
+  cudaStream_t side;
+  VLS_TRY(fork_begin(0, st, &side));
   {
     GemmArgs k;
     k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
@@ -128,8 +162,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     v.C = vt_all; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
     VLS_TRY(launch_gemm(v, side));
   }
-  if (overlap) VLS_CUDA(cudaEventRecord(ev_join, side));
-  bool joined = !overlap;
+  bool joined = false;
 
   auto attention = [&](const void* K, long long ldk, long long k_bs, const void* Vt, long long ldvt, int nk,
                        int splits) -> int {
@@ -176,7 +209,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g, st));
     }
     if (!joined) {
-      VLS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+      VLS_TRY(fork_join(0, st));
       joined = true;
     }
     VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, vt_all + (size_t)l * B * C * ldv * 2, ldv, Nk,
@@ -287,18 +320,22 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     const vls_dec_layer& L = w->layers[l];
     // -- token self attention (sam/transformer.py:183-191); layer 0 drops the PE and the residual
     const float* pe = l == 0 ? nullptr : tokens0;
+    // -- image-side projections for this layer in one GEMM: [K_t2i | V_t2i | Q_i2t], PE folded in as a residual.
+    //    They only depend on the image keys, so they run on the side stream next to the token self-attention chain.
+    {
+      cudaStream_t side;
+      VLS_TRY(fork_begin(1, st, &side));
+      GemmArgs g = lin(keys_h, C, (long long)T * C, L.img_w, T, 384, C, B, L.img_b, kvq, 1, 384, (long long)T * 384);
+      g.residual = L.img_pe_add; g.ld_res = 384; g.res_bstride = 0;
+      VLS_TRY(launch_gemm(g, side));
+    }
     VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.q_w, L.self_attn.q_b, 256, 0, nullptr, q));
     VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.k_w, L.self_attn.k_b, 256, 0, nullptr, k));
     VLS_TRY(tok_lin(queries, nullptr, 256, L.self_attn.v_w, L.self_attn.v_b, 256, 0, nullptr, v));
     VLS_TRY(launch_tok_self_attn(q, k, v, B, Nt, a, st));
     VLS_TRY(tok_lin(a, nullptr, 256, L.self_attn.o_w, L.self_attn.o_b, 256, 0, l == 0 ? nullptr : queries, q));
     VLS_TRY(launch_ln256_small(q, 256, R, L.n1_w, L.n1_b, LN_EPS, queries, 256, st));
-    // -- image-side projections for this layer in one GEMM: [K_t2i | V_t2i | Q_i2t], PE folded in as a residual
-    {
-      GemmArgs g = lin(keys_h, C, (long long)T * C, L.img_w, T, 384, C, B, L.img_b, kvq, 1, 384, (long long)T * 384);
-      g.residual = L.img_pe_add; g.ld_res = 384; g.res_bstride = 0;
-      VLS_TRY(launch_gemm(g, st));
-    }
+    VLS_TRY(fork_join(1, st));
     // -- tokens -> image cross attention (:193-198)
     VLS_TRY(t2i(L.t2i, kvq, 384, L.n2_w, L.n2_b));
     // -- token MLP (:200-203)
@@ -325,12 +362,15 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
   VLS_TRY(t2i(w->final_t2i, kvq, 256, w->nf_w, w->nf_b));
   // queries == hs: [0]=obj score token, [1]=iou token, [2..5]=mask tokens (mask_decoder.py:213-215)
 
-  // -- upscaling (mask_decoder.py:218-225): ConvT(256->64) as a GEMM, + feat_s1, LN2d, GELU
+  // -- upscaling (mask_decoder.py:218-225): ConvT(256->64) as a GEMM, + feat_s1, LN2d, GELU: on the side stream, next to
+  //    the hyper-network MLPs that only need the mask tokens
+  cudaStream_t up_side;
+  VLS_TRY(fork_begin(1, st, &up_side));
   {
     GemmArgs g = lin(keys_h, C, (long long)T * C, w->up1_w, T, 256, C, B, w->up1_b, scratch, 0, 256, (long long)T * 256);
-    VLS_TRY(launch_gemm(g, st));
+    VLS_TRY(launch_gemm(g, up_side));
   }
-  VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, st));
+  VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, up_side));
   // -- hyper-network MLPs on the 4 mask tokens, batched over tokens (mask_decoder.py:227-232)
   {
     SmallLinArgs s;
@@ -347,8 +387,11 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     s.out = hyper; s.o_sg = 32; s.o_sr = 4 * 32;
     VLS_TRY(launch_small_linear(s, st));
   }
-  // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234)
-  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, st));
+  // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234): needs both branches; it
+  //    then runs on the side stream while the IoU / object-score heads use the caller's
+  VLS_TRY(fork_join(1, st));
+  VLS_TRY(fork_begin(1, st, &up_side));
+  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, up_side));
   // -- IoU head on hs[:,1] and object-score head on hs[:,0] (mask_decoder.py:237-240)
   for (int head = 0; head < 2; ++head) {
     const void* const* Wt = head == 0 ? w->iou_w : w->obj_w;
@@ -366,7 +409,8 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     VLS_TRY(launch_small_linear(s, st));
   }
   // -- mask tokens out
-  return launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st);
+  VLS_TRY(launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st));
+  return fork_join(1, st);
 }
 
 // ================================================================== post-decoder glue
