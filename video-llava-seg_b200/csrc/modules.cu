@@ -186,14 +186,17 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     {
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.sa_qk_w, Nq, 2 * C, C, B, Lw.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
-      VLS_TRY(launch_gemm(g, st));
+      cudaStream_t vside;          // the value projection runs next to the q/k projection (both read LN1(x))
+      VLS_TRY(fork_begin(2, st, &vside));
       GemmArgs v;  // V^T[c][t] = sum_k Wv[c][k] * t[t][k] + bv[c]
       v.A = Lw.sa_v_w; v.lda = C; v.a_bstride = 0;
       v.W = t; v.ldw = C; v.w_bstride = (long long)Nq * C;
       v.M = C; v.N = Nq; v.K = C; v.batch = B;
       v.bias = Lw.sa_v_b; v.bias_mode = 2;
       v.C = vts; v.c_bf16 = 1; v.ldc = ldvs; v.c_bstride = (long long)C * ldvs;
-      VLS_TRY(launch_gemm(v, st));
+      VLS_TRY(launch_gemm(v, vside));
+      VLS_TRY(launch_gemm(g, st));
+      VLS_TRY(fork_join(2, st));
     }
     VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, Nq, s_self));
     {
@@ -476,6 +479,19 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
   float* orow = (float*)ws.take((size_t)B * T * 64 * 4);
   VLS_REQUIRE(m1 && m2 && m3 && col && scratch && x && t && pix && hid && orow, "mem_encoder: workspace carve failed");
 
+  // x = pix_feat_proj(pix_feat) (memory_encoder.py:174) does not depend on the mask: layout / precision conversion +
+  // projection run on the side stream next to the mask down-sampler, whose last 1x1 conv then adds x as its residual
+  {
+    cudaStream_t pside;
+    VLS_TRY(fork_begin(3, st, &pside));
+    if (pix_layout == 0) {
+      VLS_TRY(launch_nchw_to_rows(pix_feat, pix_dtype, pix_strides, nullptr, 0, nullptr, B, C, H, W, nullptr, pix, pside));
+    } else {
+      VLS_TRY(launch_axpy_rows(pix_feat, pix_dtype, pix_strides[0], pix_strides[1], nullptr, 0, 0, 0, 0.f, B, T, C, nullptr,
+                               pix, pside));
+    }
+    VLS_TRY(launch_gemm(lin(pix, C, (long long)T * C, w->pix_w, T, C, C, B, w->pix_b, x, 0, C, (long long)T * C), pside));
+  }
   // mask down-sampler (memory_encoder.py:17-58): 3x (conv3x3 s2 + LN2d + GELU) on CUDA cores, the 4th as im2col + GEMM
   VLS_TRY(launch_mds1(mask, mask_mode, B, 16 * H, 16 * W, (mask_mode == 2 || mask_mode == 3) ? 4 : 1, sig_scale, sig_bias, w->c1_w, w->c1_b,
                       w->ln1_w, w->ln1_b, LN2D_EPS, m1, st));
@@ -484,17 +500,11 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
   VLS_TRY(launch_im2col3x3s2(m3, B, 2 * H, 2 * W, 64, col, st));
   VLS_TRY(launch_gemm(lin(col, 576, (long long)T * 576, w->c4_w, T, C, 576, B, w->c4_b, scratch, 0, C, (long long)T * C), st));
   VLS_TRY(launch_ln256(scratch, B, T, w->ln4_w, w->ln4_b, LN2D_EPS, 1, nullptr, 0, 0, t, (long long)T * C, C, st));
-  VLS_TRY(launch_gemm(lin(t, C, (long long)T * C, w->c5_w, T, C, C, B, w->c5_b, scratch, 0, C, (long long)T * C), st));
-  // x = pix_feat_proj(pix_feat) + mask features (memory_encoder.py:174-175)
-  if (pix_layout == 0) {
-    VLS_TRY(launch_nchw_to_rows(pix_feat, pix_dtype, pix_strides, nullptr, 0, nullptr, B, C, H, W, nullptr, pix, st));
-  } else {
-    VLS_TRY(launch_axpy_rows(pix_feat, pix_dtype, pix_strides[0], pix_strides[1], nullptr, 0, 0, 0, 0.f, B, T, C, nullptr,
-                             pix, st));
-  }
+  // x += mask features (memory_encoder.py:175)
+  VLS_TRY(fork_join(3, st));
   {
-    GemmArgs g = lin(pix, C, (long long)T * C, w->pix_w, T, C, C, B, w->pix_b, x, 0, C, (long long)T * C);
-    g.residual = scratch; g.ld_res = C; g.res_bstride = (long long)T * C;
+    GemmArgs g = lin(t, C, (long long)T * C, w->c5_w, T, C, C, B, w->c5_b, x, 0, C, (long long)T * C);
+    g.residual = x; g.ld_res = C; g.res_bstride = (long long)T * C;
     VLS_TRY(launch_gemm(g, st));
   }
   // fuser: 2 x CXBlock (memory_encoder.py:103-117); gamma is folded into pw2
