@@ -41,6 +41,8 @@ long long vls_launch_count(void);
 void vls_launch_count_add(long long n);
 /* Performance knobs (results are identical for every setting).  "attn_cluster": 1 = each CTA of the attention
  * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each.
+ * "attn_balanced": 1 (default) = long key sequences whose fixed KV split would leave SMs idle are run in balanced mode:
+ * the (query tile, key tile) units are dealt out evenly to one persistent CTA per SM; 0 = always fixed splits.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */

@@ -79,7 +79,10 @@ def test_gemm_rope(dev):
 
 
 @pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 256, 520, 1), (2, 256, 1000, 2), (1, 4096, 4096, 0),
-                                            (1, 4096, 28736, 0), (1, 4096, 28700, 4)])
+                                            (1, 4096, 28736, 0), (1, 4096, 28700, 4),
+                                            # splits=0 with long keys and few query tiles -> balanced ("stream-K") mode:
+                                            # ragged last key tile, 2 batch elements, 3 query tiles (most CTAs cross a tile)
+                                            (1, 4096, 28700, 0), (2, 2048, 16500, 0), (1, 300, 40000, 0)])
 def test_attention_d256(dev, B, Nq, Nk, splits):
     """vs softmax(QK^T/16)V in fp32 on the same bf16 inputs; P is rounded to bf16 inside the kernel
     (as flash-attention does), so the tolerance is 2e-2 on outputs of magnitude ~1."""

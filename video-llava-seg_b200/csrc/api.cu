@@ -21,6 +21,10 @@ int vls_set_tuning(const char* key, int value) {
     g_attn_cluster = value;
     return 0;
   }
+  if (std::string(key) == "attn_balanced") {   // 0: always fixed KV splits, 1: balanced ("stream-K") mode when it helps
+    g_attn_balanced = value != 0;
+    return 0;
+  }
   if (std::string(key) == "pdl") {   // programmatic dependent launch on/off (host.h)
     pdl_set(value != 0);
     return 0;
@@ -74,12 +78,12 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
   a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = vt_bstride;
   a.B = B; a.Nq = Nq; a.Nk = Nk; a.scale = scale; a.splits = splits;
   a.O = O; a.ldo = ldo; a.o_bstride = o_bstride;
-  if (splits > 1) {
+  if (splits != 1) {   // fixed KV splits, or 0 = balanced mode (picked automatically)
     const size_t need = attn_workspace_bytes(B, Nq, splits);
     VLS_REQUIRE(workspace && workspace_bytes >= need, "attention: workspace too small (%zu < %zu)", workspace_bytes,
                 need);
     a.part_o = reinterpret_cast<float*>(workspace);
-    a.part_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + align256((size_t)B * splits * Nq * 256 * 4));
+    a.part_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + attn_part_ml_offset(B, Nq, splits));
   }
   return launch_attention(a, (cudaStream_t)stream);
 }

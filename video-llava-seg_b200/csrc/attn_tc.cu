@@ -17,6 +17,10 @@
 //              more than 8 (lazy rescale of each thread's half of O in TMEM), exp2 with the 1/sqrt(d)*log2(e)
 //              scale folded in, P written back to TMEM as packed bf16.
 // With KV splits, partial (O, m, l) go to a workspace and attn_combine_kernel merges them.
+// Balanced ("stream-K") mode, used when a fixed split would leave SMs idle (B=1: 32 query tiles x 4 splits = 128 of 148
+// SMs): the (query tile, key tile) units of the launch are dealt out evenly to one persistent CTA per SM; a CTA then
+// works on up to two segments (tail of one query tile's keys, head of the next one's), reloading Q in between, and
+// attn_combine_bal_kernel merges the 5-6 partials of each query tile.  Cross-attention launch 112.6 -> 108.7 us.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -43,6 +47,8 @@ constexpr uint16_t PAIR_MASK = 0x3;
 
 struct AttnParams {
   int Nq, Nk, splits;
+  int qtiles, ntiles;    // query tiles per batch element, key tiles per query tile
+  long long units;       // balanced mode: B * qtiles * ntiles (query tile, key tile) work units over gridDim.x CTAs
   float scale_log2;
   bf16* O;
   long long ldo, o_bstride;
@@ -57,7 +63,17 @@ struct AttnParams {
       p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64();                                             \
   } while (0)
 
-template <int CL>  // CTAs per cluster (1: private loads, 2: each CTA multicasts half of every K / V^T tile)
+// One piece of work of a CTA: `n` consecutive key tiles starting at tile t0 of query tile (bz, q0).
+struct Seg {
+  int q0, bz, t0, n, slot;
+};
+
+// CL : CTAs per cluster (1: private loads, 2: each CTA multicasts half of every K / V^T tile)
+// BAL: balanced ("stream-K") mode.  The (query tile, key tile) units of the whole launch are dealt out evenly to
+//      gridDim.x = #SMs persistent CTAs, so a CTA processes up to two SEGMENTS (the tail of one query tile's keys and the
+//      head of the next one's) and every segment leaves a partial (O, m, l) in slot 2*cta + segment.  With 32 query
+//      tiles x 4 fixed KV splits only 128 of the 148 SMs had work.  Barrier phases simply keep counting across segments.
+template <int CL, bool BAL>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -77,19 +93,44 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* s_full = bars + 13;
   uint64_t* p_ready = bars + 15;
   uint64_t* pv_done = bars + 17;
-  uint64_t* o_done = bars + 18;   // single phase: all PV MMAs of this CTA have completed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
+  uint64_t* o_done = bars + 18;   // one phase per segment: all PV MMAs of the segment have completed
+  uint64_t* q_empty = bars + 19;  // BAL: every S MMA of the segment has read Q (the next query tile may be loaded)
+  uint64_t* o_free = bars + 20;   // BAL: the epilogue has read O out of TMEM (the next segment may overwrite it)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
-  const int q0 = blockIdx.x * BM;
-  const int split = blockIdx.y;
-  const int bz = blockIdx.z;
-  const int nt_all = (p.Nk + BN - 1) / BN;
-  const int t0 = (int)((long long)nt_all * split / p.splits);
-  const int t1 = (int)((long long)nt_all * (split + 1) / p.splits);
-  const int n = t1 - t0;
+  // work of this CTA: one segment (fixed KV splits) or up to two (balanced mode)
+  Seg segs[2];
+  int nseg = 1;
+  if (BAL) {
+    const long long u0 = p.units * blockIdx.x / gridDim.x, u1 = p.units * (blockIdx.x + 1) / gridDim.x;
+    const int qt = (int)(u0 / p.ntiles);
+    segs[0].t0 = (int)(u0 - (long long)qt * p.ntiles);
+    segs[0].n = (int)min((long long)(p.ntiles - segs[0].t0), u1 - u0);
+    segs[0].bz = qt / p.qtiles;
+    segs[0].q0 = (qt - segs[0].bz * p.qtiles) * BM;
+    segs[0].slot = 2 * blockIdx.x;
+    const int rest = (int)(u1 - u0) - segs[0].n;
+    segs[1] = segs[0];
+    if (rest > 0) {
+      nseg = 2;
+      segs[1].t0 = 0;
+      segs[1].n = rest;
+      segs[1].bz = (qt + 1) / p.qtiles;
+      segs[1].q0 = (qt + 1 - segs[1].bz * p.qtiles) * BM;
+      segs[1].slot = 2 * blockIdx.x + 1;
+    }
+  } else {
+    const int split = blockIdx.y;
+    segs[0].q0 = blockIdx.x * BM;
+    segs[0].bz = blockIdx.z;
+    segs[0].t0 = (int)((long long)p.ntiles * split / p.splits);
+    segs[0].n = (int)((long long)p.ntiles * (split + 1) / p.splits) - segs[0].t0;
+    segs[0].slot = 0;
+    segs[1] = segs[0];
+  }
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -105,6 +146,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     mbar_init(pv_done, 1);
     mbar_init(o_done, 1);
+    mbar_init(q_empty, 1);
+    mbar_init(o_free, SOFTMAX_THREADS);
     fence_barrier_init();
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
@@ -123,26 +166,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(q_full, Q_BYTES);
+      int jg = 0;   // tiles issued so far over all segments: barrier phases keep counting
+      for (int sg = 0; sg < nseg; ++sg) {
+        const Seg S = segs[sg];
+        if (sg > 0) mbar_wait(q_empty, (sg - 1) & 1);   // the previous segment's S MMAs are done with Q
+        mbar_expect_tx(q_full, Q_BYTES);
 #pragma unroll
-      for (int kp = 0; kp < 4; ++kp) tma_load_3d(sQ + kp * (BM * 128), &tmQ, q_full, kp * 64, q0, bz);
-      for (int j = 0; j < n; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        const int kv0 = (t0 + j) * BN;
-        mbar_wait(&k_empty[st], ph ^ 1);
-        VLS_TRACE(0, j, 0);
-        mbar_expect_tx(&k_full[st], K_BYTES);
-        if (CL > 1) {
-          // K tile: this CTA fetches key rows [rank*64, rank*64+64) of each 64-channel panel for both CTAs
+        for (int kp = 0; kp < 4; ++kp) tma_load_3d(sQ + kp * (BM * 128), &tmQ, q_full, kp * 64, S.q0, S.bz);
+        for (int j = 0; j < S.n; ++j, ++jg) {
+          const int st = jg % KV_STAGES;
+          const uint32_t ph = (jg / KV_STAGES) & 1;
+          const int kv0 = (S.t0 + j) * BN;
+          mbar_wait(&k_empty[st], ph ^ 1);
+          VLS_TRACE(0, jg, 0);
+          mbar_expect_tx(&k_full[st], K_BYTES);
+          if (CL > 1) {
+            // K tile: this CTA fetches key rows [rank*64, rank*64+64) of each 64-channel panel for both CTAs
 #pragma unroll
-          for (int kp = 0; kp < 4; ++kp)
-            tma_load_3d_mc(sK + st * K_BYTES + kp * (BN * 128) + rank * (64 * 128), &tmK, &k_full[st], kp * 64,
-                           kv0 + (int)rank * 64, bz, PAIR_MASK);
-        } else {
+            for (int kp = 0; kp < 4; ++kp)
+              tma_load_3d_mc(sK + st * K_BYTES + kp * (BN * 128) + rank * (64 * 128), &tmK, &k_full[st], kp * 64,
+                             kv0 + (int)rank * 64, S.bz, PAIR_MASK);
+          } else {
 #pragma unroll
-          for (int kp = 0; kp < 4; ++kp)
-            tma_load_3d(sK + st * K_BYTES + kp * (BN * 128), &tmK, &k_full[st], kp * 64, kv0, bz);
+            for (int kp = 0; kp < 4; ++kp)
+              tma_load_3d(sK + st * K_BYTES + kp * (BN * 128), &tmK, &k_full[st], kp * 64, kv0, S.bz);
+          }
         }
       }
     }
@@ -150,79 +198,98 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // V^T producer on its own warp: with one stage per operand an in-order K,V,K,V producer would hold K(j+1)
     // back until PV(j-1) has released the V buffer
     if (lane == 0) {
-      for (int j = 0; j < n; ++j) {
-        const int st = j % KV_STAGES;
-        const uint32_t ph = (j / KV_STAGES) & 1;
-        const int kv0 = (t0 + j) * BN;
-        mbar_wait(&v_empty[st], ph ^ 1);
-        VLS_TRACE(0, j, 1);
-        mbar_expect_tx(&v_full[st], V_BYTES);
-        // V^T tile = two 64-key panels of [256 channels x 128 B]
+      int jg = 0;
+      for (int sg = 0; sg < nseg; ++sg) {
+        const Seg S = segs[sg];
+        for (int j = 0; j < S.n; ++j, ++jg) {
+          const int st = jg % KV_STAGES;
+          const uint32_t ph = (jg / KV_STAGES) & 1;
+          const int kv0 = (S.t0 + j) * BN;
+          mbar_wait(&v_empty[st], ph ^ 1);
+          VLS_TRACE(0, jg, 1);
+          mbar_expect_tx(&v_full[st], V_BYTES);
+          // V^T tile = two 64-key panels of [256 channels x 128 B]
 #pragma unroll
-        for (int vp = 0; vp < 2; ++vp) {
-          if (CL > 1)  // this CTA fetches channel rows [rank*128, rank*128+128) of each panel for both CTAs
-            tma_load_3d_mc(sV + st * V_BYTES + vp * (D * 128) + rank * (128 * 128), &tmV, &v_full[st], kv0 + vp * 64,
-                           (int)rank * 128, bz, PAIR_MASK);
-          else
-            tma_load_3d(sV + st * V_BYTES + vp * (D * 128), &tmV, &v_full[st], kv0 + vp * 64, 0, bz);
+          for (int vp = 0; vp < 2; ++vp) {
+            if (CL > 1)  // this CTA fetches channel rows [rank*128, rank*128+128) of each panel for both CTAs
+              tma_load_3d_mc(sV + st * V_BYTES + vp * (D * 128) + rank * (128 * 128), &tmV, &v_full[st], kv0 + vp * 64,
+                             (int)rank * 128, S.bz, PAIR_MASK);
+            else
+              tma_load_3d(sV + st * V_BYTES + vp * (D * 128), &tmV, &v_full[st], kv0 + vp * 64, 0, S.bz);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && n > 0) {
+    if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D);
       const uint32_t q_addr = smem_u32(sQ);
-      mbar_wait(q_full, 0);
-      auto issue_s = [&](int j) {
-        const int st = j % KV_STAGES;
-        mbar_wait(&k_full[st], (j / KV_STAGES) & 1);
-        VLS_TRACE(1, j, 0);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(sK + st * K_BYTES);
-        const uint32_t d_s = tmem + TM_S + uint32_t(j & 1) * BN;
+      int jg0 = 0;   // global index of the segment's first tile
+      for (int sg = 0; sg < nseg; ++sg) {
+        const int n = segs[sg].n;
+        if (n <= 0) continue;
+        mbar_wait(q_full, sg & 1);
+        auto issue_s = [&](int j) {   // j: tile inside the segment; jg: global tile count (stage / phase bookkeeping)
+          const int jg = jg0 + j;
+          const int st = jg % KV_STAGES;
+          mbar_wait(&k_full[st], (jg / KV_STAGES) & 1);
+          VLS_TRACE(1, jg, 0);
+          tc_fence_after();
+          const uint32_t k_addr = smem_u32(sK + st * K_BYTES);
+          const uint32_t d_s = tmem + TM_S + uint32_t(jg & 1) * BN;
 #pragma unroll
-        for (int kp = 0; kp < 4; ++kp) {
-          const uint64_t qd = make_desc_sw128(q_addr + kp * (BM * 128));
-          const uint64_t kd = make_desc_sw128(k_addr + kp * (BN * 128));
+          for (int kp = 0; kp < 4; ++kp) {
+            const uint64_t qd = make_desc_sw128(q_addr + kp * (BM * 128));
+            const uint64_t kd = make_desc_sw128(k_addr + kp * (BN * 128));
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, qd + 2 * kk, kd + 2 * kk, idesc_s, (kp | kk) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk) umma_ss(d_s, qd + 2 * kk, kd + 2 * kk, idesc_s, (kp | kk) != 0 ? 1u : 0u);
+          }
+          if (CL > 1) umma_commit_mc(&k_empty[st], PAIR_MASK); else umma_commit(&k_empty[st]);
+          umma_commit(&s_full[jg & 1]);
+          if (BAL && j == n - 1) umma_commit(q_empty);   // last S of the segment: Q may be replaced once it completes
+          VLS_TRACE(1, jg, 1);
+        };
+        issue_s(0);
+        for (int j = 0; j < n; ++j) {
+          if (j + 1 < n) issue_s(j + 1);
+          const int jg = jg0 + j;
+          const int st = jg % KV_STAGES;
+          mbar_wait(&p_ready[jg & 1], (jg >> 1) & 1);
+          VLS_TRACE(1, jg, 2);
+          mbar_wait(&v_full[st], (jg / KV_STAGES) & 1);
+          VLS_TRACE(1, jg, 3);
+          if (BAL && sg > 0 && j == 0) mbar_wait(o_free, (sg - 1) & 1);   // the previous segment's O has been read out
+          tc_fence_after();
+          const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+          const uint32_t a_p = tmem + TM_S + uint32_t(jg & 1) * BN;
+#pragma unroll
+          for (int ks = 0; ks < BN / 16; ++ks) {
+            const uint64_t vd = make_desc_sw128(v_addr + (ks >> 2) * (D * 128));
+            umma_ts(tmem + TM_O, a_p + ks * 8, vd + 2 * (ks & 3), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+          }
+          if (CL > 1) umma_commit_mc(&v_empty[st], PAIR_MASK); else umma_commit(&v_empty[st]);
+          umma_commit(pv_done);
+          VLS_TRACE(1, jg, 4);
         }
-        if (CL > 1) umma_commit_mc(&k_empty[st], PAIR_MASK); else umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
-        VLS_TRACE(1, j, 1);
-      };
-      issue_s(0);
-      for (int j = 0; j < n; ++j) {
-        if (j + 1 < n) issue_s(j + 1);
-        const int st = j % KV_STAGES;
-        mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
-        VLS_TRACE(1, j, 2);
-        mbar_wait(&v_full[st], (j / KV_STAGES) & 1);
-        VLS_TRACE(1, j, 3);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
-        const uint32_t a_p = tmem + TM_S + uint32_t(j & 1) * BN;
-#pragma unroll
-        for (int ks = 0; ks < BN / 16; ++ks) {
-          const uint64_t vd = make_desc_sw128(v_addr + (ks >> 2) * (D * 128));
-          umma_ts(tmem + TM_O, a_p + ks * 8, vd + 2 * (ks & 3), idesc_pv, (j | ks) != 0 ? 1u : 0u);
-        }
-        if (CL > 1) umma_commit_mc(&v_empty[st], PAIR_MASK); else umma_commit(&v_empty[st]);
-        umma_commit(pv_done);
-        VLS_TRACE(1, j, 4);
+        umma_commit(o_done);
+        jg0 += n;
       }
-      umma_commit(o_done);
     }
   } else if (warp < 10) {
     const int q = warp & 3;            // TMEM lane quarter (two warps share each quarter)
     const int half = (warp - 2) >> 2;  // 0: columns 0-31 of the S tile / 0-127 of O, 1: the other halves
     const int rl = q * 32 + lane;      // row inside the tile
-    const int row = q0 + rl;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
+    int jg0 = 0;
+    for (int sg = 0; sg < nseg; ++sg) {
+    const Seg S = segs[sg];
+    const int n = S.n, t0 = S.t0, bz = S.bz;
+    const int row = S.q0 + rl;
     float m_used = -INFINITY;
     float l = 0.0f;
-    for (int j = 0; j < n; ++j) {
+    for (int jl = 0; jl < n; ++jl) {
+      const int j = jg0 + jl;          // global tile index: TMEM buffer / barrier phase bookkeeping
       const int b = j & 1;
       mbar_wait(&s_full[b], (j >> 1) & 1);
       if (threadIdx.x == 64) VLS_TRACE(2, j, 0);
@@ -231,7 +298,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       tmem_ld32(tmem + lane_off + TM_S + b * BN + half * 64, r);
       tmem_ld32(tmem + lane_off + TM_S + b * BN + half * 64 + 32, r + 32);
       tc_wait_ld();
-      const int kv0 = (t0 + j) * BN + half * 64;
+      const int kv0 = (t0 + jl) * BN + half * 64;
       const int valid = p.Nk - kv0;  // may be <= 0 for the upper half of the last tile
       float mx = -INFINITY;
       if (valid < 64) {  // only the last key tile of the sequence is ragged
@@ -257,7 +324,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           m_used = m_new;
         }
         l *= alpha;
-        if (j > 0) {
+        if (jl > 0) {
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
@@ -294,7 +361,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // PV_{n-3} has, so pv_done may be one OR two phases behind and a parity wait for phase n-1 would pass in the
       // latter case (caught by the bitwise-determinism test: O read before the last two PVs had landed).  The
       // per-tile rescale wait above is safe: S_j complete => PV_{j-2} complete => at most one phase behind.
-      mbar_wait(o_done, 0);
+      mbar_wait(o_done, sg & 1);
       tc_fence_after();
     }
     // total row sum = sum of the two halves (same m_used on both)
@@ -303,7 +370,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     asm volatile("bar.sync 1, 256;" ::: "memory");
     l += lx[(half ^ 1) * BM + rl];
     const bool row_ok = row < p.Nq;
-    if (p.splits == 1) {
+    if (!BAL && p.splits == 1) {
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
       bf16* out = p.O + (long long)bz * p.o_bstride + (long long)row * p.ldo + half * 128;
 #pragma unroll 1
@@ -322,7 +389,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     } else {
-      const long long prow = ((long long)bz * p.splits + split) * p.Nq + row;
+      // partial row: balanced mode -> [slot][row in tile]; fixed splits -> [batch][split][query row]
+      const long long prow = BAL ? (long long)S.slot * BM + rl : ((long long)bz * p.splits + blockIdx.y) * p.Nq + row;
       float* po = p.part_o + prow * D + half * 128;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
@@ -342,6 +410,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         p.part_ml[prow * 2 + 1] = l;
       }
     }
+    if (BAL) {               // O has left TMEM: the MMA warp may start the next segment's PV accumulation
+      tc_fence_before();
+      mbar_arrive(o_free);
+    }
+    jg0 += n;
+    }  // segments
   }
   tc_fence_before();
   __syncthreads();
@@ -377,14 +451,62 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
   *reinterpret_cast<uint4*>(O + (long long)b * o_bstride + (long long)row * ldo + lane * 8) = o;
 }
 
+// Balanced mode: query tile qt received one partial from every CTA whose unit range overlaps [qt*ntiles, (qt+1)*ntiles);
+// CTA c owns units [c*U/G, (c+1)*U/G) and its partial for qt is its segment 0 if its range STARTS inside qt, else 1.
+__global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
+                                        int qtiles, int ntiles, int G, bf16* __restrict__ O, long long ldo,
+                                        long long o_bstride) {
+  pdl_enter();
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (long long)B * Nq) return;
+  const int lane = threadIdx.x & 31;
+  const int b = (int)(gw / Nq);
+  const int row = (int)(gw % Nq);
+  const int qt = b * qtiles + row / BM, rl = row % BM;
+  const long long U = (long long)B * qtiles * ntiles;
+  const long long first_u = (long long)qt * ntiles, last_u = first_u + ntiles - 1;
+  const int c_first = (int)(((first_u + 1) * G - 1) / U), c_last = (int)(((last_u + 1) * G - 1) / U);
+  float m = -INFINITY;
+  for (int c = c_first; c <= c_last; ++c) {
+    const int seg = ((U * c / G) / ntiles == qt) ? 0 : 1;
+    m = fmaxf(m, part_ml[((long long)(2 * c + seg) * BM + rl) * 2]);
+  }
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float l = 0.0f;
+  for (int c = c_first; c <= c_last; ++c) {
+    const int seg = ((U * c / G) / ntiles == qt) ? 0 : 1;
+    const long long prow = (long long)(2 * c + seg) * BM + rl;
+    const float w = exp2f(part_ml[prow * 2] - m);
+    l += w * part_ml[prow * 2 + 1];
+    const float4* src = reinterpret_cast<const float4*>(part_o + prow * D + lane * 8);
+    const float4 a = src[0], d = src[1];
+    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
+    acc[4] += w * d.x; acc[5] += w * d.y; acc[6] += w * d.z; acc[7] += w * d.w;
+  }
+  const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+  uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                       pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  *reinterpret_cast<uint4*>(O + (long long)b * o_bstride + (long long)row * ldo + lane * 8) = o;
+}
+
+constexpr int BAL_CTAS = 148;   // one persistent CTA per SM of a B200
+
 }  // namespace
 
 long long* g_attn_trace = nullptr;  // dev-only timeline buffer (3*64*8 int64), see tools/trace_attention.py
+int g_attn_balanced = 1;  // 1: balanced mode may be picked by attn_pick_splits (vls_set_tuning "attn_balanced")
 int g_attn_cluster = 1;  // 1: private K/V loads; 2: pairs of query tiles multicast K/V (vls_set_tuning "attn_cluster")
 
+// splits == 0 selects the balanced ("stream-K") mode: 2 partial slots per persistent CTA
 size_t attn_workspace_bytes(int B, int Nq, int splits) {
+  if (splits == 0) return align256((size_t)BAL_CTAS * 2 * BM * D * 4) + align256((size_t)BAL_CTAS * 2 * BM * 2 * 4);
   if (splits <= 1) return 0;
   return align256((size_t)B * splits * Nq * D * 4) + align256((size_t)B * splits * Nq * 2 * 4);
+}
+
+size_t attn_part_ml_offset(int B, int Nq, int splits) {   // byte offset of the (m, l) partials inside the workspace
+  if (splits == 0) return align256((size_t)BAL_CTAS * 2 * BM * D * 4);
+  return align256((size_t)B * splits * Nq * D * 4);
 }
 
 int attn_pick_splits(int B, int Nq, int Nk) {
@@ -394,36 +516,45 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   if (s < 1) s = 1;
   if (s > 8) s = 8;
   while (s > 1 && ntiles / s < 4) --s;  // keep at least 4 KV tiles per split
+  // long key sequences whose fixed split leaves SMs idle (B=1: 32 query tiles x 4 splits = 128 of 148): deal the
+  // (query tile, key tile) units out evenly instead.  Needs <= 2 segments per CTA, i.e. query tiles <= CTAs.
+  const int qt = qtiles * B;
+  if (g_attn_balanced && ntiles >= 64 && qt <= BAL_CTAS && qt * s < BAL_CTAS - 8) return 0;
   return s;
 }
 
 int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.Q && a.K && a.Vt && a.O, "attention: null operand");
-  VLS_REQUIRE(a.Nq > 0 && a.Nk > 0 && a.B > 0 && a.splits >= 1, "attention: bad shape");
+  VLS_REQUIRE(a.Nq > 0 && a.Nk > 0 && a.B > 0 && a.splits >= 0, "attention: bad shape");
   VLS_REQUIRE(a.ldo % 8 == 0, "attention: ldo must be a multiple of 8");
   const int nt = (a.Nk + BN - 1) / BN;
   VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
   VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
   const int qtiles = (a.Nq + BM - 1) / BM;
-  const int cl = (qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
+  const bool bal = a.splits == 0;
+  VLS_REQUIRE(!bal || ((long long)qtiles * a.B <= BAL_CTAS && (long long)qtiles * a.B * nt >= BAL_CTAS),
+              "attention: balanced mode needs query tiles <= %d <= work units", BAL_CTAS);
+  const int cl = (!bal && qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
   CUtensorMap tmQ, tmK, tmV;
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
   VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, cl > 1 ? BN / 2 : BN));
   VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, D, a.B, a.ldvt, a.vt_bstride, cl > 1 ? D / 2 : D));
   AttnParams p;
   p.Nq = a.Nq; p.Nk = a.Nk; p.splits = a.splits;
+  p.qtiles = qtiles; p.ntiles = nt; p.units = (long long)a.B * qtiles * nt;
   p.scale_log2 = a.scale * 1.4426950408889634f;
   p.O = reinterpret_cast<bf16*>(a.O); p.ldo = a.ldo; p.o_bstride = a.o_bstride;
   p.part_o = a.part_o; p.part_ml = a.part_ml;
   p.trace = g_attn_trace;
   static bool attr_set = false;
   if (!attr_set) {
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(qtiles, a.splits, a.B);
+  cfg.gridDim = bal ? dim3(BAL_CTAS, 1, 1) : dim3(qtiles, a.splits, a.B);
   cfg.blockDim = dim3(THREADS);
   cfg.dynamicSmemBytes = SMEM_BYTES;
   cfg.stream = stream;
@@ -435,11 +566,18 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
   prof_begin(slot, stream);
-  if (cl > 1) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2>, tmQ, tmK, tmV, p));
-  else VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1>, tmQ, tmK, tmV, p));
+  if (bal) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1, true>, tmQ, tmK, tmV, p));
+  else if (cl > 1) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, false>, tmQ, tmK, tmV, p));
+  else VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1, false>, tmQ, tmK, tmV, p));
   prof_end(slot, stream);
   VLS_POST_LAUNCH(1);
-  if (a.splits > 1) {
+  if (bal) {
+    const long long rows = (long long)a.B * a.Nq;
+    const int wpb = 8;
+    VLS_CUDA(launch_k(attn_combine_bal_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, a.part_o,
+                      a.part_ml, a.B, a.Nq, qtiles, nt, BAL_CTAS, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
+    VLS_POST_LAUNCH(1);
+  } else if (a.splits > 1) {
     const long long rows = (long long)a.B * a.Nq;
     const int wpb = 8;
     VLS_CUDA(launch_k(attn_combine_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream,  a.part_o, a.part_ml, a.B, a.Nq, a.splits, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));

@@ -43,15 +43,17 @@ struct AttnArgs {
   const void* Vt = nullptr; long long ldvt = 0, vt_bstride = 0;
   int B = 1, Nq = 0, Nk = 0;
   float scale = 0.0625f;
-  int splits = 1;            // KV splits per query tile (>=1)
+  int splits = 1;            // KV splits per query tile (>=1); 0 = balanced ("stream-K") mode
   void* O = nullptr;         // bf16 [B][Nq][ldo]
   long long ldo = 0, o_bstride = 0;
   float* part_o = nullptr;   // workspace when splits > 1: f32 [B][splits][Nq][256]
   float* part_ml = nullptr;  // f32 [B][splits][Nq][2] (running max in log2 domain, sum)
 };
 extern int g_attn_cluster;
+extern int g_attn_balanced;
 extern long long* g_attn_trace;
 size_t attn_workspace_bytes(int B, int Nq, int splits);
+size_t attn_part_ml_offset(int B, int Nq, int splits);
 int attn_pick_splits(int B, int Nq, int Nk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 

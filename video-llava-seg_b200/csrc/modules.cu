@@ -172,9 +172,9 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = (long long)C * ldvt;
     a.B = B; a.Nq = Nq; a.Nk = nk; a.scale = 0.0625f; a.splits = splits;
     a.O = ao; a.ldo = C; a.o_bstride = (long long)Nq * C;
-    if (splits > 1) {
+    if (splits != 1) {   // fixed KV splits, or 0 = balanced mode
       a.part_o = (float*)aws;
-      a.part_ml = (float*)(aws + align256((size_t)B * splits * Nq * 256 * 4));
+      a.part_ml = (float*)(aws + attn_part_ml_offset(B, Nq, splits));
     }
     return launch_attention(a, st);
   };
