@@ -423,7 +423,45 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// Merge KV-split partials: one warp per query row, lane owns 8 channels.
+// Merge partials: one warp per query row, lane owns 8 channels.  The partial rows of a query row (at most 8) are
+// addressed first, then ALL their (m, l) pairs and ALL their O vectors are loaded before any arithmetic: two L2 round
+// trips per row instead of two per partial (the loops over partials used to be latency chains: 9.8 us for 6 partials).
+constexpr int MAX_PARTS = 8;
+__device__ __forceinline__ void combine_row(const float* __restrict__ part_o, const float* __restrict__ part_ml,
+                                            const long long (&prow)[MAX_PARTS], int cnt, int lane, bf16* __restrict__ dst) {
+  float2 ml[MAX_PARTS];
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k)
+    ml[k] = k < cnt ? *reinterpret_cast<const float2*>(part_ml + prow[k] * 2) : make_float2(-INFINITY, 0.f);
+  float4 pa[MAX_PARTS], pd[MAX_PARTS];
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k) {
+    if (k < cnt) {
+      const float4* src = reinterpret_cast<const float4*>(part_o + prow[k] * D + lane * 8);
+      pa[k] = src[0];
+      pd[k] = src[1];
+    }
+  }
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k) m = fmaxf(m, ml[k].x);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float l = 0.0f;
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k) {
+    if (k < cnt) {
+      const float w = exp2f(ml[k].x - m);
+      l += w * ml[k].y;
+      acc[0] += w * pa[k].x; acc[1] += w * pa[k].y; acc[2] += w * pa[k].z; acc[3] += w * pa[k].w;
+      acc[4] += w * pd[k].x; acc[5] += w * pd[k].y; acc[6] += w * pd[k].z; acc[7] += w * pd[k].w;
+    }
+  }
+  const float inv = l > 0.0f ? 1.0f / l : 0.0f;
+  *reinterpret_cast<uint4*>(dst) =
+      make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                 pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+}
+
 __global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
                                     int splits, bf16* __restrict__ O, long long ldo, long long o_bstride) {
   pdl_enter();
@@ -432,61 +470,38 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
   const int lane = threadIdx.x & 31;
   const int b = (int)(gw / Nq);
   const int row = (int)(gw % Nq);
-  float m = -INFINITY;
-  for (int s = 0; s < splits; ++s) m = fmaxf(m, part_ml[(((long long)b * splits + s) * Nq + row) * 2]);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float l = 0.0f;
-  for (int s = 0; s < splits; ++s) {
-    const long long prow = ((long long)b * splits + s) * Nq + row;
-    const float w = exp2f(part_ml[prow * 2] - m);
-    l += w * part_ml[prow * 2 + 1];
-    const float4* src = reinterpret_cast<const float4*>(part_o + prow * D + lane * 8);
-    const float4 a = src[0], c = src[1];
-    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-    acc[4] += w * c.x; acc[5] += w * c.y; acc[6] += w * c.z; acc[7] += w * c.w;
-  }
-  const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-  uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                       pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
-  *reinterpret_cast<uint4*>(O + (long long)b * o_bstride + (long long)row * ldo + lane * 8) = o;
+  long long prow[MAX_PARTS];
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k) prow[k] = ((long long)b * splits + (k < splits ? k : 0)) * Nq + row;
+  combine_row(part_o, part_ml, prow, splits, lane, O + (long long)b * o_bstride + (long long)row * ldo + lane * 8);
 }
 
 // Balanced mode: query tile qt received one partial from every CTA whose unit range overlaps [qt*ntiles, (qt+1)*ntiles);
 // CTA c owns units [c*U/G, (c+1)*U/G) and its partial for qt is its segment 0 if its range STARTS inside qt, else 1.
+// The launcher works that out on the host: entry qt = first CTA | count << 8 | (segment bit per partial) << 16
+// (the first device version did it with 64-bit divisions per row: 940 instructions per row in ncu).
+struct BalTable {
+  uint32_t e[148];
+};
 __global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
-                                        int qtiles, int ntiles, int G, bf16* __restrict__ O, long long ldo,
+                                        int qtiles, const BalTable tab, bf16* __restrict__ O, long long ldo,
                                         long long o_bstride) {
   pdl_enter();
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (gw >= (long long)B * Nq) return;
+  const int gw = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= B * Nq) return;
   const int lane = threadIdx.x & 31;
-  const int b = (int)(gw / Nq);
-  const int row = (int)(gw % Nq);
-  const int qt = b * qtiles + row / BM, rl = row % BM;
-  const long long U = (long long)B * qtiles * ntiles;
-  const long long first_u = (long long)qt * ntiles, last_u = first_u + ntiles - 1;
-  const int c_first = (int)(((first_u + 1) * G - 1) / U), c_last = (int)(((last_u + 1) * G - 1) / U);
-  float m = -INFINITY;
-  for (int c = c_first; c <= c_last; ++c) {
-    const int seg = ((U * c / G) / ntiles == qt) ? 0 : 1;
-    m = fmaxf(m, part_ml[((long long)(2 * c + seg) * BM + rl) * 2]);
+  const int b = gw / Nq;
+  const int row = gw - b * Nq;
+  const int rl = row % BM;
+  const uint32_t e = tab.e[b * qtiles + row / BM];
+  const int c_first = e & 0xff, cnt = (e >> 8) & 0xff;
+  long long prow[MAX_PARTS];
+#pragma unroll
+  for (int k = 0; k < MAX_PARTS; ++k) {
+    const int kk = k < cnt ? k : 0;
+    prow[k] = (long long)(2 * (c_first + kk) + ((e >> (16 + kk)) & 1)) * BM + rl;
   }
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  float l = 0.0f;
-  for (int c = c_first; c <= c_last; ++c) {
-    const int seg = ((U * c / G) / ntiles == qt) ? 0 : 1;
-    const long long prow = (long long)(2 * c + seg) * BM + rl;
-    const float w = exp2f(part_ml[prow * 2] - m);
-    l += w * part_ml[prow * 2 + 1];
-    const float4* src = reinterpret_cast<const float4*>(part_o + prow * D + lane * 8);
-    const float4 a = src[0], d = src[1];
-    acc[0] += w * a.x; acc[1] += w * a.y; acc[2] += w * a.z; acc[3] += w * a.w;
-    acc[4] += w * d.x; acc[5] += w * d.y; acc[6] += w * d.z; acc[7] += w * d.w;
-  }
-  const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-  uint4 o = make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                       pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
-  *reinterpret_cast<uint4*>(O + (long long)b * o_bstride + (long long)row * ldo + lane * 8) = o;
+  combine_row(part_o, part_ml, prow, cnt, lane, O + (long long)b * o_bstride + (long long)row * ldo + lane * 8);
 }
 
 constexpr int BAL_CTAS = 148;   // one persistent CTA per SM of a B200
@@ -519,7 +534,8 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   // long key sequences whose fixed split leaves SMs idle (B=1: 32 query tiles x 4 splits = 128 of 148): deal the
   // (query tile, key tile) units out evenly instead.  Needs <= 2 segments per CTA, i.e. query tiles <= CTAs.
   const int qt = qtiles * B;
-  if (g_attn_balanced && ntiles >= 64 && qt <= BAL_CTAS && qt * s < BAL_CTAS - 8) return 0;
+  // (a query tile then gets at most BAL_CTAS / qt + 2 partials, which must fit the combine's MAX_PARTS)
+  if (g_attn_balanced && ntiles >= 64 && qt <= BAL_CTAS && qt * s < BAL_CTAS - 8 && BAL_CTAS / qt + 2 <= MAX_PARTS) return 0;
   return s;
 }
 
@@ -529,11 +545,13 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.ldo % 8 == 0, "attention: ldo must be a multiple of 8");
   const int nt = (a.Nk + BN - 1) / BN;
   VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
+  VLS_REQUIRE(a.splits <= MAX_PARTS, "attention: at most %d KV splits", MAX_PARTS);
   VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
   const int qtiles = (a.Nq + BM - 1) / BM;
   const bool bal = a.splits == 0;
-  VLS_REQUIRE(!bal || ((long long)qtiles * a.B <= BAL_CTAS && (long long)qtiles * a.B * nt >= BAL_CTAS),
-              "attention: balanced mode needs query tiles <= %d <= work units", BAL_CTAS);
+  VLS_REQUIRE(!bal || ((long long)qtiles * a.B <= BAL_CTAS && (long long)qtiles * a.B * nt >= BAL_CTAS &&
+                       BAL_CTAS / (qtiles * a.B) + 2 <= MAX_PARTS),
+              "attention: balanced mode needs %d / %d <= query tiles <= %d <= work units", BAL_CTAS, MAX_PARTS - 2, BAL_CTAS);
   const int cl = (!bal && qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
   CUtensorMap tmQ, tmK, tmV;
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
@@ -574,8 +592,19 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   if (bal) {
     const long long rows = (long long)a.B * a.Nq;
     const int wpb = 8;
+    BalTable tab;
+    const long long U = (long long)a.B * qtiles * nt;
+    for (int qt = 0; qt < a.B * qtiles; ++qt) {
+      const long long first_u = (long long)qt * nt, last_u = first_u + nt - 1;
+      const int c_first = (int)(((first_u + 1) * BAL_CTAS - 1) / U), c_last = (int)(((last_u + 1) * BAL_CTAS - 1) / U);
+      uint32_t e = (uint32_t)c_first | ((uint32_t)(c_last - c_first + 1) << 8);
+      for (int c = c_first; c <= c_last; ++c)
+        if ((U * c / BAL_CTAS) / nt != qt) e |= 1u << (16 + c - c_first);   // that CTA's range started in an earlier tile
+      tab.e[qt] = e;
+    }
+    VLS_REQUIRE(rows < (1ll << 31), "attention: too many query rows");
     VLS_CUDA(launch_k(attn_combine_bal_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, a.part_o,
-                      a.part_ml, a.B, a.Nq, qtiles, nt, BAL_CTAS, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
+                      a.part_ml, a.B, a.Nq, qtiles, tab, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
     VLS_POST_LAUNCH(1);
   } else if (a.splits > 1) {
     const long long rows = (long long)a.B * a.Nq;
