@@ -564,12 +564,11 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   p.O = reinterpret_cast<bf16*>(a.O); p.ldo = a.ldo; p.o_bstride = a.o_bstride;
   p.part_o = a.part_o; p.part_ml = a.part_ml;
   p.trace = g_attn_trace;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (first_use_on_device(&attr_set)) {
     VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = bal ? dim3(BAL_CTAS, 1, 1) : dim3(qtiles, a.splits, a.B);

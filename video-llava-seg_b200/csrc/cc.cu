@@ -618,11 +618,10 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   VLS_REQUIRE((w % 2) == 0, "width must be an even number");   // connected_components.cu:227
   if (n == 0 || h == 0 || w == 0) return 0;
   if (small_ok(h, w)) {
-    static bool attr[2] = {false, false};
-    if (!attr[FILL]) {
+    static unsigned long long attr[2] = {0, 0};
+    if (first_use_on_device(&attr[FILL])) {
       VLS_CUDA(cudaFuncSetAttribute(cc_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     CC_MAX_BLOCKS * 5));
-      attr[FILL] = true;
     }
     // 128-bit loads need 16-byte aligned rows: W % 16 (uint8) / W % 4 (f32) and an aligned base
     const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0)

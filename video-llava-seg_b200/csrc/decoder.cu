@@ -392,10 +392,9 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
                      cudaStream_t stream) {
   VLS_REQUIRE(M == 4, "decoder: num_mask_tokens must be 4");
   const size_t smem = (size_t)(4 * 32 * 64 + 64 * 33 + 2 * 32 * 65 + 4 * 32 + 32) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (first_use_on_device(&attr)) {
     VLS_CUDA(cudaFuncSetAttribute(up2_masks_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   VLS_CUDA(launch_k(up2_masks_kernel<4>, dim3(dim3((w2 + 31) / 32, h2, B)), dim3(128), smem, stream, reinterpret_cast<const bf16*>(u), w2t, bias, feat, feat_bf16, feat_sb, hyper, h2, w2, masks));
   VLS_POST_LAUNCH(1);

@@ -266,10 +266,9 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   e.residual = a.residual; e.ld_res = a.ld_res; e.res_bstride = a.res_bstride;
   e.C = a.C; e.c_bf16 = a.c_bf16; e.ldc = a.ldc; e.c_bstride = a.c_bstride;
   e.a_div = a.a_div; e.a_mod = a.a_batches; e.w_div = a.w_div; e.w_mod = a.w_batches;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_set = 0;
+  if (first_use_on_device(&attr_set)) {
     VLS_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, STAGES_>, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
-    attr_set = true;
   }
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.batch);
   VLS_CUDA(launch_k(gemm_tn_kernel<BN, STAGES_>, dim3(grid), dim3(THREADS), C_::SMEM, stream, tmA, tmB, e));

@@ -35,6 +35,14 @@ bool pdl_enabled() {
 }
 void pdl_set(bool on) { g_pdl = on ? 1 : 0; }
 
+bool first_use_on_device(unsigned long long* flag_word) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;   // unknown device: just redo the setup
+  const unsigned long long bit = 1ull << dev;
+  const unsigned long long old = __atomic_fetch_or(flag_word, bit, __ATOMIC_ACQ_REL);
+  return (old & bit) == 0;
+}
+
 struct ProfSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
   cudaEvent_t open = nullptr;

@@ -58,6 +58,10 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// One-time per-DEVICE initialisation (cudaFuncSetAttribute is a per-device setting): returns true the first time it is
+// called with this flag word on the current device.  Thread-safe.
+bool first_use_on_device(unsigned long long* flag_word);
+
 // Optional per-kernel device timing (CUDA events on the launching stream), off by default.
 // Used by bench.py to measure the dominant kernel's average launch duration live.
 bool prof_enabled();

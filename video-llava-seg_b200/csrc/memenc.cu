@@ -500,10 +500,9 @@ int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, con
     int R = H;
     while (R > 16 && strips * ((H + R - 1) / R) < 2368) R = (R + 1) / 2;
     const size_t smem = 49 * 128 * sizeof(float2) + 2 * 4 * 16 * sizeof(float);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr = 0;
+    if (first_use_on_device(&attr)) {
       VLS_CUDA(cudaFuncSetAttribute(dwconv7_ln_strip_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr = true;
     }
     VLS_CUDA(launch_k(dwconv7_ln_strip_kernel, dim3((W + DW_TX - 1) / DW_TX, (H + R - 1) / R, B), dim3(128), smem, stream, x, H, W, R, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   }

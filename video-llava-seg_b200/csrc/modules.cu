@@ -42,8 +42,12 @@ bool overlap_enabled() {
   return on;
 }
 int fork_get(int idx, Fork** out) {
-  static Fork forks[4];
-  Fork& f = forks[idx];
+  // per host thread and per device: concurrent callers never share a side stream or its events
+  static thread_local Fork forks[16][4];
+  int dev = 0;
+  VLS_CUDA(cudaGetDevice(&dev));
+  VLS_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
+  Fork& f = forks[dev][idx];
   if (!f.side) {
     VLS_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
     VLS_CUDA(cudaEventCreateWithFlags(&f.ev_fork, cudaEventDisableTiming));
