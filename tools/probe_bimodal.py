@@ -33,11 +33,17 @@ for rep in range(6):
             next(gen)
         torch.cuda.synchronize()
     agg = collections.OrderedDict()
+    evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+    ax = [i for i, e in enumerate(evs) if "axpy_rows" in e.name]
+    firsts = [i for k, i in enumerate(ax) if k % 5 == 0]
+    a_, b_ = firsts[-2], firsts[-1]
+    base = evs[a_].time_range.start
+    line = [(e.time_range.start - base, e.time_range.end - e.time_range.start, re.sub(r"vls::\(anonymous namespace\)::", "", e.name).replace("void ", "")[:30]) for e in evs[a_:b_]]
     for e in prof.events():
         if e.device_type == torch.autograd.DeviceType.CUDA:
             n = re.sub(r"vls::\(anonymous namespace\)::", "", e.name).replace("void ", "")[:34]
             a = agg.setdefault(n, [0, 0.0]); a[0] += 1; a[1] += (e.time_range.end - e.time_range.start) / 4
-    results.append((ms, agg))
+    results.append((ms, agg, line))
     print(f"capture {rep}: {ms:.4f} ms/frame", flush=True)
     gen.close()
 results.sort(key=lambda r: r[0])
@@ -47,3 +53,8 @@ for n in slow[1]:
     d = slow[1][n][1] - fast[1].get(n, [0, 0.0])[1]
     if abs(d) > 1.5:
         print(f"  {d:+8.1f}  {slow[1][n][1]:8.1f} vs {fast[1].get(n, [0, 0.0])[1]:8.1f}  x{slow[1][n][0] // 4}  {n}")
+
+print("side by side (start us, dur): fast | slow")
+for (fs, fd, fn), (ss, sd, sn) in zip(fast[2], slow[2]):
+    flag = " <<<" if abs((ss - fs)) > 15 and fn == sn else ""
+    print(f"{fs:8.1f} {fd:6.1f} {fn:30s} | {ss:8.1f} {sd:6.1f} {sn:30s}{flag}")

@@ -89,6 +89,7 @@ struct SmallLinArgs {
   int G = 1, R = 0, N = 0, K = 0, act = 0;              // act: 0 none, 1 relu, 3 sigmoid
 };
 int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream);
+int launch_small_linear_multi(const SmallLinArgs* a, int count, cudaStream_t stream);  // up to 4 independent problems, one launch
 int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w, const float* b, float eps, float* out,
                        long long o_sr, cudaStream_t stream);
 

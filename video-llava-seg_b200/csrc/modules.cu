@@ -308,13 +308,17 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
   VLS_TRY(launch_nchw_to_rows(image_embeddings, emb_dtype, emb_strides, dense, dense_dtype, dense_strides, B, C, H, W, keys,
                               keys_h, st));
 
-  auto tok_lin = [&](const float* x, const float* xadd, int K, const void* Wt, const float* bias, int N, int act,
-                     const float* res, float* out) -> int {
+  auto tok_args = [&](const float* x, const float* xadd, int K, const void* Wt, const float* bias, int N, int act,
+                      const float* res, float* out) {
     SmallLinArgs s;
     s.x = x; s.x_sr = K; s.xadd = xadd; s.xa_sr = K;
     s.W = Wt; s.bias = bias; s.res = res; s.r_sr = N; s.out = out; s.o_sr = N;
     s.G = 1; s.R = R; s.N = N; s.K = K; s.act = act;
-    return launch_small_linear(s, st);
+    return s;
+  };
+  auto tok_lin = [&](const float* x, const float* xadd, int K, const void* Wt, const float* bias, int N, int act,
+                     const float* res, float* out) -> int {
+    return launch_small_linear(tok_args(x, xadd, K, Wt, bias, N, act, res, out), st);
   };
   auto t2i = [&](const vls_attn_w& A, const void* rows, long long ld, const float* nw, const float* nb) -> int {
     VLS_TRY(tok_lin(queries, tokens0, 256, A.q_w, A.q_b, 128, 0, nullptr, qt));
@@ -336,9 +340,12 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
       g.residual = L.img_pe_add; g.ld_res = 384; g.res_bstride = 0;
       VLS_TRY(launch_gemm(g, side));
     }
-    VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.q_w, L.self_attn.q_b, 256, 0, nullptr, q));
-    VLS_TRY(tok_lin(queries, pe, 256, L.self_attn.k_w, L.self_attn.k_b, 256, 0, nullptr, k));
-    VLS_TRY(tok_lin(queries, nullptr, 256, L.self_attn.v_w, L.self_attn.v_b, 256, 0, nullptr, v));
+    {   // q, k, v projections: three independent problems, one launch
+      const SmallLinArgs qkv[3] = {tok_args(queries, pe, 256, L.self_attn.q_w, L.self_attn.q_b, 256, 0, nullptr, q),
+                                   tok_args(queries, pe, 256, L.self_attn.k_w, L.self_attn.k_b, 256, 0, nullptr, k),
+                                   tok_args(queries, nullptr, 256, L.self_attn.v_w, L.self_attn.v_b, 256, 0, nullptr, v)};
+      VLS_TRY(launch_small_linear_multi(qkv, 3, st));
+    }
     VLS_TRY(launch_tok_self_attn(q, k, v, B, Nt, a, st));
     VLS_TRY(tok_lin(a, nullptr, 256, L.self_attn.o_w, L.self_attn.o_b, 256, 0, l == 0 ? nullptr : queries, q));
     VLS_TRY(launch_ln256_small(q, 256, R, L.n1_w, L.n1_b, LN_EPS, queries, 256, st));
@@ -350,8 +357,11 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     VLS_TRY(tok_lin(hid, nullptr, 2048, L.mlp2_w, L.mlp2_b, 256, 0, queries, a));
     VLS_TRY(launch_ln256_small(a, 256, R, L.n3_w, L.n3_b, LN_EPS, queries, 256, st));
     // -- image -> tokens cross attention (:205-210)
-    VLS_TRY(tok_lin(queries, tokens0, 256, L.i2t.k_w, L.i2t.k_b, 128, 0, nullptr, kt));
-    VLS_TRY(tok_lin(queries, nullptr, 256, L.i2t.v_w, L.i2t.v_b, 128, 0, nullptr, vt));
+    {
+      const SmallLinArgs kv[2] = {tok_args(queries, tokens0, 256, L.i2t.k_w, L.i2t.k_b, 128, 0, nullptr, kt),
+                                  tok_args(queries, nullptr, 256, L.i2t.v_w, L.i2t.v_b, 128, 0, nullptr, vt)};
+      VLS_TRY(launch_small_linear_multi(kv, 2, st));
+    }
     VLS_TRY(launch_i2t_attn(kvq, 384, (long long)T * 384, 256, kt, vt, B, Nt, T, ai, st));
     {
       GemmArgs g = lin(ai, 128, (long long)T * 128, L.i2t.o_w, T, C, 128, B, L.i2t.o_b, scratch, 0, C, (long long)T * C);
@@ -399,21 +409,33 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
   VLS_TRY(fork_join(1, st));
   VLS_TRY(fork_begin(1, st, &up_side));
   VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, up_side));
-  // -- IoU head on hs[:,1] and object-score head on hs[:,0] (mask_decoder.py:237-240)
-  for (int head = 0; head < 2; ++head) {
-    const void* const* Wt = head == 0 ? w->iou_w : w->obj_w;
-    const float* const* bs = head == 0 ? w->iou_b : w->obj_b;
-    SmallLinArgs s;
-    s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
-    s.x = queries + (head == 0 ? 256 : 0); s.x_sr = (long long)Nt * 256;
-    s.W = Wt[0]; s.bias = bs[0]; s.out = hd1; s.o_sr = 256;
-    VLS_TRY(launch_small_linear(s, st));
-    s.x = hd1; s.x_sr = 256; s.W = Wt[1]; s.bias = bs[1]; s.out = hd2;
-    VLS_TRY(launch_small_linear(s, st));
-    s.x = hd2; s.W = Wt[2]; s.bias = bs[2];
-    if (head == 0) { s.N = 4; s.act = w->iou_sigmoid ? 3 : 0; s.out = iou; s.o_sr = 4; }
-    else { s.N = 1; s.act = 0; s.out = obj_logits; s.o_sr = 1; }
-    VLS_TRY(launch_small_linear(s, st));
+  // -- IoU head on hs[:,1] and object-score head on hs[:,0] (mask_decoder.py:237-240): the two 3-layer MLPs advance
+  //    layer by layer in one launch per layer
+  {
+    SmallLinArgs h[2];
+    for (int head = 0; head < 2; ++head) {   // 0: IoU, 1: object score
+      SmallLinArgs& s = h[head];
+      s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
+      s.x = queries + (head == 0 ? 256 : 0); s.x_sr = (long long)Nt * 256;
+      s.W = (head == 0 ? w->iou_w : w->obj_w)[0]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[0];
+      s.out = hd1 + (size_t)head * B * 256; s.o_sr = 256;
+    }
+    VLS_TRY(launch_small_linear_multi(h, 2, st));
+    for (int head = 0; head < 2; ++head) {
+      SmallLinArgs& s = h[head];
+      s.x = hd1 + (size_t)head * B * 256; s.x_sr = 256;
+      s.W = (head == 0 ? w->iou_w : w->obj_w)[1]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[1];
+      s.out = hd2 + (size_t)head * B * 256;
+    }
+    VLS_TRY(launch_small_linear_multi(h, 2, st));
+    for (int head = 0; head < 2; ++head) {
+      SmallLinArgs& s = h[head];
+      s.x = hd2 + (size_t)head * B * 256;
+      s.W = (head == 0 ? w->iou_w : w->obj_w)[2]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[2];
+      if (head == 0) { s.N = 4; s.act = w->iou_sigmoid ? 3 : 0; s.out = iou; s.o_sr = 4; }
+      else { s.N = 1; s.act = 0; s.out = obj_logits; s.o_sr = 1; }
+    }
+    VLS_TRY(launch_small_linear_multi(h, 2, st));
   }
   // -- mask tokens out
   VLS_TRY(launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st));

@@ -151,12 +151,7 @@ struct SmallLin {
   float* out; long long o_sg, o_sr;
   int G, R, N, K, act;  // act: 0 none, 1 relu, 3 sigmoid
 };
-__global__ void small_linear_kernel(const SmallLin p) {
-  pdl_enter();
-  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long total = (long long)p.G * p.R * p.N;
-  if (gw >= total) return;
-  const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void small_linear_warp(const SmallLin& p, long long gw, int lane) {
   const int n = (int)(gw % p.N);
   const int r = (int)((gw / p.N) % p.R);
   const int g = (int)(gw / ((long long)p.N * p.R));
@@ -188,6 +183,30 @@ __global__ void small_linear_kernel(const SmallLin p) {
     if (p.res) acc += p.res[g * p.r_sg + r * p.r_sr + n];
     p.out[g * p.o_sg + r * p.o_sr + n] = acc;
   }
+}
+
+__global__ void small_linear_kernel(const SmallLin p) {
+  pdl_enter();
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= (long long)p.G * p.R * p.N) return;
+  small_linear_warp(p, gw, threadIdx.x & 31);
+}
+
+// Several INDEPENDENT small linears in one launch (the token side of the mask decoder is a chain of 2-3 us kernels:
+// q/k/v projections, the first layers of the hyper-network / IoU / object-score heads, ... run side by side).
+constexpr int SMALL_LIN_MAX = 4;
+struct SmallLinMulti {
+  SmallLin p[SMALL_LIN_MAX];
+  long long first[SMALL_LIN_MAX + 1];   // prefix sums of G*R*N
+};
+__global__ void small_linear_multi_kernel(const SmallLinMulti m, int count) {
+  pdl_enter();
+  const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gw >= m.first[count]) return;
+  int i = 0;
+#pragma unroll
+  for (int k = 1; k < SMALL_LIN_MAX; ++k) i += (k < count && gw >= m.first[k]) ? 1 : 0;
+  small_linear_warp(m.p[i], gw - m.first[i], threadIdx.x & 31);
 }
 
 // LayerNorm over 256 for a handful of token rows (f32 in/out), optional residual-free in-place.
@@ -419,6 +438,36 @@ int launch_small_linear(const SmallLinArgs& a, cudaStream_t stream) {
   if (total == 0) return 0;
   const int wpb = 8;
   VLS_CUDA(launch_k(small_linear_kernel, dim3((unsigned)((total + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, p));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+static int fill_small_lin(const SmallLinArgs& a, SmallLin* p) {
+  VLS_REQUIRE(a.K % 8 == 0, "small_linear: K must be a multiple of 8");
+  p->x = a.x; p->x_sg = a.x_sg; p->x_sr = a.x_sr;
+  p->xadd = a.xadd; p->xa_sg = a.xa_sg; p->xa_sr = a.xa_sr;
+  p->W = reinterpret_cast<const bf16*>(a.W); p->w_sg = a.w_sg;
+  p->bias = a.bias; p->b_sg = a.b_sg;
+  p->res = a.res; p->r_sg = a.r_sg; p->r_sr = a.r_sr;
+  p->out = a.out; p->o_sg = a.o_sg; p->o_sr = a.o_sr;
+  p->G = a.G; p->R = a.R; p->N = a.N; p->K = a.K; p->act = a.act;
+  return 0;
+}
+
+int launch_small_linear_multi(const SmallLinArgs* a, int count, cudaStream_t stream) {
+  VLS_REQUIRE(count >= 1 && count <= SMALL_LIN_MAX, "small_linear_multi: between 1 and %d problems", SMALL_LIN_MAX);
+  if (count == 1) return launch_small_linear(a[0], stream);
+  SmallLinMulti m;
+  m.first[0] = 0;
+  for (int i = 0; i < SMALL_LIN_MAX; ++i) {
+    const SmallLinArgs& src = a[i < count ? i : 0];
+    VLS_TRY(fill_small_lin(src, &m.p[i]));
+    m.first[i + 1] = m.first[i] + (i < count ? (long long)src.G * src.R * src.N : 0);
+  }
+  if (m.first[count] == 0) return 0;
+  const int wpb = 8;
+  VLS_CUDA(launch_k(small_linear_multi_kernel, dim3((unsigned)((m.first[count] + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, m,
+                    count));
   VLS_POST_LAUNCH(1);
   return 0;
 }
