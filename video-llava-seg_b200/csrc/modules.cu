@@ -388,58 +388,49 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     VLS_TRY(launch_gemm(g, up_side));
   }
   VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, up_side));
-  // -- hyper-network MLPs on the 4 mask tokens, batched over tokens (mask_decoder.py:227-232)
+  // -- the three token-side heads advance layer by layer in ONE launch per layer: hyper-network MLPs on the 4 mask
+  //    tokens (mask_decoder.py:227-232), IoU head on hs[:,1] and object-score head on hs[:,0] (:237-240)
   {
-    SmallLinArgs s;
-    s.G = 4; s.R = B; s.K = 256; s.N = 256; s.act = 1;
-    s.x = queries + 2 * 256; s.x_sg = 256; s.x_sr = (long long)Nt * 256;
-    s.W = w->hyper_w[0]; s.w_sg = 256 * 256; s.bias = w->hyper_b[0]; s.b_sg = 256;
-    s.out = hy1; s.o_sg = (long long)B * 256; s.o_sr = 256;
-    VLS_TRY(launch_small_linear(s, st));
-    s.x = hy1; s.x_sg = (long long)B * 256; s.x_sr = 256;
-    s.W = w->hyper_w[1]; s.bias = w->hyper_b[1]; s.out = hy2;
-    VLS_TRY(launch_small_linear(s, st));
-    s.x = hy2; s.N = 32; s.act = 0;
-    s.W = w->hyper_w[2]; s.w_sg = 32 * 256; s.bias = w->hyper_b[2]; s.b_sg = 32;
-    s.out = hyper; s.o_sg = 32; s.o_sr = 4 * 32;
-    VLS_TRY(launch_small_linear(s, st));
-  }
-  // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234): needs both branches; it
-  //    then runs on the side stream while the IoU / object-score heads use the caller's
-  VLS_TRY(fork_join(1, st));
-  VLS_TRY(fork_begin(1, st, &up_side));
-  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, up_side));
-  // -- IoU head on hs[:,1] and object-score head on hs[:,0] (mask_decoder.py:237-240): the two 3-layer MLPs advance
-  //    layer by layer in one launch per layer
-  {
-    SmallLinArgs h[2];
+    SmallLinArgs h[3];
+    SmallLinArgs& hy = h[0];
+    hy.G = 4; hy.R = B; hy.K = 256; hy.N = 256; hy.act = 1;
+    hy.x = queries + 2 * 256; hy.x_sg = 256; hy.x_sr = (long long)Nt * 256;
+    hy.W = w->hyper_w[0]; hy.w_sg = 256 * 256; hy.bias = w->hyper_b[0]; hy.b_sg = 256;
+    hy.out = hy1; hy.o_sg = (long long)B * 256; hy.o_sr = 256;
     for (int head = 0; head < 2; ++head) {   // 0: IoU, 1: object score
-      SmallLinArgs& s = h[head];
+      SmallLinArgs& s = h[1 + head];
       s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
       s.x = queries + (head == 0 ? 256 : 0); s.x_sr = (long long)Nt * 256;
       s.W = (head == 0 ? w->iou_w : w->obj_w)[0]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[0];
       s.out = hd1 + (size_t)head * B * 256; s.o_sr = 256;
     }
-    VLS_TRY(launch_small_linear_multi(h, 2, st));
+    VLS_TRY(launch_small_linear_multi(h, 3, st));
+    hy.x = hy1; hy.x_sg = (long long)B * 256; hy.x_sr = 256;
+    hy.W = w->hyper_w[1]; hy.bias = w->hyper_b[1]; hy.out = hy2;
     for (int head = 0; head < 2; ++head) {
-      SmallLinArgs& s = h[head];
+      SmallLinArgs& s = h[1 + head];
       s.x = hd1 + (size_t)head * B * 256; s.x_sr = 256;
       s.W = (head == 0 ? w->iou_w : w->obj_w)[1]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[1];
       s.out = hd2 + (size_t)head * B * 256;
     }
-    VLS_TRY(launch_small_linear_multi(h, 2, st));
+    VLS_TRY(launch_small_linear_multi(h, 3, st));
+    hy.x = hy2; hy.N = 32; hy.act = 0;
+    hy.W = w->hyper_w[2]; hy.w_sg = 32 * 256; hy.bias = w->hyper_b[2]; hy.b_sg = 32;
+    hy.out = hyper; hy.o_sg = 32; hy.o_sr = 4 * 32;
     for (int head = 0; head < 2; ++head) {
-      SmallLinArgs& s = h[head];
+      SmallLinArgs& s = h[1 + head];
       s.x = hd2 + (size_t)head * B * 256;
       s.W = (head == 0 ? w->iou_w : w->obj_w)[2]; s.bias = (head == 0 ? w->iou_b : w->obj_b)[2];
       if (head == 0) { s.N = 4; s.act = w->iou_sigmoid ? 3 : 0; s.out = iou; s.o_sr = 4; }
       else { s.N = 1; s.act = 0; s.out = obj_logits; s.o_sr = 1; }
     }
-    VLS_TRY(launch_small_linear_multi(h, 2, st));
+    VLS_TRY(launch_small_linear_multi(h, 3, st));
   }
+  // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234): needs both branches
+  VLS_TRY(fork_join(1, st));
+  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, st));
   // -- mask tokens out
-  VLS_TRY(launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st));
-  return fork_join(1, st);
+  return launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st);
 }
 
 // ================================================================== post-decoder glue
