@@ -85,7 +85,9 @@ typedef struct vls_gemm_desc {
 int vls_gemm_bf16(const vls_gemm_desc* d, vls_stream_t stream);
 
 /* softmax(Q K^T * scale) V, one head of dim 256. Q bf16 [B][Nq][ldq], K bf16 [B][Nk][ldk],
- * Vt bf16 [B][256][ldvt] (V transposed), O bf16 [B][Nq][ldo].  splits <= 0: chosen automatically. */
+ * Vt bf16 [B][256][ldvt] (V transposed), O bf16 [B][Nq][ldo].  splits > 0: that many KV splits per query tile;
+ * 0: chosen automatically (fixed splits, or the balanced mode that deals (query tile, key tile) units out evenly to one
+ * persistent CTA per SM when fixed splits would idle SMs); -1: force the balanced mode (fails if the shape does not fit). */
 size_t vls_attention_workspace_bytes(int B, int Nq, int Nk, int splits);
 int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
                        long long k_bstride, const void* Vt, long long ldvt, long long vt_bstride, int B, int Nq, int Nk,

@@ -82,7 +82,11 @@ def test_gemm_rope(dev):
                                             (1, 4096, 28736, 0), (1, 4096, 28700, 4),
                                             # splits=0 with long keys and few query tiles -> balanced ("stream-K") mode:
                                             # ragged last key tile, 2 batch elements, 3 query tiles (most CTAs cross a tile)
-                                            (1, 4096, 28700, 0), (2, 2048, 16500, 0), (1, 300, 40000, 0)])
+                                            (1, 4096, 28700, 0), (2, 2048, 16500, 0), (1, 300, 40000, 0),
+                                            (4, 1024, 16500, 0),
+                                            # forced balanced mode (-1): 256 query tiles over 148 CTAs = up to 3 segments
+                                            # per CTA (tail of a tile, a whole tile, head of the next)
+                                            (8, 4096, 9000, -1), (4, 2048, 16500, -1)])
 def test_attention_d256(dev, B, Nq, Nk, splits):
     """vs softmax(QK^T/16)V in fp32 on the same bf16 inputs; P is rounded to bf16 inside the kernel
     (as flash-attention does), so the tolerance is 2e-2 on outputs of magnitude ~1."""

@@ -62,16 +62,20 @@ int vls_gemm_bf16(const vls_gemm_desc* d, vls_stream_t stream) {
   return launch_gemm(a, (cudaStream_t)stream);
 }
 
+// splits > 0: fixed KV splits; 0: automatic; -1: force the balanced ("stream-K") mode (tests / tuning)
+static int resolve_splits(int B, int Nq, int Nk, int splits) {
+  if (splits == -1) return 0;
+  return splits > 0 ? splits : attn_pick_splits(B, Nq, Nk);
+}
 size_t vls_attention_workspace_bytes(int B, int Nq, int Nk, int splits) {
-  if (splits <= 0) splits = attn_pick_splits(B, Nq, Nk);
-  return attn_workspace_bytes(B, Nq, splits);
+  return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits));
 }
 
 int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
                        long long k_bstride, const void* Vt, long long ldvt, long long vt_bstride, int B, int Nq, int Nk,
                        float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
                        size_t workspace_bytes, vls_stream_t stream) {
-  if (splits <= 0) splits = attn_pick_splits(B, Nq, Nk);
+  splits = resolve_splits(B, Nq, Nk, splits);
   AttnArgs a;
   a.Q = Q; a.ldq = ldq; a.q_bstride = q_bstride;
   a.K = K; a.ldk = ldk; a.k_bstride = k_bstride;

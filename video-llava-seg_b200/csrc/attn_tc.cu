@@ -63,6 +63,7 @@ struct AttnParams {
       p.trace[((role) * 64 + (tile)) * 8 + (slot)] = clock64();                                             \
   } while (0)
 
+constexpr int MAX_SEGS = 4;   // balanced mode: segments per CTA (needs query tiles <= (MAX_SEGS - 1) * CTAs)
 // One piece of work of a CTA: `n` consecutive key tiles starting at tile t0 of query tile (bz, q0).
 struct Seg {
   int q0, bz, t0, n, slot;
@@ -101,26 +102,28 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = CL > 1 ? cluster_ctarank() : 0u;
-  // work of this CTA: one segment (fixed KV splits) or up to two (balanced mode)
-  Seg segs[2];
+  // work of this CTA: one segment (fixed KV splits) or up to MAX_SEGS (balanced mode: its unit range may end one query
+  // tile, cover whole ones and begin another)
+  Seg segs[MAX_SEGS];
   int nseg = 1;
   if (BAL) {
-    const long long u0 = p.units * blockIdx.x / gridDim.x, u1 = p.units * (blockIdx.x + 1) / gridDim.x;
-    const int qt = (int)(u0 / p.ntiles);
-    segs[0].t0 = (int)(u0 - (long long)qt * p.ntiles);
-    segs[0].n = (int)min((long long)(p.ntiles - segs[0].t0), u1 - u0);
-    segs[0].bz = qt / p.qtiles;
-    segs[0].q0 = (qt - segs[0].bz * p.qtiles) * BM;
-    segs[0].slot = 2 * blockIdx.x;
-    const int rest = (int)(u1 - u0) - segs[0].n;
-    segs[1] = segs[0];
-    if (rest > 0) {
-      nseg = 2;
-      segs[1].t0 = 0;
-      segs[1].n = rest;
-      segs[1].bz = (qt + 1) / p.qtiles;
-      segs[1].q0 = (qt + 1 - segs[1].bz * p.qtiles) * BM;
-      segs[1].slot = 2 * blockIdx.x + 1;
+    long long u = p.units * blockIdx.x / gridDim.x;
+    const long long u1 = p.units * (blockIdx.x + 1) / gridDim.x;
+    nseg = 0;
+#pragma unroll
+    for (int k = 0; k < MAX_SEGS; ++k) {
+      segs[k] = Seg{0, 0, 0, 0, 0};
+      if (u < u1) {
+        const int qt = (int)(u / p.ntiles);
+        Seg& S = segs[k];
+        S.t0 = (int)(u - (long long)qt * p.ntiles);
+        S.n = (int)min((long long)(p.ntiles - S.t0), u1 - u);
+        S.bz = qt / p.qtiles;
+        S.q0 = (qt - S.bz * p.qtiles) * BM;
+        S.slot = MAX_SEGS * blockIdx.x + k;
+        u += S.n;
+        nseg = k + 1;
+      }
     }
   } else {
     const int split = blockIdx.y;
@@ -129,9 +132,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     segs[0].t0 = (int)((long long)p.ntiles * split / p.splits);
     segs[0].n = (int)((long long)p.ntiles * (split + 1) / p.splits) - segs[0].t0;
     segs[0].slot = 0;
-    segs[1] = segs[0];
   }
-
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
     for (int s = 0; s < KV_STAGES; ++s) {
@@ -477,11 +478,11 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
 }
 
 // Balanced mode: query tile qt received one partial from every CTA whose unit range overlaps [qt*ntiles, (qt+1)*ntiles);
-// CTA c owns units [c*U/G, (c+1)*U/G) and its partial for qt is its segment 0 if its range STARTS inside qt, else 1.
-// The launcher works that out on the host: entry qt = first CTA | count << 8 | (segment bit per partial) << 16
+// CTA c owns units [c*U/G, (c+1)*U/G) and its partial for qt is its segment number (qt - first query tile of c).
+// The launcher works that out on the host: entry qt = first CTA | count << 8 | (2-bit segment number per partial) << 16
 // (the first device version did it with 64-bit divisions per row: 940 instructions per row in ncu).
 struct BalTable {
-  uint32_t e[148];
+  uint32_t e[3 * 148];
 };
 __global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
                                         int qtiles, const BalTable tab, bf16* __restrict__ O, long long ldo,
@@ -499,7 +500,7 @@ __global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const 
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k) {
     const int kk = k < cnt ? k : 0;
-    prow[k] = (long long)(2 * (c_first + kk) + ((e >> (16 + kk)) & 1)) * BM + rl;
+    prow[k] = (long long)(MAX_SEGS * (c_first + kk) + ((e >> (16 + 2 * kk)) & 3)) * BM + rl;
   }
   combine_row(part_o, part_ml, prow, cnt, lane, O + (long long)b * o_bstride + (long long)row * ldo + lane * 8);
 }
@@ -512,15 +513,26 @@ long long* g_attn_trace = nullptr;  // dev-only timeline buffer (3*64*8 int64), 
 int g_attn_balanced = 1;  // 1: balanced mode may be picked by attn_pick_splits (vls_set_tuning "attn_balanced")
 int g_attn_cluster = 1;  // 1: private K/V loads; 2: pairs of query tiles multicast K/V (vls_set_tuning "attn_cluster")
 
+// balanced mode is possible when every CTA gets at least one unit, at most MAX_SEGS segments, a query tile at most
+// MAX_PARTS partials, and the combine table has room
+static bool bal_ok(int qt, int ntiles) {
+  const long long U = (long long)qt * ntiles;
+  if (U < BAL_CTAS || qt > 3 * BAL_CTAS) return false;
+  const long long per = (U + BAL_CTAS - 1) / BAL_CTAS;          // units per CTA (upper bound)
+  if ((per + ntiles - 1) / ntiles + 1 > MAX_SEGS) return false;  // segments per CTA
+  if (ntiles / (U / BAL_CTAS) + 2 > MAX_PARTS) return false;     // partials per query tile
+  return true;
+}
+
 // splits == 0 selects the balanced ("stream-K") mode: 2 partial slots per persistent CTA
 size_t attn_workspace_bytes(int B, int Nq, int splits) {
-  if (splits == 0) return align256((size_t)BAL_CTAS * 2 * BM * D * 4) + align256((size_t)BAL_CTAS * 2 * BM * 2 * 4);
+  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * D * 4) + align256((size_t)BAL_CTAS * MAX_SEGS * BM * 2 * 4);
   if (splits <= 1) return 0;
   return align256((size_t)B * splits * Nq * D * 4) + align256((size_t)B * splits * Nq * 2 * 4);
 }
 
 size_t attn_part_ml_offset(int B, int Nq, int splits) {   // byte offset of the (m, l) partials inside the workspace
-  if (splits == 0) return align256((size_t)BAL_CTAS * 2 * BM * D * 4);
+  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * D * 4);
   return align256((size_t)B * splits * Nq * D * 4);
 }
 
@@ -531,11 +543,15 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   if (s < 1) s = 1;
   if (s > 8) s = 8;
   while (s > 1 && ntiles / s < 4) --s;  // keep at least 4 KV tiles per split
-  // long key sequences whose fixed split leaves SMs idle (B=1: 32 query tiles x 4 splits = 128 of 148): deal the
-  // (query tile, key tile) units out evenly instead.  Needs <= 2 segments per CTA, i.e. query tiles <= CTAs.
-  const int qt = qtiles * B;
-  // (a query tile then gets at most BAL_CTAS / qt + 2 partials, which must fit the combine's MAX_PARTS)
-  if (g_attn_balanced && ntiles >= 64 && qt <= BAL_CTAS && qt * s < BAL_CTAS - 8 && BAL_CTAS / qt + 2 <= MAX_PARTS) return 0;
+  // long key sequences whose fixed split leaves SMs idle (B=1: 32 query tiles x 4 splits = 128 of 148; B=8: 256 CTAs =
+  // 1.73 waves): deal the (query tile, key tile) units out evenly instead.
+  // Only where the fixed path needs KV splits (and therefore partials + a combine) anyway: with many query tiles
+  // (s == 1) it writes bf16 outputs directly, and trading that for f32 partials cost 17 % at B=8 (measured).
+  if (g_attn_balanced && s >= 2 && ntiles >= 64 && bal_ok(qtiles * B, ntiles)) {
+    const long long ctas = (long long)qtiles * B * s;
+    const long long waves = (ctas + BAL_CTAS - 1) / BAL_CTAS;
+    if (ctas * 100 < waves * BAL_CTAS * 94) return 0;     // the fixed split would leave > 6 % of the SM-waves idle
+  }
   return s;
 }
 
@@ -549,9 +565,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
   const int qtiles = (a.Nq + BM - 1) / BM;
   const bool bal = a.splits == 0;
-  VLS_REQUIRE(!bal || ((long long)qtiles * a.B <= BAL_CTAS && (long long)qtiles * a.B * nt >= BAL_CTAS &&
-                       BAL_CTAS / (qtiles * a.B) + 2 <= MAX_PARTS),
-              "attention: balanced mode needs %d / %d <= query tiles <= %d <= work units", BAL_CTAS, MAX_PARTS - 2, BAL_CTAS);
+  VLS_REQUIRE(!bal || bal_ok(qtiles * a.B, nt), "attention: shape not supported by the balanced mode");
   const int cl = (!bal && qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
   CUtensorMap tmQ, tmK, tmV;
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
@@ -596,9 +610,13 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
     for (int qt = 0; qt < a.B * qtiles; ++qt) {
       const long long first_u = (long long)qt * nt, last_u = first_u + nt - 1;
       const int c_first = (int)(((first_u + 1) * BAL_CTAS - 1) / U), c_last = (int)(((last_u + 1) * BAL_CTAS - 1) / U);
+      VLS_REQUIRE(c_last - c_first + 1 <= MAX_PARTS, "attention: too many partials per query tile");
       uint32_t e = (uint32_t)c_first | ((uint32_t)(c_last - c_first + 1) << 8);
-      for (int c = c_first; c <= c_last; ++c)
-        if ((U * c / BAL_CTAS) / nt != qt) e |= 1u << (16 + c - c_first);   // that CTA's range started in an earlier tile
+      for (int c = c_first; c <= c_last; ++c) {
+        const int seg = qt - (int)((U * c / BAL_CTAS) / nt);   // segment number inside CTA c = tiles since its first one
+        VLS_REQUIRE(seg >= 0 && seg < MAX_SEGS, "attention: segment index out of range");
+        e |= (uint32_t)seg << (16 + 2 * (c - c_first));
+      }
       tab.e[qt] = e;
     }
     VLS_REQUIRE(rows < (1ll << 31), "attention: too many query rows");
