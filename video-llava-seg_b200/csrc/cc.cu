@@ -32,6 +32,7 @@ constexpr int CC_THREADS = 512;
 constexpr int CC_MAX_BLOCKS = 16384;
 constexpr int CC_IDX_BITS = 14;                       // block index < 16384; bits 14.. of a ROOT's word hold its area
 constexpr int CC_IDX_MASK = (1 << CC_IDX_BITS) - 1;
+constexpr int CC_NAME_CAP = 4096;                     // entries of the shared-memory list of NAME blocks (phase D)
 constexpr uint32_t CC_NAME = 0x10u;                   // occupancy byte, bit 4: the block started a new label in phase B
 
 __device__ __forceinline__ int uf_find(const volatile int* s, int n) {
@@ -176,6 +177,8 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
   int* lab = cc_smem;
   uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + nb);
+  uint16_t* name_list = reinterpret_cast<uint16_t*>(occ + ((nb + 15) & ~15));
+  int* name_count = reinterpret_cast<int*>(name_list + CC_NAME_CAP);
   const size_t img_off = (size_t)blockIdx.x * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
@@ -364,16 +367,47 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   __syncthreads();
   CC_MARK(3);
   // D. every parent pointer written so far targets a NAME block (a run that started a new label): flatten the names
-  //    (the only loop-y finds left, a few per region) and hand the area parked on a name to its root.  Afterwards
-  //    block -> name -> root is two plain loads and a root's word is root | area << 14.
-  for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) {
-    if (occ[bi] & CC_NAME) {
-      const int root = ufa_find(lab, bi);
-      if (root != bi) {
-        ufa_move_area(lab, lab[bi], root);
-        lab[bi] = root;
+  //    (the only loop-y finds left) and hand the area parked on a name to its root.  Afterwards block -> name -> root is
+  //    two plain loads and a root's word is root | area << 14.  Names are a few % of the blocks, so they are first
+  //    gathered into a list (128-bit scan of the occupancy bytes) and then handled one per thread with full warps;
+  //    a scan that overflows the list flattens the surplus names in place.
+  auto flatten = [&](int bi) {
+    const int root = ufa_find(lab, bi);
+    if (root != bi) {
+      ufa_move_area(lab, lab[bi], root);
+      lab[bi] = root;
+    }
+  };
+  if (threadIdx.x == 0) *name_count = 0;
+  __syncthreads();
+  {
+    auto push = [&](int bi) {
+      const int slot = atomicAdd(name_count, 1);
+      if (slot < CC_NAME_CAP) name_list[slot] = (uint16_t)bi;
+      else flatten(bi);
+    };
+    const int nvec = (nb & 3) == 0 ? nb >> 4 : 0;     // the occupancy array starts 4*nb bytes into shared memory
+    const uint4* occ4 = reinterpret_cast<const uint4*>(occ);
+    for (int v = threadIdx.x; v < nvec; v += CC_THREADS) {
+      const uint4 o = occ4[v];
+      const uint32_t wds[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        uint32_t m = wds[wi] & 0x10101010u;
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          m &= m - 1;
+          push((v << 4) + (wi << 2) + (bit >> 3));
+        }
       }
     }
+    for (int bi = (nvec << 4) + threadIdx.x; bi < nb; bi += CC_THREADS)
+      if (occ[bi] & CC_NAME) push(bi);
+  }
+  __syncthreads();
+  {
+    const int cnt = min(*name_count, CC_NAME_CAP);
+    for (int i = threadIdx.x; i < cnt; i += CC_THREADS) flatten(name_list[i]);
   }
   __syncthreads();
   CC_MARK(4);
@@ -607,7 +641,7 @@ __global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, in
 bool small_ok(int h, int w) { return (h / 2) * (w / 2) <= CC_MAX_BLOCKS; }
 size_t small_smem(int h, int w) {
   const size_t nb = (size_t)(h / 2) * (w / 2);
-  return (nb * 5 + 15) & ~(size_t)15;
+  return nb * 4 + ((nb + 15) & ~(size_t)15) + CC_NAME_CAP * 2 + 16;
 }
 
 template <bool FILL>
@@ -621,7 +655,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     static unsigned long long attr[2] = {0, 0};
     if (first_use_on_device(&attr[FILL])) {
       VLS_CUDA(cudaFuncSetAttribute(cc_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    CC_MAX_BLOCKS * 5));
+                                    (int)small_smem(256, 256)));
     }
     // 128-bit loads need 16-byte aligned rows: W % 16 (uint8) / W % 4 (f32) and an aligned base
     const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0)
