@@ -164,71 +164,20 @@ __device__ __forceinline__ RowOcc row_occ(const uint8_t* occ, int BW, int by, in
   return o;
 }
 
-// FILL=false: img uint8 -> labels/counts int32.   FILL=true: scores f32 updated in place.
-// Shared memory: one int32 per block (union-find parent; a root's word additionally carries area << 14 once the
-// areas are accumulated) + one occupancy byte per block = 5 B/block, 80 KB at 256 x 256 -> two CTAs per SM, so one
-// image's loads/stores overlap the other's union-find.
-template <bool FILL>
-__global__ void __launch_bounds__(CC_THREADS, 2)
-cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t* counts_all, float* scores_all,
-                int max_area, float fill_value, int vec) {
-  pdl_enter();
-  extern __shared__ int cc_smem[];
-  const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
-  int* lab = cc_smem;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + nb);
-  uint16_t* name_list = reinterpret_cast<uint16_t*>(occ + ((nb + 15) & ~15));
-  int* name_count = reinterpret_cast<int*>(name_list + CC_NAME_CAP);
-  const size_t img_off = (size_t)blockIdx.x * H * W;
-  const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
-                         : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = CC_THREADS / 32;
+// Phases B-D of the shared-memory labeller on a BH x BW block region held in `lab` / `occ` (row pitch BW), executed by
+// the whole CTA (nthreads = blockDim.x, a multiple of 32).  `occ` must be complete (followed by __syncthreads) on
+// entry; on return (after the caller's __syncthreads) every occupied block's word is a NAME block index, every name's
+// word its root, and a root's word root | area << 14.
+__device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, int BW, uint16_t* name_list,
+                                                int* name_count, int name_cap) {
+  const int nthreads = blockDim.x;
+  const int nb = BH * BW;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
   const int chunks = (BW + 31) >> 5;
   // warp-row tasks in column-strip-major order; each warp owns a contiguous band of rows of one strip and walks it
   // top-down, which (with path compression) keeps the union-find chains a few hops long
   const int ntask = BH * chunks, per = (ntask + nwarps - 1) / nwarps;
   const int t_begin = warp * per, t_end = min(ntask, t_begin + per);
-
-#ifdef CC_TRACE
-  long long tr[6];
-  tr[0] = clock64();
-#define CC_MARK(i) tr[i] = clock64()
-#else
-#define CC_MARK(i)
-#endif
-  // A. occupancy
-  if (vec) {
-    if (FILL) {  // 2 x float4 -> 2 blocks
-      const float* f = reinterpret_cast<const float*>(img);
-      const int upr = W >> 2, units = BH * upr;
-#pragma unroll 4
-      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
-        const int by = u / upr, k = u - by * upr;
-        const float4 t = *reinterpret_cast<const float4*>(f + (size_t)(2 * by) * W + 4 * k);
-        const float4 b = *reinterpret_cast<const float4*>(f + (size_t)(2 * by + 1) * W + 4 * k);
-        const uint32_t o0 = (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
-        const uint32_t o1 = (t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u);
-        *reinterpret_cast<uint16_t*>(occ + by * BW + 2 * k) = (uint16_t)(o0 | (o1 << 8));
-      }
-    } else {     // 2 x 16 pixels -> 8 blocks
-      const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
-      const int upr = W >> 4, units = BH * upr;
-#pragma unroll 2
-      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
-        const int by = u / upr, k = u - by * upr;
-        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 16 * k);
-        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 16 * k);
-        uint2 o;
-        o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
-        o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
-        *reinterpret_cast<uint2*>(occ + by * BW + 8 * k) = o;
-      }
-    }
-  } else {
-    for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
-  }
-  __syncthreads();
-  CC_MARK(1);
   // B. region labelling.  A region = this warp's band of rows within one 32-block column strip, walked top-down with
   //    the previous row's labels kept in REGISTERS: a run takes the smallest label among the upper blocks it touches
   //    (segmented min-scan over the run's lanes) or becomes a new root; shared memory sees one store per block.
@@ -320,7 +269,6 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
     if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
   }
   __syncthreads();
-  CC_MARK(2);
   // C. seams between regions (generic lock-free unions; every region is already labelled)
   //    C1: the first row of each band against the last row of the band above, inside the strip
   if (t_begin < t_end) {
@@ -365,7 +313,6 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
     }
   }
   __syncthreads();
-  CC_MARK(3);
   // D. every parent pointer written so far targets a NAME block (a run that started a new label): flatten the names
   //    (the only loop-y finds left) and hand the area parked on a name to its root.  Afterwards block -> name -> root is
   //    two plain loads and a root's word is root | area << 14.  Names are a few % of the blocks, so they are first
@@ -383,12 +330,12 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   {
     auto push = [&](int bi) {
       const int slot = atomicAdd(name_count, 1);
-      if (slot < CC_NAME_CAP) name_list[slot] = (uint16_t)bi;
+      if (slot < name_cap) name_list[slot] = (uint16_t)bi;
       else flatten(bi);
     };
     const int nvec = (nb & 3) == 0 ? nb >> 4 : 0;     // the occupancy array starts 4*nb bytes into shared memory
     const uint4* occ4 = reinterpret_cast<const uint4*>(occ);
-    for (int v = threadIdx.x; v < nvec; v += CC_THREADS) {
+    for (int v = threadIdx.x; v < nvec; v += nthreads) {
       const uint4 o = occ4[v];
       const uint32_t wds[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
@@ -401,14 +348,77 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
         }
       }
     }
-    for (int bi = (nvec << 4) + threadIdx.x; bi < nb; bi += CC_THREADS)
+    for (int bi = (nvec << 4) + threadIdx.x; bi < nb; bi += nthreads)
       if (occ[bi] & CC_NAME) push(bi);
   }
   __syncthreads();
   {
-    const int cnt = min(*name_count, CC_NAME_CAP);
-    for (int i = threadIdx.x; i < cnt; i += CC_THREADS) flatten(name_list[i]);
+    const int cnt = min(*name_count, name_cap);
+    for (int i = threadIdx.x; i < cnt; i += nthreads) flatten(name_list[i]);
   }
+}
+
+// FILL=false: img uint8 -> labels/counts int32.   FILL=true: scores f32 updated in place.
+// Shared memory: one int32 per block (union-find parent; a root's word additionally carries area << 14 once the
+// areas are accumulated) + one occupancy byte per block = 5 B/block, 80 KB at 256 x 256 -> two CTAs per SM, so one
+// image's loads/stores overlap the other's union-find.
+template <bool FILL>
+__global__ void __launch_bounds__(CC_THREADS, 2)
+cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t* counts_all, float* scores_all,
+                int max_area, float fill_value, int vec) {
+  pdl_enter();
+  extern __shared__ int cc_smem[];
+  const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
+  int* lab = cc_smem;
+  uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + nb);
+  uint16_t* name_list = reinterpret_cast<uint16_t*>(occ + ((nb + 15) & ~15));
+  int* name_count = reinterpret_cast<int*>(name_list + CC_NAME_CAP);
+  const size_t img_off = (size_t)blockIdx.x * H * W;
+  const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
+                         : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = CC_THREADS / 32;
+
+#ifdef CC_TRACE
+  long long tr[6];
+  tr[0] = clock64();
+#define CC_MARK(i) tr[i] = clock64()
+#else
+#define CC_MARK(i)
+#endif
+  // A. occupancy
+  if (vec) {
+    if (FILL) {  // 2 x float4 -> 2 blocks
+      const float* f = reinterpret_cast<const float*>(img);
+      const int upr = W >> 2, units = BH * upr;
+#pragma unroll 4
+      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
+        const int by = u / upr, k = u - by * upr;
+        const float4 t = *reinterpret_cast<const float4*>(f + (size_t)(2 * by) * W + 4 * k);
+        const float4 b = *reinterpret_cast<const float4*>(f + (size_t)(2 * by + 1) * W + 4 * k);
+        const uint32_t o0 = (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
+        const uint32_t o1 = (t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u);
+        *reinterpret_cast<uint16_t*>(occ + by * BW + 2 * k) = (uint16_t)(o0 | (o1 << 8));
+      }
+    } else {     // 2 x 16 pixels -> 8 blocks
+      const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
+      const int upr = W >> 4, units = BH * upr;
+#pragma unroll 2
+      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
+        const int by = u / upr, k = u - by * upr;
+        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 16 * k);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 16 * k);
+        uint2 o;
+        o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
+        o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
+        *reinterpret_cast<uint2*>(occ + by * BW + 8 * k) = o;
+      }
+    }
+  } else {
+    for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
+  }
+  __syncthreads();
+  CC_MARK(1);
+  cc_label_region(lab, occ, BH, BW, name_list, name_count, CC_NAME_CAP);
   __syncthreads();
   CC_MARK(4);
   // E. outputs
@@ -484,75 +494,136 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
 }
 
 // ------------------------------------------------------------------ tiled path (images larger than 256 x 256)
-// Tile = 64 x 128 pixels = 32 x 64 blocks, labelled entirely in shared memory with the same warp-level
-// run merge as the small path; only tile-border blocks take part in global atomicMin unions.
-//   cc_t_label   : occupancy (also cached as 1 byte / block for the later passes), local union-find,
-//                  forest[block's top-left pixel] = GLOBAL pixel index of the local root
-//   cc_t_border  : unions across tile borders (top row: up / up-left / up-right; left column: left / up-left;
-//                  right column: up-right)
-//   cc_t_count   : global find + path compression, area[root] += popcount (warp-aggregated atomics)
-//   cc_t_final   : 8-byte stores of labels / areas (or sparse in-place fill of small holes)
-constexpr int TBH = 32, TBW = 64, T_THREADS = 256;
+// Tile = 64 x 128 pixels = 32 x 64 blocks, labelled in shared memory by the same region labeller as the small path.
+// Global state is COMPACT (per 2x2 block, not per pixel):
+//   forest[block] = parent block index << 4 | occupancy nibble      (1 B / pixel; doubles as the occupancy array)
+//   area[block]   = pixel count, valid at tile-local roots only     (sparse writes, never cleared)
+//   list          = the tile-local roots that touch their tile's border (the only ones a border union can demote)
+//   cc_t_label  : occupancy -> shared-memory labelling -> forest words, root areas, open-root list
+//   cc_t_border : lock-free min-root unions across tile borders on the forest words
+//   cc_t_areas  : every listed root that is no longer a root hands its area to its new root
+//   cc_t_final  : block -> root (usually one hop), 8-byte stores of labels / areas (or sparse fill of small holes)
+// DRAM traffic ~11 B/pixel for 9 algorithmic (the first version scattered the forest into the labels array, kept separate
+// occupancy and area arrays and cleared one of them: ~23 B/pixel).
+constexpr int TBH = 32, TBW = 64, T_THREADS = 256, T_NAME_CAP = 512;
+constexpr int T_BORDER = 2 * (TBH + TBW);   // open-root list entries per tile (one per border block at most)
 
-template <bool FILL>
-__global__ void __launch_bounds__(T_THREADS)
-cc_t_label(const void* img_all, const float* scores_all, int H, int W, int32_t* forest_all, uint8_t* occ_all) {
-  pdl_enter();
-  __shared__ int lab[TBH * TBW];
-  __shared__ uint8_t occ[TBH * TBW];
-  const int BH = H >> 1, BW = W >> 1;
-  const size_t off = (size_t)blockIdx.z * H * W;
-  const void* img = FILL ? static_cast<const void*>(scores_all + off)
-                         : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + off);
-  const int by0 = blockIdx.y * TBH, bx0 = blockIdx.x * TBW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = T_THREADS / 32;
-  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
-    const int by = by0 + i / TBW, bx = bx0 + i % TBW;
-    const uint32_t o = (by < BH && bx < BW) ? load_occ<FILL>(img, H, W, by, bx, 0.f) : 0u;
-    occ[i] = (uint8_t)o;
-    if (by < BH && bx < BW) occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx] = (uint8_t)o;
+__device__ __forceinline__ int gfind(const volatile uint32_t* f, int n) {
+  uint32_t w = f[n];
+  while ((int)(w >> 4) != n) {
+    n = (int)(w >> 4);
+    w = f[n];
   }
-  __syncthreads();
-  constexpr int CH = TBW / 32;
-  for (int t = warp; t < TBH * CH; t += nwarps) {
-    const int ly = t / CH, c0 = (t % CH) << 5, lx = c0 + lane, li = ly * TBW + lx;
-    const uint32_t me = occ[li], left = lx > 0 ? occ[li - 1] : 0u;
-    const uint32_t hm = __ballot_sync(0xffffffffu, conn_left(me, left));
-    const uint32_t stops = (~hm | 1u) & (0xffffffffu >> (31 - lane));
-    lab[li] = ly * TBW + c0 + (31 - __clz(stops));
-  }
-  __syncthreads();
-  for (int t = warp; t < TBH * CH; t += nwarps) {
-    const int ly = t / CH, c0 = (t % CH) << 5, lx = c0 + lane, li = ly * TBW + lx;
-    const uint32_t me = occ[li], left = lx > 0 ? occ[li - 1] : 0u;
-    const bool h = conn_left(me, left);
-    uint32_t up = 0, ul = 0, ur = 0;
-    if (ly > 0) {
-      up = occ[li - TBW];
-      if (lx > 0) ul = occ[li - TBW - 1];
-      if (lx + 1 < TBW) ur = occ[li - TBW + 1];
+  return n;
+}
+// min-root union on words parent << 4 | occupancy: the nibble of a node never changes, so comparing whole words orders
+// by parent
+__device__ __forceinline__ void gunion(uint32_t* f, int a, int b) {
+  int ra = gfind(f, a), rb = gfind(f, b);
+  while (ra != rb) {
+    if (ra < rb) {
+      const int t = ra;
+      ra = rb;
+      rb = t;
     }
-    const bool cu = conn_up(me, up);
-    const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
-    const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
-    const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
-    const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
-    if (lane == 0 && h) uf_union(lab, li, li - 1);
-    if (cu && !cu_redundant) uf_union(lab, li, li - TBW);
-    if (cul) uf_union(lab, li, li - TBW - 1);
-    if (cur) uf_union(lab, li, li - TBW + 1);
-  }
-  __syncthreads();
-  int32_t* forest = forest_all + off;
-  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
-    const int by = by0 + i / TBW, bx = bx0 + i % TBW;
-    if (by >= BH || bx >= BW) continue;
-    const int r = occ[i] ? uf_find(lab, i) : i;
-    forest[(2 * by) * W + 2 * bx] = (2 * (by0 + r / TBW)) * W + 2 * (bx0 + r % TBW);
+    const uint32_t nib = reinterpret_cast<const volatile uint32_t*>(f)[ra] & 15u;
+    const uint32_t old = atomicMin(f + ra, ((uint32_t)rb << 4) | nib);
+    if ((int)(old >> 4) == ra) break;
+    ra = gfind(f, (int)(old >> 4));
+    rb = gfind(f, rb);
   }
 }
 
-__global__ void cc_t_border(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all) {
+template <bool FILL>
+__global__ void __launch_bounds__(T_THREADS)
+cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, uint32_t* forest_all, int32_t* area_all,
+           int* list_count, int2* list) {
+  pdl_enter();
+  __shared__ int lab[TBH * TBW];
+  __shared__ __align__(16) uint8_t occ[TBH * TBW];
+  __shared__ uint16_t names[T_NAME_CAP];
+  __shared__ int name_count;
+  const int BHg = H >> 1, BWg = W >> 1;
+  const int z = blockIdx.z;
+  const size_t off = (size_t)z * H * W;
+  const void* img = FILL ? static_cast<const void*>(scores_all + off)
+                         : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + off);
+  const int by0 = blockIdx.y * TBH, bx0 = blockIdx.x * TBW;
+  // A. occupancy of the tile (blocks outside the image are empty)
+  if (vec && !FILL) {   // 2 x 16 pixels -> 8 blocks per thread: exactly one unit per thread
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
+    for (int u = threadIdx.x; u < TBH * (TBW / 8); u += T_THREADS) {
+      const int ly = u / (TBW / 8), k = u % (TBW / 8);
+      const int by = by0 + ly, bx = bx0 + 8 * k;
+      uint2 o = make_uint2(0u, 0u);
+      if (by < BHg && bx < BWg) {   // W % 16 == 0: a unit is inside the image or completely outside
+        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 2 * bx);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 2 * bx);
+        o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
+        o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
+      }
+      *reinterpret_cast<uint2*>(occ + ly * TBW + 8 * k) = o;
+    }
+  } else if (vec && FILL) {   // 2 x float4 -> 2 blocks
+    const float* f = reinterpret_cast<const float*>(img);
+#pragma unroll 4
+    for (int u = threadIdx.x; u < TBH * (TBW / 2); u += T_THREADS) {
+      const int ly = u / (TBW / 2), k = u % (TBW / 2);
+      const int by = by0 + ly, bx = bx0 + 2 * k;
+      uint32_t o = 0;
+      if (by < BHg && bx < BWg) {   // W % 4 == 0
+        const float4 t = *reinterpret_cast<const float4*>(f + (size_t)(2 * by) * W + 2 * bx);
+        const float4 b = *reinterpret_cast<const float4*>(f + (size_t)(2 * by + 1) * W + 2 * bx);
+        o = (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
+        o |= ((t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u)) << 8;
+      }
+      *reinterpret_cast<uint16_t*>(occ + ly * TBW + 2 * k) = (uint16_t)o;
+    }
+  } else {
+    for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
+      const int by = by0 + i / TBW, bx = bx0 + i % TBW;
+      occ[i] = (by < BHg && bx < BWg) ? (uint8_t)load_occ<FILL>(img, H, W, by, bx, 0.f) : (uint8_t)0;
+    }
+  }
+  __syncthreads();
+  cc_label_region(lab, occ, TBH, TBW, names, &name_count, T_NAME_CAP);
+  __syncthreads();
+  // roots that reach the tile border (bit 5 of the root's occupancy byte; every writer stores the same bit)
+  for (int k = threadIdx.x; k < T_BORDER; k += T_THREADS) {
+    int ly, lx;
+    if (k < TBW) { ly = 0; lx = k; }
+    else if (k < 2 * TBW) { ly = TBH - 1; lx = k - TBW; }
+    else if (k < 2 * TBW + TBH) { ly = k - 2 * TBW; lx = 0; }
+    else { ly = k - 2 * TBW - TBH; lx = TBW - 1; }
+    const int i = ly * TBW + lx;
+    if (occ[i] & 0xFu) {
+      const int root = lab[lab[i] & CC_IDX_MASK] & CC_IDX_MASK;
+      occ[root] = (uint8_t)(occ[root] | 0x20u);
+    }
+  }
+  __syncthreads();
+  uint32_t* forest = forest_all + (size_t)z * BHg * BWg;
+  int32_t* area = area_all + (size_t)z * BHg * BWg;
+  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
+    const int ly = i / TBW, lx = i % TBW, by = by0 + ly, bx = bx0 + lx;
+    if (by >= BHg || bx >= BWg) continue;
+    const uint32_t o = occ[i];
+    const int gb = by * BWg + bx;
+    if (o & 0xFu) {
+      const int root = lab[lab[i] & CC_IDX_MASK] & CC_IDX_MASK;
+      const int groot = (by0 + root / TBW) * BWg + bx0 + root % TBW;
+      forest[gb] = ((uint32_t)groot << 4) | (o & 0xFu);
+      if (root == i) {
+        area[gb] = (int)((uint32_t)lab[i] >> CC_IDX_BITS);
+        if (o & 0x20u) list[atomicAdd(list_count, 1)] = make_int2(z, gb);
+      }
+    } else {
+      forest[gb] = (uint32_t)gb << 4;
+    }
+  }
+}
+
+__global__ void cc_t_border(int H, int W, uint32_t* forest_all) {
   pdl_enter();
   const int BH = H >> 1, BW = W >> 1;
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
@@ -567,57 +638,58 @@ __global__ void cc_t_border(const uint8_t* __restrict__ occ_all, int H, int W, i
   else { ly = k - TBW - TBH; lx = TBW - 1; kind = 2; }
   const int by = ty * TBH + ly, bx = tx * TBW + lx;
   if (by >= BH || bx >= BW) return;
-  const uint8_t* occ = occ_all + (size_t)blockIdx.z * BH * BW;
-  int32_t* forest = forest_all + (size_t)blockIdx.z * H * W;
-  const uint32_t me = occ[(size_t)by * BW + bx];
+  uint32_t* forest = forest_all + (size_t)blockIdx.z * BH * BW;
+  const int idx = by * BW + bx;
+  const uint32_t me = forest[idx] & 15u;   // the nibble of a word never changes
   if (!me) return;
-  const int idx = 2 * by * W + 2 * bx;
-  auto at = [&](int y, int x) -> uint32_t { return (y >= 0 && x >= 0 && x < BW) ? occ[(size_t)y * BW + x] : 0u; };
+  auto at = [&](int y, int x) -> uint32_t { return (y >= 0 && x >= 0 && x < BW) ? (forest[y * BW + x] & 15u) : 0u; };
   if (kind == 0 && by > 0) {
-    if (conn_up(me, at(by - 1, bx))) uf_union(forest, idx, idx - 2 * W);
-    if (conn_upleft(me, at(by - 1, bx - 1))) uf_union(forest, idx, idx - 2 * W - 2);
-    if (conn_upright(me, at(by - 1, bx + 1))) uf_union(forest, idx, idx - 2 * W + 2);
+    if (conn_up(me, at(by - 1, bx))) gunion(forest, idx, idx - BW);
+    if (conn_upleft(me, at(by - 1, bx - 1))) gunion(forest, idx, idx - BW - 1);
+    if (conn_upright(me, at(by - 1, bx + 1))) gunion(forest, idx, idx - BW + 1);
   } else if (kind == 1 && bx > 0) {
-    if (conn_left(me, at(by, bx - 1))) uf_union(forest, idx, idx - 2);
-    if (ly > 0 && conn_upleft(me, at(by - 1, bx - 1))) uf_union(forest, idx, idx - 2 * W - 2);
+    if (conn_left(me, at(by, bx - 1))) gunion(forest, idx, idx - 1);
+    if (ly > 0 && conn_upleft(me, at(by - 1, bx - 1))) gunion(forest, idx, idx - BW - 1);
   } else if (kind == 2 && ly > 0) {
-    if (conn_upright(me, at(by - 1, bx + 1))) uf_union(forest, idx, idx - 2 * W + 2);
+    if (conn_upright(me, at(by - 1, bx + 1))) gunion(forest, idx, idx - BW + 1);
   }
 }
 
-__global__ void cc_t_count(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* forest_all, int32_t* area_all) {
+__global__ void cc_t_areas(int H, int W, const uint32_t* __restrict__ forest_all, int32_t* area_all,
+                           const int* __restrict__ list_count, const int2* __restrict__ list) {
   pdl_enter();
-  const int BW = W >> 1, BH = H >> 1;
-  const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
-  const bool in = bx < BW && by < BH;
-  const size_t off = (size_t)blockIdx.z * H * W;
-  const uint32_t me = in ? occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx] : 0u;
-  int root = -1 - (int)(threadIdx.x & 31);
-  if (me) {
-    const int idx = 2 * by * W + 2 * bx;
-    root = uf_find(forest_all + off, idx);
-    forest_all[off + idx] = root;
-  }
-  const uint32_t peers = __match_any_sync(0xffffffffu, root);
-  const int area = __reduce_add_sync(peers, (int)__popc(me));
-  if (me && (int)(threadIdx.x & 31) == (__ffs(peers) - 1)) atomicAdd(area_all + off + root, area);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *list_count) return;
+  const int2 e = list[i];
+  const size_t nblk = (size_t)(H >> 1) * (W >> 1);
+  const int g = gfind(forest_all + (size_t)e.x * nblk, e.y);
+  if (g != e.y) atomicAdd(area_all + (size_t)e.x * nblk + g, area_all[(size_t)e.x * nblk + e.y]);
 }
 
 template <bool FILL>
-__global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, int32_t* labels_all,
-                           const int32_t* __restrict__ area_all, int32_t* counts_all, float* scores_all, int max_area,
-                           float fill_value) {
+__global__ void cc_t_final(int H, int W, const uint32_t* __restrict__ forest_all, const int32_t* __restrict__ area_all,
+                           int32_t* labels_all, int32_t* counts_all, float* scores_all, int max_area, float fill_value) {
   pdl_enter();
   const int BW = W >> 1, BH = H >> 1;
   const int bx = blockIdx.x * blockDim.x + threadIdx.x, by = blockIdx.y;
   if (bx >= BW || by >= BH) return;
+  const size_t nblk = (size_t)BH * BW;
+  const uint32_t* forest = forest_all + (size_t)blockIdx.z * nblk;
+  const uint32_t w0 = forest[by * BW + bx];
+  const uint32_t me = w0 & 15u;
   const size_t off = (size_t)blockIdx.z * H * W;
-  const uint32_t me = occ_all[(size_t)blockIdx.z * BH * BW + (size_t)by * BW + bx];
   const int idx = 2 * by * W + 2 * bx;
-  int root = 0, n = 0;
+  int y = 0, n = 0;
   if (me) {
-    root = labels_all[off + idx];
-    n = area_all[off + root];
+    int root = (int)(w0 >> 4);
+    uint32_t w1 = forest[root];
+    while ((int)(w1 >> 4) != root) {
+      root = (int)(w1 >> 4);
+      w1 = forest[root];
+    }
+    n = area_all[(size_t)blockIdx.z * nblk + root];
+    const int ry = root / BW;
+    y = 2 * ry * W + 2 * (root - ry * BW) + 1;
   }
   if (FILL) {
     if (me && n <= max_area) {
@@ -630,11 +702,10 @@ __global__ void cc_t_final(const uint8_t* __restrict__ occ_all, int H, int W, in
   } else {
     int32_t* L = labels_all + off;
     int32_t* C = counts_all + off;
-    const int y = root + 1;
-    *reinterpret_cast<int2*>(L + idx) = make_int2((me & 1u) ? y : 0, (me & 2u) ? y : 0);
-    *reinterpret_cast<int2*>(L + idx + W) = make_int2((me & 4u) ? y : 0, (me & 8u) ? y : 0);
-    *reinterpret_cast<int2*>(C + idx) = make_int2((me & 1u) ? n : 0, (me & 2u) ? n : 0);
-    *reinterpret_cast<int2*>(C + idx + W) = make_int2((me & 4u) ? n : 0, (me & 8u) ? n : 0);
+    __stcs(reinterpret_cast<int2*>(L + idx), make_int2((me & 1u) ? y : 0, (me & 2u) ? y : 0));
+    __stcs(reinterpret_cast<int2*>(L + idx + W), make_int2((me & 4u) ? y : 0, (me & 8u) ? y : 0));
+    __stcs(reinterpret_cast<int2*>(C + idx), make_int2((me & 1u) ? n : 0, (me & 2u) ? n : 0));
+    __stcs(reinterpret_cast<int2*>(C + idx + W), make_int2((me & 4u) ? n : 0, (me & 8u) ? n : 0));
   }
 }
 
@@ -664,31 +735,39 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     VLS_POST_LAUNCH(1);
     return 0;
   }
-  const size_t px = (size_t)n * h * w;
-  const size_t blocks = px / 4;
-  const size_t need = (FILL ? 2 * px * 4 : px * 4) + blocks;
+  const size_t need = cc_workspace_bytes(n, h, w, FILL);
   VLS_REQUIRE(ws != nullptr && ws_bytes >= need, "cc: workspace too small (%zu < %zu)", ws_bytes, need);
-  int32_t* area = reinterpret_cast<int32_t*>(ws);
-  int32_t* forest = FILL ? area + px : labels;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(area + (FILL ? 2 * px : px));
-  VLS_CUDA(cudaMemsetAsync(area, 0, px * 4, stream));
+  VLS_REQUIRE(((uintptr_t)ws % 16) == 0, "cc: workspace must be 16-byte aligned");
   const int BH = h / 2, BW = w / 2;
+  const size_t nblk = (size_t)n * BH * BW;
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
-  VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(dim3(tiles_x, tiles_y, n)), dim3(T_THREADS), 0, stream, img, scores, h, w, forest, occ));
+  uint32_t* forest = reinterpret_cast<uint32_t*>(ws);
+  int32_t* area = reinterpret_cast<int32_t*>(forest + nblk);
+  int* list_count = reinterpret_cast<int*>(area + nblk);
+  int2* list = reinterpret_cast<int2*>(list_count + 4);
+  const long long list_cap = (long long)n * tiles_x * tiles_y * T_BORDER;
+  VLS_CUDA(cudaMemsetAsync(list_count, 0, 16, stream));
+  const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0) : ((w % 16) == 0 && ((uintptr_t)img % 16) == 0);
+  VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(tiles_x, tiles_y, n), dim3(T_THREADS), 0, stream, img, scores, h, w, vec, forest, area,
+                    list_count, list));
   const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
-  VLS_CUDA(launch_k(cc_t_border, dim3(dim3((unsigned)((border + 255) / 256), 1, n)), dim3(256), 0, stream, occ, h, w, forest));
+  VLS_CUDA(launch_k(cc_t_border, dim3((unsigned)((border + 255) / 256), 1, n), dim3(256), 0, stream, h, w, forest));
+  VLS_CUDA(launch_k(cc_t_areas, dim3((unsigned)((list_cap + 255) / 256)), dim3(256), 0, stream, h, w, forest, area, list_count, list));
   dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, n);
-  VLS_CUDA(launch_k(cc_t_count, dim3(grd), dim3(blk), 0, stream, occ, h, w, forest, area));
-  VLS_CUDA(launch_k(cc_t_final<FILL>, dim3(grd), dim3(blk), 0, stream, occ, h, w, forest, area, counts, scores, max_area, fill_value));
+  VLS_CUDA(launch_k(cc_t_final<FILL>, grd, blk, 0, stream, h, w, forest, area, labels, counts, scores, max_area, fill_value));
   VLS_POST_LAUNCH(4);
   return 0;
 }
 
 }  // namespace
 
+// tiled path: forest + area words per 2x2 block, the open-root list and its counter
 size_t cc_workspace_bytes(int n, int h, int w, bool fill) {
+  (void)fill;
   if (n <= 0 || h <= 0 || w <= 0 || small_ok(h, w)) return 0;
-  return (size_t)n * h * w * 4 * (fill ? 2 : 1) + (size_t)n * h * w / 4;
+  const size_t nblk = (size_t)n * (h / 2) * (w / 2);
+  const size_t tiles = (size_t)n * ((w / 2 + TBW - 1) / TBW) * ((h / 2 + TBH - 1) / TBH);
+  return nblk * 8 + 16 + tiles * T_BORDER * 8 + 256;
 }
 
 int launch_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* ws,
