@@ -532,6 +532,19 @@ __device__ __forceinline__ void gunion(uint32_t* f, int a, int b) {
     ra = gfind(f, (int)(old >> 4));
     rb = gfind(f, rb);
   }
+  // path compression: a large component spans hundreds of tiles, and without it every border union walks the whole
+  // chain of tile roots through L2 (the border kernel took 81 us for 1 M threads)
+  const int r = ra < rb ? ra : rb;
+  for (int side = 0; side < 2; ++side) {
+    int n = side ? b : a;
+    while (n > r) {
+      const uint32_t w = reinterpret_cast<const volatile uint32_t*>(f)[n];
+      const int p = (int)(w >> 4);
+      if (p == n) break;
+      if (p > r) atomicMin(f + n, ((uint32_t)r << 4) | (w & 15u));
+      n = p;
+    }
+  }
 }
 
 template <bool FILL>
@@ -655,15 +668,19 @@ __global__ void cc_t_border(int H, int W, uint32_t* forest_all) {
   }
 }
 
-__global__ void cc_t_areas(int H, int W, const uint32_t* __restrict__ forest_all, int32_t* area_all,
+__global__ void cc_t_areas(int H, int W, uint32_t* forest_all, int32_t* area_all,
                            const int* __restrict__ list_count, const int2* __restrict__ list) {
   pdl_enter();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= *list_count) return;
   const int2 e = list[i];
   const size_t nblk = (size_t)(H >> 1) * (W >> 1);
-  const int g = gfind(forest_all + (size_t)e.x * nblk, e.y);
-  if (g != e.y) atomicAdd(area_all + (size_t)e.x * nblk + g, area_all[(size_t)e.x * nblk + e.y]);
+  uint32_t* forest = forest_all + (size_t)e.x * nblk;
+  const int g = gfind(forest, e.y);
+  if (g != e.y) {
+    atomicAdd(area_all + (size_t)e.x * nblk + g, area_all[(size_t)e.x * nblk + e.y]);
+    forest[e.y] = ((uint32_t)g << 4) | (forest[e.y] & 15u);   // flatten: cc_t_final then needs at most two hops
+  }
 }
 
 template <bool FILL>
@@ -739,23 +756,40 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   VLS_REQUIRE(ws != nullptr && ws_bytes >= need, "cc: workspace too small (%zu < %zu)", ws_bytes, need);
   VLS_REQUIRE(((uintptr_t)ws % 16) == 0, "cc: workspace must be 16-byte aligned");
   const int BH = h / 2, BW = w / 2;
-  const size_t nblk = (size_t)n * BH * BW;
+  const size_t nblk1 = (size_t)BH * BW;                       // blocks per image
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
   uint32_t* forest = reinterpret_cast<uint32_t*>(ws);
-  int32_t* area = reinterpret_cast<int32_t*>(forest + nblk);
-  int* list_count = reinterpret_cast<int*>(area + nblk);
+  int32_t* area = reinterpret_cast<int32_t*>(forest + nblk1 * n);
+  int* list_count = reinterpret_cast<int*>(area + nblk1 * n);   // two counters (one per half), 16 bytes reserved
   int2* list = reinterpret_cast<int2*>(list_count + 4);
-  const long long list_cap = (long long)n * tiles_x * tiles_y * T_BORDER;
+  const size_t list_per_image = (size_t)tiles_x * tiles_y * T_BORDER;
   VLS_CUDA(cudaMemsetAsync(list_count, 0, 16, stream));
   const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0) : ((w % 16) == 0 && ((uintptr_t)img % 16) == 0);
-  VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(tiles_x, tiles_y, n), dim3(T_THREADS), 0, stream, img, scores, h, w, vec, forest, area,
-                    list_count, list));
-  const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
-  VLS_CUDA(launch_k(cc_t_border, dim3((unsigned)((border + 255) / 256), 1, n), dim3(256), 0, stream, h, w, forest));
-  VLS_CUDA(launch_k(cc_t_areas, dim3((unsigned)((list_cap + 255) / 256)), dim3(256), 0, stream, h, w, forest, area, list_count, list));
-  dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, n);
-  VLS_CUDA(launch_k(cc_t_final<FILL>, grd, blk, 0, stream, h, w, forest, area, labels, counts, scores, max_area, fill_value));
-  VLS_POST_LAUNCH(4);
+  // The labelling kernel is issue bound and the final pass bandwidth bound, so a large batch is split in two halves
+  // that run on two streams: one half's output pass overlaps the other half's labelling.
+  const int halves = n >= 8 ? 2 : 1;
+  for (int hf = halves - 1; hf >= 0; --hf) {   // the forked half first: the fork point precedes all of this call's work
+    const int i0 = hf == 0 ? 0 : n / 2, cnt = halves == 1 ? n : (hf == 0 ? n / 2 : n - n / 2);
+    cudaStream_t st = stream;
+    if (hf == 1) VLS_TRY(fork_begin(3, stream, &st));
+    const size_t px0 = (size_t)i0 * h * w;
+    const void* img_h = FILL ? nullptr : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img) + px0);
+    float* sc_h = FILL ? scores + px0 : nullptr;
+    uint32_t* f_h = forest + nblk1 * i0;
+    int32_t* a_h = area + nblk1 * i0;
+    int2* l_h = list + list_per_image * i0;
+    const long long list_cap = (long long)cnt * list_per_image;
+    VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(tiles_x, tiles_y, cnt), dim3(T_THREADS), 0, st, img_h, sc_h, h, w, vec, f_h, a_h,
+                      list_count + hf, l_h));
+    const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
+    VLS_CUDA(launch_k(cc_t_border, dim3((unsigned)((border + 255) / 256), 1, cnt), dim3(256), 0, st, h, w, f_h));
+    VLS_CUDA(launch_k(cc_t_areas, dim3((unsigned)((list_cap + 255) / 256)), dim3(256), 0, st, h, w, f_h, a_h, list_count + hf, l_h));
+    dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, cnt);
+    VLS_CUDA(launch_k(cc_t_final<FILL>, grd, blk, 0, st, h, w, f_h, a_h, FILL ? nullptr : labels + px0, FILL ? nullptr : counts + px0,
+                      sc_h, max_area, fill_value));
+    VLS_POST_LAUNCH(4);
+  }
+  if (halves == 2) VLS_TRY(fork_join(3, stream));
   return 0;
 }
 

@@ -82,6 +82,54 @@ int prof_collect(int slot, int* count, double* total_ms) {
   return 0;
 }
 
+// Fork / join of independent kernel chains onto an internal side stream (events only: no host synchronisation, and
+// the pattern is captured into CUDA graphs as parallel branches).  The per-frame path is a chain of small kernels
+// that each fill a fraction of the 148 SMs, so independent sub-chains are run side by side.  VLS_NO_SIDE_STREAM=1
+// keeps everything on the caller's stream.
+struct Fork {
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+};
+bool overlap_enabled() {
+  static const bool on = !(getenv("VLS_NO_SIDE_STREAM") && getenv("VLS_NO_SIDE_STREAM")[0] == '1');
+  return on;
+}
+int fork_get(int idx, Fork** out) {
+  // per host thread and per device: concurrent callers never share a side stream or its events
+  static thread_local Fork forks[16][4];
+  int dev = 0;
+  VLS_CUDA(cudaGetDevice(&dev));
+  VLS_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
+  Fork& f = forks[dev][idx];
+  if (!f.side) {
+    VLS_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
+    VLS_CUDA(cudaEventCreateWithFlags(&f.ev_fork, cudaEventDisableTiming));
+    VLS_CUDA(cudaEventCreateWithFlags(&f.ev_join, cudaEventDisableTiming));
+  }
+  *out = &f;
+  return 0;
+}
+// returns the stream the forked chain must be launched on (the caller's own stream when overlap is disabled)
+int fork_begin(int idx, cudaStream_t main, cudaStream_t* side) {
+  *side = main;
+  if (!overlap_enabled()) return 0;
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  VLS_CUDA(cudaEventRecord(f->ev_fork, main));
+  VLS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
+  *side = f->side;
+  return 0;
+}
+int fork_join(int idx, cudaStream_t main) {
+  if (!overlap_enabled()) return 0;
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  VLS_CUDA(cudaEventRecord(f->ev_join, f->side));
+  VLS_CUDA(cudaStreamWaitEvent(main, f->ev_join, 0));
+  return 0;
+}
+
+
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static std::once_flag g_encode_once;
 

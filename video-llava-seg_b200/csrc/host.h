@@ -58,6 +58,13 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Fork / join of independent kernel chains onto internal side streams (events only, graph-capturable; per host thread
+// and device).  fork_begin returns the stream the forked chain must be launched on (the caller's own stream when
+// VLS_NO_SIDE_STREAM=1); fork_join makes `main` wait for everything enqueued on that side stream.  idx 0..3 select
+// independent side streams.
+int fork_begin(int idx, cudaStream_t main, cudaStream_t* side);
+int fork_join(int idx, cudaStream_t main);
+
 // One-time per-DEVICE initialisation (cudaFuncSetAttribute is a per-device setting): returns true the first time it is
 // called with this flag word on the current device.  Thread-safe.
 bool first_use_on_device(unsigned long long* flag_word);
