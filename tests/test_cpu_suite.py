@@ -119,7 +119,9 @@ def test_library_exports_every_declared_symbol(vls_lib):
     rc = vls_lib.vls_cc_label(None, 1, 5, 4, None, None, None, 0, None)
     assert rc != 0 and b"null" in vls_lib.vls_last_error().lower()
     assert vls_lib.vls_cc_workspace_bytes(8, 256, 256) == 0
-    assert vls_lib.vls_cc_workspace_bytes(1, 1024, 1024) == 1024 * 1024 * 4 + 1024 * 1024 // 4
+    # tiled path: forest + area word per 2x2 block, counters, one open-root list entry per tile-border block
+    blocks, tiles = 512 * 512, (512 // 64) * (512 // 32)
+    assert vls_lib.vls_cc_workspace_bytes(1, 1024, 1024) == blocks * 8 + 16 + tiles * 2 * (32 + 64) * 8 + 256
     assert vls_lib.vls_mem_attn_workspace_bytes(1, 4096, 28736) > 64 << 20
 
 
