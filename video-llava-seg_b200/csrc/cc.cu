@@ -19,8 +19,9 @@
 //   D. the few blocks that ever started a label are flattened onto their roots (the only loop-y finds)
 //   E. block -> label -> root -> area with plain loads; 128-bit streaming stores of labels and areas
 //      (or, for hole filling, sparse in-place stores of 0.1)
-// Larger images: 64 x 128 pixel tiles labelled in shared memory the same way, tile-border unions in global
-// memory (the labels array is the forest, as in the reference), batched over N, four launches.
+// Larger images: 64 x 128 pixel tiles labelled in shared memory by the same region labeller; the global state is one
+// forest word (parent << 4 | occupancy) and one area word per 2x2 block plus a list of the tile-local roots that touch
+// a tile border; border unions (one warp per tile edge piece, pruned per run), area hand-over, output pass.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -488,8 +489,8 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   __syncthreads();
   CC_MARK(5);
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-    printf("cc_small<%d> cta %d: A %lld B %lld C %lld D %lld E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
-           tr[2] - tr[1], tr[3] - tr[2], tr[4] - tr[3], tr[5] - tr[4]);
+    printf("cc_small<%d> cta %d: A %lld  B-D (region labeller) %lld  E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
+           tr[4] - tr[1], tr[5] - tr[4]);
 #endif
 }
 
@@ -636,35 +637,62 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
   }
 }
 
+// One warp per tile edge piece: the two 32-block halves of the top row (lanes = consecutive blocks: coalesced loads,
+// neighbours by shuffle, and the same pruning as inside a tile -- a run that crosses the border costs ONE union, not one
+// per block), the left column and the right column (lanes = rows).
 __global__ void cc_t_border(int H, int W, uint32_t* forest_all) {
   pdl_enter();
   const int BH = H >> 1, BW = W >> 1;
   const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
-  const int per_tile = TBW + 2 * TBH;  // top row, left column, right column
-  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= (long long)tiles_x * tiles_y * per_tile) return;
-  const int tile = (int)(id / per_tile), k = (int)(id % per_tile);
-  const int ty = tile / tiles_x, tx = tile % tiles_x;
-  int ly, lx, kind;  // kind 0: top row, 1: left column, 2: right column
-  if (k < TBW) { ly = 0; lx = k; kind = 0; }
-  else if (k < TBW + TBH) { ly = k - TBW; lx = 0; kind = 1; }
-  else { ly = k - TBW - TBH; lx = TBW - 1; kind = 2; }
-  const int by = ty * TBH + ly, bx = tx * TBW + lx;
-  if (by >= BH || bx >= BW) return;
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= tiles_x * tiles_y * 4) return;
+  const int tile = gw >> 2, piece = gw & 3;
+  const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
+  const int by0 = ty * TBH, bx0 = tx * TBW;
   uint32_t* forest = forest_all + (size_t)blockIdx.z * BH * BW;
-  const int idx = by * BW + bx;
-  const uint32_t me = forest[idx] & 15u;   // the nibble of a word never changes
-  if (!me) return;
-  auto at = [&](int y, int x) -> uint32_t { return (y >= 0 && x >= 0 && x < BW) ? (forest[y * BW + x] & 15u) : 0u; };
-  if (kind == 0 && by > 0) {
-    if (conn_up(me, at(by - 1, bx))) gunion(forest, idx, idx - BW);
-    if (conn_upleft(me, at(by - 1, bx - 1))) gunion(forest, idx, idx - BW - 1);
-    if (conn_upright(me, at(by - 1, bx + 1))) gunion(forest, idx, idx - BW + 1);
-  } else if (kind == 1 && bx > 0) {
-    if (conn_left(me, at(by, bx - 1))) gunion(forest, idx, idx - 1);
-    if (ly > 0 && conn_upleft(me, at(by - 1, bx - 1))) gunion(forest, idx, idx - BW - 1);
-  } else if (kind == 2 && ly > 0) {
-    if (conn_upright(me, at(by - 1, bx + 1))) gunion(forest, idx, idx - BW + 1);
+  auto nib = [&](int y, int x) -> uint32_t {
+    return (y >= 0 && y < BH && x >= 0 && x < BW) ? (forest[y * BW + x] & 15u) : 0u;   // a word's nibble never changes
+  };
+  if (piece < 2) {   // top row, blocks bx0 + 32*piece + lane
+    const int by = by0, bx = bx0 + 32 * piece + lane;
+    if (by == 0 || by >= BH) return;
+    const uint32_t me = nib(by, bx), up = nib(by - 1, bx);
+    uint32_t left = __shfl_up_sync(0xffffffffu, me, 1), ul = __shfl_up_sync(0xffffffffu, up, 1);
+    uint32_t ur = __shfl_down_sync(0xffffffffu, up, 1);
+    if (lane == 0) {
+      left = piece == 1 ? nib(by, bx - 1) : 0u;   // the block before the tile's first one belongs to another tile
+      ul = nib(by - 1, bx - 1);
+    }
+    if (lane == 31) ur = nib(by - 1, bx + 1);
+    const bool h = conn_left(me, left);          // same tile: already one component
+    const bool cu = conn_up(me, up);
+    const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
+    const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
+    const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
+    const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
+    const int idx = by * BW + bx;
+    if (cu && !cu_redundant) gunion(forest, idx, idx - BW);
+    if (cul) gunion(forest, idx, idx - BW - 1);
+    if (cur) gunion(forest, idx, idx - BW + 1);
+  } else if (piece == 2) {   // left column, rows by0 + lane
+    const int by = by0 + lane, bx = bx0;
+    if (bx == 0 || by >= BH) return;
+    const uint32_t me = nib(by, bx);
+    if (!me) return;
+    const uint32_t lf = nib(by, bx - 1);
+    const int idx = by * BW + bx;
+    if (conn_left(me, lf)) gunion(forest, idx, idx - 1);
+    if (lane > 0) {          // the tile's first row is the top-row piece's business
+      const uint32_t up = nib(by - 1, bx), ul = nib(by - 1, bx - 1);
+      if (conn_upleft(me, ul) && !(conn_up(me, up) && conn_left(up, ul))) gunion(forest, idx, idx - BW - 1);
+    }
+  } else {   // right column
+    const int by = by0 + lane, bx = bx0 + TBW - 1;
+    if (lane == 0 || bx + 1 >= BW || by >= BH) return;
+    const uint32_t me = nib(by, bx);
+    if (!me) return;
+    const uint32_t up = nib(by - 1, bx), ur = nib(by - 1, bx + 1);
+    if (conn_upright(me, ur) && !(conn_up(me, up) && conn_left(ur, up))) gunion(forest, by * BW + bx, (by - 1) * BW + bx + 1);
   }
 }
 
@@ -781,7 +809,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     const long long list_cap = (long long)cnt * list_per_image;
     VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(tiles_x, tiles_y, cnt), dim3(T_THREADS), 0, st, img_h, sc_h, h, w, vec, f_h, a_h,
                       list_count + hf, l_h));
-    const long long border = (long long)tiles_x * tiles_y * (TBW + 2 * TBH);
+    const long long border = (long long)tiles_x * tiles_y * 4 * 32;   // four warps per tile
     VLS_CUDA(launch_k(cc_t_border, dim3((unsigned)((border + 255) / 256), 1, cnt), dim3(256), 0, st, h, w, f_h));
     VLS_CUDA(launch_k(cc_t_areas, dim3((unsigned)((list_cap + 255) / 256)), dim3(256), 0, st, h, w, f_h, a_h, list_count + hf, l_h));
     dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, cnt);
