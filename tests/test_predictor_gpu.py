@@ -309,3 +309,57 @@ def test_fused_binary_output_stage(predictor, mode):
             predictor.add_new_points_or_box(predictor.init_state(src), 0, 1, points=point, labels=[1], normalize_coords=False)
         finally:
             predictor.output_mode = "logits"
+
+
+def test_captured_graph_is_reused_across_clips(predictor):
+    """A second clip of the same shape must take over the first clip's captured graph (no re-capture) and still
+    reproduce the eager path; two sessions that are alive at the same time must get separate graphs."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 20
+
+    def track(seed, use_graph, keep_state=None):
+        predictor.use_cuda_graph = use_graph
+        clip = synth.SyntheticClip(seed, T)
+        st = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+        predictor.add_new_points_or_box(st, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
+        outs = [st["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]["pred_masks"].float().cpu()
+                for f, _, _ in predictor.propagate_in_video(st)]
+        return outs, st
+
+    try:
+        predictor.__dict__.pop("_graph_cache", None)
+        a_graph, st_a = track(21, True)
+        g1 = st_a["steady_graph"]
+        assert g1 is not None and g1.graph is not None
+        b_graph, st_b = track(22, True)                       # clip A is finished: its graph is idle
+        assert st_b["steady_graph"] is g1, "the captured graph was not re-used"
+        c_graph, st_c = track(23, True)
+        assert st_c["steady_graph"] is g1
+        # clip A's retained outputs must not have been overwritten by the clips that re-used its graph
+        a_again = [st_a["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]["pred_masks"].float().cpu()
+                   for f in range(T)]
+        assert all(torch.equal(x, y) for x, y in zip(a_graph, a_again))
+        b_eager, _ = track(22, False)
+        c_eager, _ = track(23, False)
+        for got, ref in ((b_graph, b_eager), (c_graph, c_eager)):
+            for t in range(T):
+                same_sign = ((got[t] > 0) == (ref[t] > 0)).float().mean().item()
+                assert same_sign > 0.9995, (t, same_sign)
+                d = (got[t] - ref[t]).abs()
+                assert d[(got[t] != 0.1) & (ref[t] != 0.1)].median() < 1e-4
+        # a session that is still in the middle of its video keeps its graph: a concurrent one gets another
+        predictor.use_cuda_graph = True
+        clip = synth.SyntheticClip(24, T)
+        st_d = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+        predictor.add_new_points_or_box(st_d, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
+        gen = predictor.propagate_in_video(st_d)
+        for _ in range(18):
+            next(gen)
+        assert st_d["steady_graph"] is g1                     # took over the idle graph ...
+        _, st_e = track(25, True)
+        assert st_e["steady_graph"] is not g1                 # ... which is busy now
+        gen.close()
+    finally:
+        predictor.use_cuda_graph = True

@@ -17,6 +17,7 @@ Results are those of the eager path (same kernels, same key order); the eager pa
 (ragged bank during the ramp, prompts, reverse tracking, CPU offload, several conditioning frames).
 """
 import os
+import weakref
 
 import torch
 
@@ -28,8 +29,9 @@ from .utils.misc import fill_holes_in_mask_scores
 class SteadyStateGraph:
     ARENA_FRAMES = 64     # frames of retained outputs allocated at once
 
-    def __init__(self, model, state, frame_idx, batch_size):
+    def __init__(self, model, state, frame_idx, batch_size, owner=None):
         self._arena, self._arena_pos = None, 0
+        self._owner = weakref.ref(owner) if owner is not None else None
         self.model, self.B = model, batch_size
         self.dev = state["device"]
         self.num_frames = state["num_frames"]
@@ -40,7 +42,6 @@ class SteadyStateGraph:
         self.n_ptr = min(self.num_frames, m.max_obj_ptrs_in_encoder)   # 16
         self.k = m.hidden_dim // m.mem_dim               # 4 tokens per pointer
         self.Nk = self.n_mem * self.HW + self.n_ptr * self.k
-        self.cond_idx = next(iter(state["output_dict"]["cond_frame_outputs"]))
         self.output_mode = model.output_mode
         self.graph = None
         self.next_frame = None
@@ -73,13 +74,28 @@ class SteadyStateGraph:
 
     # ------------------------------------------------------------------ static buffers
     def _build_static(self, state, frame_idx):
+        """Allocate the static buffers (once per captured graph) and fill them from `state`."""
+        m, B, dev = self.model, self.B, self.dev
+        self.bank_mem = torch.empty((B, self.Nk, m.mem_dim), device=dev, dtype=torch.bfloat16)
+        self.bank_pos = torch.empty((self.Nk, m.mem_dim), device=dev, dtype=torch.float32)
+        self.ptr_off = self.n_mem * self.HW
+        # static inputs: same strides as the tensors the feature source hands out
+        _, bo, _, _, _ = m._get_image_feature(state, frame_idx, 1)
+        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
+        self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in fpn[-3:])
+        self.in_pos = torch.empty_like(pe[-1])
+        self._fill_static(state, frame_idx)
+
+    def _fill_static(self, state, frame_idx):
+        """(Re)initialise the bank and the positional rows for `state` at `frame_idx`, in place: the captured graph only
+        knows the buffers' addresses, so a finished graph can be handed to the next clip of the same shape."""
         m, B, dev, HW = self.model, self.B, self.dev, self.HW
         c = m._constants()
         out = state["output_dict"]
+        self.cond_idx = next(iter(out["cond_frame_outputs"]))
+        self.num_frames = state["num_frames"]
         cond = out["cond_frame_outputs"][self.cond_idx]
         non = out["non_cond_frame_outputs"]
-        self.bank_mem = torch.empty((B, self.Nk, m.mem_dim), device=dev, dtype=torch.bfloat16)
-        self.bank_pos = torch.empty((self.Nk, m.mem_dim), device=dev, dtype=torch.float32)
         # memories: conditioning frame (t_pos 0), then t-6 ... t-1 (t_pos 1..6)   (sam2_base.py:533-568)
         self.bank_mem[:, :HW] = m._mem_rows(cond).to(dev)
         self.bank_pos[:HW] = c["mem_pos_rows"][0]
@@ -88,7 +104,6 @@ class SteadyStateGraph:
             self.bank_mem[:, t_pos * HW:(t_pos + 1) * HW] = m._mem_rows(non[frame_idx - t_rel]).to(dev)
             self.bank_pos[t_pos * HW:(t_pos + 1) * HW] = c["mem_pos_rows"][t_pos]
         # pointers: conditioning frame, then t-1 ... t-15, 4 tokens of 64 each   (sam2_base.py:599-646)
-        self.ptr_off = self.n_mem * HW
         ptrs = [cond["obj_ptr"]] + [non[frame_idx - d]["obj_ptr"] for d in range(1, self.n_ptr)]
         self.bank_mem[:, self.ptr_off:] = torch.stack(ptrs, 1).reshape(B, self.n_ptr * self.k, m.mem_dim).to(torch.bfloat16)
         # pointer temporal encodings for every possible distance: one table, rows repeated x4
@@ -98,13 +113,37 @@ class SteadyStateGraph:
         self.ptr_pos_table = table.repeat_interleave(self.k, dim=0).reshape(self.num_frames + 1, self.k, m.mem_dim)
         for d in range(1, self.n_ptr):
             self.bank_pos[self.ptr_off + d * self.k: self.ptr_off + (d + 1) * self.k] = self.ptr_pos_table[d]
-        # static inputs: same strides as the tensors the feature source hands out
-        _, bo, _, _, _ = m._get_image_feature(state, frame_idx, 1)
-        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
-        self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in fpn[-3:])
-        self.in_pos = torch.empty_like(pe[-1])
         self._pos_src = None
+        self._arena, self._arena_pos = None, 0      # retained outputs of the previous clip stay with that clip
         self.next_frame = frame_idx
+
+    # ------------------------------------------------------------------ reuse across clips
+    def key(self):
+        return (self.B, self.hw, self.n_ptr, self.output_mode, tuple(self.in_s0.shape), tuple(self.in_s1.shape),
+                tuple(self.in_feat.shape), self.in_feat.dtype)
+
+    @staticmethod
+    def key_for(model, state, frame_idx, batch_size):
+        _, bo, _, _, _ = model._get_image_feature(state, frame_idx, 1)
+        fpn = bo["backbone_fpn"]
+        return (batch_size, (state["video_height"], state["video_width"]),
+                min(state["num_frames"], model.max_obj_ptrs_in_encoder), model.output_mode, tuple(fpn[-3].shape),
+                tuple(fpn[-2].shape), tuple(fpn[-1].shape), fpn[-1].dtype)
+
+    def idle(self):
+        """True when the session this graph was serving is gone or has been tracked to its last frame."""
+        owner = self._owner() if self._owner is not None else None
+        return owner is None or self.next_frame is None or self.next_frame >= self.num_frames
+
+    def release(self):
+        self._owner = None
+
+    def rebind(self, state, frame_idx, owner):
+        """Hand a captured graph to another session of the same shape: refill the static buffers, keep the capture
+        (re-capturing costs 20-90 ms per clip: torch.cuda.graph synchronises, collects garbage and empties the allocator
+        cache, more than the 48 steady-state frames of a 64-frame clip take)."""
+        self._owner = weakref.ref(owner)
+        self._fill_static(state, frame_idx)
 
     def _load_inputs(self, state, frame_idx):
         _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx, 1)

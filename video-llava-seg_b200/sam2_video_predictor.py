@@ -30,6 +30,10 @@ def _empty_frame_store():
     return {"cond_frame_outputs": {}, "non_cond_frame_outputs": {}}
 
 
+class _GraphOwner:
+    """Lifetime token of a session (plain dicts cannot be weakly referenced)."""
+
+
 class SAM2VideoPredictor(SAM2Base):
     def __init__(self, fill_hole_area=0, non_overlap_masks=False, clear_non_cond_mem_around_input=False,
                  clear_non_cond_mem_for_multi_obj=False, add_all_frames_to_correct_as_cond=False, **kwargs):
@@ -101,7 +105,7 @@ class SAM2VideoPredictor(SAM2Base):
     # ------------------------------------------------------------------ prompts
     def _prompt_frame(self, st, frame_idx, obj_idx, point_inputs, mask_inputs):
         """Shared tail of add_new_points_or_box / add_new_mask (sam2_video_predictor.py:250-314,355-402)."""
-        st["steady_graph"] = None  # new prompts change the memory bank
+        self._drop_graph(st)  # new prompts change the memory bank
         is_init = frame_idx not in st["frames_already_tracked"]
         reverse = False if is_init else st["frames_already_tracked"][frame_idx]["reverse"]
         obj_out, obj_tmp = st["output_dict_per_obj"][obj_idx], st["temp_output_dict_per_obj"][obj_idx]
@@ -339,9 +343,10 @@ class SAM2VideoPredictor(SAM2Base):
                 key = "non_cond_frame_outputs"
                 g = st.get("steady_graph")
                 if g is not None and (g.next_frame != f or g.B != B or not g.valid()):
-                    g = st["steady_graph"] = None
+                    self._drop_graph(st)
+                    g = None
                 if g is None and SteadyStateGraph.eligible(self, st, f, B, reverse):
-                    g = st["steady_graph"] = SteadyStateGraph(self, st, f, B)
+                    g = st["steady_graph"] = self._acquire_graph(st, f, B)
                 if g is not None:   # full memory bank: one CUDA-graph replay per frame
                     cur, video_res = g.run(st, f)
                     pred = None
@@ -355,6 +360,32 @@ class SAM2VideoPredictor(SAM2Base):
             if pred is not None:
                 _, video_res = self._get_orig_video_res_output(st, pred)
             yield f, obj_ids, video_res
+
+    @staticmethod
+    def _drop_graph(st):
+        """The session stops using its captured graph (new prompts, object removed, ...): the graph becomes re-usable."""
+        g = st.get("steady_graph")
+        if g is not None:
+            g.release()
+        st["steady_graph"] = None
+
+    def _acquire_graph(self, st, frame_idx, batch_size):
+        """A captured steady-state graph for this session: an idle one of the same shape is re-used (its static bank is
+        refilled in place), otherwise a new one is built and remembered.  Sessions own a token whose lifetime tells the
+        cache when a graph is free again."""
+        if "graph_owner" not in st:
+            st["graph_owner"] = _GraphOwner()
+        cache = self.__dict__.setdefault("_graph_cache", {})
+        key = SteadyStateGraph.key_for(self, st, frame_idx, batch_size)
+        for g in cache.get(key, []):
+            if g.idle() and g.valid():
+                g.rebind(st, frame_idx, st["graph_owner"])
+                return g
+        g = SteadyStateGraph(self, st, frame_idx, batch_size, owner=st["graph_owner"])
+        graphs = cache.setdefault(key, [])
+        graphs[:] = [x for x in graphs if x.valid()][-3:]      # bound the cache: at most 4 graphs per shape
+        graphs.append(g)
+        return g
 
     def _add_output_per_object(self, st, frame_idx, cur, key):
         """Per-object views sharing storage with the batched output (sam2_video_predictor.py:747-774)."""
@@ -427,7 +458,7 @@ class SAM2VideoPredictor(SAM2Base):
         if len(st["obj_id_to_idx"]) == 1:
             self.reset_state(st)
             return st["obj_ids"], updated
-        st["steady_graph"] = None                     # the captured graph is specialised on the object count
+        self._drop_graph(st)                          # the captured graph is specialised on the object count
         input_frames = set(st["point_inputs_per_obj"][rm]) | set(st["mask_inputs_per_obj"][rm])
         for f in input_frames:
             self.clear_all_prompts_in_frame(st, f, obj_id, need_output=False)
@@ -471,7 +502,7 @@ class SAM2VideoPredictor(SAM2Base):
             st[k].clear()
 
     def _reset_tracking_results(self, st):
-        st["steady_graph"] = None
+        self._drop_graph(st)
         for k in ("point_inputs_per_obj", "mask_inputs_per_obj"):
             for v in st[k].values():
                 v.clear()
