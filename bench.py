@@ -250,6 +250,26 @@ def run_ours(args):
     pinned = FeatureClip(lambda t: frames[t], T, pinned=True)
     e2e, _, _, _, out_bytes = timed_pass(pinned, d2h=True)
     sampler.stop()
+    # (3) informational: whole 64-frame clips (configs[1] as a user runs it: prompt frame, 16 frames with a growing
+    # bank, then steady state; captured graph re-used from clip to clip), wall clock around complete sessions
+    def whole_clips(n_clips=3, T_clip=64):
+        src = FeatureClip(lambda t: frames[t % T], T_clip, resident_device=dev)
+        predictor.output_mode = "logits"
+        times = []
+        for _ in range(n_clips + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            st = predictor.init_state(src)
+            predictor.add_new_points_or_box(st, 0, 1, points=prompt, labels=[1])
+            for _ in predictor.propagate_in_video(st):
+                pass
+            torch.cuda.synchronize()
+            times.append(time.perf_counter() - t0)
+        best = min(times[1:])
+        return {"frames_per_clip": T_clip, "value": round(T_clip / best, 1), "unit": UNIT, "ms_per_clip": round(best * 1e3, 2),
+                "note": "complete sessions incl. prompt frame and 16-frame ramp, resident features, best of %d" % n_clips}
+
+    clip_info = whole_clips()
     line = {
         "metric": METRIC, "value": round(value, 3), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": round(ms / K, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -259,7 +279,7 @@ def run_ours(args):
                    "parallelism": f"{world} independent replica(s), sharded by clip, no collective on the path",
                    "execution": "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay",
                    "e2e_path": "pinned host features -> double-buffered H2D -> propagate_in_video(output_mode='binary': fused resize+threshold) -> uint8 mask D2H into pinned memory every step, consumer pipelined by one frame"},
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "whole_clip": clip_info,
         "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes_per_frame),
                 "d2h_bytes_per_step": int(out_bytes)},
     }
