@@ -363,3 +363,37 @@ def test_captured_graph_is_reused_across_clips(predictor):
         gen.close()
     finally:
         predictor.use_cuda_graph = True
+
+
+def test_ramp_frames_replay_graphs_from_the_second_clip_on(predictor):
+    """Frames whose memory bank is still growing (1..15) are replayed from per-shape FrameGraphs once their shape has
+    been seen before: the third pass over a clip (ramp graphs active) must reproduce the first (eager ramp)."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 19
+    clip = synth.SyntheticClip(31, T)
+    src = FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0")
+    point = clip.point_prompt(1)["point_coords"][0].tolist()
+
+    def track():
+        st = predictor.init_state(src)
+        predictor.add_new_points_or_box(st, 0, 1, points=point, labels=[1])
+        outs = []
+        for f, _, video in predictor.propagate_in_video(st):
+            o = st["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]
+            outs.append((o["pred_masks"].float().cpu(), o["obj_ptr"].float().cpu(), o["maskmem_features"].float().cpu(),
+                         video.float().cpu()))
+        return outs
+
+    predictor.__dict__.pop("_frame_graphs", None)
+    predictor.__dict__.pop("_frame_shapes_seen", None)
+    first = track()
+    assert not predictor.__dict__.get("_frame_graphs"), "no shape has been seen twice yet"
+    track()
+    third = track()
+    graphs = predictor.__dict__.get("_frame_graphs", {})
+    assert len(graphs) >= 15 and all(g.graph is not None for g in graphs.values()), "the ramp frames were not graphed"
+    for t in range(T):
+        for a, b, name in zip(first[t], third[t], ("pred_masks", "obj_ptr", "maskmem", "video")):
+            assert (a - b).abs().max().item() < 1e-4, (t, name, (a - b).abs().max().item())

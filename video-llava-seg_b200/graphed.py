@@ -26,6 +26,97 @@ from .modeling.sam2_utils import get_1d_sine_pe
 from .utils.misc import fill_holes_in_mask_scores
 
 
+def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw, side_stream):
+    """memory attention -> mask decoder -> SAM-heads glue -> {hole filling + output stage || memory encoder} of one
+    tracked frame on static buffers: what both kinds of captured graph replay."""
+    dev = in_feat.device
+    s = m.sam_image_embedding_size
+    vf = in_feat.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+    vp = in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+    pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=mem.transpose(0, 1),
+                             memory_pos=pos[None].expand(B, -1, -1).transpose(0, 1), num_obj_ptr_tokens=n_ptr_tokens)
+    pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
+    high = [in_s0.expand(B, -1, -1, -1), in_s1.expand(B, -1, -1, -1)]
+    _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
+        pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False)
+    # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
+    # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
+    main = torch.cuda.current_stream(dev)
+    side = side_stream if os.environ.get("VLS_NO_SIDE_STREAM", "0") != "1" else main
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
+        video = m._video_res_output(pred, hw)
+    nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
+    main.wait_stream(side)
+    return pred, obj_ptr, obj_logits, nchw, rows, video
+
+
+def _signature_objects(m):
+    """What a captured graph has baked addresses of: workspaces, packed weights and constants of the three modules."""
+    return [m.memory_attention._ws, m.memory_attention._packed, m.sam_mask_decoder._ws, m.sam_mask_decoder._packed,
+            m.memory_encoder._ws, m.memory_encoder._packed, m._consts]
+
+
+class FrameGraph:
+    """One tracked frame with an ARBITRARY memory bank as a CUDA-graph replay: the bank is gathered exactly as the eager
+    path does (sam2_base.py:533-646), but into static buffers, so every frame whose bank has the same shape -- in
+    practice the 15 ramp frames of each clip, whose bank is still growing -- replays one captured graph.  The graph holds
+    no state between frames and is shared by all sessions of a predictor.  Same kernels and key order as the eager path."""
+
+    def __init__(self, model, batch_size, Nk, n_ptr_tokens, hw, feats):
+        self.model, self.B, self.Nk, self.n_ptr_tokens, self.hw = model, batch_size, Nk, n_ptr_tokens, hw
+        dev = feats[-1].device
+        self.dev = dev
+        self.mem = torch.empty((batch_size, Nk, model.mem_dim), device=dev, dtype=torch.bfloat16)
+        self.pos = torch.empty((Nk, model.mem_dim), device=dev, dtype=torch.float32)
+        self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in feats[:3])
+        self.in_pos = torch.empty_like(feats[3])
+        self._side = torch.cuda.Stream(device=dev)
+        self.output_mode = model.output_mode
+        self.graph = None
+
+    def _step(self):
+        return _frame_body(self.model, self.B, self.in_feat, self.in_pos, self.in_s0, self.in_s1, self.mem, self.pos,
+                           self.n_ptr_tokens, self.hw, self._side)
+
+    def _capture(self):
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        before = _lib.lib().vls_launch_count()
+        hi = torch.cuda.Stream(device=self.dev, priority=-1)
+        with torch.cuda.graph(self.graph, stream=hi):
+            self.outputs = self._step()
+        self.launches_per_replay = _lib.lib().vls_launch_count() - before
+        self._keepalive = _signature_objects(self.model)
+        self._sig = tuple(id(o) for o in self._keepalive)
+
+    def valid(self):
+        if self.output_mode != self.model.output_mode:
+            return False
+        return self.graph is None or self._sig == tuple(id(o) for o in _signature_objects(self.model))
+
+    def run(self, mem_parts, pos_parts, fpn, pe):
+        """mem_parts / pos_parts: the eager path's lists of [B, n_i, 64] memories and [n_i, 64] positional rows."""
+        torch.cat(mem_parts, dim=1, out=self.mem)
+        torch.cat(pos_parts, dim=0, out=self.pos)
+        self.in_s0.copy_(fpn[-3], non_blocking=True)
+        self.in_s1.copy_(fpn[-2], non_blocking=True)
+        self.in_feat.copy_(fpn[-1], non_blocking=True)
+        self.in_pos.copy_(pe[-1], non_blocking=True)
+        if self.graph is None:
+            self._capture()
+        self.graph.replay()
+        _lib.lib().vls_launch_count_add(self.launches_per_replay)
+        pred, obj_ptr, obj_logits, nchw, rows, video = ops.clone_many(list(self.outputs))
+        return pred, obj_ptr, obj_logits, nchw, rows, video
+
+
 class SteadyStateGraph:
     ARENA_FRAMES = 64     # frames of retained outputs allocated at once
 
@@ -159,29 +250,11 @@ class SteadyStateGraph:
 
     # ------------------------------------------------------------------ the captured step
     def _step(self):
-        m, B, HW = self.model, self.B, self.HW
-        s = m.sam_image_embedding_size
-        vf = self.in_feat.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
-        vp = self.in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
-        pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=self.bank_mem.transpose(0, 1),
-                                 memory_pos=self.bank_pos[None].expand(B, -1, -1).transpose(0, 1),
-                                 num_obj_ptr_tokens=self.n_ptr * self.k)
-        pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
-        high = [self.in_s0.expand(B, -1, -1, -1), self.in_s1.expand(B, -1, -1, -1)]
-        _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
-            pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False)
-        # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
-        # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
-        main = torch.cuda.current_stream(self.dev)
-        side = self._side if os.environ.get("VLS_NO_SIDE_STREAM", "0") != "1" else main
-        side.wait_stream(main)
-        with torch.cuda.stream(side):
-            pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
-            video = m._video_res_output(pred, self.hw)
-        nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
-        main.wait_stream(side)
+        pred, obj_ptr, obj_logits, nchw, rows, video = _frame_body(
+            self.model, self.B, self.in_feat, self.in_pos, self.in_s0, self.in_s1, self.bank_mem, self.bank_pos,
+            self.n_ptr * self.k, self.hw, self._side)
         # bank shift for the next frame (one launch, in place): memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
-        ops.bank_shift(self.bank_mem, HW, self.n_mem, self.n_ptr, self.k, rows.contiguous(), obj_ptr.float().contiguous())
+        ops.bank_shift(self.bank_mem, self.HW, self.n_mem, self.n_ptr, self.k, rows.contiguous(), obj_ptr.float().contiguous())
         return pred, obj_ptr, obj_logits, nchw, rows, video
 
     def _capture(self):
@@ -209,9 +282,7 @@ class SteadyStateGraph:
         self._sig = tuple(id(o) for o in self._keepalive)
 
     def _signature_objects(self):
-        m = self.model
-        return [m.memory_attention._ws, m.memory_attention._packed, m.sam_mask_decoder._ws, m.sam_mask_decoder._packed,
-                m.memory_encoder._ws, m.memory_encoder._packed, m._consts]
+        return _signature_objects(self.model)
 
     def valid(self):
         """False once weights were re-packed / moved (the captured pointers would be stale)."""

@@ -327,24 +327,30 @@ class SAM2Base(nn.Module):
             # directly_add_no_mem_embed (sam2_base.py:651-655); a 1 MB broadcast add on a prompt frame only
             out = ops.add_rowvec(feats, self._constants()["no_mem_rows"].to(dev))
             return out.permute(1, 2, 0).reshape(B, C, H, W)
-        c = self._constants()
-        mems, ptrs = self._gather_memory(frame_idx, output_dict, num_frames, track_in_reverse)
-        mem_parts = [self._mem_rows(o).to(dev, non_blocking=True) for _, o in mems]
-        pos_parts = [c["mem_pos_rows"][t_pos] for t_pos, _ in mems]
-        n_ptr_tokens = 0
-        if ptrs:
-            k = C // self.mem_dim
-            dists = tuple(int(d) for d, _ in ptrs)
-            ptr_stack = torch.stack([p for _, p in ptrs], dim=1)              # [B, P, 256]
-            mem_parts.append(ptr_stack.reshape(B, len(ptrs) * k, self.mem_dim).to(mem_parts[0].dtype))
-            pos_parts.append(self._ptr_pos_rows(dists, num_frames))
-            n_ptr_tokens = len(ptrs) * k
+        mem_parts, pos_parts, n_ptr_tokens = self._gather_bank(frame_idx, output_dict, num_frames, track_in_reverse, B, dev)
         memory = torch.cat(mem_parts, dim=1)                                   # [B, Nk, 64]  (data movement only)
         memory_pos = torch.cat(pos_parts, dim=0)[None].expand(B, -1, -1)       # [B, Nk, 64], batch stride 0
         out = self.memory_attention(curr=current_vision_feats, curr_pos=current_vision_pos_embeds,
                                     memory=memory.transpose(0, 1), memory_pos=memory_pos.transpose(0, 1),
                                     num_obj_ptr_tokens=n_ptr_tokens)
         return out.permute(1, 2, 0).reshape(B, C, H, W)
+
+    def _gather_bank(self, frame_idx, output_dict, num_frames, track_in_reverse, B, dev):
+        """The memory bank of `frame_idx` as lists of [B, n_i, 64] memories and [n_i, 64] positional rows in the
+        reference's key order (sam2_base.py:533-646), plus the number of pointer tokens at the end."""
+        c = self._constants()
+        mems, ptrs = self._gather_memory(frame_idx, output_dict, num_frames, track_in_reverse)
+        mem_parts = [self._mem_rows(o).to(dev, non_blocking=True) for _, o in mems]
+        pos_parts = [c["mem_pos_rows"][t_pos] for t_pos, _ in mems]
+        n_ptr_tokens = 0
+        if ptrs:
+            k = self.hidden_dim // self.mem_dim
+            dists = tuple(int(d) for d, _ in ptrs)
+            ptr_stack = torch.stack([p for _, p in ptrs], dim=1)              # [B, P, 256]
+            mem_parts.append(ptr_stack.reshape(B, len(ptrs) * k, self.mem_dim).to(mem_parts[0].dtype))
+            pos_parts.append(self._ptr_pos_rows(dists, num_frames))
+            n_ptr_tokens = len(ptrs) * k
+        return mem_parts, pos_parts, n_ptr_tokens
 
     # ------------------------------------------------------------------ memory encoding
     def _encode_new_memory(self, current_vision_feats, feat_sizes, pred_masks_high_res, object_score_logits,

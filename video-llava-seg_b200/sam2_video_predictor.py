@@ -14,7 +14,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .graphed import SteadyStateGraph
+from .graphed import FrameGraph, SteadyStateGraph
 from .modeling.sam2_base import NO_OBJ_SCORE, SAM2Base
 from .utils.misc import fill_holes_in_mask_scores, load_video_frames
 
@@ -347,8 +347,12 @@ class SAM2VideoPredictor(SAM2Base):
                     g = None
                 if g is None and SteadyStateGraph.eligible(self, st, f, B, reverse):
                     g = st["steady_graph"] = self._acquire_graph(st, f, B)
+                fg = None if g is not None else self._frame_graph_step(st, f, B, reverse)
                 if g is not None:   # full memory bank: one CUDA-graph replay per frame
                     cur, video_res = g.run(st, f)
+                    pred = None
+                elif fg is not None:   # growing bank of a shape seen before (ramp frames): replay too
+                    cur, video_res = fg
                     pred = None
                 else:
                     cur, pred = self._run_single_frame_inference(
@@ -360,6 +364,46 @@ class SAM2VideoPredictor(SAM2Base):
             if pred is not None:
                 _, video_res = self._get_orig_video_res_output(st, pred)
             yield f, obj_ids, video_res
+
+    def _frame_graph_step(self, st, frame_idx, batch_size, reverse):
+        """Track `frame_idx` through a FrameGraph if its memory-bank shape has been seen before (so that a capture,
+        ~20+ ms, is only paid for shapes that recur: the ramp frames of the second and later clips).  Returns
+        (compact state entry, video-resolution output) or None when the eager path must be used."""
+        if not self.use_cuda_graph or st["offload_state_to_cpu"] or self.non_overlap_masks \
+                or self.non_overlap_masks_for_mem_enc or self.num_maskmem == 0 or self.training:
+            return None
+        out_all = st["output_dict"]
+        if not out_all["cond_frame_outputs"]:
+            return None
+        dev = st["device"]
+        _, bo, _, _, _ = self._get_image_feature(st, frame_idx, 1)
+        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
+        mem_parts, pos_parts, n_ptr_tokens = self._gather_bank(frame_idx, out_all, st["num_frames"], reverse, batch_size, dev)
+        if any(p.shape[0] != batch_size for p in mem_parts):
+            return None
+        Nk = sum(p.shape[1] for p in mem_parts)
+        hw = (st["video_height"], st["video_width"])
+        key = (batch_size, Nk, n_ptr_tokens, hw, self.output_mode, tuple(fpn[-3].shape), tuple(fpn[-2].shape),
+               tuple(fpn[-1].shape), fpn[-1].dtype)
+        cache = self.__dict__.setdefault("_frame_graphs", {})
+        seen = self.__dict__.setdefault("_frame_shapes_seen", {})
+        seen[key] = seen.get(key, 0) + 1
+        g = cache.get(key)
+        if g is not None and not g.valid():      # weights re-packed / workspaces re-allocated since the capture
+            del cache[key]
+            g = None
+        if g is None:
+            if seen[key] < 2 or len(cache) >= 64:
+                return None
+            g = cache[key] = FrameGraph(self, batch_size, Nk, n_ptr_tokens, hw, [fpn[-3], fpn[-2], fpn[-1], pe[-1]])
+        pred, obj_ptr, obj_logits, nchw, rows, video = g.run(mem_parts, pos_parts, fpn, pe)
+        compact = {
+            "maskmem_features": nchw, "maskmem_rows": rows,
+            "maskmem_pos_enc": self._get_maskmem_pos_enc(st, {"maskmem_pos_enc": [
+                self._constants()["maskmem_pos"].expand(batch_size, -1, -1, -1)]}),
+            "pred_masks": pred, "obj_ptr": obj_ptr, "object_score_logits": obj_logits,
+        }
+        return compact, video
 
     @staticmethod
     def _drop_graph(st):
