@@ -13,8 +13,18 @@ video-resolution resize -> bank shift} into a torch.cuda.CUDAGraph, and replays 
 copies the frame's backbone features into the static inputs, patches 4 positional rows, launches the graph and
 clones the outputs it must retain -- ~10 stream operations instead of ~190 kernel launches.
 
+A captured graph outlives its session: the predictor hands an idle one to the next clip of the same shape
+(`SAM2VideoPredictor._acquire_graph`, `rebind`), because torch.cuda.graph synchronises, collects garbage and empties
+the allocator cache on every capture (20-90 ms, more than the 48 steady-state frames of a 64-frame clip).  The outputs
+a session retains per frame are snapshotted into 64-frame arenas, so steady state makes no allocator call that can
+reach cudaMalloc.
+
+`FrameGraph` covers frames whose bank is not (yet) the full steady-state one -- the 15 ramp frames of every clip: the
+bank is gathered like the eager path gathers it, but into static buffers, and the frame body is replayed from a graph
+captured per bank shape (from the second occurrence of a shape on).
+
 Results are those of the eager path (same kernels, same key order); the eager path remains the general one
-(ragged bank during the ramp, prompts, reverse tracking, CPU offload, several conditioning frames).
+(first occurrence of a bank shape, prompts, CPU offload, non-overlap constraints).
 """
 import os
 import weakref
@@ -209,10 +219,6 @@ class SteadyStateGraph:
         self.next_frame = frame_idx
 
     # ------------------------------------------------------------------ reuse across clips
-    def key(self):
-        return (self.B, self.hw, self.n_ptr, self.output_mode, tuple(self.in_s0.shape), tuple(self.in_s1.shape),
-                tuple(self.in_feat.shape), self.in_feat.dtype)
-
     @staticmethod
     def key_for(model, state, frame_idx, batch_size):
         _, bo, _, _, _ = model._get_image_feature(state, frame_idx, 1)
