@@ -397,3 +397,35 @@ def test_ramp_frames_replay_graphs_from_the_second_clip_on(predictor):
     for t in range(T):
         for a, b, name in zip(first[t], third[t], ("pred_masks", "obj_ptr", "maskmem", "video")):
             assert (a - b).abs().max().item() < 1e-4, (t, name, (a - b).abs().max().item())
+
+
+def test_steady_state_matches_oracle_beyond_the_golden_clips(predictor):
+    """The reference goldens stop at 8 frames (bank of 7 memories, 8 pointers).  This runs 19 frames -- 16 pointers, the
+    CUDA-graph steady state from frame 16 on -- against the CPU oracle (itself pinned to the reference on the golden
+    clips).  bf16 drift accumulates through the memory bank, so the bars are the north-star ones on every frame:
+    logits within 1e-2 where the oracle is not within 1e-2 of the threshold, binarised-mask IoU >= 0.995."""
+    from oracle import cc as cc_oracle
+    from oracle import sam2_path as O
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 19
+    sd = synth.init_state_dict(0)
+    clip = synth.SyntheticClip(41, T)
+    st = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+    predictor.add_new_points_or_box(st, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
+    got = {}
+    for f, _, _ in predictor.propagate_in_video(st):
+        got[f] = st["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]["pred_masks"].float().cpu()
+    assert st["steady_graph"] is not None, "frames 16+ must have taken the graph path"
+    ref = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, 1), clip.point_prompt(1), T, cc=cc_oracle.cc_label)
+    worst_iou, worst_err = 1.0, 0.0
+    for t in range(T):
+        a, b = got[t], ref[t]["pred_masks"]
+        iou = ((a > 0) & (b > 0)).sum().item() / max(((a > 0) | (b > 0)).sum().item(), 1)
+        unfilled = (a != 0.1) & (b != 0.1)            # hole filling is a discrete decision on pixels at logit ~ 0
+        err = (a - b).abs()[unfilled].max().item()
+        worst_iou, worst_err = min(worst_iou, iou), max(worst_err, err)
+        assert iou >= 0.995, (t, iou)
+        assert err < 1e-2, (t, err)
+    print(f"19 frames vs oracle: worst IoU {worst_iou:.5f}, worst logit error {worst_err:.3e}")
