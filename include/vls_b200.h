@@ -43,6 +43,8 @@ void vls_launch_count_add(long long n);
  * kernel loads its own K / V^T tiles, 2 = CTAs run as cluster pairs that TMA-multicast half a tile each.
  * "attn_balanced": 1 (default) = long key sequences whose fixed KV split would leave SMs idle are run in balanced mode:
  * the (query tile, key tile) units are dealt out evenly to one persistent CTA per SM; 0 = always fixed splits.
+ * "attn_v_rows": 1 (default) = the memory cross-attention reads its value operand straight from the bank rows; 0 = from
+ * a transposed copy made once per frame.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -93,6 +95,17 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
                        long long k_bstride, const void* Vt, long long ldvt, long long vt_bstride, int B, int Nq, int Nk,
                        float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
                        size_t workspace_bytes, vls_stream_t stream);
+
+/* Generalisation used by the memory cross-attention (r2): q/k head dimension 256, VALUE dimension dv in {256, 64}.
+ * v_rows = 0: V is given transposed, bf16 [B][dv][ldv]; v_rows = 1 (dv == 64 only): V is given as rows bf16 [B][Nk][ldv],
+ * exactly as the memory bank stores it (consumed as an MN-major tensor-core operand; nothing is transposed or copied).
+ * O: bf16 [B][Nq][ldo] with dv columns.  With dv = 64 the memory attention computes softmax(QK^T) mem and folds the
+ * value projection into the output projection (sam/transformer.py:311-360, memory_attention.py:66-81). */
+size_t vls_attention_qk256_workspace_bytes(int B, int Nq, int Nk, int dv, int splits);
+int vls_attention_qk256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
+                        long long k_bstride, const void* V, long long ldv, long long v_bstride, int dv, int v_rows, int B,
+                        int Nq, int Nk, float scale, int splits, void* O, long long ldo, long long o_bstride,
+                        void* workspace, size_t workspace_bytes, vls_stream_t stream);
 
 /* Bilinear resize of n f32 images [h,w] -> [H,W], align_corners=False, no antialiasing
  * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */
@@ -147,7 +160,9 @@ typedef struct vls_mem_attn_layer {
   const void* sa_v_w;  const float* sa_v_b;   /* [256,256] */
   const void* sa_o_w;  const float* sa_o_b;   /* [256,256] */
   const void* ca_q_w;  const float* ca_q_b;   /* [256,256] cross_attn_image.q_proj */
-  const void* ca_o_w;  const float* ca_o_b;   /* [256,256] */
+  const void* ca_ov_w; const float* ca_ov_b;  /* [256,64] = out_proj.W @ v_proj.W, out_proj.W @ v_proj.b + out_proj.b:
+                                               * the cross-attention value and output projections folded into one
+                                               * (softmax rows sum to 1, so P (mem Wv^T + bv) Wo^T = (P mem)(Wo Wv)^T + Wo bv) */
   const void* l1_w;    const float* l1_b;     /* [2048,256] */
   const void* l2_w;    const float* l2_b;     /* [256,2048] */
   const float *n1_w, *n1_b, *n2_w, *n2_b, *n3_w, *n3_b;
@@ -156,10 +171,9 @@ typedef struct vls_mem_attn_weights {
   int num_layers;                 /* <= 8 */
   vls_mem_attn_layer layers[8];
   const float *norm_w, *norm_b;
-  /* cross_attn_image.k_proj / v_proj of all layers stacked, so the memory bank is projected for every
-   * layer in one launch: bf16 [num_layers][256][64], f32 [num_layers][256] */
+  /* cross_attn_image.k_proj of all layers stacked, so the memory bank is projected for every layer in one launch:
+   * bf16 [num_layers][256][64], f32 [num_layers][256].  (There is no value projection: see ca_ov_w.) */
   const void* ca_k_w_all; const float* ca_k_b_all;
-  const void* ca_v_w_all; const float* ca_v_b_all;
   const float *rope_cos, *rope_sin; /* f32 [Nq][128]: axial table for a sqrt(Nq) x sqrt(Nq) grid */
   int rope_len;                   /* must equal Nq */
 } vls_mem_attn_weights;

@@ -138,7 +138,43 @@ def run_reference_clip(model, clip, batch, num_frames):
     return per_frame
 
 
-def clip_case(model, sd, name, seed, num_frames, batch, sub=2):
+def patch_reference_session(model, clip, num_frames):
+    """Feeds the reference predictor the synthetic backbone features of `clip` (the image encoder is out of scope) and
+    routes its hole filling through the C oracle; returns init_state(**kw)."""
+    import sam2.sam2_video_predictor as vp
+    import sam2.utils.misc as misc
+
+    misc.get_connected_components = lambda m: cc_oracle.cc_label(m)
+    vp.fill_holes_in_mask_scores.__globals__["get_connected_components"] = misc.get_connected_components
+    imgs = torch.arange(num_frames, dtype=torch.float32).view(-1, 1, 1, 1).expand(-1, 3, 1, 1).contiguous()
+    vp.load_video_frames = lambda **kw: (imgs, 1024, 1024)
+
+    def forward_image(img):
+        t = int(img.flatten()[0].item())
+        f = clip.frame(t, 1)
+        feat = f["vision_feat"].permute(1, 2, 0).reshape(1, 256, 64, 64)
+        pos = f["vision_pos"].permute(1, 2, 0).reshape(1, 256, 64, 64)
+        return {"backbone_fpn": [f["feat_s0"], f["feat_s1"], feat],
+                "vision_pos_enc": [torch.zeros(1, 1, 256, 256), torch.zeros(1, 1, 128, 128), pos]}
+
+    model.forward_image = forward_image
+    return lambda **kw: model.init_state(video_path="synthetic", **kw)
+
+
+def api_case(model):
+    """tests/golden/api.npz: the reference's answers to golden_cases.api_scenarios."""
+    clip = synth.SyntheticClip(golden_cases.API_CLIP_SEED, golden_cases.API_FRAMES)
+    init = patch_reference_session(model, clip, golden_cases.API_FRAMES)
+    rec = golden_cases.api_scenarios(model, init)
+    for k in sorted(rec):
+        if "ptr" not in k:
+            print(f"api {k}: fg {np.unpackbits(rec[k], axis=1).mean():.4f}")
+    np.savez_compressed(os.path.join(OUT, "api.npz"), **rec)
+
+
+def clip_case(model, sd, name, seed, num_frames, batch, sub=2, dense=None):
+    """dense: frames whose logits / memories are stored (None = all); every frame stores the bit-packed binary mask,
+    the object pointer and the object score, so IoU and the gate are checked on all of them."""
     clip = synth.SyntheticClip(seed, num_frames)
     ref = run_reference_clip(model, clip, batch, num_frames)
     ora = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, batch), clip.point_prompt(batch), num_frames,
@@ -153,13 +189,24 @@ def clip_case(model, sd, name, seed, num_frames, batch, sub=2):
               f"obj {r['object_score_logits'].flatten().tolist()} fg {fg:.4f} "
               f"range [{r['pred_masks'].min():.2f},{r['pred_masks'].max():.2f}]")
         assert d_mask < 2e-3 and d_ptr < 1e-3, "oracle drifted from the reference"
-        out[f"mask_s{sub}_{t}"] = r["pred_masks"][:, :, ::sub, ::sub].numpy()
-        out[f"prefill_s{sub}_{t}"] = r["pred_masks_prefill"][:, :, ::sub, ::sub].numpy()
+        if dense is None or t in dense:
+            out[f"mask_s{sub}_{t}"] = r["pred_masks"][:, :, ::sub, ::sub].numpy()
+            out[f"prefill_s{sub}_{t}"] = r["pred_masks_prefill"][:, :, ::sub, ::sub].numpy()
+            out[f"mem_s4_{t}"] = r["maskmem_features"].float()[:, :, ::4, ::4].numpy()
         out[f"maskbits_{t}"] = np.packbits((r["pred_masks"] > 0).numpy().reshape(batch, -1), axis=1)
         out[f"obj_ptr_{t}"] = r["obj_ptr"].numpy()
         out[f"obj_score_{t}"] = r["object_score_logits"].numpy()
-        out[f"mem_s4_{t}"] = r["maskmem_features"].float()[:, :, ::4, ::4].numpy()
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+
+
+# Clips whose weights differ from synth.init_state_dict(0) only in the object-score bias (synth.init_state_dict's
+# `obj_score_bias`).  With random weights the object score is nearly the same on every frame (0.09 on the prompt frame,
+# 0.15 afterwards at bias 0), so the -1024 gate -> no_obj_ptr -> no_obj_embed_spatial chain (sam2_base.py:359-403,
+# 716-722) is reached by moving the bias: -0.12 puts only the PROMPT frame below 0 (its memory and pointer then enter
+# every later frame through the conditioning slot), -0.9 puts every frame below 0 (the chain runs on propagated frames).
+GATE_CLIPS = (("clip_gate_cond_t6", dict(seed=6, num_frames=6, batch=1), -0.12),
+              ("clip_gate_all_t6", dict(seed=7, num_frames=6, batch=2), -0.9))
+STEADY = {0, 1, 2, 8, 15, 16, 17, 18, 19}
 
 
 def main():
@@ -175,9 +222,22 @@ def main():
         for name, kw in (("clip_b1_t8", dict(seed=1, num_frames=8, batch=1)),
                          ("clip_b2_t4", dict(seed=2, num_frames=4, batch=2)),
                          # BASELINE configs[2]: 8 objects tracked jointly (batched memory bank / object pointers)
-                         ("clip_b8_t3", dict(seed=3, num_frames=3, batch=8, sub=4))):
+                         ("clip_b8_t3", dict(seed=3, num_frames=3, batch=8, sub=4)),
+                         # steady state pinned to the REFERENCE (r1 pinned it to the oracle only): 7 memories + 16
+                         # pointers from frame 16 on, i.e. the CUDA-graph path and the balanced attention mode ...
+                         ("clip_b1_t20", dict(seed=4, num_frames=20, batch=1, dense=STEADY)),
+                         # ... and configs[2]'s shape at full bank (8 objects: fixed-split attention, direct bf16 store)
+                         ("clip_b8_t20", dict(seed=5, num_frames=20, batch=8, sub=4, dense=STEADY))):
             if not only or name in only:
                 clip_case(model, sd, name, **kw)
+        if not only or "api" in only:
+            api_case(model)
+        for name, kw, bias in GATE_CLIPS:
+            if not only or name in only:
+                sd_g = synth.init_state_dict(0, obj_score_bias=bias)
+                load_synth_weights(model, sd_g)
+                clip_case(model, sd_g, name, **kw)
+                load_synth_weights(model, sd)
     print("golden vectors written to", OUT)
 
 

@@ -19,3 +19,76 @@ def module_inputs():
     d["pix"] = rn(2, 256, 64, 64) * 0.5
     d["msk"] = torch.sigmoid(rn(2, 1, 1024, 1024) * 3) * 20 - 10
     return d
+
+
+# ----------------------------------------------------------------------------- predictor API scenarios
+def blob_mask(cx=300.0, cy=500.0, radius=90.0, size=1024):
+    """Boolean [size,size] disk: the mask prompt of the add_new_mask scenario."""
+    yy = torch.arange(size, dtype=torch.float32).view(size, 1) + 0.5
+    xx = torch.arange(size, dtype=torch.float32).view(1, size) + 0.5
+    return ((xx - cx) ** 2 + (yy - cy) ** 2) <= radius * radius
+
+
+API_FRAMES = 4
+API_CLIP_SEED = 8
+
+
+def api_scenarios(predictor, init_state, names=None):
+    """Drives a predictor with the reference's public API (sam2_video_predictor.py) through the calls r1 left untested --
+    add_new_mask (:321), re-click on a tracked frame with prev_sam_mask_logits (:269-297), clear_all_prompts_in_frame
+    (:777), non_overlap_masks (_apply_non_overlapping_constraints, sam2_base.py:889), reverse propagation,
+    offload_state_to_cpu (:70-75) -- and records what they return.  The SAME function runs the unmodified reference
+    (tests/golden/make_golden.py -> tests/golden/api.npz) and this repository's predictor (tests/test_predictor_gpu.py).
+    `init_state(**kw)` opens a session on the API_CLIP_SEED clip with API_FRAMES frames."""
+    import numpy as np
+
+    rec = {}
+
+    def bits(name, video_res):
+        rec[name] = np.packbits((video_res.detach().float().cpu() > 0).numpy().reshape(video_res.shape[0], -1), axis=1)
+
+    def track(tag, st, **kw):
+        for f, ids, video in predictor.propagate_in_video(st, **kw):
+            bits(f"{tag}_f{f}", video)
+            key = "cond_frame_outputs" if f in st["output_dict"]["cond_frame_outputs"] else "non_cond_frame_outputs"
+            rec[f"{tag}_ptr{f}"] = st["output_dict"][key][f]["obj_ptr"].detach().float().cpu().numpy()
+
+    want = lambda n: names is None or n in names
+    if want("mask"):
+        st = init_state()
+        f, ids, video = predictor.add_new_mask(st, 0, 1, blob_mask())
+        assert f == 0 and list(ids) == [1]
+        bits("mask_prompt", video)
+        track("mask", st)
+    if want("reclick"):
+        st = init_state()
+        predictor.add_new_points_or_box(st, 0, 1, points=[[300.0, 500.0]], labels=[1])
+        track("reclick_first", st)
+        # a negative click on an already tracked frame: the decoder also gets the frame's previous logits
+        f, ids, video = predictor.add_new_points_or_box(st, 2, 1, points=[[400.0, 520.0]], labels=[0])
+        assert f == 2
+        bits("reclick_edit", video)
+        track("reclick_second", st)
+        f, ids, video = predictor.clear_all_prompts_in_frame(st, 2, 1)
+        bits("reclick_cleared", video)
+        track("reclick_third", st)
+    if want("nonoverlap"):
+        old = predictor.non_overlap_masks
+        predictor.non_overlap_masks = True
+        try:
+            st = init_state()
+            predictor.add_new_points_or_box(st, 0, 1, points=[[300.0, 500.0]], labels=[1])
+            f, ids, video = predictor.add_new_points_or_box(st, 0, 2, points=[[340.0, 500.0]], labels=[1])
+            bits("nonoverlap_prompt", video)
+            track("nonoverlap", st)
+        finally:
+            predictor.non_overlap_masks = old
+    if want("reverse"):
+        st = init_state()
+        predictor.add_new_points_or_box(st, API_FRAMES - 1, 1, points=[[360.0, 530.0]], labels=[1])
+        track("reverse", st, reverse=True)
+    if want("offload"):
+        st = init_state(offload_state_to_cpu=True)
+        predictor.add_new_points_or_box(st, 0, 1, box=[200.0, 400.0, 420.0, 620.0])
+        track("offload", st)
+    return rec

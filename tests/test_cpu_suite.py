@@ -114,7 +114,7 @@ def test_library_exports_every_declared_symbol(vls_lib):
     handle = ctypes.CDLL(_lib.LIB_PATH)
     missing = [s for s in syms if not hasattr(handle, s)]
     assert not missing, missing
-    assert vls_lib.vls_abi_version() == 1
+    assert vls_lib.vls_abi_version() == 2
     # argument validation happens before any CUDA call, so it is testable without a device
     rc = vls_lib.vls_cc_label(None, 1, 5, 4, None, None, None, 0, None)
     assert rc != 0 and b"null" in vls_lib.vls_last_error().lower()
@@ -125,19 +125,27 @@ def test_library_exports_every_declared_symbol(vls_lib):
     assert vls_lib.vls_mem_attn_workspace_bytes(1, 4096, 28736) > 64 << 20
 
 
-def test_ctypes_structs_match_header_sizes():
-    """The weight structs are pointer/int records: their ctypes size must equal the C layout."""
-    from video_llava_seg_b200 import _pack
+def test_ctypes_structs_match_header_sizes(tmp_path):
+    """The ctypes mirrors in _pack.py must have the C layout of include/vls_b200.h: sizeof() of every weight struct is
+    taken from the header itself by compiling a probe with gcc."""
+    import subprocess
 
-    P, I = ctypes.sizeof(ctypes.c_void_p), ctypes.sizeof(ctypes.c_int)
-    assert ctypes.sizeof(_pack.MemAttnLayer) == 20 * P
-    assert ctypes.sizeof(_pack.MemAttnWeights) == P + 8 * 20 * P + 8 * P + P  # ints padded to pointer alignment
-    assert ctypes.sizeof(_pack.AttnW) == 8 * P
-    assert ctypes.sizeof(_pack.DecLayer) == 3 * 8 * P + 15 * P
-    assert ctypes.sizeof(_pack.CxBlock) == 8 * P
-    assert ctypes.sizeof(_pack.MemEncoderWeights) == 20 * P + 2 * 8 * P + 3 * P
-    assert ctypes.sizeof(_pack.ObjPtrWeights) == 7 * P
-    assert I == 4
+    from video_llava_seg_b200 import _lib, _pack
+
+    pairs = [("vls_mem_attn_layer", _pack.MemAttnLayer), ("vls_mem_attn_weights", _pack.MemAttnWeights),
+             ("vls_attn_w", _pack.AttnW), ("vls_dec_layer", _pack.DecLayer),
+             ("vls_mask_decoder_weights", _pack.MaskDecoderWeights), ("vls_cx_block", _pack.CxBlock),
+             ("vls_mem_encoder_weights", _pack.MemEncoderWeights), ("vls_obj_ptr_weights", _pack.ObjPtrWeights),
+             ("vls_gemm_desc", _lib.GemmDesc)]
+    src = tmp_path / "probe.c"
+    src.write_text('#include <stdio.h>\n#include "vls_b200.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n, _ in pairs) + "  return 0;\n}\n")
+    exe = tmp_path / "probe"
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.run(["gcc", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for n, ct in pairs:
+        assert ctypes.sizeof(ct) == int(sizes[n]), (n, ctypes.sizeof(ct), sizes[n])
 
 
 def test_product_path_fails_loudly_without_cuda(sd):
@@ -159,6 +167,28 @@ def test_product_path_fails_loudly_without_cuda(sd):
 
 
 # ----------------------------------------------------------------------------- host logic
+def test_load_state_dict_invalidates_weight_derived_caches(sd):
+    """r1 advisor finding: an in-place load_state_dict keeps every data_ptr, so caches keyed on pointers would survive a
+    checkpoint swap.  Each cache owner registers a load_state_dict post hook."""
+    from video_llava_seg_b200 import build_sam
+    from video_llava_seg_b200.llava_seg_head import SegmentationHeadSAM2
+
+    model = build_sam.build_sam2_video_predictor(None, sd, "cpu")
+    pe0 = model.sam_prompt_encoder.get_dense_pe()
+    v0 = pe0._vls_version
+    model._consts = {"stale": True}
+    model.memory_attention._packed = ("stale",)
+    head = SegmentationHeadSAM2(n_token_dims=32, n_seg_queries=1, sam2_model=model)
+    head._w = ("stale",)
+    sd2 = {k: v + 0.01 for k, v in sd.items()}
+    model.load_state_dict(sd2, strict=True)
+    assert model._consts is None and model.memory_attention._packed is None
+    pe1 = model.sam_prompt_encoder.get_dense_pe()
+    assert pe1._vls_version == v0 + 1 and not torch.equal(pe0, pe1)
+    head.load_state_dict(head.state_dict())
+    assert head._w is None
+
+
 def test_state_dict_layout_is_the_reference_layout(sd):
     from video_llava_seg_b200 import build_sam, synth
 

@@ -105,6 +105,52 @@ def test_attention_d256(dev, B, Nq, Nk, splits):
     assert err < 2e-2, err
 
 
+@pytest.mark.parametrize("v_rows", [True, False])
+@pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 256, 520, 1), (2, 256, 1000, 2), (1, 4096, 28736, 0),
+                                            (1, 4096, 28700, 4), (1, 4096, 28700, 0), (2, 2048, 16500, 0),
+                                            (1, 300, 40000, 0), (8, 4096, 9000, -1), (8, 4096, 28736, 0),
+                                            (3, 1024, 4100, 1)])
+def test_attention_value_dim_64(dev, B, Nq, Nk, splits, v_rows):
+    """The memory cross-attention's shape since r2: q/k dim 256, VALUE dim 64 (the raw memory rows; the value projection
+    is folded into the output projection).  v_rows: V read as [Nk,64] rows (MN-major tensor-core operand) or from a
+    transposed [64,ld] copy.  vs fp32 SDPA on the same bf16 inputs; P is rounded to bf16 inside the kernel."""
+    from video_llava_seg_b200 import ops
+
+    q = _rand((B, Nq, 256), dev, 11).bfloat16()
+    k = _rand((B, Nk, 256), dev, 12).bfloat16()
+    v = _rand((B, Nk, 64), dev, 13).bfloat16()
+    if v_rows:
+        out = ops.attention_qk256(q, k, v, True, splits=splits)
+    else:
+        ld = (Nk + 63) // 64 * 64
+        vt = torch.zeros((B, 64, ld), device=dev, dtype=torch.bfloat16)
+        vt[:, :, :Nk] = v.transpose(1, 2)
+        out = ops.attention_qk256(q, k, vt, False, splits=splits)
+    assert out.shape == (B, Nq, 64)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 2e-2, err
+
+
+def test_attention_value_dim_64_is_bitwise_deterministic(dev, vls_lib):
+    """Race detector for the two-stage K ring + single V stage of the dv = 64 kernel (balanced mode, full bank)."""
+    from video_llava_seg_b200 import ops
+
+    q = _rand((1, 4096, 256), dev, 41).bfloat16()
+    k = _rand((1, 28736, 256), dev, 42).bfloat16()
+    v = _rand((1, 28736, 64), dev, 43).bfloat16()
+    flush = torch.empty(300 << 20, dtype=torch.uint8, device=dev)
+    base = ops.attention_qk256(q, k, v, True).clone()
+    for it in range(120):
+        if it % 3 == 0:
+            flush.zero_()
+        if it % 7 == 0:
+            (q.float() @ k.float().transpose(1, 2)).sum()
+        out = ops.attention_qk256(q, k, v, True)
+        assert torch.equal(out, base), f"run {it} differs from run 0"
+
+
 @pytest.mark.parametrize("shape,density", [((1, 1, 256, 256), 0.5), ((8, 1, 256, 256), 0.62), ((3, 1, 64, 96), 0.4),
                                            ((2, 1, 2, 2), 0.5), ((1, 1, 250, 130), 0.55), ((2, 1, 512, 384), 0.6),
                                            ((1, 1, 1024, 1024), 0.58), ((4, 1, 256, 256), 0.0), ((4, 1, 256, 256), 1.0)])

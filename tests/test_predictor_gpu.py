@@ -20,6 +20,21 @@ def predictor(vls_lib):
     return build_sam.build_sam2_video_predictor(None, synth.init_state_dict(0), "cuda:0")
 
 
+@pytest.fixture(scope="module")
+def predictor_with_bias(vls_lib, predictor):
+    """Predictors whose weights differ only in the object-score bias (the gate clips of make_golden.py)."""
+    from video_llava_seg_b200 import build_sam, synth
+
+    cache = {0.75: predictor}
+
+    def get(bias):
+        if bias not in cache:
+            cache[bias] = build_sam.build_sam2_video_predictor(None, synth.init_state_dict(0, obj_score_bias=bias), "cuda:0")
+        return cache[bias]
+
+    return get
+
+
 def _run(predictor, seed, num_frames, batch):
     from video_llava_seg_b200 import synth
     from video_llava_seg_b200.features import FeatureClip
@@ -52,46 +67,71 @@ def _run(predictor, seed, num_frames, batch):
     return [tuple(f) + (p,) for f, p in zip(frames, pre)]
 
 
-@pytest.mark.parametrize("name,seed,T,B", [("clip_b1_t8", 1, 8, 1), ("clip_b2_t4", 2, 4, 2), ("clip_b8_t3", 3, 3, 8)])
-def test_propagation_matches_reference(predictor, name, seed, T, B):
-    """clip_b8_t3 is BASELINE configs[2]'s shape: 8 objects tracked jointly (batched bank, pointers, decoder)."""
+CLIPS = [("clip_b1_t8", 1, 8, 1, 0.75), ("clip_b2_t4", 2, 4, 2, 0.75), ("clip_b8_t3", 3, 3, 8, 0.75),
+         # reference-generated steady state (7 memories + 16 pointers, CUDA-graph frames 16-19, balanced attention) ...
+         ("clip_b1_t20", 4, 20, 1, 0.75),
+         # ... and BASELINE configs[2]'s shape at FULL bank: 8 objects tracked jointly, fixed-split attention
+         ("clip_b8_t20", 5, 20, 8, 0.75),
+         # object gate (sam2_base.py:359-403,716-722): prompt frame below 0 / every frame below 0
+         ("clip_gate_cond_t6", 6, 6, 1, -0.12), ("clip_gate_all_t6", 7, 6, 2, -0.9)]
+
+
+@pytest.mark.parametrize("name,seed,T,B,bias", CLIPS)
+def test_propagation_matches_reference(predictor_with_bias, name, seed, T, B, bias):
+    """clip_b8_t3 / clip_b8_t20 are BASELINE configs[2]'s shape: 8 objects tracked jointly (batched bank, pointers,
+    decoder).  Every frame: binarised-mask IoU, object pointer and object score against the unmodified reference; the
+    frames the golden file stores densely: raw logits, hole-filled logits and the encoded memory too."""
     gold = np.load(os.path.join(GOLD, name + ".npz"))
     sub = 4 if "mask_s4_0" in gold.files else 2          # spatial sub-sampling of the stored reference logits
+    predictor = predictor_with_bias(bias)
     frames = _run(predictor, seed, T, B)
     assert [f[0] for f in frames] == list(range(T))
     worst = dict(err=0.0, iou=1.0, flips=0.0)
+    gated = 0
     for t, out, video_res, prefill in frames:
-        # (1) raw decoder logits (before hole filling): north-star bound 1e-2 abs
-        err = (prefill.float().cpu()[:, :, ::sub, ::sub] - torch.from_numpy(gold[f"prefill_s{sub}_{t}"])).abs().max().item()
-        # (2) stored (hole-filled) logits: binarised IoU >= 0.995; filling is a discrete decision on pixels whose
-        #     logit is within noise of 0, so a few pixels may differ by the fill value 0.1 -- bound their share
         pm = out["pred_masks"].float().cpu()
-        ref_post = torch.from_numpy(gold[f"mask_s{sub}_{t}"])
-        d = (pm[:, :, ::sub, ::sub] - ref_post).abs()
-        flips = (d > 1e-2).float().mean().item()
-        one_sided_fill = (pm[:, :, ::sub, ::sub] == 0.1) ^ (ref_post == 0.1)
-        assert ((d <= 1e-2) | one_sided_fill).all(), "post-fill differences must be pixels filled on one side only"
         ref_bits = np.unpackbits(gold[f"maskbits_{t}"], axis=1).reshape(B, 1, 256, 256).astype(bool)
         got_bits = (pm > 0).numpy()
-        iou = (ref_bits & got_bits).sum() / max((ref_bits | got_bits).sum(), 1)
+        union = (ref_bits | got_bits).sum()
+        iou = (ref_bits & got_bits).sum() / union if union else 1.0
         ptr_err = (out["obj_ptr"].cpu() - torch.from_numpy(gold[f"obj_ptr_{t}"])).abs().max().item()
-        osl_err = (out["object_score_logits"].cpu() - torch.from_numpy(gold[f"obj_score_{t}"])).abs().max().item()
-        md = (out["maskmem_features"].float().cpu()[:, :, ::4, ::4] - torch.from_numpy(gold[f"mem_s4_{t}"])).abs()
-        mem_err, mem_mean = md.max().item(), md.mean().item()
-        print(f"{name} t={t}: logit err {err:.3e} IoU {iou:.5f} fill-flips {flips:.2e} obj_ptr err {ptr_err:.3e} "
-              f"obj_score err {osl_err:.3e} mem err max {mem_err:.3e} mean {mem_mean:.3e}")
-        worst = dict(err=max(worst["err"], err), iou=min(worst["iou"], iou), flips=max(worst["flips"], flips))
-        assert err < 1e-2, f"frame {t}: mask logit error {err}"
+        ref_osl = torch.from_numpy(gold[f"obj_score_{t}"])
+        osl_err = (out["object_score_logits"].cpu() - ref_osl).abs().max().item()
+        assert torch.equal(out["object_score_logits"].cpu() > 0, ref_osl > 0), f"frame {t}: object gate differs"
+        gated += int((ref_osl <= 0).sum())
+        line = f"{name} t={t}: IoU {iou:.5f} obj_ptr err {ptr_err:.3e} obj_score err {osl_err:.3e}"
         assert iou >= 0.995, f"frame {t}: IoU {iou}"
-        assert flips < 2e-3, f"frame {t}: {flips:.2e} of the pixels changed by hole filling"
-        # memories: the prompt-frame mask is binarised to +-10 before encoding (sam2_base.py:698-700), so pixels
-        # within noise of 0 move a few features by O(0.1); bound the mean and keep the max loose
-        assert osl_err < 1e-2 and ptr_err < 5e-2 and mem_mean < 2e-2 and mem_err < 1.0
+        assert osl_err < 1e-2 and ptr_err < 5e-2, (t, osl_err, ptr_err)
         assert out["maskmem_features"].dtype == torch.bfloat16
+        if f"prefill_s{sub}_{t}" in gold.files:
+            # (1) raw decoder logits (before hole filling): north-star bound 1e-2 abs
+            err = (prefill.float().cpu()[:, :, ::sub, ::sub] - torch.from_numpy(gold[f"prefill_s{sub}_{t}"])).abs().max().item()
+            # (2) stored (hole-filled) logits: filling is a discrete decision on pixels whose logit is within noise of 0,
+            #     so a few pixels may differ by the fill value 0.1 -- bound their share
+            ref_post = torch.from_numpy(gold[f"mask_s{sub}_{t}"])
+            d = (pm[:, :, ::sub, ::sub] - ref_post).abs()
+            flips = (d > 1e-2).float().mean().item()
+            one_sided_fill = (pm[:, :, ::sub, ::sub] == 0.1) ^ (ref_post == 0.1)
+            assert ((d <= 1e-2) | one_sided_fill).all(), "post-fill differences must be pixels filled on one side only"
+            md = (out["maskmem_features"].float().cpu()[:, :, ::4, ::4] - torch.from_numpy(gold[f"mem_s4_{t}"])).abs()
+            mem_err, mem_mean = md.max().item(), md.mean().item()
+            line += f" logit err {err:.3e} fill-flips {flips:.2e} mem err max {mem_err:.3e} mean {mem_mean:.3e}"
+            worst["err"], worst["flips"] = max(worst["err"], err), max(worst["flips"], flips)
+            assert err < 1e-2, f"frame {t}: mask logit error {err}"
+            assert flips < 2e-3, f"frame {t}: {flips:.2e} of the pixels changed by hole filling"
+            # memories: the prompt-frame mask is binarised to +-10 before encoding (sam2_base.py:698-700), so pixels
+            # within noise of 0 move a few features by O(0.1); bound the mean and keep the max loose
+            assert mem_mean < 2e-2 and mem_err < 1.0
+        print(line)
+        worst["iou"] = min(worst["iou"], iou)
         # the yielded video-res logits are the bilinear up-sampling of the stored low-res logits
         up = torch.nn.functional.interpolate(out["pred_masks"].float(), size=(1024, 1024), mode="bilinear",
                                              align_corners=False)
-        assert (video_res - up).abs().max().item() < 1e-4
+        assert (video_res - up).abs().max().item() < 1e-4 * max(1.0, up.abs().max().item())
+    if "gate" in name:
+        assert gated > 0, "the gate clip must contain frames with object_score_logits <= 0"
+    if T >= 20:
+        assert frames[-1][0] == T - 1 and predictor.use_cuda_graph
     print(f"{name} worst: {worst}")
 
 
@@ -166,6 +206,35 @@ def test_api_errors(predictor):
     predictor.add_new_points_or_box(state, 2, 7, box=[200.0, 400.0, 420.0, 620.0])
     rev = [f for f, _, _ in predictor.propagate_in_video(state, reverse=True)]
     assert rev == [2, 1, 0]
+
+
+@pytest.mark.parametrize("scenario", ["mask", "reclick", "nonoverlap", "reverse", "offload"])
+def test_api_scenarios_match_reference(predictor, scenario):
+    """add_new_mask, re-click with prev_sam_mask_logits, clear_all_prompts_in_frame, non_overlap_masks, reverse
+    propagation and offload_state_to_cpu: the same driver (tests/golden_cases.api_scenarios) that recorded the unmodified
+    reference's answers into tests/golden/api.npz runs this predictor; every returned video-resolution mask must match
+    (binarised IoU >= 0.995) and every object pointer (5e-2)."""
+    from tests import golden_cases
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    gold = np.load(os.path.join(GOLD, "api.npz"))
+    clip = synth.SyntheticClip(golden_cases.API_CLIP_SEED, golden_cases.API_FRAMES)
+    src = FeatureClip(lambda t: clip.frame(t, 1), golden_cases.API_FRAMES, resident_device="cuda:0")
+    rec = golden_cases.api_scenarios(predictor, lambda **kw: predictor.init_state(src, **kw), names=[scenario])
+    keys = [k for k in gold.files if k.startswith(scenario)]
+    assert keys and set(keys) == set(rec), (sorted(set(keys) ^ set(rec)))
+    for k in keys:
+        if "_ptr" in k:
+            err = np.abs(rec[k] - gold[k]).max()
+            assert err < 5e-2, (k, err)
+        else:
+            a, b = np.unpackbits(rec[k], axis=1).astype(bool), np.unpackbits(gold[k], axis=1).astype(bool)
+            assert a.shape == b.shape
+            union = (a | b).sum()
+            iou = (a & b).sum() / union if union else 1.0
+            print(f"{k}: IoU {iou:.5f} fg {b.mean():.4f}")
+            assert iou >= 0.995, (k, iou)
 
 
 def test_seg_embedding_prompt_then_propagation(predictor):
@@ -363,6 +432,66 @@ def test_captured_graph_is_reused_across_clips(predictor):
         gen.close()
     finally:
         predictor.use_cuda_graph = True
+
+
+def test_interleaved_sessions_never_share_a_graph(predictor):
+    """r1 advisor finding: a FINISHED session keeps a reference to its captured graph; after that graph has been handed
+    to another clip, resetting / re-propagating the finished session must not release or re-enter it.  Three sessions
+    are advanced in lockstep after session A (finished, graph re-bound to B) is reset; every session must reproduce
+    its own eager track."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 20
+
+    def new_session(seed):
+        clip = synth.SyntheticClip(seed, T)
+        st = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
+        predictor.add_new_points_or_box(st, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
+        return st
+
+    def masks_of(st, f):
+        return st["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]["pred_masks"].float().cpu()
+
+    def eager(seed):
+        predictor.use_cuda_graph = False
+        try:
+            st = new_session(seed)
+            return [masks_of(st, f) for f, _, _ in predictor.propagate_in_video(st)]
+        finally:
+            predictor.use_cuda_graph = True
+
+    ref = {seed: eager(seed) for seed in (51, 52, 53)}
+    predictor.__dict__.pop("_graph_cache", None)
+    st_a = new_session(51)
+    for _ in predictor.propagate_in_video(st_a):
+        pass
+    g1 = st_a["steady_graph"]
+    assert g1 is not None and g1.idle()
+    st_b = new_session(52)
+    gen_b = predictor.propagate_in_video(st_b)
+    got_b = [masks_of(st_b, next(gen_b)[0]) for _ in range(18)]          # B is now mid-clip on A's old graph
+    assert st_b["steady_graph"] is g1 and not g1.idle()
+    predictor.reset_state(st_a)                                          # must NOT release B's graph
+    assert not g1.idle() and g1.owned_by(st_b["graph_owner"])
+    predictor.add_new_points_or_box(st_a, 0, 1, points=synth.SyntheticClip(51, T).point_prompt(1)["point_coords"][0].tolist(),
+                                    labels=[1])
+    st_c = new_session(53)
+    gen_a, gen_c = predictor.propagate_in_video(st_a), predictor.propagate_in_video(st_c)
+    got_a, got_c = [], []
+    for i in range(T):                                                   # lockstep: A and C, while B stays mid-clip
+        got_a.append(masks_of(st_a, next(gen_a)[0]))
+        got_c.append(masks_of(st_c, next(gen_c)[0]))
+    assert g1.owned_by(st_b["graph_owner"]) and g1.next_frame == 18      # nobody touched B's bank
+    got_b += [masks_of(st_b, f) for f, _, _ in gen_b]                    # B's last two frames
+    graphs = {id(st["steady_graph"]) for st in (st_a, st_b, st_c) if st["steady_graph"] is not None}
+    assert st_a["steady_graph"] is not g1 and st_c["steady_graph"] is not g1 and len(graphs) == 3
+    for got, seed in ((got_a, 51), (got_b, 52), (got_c, 53)):
+        for t in range(T):
+            same = ((got[t] > 0) == (ref[seed][t] > 0)).float().mean().item()
+            assert same > 0.9995, (seed, t, same)
+            d = (got[t] - ref[seed][t]).abs()
+            assert d[(got[t] != 0.1) & (ref[seed][t] != 0.1)].median() < 1e-4, (seed, t)
 
 
 def test_ramp_frames_replay_graphs_from_the_second_clip_on(predictor):

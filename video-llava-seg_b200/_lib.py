@@ -60,6 +60,12 @@ def _declare(lib):
     lib.vls_gemm_bf16.argtypes = [ctypes.POINTER(GemmDesc), c_void_p]
     lib.vls_attention_workspace_bytes.restype = c_size_t
     lib.vls_attention_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
+    lib.vls_attention_qk256_workspace_bytes.restype = c_size_t
+    lib.vls_attention_qk256_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_int]
+    lib.vls_attention_qk256.restype = c_int
+    lib.vls_attention_qk256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
+                                        c_int, c_int, c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t,
+                                        c_void_p]
     lib.vls_attention_d256.restype = c_int
     lib.vls_attention_d256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
                                        c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t, c_void_p]
@@ -134,10 +140,22 @@ def ptr(t):
 
 
 def stream():
+    """The current stream of the CURRENT device -- which require_cuda() has made the operands' device."""
     return c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def require_cuda(*tensors):
+    """All operands must live on ONE CUDA device; that device becomes the current one (the library launches on the
+    current device and uses per-device side streams, so operands on another device would mean foreign pointers)."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise RuntimeError("inputs must be a CUDA tensor")  # connected_components.cu:215
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"operands are on different devices ({dev} and {t.device})")
+    if dev is not None and dev.index is not None and dev.index != torch.cuda.current_device():
+        torch.cuda.set_device(dev)

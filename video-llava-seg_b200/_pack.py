@@ -18,13 +18,13 @@ def _fields(*names):
 
 
 class MemAttnLayer(ctypes.Structure):
-    _fields_ = _fields("sa_qk_w", "sa_qk_b", "sa_v_w", "sa_v_b", "sa_o_w", "sa_o_b", "ca_q_w", "ca_q_b", "ca_o_w",
-                       "ca_o_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b", "n3_w", "n3_b")
+    _fields_ = _fields("sa_qk_w", "sa_qk_b", "sa_v_w", "sa_v_b", "sa_o_w", "sa_o_b", "ca_q_w", "ca_q_b", "ca_ov_w",
+                       "ca_ov_b", "l1_w", "l1_b", "l2_w", "l2_b", "n1_w", "n1_b", "n2_w", "n2_b", "n3_w", "n3_b")
 
 
 class MemAttnWeights(ctypes.Structure):
     _fields_ = [("num_layers", c_int), ("layers", MemAttnLayer * 8), ("norm_w", c_void_p), ("norm_b", c_void_p),
-                ("ca_k_w_all", c_void_p), ("ca_k_b_all", c_void_p), ("ca_v_w_all", c_void_p), ("ca_v_b_all", c_void_p),
+                ("ca_k_w_all", c_void_p), ("ca_k_b_all", c_void_p),
                 ("rope_cos", c_void_p), ("rope_sin", c_void_p), ("rope_len", c_int)]
 
 
@@ -132,7 +132,10 @@ def pack_mem_attn(sd, prefix, device):
         L.sa_v_w, L.sa_v_b = k.h(sd[sa + "v_proj.weight"]), k.f(sd[sa + "v_proj.bias"])
         L.sa_o_w, L.sa_o_b = k.h(sd[sa + "out_proj.weight"]), k.f(sd[sa + "out_proj.bias"])
         L.ca_q_w, L.ca_q_b = k.h(sd[ca + "q_proj.weight"]), k.f(sd[ca + "q_proj.bias"])
-        L.ca_o_w, L.ca_o_b = k.h(sd[ca + "out_proj.weight"]), k.f(sd[ca + "out_proj.bias"])
+        # value + output projection folded (softmax rows sum to one): the kernel attends over the raw 64-d memory
+        wo, wv = sd[ca + "out_proj.weight"].double(), sd[ca + "v_proj.weight"].double()
+        L.ca_ov_w = k.h((wo @ wv).float())
+        L.ca_ov_b = k.f((wo @ sd[ca + "v_proj.bias"].double() + sd[ca + "out_proj.bias"].double()).float())
         L.l1_w, L.l1_b = k.h(sd[p + "linear1.weight"]), k.f(sd[p + "linear1.bias"])
         L.l2_w, L.l2_b = k.h(sd[p + "linear2.weight"]), k.f(sd[p + "linear2.bias"])
         for j in (1, 2, 3):
@@ -142,8 +145,6 @@ def pack_mem_attn(sd, prefix, device):
     ca = [f"{prefix}layers.{i}.cross_attn_image." for i in range(n)]
     w.ca_k_w_all = k.h(torch.stack([sd[c + "k_proj.weight"] for c in ca], 0))
     w.ca_k_b_all = k.f(torch.stack([sd[c + "k_proj.bias"] for c in ca], 0))
-    w.ca_v_w_all = k.h(torch.stack([sd[c + "v_proj.weight"] for c in ca], 0))
-    w.ca_v_b_all = k.f(torch.stack([sd[c + "v_proj.bias"] for c in ca], 0))
     return w, k
 
 

@@ -10,7 +10,7 @@ using namespace vls;
 extern "C" {
 
 const char* vls_last_error(void) { return last_error(); }
-int vls_abi_version(void) { return 1; }
+int vls_abi_version(void) { return 2; }
 long long vls_launch_count(void) { return launch_count(); }
 void vls_launch_count_add(long long n) { count_launches((int)n); }
 void vls_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
@@ -23,6 +23,10 @@ int vls_set_tuning(const char* key, int value) {
   }
   if (std::string(key) == "attn_balanced") {   // 0: always fixed KV splits, 1: balanced ("stream-K") mode when it helps
     g_attn_balanced = value != 0;
+    return 0;
+  }
+  if (std::string(key) == "attn_v_rows") {   // memory cross-attention value operand: 1 = bank rows (MN-major), 0 = transposed copy
+    g_attn_v_rows = value != 0;
     return 0;
   }
   if (std::string(key) == "pdl") {   // programmatic dependent launch on/off (host.h)
@@ -68,28 +72,40 @@ static int resolve_splits(int B, int Nq, int Nk, int splits) {
   return splits > 0 ? splits : attn_pick_splits(B, Nq, Nk);
 }
 size_t vls_attention_workspace_bytes(int B, int Nq, int Nk, int splits) {
-  return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits));
+  return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits), 256);
+}
+size_t vls_attention_qk256_workspace_bytes(int B, int Nq, int Nk, int dv, int splits) {
+  return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits), dv);
+}
+
+int vls_attention_qk256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
+                        long long k_bstride, const void* V, long long ldv, long long v_bstride, int dv, int v_rows, int B,
+                        int Nq, int Nk, float scale, int splits, void* O, long long ldo, long long o_bstride,
+                        void* workspace, size_t workspace_bytes, vls_stream_t stream) {
+  splits = resolve_splits(B, Nq, Nk, splits);
+  AttnArgs a;
+  a.Q = Q; a.ldq = ldq; a.q_bstride = q_bstride;
+  a.K = K; a.ldk = ldk; a.k_bstride = k_bstride;
+  a.Vt = V; a.ldvt = ldv; a.vt_bstride = v_bstride; a.dv = dv; a.v_rows = v_rows;
+  a.B = B; a.Nq = Nq; a.Nk = Nk; a.scale = scale; a.splits = splits;
+  a.O = O; a.ldo = ldo; a.o_bstride = o_bstride;
+  if (splits != 1) {   // fixed KV splits, or 0 = balanced mode (picked automatically)
+    VLS_REQUIRE(dv == 256 || dv == 64, "attention: value dimension must be 256 or 64 (got %d)", dv);
+    const size_t need = attn_workspace_bytes(B, Nq, splits, dv);
+    VLS_REQUIRE(workspace && workspace_bytes >= need, "attention: workspace too small (%zu < %zu)", workspace_bytes,
+                need);
+    a.part_o = reinterpret_cast<float*>(workspace);
+    a.part_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + attn_part_ml_offset(B, Nq, splits, dv));
+  }
+  return launch_attention(a, (cudaStream_t)stream);
 }
 
 int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
                        long long k_bstride, const void* Vt, long long ldvt, long long vt_bstride, int B, int Nq, int Nk,
                        float scale, int splits, void* O, long long ldo, long long o_bstride, void* workspace,
                        size_t workspace_bytes, vls_stream_t stream) {
-  splits = resolve_splits(B, Nq, Nk, splits);
-  AttnArgs a;
-  a.Q = Q; a.ldq = ldq; a.q_bstride = q_bstride;
-  a.K = K; a.ldk = ldk; a.k_bstride = k_bstride;
-  a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = vt_bstride;
-  a.B = B; a.Nq = Nq; a.Nk = Nk; a.scale = scale; a.splits = splits;
-  a.O = O; a.ldo = ldo; a.o_bstride = o_bstride;
-  if (splits != 1) {   // fixed KV splits, or 0 = balanced mode (picked automatically)
-    const size_t need = attn_workspace_bytes(B, Nq, splits);
-    VLS_REQUIRE(workspace && workspace_bytes >= need, "attention: workspace too small (%zu < %zu)", workspace_bytes,
-                need);
-    a.part_o = reinterpret_cast<float*>(workspace);
-    a.part_ml = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + attn_part_ml_offset(B, Nq, splits));
-  }
-  return launch_attention(a, (cudaStream_t)stream);
+  return vls_attention_qk256(Q, ldq, q_bstride, K, ldk, k_bstride, Vt, ldvt, vt_bstride, 256, 0, B, Nq, Nk, scale, splits, O,
+                             ldo, o_bstride, workspace, workspace_bytes, stream);
 }
 
 int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,

@@ -21,6 +21,13 @@
 // SMs): the (query tile, key tile) units of the launch are dealt out evenly to one persistent CTA per SM; a CTA then
 // works on up to two segments (tail of one query tile's keys, head of the next one's), reloading Q in between, and
 // attn_combine_bal_kernel merges the 5-6 partials of each query tile.  Cross-attention launch 112.6 -> 108.7 us.
+// Value dimension DV: 256 (self-attention: V^T [256][Nk], K-major) or 64 (memory cross-attention, r2): softmax rows sum
+// to one, so softmax(QK^T)(mem Wv^T + bv) = (softmax(QK^T) mem) Wv^T + bv -- the kernel attends over the raw 64-d memory
+// rows and Wo.Wv is folded into the output projection (memory_attention.py:66-81, sam/transformer.py:311-360).  PV drops
+// from M128 N256 to M128 N64 MMAs, the V tile from 64 KB to 16 KB (which pays for a SECOND K stage: with one stage the
+// 64 KB K load of tile j+2 could only start when S(j+1) had completed and the ncu capture showed ~1100 idle tensor
+// cycles per tile), O needs 64 TMEM columns, and the per-frame V^T projection GEMM (59 MB of writes) is gone.  With
+// VMN the value tile is TMA-loaded as the bank stores it ([key][64 channels] rows) and consumed as an MN-major B operand.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -31,17 +38,22 @@ namespace {
 constexpr int BM = 128;
 constexpr int BN = 128;          // keys per tile: S = Q K^T runs as M128 N128 K16 MMAs (N=64 issues at half rate)
 constexpr int D = 256;
-constexpr int KV_STAGES = 1;     // Q 64 KB + K tile 64 KB + V^T tile 64 KB; K(j+1) streams in under softmax(j) + PV(j)
 constexpr int Q_BYTES = BM * D * 2;
 constexpr int K_BYTES = BN * D * 2;
-constexpr int V_BYTES = D * BN * 2;
 constexpr int THREADS = 352;           // K-producer warp + MMA warp + 8 softmax warps + V-producer warp
 constexpr int SOFTMAX_THREADS = 256;
 constexpr int XCHG_BYTES = 3 * 2 * BM * 4;  // row-max exchange [tile parity][half][row] + row-sum exchange [half][row]
-constexpr int SMEM_BYTES = Q_BYTES + KV_STAGES * (K_BYTES + V_BYTES) + XCHG_BYTES + 256 + 1024;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr uint32_t TM_O = 0;
-constexpr uint32_t TM_S = 256;   // 2 x 128 columns (f32 scores, overwritten in place by packed bf16 P)
+// per value dimension: DV=256: Q 64 KB + K 64 KB + V^T 64 KB (one stage each); DV=64: Q 64 KB + 2 x K 64 KB + V 16 KB
+template <int DV>
+struct ACfg {
+  static constexpr int KST = DV == 64 ? 2 : 1;      // K stages
+  static constexpr int V_BYTES = DV * BN * 2;       // one V stage
+  static constexpr int SMEM = Q_BYTES + KST * K_BYTES + V_BYTES + XCHG_BYTES + 256 + 1024;
+  static constexpr uint32_t TM_S = DV == 64 ? 128 : 256;   // 2 x 128 columns (f32 scores, overwritten in place by bf16 P)
+  static constexpr int OC = DV / 2;                 // O columns owned by each of the two softmax threads of a row
+};
 constexpr float RESCALE_THRESHOLD = 8.0f;
 constexpr uint16_t PAIR_MASK = 0x3;
 
@@ -74,7 +86,9 @@ struct Seg {
 //      gridDim.x = #SMs persistent CTAs, so a CTA processes up to two SEGMENTS (the tail of one query tile's keys and the
 //      head of the next one's) and every segment leaves a partial (O, m, l) in slot 2*cta + segment.  With 32 query
 //      tiles x 4 fixed KV splits only 128 of the 148 SMs had work.  Barrier phases simply keep counting across segments.
-template <int CL, bool BAL>
+// DV : value dimension (256: V^T K-major [256][Nk]; 64: see the file header)
+// VMN: DV == 64 only -- V is given as rows [Nk][64] and consumed as an MN-major B operand (no transposed copy at all)
+template <int CL, bool BAL, int DV, bool VMN>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -83,8 +97,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sQ = smem;
   uint8_t* sK = smem + Q_BYTES;
-  uint8_t* sV = sK + KV_STAGES * K_BYTES;
-  float* xchg = reinterpret_cast<float*>(sV + KV_STAGES * V_BYTES);
+  using C_ = ACfg<DV>;
+  constexpr int KST = C_::KST;
+  constexpr int V_BYTES = C_::V_BYTES;
+  constexpr uint32_t TM_S = C_::TM_S;
+  constexpr int OC = C_::OC;
+  static_assert(DV == 256 || DV == 64, "value dimension must be 256 or 64");
+  static_assert(!VMN || DV == 64, "row-major V needs DV == 64 (one 128-byte swizzle atom per key row)");
+  uint8_t* sV = sK + KST * K_BYTES;
+  float* xchg = reinterpret_cast<float*>(sV + V_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(xchg) + XCHG_BYTES);
   uint64_t* q_full = bars;
   uint64_t* k_full = bars + 1;
@@ -135,12 +156,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   }
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < KV_STAGES; ++s) {
+    for (int s = 0; s < KST; ++s) {
       mbar_init(&k_full[s], 1);
       mbar_init(&k_empty[s], CL);  // released by the MMA commits of every CTA of the cluster
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], CL);
     }
+    mbar_init(&v_full[0], 1);
+    mbar_init(&v_empty[0], CL);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_ready[s], SOFTMAX_THREADS);
@@ -175,8 +196,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int kp = 0; kp < 4; ++kp) tma_load_3d(sQ + kp * (BM * 128), &tmQ, q_full, kp * 64, S.q0, S.bz);
         for (int j = 0; j < S.n; ++j, ++jg) {
-          const int st = jg % KV_STAGES;
-          const uint32_t ph = (jg / KV_STAGES) & 1;
+          const int st = jg % KST;
+          const uint32_t ph = (jg / KST) & 1;
           const int kv0 = (S.t0 + j) * BN;
           mbar_wait(&k_empty[st], ph ^ 1);
           VLS_TRACE(0, jg, 0);
@@ -203,20 +224,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       for (int sg = 0; sg < nseg; ++sg) {
         const Seg S = segs[sg];
         for (int j = 0; j < S.n; ++j, ++jg) {
-          const int st = jg % KV_STAGES;
-          const uint32_t ph = (jg / KV_STAGES) & 1;
+          const uint32_t ph = jg & 1;   // one V stage
           const int kv0 = (S.t0 + j) * BN;
-          mbar_wait(&v_empty[st], ph ^ 1);
+          mbar_wait(&v_empty[0], ph ^ 1);
           VLS_TRACE(0, jg, 1);
-          mbar_expect_tx(&v_full[st], V_BYTES);
-          // V^T tile = two 64-key panels of [256 channels x 128 B]
+          mbar_expect_tx(&v_full[0], V_BYTES);
+          if (VMN) {
+            // V tile as stored: 128 key rows of 64 channels (128 B each), one box
+            tma_load_3d(sV, &tmV, &v_full[0], 0, kv0, S.bz);
+          } else {
+            // V^T tile = two 64-key panels of [DV channels x 128 B]
 #pragma unroll
-          for (int vp = 0; vp < 2; ++vp) {
-            if (CL > 1)  // this CTA fetches channel rows [rank*128, rank*128+128) of each panel for both CTAs
-              tma_load_3d_mc(sV + st * V_BYTES + vp * (D * 128) + rank * (128 * 128), &tmV, &v_full[st], kv0 + vp * 64,
-                             (int)rank * 128, S.bz, PAIR_MASK);
-            else
-              tma_load_3d(sV + st * V_BYTES + vp * (D * 128), &tmV, &v_full[st], kv0 + vp * 64, 0, S.bz);
+            for (int vp = 0; vp < 2; ++vp) {
+              if (CL > 1)  // this CTA fetches channel rows [rank*DV/2, (rank+1)*DV/2) of each panel for both CTAs
+                tma_load_3d_mc(sV + vp * (DV * 128) + rank * (DV / 2 * 128), &tmV, &v_full[0], kv0 + vp * 64,
+                               (int)rank * (DV / 2), S.bz, PAIR_MASK);
+              else
+                tma_load_3d(sV + vp * (DV * 128), &tmV, &v_full[0], kv0 + vp * 64, 0, S.bz);
+            }
           }
         }
       }
@@ -224,7 +249,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
-      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, D);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(BM, DV) | (VMN ? (1u << 16) : 0u);   // bit 16: B is MN-major
       const uint32_t q_addr = smem_u32(sQ);
       int jg0 = 0;   // global index of the segment's first tile
       for (int sg = 0; sg < nseg; ++sg) {
@@ -233,8 +258,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(q_full, sg & 1);
         auto issue_s = [&](int j) {   // j: tile inside the segment; jg: global tile count (stage / phase bookkeeping)
           const int jg = jg0 + j;
-          const int st = jg % KV_STAGES;
-          mbar_wait(&k_full[st], (jg / KV_STAGES) & 1);
+          const int st = jg % KST;
+          mbar_wait(&k_full[st], (jg / KST) & 1);
           VLS_TRACE(1, jg, 0);
           tc_fence_after();
           const uint32_t k_addr = smem_u32(sK + st * K_BYTES);
@@ -255,21 +280,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         for (int j = 0; j < n; ++j) {
           if (j + 1 < n) issue_s(j + 1);
           const int jg = jg0 + j;
-          const int st = jg % KV_STAGES;
           mbar_wait(&p_ready[jg & 1], (jg >> 1) & 1);
           VLS_TRACE(1, jg, 2);
-          mbar_wait(&v_full[st], (jg / KV_STAGES) & 1);
+          mbar_wait(&v_full[0], jg & 1);
           VLS_TRACE(1, jg, 3);
           if (BAL && sg > 0 && j == 0) mbar_wait(o_free, (sg - 1) & 1);   // the previous segment's O has been read out
           tc_fence_after();
-          const uint32_t v_addr = smem_u32(sV + st * V_BYTES);
+          const uint32_t v_addr = smem_u32(sV);
           const uint32_t a_p = tmem + TM_S + uint32_t(jg & 1) * BN;
 #pragma unroll
           for (int ks = 0; ks < BN / 16; ++ks) {
-            const uint64_t vd = make_desc_sw128(v_addr + (ks >> 2) * (D * 128));
-            umma_ts(tmem + TM_O, a_p + ks * 8, vd + 2 * (ks & 3), idesc_pv, (j | ks) != 0 ? 1u : 0u);
+            // K-major V^T: 16 keys = 32 B inside the 128-byte rows of a 64-key panel; MN-major V rows: 16 keys = two
+            // 8-row groups of 1024 B (SBO), the 64 channels of a key are one 128-byte swizzle atom
+            const uint64_t vd = VMN ? make_desc_sw128(v_addr + ks * 2048)
+                                    : make_desc_sw128(v_addr + (ks >> 2) * (DV * 128)) + 2 * (ks & 3);
+            umma_ts(tmem + TM_O, a_p + ks * 8, vd, idesc_pv, (j | ks) != 0 ? 1u : 0u);
           }
-          if (CL > 1) umma_commit_mc(&v_empty[st], PAIR_MASK); else umma_commit(&v_empty[st]);
+          if (CL > 1) umma_commit_mc(&v_empty[0], PAIR_MASK); else umma_commit(&v_empty[0]);
           umma_commit(pv_done);
           VLS_TRACE(1, jg, 4);
         }
@@ -329,13 +356,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           mbar_wait(pv_done, (j - 1) & 1);
           tc_fence_after();
 #pragma unroll 1
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < OC / 32; ++c) {
             uint32_t o[32];
-            tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
+            tmem_ld32(tmem + lane_off + TM_O + half * OC + c * 32, o);
             tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-            tmem_st32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
+            tmem_st32(tmem + lane_off + TM_O + half * OC + c * 32, o);
           }
           tc_wait_st();
         }
@@ -373,11 +400,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const bool row_ok = row < p.Nq;
     if (!BAL && p.splits == 1) {
       const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-      bf16* out = p.O + (long long)bz * p.o_bstride + (long long)row * p.ldo + half * 128;
+      bf16* out = p.O + (long long)bz * p.o_bstride + (long long)row * p.ldo + half * OC;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < OC / 32; ++c) {
         uint32_t o[32];
-        tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
+        tmem_ld32(tmem + lane_off + TM_O + half * OC + c * 32, o);
         tc_wait_ld();
         if (row_ok) {
           uint4* o4 = reinterpret_cast<uint4*>(out + c * 32);
@@ -392,11 +419,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     } else {
       // partial row: balanced mode -> [slot][row in tile]; fixed splits -> [batch][split][query row]
       const long long prow = BAL ? (long long)S.slot * BM + rl : ((long long)bz * p.splits + blockIdx.y) * p.Nq + row;
-      float* po = p.part_o + prow * D + half * 128;
+      float* po = p.part_o + prow * DV + half * OC;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < OC / 32; ++c) {
         uint32_t o[32];
-        tmem_ld32(tmem + lane_off + TM_O + half * 128 + c * 32, o);
+        tmem_ld32(tmem + lane_off + TM_O + half * OC + c * 32, o);
         tc_wait_ld();
         if (row_ok) {
           float4* o4 = reinterpret_cast<float4*>(po + c * 32);
@@ -424,45 +451,60 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 1) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// Merge partials: one warp per query row, lane owns 8 channels.  The partial rows of a query row (at most 8) are
-// addressed first, then ALL their (m, l) pairs and ALL their O vectors are loaded before any arithmetic: two L2 round
-// trips per row instead of two per partial (the loops over partials used to be latency chains: 9.8 us for 6 partials).
+// Merge partials: one warp per query row, lane owns DV/32 channels (8 or 2).  The partial rows of a query row (at most
+// 8) are addressed first, then ALL their (m, l) pairs and ALL their O vectors are loaded before any arithmetic: two L2
+// round trips per row instead of two per partial (the loops over partials used to be latency chains: 9.8 us for 6).
 constexpr int MAX_PARTS = 8;
+template <int DV>
 __device__ __forceinline__ void combine_row(const float* __restrict__ part_o, const float* __restrict__ part_ml,
                                             const long long (&prow)[MAX_PARTS], int cnt, int lane, bf16* __restrict__ dst) {
+  constexpr int CPL = DV / 32;   // channels per lane
   float2 ml[MAX_PARTS];
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k)
     ml[k] = k < cnt ? *reinterpret_cast<const float2*>(part_ml + prow[k] * 2) : make_float2(-INFINITY, 0.f);
-  float4 pa[MAX_PARTS], pd[MAX_PARTS];
+  float pv[MAX_PARTS][CPL];
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k) {
     if (k < cnt) {
-      const float4* src = reinterpret_cast<const float4*>(part_o + prow[k] * D + lane * 8);
-      pa[k] = src[0];
-      pd[k] = src[1];
+      const float* src = part_o + prow[k] * DV + lane * CPL;
+      if constexpr (CPL == 8) {
+        const float4 a = reinterpret_cast<const float4*>(src)[0], d = reinterpret_cast<const float4*>(src)[1];
+        pv[k][0] = a.x; pv[k][1] = a.y; pv[k][2] = a.z; pv[k][3] = a.w;
+        pv[k][4] = d.x; pv[k][5] = d.y; pv[k][6] = d.z; pv[k][7] = d.w;
+      } else {
+        const float2 a = *reinterpret_cast<const float2*>(src);
+        pv[k][0] = a.x; pv[k][1] = a.y;
+      }
     }
   }
   float m = -INFINITY;
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k) m = fmaxf(m, ml[k].x);
-  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  float acc[CPL];
+#pragma unroll
+  for (int i = 0; i < CPL; ++i) acc[i] = 0.f;
   float l = 0.0f;
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k) {
     if (k < cnt) {
       const float w = exp2f(ml[k].x - m);
       l += w * ml[k].y;
-      acc[0] += w * pa[k].x; acc[1] += w * pa[k].y; acc[2] += w * pa[k].z; acc[3] += w * pa[k].w;
-      acc[4] += w * pd[k].x; acc[5] += w * pd[k].y; acc[6] += w * pd[k].z; acc[7] += w * pd[k].w;
+#pragma unroll
+      for (int i = 0; i < CPL; ++i) acc[i] += w * pv[k][i];
     }
   }
   const float inv = l > 0.0f ? 1.0f / l : 0.0f;
-  *reinterpret_cast<uint4*>(dst) =
-      make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
-                 pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  if constexpr (CPL == 8) {
+    *reinterpret_cast<uint4*>(dst) =
+        make_uint4(pack_bf16x2(acc[0] * inv, acc[1] * inv), pack_bf16x2(acc[2] * inv, acc[3] * inv),
+                   pack_bf16x2(acc[4] * inv, acc[5] * inv), pack_bf16x2(acc[6] * inv, acc[7] * inv));
+  } else {
+    *reinterpret_cast<uint32_t*>(dst) = pack_bf16x2(acc[0] * inv, acc[1] * inv);
+  }
 }
 
+template <int DV>
 __global__ void attn_combine_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
                                     int splits, bf16* __restrict__ O, long long ldo, long long o_bstride) {
   pdl_enter();
@@ -474,7 +516,8 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
   long long prow[MAX_PARTS];
 #pragma unroll
   for (int k = 0; k < MAX_PARTS; ++k) prow[k] = ((long long)b * splits + (k < splits ? k : 0)) * Nq + row;
-  combine_row(part_o, part_ml, prow, splits, lane, O + (long long)b * o_bstride + (long long)row * ldo + lane * 8);
+  combine_row<DV>(part_o, part_ml, prow, splits, lane,
+                  O + (long long)b * o_bstride + (long long)row * ldo + lane * (DV / 32));
 }
 
 // Balanced mode: query tile qt received one partial from every CTA whose unit range overlaps [qt*ntiles, (qt+1)*ntiles);
@@ -484,6 +527,7 @@ __global__ void attn_combine_kernel(const float* __restrict__ part_o, const floa
 struct BalTable {
   uint32_t e[3 * 148];
 };
+template <int DV>
 __global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const float* __restrict__ part_ml, int B, int Nq,
                                         int qtiles, const BalTable tab, bf16* __restrict__ O, long long ldo,
                                         long long o_bstride) {
@@ -502,7 +546,8 @@ __global__ void attn_combine_bal_kernel(const float* __restrict__ part_o, const 
     const int kk = k < cnt ? k : 0;
     prow[k] = (long long)(MAX_SEGS * (c_first + kk) + ((e >> (16 + 2 * kk)) & 3)) * BM + rl;
   }
-  combine_row(part_o, part_ml, prow, cnt, lane, O + (long long)b * o_bstride + (long long)row * ldo + lane * 8);
+  combine_row<DV>(part_o, part_ml, prow, cnt, lane,
+                  O + (long long)b * o_bstride + (long long)row * ldo + lane * (DV / 32));
 }
 
 constexpr int BAL_CTAS = 148;   // one persistent CTA per SM of a B200
@@ -511,6 +556,7 @@ constexpr int BAL_CTAS = 148;   // one persistent CTA per SM of a B200
 
 long long* g_attn_trace = nullptr;  // dev-only timeline buffer (3*64*8 int64), see tools/trace_attention.py
 int g_attn_balanced = 1;  // 1: balanced mode may be picked by attn_pick_splits (vls_set_tuning "attn_balanced")
+int g_attn_v_rows = 1;   // memory cross-attention: 1 = V read as bank rows (MN-major operand), 0 = transposed copy (K-major)
 int g_attn_cluster = 1;  // 1: private K/V loads; 2: pairs of query tiles multicast K/V (vls_set_tuning "attn_cluster")
 
 // balanced mode is possible when every CTA gets at least one unit, at most MAX_SEGS segments, a query tile at most
@@ -524,16 +570,16 @@ static bool bal_ok(int qt, int ntiles) {
   return true;
 }
 
-// splits == 0 selects the balanced ("stream-K") mode: 2 partial slots per persistent CTA
-size_t attn_workspace_bytes(int B, int Nq, int splits) {
-  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * D * 4) + align256((size_t)BAL_CTAS * MAX_SEGS * BM * 2 * 4);
+// splits == 0 selects the balanced ("stream-K") mode: MAX_SEGS partial slots per persistent CTA
+size_t attn_workspace_bytes(int B, int Nq, int splits, int dv) {
+  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * dv * 4) + align256((size_t)BAL_CTAS * MAX_SEGS * BM * 2 * 4);
   if (splits <= 1) return 0;
-  return align256((size_t)B * splits * Nq * D * 4) + align256((size_t)B * splits * Nq * 2 * 4);
+  return align256((size_t)B * splits * Nq * dv * 4) + align256((size_t)B * splits * Nq * 2 * 4);
 }
 
-size_t attn_part_ml_offset(int B, int Nq, int splits) {   // byte offset of the (m, l) partials inside the workspace
-  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * D * 4);
-  return align256((size_t)B * splits * Nq * D * 4);
+size_t attn_part_ml_offset(int B, int Nq, int splits, int dv) {   // byte offset of the (m, l) partials inside the workspace
+  if (splits == 0) return align256((size_t)BAL_CTAS * MAX_SEGS * BM * dv * 4);
+  return align256((size_t)B * splits * Nq * dv * 4);
 }
 
 int attn_pick_splits(int B, int Nq, int Nk) {
@@ -555,56 +601,48 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   return s;
 }
 
-int launch_attention(const AttnArgs& a, cudaStream_t stream) {
-  VLS_REQUIRE(a.Q && a.K && a.Vt && a.O, "attention: null operand");
-  VLS_REQUIRE(a.Nq > 0 && a.Nk > 0 && a.B > 0 && a.splits >= 0, "attention: bad shape");
-  VLS_REQUIRE(a.ldo % 8 == 0, "attention: ldo must be a multiple of 8");
-  const int nt = (a.Nk + BN - 1) / BN;
-  VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
-  VLS_REQUIRE(a.splits <= MAX_PARTS, "attention: at most %d KV splits", MAX_PARTS);
-  VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
-  const int qtiles = (a.Nq + BM - 1) / BM;
-  const bool bal = a.splits == 0;
-  VLS_REQUIRE(!bal || bal_ok(qtiles * a.B, nt), "attention: shape not supported by the balanced mode");
-  const int cl = (!bal && qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
+namespace {
+
+template <int CL, bool BAL, int DV, bool VMN>
+int launch_variant(const AttnArgs& a, const AttnParams& p, int qtiles, cudaStream_t stream) {
+  using C_ = ACfg<DV>;
   CUtensorMap tmQ, tmK, tmV;
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
-  VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, cl > 1 ? BN / 2 : BN));
-  VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, D, a.B, a.ldvt, a.vt_bstride, cl > 1 ? D / 2 : D));
-  AttnParams p;
-  p.Nq = a.Nq; p.Nk = a.Nk; p.splits = a.splits;
-  p.qtiles = qtiles; p.ntiles = nt; p.units = (long long)a.B * qtiles * nt;
-  p.scale_log2 = a.scale * 1.4426950408889634f;
-  p.O = reinterpret_cast<bf16*>(a.O); p.ldo = a.ldo; p.o_bstride = a.o_bstride;
-  p.part_o = a.part_o; p.part_ml = a.part_ml;
-  p.trace = g_attn_trace;
-  static unsigned long long attr_set = 0;
+  VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, CL > 1 ? BN / 2 : BN));
+  if (VMN) {
+    VLS_TRY(make_tmap_bf16(&tmV, a.Vt, DV, a.Nk, a.B, a.ldvt, a.vt_bstride, BN));                     // rows [Nk][64]
+  } else {
+    VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, DV, a.B, a.ldvt, a.vt_bstride, CL > 1 ? DV / 2 : DV));   // V^T [DV][Nk]
+  }
+  static unsigned long long attr_set = 0;   // one flag word per instantiation
   if (first_use_on_device(&attr_set)) {
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    VLS_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    auto kern = attn_fwd_kernel<CL, BAL, DV, VMN>;
+    VLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::SMEM));
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = bal ? dim3(BAL_CTAS, 1, 1) : dim3(qtiles, a.splits, a.B);
+  cfg.gridDim = BAL ? dim3(BAL_CTAS, 1, 1) : dim3(qtiles, a.splits, a.B);
   cfg.blockDim = dim3(THREADS);
-  cfg.dynamicSmemBytes = SMEM_BYTES;
+  cfg.dynamicSmemBytes = C_::SMEM;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
-  prof_begin(slot, stream);
-  if (bal) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1, true>, tmQ, tmK, tmV, p));
-  else if (cl > 1) VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<2, false>, tmQ, tmK, tmV, p));
-  else VLS_CUDA(cudaLaunchKernelEx(&cfg, attn_fwd_kernel<1, false>, tmQ, tmK, tmV, p));
-  prof_end(slot, stream);
+  auto kern = attn_fwd_kernel<CL, BAL, DV, VMN>;
+  VLS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, p));
   VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+template <int DV>
+int launch_combine(const AttnArgs& a, int qtiles, int nt, bool bal, cudaStream_t stream) {
+  const long long rows = (long long)a.B * a.Nq;
+  const int wpb = 8;
+  VLS_REQUIRE(rows < (1ll << 31), "attention: too many query rows");
+  const dim3 grid((unsigned)((rows + wpb - 1) / wpb));
   if (bal) {
-    const long long rows = (long long)a.B * a.Nq;
-    const int wpb = 8;
     BalTable tab;
     const long long U = (long long)a.B * qtiles * nt;
     for (int qt = 0; qt < a.B * qtiles; ++qt) {
@@ -619,16 +657,56 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
       }
       tab.e[qt] = e;
     }
-    VLS_REQUIRE(rows < (1ll << 31), "attention: too many query rows");
-    VLS_CUDA(launch_k(attn_combine_bal_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream, a.part_o,
-                      a.part_ml, a.B, a.Nq, qtiles, tab, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
-    VLS_POST_LAUNCH(1);
-  } else if (a.splits > 1) {
-    const long long rows = (long long)a.B * a.Nq;
-    const int wpb = 8;
-    VLS_CUDA(launch_k(attn_combine_kernel, dim3((unsigned)((rows + wpb - 1) / wpb)), dim3(wpb * 32), 0, stream,  a.part_o, a.part_ml, a.B, a.Nq, a.splits, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
-    VLS_POST_LAUNCH(1);
+    VLS_CUDA(launch_k(attn_combine_bal_kernel<DV>, grid, dim3(wpb * 32), 0, stream, a.part_o, a.part_ml, a.B, a.Nq, qtiles,
+                      tab, reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
+  } else {
+    VLS_CUDA(launch_k(attn_combine_kernel<DV>, grid, dim3(wpb * 32), 0, stream, a.part_o, a.part_ml, a.B, a.Nq, a.splits,
+                      reinterpret_cast<bf16*>(a.O), a.ldo, a.o_bstride));
   }
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+}  // namespace
+
+int launch_attention(const AttnArgs& a, cudaStream_t stream) {
+  VLS_REQUIRE(a.Q && a.K && a.Vt && a.O, "attention: null operand");
+  VLS_REQUIRE(a.Nq > 0 && a.Nk > 0 && a.B > 0 && a.splits >= 0, "attention: bad shape");
+  VLS_REQUIRE(a.dv == 256 || a.dv == 64, "attention: value dimension must be 256 or 64 (got %d)", a.dv);
+  VLS_REQUIRE(!a.v_rows || a.dv == 64, "attention: row-major V needs dv == 64");
+  VLS_REQUIRE(a.ldo % 8 == 0 && a.ldvt % 8 == 0, "attention: ldo / ldv must be multiples of 8");
+  const int nt = (a.Nk + BN - 1) / BN;
+  VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
+  VLS_REQUIRE(a.splits <= MAX_PARTS, "attention: at most %d KV splits", MAX_PARTS);
+  VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
+  const int qtiles = (a.Nq + BM - 1) / BM;
+  const bool bal = a.splits == 0;
+  VLS_REQUIRE(!bal || bal_ok(qtiles * a.B, nt), "attention: shape not supported by the balanced mode");
+  const int cl = (!bal && a.dv == 256 && qtiles % 2 == 0 && g_attn_cluster > 1) ? 2 : 1;
+  AttnParams p;
+  p.Nq = a.Nq; p.Nk = a.Nk; p.splits = a.splits;
+  p.qtiles = qtiles; p.ntiles = nt; p.units = (long long)a.B * qtiles * nt;
+  p.scale_log2 = a.scale * 1.4426950408889634f;
+  p.O = reinterpret_cast<bf16*>(a.O); p.ldo = a.ldo; p.o_bstride = a.o_bstride;
+  p.part_o = a.part_o; p.part_ml = a.part_ml;
+  p.trace = g_attn_trace;
+  // the profiling bracket covers the attention kernel AND its combine launch (r1 verdict: the combine was outside)
+  const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
+  prof_begin(slot, stream);
+  int rc;
+  if (a.dv == 64 && a.v_rows)
+    rc = bal ? launch_variant<1, true, 64, true>(a, p, qtiles, stream) : launch_variant<1, false, 64, true>(a, p, qtiles, stream);
+  else if (a.dv == 64)
+    rc = bal ? launch_variant<1, true, 64, false>(a, p, qtiles, stream) : launch_variant<1, false, 64, false>(a, p, qtiles, stream);
+  else if (bal) rc = launch_variant<1, true, 256, false>(a, p, qtiles, stream);
+  else if (cl > 1) rc = launch_variant<2, false, 256, false>(a, p, qtiles, stream);
+  else rc = launch_variant<1, false, 256, false>(a, p, qtiles, stream);
+  if (rc != 0) return rc;
+  if (bal || a.splits > 1) {
+    rc = a.dv == 64 ? launch_combine<64>(a, qtiles, nt, bal, stream) : launch_combine<256>(a, qtiles, nt, bal, stream);
+    if (rc != 0) return rc;
+  }
+  prof_end(slot, stream);
   return 0;
 }
 

@@ -35,25 +35,28 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- tcgen05 flash attention (attn_tc.cu)
-// O[b][q][:] = softmax(Q[b][q][:] . K[b][k][:] * scale) @ V  with head dim 256, one head.
-// Q: bf16 [B][Nq][ldq], K: bf16 [B][Nk][ldk], Vt: bf16 [B][256][ldvt] (V transposed: row = channel).
+// O[b][q][:] = softmax(Q[b][q][:] . K[b][k][:] * scale) @ V  with q/k head dim 256, one head, value dim dv (256 or 64).
+// Q: bf16 [B][Nq][ldq], K: bf16 [B][Nk][ldk], Vt: bf16 [B][dv][ldvt] (V transposed: row = channel), or -- v_rows, dv == 64
+// only -- V as rows bf16 [B][Nk][ldvt] exactly as the memory bank stores them.  O: bf16 [B][Nq][ldo] with dv columns.
 struct AttnArgs {
   const void* Q = nullptr; long long ldq = 0, q_bstride = 0;
   const void* K = nullptr; long long ldk = 0, k_bstride = 0;
   const void* Vt = nullptr; long long ldvt = 0, vt_bstride = 0;
+  int dv = 256, v_rows = 0;
   int B = 1, Nq = 0, Nk = 0;
   float scale = 0.0625f;
   int splits = 1;            // KV splits per query tile (>=1); 0 = balanced ("stream-K") mode
   void* O = nullptr;         // bf16 [B][Nq][ldo]
   long long ldo = 0, o_bstride = 0;
-  float* part_o = nullptr;   // workspace when splits > 1: f32 [B][splits][Nq][256]
+  float* part_o = nullptr;   // workspace when splits > 1: f32 [B][splits][Nq][dv]
   float* part_ml = nullptr;  // f32 [B][splits][Nq][2] (running max in log2 domain, sum)
 };
 extern int g_attn_cluster;
 extern int g_attn_balanced;
+extern int g_attn_v_rows;
 extern long long* g_attn_trace;
-size_t attn_workspace_bytes(int B, int Nq, int splits);
-size_t attn_part_ml_offset(int B, int Nq, int splits);
+size_t attn_workspace_bytes(int B, int Nq, int splits, int dv = 256);
+size_t attn_part_ml_offset(int B, int Nq, int splits, int dv = 256);
 int attn_pick_splits(int B, int Nq, int Nk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
@@ -99,6 +102,7 @@ int launch_rows_gate_cast(const float* in, int B, int T, int C, const float* gat
                           cudaStream_t stream);
 int launch_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int k, const void* new_rows, const float* new_ptr,
                       cudaStream_t stream);
+int launch_transpose_rows64(const void* in, int B, int T, void* out, long long ld, cudaStream_t stream);
 int launch_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, cudaStream_t stream);
 int launch_gather_rows(const float* src, long long sg, long long sr, int G, int R, int n, float* dst, cudaStream_t stream);
 

@@ -42,12 +42,12 @@ static size_t mem_attn_ws(int B, int Nq, int Nk, int L) {
   n += align256((size_t)B * Nq * 2 * C * 2);        // qk
   n += 2 * align256((size_t)B * Nk * CM * 2);       // mem, mempos
   n += align256((size_t)L * B * Nk * C * 2);        // rotated cross-attention keys of every layer
-  n += align256((size_t)L * B * C * ldv * 2);       // transposed cross-attention values of every layer
+  n += align256((size_t)B * CM * ldv * 2);          // transposed memory (only used with attn_v_rows = 0)
   n += align256((size_t)B * C * ldvs * 2);          // transposed self-attention values
   n += align256((size_t)B * Nq * C * 2);            // ao
   n += align256((size_t)B * Nq * FFN * 2);          // h
   const int s1 = attn_pick_splits(B, Nq, Nq), s2 = attn_pick_splits(B, Nq, Nk);
-  const size_t a1 = attn_workspace_bytes(B, Nq, s1), a2 = attn_workspace_bytes(B, Nq, s2);
+  const size_t a1 = attn_workspace_bytes(B, Nq, s1, C), a2 = attn_workspace_bytes(B, Nq, s2, CM);
   n += align256(a1 > a2 ? a1 : a2);
   return n + 4096;
 }
@@ -70,7 +70,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
               Nk - num_obj_ptr_tokens, Nq);  // rope_k_repeat (sam/transformer.py:329-338)
   const int L = w->num_layers;
   VLS_REQUIRE(workspace && workspace_bytes >= mem_attn_ws(B, Nq, Nk, L), "mem_attn: workspace too small");
-  VLS_REQUIRE(w->ca_k_w_all && w->ca_k_b_all && w->ca_v_w_all && w->ca_v_b_all, "mem_attn: stacked K/V weights missing");
+  VLS_REQUIRE(w->ca_k_w_all && w->ca_k_b_all, "mem_attn: stacked K weights missing");
   Workspace ws(workspace, workspace_bytes);
   const long long ldv = rup(Nk, 64), ldvs = rup(Nq, 64);
   float* x = (float*)ws.take((size_t)B * Nq * C * 4);
@@ -79,14 +79,14 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   void* mem = ws.take((size_t)B * Nk * CM * 2);
   void* mempos = ws.take((size_t)B * Nk * CM * 2);
   char* kc_all = (char*)ws.take((size_t)L * B * Nk * C * 2);
-  char* vt_all = (char*)ws.take((size_t)L * B * C * ldv * 2);
+  void* memT = ws.take((size_t)B * CM * ldv * 2);
   void* vts = ws.take((size_t)B * C * ldvs * 2);
   void* ao = ws.take((size_t)B * Nq * C * 2);
   void* h = ws.take((size_t)B * Nq * FFN * 2);
   const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits(B, Nq, Nk);
-  const size_t a1 = attn_workspace_bytes(B, Nq, s_self), a2 = attn_workspace_bytes(B, Nq, s_cross);
+  const size_t a1 = attn_workspace_bytes(B, Nq, s_self, C), a2 = attn_workspace_bytes(B, Nq, s_cross, CM);
   char* aws = (char*)ws.take(a1 > a2 ? a1 : a2);
-  VLS_REQUIRE(x && t && qk && mem && mempos && kc_all && vt_all && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
+  VLS_REQUIRE(x && t && qk && mem && mempos && kc_all && memT && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
               "mem_attn: workspace carve failed");
 
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
@@ -96,10 +96,13 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
                            memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, st));
 
-  // memory K / V^T projections of ALL layers in two launches (they do not depend on x): batch index z = l*B + b.
-  //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated);   V_l^T = Wv_l mem^T + bv_l
-  // They run on a forked side stream (event fork/join, capturable into CUDA graphs) so that they overlap layer 0's
-  // LayerNorm -> q/k/v projection -> self-attention -> out-projection chain, whose kernels fill < 1 wave of SMs.
+  // memory K projections of ALL layers in one launch (they do not depend on x): batch index z = l*B + b.
+  //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated)
+  // There is NO value projection: softmax rows sum to one, so softmax(QK^T)(mem Wv^T + bv) = (softmax(QK^T) mem) Wv^T
+  // + bv -- the cross-attention kernel attends over the raw 64-d memory rows and Wo.Wv / Wo.bv + bo are folded into the
+  // output projection at packing time (memory_attention.py:66-81, sam/transformer.py:311-360).
+  // The K launch runs on a forked side stream (event fork/join, capturable into CUDA graphs) so that it overlaps layer
+  // 0's LayerNorm -> q/k/v projection -> self-attention -> out-projection chain, whose kernels fill < 1 wave of SMs.
   cudaStream_t side;
   VLS_TRY(fork_begin(0, st, &side));
   {
@@ -111,27 +114,22 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
     k.C = kc_all; k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
     VLS_TRY(launch_gemm(k, side));
-    GemmArgs v;
-    v.A = w->ca_v_w_all; v.lda = CM; v.a_bstride = (long long)C * CM; v.a_batches = L; v.a_div = B;
-    v.W = mem; v.ldw = CM; v.w_bstride = (long long)Nk * CM; v.w_batches = B; v.w_div = 1;
-    v.M = C; v.N = Nk; v.K = CM; v.batch = L * B;
-    v.bias = w->ca_v_b_all; v.bias_mode = 2; v.bias_bstride = C; v.bias_batches = L; v.bias_div = B;
-    v.C = vt_all; v.c_bf16 = 1; v.ldc = ldv; v.c_bstride = (long long)C * ldv;
-    VLS_TRY(launch_gemm(v, side));
+    if (!g_attn_v_rows) VLS_TRY(launch_transpose_rows64(mem, B, Nk, memT, ldv, side));
   }
   bool joined = false;
 
-  auto attention = [&](const void* K, long long ldk, long long k_bs, const void* Vt, long long ldvt, int nk,
-                       int splits) -> int {
+  // dv = 256: V^T [256][ldvt]; dv = 64: the memory itself, as rows [Nk][64] (v_rows) or transposed [64][ldvt]
+  auto attention = [&](const void* K, long long ldk, long long k_bs, const void* V, long long ldvt, long long v_bs, int dv,
+                       int v_rows, int nk, int splits) -> int {
     AttnArgs a;
     a.Q = qk; a.ldq = 2 * C; a.q_bstride = (long long)Nq * 2 * C;
     a.K = K; a.ldk = ldk; a.k_bstride = k_bs;
-    a.Vt = Vt; a.ldvt = ldvt; a.vt_bstride = (long long)C * ldvt;
+    a.Vt = V; a.ldvt = ldvt; a.vt_bstride = v_bs; a.dv = dv; a.v_rows = v_rows;
     a.B = B; a.Nq = Nq; a.Nk = nk; a.scale = 0.0625f; a.splits = splits;
-    a.O = ao; a.ldo = C; a.o_bstride = (long long)Nq * C;
+    a.O = ao; a.ldo = dv; a.o_bstride = (long long)Nq * dv;
     if (splits != 1) {   // fixed KV splits, or 0 = balanced mode
       a.part_o = (float*)aws;
-      a.part_ml = (float*)(aws + attn_part_ml_offset(B, Nq, splits));
+      a.part_ml = (float*)(aws + attn_part_ml_offset(B, Nq, splits, dv));
     }
     return launch_attention(a, st);
   };
@@ -155,7 +153,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g, st));
       VLS_TRY(fork_join(2, st));
     }
-    VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, Nq, s_self));
+    VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, (long long)C * ldvs, C, 0, Nq, s_self));
     {
       GemmArgs g = lin(ao, C, (long long)Nq * C, Lw.sa_o_w, Nq, C, C, B, Lw.sa_o_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
@@ -172,10 +170,12 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(fork_join(0, st));
       joined = true;
     }
-    VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, vt_all + (size_t)l * B * C * ldv * 2, ldv, Nk,
-                      s_cross));
-    {
-      GemmArgs g = lin(ao, C, (long long)Nq * C, Lw.ca_o_w, Nq, C, C, B, Lw.ca_o_b, x, 0, C, (long long)Nq * C);
+    if (g_attn_v_rows)
+      VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, mem, CM, (long long)Nk * CM, CM, 1, Nk, s_cross));
+    else
+      VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, memT, ldv, (long long)CM * ldv, CM, 0, Nk, s_cross));
+    {   // x += (P mem) (Wo Wv)^T + (Wo bv + bo): the folded value/output projection, K = 64
+      GemmArgs g = lin(ao, CM, (long long)Nq * CM, Lw.ca_ov_w, Nq, C, CM, B, Lw.ca_ov_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
       VLS_TRY(launch_gemm(g, st));
     }

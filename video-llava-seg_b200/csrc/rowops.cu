@@ -326,6 +326,33 @@ __global__ void multi_copy_kernel(const MultiCopy m, int n) {
 
 }  // namespace
 
+// rows [B][T][64] bf16 -> transposed [B][64][ld] bf16 (ld >= T): the K-major V^T operand of the attention kernel when the
+// row-major (MN-major) value path is switched off (vls_set_tuning "attn_v_rows" 0).  64 x 64 tiles through shared memory.
+__global__ void transpose_rows64_kernel(const bf16* __restrict__ in, int T, bf16* __restrict__ out, long long ld) {
+  pdl_enter();
+  __shared__ bf16 tile[64][66];
+  const int b = blockIdx.y, t0 = blockIdx.x * 64;
+  const bf16* src = in + ((long long)b * T + t0) * 64;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int r = i >> 6, c = i & 63;
+    tile[r][c] = (t0 + r < T) ? src[(long long)r * 64 + c] : __float2bfloat16(0.f);
+  }
+  __syncthreads();
+  bf16* dst = out + (long long)b * 64 * ld + t0;
+  for (int i = threadIdx.x; i < 64 * 64; i += blockDim.x) {
+    const int c = i >> 6, r = i & 63;
+    if (t0 + r < ld) dst[(long long)c * ld + r] = tile[r][c];
+  }
+}
+
+int launch_transpose_rows64(const void* in, int B, int T, void* out, long long ld, cudaStream_t stream) {
+  VLS_REQUIRE(in && out && B > 0 && T > 0 && ld >= T, "transpose_rows64: bad arguments");
+  VLS_CUDA(launch_k(transpose_rows64_kernel, dim3((unsigned)((ld + 63) / 64), B), dim3(256), 0, stream,
+                    reinterpret_cast<const bf16*>(in), T, reinterpret_cast<bf16*>(out), ld));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
 int launch_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int k, const void* new_rows, const float* new_ptr,
                       cudaStream_t stream) {
   VLS_REQUIRE(bank && new_rows && new_ptr, "bank_shift: null argument");

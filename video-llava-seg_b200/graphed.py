@@ -62,6 +62,14 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     return pred, obj_ptr, obj_logits, nchw, rows, video
 
 
+def baked_settings(m):
+    """Scalar attributes a captured frame bakes into its kernel arguments / control flow.  The reference reads them on
+    every frame, so a capture is only valid (and only shared between sessions) while they are unchanged."""
+    return (m.output_mode, m.fill_hole_area, float(m.sigmoid_scale_for_mem_enc), float(m.sigmoid_bias_for_mem_enc),
+            bool(m._use_multimask(False, None)), bool(m.use_multimask_token_for_obj_ptr),
+            m.no_obj_embed_spatial is not None, bool(m.non_overlap_masks), bool(m.non_overlap_masks_for_mem_enc))
+
+
 def _signature_objects(m):
     """What a captured graph has baked addresses of: workspaces, packed weights and constants of the three modules."""
     return [m.memory_attention._ws, m.memory_attention._packed, m.sam_mask_decoder._ws, m.sam_mask_decoder._packed,
@@ -83,7 +91,7 @@ class FrameGraph:
         self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in feats[:3])
         self.in_pos = torch.empty_like(feats[3])
         self._side = torch.cuda.Stream(device=dev)
-        self.output_mode = model.output_mode
+        self.baked = baked_settings(model)
         self.graph = None
 
     def _step(self):
@@ -107,7 +115,7 @@ class FrameGraph:
         self._sig = tuple(id(o) for o in self._keepalive)
 
     def valid(self):
-        if self.output_mode != self.model.output_mode:
+        if self.baked != baked_settings(self.model):
             return False
         return self.graph is None or self._sig == tuple(id(o) for o in _signature_objects(self.model))
 
@@ -143,7 +151,7 @@ class SteadyStateGraph:
         self.n_ptr = min(self.num_frames, m.max_obj_ptrs_in_encoder)   # 16
         self.k = m.hidden_dim // m.mem_dim               # 4 tokens per pointer
         self.Nk = self.n_mem * self.HW + self.n_ptr * self.k
-        self.output_mode = model.output_mode
+        self.baked = baked_settings(model)
         self.graph = None
         self.next_frame = None
         self._side = torch.cuda.Stream(device=self.dev)
@@ -224,7 +232,7 @@ class SteadyStateGraph:
         _, bo, _, _, _ = model._get_image_feature(state, frame_idx, 1)
         fpn = bo["backbone_fpn"]
         return (batch_size, (state["video_height"], state["video_width"]),
-                min(state["num_frames"], model.max_obj_ptrs_in_encoder), model.output_mode, tuple(fpn[-3].shape),
+                min(state["num_frames"], model.max_obj_ptrs_in_encoder), baked_settings(model), tuple(fpn[-3].shape),
                 tuple(fpn[-2].shape), tuple(fpn[-1].shape), fpn[-1].dtype)
 
     def idle(self):
@@ -232,8 +240,14 @@ class SteadyStateGraph:
         owner = self._owner() if self._owner is not None else None
         return owner is None or self.next_frame is None or self.next_frame >= self.num_frames
 
-    def release(self):
-        self._owner = None
+    def owned_by(self, owner):
+        return owner is not None and self._owner is not None and self._owner() is owner
+
+    def release(self, owner):
+        """Called by a session that stops using the graph.  A no-op unless that session still owns it: a finished
+        session keeps a stale reference to a graph that may have been handed to another clip in the meantime."""
+        if self.owned_by(owner):
+            self._owner = None
 
     def rebind(self, state, frame_idx, owner):
         """Hand a captured graph to another session of the same shape: refill the static buffers, keep the capture
@@ -292,14 +306,15 @@ class SteadyStateGraph:
 
     def valid(self):
         """False once weights were re-packed / moved (the captured pointers would be stale)."""
-        if self.output_mode != self.model.output_mode:
-            return False                                   # the output stage is part of the captured graph
+        if self.baked != baked_settings(self.model):
+            return False                                   # output stage, hole filling, sigmoid scale ... are captured
         return self.graph is None or self._sig == tuple(id(o) for o in self._signature_objects())
 
     # ------------------------------------------------------------------ per frame
     def run(self, state, frame_idx):
         """One propagated frame.  Returns the compact state entry and the video-resolution logits."""
         assert frame_idx == self.next_frame, "graphed propagation must advance frame by frame"
+        assert self.owned_by(state.get("graph_owner")), "the captured graph (and its memory bank) belongs to another session"
         self._load_inputs(state, frame_idx)
         if self.graph is None:
             self._capture()

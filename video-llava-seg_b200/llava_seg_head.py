@@ -19,6 +19,7 @@ class SegmentationHeadSAM2(nn.Module):
         self.proj_token = nn.Linear(n_token_dims, 256 * n_seg_queries)
         self.sam2 = sam2_model
         self._w = None
+        self.register_load_state_dict_post_hook(lambda m, keys: setattr(m, "_w", None))
 
     def _apply(self, fn, *a, **kw):
         self._w = None

@@ -74,7 +74,7 @@ class MaskDecoder(PackedModule):
         _, C, H, W = image_embeddings.shape
         if not repeat_image:
             assert image_embeddings.shape[0] == B
-        pe_key = (image_pe.data_ptr(), tuple(image_pe.shape), image_pe.dtype)
+        pe_key = (image_pe.data_ptr(), tuple(image_pe.shape), image_pe.dtype, getattr(image_pe, "_vls_version", 0))
         if self._packed is None or self._pe_key != pe_key:
             self._packed = _pack.pack_mask_decoder(self._flat_sd(), "", dev, image_pe,
                                                    self.iou_prediction_head.sigmoid_output)

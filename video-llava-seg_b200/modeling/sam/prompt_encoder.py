@@ -23,6 +23,13 @@ class PromptEncoder(nn.Module):
             activation(), nn.Conv2d(mask_in_chans, embed_dim, kernel_size=1))
         self.no_mask_embed = nn.Embedding(1, embed_dim)
         self._dense_pe = None
+        self._pe_version = 0
+        self.register_load_state_dict_post_hook(lambda m, keys: m._drop_dense_pe())
+
+    def _drop_dense_pe(self):
+        """An in-place load_state_dict keeps data_ptr, so the cache cannot be keyed on pointers alone."""
+        self._dense_pe = None
+        self._pe_version += 1
 
     def _apply(self, fn, *a, **kw):
         self._dense_pe = None
@@ -33,7 +40,9 @@ class PromptEncoder(nn.Module):
         g = self.pe_layer.positional_encoding_gaussian_matrix
         key = (g.data_ptr(), g.device)
         if self._dense_pe is None or self._dense_pe[0] != key:
-            self._dense_pe = (key, self.pe_layer(self.image_embedding_size).unsqueeze(0))
+            pe = self.pe_layer(self.image_embedding_size).unsqueeze(0)
+            pe._vls_version = self._pe_version       # MaskDecoder keys its PE-dependent packed constants on it
+            self._dense_pe = (key, pe)
         return self._dense_pe[1]
 
     def _embed_points(self, points, labels, pad):

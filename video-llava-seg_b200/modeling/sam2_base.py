@@ -112,6 +112,8 @@ class SAM2Base(nn.Module):
         self.obj_ptr_tpos_proj = nn.Linear(self.hidden_dim, self.mem_dim)
         self.max_cond_frames_in_attn = max_cond_frames_in_attn
         self._consts = None
+        # weight-derived constants (obj_ptr_proj, no_obj_ptr, maskmem_tpos_enc, ...) follow a checkpoint load
+        self.register_load_state_dict_post_hook(lambda m, keys: setattr(m, "_consts", None))
 
     # ------------------------------------------------------------------ plumbing
     @property

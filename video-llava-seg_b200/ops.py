@@ -66,6 +66,26 @@ def attention_d256(q, k, vt, scale=None, splits=0, out=None):
     return out
 
 
+def attention_qk256(q, k, v, v_rows, scale=None, splits=0, out=None):
+    """softmax(q k^T * scale) v with q/k head dim 256 and value dim dv in {256, 64}.  v_rows=False: v is V transposed
+    [B,dv,>=Nk]; v_rows=True (dv == 64): v is [B,Nk,64] rows as the memory bank stores them.  Returns [B,Nq,dv] bf16."""
+    _lib.require_cuda(q, k, v)
+    B, Nq, D = q.shape
+    Nk = k.shape[1]
+    dv = v.shape[2] if v_rows else v.shape[1]
+    assert D == 256 and k.shape[2] == 256 and (v.shape[1] == Nk if v_rows else v.shape[2] >= Nk)
+    assert q.stride(2) == 1 and k.stride(2) == 1 and v.stride(2) == 1
+    if out is None:
+        out = torch.empty((B, Nq, dv), device=q.device, dtype=torch.bfloat16)
+    scale = float(scale) if scale is not None else 1.0 / 16.0
+    nbytes = lib().vls_attention_qk256_workspace_bytes(B, Nq, Nk, dv, splits)
+    ws = torch.empty(max(nbytes, 1), device=q.device, dtype=torch.uint8)
+    check(lib().vls_attention_qk256(ptr(q), q.stride(1), q.stride(0), ptr(k), k.stride(1), k.stride(0), ptr(v),
+                                    v.stride(1), v.stride(0), dv, int(bool(v_rows)), B, Nq, Nk, scale, splits, ptr(out),
+                                    out.stride(1), out.stride(0), ptr(ws), nbytes, stream()), "vls_attention_qk256")
+    return out
+
+
 def resize_bilinear(x, size):
     """F.interpolate(x, size, mode="bilinear", align_corners=False) for f32 [N,C,h,w]."""
     _lib.require_cuda(x)

@@ -14,7 +14,7 @@ from collections import OrderedDict
 import torch
 
 from . import ops
-from .graphed import FrameGraph, SteadyStateGraph
+from .graphed import FrameGraph, SteadyStateGraph, baked_settings
 from .modeling.sam2_base import NO_OBJ_SCORE, SAM2Base
 from .utils.misc import fill_holes_in_mask_scores, load_video_frames
 
@@ -342,6 +342,8 @@ class SAM2VideoPredictor(SAM2Base):
             else:
                 key = "non_cond_frame_outputs"
                 g = st.get("steady_graph")
+                if g is not None and not g.owned_by(st.get("graph_owner")):
+                    g = st["steady_graph"] = None     # handed to another clip since this session last used it
                 if g is not None and (g.next_frame != f or g.B != B or not g.valid()):
                     self._drop_graph(st)
                     g = None
@@ -383,7 +385,7 @@ class SAM2VideoPredictor(SAM2Base):
             return None
         Nk = sum(p.shape[1] for p in mem_parts)
         hw = (st["video_height"], st["video_width"])
-        key = (batch_size, Nk, n_ptr_tokens, hw, self.output_mode, tuple(fpn[-3].shape), tuple(fpn[-2].shape),
+        key = (batch_size, Nk, n_ptr_tokens, hw, baked_settings(self), tuple(fpn[-3].shape), tuple(fpn[-2].shape),
                tuple(fpn[-1].shape), fpn[-1].dtype)
         cache = self.__dict__.setdefault("_frame_graphs", {})
         seen = self.__dict__.setdefault("_frame_shapes_seen", {})
@@ -410,7 +412,7 @@ class SAM2VideoPredictor(SAM2Base):
         """The session stops using its captured graph (new prompts, object removed, ...): the graph becomes re-usable."""
         g = st.get("steady_graph")
         if g is not None:
-            g.release()
+            g.release(st.get("graph_owner"))     # no-op when the graph already serves another session
         st["steady_graph"] = None
 
     def _acquire_graph(self, st, frame_idx, batch_size):
