@@ -45,6 +45,7 @@ void vls_launch_count_add(long long n);
  * the (query tile, key tile) units are dealt out evenly to one persistent CTA per SM; 0 = always fixed splits.
  * "attn_v_rows": 1 (default) = the memory cross-attention reads its value operand straight from the bank rows; 0 = from
  * a transposed copy made once per frame.
+ * "ffn_fused": 1 (default) = the memory-attention FFN runs as one cluster kernel; 0 = as two GEMM launches.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -106,6 +107,12 @@ int vls_attention_qk256(const void* Q, long long ldq, long long q_bstride, const
                         long long k_bstride, const void* V, long long ldv, long long v_bstride, int dv, int v_rows, int B,
                         int Nq, int Nk, float scale, int splits, void* O, long long ldo, long long o_bstride,
                         void* workspace, size_t workspace_bytes, vls_stream_t stream);
+
+/* Back-to-back FFN of a memory-attention layer (memory_attention.py:95-98) in one cluster kernel:
+ * x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2, t bf16 [B][M][256] (row stride ldt), W1 bf16 [2048][256],
+ * W2 bf16 [256][2048], x f32 [B][M][256] updated in place.  The [M][2048] hidden tensor never leaves the SM. */
+int vls_ffn_fused(const void* t_bf16, long long ldt, long long t_bstride, const void* w1_bf16, const float* b1,
+                  const void* w2_bf16, const float* b2, float* x, long long x_bstride, int B, int M, vls_stream_t stream);
 
 /* Bilinear resize of n f32 images [h,w] -> [H,W], align_corners=False, no antialiasing
  * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */

@@ -181,7 +181,10 @@ def clip_case(model, sd, name, seed, num_frames, batch, sub=2, dense=None):
                       cc=cc_oracle.cc_label)
     out = {}
     for t, (r, o) in enumerate(zip(ref, ora)):
-        d_mask = maxdiff(r["pred_masks"], o["pred_masks"])
+        # hole filling is a discrete decision: a pixel within float rounding of 0 may be filled on one side only
+        one_sided = (r["pred_masks"] == 0.1) ^ (o["pred_masks"] == 0.1)
+        d_mask = (r["pred_masks"] - o["pred_masks"]).abs()[~one_sided].max().item()
+        assert one_sided.float().mean().item() < 1e-4
         d_ptr = maxdiff(r["obj_ptr"], o["obj_ptr"])
         d_mem = maxdiff(r["maskmem_features"], o["maskmem_features"])
         fg = (r["pred_masks"] > 0).float().mean().item()
@@ -207,6 +210,7 @@ def clip_case(model, sd, name, seed, num_frames, batch, sub=2, dense=None):
 GATE_CLIPS = (("clip_gate_cond_t6", dict(seed=6, num_frames=6, batch=1), -0.12),
               ("clip_gate_all_t6", dict(seed=7, num_frames=6, batch=2), -0.9))
 STEADY = {0, 1, 2, 8, 15, 16, 17, 18, 19}
+STEADY_B8 = {0, 1, 16, 19}          # 8 objects: fewer dense frames keep the fixture small
 
 
 def main():
@@ -227,7 +231,7 @@ def main():
                          # pointers from frame 16 on, i.e. the CUDA-graph path and the balanced attention mode ...
                          ("clip_b1_t20", dict(seed=4, num_frames=20, batch=1, dense=STEADY)),
                          # ... and configs[2]'s shape at full bank (8 objects: fixed-split attention, direct bf16 store)
-                         ("clip_b8_t20", dict(seed=5, num_frames=20, batch=8, sub=4, dense=STEADY))):
+                         ("clip_b8_t20", dict(seed=5, num_frames=20, batch=8, sub=4, dense=STEADY_B8))):
             if not only or name in only:
                 clip_case(model, sd, name, **kw)
         if not only or "api" in only:

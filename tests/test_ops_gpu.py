@@ -105,6 +105,31 @@ def test_attention_d256(dev, B, Nq, Nk, splits):
     assert err < 2e-2, err
 
 
+@pytest.mark.parametrize("B,M", [(1, 128), (1, 4096), (2, 1000), (8, 4096)])
+def test_ffn_fused(dev, B, M):
+    """x += relu(t W1^T + b1) W2^T + b2 as ONE cluster kernel (hidden activations in TMEM, partial outputs reduced over
+    distributed shared memory) vs the same math in fp32 with the hidden rounded to bf16 as the kernel rounds it; run
+    twice to check that the DSMEM reduction is bitwise deterministic."""
+    from video_llava_seg_b200 import ops
+
+    t = _rand((B, M, 256), dev, 21).bfloat16()
+    w1 = _rand((2048, 256), dev, 22, 1.0 / 16).bfloat16()
+    b1 = _rand((2048,), dev, 23, 0.1)
+    w2 = _rand((256, 2048), dev, 24, 1.0 / 45).bfloat16()
+    b2 = _rand((256,), dev, 25, 0.1)
+    x0 = _rand((B, M, 256), dev, 26)
+    h = torch.relu(t.float() @ w1.float().t() + b1).bfloat16().float()
+    ref = x0 + h @ w2.float().t() + b2
+    x = x0.clone()
+    ops.ffn_fused(t, w1, b1, w2, b2, x)
+    x2 = x0.clone()
+    ops.ffn_fused(t, w1, b1, w2, b2, x2)
+    torch.cuda.synchronize()
+    err = (x - ref).abs().max().item()
+    assert err < 5e-3, err
+    assert torch.equal(x, x2)
+
+
 @pytest.mark.parametrize("v_rows", [True, False])
 @pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 256, 520, 1), (2, 256, 1000, 2), (1, 4096, 28736, 0),
                                             (1, 4096, 28700, 4), (1, 4096, 28700, 0), (2, 2048, 16500, 0),

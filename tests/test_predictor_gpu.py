@@ -36,35 +36,44 @@ def predictor_with_bias(vls_lib, predictor):
 
 
 def _run(predictor, seed, num_frames, batch):
+    """Tracks a synthetic clip; returns [(frame, stored entry, video_res, logits entering hole filling or None)].  The
+    pre-fill logits are only observable on frames that run eagerly (prompt frame, first occurrence of a bank shape):
+    frames replayed from a captured CUDA graph do not call back into Python."""
     from video_llava_seg_b200 import synth
     from video_llava_seg_b200.features import FeatureClip
 
     import video_llava_seg_b200.sam2_video_predictor as vp
 
-    prefill, orig_fill = [], vp.fill_holes_in_mask_scores
+    pending, orig_fill = [], vp.fill_holes_in_mask_scores
 
     def recording_fill(mask, max_area):  # logits as they enter hole filling (B calls on the prompt frame, then 1/frame)
-        prefill.append(mask.clone())
+        pending.append(mask.clone())
         return orig_fill(mask, max_area)
 
     vp.fill_holes_in_mask_scores = recording_fill
-    clip = synth.SyntheticClip(seed, num_frames)
-    src = FeatureClip(lambda t: clip.frame(t, 1), num_frames, resident_device="cuda:0")
-    state = predictor.init_state(src)
-    prompt = clip.point_prompt(batch)
-    for o in range(batch):
-        fi, ids, m = predictor.add_new_points_or_box(state, frame_idx=0, obj_id=o + 1,
-                                                     points=prompt["point_coords"][o].tolist(), labels=[1])
-        assert fi == 0 and m.shape == (o + 1, 1, 1024, 1024)
-    frames = []
-    for fi, ids, video_res in predictor.propagate_in_video(state):
-        assert ids == list(range(1, batch + 1)) and video_res.shape == (batch, 1, 1024, 1024)
-        key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
-        frames.append([fi, state["output_dict"][key][fi], video_res])
-    vp.fill_holes_in_mask_scores = orig_fill
-    pre = [torch.cat(prefill[:batch], 0)] + prefill[batch:]
-    assert len(pre) == len(frames)
-    return [tuple(f) + (p,) for f, p in zip(frames, pre)]
+    try:
+        clip = synth.SyntheticClip(seed, num_frames)
+        src = FeatureClip(lambda t: clip.frame(t, 1), num_frames, resident_device="cuda:0")
+        state = predictor.init_state(src)
+        prompt = clip.point_prompt(batch)
+        for o in range(batch):
+            fi, ids, m = predictor.add_new_points_or_box(state, frame_idx=0, obj_id=o + 1,
+                                                         points=prompt["point_coords"][o].tolist(), labels=[1])
+            assert fi == 0 and m.shape == (o + 1, 1, 1024, 1024)
+        assert len(pending) == batch
+        first = torch.cat(pending, 0)
+        pending.clear()
+        frames = []
+        for fi, ids, video_res in predictor.propagate_in_video(state):
+            assert ids == list(range(1, batch + 1)) and video_res.shape == (batch, 1, 1024, 1024)
+            key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
+            assert len(pending) <= 1
+            pre = first if fi == 0 else (pending[0] if pending else None)
+            pending.clear()
+            frames.append((fi, state["output_dict"][key][fi], video_res, pre))
+    finally:
+        vp.fill_holes_in_mask_scores = orig_fill
+    return frames
 
 
 CLIPS = [("clip_b1_t8", 1, 8, 1, 0.75), ("clip_b2_t4", 2, 4, 2, 0.75), ("clip_b8_t3", 3, 3, 8, 0.75),
@@ -104,8 +113,14 @@ def test_propagation_matches_reference(predictor_with_bias, name, seed, T, B, bi
         assert osl_err < 1e-2 and ptr_err < 5e-2, (t, osl_err, ptr_err)
         assert out["maskmem_features"].dtype == torch.bfloat16
         if f"prefill_s{sub}_{t}" in gold.files:
-            # (1) raw decoder logits (before hole filling): north-star bound 1e-2 abs
-            err = (prefill.float().cpu()[:, :, ::sub, ::sub] - torch.from_numpy(gold[f"prefill_s{sub}_{t}"])).abs().max().item()
+            # (1) raw decoder logits (before hole filling): north-star bound 1e-2 abs.  Graph-replayed frames expose only
+            #     the hole-filled logits: there the bound is applied to every pixel that was not filled on either side
+            if prefill is not None:
+                err = (prefill.float().cpu()[:, :, ::sub, ::sub] - torch.from_numpy(gold[f"prefill_s{sub}_{t}"])).abs().max().item()
+            else:
+                a_, b_ = pm[:, :, ::sub, ::sub], torch.from_numpy(gold[f"mask_s{sub}_{t}"])
+                keep = (a_ != 0.1) & (b_ != 0.1)
+                err = (a_ - b_).abs()[keep].max().item()
             # (2) stored (hole-filled) logits: filling is a discrete decision on pixels whose logit is within noise of 0,
             #     so a few pixels may differ by the fill value 0.1 -- bound their share
             ref_post = torch.from_numpy(gold[f"mask_s{sub}_{t}"])

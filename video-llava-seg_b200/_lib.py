@@ -66,6 +66,9 @@ def _declare(lib):
     lib.vls_attention_qk256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
                                         c_int, c_int, c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t,
                                         c_void_p]
+    lib.vls_ffn_fused.restype = c_int
+    lib.vls_ffn_fused.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
+                                  c_void_p]
     lib.vls_attention_d256.restype = c_int
     lib.vls_attention_d256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
                                        c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t, c_void_p]

@@ -29,6 +29,10 @@ int vls_set_tuning(const char* key, int value) {
     g_attn_v_rows = value != 0;
     return 0;
   }
+  if (std::string(key) == "ffn_fused") {   // memory-attention FFN: 1 = one cluster kernel (hidden stays in TMEM), 0 = two GEMMs
+    g_ffn_fused = value != 0;
+    return 0;
+  }
   if (std::string(key) == "pdl") {   // programmatic dependent launch on/off (host.h)
     pdl_set(value != 0);
     return 0;
@@ -106,6 +110,11 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
                        size_t workspace_bytes, vls_stream_t stream) {
   return vls_attention_qk256(Q, ldq, q_bstride, K, ldk, k_bstride, Vt, ldvt, vt_bstride, 256, 0, B, Nq, Nk, scale, splits, O,
                              ldo, o_bstride, workspace, workspace_bytes, stream);
+}
+
+int vls_ffn_fused(const void* t_bf16, long long ldt, long long t_bstride, const void* w1_bf16, const float* b1,
+                  const void* w2_bf16, const float* b2, float* x, long long x_bstride, int B, int M, vls_stream_t stream) {
+  return launch_ffn_fused(t_bf16, ldt, t_bstride, w1_bf16, b1, w2_bf16, b2, x, x_bstride, B, M, (cudaStream_t)stream);
 }
 
 int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,

@@ -60,6 +60,12 @@ size_t attn_part_ml_offset(int B, int Nq, int splits, int dv = 256);
 int attn_pick_splits(int B, int Nq, int Nk);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
 
+// ---------------------------------------------------------------- fused FFN (ffn_fused.cu)
+// x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2 in one cluster kernel (hidden activations stay in TMEM).
+int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const void* w1, const float* b1, const void* w2,
+                     const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream);
+extern int g_ffn_fused;
+
 // ---------------------------------------------------------------- connected components (cc.cu)
 size_t cc_workspace_bytes(int n, int h, int w, bool fill);
 int launch_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* ws,

@@ -181,7 +181,9 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     }
     // ---- FFN (memory_attention.py:95-98)
     VLS_TRY(launch_ln256(x, B, Nq, Lw.n3_w, Lw.n3_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
-    {
+    if (g_ffn_fused) {   // one cluster kernel: the [Nq][2048] hidden tensor stays in tensor memory (ffn_fused.cu)
+      VLS_TRY(launch_ffn_fused(t, C, (long long)Nq * C, Lw.l1_w, Lw.l1_b, Lw.l2_w, Lw.l2_b, x, (long long)Nq * C, B, Nq, st));
+    } else {
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.l1_w, Nq, FFN, C, B, Lw.l1_b, h, 1, FFN, (long long)Nq * FFN);
       g.act = 1;
       VLS_TRY(launch_gemm(g, st));

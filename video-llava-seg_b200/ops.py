@@ -86,6 +86,19 @@ def attention_qk256(q, k, v, v_rows, scale=None, splits=0, out=None):
     return out
 
 
+def ffn_fused(t, w1, b1, w2, b2, x):
+    """x += relu(t @ w1^T + b1) @ w2^T + b2 in place.  t [B,M,256] bf16, w1 [2048,256] bf16, w2 [256,2048] bf16,
+    b1 / b2 f32, x [B,M,256] f32 contiguous."""
+    _lib.require_cuda(t, w1, b1, w2, b2, x)
+    B, M, C = t.shape
+    assert C == 256 and tuple(w1.shape) == (2048, 256) and tuple(w2.shape) == (256, 2048) and x.shape == t.shape
+    assert t.dtype == torch.bfloat16 and w1.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert x.dtype == torch.float32 and x.is_contiguous() and t.stride(2) == 1 and w1.is_contiguous() and w2.is_contiguous()
+    check(lib().vls_ffn_fused(ptr(t), t.stride(1), t.stride(0), ptr(w1), ptr(b1), ptr(w2), ptr(b2), ptr(x), x.stride(0), B, M,
+                              stream()), "vls_ffn_fused")
+    return x
+
+
 def resize_bilinear(x, size):
     """F.interpolate(x, size, mode="bilinear", align_corners=False) for f32 [N,C,h,w]."""
     _lib.require_cuda(x)
