@@ -46,6 +46,8 @@ void vls_launch_count_add(long long n);
  * "attn_v_rows": 1 (default) = the memory cross-attention reads its value operand straight from the bank rows; 0 = from
  * a transposed copy made once per frame.
  * "ffn_fused": 1 (default) = the memory-attention FFN runs as one cluster kernel; 0 = as two GEMM launches.
+ * "tail_fused": 1 (default, needs ffn_fused) = folded out-projection, LayerNorm3, FFN and the following LayerNorm of a
+ * memory-attention layer run as ONE launch; 0 = as separate launches.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -53,6 +55,8 @@ int vls_set_tuning(const char* key, int value);
 /* Developer aid: when non-NULL, CTA (0,0,0) of every attention launch writes clock64() stamps of its producer /
  * MMA / softmax roles for the first 64 key tiles into this device buffer of 3*64*8 int64 (tools/trace_attention.py). */
 void vls_attention_trace(long long* device_buffer);
+/* Same for the fused FFN / layer-tail kernel: 16 int64 stamps of the first epilogue thread of CTA (0,0,0) (tools/trace_ffn.py). */
+void vls_ffn_trace(long long* device_buffer);
 /* Optional live kernel timing: when enabled, the attention launcher brackets its kernel with CUDA events
  * on the launching stream; vls_prof_collect(slot) synchronises them and returns count / total ms and clears
  * the slot.  slot 0 = memory cross-attention launches (Nk > Nq), slot 1 = self-attention launches. */
@@ -113,6 +117,17 @@ int vls_attention_qk256(const void* Q, long long ldq, long long q_bstride, const
  * W2 bf16 [256][2048], x f32 [B][M][256] updated in place.  The [M][2048] hidden tensor never leaves the SM. */
 int vls_ffn_fused(const void* t_bf16, long long ldt, long long t_bstride, const void* w1_bf16, const float* b1,
                   const void* w2_bf16, const float* b2, float* x, long long x_bstride, int B, int M, vls_stream_t stream);
+
+/* The tail of a memory-attention layer in one cluster kernel (memory_attention.py:76-98 + the LayerNorm that follows):
+ *   x_mid = x_in + ao W0^T + b0          ao bf16 [B][M][64] = softmax(QK^T) mem, W0 bf16 [256][64] = out_proj.W v_proj.W
+ *   x_out = x_mid + relu(LN(x_mid) W1^T + b1) W2^T + b2
+ *   t_out = LN2(x_out)                   bf16 or f32, element (b, row, c) at b*t_out_sb + row*t_out_st + c
+ * x_in / x_out: f32 [B][M][256], DIFFERENT buffers. */
+int vls_mem_attn_layer_tail(const void* ao_bf16, const void* w0_bf16, const float* b0, const float* ln_w, const float* ln_b,
+                            float ln_eps, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                            const float* x_in, float* x_out, const float* ln2_w, const float* ln2_b, float ln2_eps,
+                            void* t_out, int t_out_dtype, long long t_out_st, long long t_out_sb, int B, int M,
+                            vls_stream_t stream);
 
 /* Bilinear resize of n f32 images [h,w] -> [H,W], align_corners=False, no antialiasing
  * (F.interpolate as used at sam2_base.py:373-378 and sam2_video_predictor.py:416-421). */

@@ -47,11 +47,20 @@ def api_scenarios(predictor, init_state, names=None):
     def bits(name, video_res):
         rec[name] = np.packbits((video_res.detach().float().cpu() > 0).numpy().reshape(video_res.shape[0], -1), axis=1)
 
-    def track(tag, st, **kw):
+    def track(tag, st, ambiguous=False, **kw):
         for f, ids, video in predictor.propagate_in_video(st, **kw):
             bits(f"{tag}_f{f}", video)
             key = "cond_frame_outputs" if f in st["output_dict"]["cond_frame_outputs"] else "non_cond_frame_outputs"
-            rec[f"{tag}_ptr{f}"] = st["output_dict"][key][f]["obj_ptr"].detach().float().cpu().numpy()
+            o = st["output_dict"][key][f]
+            rec[f"{tag}_ptr{f}"] = o["obj_ptr"].detach().float().cpu().numpy()
+            if ambiguous:
+                # the non-overlap constraint is a per-pixel ARG-MAX over the objects: where the two objects' scores are
+                # within the numerical tolerance of each other the winner is a coin flip -- mark those pixels
+                pm = torch.nn.functional.interpolate(o["pred_masks"].detach().float().cpu(), size=tuple(video.shape[-2:]),
+                                                     mode="bilinear", align_corners=False)
+                mx = pm.max(0).values        # ties only matter where an object is (nearly) foreground
+                amb = (((pm[0] - pm[1]).abs() < 3e-2) & (mx > -3e-2)) | (mx.abs() < 1e-2)
+                rec[f"{tag}_amb{f}"] = np.packbits(amb.numpy().reshape(1, -1), axis=1)
 
     want = lambda n: names is None or n in names
     if want("mask"):
@@ -76,11 +85,13 @@ def api_scenarios(predictor, init_state, names=None):
         old = predictor.non_overlap_masks
         predictor.non_overlap_masks = True
         try:
+            # two objects prompted with OVERLAPPING mask prompts: with random-init weights two click prompts give nearly the
+            # same mask for both objects and the per-pixel arg-max would be a coin flip everywhere
             st = init_state()
-            predictor.add_new_points_or_box(st, 0, 1, points=[[300.0, 500.0]], labels=[1])
-            f, ids, video = predictor.add_new_points_or_box(st, 0, 2, points=[[340.0, 500.0]], labels=[1])
+            predictor.add_new_mask(st, 0, 1, blob_mask(300.0, 500.0, 90.0))
+            f, ids, video = predictor.add_new_mask(st, 0, 2, blob_mask(400.0, 540.0, 110.0))
             bits("nonoverlap_prompt", video)
-            track("nonoverlap", st)
+            track("nonoverlap", st, ambiguous=True)
         finally:
             predictor.non_overlap_masks = old
     if want("reverse"):
@@ -92,3 +103,16 @@ def api_scenarios(predictor, init_state, names=None):
         predictor.add_new_points_or_box(st, 0, 1, box=[200.0, 400.0, 420.0, 620.0])
         track("offload", st)
     return rec
+
+
+# ----------------------------------------------------------------------------- LLaVA seg head (BASELINE configs[3])
+SEG_META = {"padding": [0, 0, 0, 448], "resized_image_size": [576, 1024], "orig_image_size": [480, 854]}
+
+
+def seg_head_inputs():
+    """Seeded inputs of the SegmentationHeadSAM2.forward parity case: 3 frames of backbone features, 2 objects x 2 seg
+    queries, 512-d `[SEG]` hidden states, the head's own projection weights."""
+    g = torch.Generator().manual_seed(4321)
+    rn = lambda *s: torch.randn(*s, generator=g)
+    return {"feats": rn(3, 256, 64, 64) * 0.5, "s0": rn(3, 32, 256, 256) * 0.3, "s1": rn(3, 64, 128, 128) * 0.3,
+            "tokens": rn(2, 512), "proj_w": rn(512, 512) * 0.05, "proj_b": rn(512) * 0.05, "n_seg_queries": 2}

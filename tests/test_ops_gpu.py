@@ -130,6 +130,40 @@ def test_ffn_fused(dev, B, M):
     assert torch.equal(x, x2)
 
 
+@pytest.mark.parametrize("B,M,out_dtype", [(1, 128, torch.bfloat16), (1, 4096, torch.bfloat16), (2, 1000, torch.float32),
+                                           (8, 4096, torch.bfloat16)])
+def test_mem_attn_layer_tail(dev, B, M, out_dtype):
+    """The whole tail of a memory-attention layer in ONE launch -- folded out-projection (K = 64) + residual, LayerNorm,
+    FFN + residual, following LayerNorm -- vs the same chain in fp32 torch (operands rounded to bf16 where the kernel
+    rounds them).  Twice: the distributed-shared-memory reductions must be bitwise deterministic."""
+    import torch.nn.functional as F
+
+    from video_llava_seg_b200 import ops
+
+    ao = _rand((B, M, 64), dev, 31).bfloat16()
+    w0 = _rand((256, 64), dev, 32, 1.0 / 8).bfloat16()
+    b0 = _rand((256,), dev, 33, 0.1)
+    ln_w, ln_b = 1.0 + _rand((256,), dev, 34, 0.1), _rand((256,), dev, 35, 0.05)
+    w1 = _rand((2048, 256), dev, 22, 1.0 / 16).bfloat16()
+    b1 = _rand((2048,), dev, 23, 0.1)
+    w2 = _rand((256, 2048), dev, 24, 1.0 / 45).bfloat16()
+    b2 = _rand((256,), dev, 25, 0.1)
+    ln2_w, ln2_b = 1.0 + _rand((256,), dev, 36, 0.1), _rand((256,), dev, 37, 0.05)
+    x_in = _rand((B, M, 256), dev, 26)
+    x_mid = x_in + ao.float() @ w0.float().t() + b0
+    t3 = F.layer_norm(x_mid, (256,), ln_w, ln_b, 1e-5).bfloat16().float()
+    h = torch.relu(t3 @ w1.float().t() + b1).bfloat16().float()
+    x_ref = x_mid + h @ w2.float().t() + b2
+    t_ref = F.layer_norm(x_ref, (256,), ln2_w, ln2_b, 1e-5)
+    x_out, t = ops.mem_attn_layer_tail(ao, w0, b0, ln_w, ln_b, w1, b1, w2, b2, x_in, ln2_w, ln2_b, out_dtype)
+    x_out2, t2 = ops.mem_attn_layer_tail(ao, w0, b0, ln_w, ln_b, w1, b1, w2, b2, x_in, ln2_w, ln2_b, out_dtype)
+    torch.cuda.synchronize()
+    ex, et = (x_out - x_ref).abs().max().item(), (t.float() - t_ref).abs().max().item()
+    print(f"layer tail B={B} M={M}: x err {ex:.3e} t err {et:.3e}")
+    assert ex < 1e-2 and et < (3e-2 if out_dtype == torch.bfloat16 else 1e-2), (ex, et)
+    assert torch.equal(x_out, x_out2) and torch.equal(t, t2)
+
+
 @pytest.mark.parametrize("v_rows", [True, False])
 @pytest.mark.parametrize("B,Nq,Nk,splits", [(1, 128, 64, 1), (1, 256, 520, 1), (2, 256, 1000, 2), (1, 4096, 28736, 0),
                                             (1, 4096, 28700, 4), (1, 4096, 28700, 0), (2, 2048, 16500, 0),

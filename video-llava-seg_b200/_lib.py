@@ -42,6 +42,8 @@ def _declare(lib):
     lib.vls_launch_count_add.argtypes = [c_ll]
     lib.vls_attention_trace.restype = None
     lib.vls_attention_trace.argtypes = [c_void_p]
+    lib.vls_ffn_trace.restype = None
+    lib.vls_ffn_trace.argtypes = [c_void_p]
     lib.vls_set_tuning.restype = c_int
     lib.vls_set_tuning.argtypes = [ctypes.c_char_p, c_int]
     lib.vls_prof_enable.restype = None
@@ -69,6 +71,10 @@ def _declare(lib):
     lib.vls_ffn_fused.restype = c_int
     lib.vls_ffn_fused.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int,
                                   c_void_p]
+    lib.vls_mem_attn_layer_tail.restype = c_int
+    lib.vls_mem_attn_layer_tail.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p,
+                                            c_int, c_ll, c_ll, c_int, c_int, c_void_p]
     lib.vls_attention_d256.restype = c_int
     lib.vls_attention_d256.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_int, c_int,
                                        c_int, c_float, c_int, c_void_p, c_ll, c_ll, c_void_p, c_size_t, c_void_p]

@@ -14,6 +14,7 @@ int vls_abi_version(void) { return 2; }
 long long vls_launch_count(void) { return launch_count(); }
 void vls_launch_count_add(long long n) { count_launches((int)n); }
 void vls_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
+void vls_ffn_trace(long long* device_buffer) { g_ffn_trace = device_buffer; }
 int vls_set_tuning(const char* key, int value) {
   VLS_REQUIRE(key != nullptr, "set_tuning: null key");
   if (std::string(key) == "attn_cluster") {
@@ -31,6 +32,10 @@ int vls_set_tuning(const char* key, int value) {
   }
   if (std::string(key) == "ffn_fused") {   // memory-attention FFN: 1 = one cluster kernel (hidden stays in TMEM), 0 = two GEMMs
     g_ffn_fused = value != 0;
+    return 0;
+  }
+  if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
+    g_tail_fused = value != 0;
     return 0;
   }
   if (std::string(key) == "pdl") {   // programmatic dependent launch on/off (host.h)
@@ -115,6 +120,20 @@ int vls_attention_d256(const void* Q, long long ldq, long long q_bstride, const 
 int vls_ffn_fused(const void* t_bf16, long long ldt, long long t_bstride, const void* w1_bf16, const float* b1,
                   const void* w2_bf16, const float* b2, float* x, long long x_bstride, int B, int M, vls_stream_t stream) {
   return launch_ffn_fused(t_bf16, ldt, t_bstride, w1_bf16, b1, w2_bf16, b2, x, x_bstride, B, M, (cudaStream_t)stream);
+}
+
+int vls_mem_attn_layer_tail(const void* ao_bf16, const void* w0_bf16, const float* b0, const float* ln_w, const float* ln_b,
+                            float ln_eps, const void* w1_bf16, const float* b1, const void* w2_bf16, const float* b2,
+                            const float* x_in, float* x_out, const float* ln2_w, const float* ln2_b, float ln2_eps,
+                            void* t_out, int t_out_dtype, long long t_out_st, long long t_out_sb, int B, int M,
+                            vls_stream_t stream) {
+  LayerTailArgs a;
+  a.ao = ao_bf16; a.w0 = w0_bf16; a.b0 = b0; a.ln_w = ln_w; a.ln_b = ln_b; a.ln_eps = ln_eps;
+  a.w1 = w1_bf16; a.b1 = b1; a.w2 = w2_bf16; a.b2 = b2; a.x_in = x_in; a.x_out = x_out;
+  a.ln2_w = ln2_w; a.ln2_b = ln2_b; a.ln2_eps = ln2_eps;
+  a.t_out = t_out; a.t_out_bf16 = t_out_dtype == VLS_BF16; a.t_out_st = t_out_st; a.t_out_sb = t_out_sb;
+  a.B = B; a.M = M;
+  return launch_layer_tail(a, (cudaStream_t)stream);
 }
 
 int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,

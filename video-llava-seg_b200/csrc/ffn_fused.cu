@@ -13,9 +13,17 @@
 //   * weights stream through PANEL rings (W1: 6 x [128 x 64] = 16 KB slots, W2: 2 x [256 x 64] = 32 KB slots) with one
 //     full/empty mbarrier pair per slot, released by a tcgen05.commit after the 4 MMAs that read the panel, so the
 //     producer runs up to 1.5 chunks ahead without a second whole-chunk stage
-//   * the four partial Y tiles (f32 [128][256] each) are reduced over DISTRIBUTED SHARED MEMORY in a fixed order (CTA r
-//     sums columns [64 r, 64 r + 64) of all four, adds b2 and the residual and writes x): deterministic, no atomics,
-//     no partials in global memory.
+//   * the four partial Y tiles (f32 [128][256] each) are reduced over DISTRIBUTED SHARED MEMORY: every CTA pushes the
+//     64-column slice owned by CTA o into o's shared memory (st.shared::cluster), then CTA r sums its four slices in rank
+//     order, adds b2 and the residual and writes x: deterministic, no atomics, no partials in global memory.
+// Optional FRONT (the whole tail of a memory-attention layer in one launch, memory_attention.py:76-98): the CTA first
+// computes  x_mid = x_in + ao (Wo Wv)^T + b  (the folded cross-attention output projection, K = 64, 4 MMAs into the Y
+// columns) and t = LayerNorm3(x_mid) itself -- thread = row, so the statistics are thread-local -- and writes t as the
+// bf16 A operand straight into shared memory in the 128B-swizzled K-major layout TMA would have produced; every CTA of
+// the cluster does this redundantly (16 KB + 32 KB of operands), CTA r parks its 64-column slice of x_mid in x_out.
+// Optional BACK: the LayerNorm that follows (next layer's norm1 or the final norm): every CTA holds a 64-column slice of
+// the new rows, so the four exchange per-row (sum, sum of squares) over distributed shared memory and each normalises its
+// slice.  A layer tail that was 6 launches (out-proj GEMM, LN, FFN-1, FFN-2, next LN + the gaps between) becomes one.
 // TMEM: Y 256 columns | D1/H 2 x 128.  SMEM: t tile 64 KB + W1 ring 96 KB + W2 ring 64 KB = 224 KB (the Y dump for the
 // cluster reduce re-uses the t tile + W1 ring once every MMA has completed).
 #include "common.cuh"
@@ -45,9 +53,23 @@ struct FfnParams {
   int M;                      // rows per batch element
   const float* b1;
   const float* b2;
-  float* x;                   // f32 [B][M][256], updated in place
+  const float* x_in;          // f32 [B][M][256] residual input
+  float* x_out;               // f32 [B][M][256] result (== x_in unless FRONT, which needs a different buffer)
   long long x_bstride;
+  // FRONT
+  const float* b0;            // [256] bias of the folded output projection
+  const float* ln_w; const float* ln_b; float ln_eps;       // LayerNorm3
+  // BACK
+  const float* ln2_w; const float* ln2_b; float ln2_eps;    // the LayerNorm applied to the result
+  void* t_out; int t_out_bf16; long long t_out_st, t_out_sb;  // element (b, row, c) at b*sb + row*st + c
+  long long* trace;           // optional dev trace: clock64 stamps of the first epilogue thread of CTA (0,0,0)
 };
+
+#define FFN_TRACE(slot)                                                                              \
+  do {                                                                                               \
+    if (p.trace && threadIdx.x == 64 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)       \
+      p.trace[slot] = clock64();                                                                     \
+  } while (0)
 
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t cta_rank) {
   uint32_t r;
@@ -60,9 +82,20 @@ __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t cluster_addr) {
   return v;
 }
 
+__device__ __forceinline__ void st_dsmem_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
+  float2 v;
+  asm volatile("ld.shared::cluster.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(cluster_addr) : "memory");
+  return v;
+}
+
+// FRONT: tmA = ao [B][M][64] (box 128 x 64), tmW0 = folded out-proj weight [256][64] (box 256 x 64); else tmA = t [B][M][256]
+template <bool FRONT, bool BACK>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
-ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW1,
-                 const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in every CTA of the cluster, so this alignment is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,7 +111,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* d1_full = w2_empty + W2_SLOTS; // 2
   uint64_t* h_ready = d1_full + 2;         // 2
   uint64_t* y_full = h_ready + 2;          // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(y_full + 1);
+  uint64_t* g0_full = y_full + 1;          // FRONT: ao tile + folded out-proj weight have landed
+  uint64_t* g0_done = g0_full + 1;         // FRONT: the out-proj MMAs have completed (x_mid partial in TMEM, W2 ring free)
+  uint64_t* a_ready = g0_done + 1;         // FRONT: 128 epilogue threads have written t = LN(x_mid) into sA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -93,7 +129,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < W2_SLOTS; ++s) { mbar_init(&w2_full[s], 1); mbar_init(&w2_empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&d1_full[s], 1); mbar_init(&h_ready[s], 128); }
     mbar_init(y_full, 1);
+    mbar_init(g0_full, 1);
+    mbar_init(g0_done, 1);
+    mbar_init(a_ready, 128);
     fence_barrier_init();
+    tma_prefetch_desc(&tmW0);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -107,12 +147,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   pdl_enter();   // global memory from here on
+  FFN_TRACE(0);
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_expect_tx(a_full, A_BYTES);
+      if (FRONT) {   // staged in the (still idle) W2 ring: slot 0 = folded out-proj weight [256 x 64], slot 1 = ao tile [128 x 64]
+        mbar_expect_tx(g0_full, W2_SLOT_BYTES + BM * 128);
+        tma_load_3d(sW2, &tmW0, g0_full, 0, 0, 0);
+        tma_load_3d(sW2 + W2_SLOT_BYTES, &tmA, g0_full, 0, m0, bz);
+      } else {
+        mbar_expect_tx(a_full, A_BYTES);
 #pragma unroll
-      for (int kp = 0; kp < 4; ++kp) tma_load_3d(sA + kp * (BM * 128), &tmA, a_full, kp * 64, m0, bz);
+        for (int kp = 0; kp < 4; ++kp) tma_load_3d(sA + kp * (BM * 128), &tmA, a_full, kp * 64, m0, bz);
+      }
       // panel streams in consumption order: chunk 0 W1 panels, [chunk c+1 W1 panels, chunk c W2 panels] ...
       int i1 = 0, i2 = 0;
       auto load_w1 = [&](int c) {
@@ -136,6 +183,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       load_w1(0);
       for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) load_w1(c + 1);
+        if (FRONT && c == 0) mbar_wait(g0_done, 0);   // the out-proj operands have been consumed: the W2 ring is free
         load_w2(c);
       }
     }
@@ -175,7 +223,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(&w2_empty[s]);
         }
       };
-      mbar_wait(a_full, 0);
+      if (FRONT) {
+        mbar_wait(g0_full, 0);
+        tc_fence_after();
+        const uint64_t ad = make_desc_sw128(smem_u32(sW2 + W2_SLOT_BYTES)), bd = make_desc_sw128(smem_u32(sW2));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + TM_Y, ad + 2 * kk, bd + 2 * kk, idesc2, kk != 0 ? 1u : 0u);
+        umma_commit(g0_done);
+        mbar_wait(a_ready, 0);     // t = LN(x_mid) is in sA (generic-proxy writes, fenced by the writers)
+      } else {
+        mbar_wait(a_full, 0);
+      }
       tc_fence_after();
       gemm1(0);
       for (int c = 0; c < NCH; ++c) {
@@ -189,10 +247,74 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int rl = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
+    if (FRONT) {
+      // x_mid = x_in + ao (Wo Wv)^T + b0;  t = LN3(x_mid) -> sA (bf16, 128B-swizzled K-major panels)
+      const int row = m0 + rl;
+      const bool row_ok = row < p.M;
+      const float* xin = p.x_in + (long long)bz * p.x_bstride + (long long)row * C;
+      float* xpark = p.x_out + (long long)bz * p.x_bstride + (long long)row * C;
+      mbar_wait(g0_done, 0);
+      tc_fence_after();
+      FFN_TRACE(1);
+      float sum = 0.f, ss = 0.f;
+#pragma unroll 1
+      for (int k = 0; k < C / 32; ++k) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          xv[i] = row_ok ? *reinterpret_cast<const float4*>(xin + k * 32 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b0 + k * 32 + 4 * i));
+          float4 m;
+          m.x = __uint_as_float(r[4 * i]) + bb.x + xv[i].x; m.y = __uint_as_float(r[4 * i + 1]) + bb.y + xv[i].y;
+          m.z = __uint_as_float(r[4 * i + 2]) + bb.z + xv[i].z; m.w = __uint_as_float(r[4 * i + 3]) + bb.w + xv[i].w;
+          sum += (m.x + m.y) + (m.z + m.w);
+          ss += (m.x * m.x + m.y * m.y) + (m.z * m.z + m.w * m.w);
+          r[4 * i] = __float_as_uint(m.x); r[4 * i + 1] = __float_as_uint(m.y);
+          r[4 * i + 2] = __float_as_uint(m.z); r[4 * i + 3] = __float_as_uint(m.w);
+          if (row_ok && (k >> 1) == (int)rank) *reinterpret_cast<float4*>(xpark + k * 32 + 4 * i) = m;   // own slice of x_mid
+        }
+        tmem_st32(tmem + lane_off + TM_Y + k * 32, r);
+      }
+      tc_wait_st();
+      FFN_TRACE(2);
+      const float mean = sum * (1.0f / C);
+      const float rstd = rsqrtf(fmaxf(ss * (1.0f / C) - mean * mean, 0.f) + p.ln_eps);
+#pragma unroll 1
+      for (int k = 0; k < C / 32; ++k) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+        tc_wait_ld();
+        uint8_t* prow = sA + (k >> 1) * (BM * 128) + rl * 128;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t pk[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int cidx = k * 32 + j * 8 + 2 * e;
+            const float2 w = __ldg(reinterpret_cast<const float2*>(p.ln_w + cidx));
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.ln_b + cidx));
+            pk[e] = pack_bf16x2((__uint_as_float(r[j * 8 + 2 * e]) - mean) * rstd * w.x + bb.x,
+                                (__uint_as_float(r[j * 8 + 2 * e + 1]) - mean) * rstd * w.y + bb.y);
+          }
+          const int c16 = (k & 1) * 4 + j;   // 16-byte chunk inside the 128-byte panel row, XOR-swizzled by the row
+          *reinterpret_cast<uint4*>(prow + ((c16 ^ (rl & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        }
+      }
+      fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      FFN_TRACE(3);
+    }
     for (int c = 0; c < NCH; ++c) {
       const int b = c & 1;
       mbar_wait(&d1_full[b], (c >> 1) & 1);
       tc_fence_after();
+      FFN_TRACE(4 + c);
       const uint32_t base = tmem + lane_off + TM_D1 + uint32_t(b) * HC;
       const float* bias = p.b1 + hbase + c * HC;   // warp-uniform addresses: broadcast loads, L1-resident
 #pragma unroll 1
@@ -211,66 +333,146 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       mbar_arrive(&h_ready[b]);
     }
-    // ---- Y partial -> shared memory as [column group of 4][row] float4 (conflict-free for thread = row)
-    mbar_wait(y_full, 0);        // every MMA has completed: the t tile and the W1 ring are dead
+    // ---- Y partial: PUSHED to the owners.  Columns [64 o, 64 o + 64) go into CTA o's shared memory, region [this rank], as
+    //      [column group of 4][row] float4 (remote stores are fire-and-forget; the first version PULLED with 64 dependent
+    //      distributed-shared-memory loads per thread, ~200 cycles each: 45 % of the kernel's stall samples in ncu)
+    FFN_TRACE(8);
+    mbar_wait(y_full, 0);        // every MMA of THIS CTA has completed ...
     tc_fence_after();
-    float4* dump = reinterpret_cast<float4*>(smem);
+    FFN_TRACE(9);
+  }
+  cluster_sync_all();            // ... and of every peer: their t tiles / W1 rings (the landing zone) are dead too
+  FFN_TRACE(10);
+  if (warp >= 2) {
+    const int q = warp & 3;
+    const int rl = q * 32 + lane;
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+    const uint32_t my = smem_u32(smem);
 #pragma unroll 1
     for (int k = 0; k < C / 32; ++k) {
       uint32_t r[32];
       tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+      const uint32_t dst = mapa_u32(my, (uint32_t)(k >> 1)) + uint32_t((((int)rank * 16 + (k & 1) * 8) * BM + rl) * 16);
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        dump[(k * 8 + i) * BM + rl] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                                  __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        st_dsmem_f4(dst + i * (BM * 16), __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
     }
   }
+  FFN_TRACE(11);
   tc_fence_before();
-  cluster_sync_all();            // all four partial tiles are in shared memory
+  cluster_sync_all();            // all four partial slices of this CTA's 64 columns are in ITS shared memory
+  FFN_TRACE(12);
+  float4 yv[16];                 // BACK: this thread's 64 new values of its row
+  float st_sum = 0.f, st_ss = 0.f;
   if (warp >= 2) {
     // CTA r reduces output columns [64 r, 64 r + 64) over the four CTAs in rank order (deterministic), adds b2 and the
     // residual, and writes x.  thread = row: 16 float4 column groups.
     const int q = warp & 3;
     const int rl = q * 32 + lane;
     const int row = m0 + rl;
-    const uint32_t my = smem_u32(smem);
-    uint32_t peer[CL];
-#pragma unroll
-    for (int r = 0; r < CL; ++r) peer[r] = mapa_u32(my, (uint32_t)r);
-    float* xr = p.x + (long long)bz * p.x_bstride + (long long)row * C + rank * 64;
+    const float4* part = reinterpret_cast<const float4*>(smem);   // [source rank][column group 0..15][row]
+    const long long xoff = (long long)bz * p.x_bstride + (long long)row * C + rank * 64;
+    const float* xres = (FRONT ? p.x_out : p.x_in) + xoff;   // FRONT: the x_mid slice parked in x_out by this thread
+    float* xr = p.x_out + xoff;
     const float* b2 = p.b2 + rank * 64;
-#pragma unroll 1
+#pragma unroll
     for (int g = 0; g < 16; g += 4) {
-      float4 acc[4], xin[4];
+      float4 v[4][CL], xin[4], bb[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const uint32_t off = uint32_t(((rank * 16 + g + i) * BM + rl) * 16);
-        acc[i] = ld_dsmem_f4(peer[0] + off);
-#pragma unroll
-        for (int r = 1; r < CL; ++r) {
-          const float4 v = ld_dsmem_f4(peer[r] + off);
-          acc[i].x += v.x; acc[i].y += v.y; acc[i].z += v.z; acc[i].w += v.w;
-        }
-        if (row < p.M) xin[i] = *reinterpret_cast<const float4*>(xr + (g + i) * 4);
+        xin[i] = row < p.M ? *reinterpret_cast<const float4*>(xres + (g + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        bb[i] = __ldg(reinterpret_cast<const float4*>(b2 + (g + i) * 4));
       }
-      if (row < p.M) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float4 bb = *reinterpret_cast<const float4*>(b2 + (g + i) * 4);
-          *reinterpret_cast<float4*>(xr + (g + i) * 4) = make_float4(acc[i].x + bb.x + xin[i].x, acc[i].y + bb.y + xin[i].y,
-                                                                     acc[i].z + bb.z + xin[i].z, acc[i].w + bb.w + xin[i].w);
+      for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int r = 0; r < CL; ++r) v[i][r] = part[(r * 16 + g + i) * BM + rl];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 acc = v[i][0];                 // fixed rank order: bitwise deterministic
+#pragma unroll
+        for (int r = 1; r < CL; ++r) { acc.x += v[i][r].x; acc.y += v[i][r].y; acc.z += v[i][r].z; acc.w += v[i][r].w; }
+        const float4 y = make_float4(acc.x + bb[i].x + xin[i].x, acc.y + bb[i].y + xin[i].y, acc.z + bb[i].z + xin[i].z,
+                                     acc.w + bb[i].w + xin[i].w);
+        if (row < p.M) *reinterpret_cast<float4*>(xr + (g + i) * 4) = y;
+        if (BACK) {
+          yv[g + i] = y;
+          st_sum += (y.x + y.y) + (y.z + y.w);
+          st_ss += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+        }
+      }
+    }
+    if (BACK) reinterpret_cast<float2*>(sW2)[rl] = make_float2(st_sum, st_ss);   // the W2 ring is dead by now
+  }
+  FFN_TRACE(13);
+  if (BACK) {
+    cluster_sync_all();          // every CTA's per-row partial statistics are in its shared memory
+    if (warp >= 2) {
+      const int q = warp & 3;
+      const int rl = q * 32 + lane;
+      const int row = m0 + rl;
+      const uint32_t mine = smem_u32(sW2) + rl * 8;
+      float2 part[CL];
+#pragma unroll
+      for (int r = 0; r < CL; ++r) part[r] = ld_dsmem_f2(mapa_u32(mine, (uint32_t)r));
+      float sum = 0.f, ss = 0.f;
+#pragma unroll
+      for (int r = 0; r < CL; ++r) { sum += part[r].x; ss += part[r].y; }   // same order in every CTA: identical statistics
+      const float mean = sum * (1.0f / C);
+      const float rstd = rsqrtf(fmaxf(ss * (1.0f / C) - mean * mean, 0.f) + p.ln2_eps);
+      if (row < p.M) {
+        const float* w = p.ln2_w + rank * 64;
+        const float* bb = p.ln2_b + rank * 64;
+        const long long toff = (long long)bz * p.t_out_sb + (long long)row * p.t_out_st + rank * 64;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 4 * i)), w1 = __ldg(reinterpret_cast<const float4*>(w + 4 * i + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + 4 * i)), b1 = __ldg(reinterpret_cast<const float4*>(bb + 4 * i + 4));
+          float o[8] = {(yv[i].x - mean) * rstd * w0.x + b0.x, (yv[i].y - mean) * rstd * w0.y + b0.y,
+                        (yv[i].z - mean) * rstd * w0.z + b0.z, (yv[i].w - mean) * rstd * w0.w + b0.w,
+                        (yv[i + 1].x - mean) * rstd * w1.x + b1.x, (yv[i + 1].y - mean) * rstd * w1.y + b1.y,
+                        (yv[i + 1].z - mean) * rstd * w1.z + b1.z, (yv[i + 1].w - mean) * rstd * w1.w + b1.w};
+          if (p.t_out_bf16) {
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.t_out) + toff + 4 * i) =
+                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          } else {
+            float* dst = reinterpret_cast<float*>(p.t_out) + toff + 4 * i;
+            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
         }
       }
     }
   }
-  cluster_sync_all();            // peers may still be reading this CTA's partial tile
+  FFN_TRACE(14);
+  cluster_sync_all();            // peers may still be reading this CTA's partial tile / statistics
+  FFN_TRACE(15);
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace
 
 int g_ffn_fused = 1;   // memory attention: 1 = this kernel, 0 = two GEMM launches (vls_set_tuning "ffn_fused")
+long long* g_ffn_trace = nullptr;   // dev-only: 16 int64 clock64 stamps (tools/trace_ffn.py)
+int g_tail_fused = 1;  // memory attention: 1 = out-proj + LN3 + FFN + next LN in one launch (needs ffn_fused), 0 = separate
+
+namespace {
+
+template <bool FRONT, bool BACK>
+int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW0, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
+                   const FfnParams& p, int B, cudaStream_t stream) {
+  static unsigned long long attr_set = 0;   // one flag word per instantiation
+  auto kern = ffn_fused_kernel<FRONT, BACK>;
+  if (first_use_on_device(&attr_set)) VLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+  VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, p));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+}  // namespace
 
 // x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2;  t bf16 [B][M][256] (row stride ldt), W1 bf16 [2048][256],
 // W2 bf16 [256][2048], b1 f32 [2048], b2 f32 [256], x f32 [B][M][256] contiguous rows.
@@ -282,14 +484,32 @@ int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const vo
   VLS_TRY(make_tmap_bf16(&tmA, t, C, M, B, ldt, t_bstride, BM));
   VLS_TRY(make_tmap_bf16(&tmW1, w1, C, FF, 1, C, (long long)FF * C, HC));
   VLS_TRY(make_tmap_bf16(&tmW2, w2, FF, C, 1, FF, (long long)FF * C, C));
-  FfnParams p;
-  p.M = M; p.b1 = b1; p.b2 = b2; p.x = x; p.x_bstride = x_bstride;
-  static unsigned long long attr_set = 0;
-  if (first_use_on_device(&attr_set))
-    VLS_CUDA(cudaFuncSetAttribute(ffn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  VLS_CUDA(launch_k(ffn_fused_kernel, dim3(CL, (M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW1, tmW2, p));
-  VLS_POST_LAUNCH(1);
-  return 0;
+  FfnParams p = {};
+  p.M = M; p.b1 = b1; p.b2 = b2; p.x_in = x; p.x_out = x; p.x_bstride = x_bstride;
+  p.trace = g_ffn_trace;
+  return launch_variant<false, false>(tmA, tmA, tmW1, tmW2, p, B, stream);
+}
+
+// The tail of a memory-attention layer in one launch (see the file header):
+//   x_mid = x_in + ao W0^T + b0;  x_out = x_mid + FFN(LN3(x_mid));  t_out = LN_next(x_out)
+// ao bf16 [B][M][64] (the cross-attention output over the 64-d memory), W0 bf16 [256][64] = Wo Wv.  x_in != x_out.
+int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
+  VLS_REQUIRE(a.ao && a.w0 && a.b0 && a.ln_w && a.ln_b && a.w1 && a.b1 && a.w2 && a.b2 && a.x_in && a.x_out && a.ln2_w &&
+              a.ln2_b && a.t_out && a.B > 0 && a.M > 0, "layer_tail: bad arguments");
+  VLS_REQUIRE(a.x_in != a.x_out, "layer_tail: x_in and x_out must be different buffers");
+  VLS_REQUIRE(a.t_out_st % 8 == 0 && a.t_out_sb % 8 == 0, "layer_tail: output strides must be multiples of 8");
+  CUtensorMap tmA, tmW0, tmW1, tmW2;
+  VLS_TRY(make_tmap_bf16(&tmA, a.ao, 64, a.M, a.B, 64, (long long)a.M * 64, BM));
+  VLS_TRY(make_tmap_bf16(&tmW0, a.w0, 64, C, 1, 64, (long long)C * 64, C));
+  VLS_TRY(make_tmap_bf16(&tmW1, a.w1, C, FF, 1, C, (long long)FF * C, HC));
+  VLS_TRY(make_tmap_bf16(&tmW2, a.w2, FF, C, 1, FF, (long long)FF * C, C));
+  FfnParams p = {};
+  p.M = a.M; p.b1 = a.b1; p.b2 = a.b2; p.x_in = a.x_in; p.x_out = a.x_out; p.x_bstride = (long long)a.M * C;
+  p.b0 = a.b0; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_eps = a.ln_eps;
+  p.ln2_w = a.ln2_w; p.ln2_b = a.ln2_b; p.ln2_eps = a.ln2_eps;
+  p.t_out = a.t_out; p.t_out_bf16 = a.t_out_bf16; p.t_out_st = a.t_out_st; p.t_out_sb = a.t_out_sb;
+  p.trace = g_ffn_trace;
+  return launch_variant<true, true>(tmA, tmW0, tmW1, tmW2, p, a.B, stream);
 }
 
 }  // namespace vls

@@ -65,6 +65,22 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream);
 int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const void* w1, const float* b1, const void* w2,
                      const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream);
 extern int g_ffn_fused;
+extern int g_tail_fused;
+extern long long* g_ffn_trace;
+// x_mid = x_in + ao W0^T + b0;  x_out = x_mid + FFN(LN(x_mid));  t_out = LN2(x_out)   -- one cluster kernel
+struct LayerTailArgs {
+  const void* ao = nullptr;      // bf16 [B][M][64]
+  const void* w0 = nullptr;      // bf16 [256][64]
+  const float* b0 = nullptr;
+  const float* ln_w = nullptr; const float* ln_b = nullptr; float ln_eps = 1e-5f;
+  const void* w1 = nullptr; const float* b1 = nullptr;   // [2048][256]
+  const void* w2 = nullptr; const float* b2 = nullptr;   // [256][2048]
+  const float* x_in = nullptr; float* x_out = nullptr;   // f32 [B][M][256], different buffers
+  const float* ln2_w = nullptr; const float* ln2_b = nullptr; float ln2_eps = 1e-5f;
+  void* t_out = nullptr; int t_out_bf16 = 1; long long t_out_st = 256, t_out_sb = 0;   // (b,row,c) at b*sb + row*st + c
+  int B = 1, M = 0;
+};
+int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- connected components (cc.cu)
 size_t cc_workspace_bytes(int n, int h, int w, bool fill);

@@ -37,7 +37,7 @@ extern "C" {
 static size_t mem_attn_ws(int B, int Nq, int Nk, int L) {
   const long long ldv = rup(Nk, 64), ldvs = rup(Nq, 64);
   size_t n = 0;
-  n += align256((size_t)B * Nq * C * 4);            // x
+  n += 2 * align256((size_t)B * Nq * C * 4);        // x (two buffers: the fused layer tail reads one and writes the other)
   n += align256((size_t)B * Nq * C * 2);            // t
   n += align256((size_t)B * Nq * 2 * C * 2);        // qk
   n += 2 * align256((size_t)B * Nk * CM * 2);       // mem, mempos
@@ -74,6 +74,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   Workspace ws(workspace, workspace_bytes);
   const long long ldv = rup(Nk, 64), ldvs = rup(Nq, 64);
   float* x = (float*)ws.take((size_t)B * Nq * C * 4);
+  float* x_alt = (float*)ws.take((size_t)B * Nq * C * 4);
   void* t = ws.take((size_t)B * Nq * C * 2);
   char* qk = (char*)ws.take((size_t)B * Nq * 2 * C * 2);
   void* mem = ws.take((size_t)B * Nk * CM * 2);
@@ -86,7 +87,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits(B, Nq, Nk);
   const size_t a1 = attn_workspace_bytes(B, Nq, s_self, C), a2 = attn_workspace_bytes(B, Nq, s_cross, CM);
   char* aws = (char*)ws.take(a1 > a2 ? a1 : a2);
-  VLS_REQUIRE(x && t && qk && mem && mempos && kc_all && memT && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
+  VLS_REQUIRE(x && x_alt && t && qk && mem && mempos && kc_all && memT && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
               "mem_attn: workspace carve failed");
 
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
@@ -134,10 +135,12 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     return launch_attention(a, st);
   };
 
+  const bool tail_fused = g_ffn_fused && g_tail_fused;
+  bool have_t = false, out_done = false;   // tail_fused: the previous layer's tail kernel already produced t = LN1(x) / the output
   for (int l = 0; l < L; ++l) {
     const vls_mem_attn_layer& Lw = w->layers[l];
     // ---- self attention (memory_attention.py:58-64): q = k = v = LN1(x); RoPE on q and k
-    VLS_TRY(launch_ln256(x, B, Nq, Lw.n1_w, Lw.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
+    if (!have_t) VLS_TRY(launch_ln256(x, B, Nq, Lw.n1_w, Lw.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.sa_qk_w, Nq, 2 * C, C, B, Lw.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
@@ -174,6 +177,27 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, mem, CM, (long long)Nk * CM, CM, 1, Nk, s_cross));
     else
       VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, memT, ldv, (long long)CM * ldv, CM, 0, Nk, s_cross));
+    if (tail_fused) {
+      // ---- the rest of the layer in ONE cluster kernel (ffn_fused.cu): folded out-projection + residual, LayerNorm3, FFN
+      //      + residual, and the LayerNorm that follows (next layer's norm1, or the final norm straight into `out`)
+      LayerTailArgs a;
+      a.ao = ao; a.w0 = Lw.ca_ov_w; a.b0 = Lw.ca_ov_b;
+      a.ln_w = Lw.n3_w; a.ln_b = Lw.n3_b; a.ln_eps = LN_EPS;
+      a.w1 = Lw.l1_w; a.b1 = Lw.l1_b; a.w2 = Lw.l2_w; a.b2 = Lw.l2_b;
+      a.x_in = x; a.x_out = x_alt; a.B = B; a.M = Nq; a.ln2_eps = LN_EPS;
+      if (l + 1 < L) {
+        a.ln2_w = w->layers[l + 1].n1_w; a.ln2_b = w->layers[l + 1].n1_b;
+        a.t_out = t; a.t_out_bf16 = 1; a.t_out_st = C; a.t_out_sb = (long long)Nq * C;
+      } else {
+        a.ln2_w = w->norm_w; a.ln2_b = w->norm_b;
+        a.t_out = out; a.t_out_bf16 = out_dtype == VLS_BF16; a.t_out_st = out_st; a.t_out_sb = out_sb;
+        out_done = true;
+      }
+      VLS_TRY(launch_layer_tail(a, st));
+      float* tmp = x; x = x_alt; x_alt = tmp;
+      have_t = true;
+      continue;
+    }
     {   // x += (P mem) (Wo Wv)^T + (Wo bv + bo): the folded value/output projection, K = 64
       GemmArgs g = lin(ao, CM, (long long)Nq * CM, Lw.ca_ov_w, Nq, C, CM, B, Lw.ca_ov_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
@@ -192,6 +216,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g2, st));
     }
   }
+  if (out_done) return 0;
   if (out_dtype == VLS_BF16)
     return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, nullptr, 0, 0, out, out_sb, out_st, st);
   return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, (float*)out, out_sb, out_st, nullptr, 0, 0, st);

@@ -33,8 +33,56 @@ class SegmentationHeadSAM2(nn.Module):
         y = ops.linear_f32(seg_tokens.float(), self._w[0], self._w[1])           # [M, Q*256]
         return y.reshape(-1, self.n_seg_queries, 256).reshape(-1, 1, 256)
 
+    # ------------------------------------------------------------------ reference entry point
+    @property
+    def has_image_encoder(self):
+        return getattr(self.sam2, "image_encoder", None) is not None
+
+    def encode_video_frames(self, video_frames):
+        """[T,3,1024,1024] RGB in [0,1] -> (backbone_feats [T,256,64,64] WITHOUT no_mem_embed, [feat_s0, feat_s1])
+        through the injected image encoder (sam2.py:34-47; the encoder itself is SURVEY row f-4)."""
+        if not self.has_image_encoder:
+            raise RuntimeError("this SAM2 model was built without an image encoder: pass backbone_features=[(feats, "
+                               "[feat_s0, feat_s1]), ...] to forward(), or build the model with one")
+        mean = torch.tensor([0.485, 0.456, 0.406], device=video_frames.device)[None, :, None, None]
+        std = torch.tensor([0.229, 0.224, 0.225], device=video_frames.device)[None, :, None, None]
+        out = self.sam2.forward_image((video_frames.float() - mean) / std)       # conv_s0 / conv_s1 already applied
+        fpn = out["backbone_fpn"]
+        return fpn[2], [fpn[0], fpn[1]]
+
     @torch.inference_mode()
-    def decode(self, backbone_feats, high_res_feats, seg_tokens, out_size=None):
+    def forward(self, video_frames, seg_tokens, seg_meta, resize_to_original_dims, **kwargs):
+        """SegmentationHeadSAM2.forward (llava/model/seg_head/sam2.py:49-131), same arguments and result:
+        video_frames: list (batch) of [T,3,H,W] RGB tensors in [0,1]; seg_tokens: list of [M,n_token_dims] `[SEG]` hidden
+        states; seg_meta: list of dicts with `padding`, `resized_image_size`, `orig_image_size`.
+        Returns a list of [M,T,H',W'] mask logits (padding removed; resized to the original size if asked).
+        Extra keyword `backbone_features`: list of (backbone_feats [T,256,64,64], [feat_s0, feat_s1]) per sample, which
+        bypasses the image encoder (precomputed features)."""
+        pre = kwargs.get("backbone_features")
+        outs = []
+        for i, (tok, meta) in enumerate(zip(seg_tokens, seg_meta)):
+            feats, high = pre[i] if pre is not None else self.encode_video_frames(video_frames[i])
+            masks = self.decode(feats, high, tok, reduce_queries=False)              # [M*Q,T,256,256]
+            masks = self.postprocess_masks(masks, meta, resize_to_original_dims)     # per query, as the reference (:116-120)
+            masks = masks.reshape(-1, self.n_seg_queries, *masks.shape[1:])
+            outs.append(masks.max(1).values)                                         # max over the Q queries AFTER the resize (:127-128)
+        return outs
+
+    def postprocess_masks(self, masks, meta_dict, resize_to_original_dims):
+        """Up-sample to the 1024^2 model input, remove the padding, optionally resize to the original image size
+        (sam2.py:133-182).  masks: [M,T,h,w] logits."""
+        masks = ops.resize_bilinear(masks.float(), (1024, 1024))
+        left, right, top, bottom = [int(p) for p in meta_dict["padding"]]            # F.pad order: last dim first
+        H, W = masks.shape[-2:]
+        masks = masks[..., top:H - bottom, left:W - right]
+        assert list(masks.shape[-2:]) == list(meta_dict["resized_image_size"]), \
+            f"Shape mismatch: {masks.shape}, {meta_dict['resized_image_size']}"
+        if not resize_to_original_dims:
+            return masks
+        return ops.resize_bilinear(masks.contiguous(), tuple(int(x) for x in meta_dict["orig_image_size"]))
+
+    @torch.inference_mode()
+    def decode(self, backbone_feats, high_res_feats, seg_tokens, out_size=None, reduce_queries=True):
         """backbone_feats [T,256,H,W] (WITHOUT no_mem_embed), high_res_feats ([T,32,4H,4W], [T,64,2H,2W]) already
         through conv_s0/conv_s1, seg_tokens [M,n_token_dims] -> mask logits [M,T,h,w] (sam2.py:96-131)."""
         m = self.sam2
@@ -48,15 +96,19 @@ class SegmentationHeadSAM2(nn.Module):
         rows = backbone_feats.flatten(2).permute(2, 0, 1)                          # [HW,T,256]
         feats = ops.add_rowvec(rows, m.no_mem_embed.detach().reshape(-1))          # + no_mem_embed (sam2.py:44)
         feats = feats.permute(1, 2, 0).reshape(T, 256, H, W)
+        # ONE decoder call per prompt with the T frames as the batch (the reference loops over frames and batches the
+        # prompts, sam2.py:103-114: T launches chains of ~60 small kernels each; here the image-side GEMMs see T*4096 rows)
         out = []
-        for t in range(T):
+        for n_i in range(n):
             masks, _, _, _ = m.sam_mask_decoder(
-                image_embeddings=feats[t:t + 1], image_pe=image_pe, sparse_prompt_embeddings=sparse,
-                dense_prompt_embeddings=dense, multimask_output=False, repeat_image=True,
-                high_res_features=[high_res_feats[0][t:t + 1], high_res_feats[1][t:t + 1]])
+                image_embeddings=feats, image_pe=image_pe, sparse_prompt_embeddings=sparse[n_i:n_i + 1].expand(T, -1, -1).contiguous(),
+                dense_prompt_embeddings=dense[:1].expand(T, -1, -1, -1), multimask_output=False, repeat_image=False,
+                high_res_features=[high_res_feats[0], high_res_feats[1]])             # [T,1,h,w]
             if out_size is not None:
                 masks = ops.resize_bilinear(masks, out_size)
-            out.append(masks)
-        masks = torch.cat(out, 1)                                                  # [M*Q,T,h,w]
+            out.append(masks.transpose(0, 1))                                          # [1,T,h,w]
+        masks = torch.cat(out, 0)                                                  # [M*Q,T,h,w]
+        if not reduce_queries:
+            return masks
         masks = masks.reshape(-1, self.n_seg_queries, *masks.shape[1:])
         return masks.max(1).values                                                 # max over the Q queries (sam2.py:127-128)

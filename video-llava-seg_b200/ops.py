@@ -99,6 +99,20 @@ def ffn_fused(t, w1, b1, w2, b2, x):
     return x
 
 
+def mem_attn_layer_tail(ao, w0, b0, ln_w, ln_b, w1, b1, w2, b2, x_in, ln2_w, ln2_b, out_dtype=torch.bfloat16, eps=1e-5):
+    """x_mid = x_in + ao @ w0^T + b0; x_out = x_mid + relu(LN(x_mid) @ w1^T + b1) @ w2^T + b2; t = LN2(x_out).
+    ao [B,M,64] bf16, w0 [256,64] bf16, x_in [B,M,256] f32.  Returns (x_out f32, t)."""
+    _lib.require_cuda(ao, w0, b0, ln_w, ln_b, w1, b1, w2, b2, x_in, ln2_w, ln2_b)
+    B, M, _ = ao.shape
+    assert ao.is_contiguous() and x_in.is_contiguous() and x_in.dtype == torch.float32
+    x_out = torch.empty_like(x_in)
+    t = torch.empty((B, M, 256), device=ao.device, dtype=out_dtype)
+    check(lib().vls_mem_attn_layer_tail(ptr(ao), ptr(w0), ptr(b0), ptr(ln_w), ptr(ln_b), eps, ptr(w1), ptr(b1), ptr(w2), ptr(b2),
+                                        ptr(x_in), ptr(x_out), ptr(ln2_w), ptr(ln2_b), eps, ptr(t), _lib.VLS_DTYPE[out_dtype],
+                                        t.stride(1), t.stride(0), B, M, stream()), "vls_mem_attn_layer_tail")
+    return x_out, t
+
+
 def resize_bilinear(x, size):
     """F.interpolate(x, size, mode="bilinear", align_corners=False) for f32 [N,C,h,w]."""
     _lib.require_cuda(x)
