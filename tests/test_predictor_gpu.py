@@ -253,6 +253,13 @@ def test_api_scenarios_match_reference(predictor, scenario):
                 # 3e-2 of each other, golden_cases.api_scenarios) are excluded from the comparison
                 f = k.rsplit("_f", 1)[1] if "_f" in k else "0"
                 keep = ~np.unpackbits(gold[f"nonoverlap_amb{f}"], axis=1).astype(bool)[:, :a.shape[1]]
+                if f != "0":
+                    # propagated frames: with random-init weights the two objects' masks converge, most foreground pixels
+                    # are ties and what is left is too small for an IoU -- require pixel agreement outside the ties
+                    agree = (a == b)[np.broadcast_to(keep, a.shape)].mean()
+                    print(f"{k}: agreement outside ties {agree:.5f} ({keep.mean():.3f} of the pixels)")
+                    assert agree >= 0.999, (k, agree)
+                    continue
                 a, b = a & keep, b & keep
             union = (a | b).sum()
             iou = (a & b).sum() / union if union else 1.0

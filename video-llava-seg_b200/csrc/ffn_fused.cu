@@ -47,7 +47,14 @@ constexpr int SMEM_BYTES = A_BYTES + W1_SLOTS * W1_SLOT_BYTES + W2_SLOTS * W2_SL
 static_assert(SMEM_BYTES <= 232448, "exceeds the 227 KB of shared memory a CTA can opt into");
 constexpr int THREADS = 192;  // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue (thread = row)
 constexpr uint32_t TM_Y = 0, TM_D1 = 256;
-static_assert(BM * C * 4 <= A_BYTES + W1_SLOTS * W1_SLOT_BYTES, "Y dump must fit into the t tile + W1 ring");
+// landing zone of the cluster reduce in every CTA: [source rank][column group of 4][row] float4 with one float4 of padding
+// per column group: the PUSH (thread = row, fixed column group) writes 512 contiguous bytes per warp -- remote stores
+// that scatter 32 x 16 B cost 2.2 x as much (measured) -- and the (row, column group) reads of the reduce hit 8 distinct
+// 16-byte bank groups per 8 lanes
+constexpr int SL_PITCH = BM * 16 + 16;            // bytes per column group of a slice
+constexpr int SL_BYTES = 16 * SL_PITCH;           // one source rank's 64-column slice
+static_assert(CL * SL_BYTES <= A_BYTES + W1_SLOTS * W1_SLOT_BYTES, "reduce landing zone must fit into the t tile + W1 ring");
+static_assert(BM * C * 4 <= A_BYTES + 4 * W1_SLOT_BYTES, "FRONT: the f32 x tile is staged in the t tile + 4 W1 slots");
 
 struct FfnParams {
   int M;                      // rows per batch element
@@ -95,7 +102,8 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
 template <bool FRONT, bool BACK>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2, const FfnParams p) {
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
+                 const __grid_constant__ CUtensorMap tmX, const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in every CTA of the cluster, so this alignment is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -114,7 +122,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* g0_full = y_full + 1;          // FRONT: ao tile + folded out-proj weight have landed
   uint64_t* g0_done = g0_full + 1;         // FRONT: the out-proj MMAs have completed (x_mid partial in TMEM, W2 ring free)
   uint64_t* a_ready = g0_done + 1;         // FRONT: 128 epilogue threads have written t = LN(x_mid) into sA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + 1);
+  uint64_t* x_full = a_ready + 1;          // FRONT: the f32 residual tile has landed in its staging area (sA + 4 W1 slots)
+  uint64_t* x_free = x_full + 1;           // FRONT: ... and has been consumed: the W1 ring may be filled
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_free + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -132,8 +142,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(g0_full, 1);
     mbar_init(g0_done, 1);
     mbar_init(a_ready, 128);
+    mbar_init(x_full, 1);
+    mbar_init(x_free, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmW0);
+    if (FRONT) tma_prefetch_desc(&tmX);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -155,6 +168,11 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_expect_tx(g0_full, W2_SLOT_BYTES + BM * 128);
         tma_load_3d(sW2, &tmW0, g0_full, 0, 0, 0);
         tma_load_3d(sW2 + W2_SLOT_BYTES, &tmA, g0_full, 0, m0, bz);
+        // residual tile x_in[m0 : m0+128][0:256] f32 = 8 boxes of [128 rows x 32 floats] (128B-swizzled): coalesced and
+        // asynchronous (thread = row loads from global memory cost 12.6 k cycles in the first version of the prologue)
+        mbar_expect_tx(x_full, BM * C * 4);
+#pragma unroll
+        for (int kb = 0; kb < 8; ++kb) tma_load_3d(smem + kb * (BM * 128), &tmX, x_full, kb * 32, m0, bz);
       } else {
         mbar_expect_tx(a_full, A_BYTES);
 #pragma unroll
@@ -162,6 +180,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // panel streams in consumption order: chunk 0 W1 panels, [chunk c+1 W1 panels, chunk c W2 panels] ...
       int i1 = 0, i2 = 0;
+      if (FRONT) mbar_wait(x_free, 0);
       auto load_w1 = [&](int c) {
 #pragma unroll 1
         for (int kp = 0; kp < 4; ++kp, ++i1) {
@@ -251,9 +270,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // x_mid = x_in + ao (Wo Wv)^T + b0;  t = LN3(x_mid) -> sA (bf16, 128B-swizzled K-major panels)
       const int row = m0 + rl;
       const bool row_ok = row < p.M;
-      const float* xin = p.x_in + (long long)bz * p.x_bstride + (long long)row * C;
       float* xpark = p.x_out + (long long)bz * p.x_bstride + (long long)row * C;
       mbar_wait(g0_done, 0);
+      mbar_wait(x_full, 0);
       tc_fence_after();
       FFN_TRACE(1);
       float sum = 0.f, ss = 0.f;
@@ -261,10 +280,10 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int k = 0; k < C / 32; ++k) {
         uint32_t r[32];
         tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+        const uint8_t* xrow = smem + k * (BM * 128) + rl * 128;   // staged residual: box k, this thread's row
         float4 xv[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          xv[i] = row_ok ? *reinterpret_cast<const float4*>(xin + k * 32 + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xrow + ((i ^ (rl & 7)) << 4));
         tc_wait_ld();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -281,28 +300,33 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_st32(tmem + lane_off + TM_Y + k * 32, r);
       }
       tc_wait_st();
+      // every thread is done with the staged residual: pass 2 overwrites the first 64 KB of it (sA), the producer the rest
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) mbar_arrive(x_free);
       FFN_TRACE(2);
       const float mean = sum * (1.0f / C);
       const float rstd = rsqrtf(fmaxf(ss * (1.0f / C) - mean * mean, 0.f) + p.ln_eps);
-#pragma unroll 1
+#pragma unroll 2
       for (int k = 0; k < C / 32; ++k) {
         uint32_t r[32];
         tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+        float4 w4[8], b4[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          w4[i] = __ldg(reinterpret_cast<const float4*>(p.ln_w + k * 32 + 4 * i));
+          b4[i] = __ldg(reinterpret_cast<const float4*>(p.ln_b + k * 32 + 4 * i));
+        }
         tc_wait_ld();
         uint8_t* prow = sA + (k >> 1) * (BM * 128) + rl * 128;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t pk[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int cidx = k * 32 + j * 8 + 2 * e;
-            const float2 w = __ldg(reinterpret_cast<const float2*>(p.ln_w + cidx));
-            const float2 bb = __ldg(reinterpret_cast<const float2*>(p.ln_b + cidx));
-            pk[e] = pack_bf16x2((__uint_as_float(r[j * 8 + 2 * e]) - mean) * rstd * w.x + bb.x,
-                                (__uint_as_float(r[j * 8 + 2 * e + 1]) - mean) * rstd * w.y + bb.y);
-          }
+          const float4 wa = w4[2 * j], wb = w4[2 * j + 1], ba = b4[2 * j], bbv = b4[2 * j + 1];
+          const uint32_t p0 = pack_bf16x2((__uint_as_float(r[8 * j]) - mean) * rstd * wa.x + ba.x, (__uint_as_float(r[8 * j + 1]) - mean) * rstd * wa.y + ba.y);
+          const uint32_t p1 = pack_bf16x2((__uint_as_float(r[8 * j + 2]) - mean) * rstd * wa.z + ba.z, (__uint_as_float(r[8 * j + 3]) - mean) * rstd * wa.w + ba.w);
+          const uint32_t p2 = pack_bf16x2((__uint_as_float(r[8 * j + 4]) - mean) * rstd * wb.x + bbv.x, (__uint_as_float(r[8 * j + 5]) - mean) * rstd * wb.y + bbv.y);
+          const uint32_t p3 = pack_bf16x2((__uint_as_float(r[8 * j + 6]) - mean) * rstd * wb.z + bbv.z, (__uint_as_float(r[8 * j + 7]) - mean) * rstd * wb.w + bbv.w);
           const int c16 = (k & 1) * 4 + j;   // 16-byte chunk inside the 128-byte panel row, XOR-swizzled by the row
-          *reinterpret_cast<uint4*>(prow + ((c16 ^ (rl & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + ((c16 ^ (rl & 7)) << 4)) = make_uint4(p0, p1, p2, p3);
         }
       }
       fence_proxy_async();        // generic-proxy smem writes -> visible to the tensor core's async-proxy reads
@@ -352,97 +376,94 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int k = 0; k < C / 32; ++k) {
       uint32_t r[32];
       tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
-      const uint32_t dst = mapa_u32(my, (uint32_t)(k >> 1)) + uint32_t((((int)rank * 16 + (k & 1) * 8) * BM + rl) * 16);
+      const uint32_t dst = mapa_u32(my, (uint32_t)(k >> 1)) + uint32_t((int)rank * SL_BYTES + (k & 1) * 8 * SL_PITCH + rl * 16);
       tc_wait_ld();
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        st_dsmem_f4(dst + i * (BM * 16), __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                    __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+        st_dsmem_f4(dst + i * SL_PITCH, __uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                    __uint_as_float(r[4 * i + 3]));
     }
   }
   FFN_TRACE(11);
   tc_fence_before();
   cluster_sync_all();            // all four partial slices of this CTA's 64 columns are in ITS shared memory
   FFN_TRACE(12);
-  float4 yv[16];                 // BACK: this thread's 64 new values of its row
-  float st_sum = 0.f, st_ss = 0.f;
+  // ---- reduce: thread t owns column group cg = t % 16 (4 columns) of rows t / 16 + 8 j: a half-warp reads / writes 256
+  //      contiguous bytes of a row of x (thread = row made every global access a 16-byte gather at 1 KB stride)
+  float4 yv[16];                 // BACK: the new values (rows t/16 + 8j, column group t%16)
+  float2 stat[16];               // BACK: per-row partial (sum, sum of squares) of this CTA's 64 columns
   if (warp >= 2) {
-    // CTA r reduces output columns [64 r, 64 r + 64) over the four CTAs in rank order (deterministic), adds b2 and the
-    // residual, and writes x.  thread = row: 16 float4 column groups.
-    const int q = warp & 3;
-    const int rl = q * 32 + lane;
-    const int row = m0 + rl;
-    const float4* part = reinterpret_cast<const float4*>(smem);   // [source rank][column group 0..15][row]
-    const long long xoff = (long long)bz * p.x_bstride + (long long)row * C + rank * 64;
-    const float* xres = (FRONT ? p.x_out : p.x_in) + xoff;   // FRONT: the x_mid slice parked in x_out by this thread
-    float* xr = p.x_out + xoff;
-    const float* b2 = p.b2 + rank * 64;
+    const int et = threadIdx.x - 64;
+    const int cg = et & 15, rsub = et >> 4;
+    const long long xbase = (long long)bz * p.x_bstride + rank * 64 + cg * 4;
+    const float* xres = (FRONT ? p.x_out : p.x_in) + xbase;   // FRONT: the x_mid slice parked in x_out by the prologue
+    float* xr = p.x_out + xbase;
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + rank * 64 + cg * 4));
 #pragma unroll
-    for (int g = 0; g < 16; g += 4) {
-      float4 v[4][CL], xin[4], bb[4];
+    for (int j0 = 0; j0 < 16; j0 += 4) {
+      float4 v[4][CL], xin[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        xin[i] = row < p.M ? *reinterpret_cast<const float4*>(xres + (g + i) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        bb[i] = __ldg(reinterpret_cast<const float4*>(b2 + (g + i) * 4));
+        const int rl = rsub + 8 * (j0 + i);
+        xin[i] = (m0 + rl) < p.M ? *reinterpret_cast<const float4*>(xres + (long long)(m0 + rl) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < CL; ++r) v[i][r] = *reinterpret_cast<const float4*>(smem + r * SL_BYTES + cg * SL_PITCH + rl * 16);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-#pragma unroll
-        for (int r = 0; r < CL; ++r) v[i][r] = part[(r * 16 + g + i) * BM + rl];
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
+        const int rl = rsub + 8 * (j0 + i);
         float4 acc = v[i][0];                 // fixed rank order: bitwise deterministic
 #pragma unroll
         for (int r = 1; r < CL; ++r) { acc.x += v[i][r].x; acc.y += v[i][r].y; acc.z += v[i][r].z; acc.w += v[i][r].w; }
-        const float4 y = make_float4(acc.x + bb[i].x + xin[i].x, acc.y + bb[i].y + xin[i].y, acc.z + bb[i].z + xin[i].z,
-                                     acc.w + bb[i].w + xin[i].w);
-        if (row < p.M) *reinterpret_cast<float4*>(xr + (g + i) * 4) = y;
+        const float4 y = make_float4(acc.x + bb.x + xin[i].x, acc.y + bb.y + xin[i].y, acc.z + bb.z + xin[i].z, acc.w + bb.w + xin[i].w);
+        if ((m0 + rl) < p.M) *reinterpret_cast<float4*>(xr + (long long)(m0 + rl) * C) = y;
         if (BACK) {
-          yv[g + i] = y;
-          st_sum += (y.x + y.y) + (y.z + y.w);
-          st_ss += (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+          yv[j0 + i] = y;
+          float s1 = (y.x + y.y) + (y.z + y.w), s2 = (y.x * y.x + y.y * y.y) + (y.z * y.z + y.w * y.w);
+#pragma unroll
+          for (int o = 8; o > 0; o >>= 1) {   // the 16 lanes that share a row
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          stat[j0 + i] = make_float2(s1, s2);
         }
       }
     }
-    if (BACK) reinterpret_cast<float2*>(sW2)[rl] = make_float2(st_sum, st_ss);   // the W2 ring is dead by now
+    if (BACK) {
+      // lanes cg = 0..3 push this CTA's per-row statistics to CTA cg: stats[source rank][row] in the dead W2 ring
+      if (cg < CL) {
+        const uint32_t dst = mapa_u32(smem_u32(sW2), (uint32_t)cg) + uint32_t((int)rank * BM * 8);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(dst + uint32_t((rsub + 8 * j) * 8)), "f"(stat[j].x), "f"(stat[j].y) : "memory");
+      }
+    }
   }
   FFN_TRACE(13);
   if (BACK) {
-    cluster_sync_all();          // every CTA's per-row partial statistics are in its shared memory
+    cluster_sync_all();          // every CTA holds all four CTAs' per-row partial statistics
     if (warp >= 2) {
-      const int q = warp & 3;
-      const int rl = q * 32 + lane;
-      const int row = m0 + rl;
-      const uint32_t mine = smem_u32(sW2) + rl * 8;
-      float2 part[CL];
+      const int et = threadIdx.x - 64;
+      const int cg = et & 15, rsub = et >> 4;
+      const float2* stats = reinterpret_cast<const float2*>(sW2);
+      const float4 w = __ldg(reinterpret_cast<const float4*>(p.ln2_w + rank * 64 + cg * 4));
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.ln2_b + rank * 64 + cg * 4));
 #pragma unroll
-      for (int r = 0; r < CL; ++r) part[r] = ld_dsmem_f2(mapa_u32(mine, (uint32_t)r));
-      float sum = 0.f, ss = 0.f;
+      for (int j = 0; j < 16; ++j) {
+        const int rl = rsub + 8 * j;
+        float sum = 0.f, ss = 0.f;
 #pragma unroll
-      for (int r = 0; r < CL; ++r) { sum += part[r].x; ss += part[r].y; }   // same order in every CTA: identical statistics
-      const float mean = sum * (1.0f / C);
-      const float rstd = rsqrtf(fmaxf(ss * (1.0f / C) - mean * mean, 0.f) + p.ln2_eps);
-      if (row < p.M) {
-        const float* w = p.ln2_w + rank * 64;
-        const float* bb = p.ln2_b + rank * 64;
-        const long long toff = (long long)bz * p.t_out_sb + (long long)row * p.t_out_st + rank * 64;
-#pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-          const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + 4 * i)), w1 = __ldg(reinterpret_cast<const float4*>(w + 4 * i + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + 4 * i)), b1 = __ldg(reinterpret_cast<const float4*>(bb + 4 * i + 4));
-          float o[8] = {(yv[i].x - mean) * rstd * w0.x + b0.x, (yv[i].y - mean) * rstd * w0.y + b0.y,
-                        (yv[i].z - mean) * rstd * w0.z + b0.z, (yv[i].w - mean) * rstd * w0.w + b0.w,
-                        (yv[i + 1].x - mean) * rstd * w1.x + b1.x, (yv[i + 1].y - mean) * rstd * w1.y + b1.y,
-                        (yv[i + 1].z - mean) * rstd * w1.z + b1.z, (yv[i + 1].w - mean) * rstd * w1.w + b1.w};
-          if (p.t_out_bf16) {
-            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.t_out) + toff + 4 * i) =
-                make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
-          } else {
-            float* dst = reinterpret_cast<float*>(p.t_out) + toff + 4 * i;
-            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
+        for (int r = 0; r < CL; ++r) { const float2 q2 = stats[r * BM + rl]; sum += q2.x; ss += q2.y; }   // same order everywhere
+        const float mean = sum * (1.0f / C);
+        const float rstd = rsqrtf(fmaxf(ss * (1.0f / C) - mean * mean, 0.f) + p.ln2_eps);
+        if ((m0 + rl) < p.M) {
+          const float o0 = (yv[j].x - mean) * rstd * w.x + bb.x, o1 = (yv[j].y - mean) * rstd * w.y + bb.y;
+          const float o2 = (yv[j].z - mean) * rstd * w.z + bb.z, o3 = (yv[j].w - mean) * rstd * w.w + bb.w;
+          const long long toff = (long long)bz * p.t_out_sb + (long long)(m0 + rl) * p.t_out_st + rank * 64 + cg * 4;
+          if (p.t_out_bf16)
+            *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.t_out) + toff) = make_uint2(pack_bf16x2(o0, o1), pack_bf16x2(o2, o3));
+          else
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.t_out) + toff) = make_float4(o0, o1, o2, o3);
         }
       }
     }
@@ -463,11 +484,11 @@ namespace {
 
 template <bool FRONT, bool BACK>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW0, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   const FfnParams& p, int B, cudaStream_t stream) {
+                   const CUtensorMap& tmX, const FfnParams& p, int B, cudaStream_t stream) {
   static unsigned long long attr_set = 0;   // one flag word per instantiation
   auto kern = ffn_fused_kernel<FRONT, BACK>;
   if (first_use_on_device(&attr_set)) VLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, p));
+  VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, tmX, p));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -487,7 +508,7 @@ int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const vo
   FfnParams p = {};
   p.M = M; p.b1 = b1; p.b2 = b2; p.x_in = x; p.x_out = x; p.x_bstride = x_bstride;
   p.trace = g_ffn_trace;
-  return launch_variant<false, false>(tmA, tmA, tmW1, tmW2, p, B, stream);
+  return launch_variant<false, false>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
 }
 
 // The tail of a memory-attention layer in one launch (see the file header):
@@ -497,8 +518,9 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.ao && a.w0 && a.b0 && a.ln_w && a.ln_b && a.w1 && a.b1 && a.w2 && a.b2 && a.x_in && a.x_out && a.ln2_w &&
               a.ln2_b && a.t_out && a.B > 0 && a.M > 0, "layer_tail: bad arguments");
   VLS_REQUIRE(a.x_in != a.x_out, "layer_tail: x_in and x_out must be different buffers");
-  VLS_REQUIRE(a.t_out_st % 8 == 0 && a.t_out_sb % 8 == 0, "layer_tail: output strides must be multiples of 8");
-  CUtensorMap tmA, tmW0, tmW1, tmW2;
+  VLS_REQUIRE(a.t_out_st % 4 == 0 && a.t_out_sb % 4 == 0, "layer_tail: output strides must be multiples of 4");
+  CUtensorMap tmA, tmW0, tmW1, tmW2, tmX;
+  VLS_TRY(make_tmap_f32(&tmX, a.x_in, C, a.M, a.B, C, (long long)a.M * C, BM));
   VLS_TRY(make_tmap_bf16(&tmA, a.ao, 64, a.M, a.B, 64, (long long)a.M * 64, BM));
   VLS_TRY(make_tmap_bf16(&tmW0, a.w0, 64, C, 1, 64, (long long)C * 64, C));
   VLS_TRY(make_tmap_bf16(&tmW1, a.w1, C, FF, 1, C, (long long)FF * C, HC));
@@ -509,7 +531,7 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
   p.ln2_w = a.ln2_w; p.ln2_b = a.ln2_b; p.ln2_eps = a.ln2_eps;
   p.t_out = a.t_out; p.t_out_bf16 = a.t_out_bf16; p.t_out_st = a.t_out_st; p.t_out_sb = a.t_out_sb;
   p.trace = g_ffn_trace;
-  return launch_variant<true, true>(tmA, tmW0, tmW1, tmW2, p, a.B, stream);
+  return launch_variant<true, true>(tmA, tmW0, tmW1, tmW2, tmX, p, a.B, stream);
 }
 
 }  // namespace vls

@@ -163,4 +163,24 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
   return 0;
 }
 
+// f32 variant: box = (32 cols = 128 B, box_rows, 1), SWIZZLE_128B
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                  uint64_t batch_stride, uint32_t box_rows) {
+  std::call_once(g_encode_once, resolve_encode);
+  VLS_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  VLS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VLS_REQUIRE((row_stride * 4) % 16 == 0 && (batch <= 1 || (batch_stride * 4) % 16 == 0), "TMA strides must be multiples of 16 bytes");
+  VLS_REQUIRE(box_rows >= 1 && box_rows <= 256, "TMA box rows out of range");
+  if (batch < 1) batch = 1;
+  cuuint64_t gdim[3] = {cols, rows, batch};
+  cuuint64_t gstr[2] = {row_stride * 4, (batch > 1 ? batch_stride : rows * row_stride) * 4};
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VLS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace vls

@@ -97,6 +97,9 @@ int prof_collect(int slot, int* count, double* total_ms);
 int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch,
                    uint64_t row_stride, uint64_t batch_stride, uint32_t box_rows);
 
+int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                  uint64_t batch_stride, uint32_t box_rows);
+
 struct Workspace {  // bump allocator over a caller-owned device buffer
   char* base;
   size_t size, off;
