@@ -26,6 +26,15 @@ int vls_set_tuning(const char* key, int value) {
     g_attn_balanced = value != 0;
     return 0;
   }
+  if (std::string(key) == "attn_x2") {   // memory cross-attention: 1 = two query tiles per CTA (attn_x2.cu), 0 = attn_tc.cu
+    g_attn_x2 = value != 0;
+    return 0;
+  }
+  if (std::string(key) == "attn_x2_poly") {   // exponentials of every 4 score pairs computed on the FMA pipe (rest: MUFU)
+    VLS_REQUIRE(value >= 0 && value <= 3, "attn_x2_poly must be 0..3");
+    g_attn_x2_poly = value;
+    return 0;
+  }
   if (std::string(key) == "attn_v_rows") {   // memory cross-attention value operand: 1 = bank rows (MN-major), 0 = transposed copy
     g_attn_v_rows = value != 0;
     return 0;
@@ -76,22 +85,25 @@ int vls_gemm_bf16(const vls_gemm_desc* d, vls_stream_t stream) {
 }
 
 // splits > 0: fixed KV splits; 0: automatic; -1: force the balanced ("stream-K") mode (tests / tuning)
-static int resolve_splits(int B, int Nq, int Nk, int splits) {
+static int resolve_splits(int B, int Nq, int Nk, int splits, int dv = 256, int v_rows = 0) {
   if (splits == -1) return 0;
-  return splits > 0 ? splits : attn_pick_splits(B, Nq, Nk);
+  return splits > 0 ? splits : attn_pick_splits_for(B, Nq, Nk, dv, v_rows);
 }
 size_t vls_attention_workspace_bytes(int B, int Nq, int Nk, int splits) {
   return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits), 256);
 }
 size_t vls_attention_qk256_workspace_bytes(int B, int Nq, int Nk, int dv, int splits) {
-  return attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits), dv);
+  // sized for either picker (v_rows is not known here): the two-query-tile kernel may use more splits
+  const size_t a = attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits), dv);
+  const size_t b = dv == 64 ? attn_workspace_bytes(B, Nq, resolve_splits(B, Nq, Nk, splits, dv, 1), dv) : 0;
+  return a > b ? a : b;
 }
 
 int vls_attention_qk256(const void* Q, long long ldq, long long q_bstride, const void* K, long long ldk,
                         long long k_bstride, const void* V, long long ldv, long long v_bstride, int dv, int v_rows, int B,
                         int Nq, int Nk, float scale, int splits, void* O, long long ldo, long long o_bstride,
                         void* workspace, size_t workspace_bytes, vls_stream_t stream) {
-  splits = resolve_splits(B, Nq, Nk, splits);
+  splits = resolve_splits(B, Nq, Nk, splits, dv, v_rows);
   AttnArgs a;
   a.Q = Q; a.ldq = ldq; a.q_bstride = q_bstride;
   a.K = K; a.ldk = ldk; a.k_bstride = k_bstride;

@@ -187,7 +187,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   pdl_enter();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       int jg = 0;   // tiles issued so far over all segments: barrier phases keep counting
       for (int sg = 0; sg < nseg; ++sg) {
         const Seg S = segs[sg];
@@ -219,7 +219,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   } else if (warp == 10) {
     // V^T producer on its own warp: with one stage per operand an in-order K,V,K,V producer would hold K(j+1)
     // back until PV(j-1) has released the V buffer
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       int jg = 0;
       for (int sg = 0; sg < nseg; ++sg) {
         const Seg S = segs[sg];
@@ -247,7 +247,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       constexpr uint32_t idesc_s = make_idesc_bf16(BM, BN);
       constexpr uint32_t idesc_pv = make_idesc_bf16(BM, DV) | (VMN ? (1u << 16) : 0u);   // bit 16: B is MN-major
       const uint32_t q_addr = smem_u32(sQ);
@@ -601,6 +601,11 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   return s;
 }
 
+int attn_pick_splits_for(int B, int Nq, int Nk, int dv, int v_rows) {
+  if (dv == 64 && v_rows && g_attn_x2) return attn_x2_pick_splits(B, Nq, Nk);
+  return attn_pick_splits(B, Nq, Nk);
+}
+
 namespace {
 
 template <int CL, bool BAL, int DV, bool VMN>
@@ -677,7 +682,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.ldo % 8 == 0 && a.ldvt % 8 == 0, "attention: ldo / ldv must be multiples of 8");
   const int nt = (a.Nk + BN - 1) / BN;
   VLS_REQUIRE(a.splits <= nt, "attention: more KV splits (%d) than KV tiles (%d)", a.splits, nt);
-  VLS_REQUIRE(a.splits <= MAX_PARTS, "attention: at most %d KV splits", MAX_PARTS);
+  const bool x2 = a.dv == 64 && a.v_rows && g_attn_x2 && a.splits >= 1;
+  VLS_REQUIRE(x2 || a.splits <= MAX_PARTS, "attention: at most %d KV splits", MAX_PARTS);
   VLS_REQUIRE(a.splits == 1 || (a.part_o && a.part_ml), "attention: split workspace missing");
   const int qtiles = (a.Nq + BM - 1) / BM;
   const bool bal = a.splits == 0;
@@ -694,6 +700,12 @@ int launch_attention(const AttnArgs& a, cudaStream_t stream) {
   const int slot = a.Nk > a.Nq ? PROF_ATTN_CROSS : PROF_ATTN_SELF;
   prof_begin(slot, stream);
   int rc;
+  if (a.dv == 64 && a.v_rows && g_attn_x2 && a.splits >= 1) {   // two query tiles per CTA, fixed KV splits (attn_x2.cu)
+    rc = launch_attention_x2(a, stream);
+    if (rc != 0) return rc;
+    prof_end(slot, stream);
+    return 0;
+  }
   if (a.dv == 64 && a.v_rows)
     rc = bal ? launch_variant<1, true, 64, true>(a, p, qtiles, stream) : launch_variant<1, false, 64, true>(a, p, qtiles, stream);
   else if (a.dv == 64)

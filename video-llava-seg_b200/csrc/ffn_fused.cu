@@ -163,7 +163,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   FFN_TRACE(0);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       if (FRONT) {   // staged in the (still idle) W2 ring: slot 0 = folded out-proj weight [256 x 64], slot 1 = ao tile [128 x 64]
         mbar_expect_tx(g0_full, W2_SLOT_BYTES + BM * 128);
         tma_load_3d(sW2, &tmW0, g0_full, 0, 0, 0);
@@ -207,7 +207,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       constexpr uint32_t idesc1 = make_idesc_bf16(BM, HC);
       constexpr uint32_t idesc2 = make_idesc_bf16(BM, C);
       const uint32_t a_addr = smem_u32(sA);

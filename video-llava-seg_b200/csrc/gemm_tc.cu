@@ -97,7 +97,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   pdl_enter();   // barriers, TMEM and descriptor prefetch above overlap the previous kernel's tail; global memory from here on
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       const int az = (bz / e.a_div) % e.a_mod;
       const int wz = (bz / e.w_div) % e.w_mod;
       for (int kb = 0; kb < kblocks; ++kb) {
@@ -111,7 +111,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
       for (int kb = 0; kb < kblocks; ++kb) {
         const int s = kb % STAGES;

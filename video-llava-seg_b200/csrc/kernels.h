@@ -58,7 +58,14 @@ extern long long* g_attn_trace;
 size_t attn_workspace_bytes(int B, int Nq, int splits, int dv = 256);
 size_t attn_part_ml_offset(int B, int Nq, int splits, int dv = 256);
 int attn_pick_splits(int B, int Nq, int Nk);
+// picker for a given value operand: the two-query-tile kernel (attn_x2.cu) serves dv == 64 with V as rows when g_attn_x2
+int attn_pick_splits_for(int B, int Nq, int Nk, int dv, int v_rows);
 int launch_attention(const AttnArgs& a, cudaStream_t stream);
+// memory cross-attention with two query tiles per CTA (attn_x2.cu): dv == 64, v_rows, 1..16 fixed KV splits
+extern int g_attn_x2;
+extern int g_attn_x2_poly;
+int attn_x2_pick_splits(int B, int Nq, int Nk);
+int launch_attention_x2(const AttnArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- fused FFN (ffn_fused.cu)
 // x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2 in one cluster kernel (hidden activations stay in TMEM).

@@ -46,9 +46,10 @@ static size_t mem_attn_ws(int B, int Nq, int Nk, int L) {
   n += align256((size_t)B * C * ldvs * 2);          // transposed self-attention values
   n += align256((size_t)B * Nq * C * 2);            // ao
   n += align256((size_t)B * Nq * FFN * 2);          // h
-  const int s1 = attn_pick_splits(B, Nq, Nq), s2 = attn_pick_splits(B, Nq, Nk);
+  const int s1 = attn_pick_splits(B, Nq, Nq), s2 = attn_pick_splits(B, Nq, Nk), s3 = attn_x2_pick_splits(B, Nq, Nk);
   const size_t a1 = attn_workspace_bytes(B, Nq, s1, C), a2 = attn_workspace_bytes(B, Nq, s2, CM);
-  n += align256(a1 > a2 ? a1 : a2);
+  const size_t a3 = attn_workspace_bytes(B, Nq, s3, CM);   // either cross-attention kernel may be selected at run time
+  n += align256(a1 > a2 ? (a1 > a3 ? a1 : a3) : (a2 > a3 ? a2 : a3));
   return n + 4096;
 }
 
@@ -84,7 +85,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   void* vts = ws.take((size_t)B * C * ldvs * 2);
   void* ao = ws.take((size_t)B * Nq * C * 2);
   void* h = ws.take((size_t)B * Nq * FFN * 2);
-  const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits(B, Nq, Nk);
+  const int s_self = attn_pick_splits(B, Nq, Nq), s_cross = attn_pick_splits_for(B, Nq, Nk, CM, g_attn_v_rows);
   const size_t a1 = attn_workspace_bytes(B, Nq, s_self, C), a2 = attn_workspace_bytes(B, Nq, s_cross, CM);
   char* aws = (char*)ws.take(a1 > a2 ? a1 : a2);
   VLS_REQUIRE(x && x_alt && t && qk && mem && mempos && kc_all && memT && vts && ao && h && (aws || (a1 == 0 && a2 == 0)),
