@@ -211,9 +211,9 @@ def run_ours(args):
     frames = [clip.frame(t, 1) for t in range(PERIOD)]
     prompts = clip.point_prompt(B)["point_coords"]
 
-    def prompt_all(state):
+    def prompt_all(state, pred=None):
         for o in range(B):
-            predictor.add_new_points_or_box(state, 0, o + 1, points=prompts[o].tolist(), labels=[1])
+            (pred or predictor).add_new_points_or_box(state, 0, o + 1, points=prompts[o].tolist(), labels=[1])
 
     if wl["kind"] == "clips":
         run_clip_workload(args, line, wl, predictor, frames, prompts, sampler, lib, dev, world, rank, torch, dist,
@@ -224,7 +224,7 @@ def run_ours(args):
     R = args.repeats if args.repeats > 0 else max(1, math.ceil(200 / K))
     T = RAMP + W + K * R + 1
 
-    def timed_pass(source, d2h):
+    def timed_pass(source, d2h, predictor=predictor, R=R, init_kw=None):
         """Ramp + warm-up untimed, then R windows of exactly K steps, each step bracketed by CUDA events, L2 flushed between
         steps.  With d2h the binarised video-resolution mask of EVERY step is read back into pinned host memory inside the
         step's events; the consumer is software-pipelined by one frame (it waits for frame t-1's mask after frame t
@@ -241,8 +241,8 @@ def run_ours(args):
 
         predictor.output_mode = "binary" if d2h else "logits"
         with sampler as clocks:
-            state = predictor.init_state(source)
-            prompt_all(state)
+            state = predictor.init_state(source, **(init_kw or {}))
+            prompt_all(state, predictor)
             gen = predictor.propagate_in_video(state)
             for j in range(RAMP + W):
                 _, _, m = next(gen)
@@ -325,12 +325,17 @@ def run_ours(args):
                 "note": "complete sessions incl. prompt frame and 16-frame ramp, resident features, best of %d" % n_clips}
 
     clip_info = whole_clips()
+    pixels_info = None
+    if rank == 0 and world == 1 and B == 1 and not args.no_pixels:
+        pixels_info = from_pixels(timed_pass, build_sam, synth, dev, torch, RAMP + W + K + 1)
     config["timing"] = f"{R} back-to-back windows of exactly {K} steps; value / ms_per_step / e2e are the MEDIAN window; windows_ms_per_step lists all"
     line.update({"value": round(value, 3), "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
                  "windows_ms_per_step": win_ms, "spread": {"min": min(win_ms), "max": max(win_ms), "windows": R},
                  "clocks": clocks, "gpu_launches": int(launches), "whole_clip": clip_info,
                  "e2e": {"value": round(e2e, 3), "unit": UNIT, "h2d_bytes_per_step": int(pinned.h2d_bytes_per_frame),
                          "d2h_bytes_per_step": int(out_bytes), "windows_ms_per_step": e2e_win}})
+    if pixels_info is not None:
+        line["e2e_from_pixels"] = pixels_info
     if B > 1:
         line["frame_objects_per_s"] = round(value * B, 1)
     if rank == 0:
@@ -349,6 +354,38 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def from_pixels(timed_pass, build_sam, synth, dev, torch, T):
+    """Informational second end-to-end number: the SAME public call path, but starting
+    from PIXELS -- normalised f32 frames in pinned host memory, uploaded frame by frame (offload_video_to_cpu=True), the
+    Hiera-B+ + FPN image encoder hosted in PyTorch (bf16, one CUDA graph), then the CUDA hot path and the uint8 mask read
+    back every step.  One window; not the roofline basis (the encoder is library code: cuDNN / cuBLAS / SDPA)."""
+    try:
+        sd = dict(synth.init_state_dict(0))
+        sd.update({"image_encoder." + k: v for k, v in synth.init_image_encoder_state_dict("b+", 0).items()})
+        pred = build_sam.build_sam2_video_predictor("b+", sd, dev, image_encoder_dtype=torch.bfloat16)
+        base = synth.synthetic_frames(8, 1024, seed=1)                      # 8 distinct frames, cycled (12.6 MB each)
+        frames = base[torch.arange(T) % 8].contiguous().pin_memory()
+        fps, ms, _, _, out_bytes, win = timed_pass(frames, True, predictor=pred, R=1, init_kw={"offload_video_to_cpu": True})
+        enc_ms = None
+        x = frames[:1].to(dev)
+        for _ in range(3):
+            pred.forward_image(x)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(10):
+            pred.forward_image(x)
+        b.record()
+        torch.cuda.synchronize()
+        enc_ms = a.elapsed_time(b) / 10
+        del pred
+        return {"value": round(fps, 2), "unit": UNIT, "ms_per_step": win[0], "image_encoder_ms": round(enc_ms, 3),
+                "h2d_bytes_per_step": int(frames[0].numel() * frames[0].element_size()), "d2h_bytes_per_step": int(out_bytes),
+                "note": "Hiera-B+ + FPN image encoder in PyTorch (bf16, CUDA graph) + the CUDA hot path, from pinned f32 frames; "
+                        "informational, not the headline metric"}
+    except Exception as e:  # informational leg: never lose the bench line over it
+        return {"unavailable": repr(e)[:300]}
 
 
 def run_clip_workload(args, line, wl, predictor, frames, prompts, sampler, lib, dev, world, rank, torch, dist, FeatureClip,
@@ -617,6 +654,7 @@ def main():
     ap.add_argument("--workload", default="configs[1]", choices=sorted(WORKLOADS))
     ap.add_argument("--sweep-clips", type=int, default=512, help="configs[4]: clips of the whole job")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pixels", action="store_true", help="skip the informational e2e_from_pixels leg (image encoder + hot path)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -247,6 +247,81 @@ def clip_case(model, sd, name, seed, num_frames, batch, sub=2, dense=None):
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
 
 
+def image_encoder_case():
+    """tests/golden/image_encoder.npz: the reference's Hiera + FPN image encoder
+    (backbones/hieradet.py:161-317, image_encoder.py:14-136) on two 256^2 synthetic frames, variants t and b+
+    (windows that need padding, pooled-q stage changes, global blocks), with the seeded weights of
+    synth.init_image_encoder_state_dict.  Feature maps are stored sub-sampled to keep the fixture small."""
+    ref_import._install_stubs()
+    out = {}
+    x = synth.synthetic_frames(2, 256, seed=1)
+    for variant in ("t", "b+"):
+        enc = ref_import._inst(ref_import.load_cfg(variant)["image_encoder"]).eval()
+        enc.load_state_dict(synth.init_image_encoder_state_dict(variant, 0), strict=True)
+        y = enc(x)
+        assert len(y["backbone_fpn"]) == 3 and y["vision_features"] is y["backbone_fpn"][-1]
+        tag = variant.replace("+", "p")
+        for lvl, sub in ((0, 8), (1, 4), (2, 2)):     # 8 x 8 samples of every level, both frames
+            out[f"{tag}_fpn{lvl}_s{sub}"] = y["backbone_fpn"][lvl][:, :, ::sub, ::sub].numpy().astype(np.float32)
+            out[f"{tag}_pos{lvl}_s{sub}"] = y["vision_pos_enc"][lvl][:1, :, ::sub, ::sub].numpy()
+        print(f"image encoder {variant}:", [tuple(f.shape) for f in y["backbone_fpn"]],
+              "max abs", [round(f.abs().max().item(), 3) for f in y["backbone_fpn"]])
+    np.savez_compressed(os.path.join(OUT, "image_encoder.npz"), **out)
+
+
+def pixels_clip_case(name="clip_pixels_t8", variant="t", num_frames=8, sub=2):
+    """BASELINE configs[0] from PIXELS: the reference SAM2VideoPredictor (Hiera-T) with its OWN image encoder on 8
+    synthetic 1024^2 frames, one point prompt -- nothing patched except load_video_frames (frames are handed over as a
+    tensor) and the connected-components stand-in.  Pins forward_image (trunk, neck, conv_s0 / conv_s1) + the hot path
+    end to end."""
+    import time
+
+    import sam2.sam2_video_predictor as vp
+    import sam2.utils.misc as misc
+
+    model = ref_import.build_video_predictor(variant, with_image_encoder=True)
+    sd = synth.init_state_dict(0)
+    sd_img = synth.init_image_encoder_state_dict(variant, 0)
+    full = dict(sd)
+    full.update({"image_encoder." + k: v for k, v in sd_img.items()})
+    model.load_state_dict(full, strict=True)
+    misc.get_connected_components = lambda m: cc_oracle.cc_label(m)
+    vp.fill_holes_in_mask_scores.__globals__["get_connected_components"] = misc.get_connected_components
+    prefill = []
+    orig_fill = misc.fill_holes_in_mask_scores
+
+    def recording_fill(mask, max_area):
+        prefill.append(mask.clone())
+        return orig_fill(mask, max_area)
+
+    vp.fill_holes_in_mask_scores = recording_fill
+    frames = synth.synthetic_frames(num_frames, 1024, seed=1)
+    vp.load_video_frames = lambda **kw: (frames, 1024, 1024)
+    t0 = time.time()
+    state = model.init_state(video_path="synthetic")
+    model.add_new_points_or_box(state, frame_idx=0, obj_id=1, points=[[300.0, 500.0]], labels=[1])
+    out = {}
+    for fi, obj_ids, video_res in model.propagate_in_video(state):
+        key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
+        o = state["output_dict"][key][fi]
+        pm = o["pred_masks"]
+        out[f"mask_s{sub}_{fi}"] = pm[:, :, ::sub, ::sub].numpy()
+        out[f"maskbits_{fi}"] = np.packbits((pm > 0).numpy().reshape(1, -1), axis=1)
+        out[f"obj_ptr_{fi}"] = o["obj_ptr"].numpy()
+        out[f"obj_score_{fi}"] = o["object_score_logits"].numpy()
+        out[f"mem_s4_{fi}"] = o["maskmem_features"].float()[:, :, ::4, ::4].numpy()
+        print(f"{name} t={fi} obj {o['object_score_logits'].flatten().tolist()} fg {(pm > 0).float().mean().item():.4f} "
+              f"range [{pm.min():.2f},{pm.max():.2f}]")
+    vp.fill_holes_in_mask_scores = orig_fill
+    # prefill[0] is the prompt frame (one call per object), then one call per propagated frame
+    for fi, pf in enumerate(prefill[:num_frames]):
+        out[f"prefill_s{sub}_{fi}"] = pf[:, :, ::sub, ::sub].numpy()
+    dt = time.time() - t0
+    out["reference_seconds_per_frame"] = np.float32(dt / num_frames)
+    print(f"{name}: reference CPU {dt / num_frames:.2f} s/frame ({torch.get_num_threads()} threads)")
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+
+
 # Clips whose weights differ from synth.init_state_dict(0) only in the object-score bias (synth.init_state_dict's
 # `obj_score_bias`).  With random weights the object score is nearly the same on every frame (0.09 on the prompt frame,
 # 0.15 afterwards at bias 0), so the -1024 gate -> no_obj_ptr -> no_obj_embed_spatial chain (sam2_base.py:359-403,
@@ -283,6 +358,10 @@ def main():
             api_case(model)
         if not only or "seg_head" in only:
             seg_head_case(model)
+        if not only or "image_encoder" in only:
+            image_encoder_case()
+        if not only or "clip_pixels_t8" in only:
+            pixels_clip_case()
         for name, kw, bias in GATE_CLIPS:
             if not only or name in only:
                 sd_g = synth.init_state_dict(0, obj_score_bias=bias)

@@ -283,3 +283,38 @@ def test_synthetic_generators_are_deterministic():
     f1, f2 = c1.frame(3, 2), c2.frame(3, 2)
     assert all(torch.equal(f1[k], f2[k]) for k in f1)
     assert f1["vision_feat"].shape == (4096, 2, 256) and f1["feat_s0"].shape == (2, 32, 256, 256)
+
+
+@pytest.mark.parametrize("variant", ["t", "b+"])
+def test_image_encoder_matches_reference_golden(variant):
+    """the PyTorch-hosted Hiera + FPN image encoder against the unmodified reference
+    (backbones/hieradet.py:161-317, image_encoder.py:14-136; tests/golden/image_encoder.npz) in fp32 on CPU: strict
+    load of reference-keyed weights, padded windows, pooled-q stage changes, global-attention blocks, FPN top-down."""
+    from video_llava_seg_b200 import build_sam, synth
+
+    gold = np.load(os.path.join(GOLD, "image_encoder.npz"))
+    enc = build_sam.build_image_encoder(variant).eval()
+    enc.load_state_dict(synth.init_image_encoder_state_dict(variant, 0), strict=True)
+    with torch.inference_mode():
+        y = enc(synth.synthetic_frames(2, 256, seed=1))
+    assert y["vision_features"] is y["backbone_fpn"][-1] and len(y["backbone_fpn"]) == 3
+    tag = variant.replace("+", "p")
+    for lvl, sub in ((0, 8), (1, 4), (2, 2)):
+        ref = torch.from_numpy(gold[f"{tag}_fpn{lvl}_s{sub}"])
+        err = (y["backbone_fpn"][lvl][:, :, ::sub, ::sub] - ref).abs().max().item()
+        assert err < 1e-4 * max(1.0, ref.abs().max().item()), (variant, lvl, err)   # same torch ops: float-rounding level
+        perr = (y["vision_pos_enc"][lvl][:1, :, ::sub, ::sub] - torch.from_numpy(gold[f"{tag}_pos{lvl}_s{sub}"])).abs().max().item()
+        assert perr < 1e-5, (variant, lvl, perr)
+
+
+def test_image_encoder_variants_and_builder():
+    """Channel lists / block counts of the four sam2.1 configurations (sam2.1_hiera_{t,s,b+,l}.yaml:6-24) and the
+    predictor factory wiring: `image_encoder.*` keys of a checkpoint reach the encoder."""
+    from video_llava_seg_b200 import build_sam
+
+    expect = {"t": ([768, 384, 192, 96], 12), "s": ([768, 384, 192, 96], 16), "b+": ([896, 448, 224, 112], 24),
+              "l": ([1152, 576, 288, 144], 48)}
+    for v, (chans, depth) in expect.items():
+        enc = build_sam.build_image_encoder(v)
+        assert list(enc.trunk.channel_list) == chans and enc.trunk.get_num_layers() == depth and enc.scalp == 1
+        assert [c.conv.in_channels for c in enc.neck.convs] == chans

@@ -1,6 +1,6 @@
 """Model factory for the hot-path modules with the hyper-parameters every sam2.1_hiera_{t,s,b+,l}.yaml
-shares (sam2/configs/sam2.1/*.yaml:26-116; the four files differ only in the image-encoder trunk/neck,
-which is outside this package).  Hydra is not needed: the configuration is spelled out here."""
+shares (sam2/configs/sam2.1/*.yaml:26-116; the four files differ only in the image-encoder trunk/neck:
+IMAGE_ENCODER_VARIANTS below).  Hydra is not needed: the configuration is spelled out here."""
 import torch
 
 from .modeling.memory_attention import MemoryAttention, MemoryAttentionLayer
@@ -9,6 +9,30 @@ from .modeling.position_encoding import PositionEmbeddingSine
 from .modeling.sam.mask_decoder import MaskDecoder
 from .modeling.sam.prompt_encoder import PromptEncoder
 from .modeling.sam.transformer import RoPEAttention, TwoWayTransformer
+
+
+# sam2/configs/sam2.1/sam2.1_hiera_{t,s,b+,l}.yaml:6-24 (trunk keywords; the neck's channel list follows from them)
+IMAGE_ENCODER_VARIANTS = {
+    "t": dict(embed_dim=96, num_heads=1, stages=(1, 2, 7, 2), global_att_blocks=(5, 7, 9),
+              window_pos_embed_bkg_spatial_size=(7, 7)),
+    "s": dict(embed_dim=96, num_heads=1, stages=(1, 2, 11, 2), global_att_blocks=(7, 10, 13),
+              window_pos_embed_bkg_spatial_size=(7, 7)),
+    "b+": dict(embed_dim=112, num_heads=2),
+    "l": dict(embed_dim=144, num_heads=2, stages=(2, 6, 36, 4), global_att_blocks=(23, 33, 43),
+              window_pos_embed_bkg_spatial_size=(7, 7), window_spec=(8, 4, 16, 8)),
+}
+
+
+def build_image_encoder(variant="b+"):
+    """Hiera trunk + FPN neck of sam2.1_hiera_<variant>.yaml; PyTorch modules."""
+    from .modeling.backbones.hieradet import Hiera
+    from .modeling.backbones.image_encoder import FpnNeck, ImageEncoder
+
+    trunk = Hiera(**IMAGE_ENCODER_VARIANTS[variant])
+    neck = FpnNeck(position_encoding=PositionEmbeddingSine(num_pos_feats=256, normalize=True, scale=None, temperature=10000),
+                   d_model=256, backbone_channel_list=list(trunk.channel_list), fpn_top_down_levels=[2, 3],
+                   fpn_interp_model="nearest")
+    return ImageEncoder(trunk=trunk, neck=neck, scalp=1)
 
 
 def build_memory_attention():
@@ -62,11 +86,14 @@ SAM21_MODEL_KWARGS = dict(  # sam2/configs/sam2.1/sam2.1_hiera_*.yaml:84-116 (id
     use_mlp_for_obj_ptr_proj=True, compile_image_encoder=False)
 
 
-def build_sam2_video_predictor(image_encoder=None, state_dict=None, device="cuda", apply_postprocessing=True, **overrides):
-    """Counterpart of sam2/build_sam.py:79-118.  `image_encoder` is any module returning the reference's
-    {"backbone_fpn", "vision_pos_enc"} dict (the Hiera + FPN encoder is outside this package; None when frames
-    come with precomputed features).  `state_dict`: reference checkpoint["model"] (image_encoder.* keys are
-    forwarded to the encoder if given, otherwise ignored)."""
+def build_sam2_video_predictor(image_encoder=None, state_dict=None, device="cuda", apply_postprocessing=True,
+                               image_encoder_dtype=None, **overrides):
+    """Counterpart of sam2/build_sam.py:79-118.  `image_encoder`: a variant name ("t", "s", "b+", "l": the Hiera + FPN
+    encoder of that configuration is built), any module returning the reference's {"backbone_fpn", "vision_pos_enc"}
+    dict, or None when frames come with precomputed features.  `state_dict`: reference checkpoint["model"]
+    (image_encoder.* keys are loaded into the encoder if there is one, otherwise ignored).
+    `image_encoder_dtype` (e.g. torch.bfloat16): after loading, run forward_image in that precision under a CUDA graph
+    (GraphedImageEncoder); None keeps the f32 eager module, as the reference."""
     from .sam2_video_predictor import SAM2VideoPredictor
 
     kw = dict(SAM21_MODEL_KWARGS)
@@ -76,6 +103,8 @@ def build_sam2_video_predictor(image_encoder=None, state_dict=None, device="cuda
                                                    dynamic_multimask_stability_delta=0.05,
                                                    dynamic_multimask_stability_thresh=0.98))
     kw.update(overrides)
+    if isinstance(image_encoder, str):
+        image_encoder = build_image_encoder(image_encoder)
     model = SAM2VideoPredictor(image_encoder=image_encoder, memory_attention=build_memory_attention(),
                                memory_encoder=build_memory_encoder(), **kw)
     if state_dict is not None:
@@ -85,4 +114,10 @@ def build_sam2_video_predictor(image_encoder=None, state_dict=None, device="cuda
         if missing:
             raise RuntimeError(f"checkpoint is missing hot-path keys, e.g. {missing[:5]}")
         model.load_state_dict(sd, strict=True)
-    return model.to(device).eval()
+    model = model.to(device).eval()
+    if image_encoder_dtype is not None and model.image_encoder is not None:
+        from .modeling.backbones.image_encoder import GraphedImageEncoder
+
+        model.image_encoder = GraphedImageEncoder(model.image_encoder, model.sam_mask_decoder.conv_s0,
+                                                  model.sam_mask_decoder.conv_s1, dtype=image_encoder_dtype)
+    return model

@@ -172,6 +172,8 @@ class SAM2Base(nn.Module):
     def forward_image(self, img_batch):
         """Image encoder + conv_s0/conv_s1 (sam2_base.py:467-479). Runs in PyTorch: outside the hot path."""
         out = self.image_encoder(img_batch)
+        if getattr(self.image_encoder, "applies_high_res_convs", False):   # GraphedImageEncoder: captured with the trunk
+            return out
         dec = self.sam_mask_decoder
         out["backbone_fpn"][0] = nn.functional.conv2d(out["backbone_fpn"][0], dec.conv_s0.weight, dec.conv_s0.bias)
         out["backbone_fpn"][1] = nn.functional.conv2d(out["backbone_fpn"][1], dec.conv_s1.weight, dec.conv_s1.bias)

@@ -235,3 +235,55 @@ class SyntheticClip:
         """One positive click per object at (300+40*o, 500) in 1024-space."""
         pts = torch.tensor([[[300.0 + 40.0 * o, 500.0]] for o in range(batch)])
         return {"point_coords": pts, "point_labels": torch.ones(batch, 1, dtype=torch.int32)}
+
+
+# ----------------------------------------------------------------------------- image encoder (SURVEY section 8 row f-4)
+def init_image_encoder_state_dict(variant: str = "t", seed: int = 0):
+    """Seeded weights for the Hiera + FPN image encoder of sam2.1_hiera_<variant>.yaml, keyed like the reference's
+    `image_encoder.*` slice WITHOUT the prefix (keys / shapes come from the module itself; the strict load into the
+    reference module in tests/golden/make_golden.py verifies them).  U(+-1/sqrt(fan_in)) matrices, non-trivial
+    LayerNorm affines, N(0, 0.1) positional embeddings: every block contributes at the 1e-1 level."""
+    from .build_sam import build_image_encoder
+
+    shapes = {k: tuple(v.shape) for k, v in build_image_encoder(variant).state_dict().items()}
+    g = torch.Generator().manual_seed(7_000_003 * (seed + 1) + sum(map(ord, variant)))
+    sd = {}
+    for k in sorted(shapes):
+        shp = shapes[k]
+        leaf = k.rsplit(".", 2)[-2] if k.count(".") else k
+        if "pos_embed" in k:
+            v = 0.1 * torch.randn(shp, generator=g)
+        elif leaf.startswith("norm") and k.endswith(".weight"):
+            v = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif leaf.startswith("norm") and k.endswith(".bias"):
+            v = 0.05 * torch.randn(shp, generator=g)
+        else:
+            w = shapes[k.rsplit(".", 1)[0] + ".weight"]
+            fan_in = 1
+            for d in w[1:]:
+                fan_in *= d
+            v = (torch.rand(shp, generator=g) * 2 - 1) / math.sqrt(fan_in)
+        sd[k] = v.float()
+    return sd
+
+
+def synthetic_frames(num_frames: int, size: int = 1024, seed: int = 1, start: int = 0):
+    """ImageNet-normalised synthetic video frames [T,3,size,size] f32: a low-frequency
+    bicubic noise field plus a Gaussian blob (sigma 80 px at 1024) whose centre moves from (300, 500) by (20, 10) px per
+    frame, and a little per-frame pixel noise."""
+    g = torch.Generator().manual_seed(1_000_003 * seed + 29)
+    scene = F.interpolate(torch.randn(1, 3, 12, 12, generator=g), size=(size, size), mode="bicubic", align_corners=False)[0]
+    scene = 0.5 + 0.18 * scene
+    colour = torch.tensor([0.9, 0.2, -0.4]).view(3, 1, 1)
+    yy = torch.arange(size, dtype=torch.float32).view(size, 1) + 0.5
+    xx = torch.arange(size, dtype=torch.float32).view(1, size) + 0.5
+    mean = torch.tensor([0.485, 0.456, 0.406]).view(3, 1, 1)
+    std = torch.tensor([0.229, 0.224, 0.225]).view(3, 1, 1)
+    out = []
+    for t in range(start, start + num_frames):
+        gt = torch.Generator().manual_seed(7919 * seed + 104729 * t + 11)
+        cx, cy, sig = (300.0 + 20.0 * t) / 1024.0 * size, (500.0 + 10.0 * t) / 1024.0 * size, 80.0 / 1024.0 * size
+        blob = torch.exp(-((xx - cx) ** 2 + (yy - cy) ** 2) / (2 * sig * sig))
+        img = (scene + 0.45 * colour * blob + 0.01 * torch.randn(3, size, size, generator=gt)).clamp_(0.0, 1.0)
+        out.append((img - mean) / std)
+    return torch.stack(out, 0)
