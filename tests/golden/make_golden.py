@@ -247,6 +247,50 @@ def clip_case(model, sd, name, seed, num_frames, batch, sub=2, dense=None):
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
 
 
+def seg_prompt_clip_case(model, sd, name="clip_segprompt_t4", seed=9, num_frames=4, sub=2):
+    """SURVEY section 8 row f-1, pinned to the REFERENCE: a `[SEG]`-style sparse prompt EMBEDDING on frame 0, then normal
+    propagation.  The reference has no such entry point (its LLaVA head decodes every frame independently,
+    llava/model/seg_head/sam2.py:103-114), so -- as SURVEY prescribes -- the reference predictor is driven with
+    `sam_prompt_encoder.forward` patched to return the embedding on the prompted frame (a dummy click carries the call)
+    and `_use_multimask` returning False there (the head decodes with multimask_output=False, sam2.py:111).  Propagated
+    frames use the unpatched prompt encoder."""
+    import types
+
+    clip = synth.SyntheticClip(seed, num_frames)
+    emb = torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(21))
+    pe = model.sam_prompt_encoder
+    orig_forward, orig_multimask = pe.forward, model._use_multimask
+
+    def patched_forward(points, boxes, masks):
+        sparse, dense = orig_forward(points=points, boxes=boxes, masks=masks)
+        if points is not None and (points[1] >= 0).any():      # a real prompt: replace the click by the embedding
+            return emb.expand(sparse.shape[0], -1, -1), dense
+        return sparse, dense
+
+    pe.forward = patched_forward
+    model._use_multimask = types.MethodType(
+        lambda self, is_init, pts: False if pts is not None else orig_multimask(is_init, pts), model)
+    try:
+        ref = run_reference_clip(model, clip, 1, num_frames)
+    finally:
+        pe.forward, model._use_multimask = orig_forward, orig_multimask
+    ora = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, 1), {"prompt_embedding": emb}, num_frames, cc=cc_oracle.cc_label)
+    out = {"embedding": emb.numpy()}
+    for t, (r, o) in enumerate(zip(ref, ora)):
+        one_sided = (r["pred_masks"] == 0.1) ^ (o["pred_masks"] == 0.1)
+        d_mask = (r["pred_masks"] - o["pred_masks"]).abs()[~one_sided].max().item()
+        d_ptr = maxdiff(r["obj_ptr"], o["obj_ptr"])
+        print(f"{name} t={t} oracle-vs-ref mask {d_mask:.2e} ptr {d_ptr:.2e} obj {r['object_score_logits'].flatten().tolist()} "
+              f"fg {(r['pred_masks'] > 0).float().mean().item():.4f}")
+        assert d_mask < 2e-3 and d_ptr < 1e-3, "oracle adapter drifted from the patched reference"
+        out[f"mask_s{sub}_{t}"] = r["pred_masks"][:, :, ::sub, ::sub].numpy()
+        out[f"prefill_s{sub}_{t}"] = r["pred_masks_prefill"][:, :, ::sub, ::sub].numpy()
+        out[f"maskbits_{t}"] = np.packbits((r["pred_masks"] > 0).numpy().reshape(1, -1), axis=1)
+        out[f"obj_ptr_{t}"] = r["obj_ptr"].numpy()
+        out[f"obj_score_{t}"] = r["object_score_logits"].numpy()
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
+
+
 def image_encoder_case():
     """tests/golden/image_encoder.npz: the reference's Hiera + FPN image encoder
     (backbones/hieradet.py:161-317, image_encoder.py:14-136) on two 256^2 synthetic frames, variants t and b+
@@ -358,6 +402,8 @@ def main():
             api_case(model)
         if not only or "seg_head" in only:
             seg_head_case(model)
+        if not only or "clip_segprompt_t4" in only:
+            seg_prompt_clip_case(model, sd)
         if not only or "image_encoder" in only:
             image_encoder_case()
         if not only or "clip_pixels_t8" in only:

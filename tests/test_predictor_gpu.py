@@ -268,33 +268,34 @@ def test_api_scenarios_match_reference(predictor, scenario):
 
 
 def test_seg_embedding_prompt_then_propagation(predictor):
-    """BASELINE config 4 / SURVEY f-1: a [SEG]-style sparse prompt embedding on frame 0, then propagation.
-    Checked live against the oracle with the same embedding (3 frames)."""
-    from oracle import cc as cc_oracle
-    from oracle import sam2_path as O
+    """BASELINE config 4 / SURVEY f-1: a [SEG]-style sparse prompt embedding on frame 0, then propagation, against the
+    REFERENCE predictor driven with `sam_prompt_encoder.forward` patched to return that embedding
+    (tests/golden/clip_segprompt_t4.npz, make_golden.py::seg_prompt_clip_case)."""
     from video_llava_seg_b200 import synth
     from video_llava_seg_b200.features import FeatureClip
 
-    sd = synth.init_state_dict(0)
-    T = 3
+    gold = np.load(os.path.join(GOLD, "clip_segprompt_t4.npz"))
+    T = 4
     clip = synth.SyntheticClip(9, T)
-    emb = torch.randn(1, 1, 256, generator=torch.Generator().manual_seed(21))
+    emb = torch.from_numpy(gold["embedding"])
     state = predictor.init_state(FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0"))
     fi, ids, m = predictor.add_new_prompt_embedding(state, 0, 5, emb[0])
     assert fi == 0 and ids == [5] and m.shape == (1, 1, 1024, 1024)
     got = {}
     for fi, ids, _ in predictor.propagate_in_video(state):
         key = "cond_frame_outputs" if fi == 0 else "non_cond_frame_outputs"
-        got[fi] = state["output_dict"][key][fi]["pred_masks"].float().cpu()
-    with torch.inference_mode():
-        ref = O.propagate(sd, O.Cfg, lambda t: clip.frame(t, 1), {"prompt_embedding": emb}, T, cc=cc_oracle.cc_label)
+        got[fi] = state["output_dict"][key][fi]
     for t in range(T):
-        a, b = got[t] > 0, ref[t]["pred_masks"] > 0
-        iou = (a & b).sum().item() / max((a | b).sum().item(), 1)
-        d = (got[t] - ref[t]["pred_masks"]).abs()
-        one_sided = (got[t] == 0.1) ^ (ref[t]["pred_masks"] == 0.1)
-        print(f"seg-embedding t={t}: IoU {iou:.5f} max logit err (non-fill) {d[~one_sided].max():.3e}")
-        assert iou >= 0.995 and d[~one_sided].max() < 1e-2
+        pm = got[t]["pred_masks"].float().cpu()
+        ref = torch.from_numpy(gold[f"mask_s2_{t}"])
+        ref_bits = np.unpackbits(gold[f"maskbits_{t}"], axis=1).reshape(1, 1, 256, 256).astype(bool)
+        a = (pm > 0).numpy()
+        iou = (a & ref_bits).sum() / max((a | ref_bits).sum(), 1)
+        d = (pm[:, :, ::2, ::2] - ref).abs()
+        one_sided = (pm[:, :, ::2, ::2] == 0.1) ^ (ref == 0.1)
+        ptr_err = (got[t]["obj_ptr"].cpu() - torch.from_numpy(gold[f"obj_ptr_{t}"])).abs().max().item()
+        print(f"seg-embedding t={t}: IoU {iou:.5f} max logit err (non-fill) {d[~one_sided].max():.3e} ptr err {ptr_err:.3e}")
+        assert iou >= 0.995 and d[~one_sided].max() < 1e-2 and ptr_err < 5e-2
     with pytest.raises(ValueError):
         predictor.add_new_prompt_embedding(state, 0, 5, torch.zeros(3))
 
