@@ -34,12 +34,11 @@ namespace vls {
 namespace {
 
 constexpr int C = 256;        // d_model
-constexpr int FF = 2048;      // hidden
 constexpr int BM = 128;       // rows per cluster
 constexpr int CL = 4;         // CTAs per cluster = hidden quarters
-constexpr int HPR = FF / CL;  // hidden units per CTA
 constexpr int HC = 128;       // hidden chunk
-constexpr int NCH = HPR / HC; // chunks per CTA
+// hidden width FF = CL * NCH * HC: NCH = 4 chunks per CTA for the memory-attention FFN (2048), 2 for the CXBlock of the
+// memory encoder's fuser (256 -> 1024 -> 256 with GELU, memory_encoder.py:86-100)
 constexpr int W1_SLOTS = 6, W1_SLOT_BYTES = HC * 64 * 2;    // [128 hidden x 64 channels]
 constexpr int W2_SLOTS = 2, W2_SLOT_BYTES = C * 64 * 2;     // [256 outputs x 64 hidden]
 constexpr int A_BYTES = BM * C * 2;                         // 4 panels [128 rows x 64 channels]
@@ -99,7 +98,7 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
 }
 
 // FRONT: tmA = ao [B][M][64] (box 128 x 64), tmW0 = folded out-proj weight [256][64] (box 256 x 64); else tmA = t [B][M][256]
-template <bool FRONT, bool BACK>
+template <bool FRONT, bool BACK, int NCH, bool GELU>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
@@ -131,6 +130,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const uint32_t rank = cluster_ctarank();
   const int m0 = blockIdx.y * BM;
   const int bz = blockIdx.z;
+  constexpr int HPR = NCH * HC;   // hidden units per CTA
   const int hbase = (int)rank * HPR;
 
   if (threadIdx.x == 0) {
@@ -349,7 +349,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float2 bb = __ldg(reinterpret_cast<const float2*>(bias + k * 32 + 2 * i));
-          h[i] = pack_bf16x2(fmaxf(__uint_as_float(r[2 * i]) + bb.x, 0.f), fmaxf(__uint_as_float(r[2 * i + 1]) + bb.y, 0.f));
+          const float h0 = __uint_as_float(r[2 * i]) + bb.x, h1 = __uint_as_float(r[2 * i + 1]) + bb.y;
+          h[i] = GELU ? pack_bf16x2(gelu_erf(h0), gelu_erf(h1)) : pack_bf16x2(fmaxf(h0, 0.f), fmaxf(h1, 0.f));
         }
         tmem_st16(base + k * 16, h);
       }
@@ -482,11 +483,11 @@ int g_tail_fused = 1;  // memory attention: 1 = out-proj + LN3 + FFN + next LN i
 
 namespace {
 
-template <bool FRONT, bool BACK>
+template <bool FRONT, bool BACK, int NCH, bool GELU>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW0, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
                    const CUtensorMap& tmX, const FfnParams& p, int B, cudaStream_t stream) {
   static unsigned long long attr_set = 0;   // one flag word per instantiation
-  auto kern = ffn_fused_kernel<FRONT, BACK>;
+  auto kern = ffn_fused_kernel<FRONT, BACK, NCH, GELU>;
   if (first_use_on_device(&attr_set)) VLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
   VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, tmX, p));
   VLS_POST_LAUNCH(1);
@@ -495,20 +496,23 @@ int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW0, const CUtens
 
 }  // namespace
 
-// x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2;  t bf16 [B][M][256] (row stride ldt), W1 bf16 [2048][256],
-// W2 bf16 [256][2048], b1 f32 [2048], b2 f32 [256], x f32 [B][M][256] contiguous rows.
+// x[b][m][:] += act(t[b][m][:] W1^T + b1) W2^T + b2;  t bf16 [B][M][256] (row stride ldt), W1 bf16 [ff][256],
+// W2 bf16 [256][ff], b1 f32 [ff], b2 f32 [256], x f32 [B][M][256] contiguous rows.  (ff, act) = (2048, ReLU): the FFN of a
+// memory-attention layer; (1024, GELU): the point-wise pair of a CXBlock of the memory encoder's fuser.
 int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const void* w1, const float* b1, const void* w2,
-                     const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream) {
+                     const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream, int ff, int gelu) {
   VLS_REQUIRE(t && w1 && b1 && w2 && b2 && x && B > 0 && M > 0, "ffn_fused: bad arguments");
   VLS_REQUIRE(ldt % 8 == 0, "ffn_fused: ldt must be a multiple of 8");
+  VLS_REQUIRE((ff == 2048 && !gelu) || (ff == 1024 && gelu), "ffn_fused: (hidden, activation) must be (2048, ReLU) or (1024, GELU)");
   CUtensorMap tmA, tmW1, tmW2;
   VLS_TRY(make_tmap_bf16(&tmA, t, C, M, B, ldt, t_bstride, BM));
-  VLS_TRY(make_tmap_bf16(&tmW1, w1, C, FF, 1, C, (long long)FF * C, HC));
-  VLS_TRY(make_tmap_bf16(&tmW2, w2, FF, C, 1, FF, (long long)FF * C, C));
+  VLS_TRY(make_tmap_bf16(&tmW1, w1, C, ff, 1, C, (long long)ff * C, HC));
+  VLS_TRY(make_tmap_bf16(&tmW2, w2, ff, C, 1, ff, (long long)ff * C, C));
   FfnParams p = {};
   p.M = M; p.b1 = b1; p.b2 = b2; p.x_in = x; p.x_out = x; p.x_bstride = x_bstride;
   p.trace = g_ffn_trace;
-  return launch_variant<false, false>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
+  if (gelu) return launch_variant<false, false, 2, true>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
+  return launch_variant<false, false, 4, false>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
 }
 
 // The tail of a memory-attention layer in one launch (see the file header):
@@ -523,6 +527,7 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
   VLS_TRY(make_tmap_f32(&tmX, a.x_in, C, a.M, a.B, C, (long long)a.M * C, BM));
   VLS_TRY(make_tmap_bf16(&tmA, a.ao, 64, a.M, a.B, 64, (long long)a.M * 64, BM));
   VLS_TRY(make_tmap_bf16(&tmW0, a.w0, 64, C, 1, 64, (long long)C * 64, C));
+  constexpr int FF = 2048;
   VLS_TRY(make_tmap_bf16(&tmW1, a.w1, C, FF, 1, C, (long long)FF * C, HC));
   VLS_TRY(make_tmap_bf16(&tmW2, a.w2, FF, C, 1, FF, (long long)FF * C, C));
   FfnParams p = {};
@@ -531,7 +536,7 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
   p.ln2_w = a.ln2_w; p.ln2_b = a.ln2_b; p.ln2_eps = a.ln2_eps;
   p.t_out = a.t_out; p.t_out_bf16 = a.t_out_bf16; p.t_out_st = a.t_out_st; p.t_out_sb = a.t_out_sb;
   p.trace = g_ffn_trace;
-  return launch_variant<true, true>(tmA, tmW0, tmW1, tmW2, tmX, p, a.B, stream);
+  return launch_variant<true, true, 4, false>(tmA, tmW0, tmW1, tmW2, tmX, p, a.B, stream);
 }
 
 }  // namespace vls

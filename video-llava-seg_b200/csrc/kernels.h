@@ -68,9 +68,11 @@ int attn_x2_pick_splits(int B, int Nq, int Nk);
 int launch_attention_x2(const AttnArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- fused FFN (ffn_fused.cu)
-// x[b][m][:] += relu(t[b][m][:] W1^T + b1) W2^T + b2 in one cluster kernel (hidden activations stay in TMEM).
+// x[b][m][:] += act(t[b][m][:] W1^T + b1) W2^T + b2 in one cluster kernel (hidden activations stay in TMEM);
+// (ff, gelu) = (2048, 0): memory-attention FFN, (1024, 1): CXBlock point-wise pair.
 int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const void* w1, const float* b1, const void* w2,
-                     const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream);
+                     const float* b2, float* x, long long x_bstride, int B, int M, cudaStream_t stream, int ff = 2048,
+                     int gelu = 0);
 extern int g_ffn_fused;
 extern int g_tail_fused;
 extern long long* g_ffn_trace;

@@ -509,6 +509,10 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
   for (int i = 0; i < 2; ++i) {
     const vls_cx_block& cx = w->cx[i];
     VLS_TRY(launch_dwconv7_ln(x, B, H, W, cx.dw_w, cx.dw_b, cx.ln_w, cx.ln_b, LN2D_EPS, t, st));
+    if (g_ffn_fused) {   // pwconv1 + GELU + pwconv2 + residual in one cluster kernel: the [T][1024] hidden tensor stays in TMEM
+      VLS_TRY(launch_ffn_fused(t, C, (long long)T * C, cx.pw1_w, cx.pw1_b, cx.pw2_w, cx.pw2_b, x, (long long)T * C, B, T, st, 1024, 1));
+      continue;
+    }
     GemmArgs g1 = lin(t, C, (long long)T * C, cx.pw1_w, T, 1024, C, B, cx.pw1_b, hid, 1, 1024, (long long)T * 1024);
     g1.act = 2;
     VLS_TRY(launch_gemm(g1, st));
