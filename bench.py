@@ -505,7 +505,7 @@ def roofline(predictor, source, prompt_all, lib, torch, B, clocks):
     prof = os.path.join(ROOT, "profiles", "attn_cross_dram_bytes.json")
     if os.path.exists(prof) and B == 1:
         traffic = json.load(open(prof)).get("dram_bytes_per_launch")
-    return {"bound": "tensor", "kernel": "attn_fwd_kernel + combine (memory cross-attention, Nq=4096, Nk=28736, qk dim 256, value dim 64)",
+    return {"bound": "tensor", "kernel": "attn_x2_kernel + combine (memory cross-attention, two query tiles per CTA, Nq=4096, Nk=28736, qk dim 256, value dim 64)",
             "achieved": round(achieved, 2), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
             "executed": round(executed, 2), "frac_executed": round(executed / peak, 4),
             "traffic": traffic, "peak_source": peak_source, "launches_timed": cnt.value,
