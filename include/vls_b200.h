@@ -262,6 +262,15 @@ int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const f
                        const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
                        int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
                        vls_stream_t stream);
+/* Same, but the object-pointer MLP (obj_ptr is only needed by the memory-bank update and the session state) is enqueued
+ * on an internal forked stream and NOT joined: low_res_masks / best_idx / is_obj / occluded are ordered on `stream` as
+ * usual, obj_ptr only after vls_sam_heads_join(stream).  Lets the caller overlap it with the memory encoder
+ * (sam2_base.py:396-403 vs :709-722 are independent). */
+int vls_sam_heads_post_deferred(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                                const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                                int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                                vls_stream_t stream);
+int vls_sam_heads_join(vls_stream_t stream);
 
 /* Memory encoder (memory_encoder.py:158-181). */
 typedef struct vls_cx_block {

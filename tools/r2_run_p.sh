@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -8 | tee gpurun_out/p_tests.log
+timeout 300 python tools/timeline_frame.py > gpurun_out/p_timeline.txt 2>&1
+grep -E "frame span" gpurun_out/p_timeline.txt
+timeout 900 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-pixels 2>gpurun_out/p_bench.err | tail -1 > gpurun_out/p_bench.json
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/p_bench.json'))
+print({k:d.get(k) for k in ('value','ms_per_step','windows_ms_per_step')}, d['e2e']['value'])
+PY

@@ -115,6 +115,10 @@ def _declare_modules(lib):
     lib.vls_sam_heads_post.restype = c_int
     lib.vls_sam_heads_post.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]
+    lib.vls_sam_heads_post_deferred.restype = c_int
+    lib.vls_sam_heads_post_deferred.argtypes = lib.vls_sam_heads_post.argtypes
+    lib.vls_sam_heads_join.restype = c_int
+    lib.vls_sam_heads_join.argtypes = [c_void_p]
     lib.vls_mem_encoder_workspace_bytes.restype = c_size_t
     lib.vls_mem_encoder_workspace_bytes.argtypes = [c_int, c_int, c_int]
     lib.vls_mem_encoder_forward.restype = c_int

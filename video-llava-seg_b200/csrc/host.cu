@@ -96,7 +96,7 @@ bool overlap_enabled() {
 }
 int fork_get(int idx, Fork** out) {
   // per host thread and per device: concurrent callers never share a side stream or its events
-  static thread_local Fork forks[16][4];
+  static thread_local Fork forks[16][6];
   int dev = 0;
   VLS_CUDA(cudaGetDevice(&dev));
   VLS_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);

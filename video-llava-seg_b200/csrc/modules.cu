@@ -415,11 +415,12 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
 }
 
 // ================================================================== post-decoder glue
-int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
-                       const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
-                       int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
-                       vls_stream_t stream_) {
-  cudaStream_t st = (cudaStream_t)stream_;
+// defer: the object-pointer MLP (3 token linears + gate; only the bank shift / the session state need its result) runs on
+// a forked stream and is NOT joined here: the caller overlaps it with the memory encoder and calls vls_sam_heads_join.
+static int sam_heads_post_impl(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                               const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                               int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                               cudaStream_t st, bool defer) {
   VLS_REQUIRE(w && masks && iou && tokens && obj_logits && low_res_masks && obj_ptr && best_idx && is_obj && occluded,
               "sam_heads_post: null argument");
   VLS_REQUIRE(workspace && workspace_bytes >= (size_t)B * 256 * 3 * 4, "sam_heads_post: workspace too small");
@@ -428,16 +429,36 @@ int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const f
   float* h2 = h1 + (size_t)B * 256;
   VLS_TRY(launch_select_best(masks, iou, tokens, obj_logits, B, 4, multimask, HW, low_res_masks, tok, best_idx, is_obj,
                              occluded, st));
+  cudaStream_t ps = st;
+  if (defer) VLS_TRY(fork_begin(4, st, &ps));
   SmallLinArgs s;
   s.G = 1; s.R = B; s.K = 256; s.N = 256; s.act = 1;
   s.x = tok; s.x_sr = 256; s.W = w->w[0]; s.bias = w->b[0]; s.out = h1; s.o_sr = 256;
-  VLS_TRY(launch_small_linear(s, st));
+  VLS_TRY(launch_small_linear(s, ps));
   s.x = h1; s.W = w->w[1]; s.bias = w->b[1]; s.out = h2;
-  VLS_TRY(launch_small_linear(s, st));
+  VLS_TRY(launch_small_linear(s, ps));
   s.x = h2; s.W = w->w[2]; s.bias = w->b[2]; s.out = obj_ptr; s.act = 0;
-  VLS_TRY(launch_small_linear(s, st));
-  return launch_gate_ptr(obj_ptr, is_obj, w->no_obj_ptr, B, st);
+  VLS_TRY(launch_small_linear(s, ps));
+  return launch_gate_ptr(obj_ptr, is_obj, w->no_obj_ptr, B, ps);
 }
+
+int vls_sam_heads_post(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                       const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                       int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                       vls_stream_t stream_) {
+  return sam_heads_post_impl(w, masks, iou, tokens, obj_logits, B, multimask, HW, low_res_masks, obj_ptr, best_idx, is_obj,
+                             occluded, workspace, workspace_bytes, (cudaStream_t)stream_, false);
+}
+
+int vls_sam_heads_post_deferred(const vls_obj_ptr_weights* w, const float* masks, const float* iou, const float* tokens,
+                                const float* obj_logits, int B, int multimask, int HW, float* low_res_masks, float* obj_ptr,
+                                int* best_idx, float* is_obj, float* occluded, void* workspace, size_t workspace_bytes,
+                                vls_stream_t stream_) {
+  return sam_heads_post_impl(w, masks, iou, tokens, obj_logits, B, multimask, HW, low_res_masks, obj_ptr, best_idx, is_obj,
+                             occluded, workspace, workspace_bytes, (cudaStream_t)stream_, true);
+}
+
+int vls_sam_heads_join(vls_stream_t stream_) { return fork_join(4, (cudaStream_t)stream_); }
 
 // ================================================================== memory encoder
 size_t vls_mem_encoder_workspace_bytes(int B, int H, int W) {

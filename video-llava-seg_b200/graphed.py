@@ -48,7 +48,8 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
     high = [in_s0.expand(B, -1, -1, -1), in_s1.expand(B, -1, -1, -1)]
     _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
-        pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False)
+        pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False,
+        defer_obj_ptr=True)        # obj_ptr MLP on a forked stream, joined below: nothing before the bank update needs it
     # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
     # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
     main = torch.cuda.current_stream(dev)
@@ -58,6 +59,7 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
         pred = fill_holes_in_mask_scores(low, m.fill_hole_area) if m.fill_hole_area > 0 else low
         video = m._video_res_output(pred, hw)
     nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
+    _lib.check(_lib.lib().vls_sam_heads_join(_lib.stream()), "vls_sam_heads_join")
     main.wait_stream(side)
     return pred, obj_ptr, obj_logits, nchw, rows, video
 

@@ -191,8 +191,10 @@ class SAM2Base(nn.Module):
 
     # ------------------------------------------------------------------ SAM heads
     def _forward_sam_heads(self, backbone_features, point_inputs=None, mask_inputs=None, high_res_features=None,
-                           multimask_output=False, need_high_res=True):
-        """sam2_base.py:257-413. Returns the same 7-tuple; `high_res_*` entries are None unless need_high_res."""
+                           multimask_output=False, need_high_res=True, defer_obj_ptr=False):
+        """sam2_base.py:257-413. Returns the same 7-tuple; `high_res_*` entries are None unless need_high_res.
+        defer_obj_ptr: the object-pointer MLP is enqueued on a forked stream and obj_ptr is only valid after
+        `lib().vls_sam_heads_join(stream())` (the captured frame overlaps it with the memory encoder)."""
         B = backbone_features.size(0)
         dev = backbone_features.device
         require_cuda(backbone_features)
@@ -237,9 +239,10 @@ class SAM2Base(nn.Module):
         is_obj = torch.empty((B,), device=dev, dtype=torch.float32)
         occluded = torch.empty((B,), device=dev, dtype=torch.float32)
         ws = torch.empty((B * 256 * 3 * 4,), device=dev, dtype=torch.uint8)
-        check(lib().vls_sam_heads_post(ctypes_ref(c["ptr_w"]), ptr(masks4), ptr(iou4), ptr(tok4), ptr(obj_logits), B,
-                                       int(bool(multimask_output)), hw, ptr(low), ptr(obj_ptr), ptr(best), ptr(is_obj),
-                                       ptr(occluded), ptr(ws), ws.numel(), stream()), "vls_sam_heads_post")
+        heads_post = lib().vls_sam_heads_post_deferred if defer_obj_ptr else lib().vls_sam_heads_post
+        check(heads_post(ctypes_ref(c["ptr_w"]), ptr(masks4), ptr(iou4), ptr(tok4), ptr(obj_logits), B,
+                         int(bool(multimask_output)), hw, ptr(low), ptr(obj_ptr), ptr(best), ptr(is_obj),
+                         ptr(occluded), ptr(ws), ws.numel(), stream()), "vls_sam_heads_post")
         if multimask_output:
             low_multi, ious = masks4[:, 1:], iou4[:, 1:]
         else:
