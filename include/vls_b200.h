@@ -48,6 +48,9 @@ void vls_launch_count_add(long long n);
  * "ffn_fused": 1 (default) = the memory-attention FFN runs as one cluster kernel; 0 = as two GEMM launches.
  * "tail_fused": 1 (default, needs ffn_fused) = folded out-projection, LayerNorm3, FFN and the following LayerNorm of a
  * memory-attention layer run as ONE launch; 0 = as separate launches.
+ * "dec_fused": 1 (default) = the token side of the mask decoder's two-way layers (<= 16 token rows, image tokens a
+ * multiple of 64) runs as thread-block-cluster kernels (dec_tok.cu) over head-major image projections; 0 = as the chain
+ * of small kernels.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -57,6 +60,9 @@ int vls_set_tuning(const char* key, int value);
 void vls_attention_trace(long long* device_buffer);
 /* Same for the fused FFN / layer-tail kernel: 16 int64 stamps of the first epilogue thread of CTA (0,0,0) (tools/trace_ffn.py). */
 void vls_ffn_trace(long long* device_buffer);
+/* Same for the mask decoder's token-side cluster kernel: every launch while the buffer is set writes 24 int64 stamps of
+ * thread 0 of CTA (0,0) and advances the buffer by 24 entries (tools/trace_dec.py); NULL switches it off. */
+void vls_dec_trace(long long* device_buffer);
 /* Optional live kernel timing: when enabled, the attention launcher brackets its kernel with CUDA events
  * on the launching stream; vls_prof_collect(slot) synchronises them and returns count / total ms and clears
  * the slot.  slot 0 = memory cross-attention launches (Nk > Nq), slot 1 = self-attention launches. */

@@ -44,6 +44,8 @@ def _declare(lib):
     lib.vls_attention_trace.argtypes = [c_void_p]
     lib.vls_ffn_trace.restype = None
     lib.vls_ffn_trace.argtypes = [c_void_p]
+    lib.vls_dec_trace.restype = None
+    lib.vls_dec_trace.argtypes = [c_void_p]
     lib.vls_set_tuning.restype = c_int
     lib.vls_set_tuning.argtypes = [ctypes.c_char_p, c_int]
     lib.vls_prof_enable.restype = None

@@ -15,6 +15,7 @@ long long vls_launch_count(void) { return launch_count(); }
 void vls_launch_count_add(long long n) { count_launches((int)n); }
 void vls_attention_trace(long long* device_buffer) { g_attn_trace = device_buffer; }
 void vls_ffn_trace(long long* device_buffer) { g_ffn_trace = device_buffer; }
+void vls_dec_trace(long long* device_buffer) { g_dec_trace = device_buffer; }
 int vls_set_tuning(const char* key, int value) {
   VLS_REQUIRE(key != nullptr, "set_tuning: null key");
   if (std::string(key) == "attn_cluster") {
@@ -41,6 +42,10 @@ int vls_set_tuning(const char* key, int value) {
   }
   if (std::string(key) == "ffn_fused") {   // memory-attention FFN: 1 = one cluster kernel (hidden stays in TMEM), 0 = two GEMMs
     g_ffn_fused = value != 0;
+    return 0;
+  }
+  if (std::string(key) == "dec_fused") {   // mask decoder token side: 1 = cluster kernels (dec_tok.cu), 0 = chain of small kernels
+    g_dec_fused = value != 0;
     return 0;
   }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch

@@ -124,7 +124,7 @@ t2i_attn_kernel(const float* __restrict__ q, const bf16* __restrict__ kv, long l
 // q: bf16 rows [B][T][ld] at column qoff; k_tok, v_tok f32 [B][Nt][128]; out bf16 [B][T][128].
 __global__ void __launch_bounds__(256)
 i2t_attn_kernel(const bf16* __restrict__ qrows, long long ld, long long q_sb, int qoff, const float* __restrict__ ktok,
-                const float* __restrict__ vtok, int Nt, int T, bf16* __restrict__ out) {
+                const float* __restrict__ vtok, int Nt, int T, bf16* __restrict__ out, int planes) {
   pdl_enter();
   extern __shared__ float sm_i2t[];
   float* sk = sm_i2t;
@@ -137,8 +137,10 @@ i2t_attn_kernel(const bf16* __restrict__ qrows, long long ld, long long q_sb, in
   __syncthreads();
   const long long id = (long long)blockIdx.x * 256 + threadIdx.x;
   if (id >= (long long)T * 8) return;
-  const int t = (int)(id >> 3), h = (int)(id & 7);
-  const uint4* qp = reinterpret_cast<const uint4*>(qrows + (long long)b * q_sb + (long long)t * ld + qoff + h * 16);
+  // rows: q of (t, h) at t * ld + qoff + 16 h, thread = (t, h);  planes: head-major [qoff + h][T][16], thread = (h, t)
+  const int t = planes ? (int)(id % T) : (int)(id >> 3), h = planes ? (int)(id / T) : (int)(id & 7);
+  const uint4* qp = reinterpret_cast<const uint4*>(qrows + (long long)b * q_sb +
+                                                   (planes ? ((long long)(qoff + h) * T + t) * 16 : (long long)t * ld + qoff + h * 16));
   const uint4 q0 = qp[0], q1 = qp[1];
   const uint32_t qu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
   float qv[16];
@@ -373,9 +375,9 @@ int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_s
 }
 
 int launch_i2t_attn(const void* qrows, long long ld, long long q_sb, int qoff, const float* ktok, const float* vtok, int B,
-                    int Nt, int T, void* out, cudaStream_t stream) {
+                    int Nt, int T, void* out, cudaStream_t stream, int planes) {
   const size_t smem = (size_t)Nt * 128 * 2 * sizeof(float);
-  VLS_CUDA(launch_k(i2t_attn_kernel, dim3(dim3((T * 8 + 255) / 256, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(qrows), ld, q_sb, qoff, ktok, vtok, Nt, T, reinterpret_cast<bf16*>(out)));
+  VLS_CUDA(launch_k(i2t_attn_kernel, dim3(dim3((T * 8 + 255) / 256, B)), dim3(256), smem, stream, reinterpret_cast<const bf16*>(qrows), ld, q_sb, qoff, ktok, vtok, Nt, T, reinterpret_cast<bf16*>(out), planes));
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -52,6 +52,8 @@ struct Epi {
   void* C;
   int c_bf16;
   long long ldc, c_bstride;
+  int c_colblock;                   // > 0: column n lives at (n / colblock) * colblock_stride + n % colblock ("planes")
+  long long c_colblock_stride;
   int a_div, a_mod, w_div, w_mod;   // operand batch index = (blockIdx.z / div) % mod
 };
 
@@ -166,7 +168,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // epilogue at 0.8 TB/s of output.
     const int row_first = m0 + rsub;
     const long long c_elem = c_bf16 ? 2 : 4;
-    char* cptr = reinterpret_cast<char*>(e.C) + ((long long)bz * e.c_bstride + (long long)row_first * e.ldc + col) * c_elem;
+    const long long col_off = e.c_colblock > 0 ? (long long)(col / e.c_colblock) * e.c_colblock_stride + col % e.c_colblock : col;
+    char* cptr = reinterpret_cast<char*>(e.C) + ((long long)bz * e.c_bstride + (long long)row_first * e.ldc + col_off) * c_elem;
     const long long c_step = (long long)RPP * e.ldc * c_elem;
     const float* rptr = e.residual ? e.residual + (long long)bz * e.res_bstride + (long long)row_first * e.ld_res + col : nullptr;
     const long long r_step = (long long)RPP * e.ld_res;
@@ -265,6 +268,7 @@ int launch_cfg(const GemmArgs& a, cudaStream_t stream) {
   e.rope_rows = a.rope_rows;
   e.residual = a.residual; e.ld_res = a.ld_res; e.res_bstride = a.res_bstride;
   e.C = a.C; e.c_bf16 = a.c_bf16; e.ldc = a.ldc; e.c_bstride = a.c_bstride;
+  e.c_colblock = a.c_colblock; e.c_colblock_stride = a.c_colblock_stride;
   e.a_div = a.a_div; e.a_mod = a.a_batches; e.w_div = a.w_div; e.w_mod = a.w_batches;
   static unsigned long long attr_set = 0;
   if (first_use_on_device(&attr_set)) {
@@ -299,6 +303,7 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   VLS_REQUIRE(a.lda % 8 == 0 && a.ldw % 8 == 0, "gemm: lda/ldw must be multiples of 8 elements");
   VLS_REQUIRE(a.N % 4 == 0 && a.ldc % 4 == 0, "gemm: N and ldc must be multiples of 4");
   VLS_REQUIRE(!a.residual || a.ld_res % 4 == 0, "gemm: ld_res must be a multiple of 4");
+  VLS_REQUIRE(a.c_colblock == 0 || (a.c_colblock % 4 == 0 && a.c_colblock_stride % 4 == 0), "gemm: column blocks must be multiples of 4");
   VLS_REQUIRE(!a.rope_cos || (a.rope_sin && a.rope_period > 0), "gemm: incomplete RoPE arguments");
   VLS_REQUIRE(!(a.rope_cos && a.act == 2), "gemm: GELU + RoPE epilogue is not instantiated");
   // default batch indexing: operand batch = blockIdx.z when it has a batch stride, else shared

@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include "host.h"
+#include "vls_b200.h"
 
 namespace vls {
 
@@ -31,6 +32,9 @@ struct GemmArgs {
   void* C = nullptr;
   int c_bf16 = 1;            // 1: bf16 output, 0: f32 output
   long long ldc = 0, c_bstride = 0;
+  // optional "plane" output: column n is stored at (n / c_colblock) * c_colblock_stride + n % c_colblock (+ m * ldc): the
+  // mask decoder's image-side projections are written head-major, [head][T][16], so that a head's keys are contiguous
+  int c_colblock = 0; long long c_colblock_stride = 0;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
 
@@ -141,8 +145,9 @@ int launch_gather_rows(const float* src, long long sg, long long sr, int G, int 
 int launch_tok_self_attn(const float* q, const float* k, const float* v, int B, int Nt, float* out, cudaStream_t stream);
 int launch_t2i_attn(const float* q, const void* kv, long long ld, long long kv_sb, int koff, int voff, int B, int Nt,
                     int T, float* out, cudaStream_t stream);
+// planes = 1: q is stored head-major, [qoff + h][T][16] per batch element (ld unused)
 int launch_i2t_attn(const void* qrows, long long ld, long long q_sb, int qoff, const float* ktok, const float* vtok, int B,
-                    int Nt, int T, void* out, cudaStream_t stream);
+                    int Nt, int T, void* out, cudaStream_t stream, int planes = 0);
 int launch_up1_post(const void* g, const void* feat, int feat_bf16, long long feat_sb, int B, int h, int w,
                     const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream);
 int launch_up2_masks(const void* u, const float* w2t, const float* bias, const void* feat, int feat_bf16,
@@ -152,6 +157,30 @@ int launch_select_best(const float* masks, const float* iou, const float* tokens
                        int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
                        float* occluded, cudaStream_t stream);
 int launch_gate_ptr(float* ptr, const float* is_obj, const float* no_obj_ptr, int B, cudaStream_t stream);
+
+// ---------------------------------------------------------------- mask decoder, token side of a layer (dec_tok.cu)
+// One cluster kernel (8 CTAs = 8 heads per batch element) runs any combination of the three token-side stages of a
+// TwoWayAttentionBlock on the <= 16 token rows: SELF (self-attention + norm1), CROSS (token->image attention over the
+// head-major K / V planes + norm2, also the decoder's final attention), MLP (MLP + norm3 + the k / v projections of the
+// image->token attention).
+enum { DEC_TOK_SELF = 1, DEC_TOK_CROSS = 2, DEC_TOK_MLP = 4, DEC_TOK_FIRST = 8 /* self-attention without PE / residual */ };
+struct DecTokArgs {
+  int B = 1, Nt = 0, T = 0, flags = 0;
+  float eps = 1e-5f;
+  float* queries = nullptr;        // f32 [B][Nt][256] in / out
+  const float* pe = nullptr;       // f32 [B][Nt][256]
+  const vls_attn_w* self_attn = nullptr; const float* n1_w = nullptr; const float* n1_b = nullptr;
+  const vls_attn_w* t2i = nullptr; const float* n2_w = nullptr; const float* n2_b = nullptr;
+  const void* planes = nullptr; long long planes_bstride = 0; int kplane = 0, vplane = 8;   // bf16 [B][planes][T][16]
+  const void* m1_w = nullptr; const float* m1_b = nullptr; const void* m2_w = nullptr; const float* m2_b = nullptr;
+  const float* n3_w = nullptr; const float* n3_b = nullptr;
+  const vls_attn_w* i2t = nullptr;
+  float* kt = nullptr; float* vt = nullptr;   // f32 [B][Nt][128]
+};
+extern int g_dec_fused;
+extern long long* g_dec_trace;
+bool dec_tok_supported(int Nt, int T);
+int launch_dec_tok(const DecTokArgs& a, cudaStream_t stream);
 
 // ---------------------------------------------------------------- memory encoder kernels (memenc.cu)
 int launch_mds1(const float* src, int mode, int B, int H, int W, int factor, float scale, float bias_v, const float* wgt,

@@ -308,6 +308,29 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     return launch_ln256_small(a, 256, R, nw, nb, LN_EPS, queries, 256, st);
   };
 
+  // Token side of a layer as cluster kernels (dec_tok.cu) when the shape allows it: the image-side projections are then
+  // written head-major ("planes" [24 or 16][T][16]) so that the token->image attention reads contiguous keys per head.
+  const bool fused = dec_tok_supported(Nt, T);
+  auto planes_out = [&](GemmArgs& g) {
+    if (!fused) return;
+    g.ldc = 16; g.c_colblock = 16; g.c_colblock_stride = (long long)T * 16;
+  };
+  auto dec_tok = [&](int flags, const vls_dec_layer* L, const vls_attn_w* t2i_w, const float* n2w, const float* n2b,
+                     long long planes_bstride, cudaStream_t s_) -> int {
+    DecTokArgs d;
+    d.B = B; d.Nt = Nt; d.T = T; d.flags = flags; d.eps = LN_EPS;
+    d.queries = queries; d.pe = tokens0;
+    if (L) {
+      d.self_attn = &L->self_attn; d.n1_w = L->n1_w; d.n1_b = L->n1_b;
+      d.m1_w = L->mlp1_w; d.m1_b = L->mlp1_b; d.m2_w = L->mlp2_w; d.m2_b = L->mlp2_b; d.n3_w = L->n3_w; d.n3_b = L->n3_b;
+      d.i2t = &L->i2t;
+    }
+    d.t2i = t2i_w; d.n2_w = n2w; d.n2_b = n2b;
+    d.planes = kvq; d.planes_bstride = planes_bstride; d.kplane = 0; d.vplane = 8;
+    d.kt = kt; d.vt = vt;
+    return launch_dec_tok(d, s_);
+  };
+
   for (int l = 0; l < 2; ++l) {
     const vls_dec_layer& L = w->layers[l];
     // -- token self attention (sam/transformer.py:183-191); layer 0 drops the PE and the residual
@@ -319,8 +342,16 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
       VLS_TRY(fork_begin(1, st, &side));
       GemmArgs g = lin(keys_h, C, (long long)T * C, L.img_w, T, 384, C, B, L.img_b, kvq, 1, 384, (long long)T * 384);
       g.residual = L.img_pe_add; g.ld_res = 384; g.res_bstride = 0;
+      planes_out(g);
       VLS_TRY(launch_gemm(g, side));
     }
+    if (fused) {
+      // self-attention + norm1 next to the image-side GEMM, then token->image attention + MLP + i2t k/v in one launch
+      VLS_TRY(dec_tok(DEC_TOK_SELF | (l == 0 ? DEC_TOK_FIRST : 0), &L, nullptr, nullptr, nullptr, 0, st));
+      VLS_TRY(fork_join(1, st));
+      VLS_TRY(dec_tok(DEC_TOK_CROSS | DEC_TOK_MLP, &L, &L.t2i, L.n2_w, L.n2_b, (long long)T * 384, st));
+      VLS_TRY(launch_i2t_attn(kvq, 384, (long long)T * 384, 16, kt, vt, B, Nt, T, ai, st, 1));
+    } else {
     {   // q, k, v projections: three independent problems, one launch
       const SmallLinArgs qkv[3] = {tok_args(queries, pe, 256, L.self_attn.q_w, L.self_attn.q_b, 256, 0, nullptr, q),
                                    tok_args(queries, pe, 256, L.self_attn.k_w, L.self_attn.k_b, 256, 0, nullptr, k),
@@ -344,6 +375,7 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
       VLS_TRY(launch_small_linear_multi(kv, 2, st));
     }
     VLS_TRY(launch_i2t_attn(kvq, 384, (long long)T * 384, 256, kt, vt, B, Nt, T, ai, st));
+    }
     {
       GemmArgs g = lin(ai, 128, (long long)T * 128, L.i2t.o_w, T, C, 128, B, L.i2t.o_b, scratch, 0, C, (long long)T * C);
       g.residual = keys; g.ld_res = C; g.res_bstride = (long long)T * C;
@@ -351,17 +383,8 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     }
     VLS_TRY(launch_ln256(scratch, B, T, L.n4_w, L.n4_b, LN_EPS, 0, keys, (long long)T * C, C, keys_h, (long long)T * C, C, st));
   }
-  // -- final tokens -> image attention (sam/transformer.py:127-132)
-  {
-    GemmArgs g = lin(keys_h, C, (long long)T * C, w->final_img_w, T, 256, C, B, w->final_img_b, kvq, 1, 256, (long long)T * 256);
-    g.residual = w->final_pe_add; g.ld_res = 256; g.res_bstride = 0;
-    VLS_TRY(launch_gemm(g, st));
-  }
-  VLS_TRY(t2i(w->final_t2i, kvq, 256, w->nf_w, w->nf_b));
-  // queries == hs: [0]=obj score token, [1]=iou token, [2..5]=mask tokens (mask_decoder.py:213-215)
-
-  // -- upscaling (mask_decoder.py:218-225): ConvT(256->64) as a GEMM, + feat_s1, LN2d, GELU: on the side stream, next to
-  //    the hyper-network MLPs that only need the mask tokens
+  // -- upscaling (mask_decoder.py:218-225): ConvT(256->64) as a GEMM, + feat_s1, LN2d, GELU.  It only needs the final image
+  //    keys, so it runs on the side stream next to the final token->image attention and the token-side heads
   cudaStream_t up_side;
   VLS_TRY(fork_begin(1, st, &up_side));
   {
@@ -369,6 +392,17 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     VLS_TRY(launch_gemm(g, up_side));
   }
   VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, up_side));
+  // -- final tokens -> image attention (sam/transformer.py:127-132)
+  {
+    GemmArgs g = lin(keys_h, C, (long long)T * C, w->final_img_w, T, 256, C, B, w->final_img_b, kvq, 1, 256, (long long)T * 256);
+    g.residual = w->final_pe_add; g.ld_res = 256; g.res_bstride = 0;
+    planes_out(g);
+    VLS_TRY(launch_gemm(g, st));
+  }
+  if (fused) VLS_TRY(dec_tok(DEC_TOK_CROSS, nullptr, &w->final_t2i, w->nf_w, w->nf_b, (long long)T * 256, st));
+  else VLS_TRY(t2i(w->final_t2i, kvq, 256, w->nf_w, w->nf_b));
+  // queries == hs: [0]=obj score token, [1]=iou token, [2..5]=mask tokens (mask_decoder.py:213-215)
+
   // -- the three token-side heads advance layer by layer in ONE launch per layer: hyper-network MLPs on the 4 mask
   //    tokens (mask_decoder.py:227-232), IoU head on hs[:,1] and object-score head on hs[:,0] (:237-240)
   {
