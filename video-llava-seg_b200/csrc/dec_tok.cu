@@ -62,18 +62,23 @@ struct DecTokParams {
     if (p.trace && tid == 0 && rank == 0 && blockIdx.y == 0) p.trace[slot] = clock64(); \
   } while (0)
 
+// parameter block staged in shared memory at kernel start (a dependent global load costs ~330 cycles each time)
+enum { P_N1W = 0, P_N1B = 256, P_N2W = 512, P_N2B = 768, P_N3W = 1024, P_N3B = 1280, P_SO = 1536, P_TO = 1568, P_M2 = 1600,
+       P_TQ = 1632, P_IK = 1648, P_IV = 1664, P_M1 = 1680, P_SQ = 1936, P_SK = 1968, P_SV = 2000, P_END = 2032 };
+
 struct __align__(16) DecTokSmem {
   float xs[ROWS][256];            // current token rows (replicated in every CTA)
   float pes[ROWS][256];
-  float ybuf[ROWS][256];          // all-gather landing zone of the pre-LayerNorm rows
+  float ybuf[ROWS][256];          // all-gather landing zone of the pre-LayerNorm rows (+ local staging of the MLP partials)
   bf16 opA[2][ROWS][OPS];         // MMA operand (hi, lo): x + pe
   bf16 opB[2][ROWS][OPS];         // x
   bf16 opC[2][ROWS][OPS];         // attention outputs (all-gather landing zone)
   bf16 opH[2][ROWS][OPS];         // this CTA's 256 hidden units
-  float qkv[3][ROWS][33];         // q, k, v of this CTA's self-attention head
-  float tqs[ROWS][16];            // scaled q of this CTA's token->image head
+  float qkv[3][ROWS][33];         // q, k, v of this CTA's self-attention head (q rows are overwritten by the head's output)
+  float tqs[ROWS][16];            // scaled q of this CTA's token->image head (then the head's output)
   float part[CLD][ROWS][32];      // partial sums of the second MLP GEMM: [source CTA][row][this CTA's 32 columns]
-  float tpart[DT_WARPS][ROWS][20];  // per-warp flash-attention partials: 16 channels, max, sum
+  float tpart[DT_WARPS][ROWS][20];  // per-warp flash-attention partials: 16 channels, max, sum; also the K-split scratch
+  float prm[P_END];               // LayerNorm weights and this CTA's bias slices
 };
 
 __device__ __forceinline__ void mma_bf16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
@@ -96,6 +101,16 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 __device__ __forceinline__ void st_cluster_f32(uint32_t addr, float v) {
   asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
 }
+__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// one 16-byte piece to the same shared-memory offset of every CTA of the cluster (remote stores cost ~10 cycles of issue
+// per warp instruction whatever their width: measured, tools/micro/cluster_latency.cu)
+__device__ __forceinline__ void bcast_v4(const void* local, uint4 v) {
+  const uint32_t a = smem_u32(local);
+#pragma unroll
+  for (int r = 0; r < CLD; ++r) st_cluster_v4(mapa_u32(a, (uint32_t)r), v);
+}
 // v = hi + lo with hi, lo bf16 (|v - hi - lo| <= 2^-17 |v|)
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(v);
@@ -108,6 +123,8 @@ __device__ __forceinline__ uint16_t bf16_bits(bf16 v) { return *reinterpret_cast
 // The k index of a 32-wide step is permuted (thread t owns physical k = 8t .. 8t+7: 4 for each of the two MMAs), so that
 // the weight fragment is ONE 16-byte load per row and the activation fragment one 16-byte shared-memory load.
 // Loads and MMAs are separate calls: the weights of the NEXT stage are requested before the barrier that precedes it.
+// mma.sync issues at 16 cycles per instruction and SM sub-partition on B200 (measured), so the MMA count matters: XLO = false
+// drops the lo half of the activations (used where they are bf16-rounded anyway).
 template <int K>
 struct WTile {
   uint4 a0[K / 32], a1[K / 32];
@@ -122,13 +139,14 @@ __device__ __forceinline__ void load_w(WTile<K>& w, const bf16* __restrict__ W, 
     w.a1[i] = __ldg(wb + 4 * i);
   }
 }
-// K0: first column of the operand rows this tile multiplies (K-split stages pass their slice offset)
-template <int K, int NT8>
+// k0: first column of the operand rows this tile multiplies (K-split stages pass their slice offset)
+template <int K, int NT8, bool XLO>
 __device__ __forceinline__ void mma_w(const WTile<K>& w, const bf16 (*op)[ROWS][OPS], int k0, float (&out)[NT8][4], int g,
                                       int t) {
-  float acc[4][NT8][4];
+  constexpr int CH = XLO ? 4 : 2;
+  float acc[CH][NT8][4];
 #pragma unroll
-  for (int c = 0; c < 4; ++c)
+  for (int c = 0; c < CH; ++c)
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
@@ -138,17 +156,23 @@ __device__ __forceinline__ void mma_w(const WTile<K>& w, const bf16 (*op)[ROWS][
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt) {
       const uint4 bh = *reinterpret_cast<const uint4*>(&op[0][nt * 8 + g][k0 + 32 * i + 8 * t]);
-      const uint4 bl = *reinterpret_cast<const uint4*>(&op[1][nt * 8 + g][k0 + 32 * i + 8 * t]);
       mma_bf16(acc[0][nt], w.a0[i].x, w.a1[i].x, w.a0[i].y, w.a1[i].y, bh.x, bh.y);
       mma_bf16(acc[1][nt], w.a0[i].z, w.a1[i].z, w.a0[i].w, w.a1[i].w, bh.z, bh.w);
-      mma_bf16(acc[2][nt], w.a0[i].x, w.a1[i].x, w.a0[i].y, w.a1[i].y, bl.x, bl.y);
-      mma_bf16(acc[3][nt], w.a0[i].z, w.a1[i].z, w.a0[i].w, w.a1[i].w, bl.z, bl.w);
+      if (XLO) {
+        const uint4 bl = *reinterpret_cast<const uint4*>(&op[1][nt * 8 + g][k0 + 32 * i + 8 * t]);
+        mma_bf16(acc[CH - 2][nt], w.a0[i].x, w.a1[i].x, w.a0[i].y, w.a1[i].y, bl.x, bl.y);
+        mma_bf16(acc[CH - 1][nt], w.a0[i].z, w.a1[i].z, w.a0[i].w, w.a1[i].w, bl.z, bl.w);
+      }
     }
   }
 #pragma unroll
   for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) out[nt][e] = (acc[0][nt][e] + acc[1][nt][e]) + (acc[2][nt][e] + acc[3][nt][e]);
+    for (int e = 0; e < 4; ++e) {
+      float v = acc[0][nt][e] + acc[1][nt][e];
+      if (XLO) v += acc[CH - 2][nt][e] + acc[CH - 1][nt][e];
+      out[nt][e] = v;
+    }
 }
 
 __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo) {
@@ -165,7 +189,7 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4& hi, uint4& lo
   lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-struct KV4 {   // 32 keys of one head: fragment pieces of 4 tiles of 8 keys
+struct KV2 {   // 32 keys of one head = 2 tiles of 16 keys: k[j] / v[j] = (key 16 j' + g (j even) or + g + 8 (j odd), channels 4t..4t+3)
   uint2 k[4], v[4];
 };
 
@@ -197,13 +221,35 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
     xin[0] = xq[0]; xin[1] = xq[1];
     pin[0] = __ldg(pq); pin[1] = __ldg(pq + 1);
   }
+  float4 prm_in = make_float4(0.f, 0.f, 0.f, 0.f);
+  {
+    const int i = 4 * tid;
+    const float* src = nullptr;
+    if (i < P_N1B) src = p.n1_w ? p.n1_w + i : nullptr;
+    else if (i < P_N2W) src = p.n1_b ? p.n1_b + (i - P_N1B) : nullptr;
+    else if (i < P_N2B) src = p.n2_w ? p.n2_w + (i - P_N2W) : nullptr;
+    else if (i < P_N3W) src = p.n2_b ? p.n2_b + (i - P_N2B) : nullptr;
+    else if (i < P_N3B) src = p.n3_w ? p.n3_w + (i - P_N3W) : nullptr;
+    else if (i < P_SO) src = p.n3_b ? p.n3_b + (i - P_N3B) : nullptr;
+    else if (i < P_TO) src = p.so_b ? p.so_b + 32 * rank + (i - P_SO) : nullptr;
+    else if (i < P_M2) src = p.to_b ? p.to_b + 32 * rank + (i - P_TO) : nullptr;
+    else if (i < P_TQ) src = p.m2_b ? p.m2_b + 32 * rank + (i - P_M2) : nullptr;
+    else if (i < P_IK) src = p.tq_b ? p.tq_b + 16 * rank + (i - P_TQ) : nullptr;
+    else if (i < P_IV) src = p.ik_b ? p.ik_b + 16 * rank + (i - P_IK) : nullptr;
+    else if (i < P_M1) src = p.iv_b ? p.iv_b + 16 * rank + (i - P_IV) : nullptr;
+    else if (i < P_SQ) src = p.m1_b ? p.m1_b + 256 * rank + (i - P_M1) : nullptr;
+    else if (i < P_SK) src = p.sq_b ? p.sq_b + 32 * rank + (i - P_SQ) : nullptr;
+    else if (i < P_SV) src = p.sk_b ? p.sk_b + 32 * rank + (i - P_SK) : nullptr;
+    else if (i < P_END) src = p.sv_b ? p.sv_b + 32 * rank + (i - P_SV) : nullptr;
+    if (src) prm_in = __ldg(reinterpret_cast<const float4*>(src));
+  }
   WTile<256> wt;     // full-K tile of the next "one tile per warp" stage (qkv / mlp1 / mlp2)
   WTile<32> ws;      // K-slice of the next K-split stage (o-proj, q, i2t k/v)
-  KV4 kv0, kv1;      // token->image attention: double-buffered key / value fragments
+  KV2 kv0, kv1;      // token->image attention: double-buffered key / value fragments
   const int groups = p.T >> 5;
   const bf16* Kp = nullptr;
   const bf16* Vp = nullptr;
-  auto attn_load = [&](KV4& buf, int grp) {
+  auto attn_load = [&](KV2& buf, int grp) {
     const long long key0 = (long long)grp * 32;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -250,6 +296,7 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
     *reinterpret_cast<float4*>(&s.pes[r0][c0]) = pin[0];
     *reinterpret_cast<float4*>(&s.pes[r0][c0 + 4]) = pin[1];
     put_rows(r0, c0, x, pe, !((flags & DEC_TOK_SELF) && first));
+    if (4 * tid < P_END) *reinterpret_cast<float4*>(&s.prm[4 * tid]) = prm_in;
   }
   __syncthreads();
   DT_TRACE(1);
@@ -257,32 +304,19 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
   // sits right in front of it
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
 
-  auto bcast_f32 = [&](float* local, float v) {
-    const uint32_t a = smem_u32(local);
-#pragma unroll
-    for (int r = 0; r < CLD; ++r) st_cluster_f32(mapa_u32(a, (uint32_t)r), v);
-  };
-  // all-gather of an attention output as MMA operand: the even lane of a pair stores the two hi halves, the odd lane the two
-  // lo halves (columns col & ~1, col | 1 of `row`)
-  auto bcast_op_pair = [&](bf16 (*op)[ROWS][OPS], int row, int col, float v, bool active) {
-    bf16 hi, lo;
-    split_bf16(v, hi, lo);
-    const uint32_t mine = (lane & 1) ? bf16_bits(lo) : bf16_bits(hi);       // what this lane contributes to its own word
-    const uint32_t give = (lane & 1) ? bf16_bits(hi) : bf16_bits(lo);       // ... and to the neighbour's word
-    const uint32_t got = __shfl_xor_sync(0xffffffffu, give, 1);
-    const uint32_t word = (lane & 1) ? (got | (mine << 16)) : (mine | (got << 16));
-    if (active) {
-      const uint32_t a = smem_u32(&op[lane & 1][row][col & ~1]);
-#pragma unroll
-      for (int r = 0; r < CLD; ++r) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(mapa_u32(a, (uint32_t)r)), "r"(word) : "memory");
-    }
+  // all-gather of 8 consecutive columns of an attention output as MMA operand (hi + lo): two 16-byte stores per CTA
+  auto bcast_op8 = [&](bf16 (*op)[ROWS][OPS], int row, int col, const float (&v)[8]) {
+    uint4 hi, lo;
+    split8(v, hi, lo);
+    bcast_v4(&op[0][row][col], hi);
+    bcast_v4(&op[1][row][col], lo);
   };
   // xs = LayerNorm(ybuf) (warp = row, lane = 8 consecutive columns); optionally the MMA operands and the global copy
-  auto layer_norm = [&](const float* w, const float* bb, bool ops, bool to_global) {
+  auto layer_norm = [&](int pw, int pb, bool ops, bool to_global) {
     if (warp < Nt) {
       const int c = 8 * lane;
-      const float4 w0 = __ldg(reinterpret_cast<const float4*>(w + c)), w1 = __ldg(reinterpret_cast<const float4*>(w + c + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bb + c)), b1 = __ldg(reinterpret_cast<const float4*>(bb + c + 4));
+      const float4 w0 = *reinterpret_cast<const float4*>(&s.prm[pw + c]), w1 = *reinterpret_cast<const float4*>(&s.prm[pw + c + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&s.prm[pb + c]), b1 = *reinterpret_cast<const float4*>(&s.prm[pb + c + 4]);
       const float4 y0 = *reinterpret_cast<const float4*>(&s.ybuf[warp][c]), y1 = *reinterpret_cast<const float4*>(&s.ybuf[warp][c + 4]);
       float v[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
       float sum = 0.f;
@@ -312,22 +346,40 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
     }
   };
   // K-split stage: warp w owns k-slice (w % NSL) of tile (w / NSL); partial sums go through shared memory
-  // (scr = tpart, [warp][token][20]: conflict-free fragment stores) and are summed in slice order by thread (tile, token, col)
+  // (scr = tpart, [warp][token][20]: conflict-free fragment stores) and are summed in slice order by thread
+  // (tile, token, 4 columns) -- tid < 128
   float (*scr)[ROWS][20] = s.tpart;
   auto ks_mma = [&](const bf16 (*op)[ROWS][OPS], int kslice) {
     float o[NT8][4];
-    mma_w<32, NT8>(ws, op, 32 * kslice, o, g, t);
+    mma_w<32, NT8, true>(ws, op, 32 * kslice, o, g, t);
 #pragma unroll
     for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) scr[warp][nt * 8 + 2 * t + (e & 1)][g + 8 * (e >> 1)] = o[nt][e];
   };
-  auto ks_sum = [&](int tile, int nsl, int tok, int col) {
-    float v = scr[tile * nsl][tok][col];
-    for (int k = 1; k < nsl; ++k) v += scr[tile * nsl + k][tok][col];
+  const int e_cg = (tid & 3) * 4, e_tok = (tid >> 2) & 15, e_tile = (tid >> 6) & 1;
+  auto ks_sum4 = [&](int tile, int nsl) {
+    float4 v = *reinterpret_cast<const float4*>(&scr[tile * nsl][e_tok][e_cg]);
+    for (int k = 1; k < nsl; ++k) {
+      const float4 u = *reinterpret_cast<const float4*>(&scr[tile * nsl + k][e_tok][e_cg]);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
     return v;
   };
-  const int e_col = tid & 15, e_tok = (tid >> 4) & 15, e_tile = tid >> 8;   // thread -> element of a K-split stage's output
+  // pre-LayerNorm rows: columns [32 r + 16 tile + cg, + 4) of token e_tok = K-split sum + bias + residual -> every CTA's ybuf
+  auto ks_bcast_rows = [&](int nsl, int pbias, bool residual) {
+    if (tid < 128 && e_tok < Nt) {
+      float4 v = ks_sum4(e_tile, nsl);
+      const int cl = 16 * e_tile + e_cg, col = 32 * (int)rank + cl;
+      const float4 bz = *reinterpret_cast<const float4*>(&s.prm[pbias + cl]);
+      v.x += bz.x; v.y += bz.y; v.z += bz.z; v.w += bz.w;
+      if (residual) {
+        const float4 xr = *reinterpret_cast<const float4*>(&s.xs[e_tok][col]);
+        v.x += xr.x; v.y += xr.y; v.z += xr.z; v.w += xr.w;
+      }
+      bcast_v4(&s.ybuf[e_tok][col], make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+    }
+  };
   bool waited0 = false;
   auto wait_cluster_start = [&]() {   // uniform across the CTA
     if (!waited0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -338,10 +390,10 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
   if (flags & DEC_TOK_SELF) {
     if (warp < 6) {
       const int which = warp >> 1, half = warp & 1;
-      const float* bias = (which == 0 ? p.sq_b : which == 1 ? p.sk_b : p.sv_b) + 32 * rank + 16 * half;
-      const float bz0 = __ldg(bias + g), bz1 = __ldg(bias + g + 8);
+      const float* bias = &s.prm[P_SQ + 32 * which + 16 * half];
+      const float bz0 = bias[g], bz1 = bias[g + 8];
       float o[NT8][4];
-      mma_w<256, NT8>(wt, which == 2 ? s.opB : s.opA, 0, o, g, t);
+      mma_w<256, NT8, true>(wt, which == 2 ? s.opB : s.opA, 0, o, g, t);
 #pragma unroll
       for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
@@ -352,7 +404,6 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
     load_w<32>(ws, p.so_w + (long long)(32 * rank + 16 * (warp >> 3)) * 256 + 32 * (warp & 7), 256, g, t);
     __syncthreads();
     DT_TRACE(2);
-    float sa = 0.f;
     if (warp < Nt) {   // warp = query row, lane = key row for the scores, = channel for the output
       float sc = -INFINITY;
       if (lane < Nt) {
@@ -367,26 +418,32 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
       const float m = warp_max(sc);
       const float pr = lane < Nt ? __expf(sc - m) : 0.f;
       const float l = warp_sum(pr);
+      float sa = 0.f;
       for (int j = 0; j < Nt; ++j) sa += __shfl_sync(0xffffffffu, pr, j) * s.qkv[2][j][lane];
-      sa /= l;
+      __syncwarp();
+      s.qkv[0][warp][lane] = sa / l;   // only this warp reads q row `warp`
     }
+    __syncthreads();
     wait_cluster_start();
-    bcast_op_pair(s.opC, warp < Nt ? warp : 0, 32 * (int)rank + lane, sa, warp < Nt);
+    if (tid < 4 * Nt) {   // (row, 8 columns) -> operand pieces in every CTA
+      const int row = tid >> 2, c8 = (tid & 3) * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s.qkv[0][row][c8 + j];
+      bcast_op8(s.opC, row, 32 * (int)rank + c8, v);
+    }
     DT_TRACE(3);
     cluster_sync_all();
     DT_TRACE(4);
     ks_mma(s.opC, warp & 7);
     __syncthreads();
-    if (e_tok < Nt) {
-      const int col = 32 * (int)rank + 16 * e_tile + e_col;
-      bcast_f32(&s.ybuf[e_tok][col], ks_sum(e_tile, 8, e_tok, e_col) + __ldg(p.so_b + col) + (first ? 0.f : s.xs[e_tok][col]));
-    }
+    ks_bcast_rows(8, P_SO, !first);
     DT_TRACE(5);
     cluster_sync_all();
     DT_TRACE(6);
     const bool more = (flags & (DEC_TOK_CROSS | DEC_TOK_MLP)) != 0;
     if (more && warp < 8) load_w<32>(ws, p.tq_w + (long long)(16 * rank) * 256 + 32 * warp, 256, g, t);
-    layer_norm(p.n1_w, p.n1_b, more, !more);
+    layer_norm(P_N1W, P_N1B, more, !more);
     if (more && (flags & DEC_TOK_CROSS)) {
       Kp = p.planes + (long long)b * p.planes_bstride + (long long)(p.kplane + (int)rank) * p.T * 16;
       Vp = p.planes + (long long)b * p.planes_bstride + (long long)(p.vplane + (int)rank) * p.T * 16;
@@ -402,75 +459,78 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
     if (warp < 8) ks_mma(s.opA, warp);
     if (warp < 8) load_w<32>(ws, p.to_w + (long long)(32 * rank + 16 * (warp >> 2)) * 128 + 32 * (warp & 3), 128, g, t);   // o-proj slices
     __syncthreads();
-    if (tid < 256) s.tqs[e_tok][e_col] = (ks_sum(0, 8, e_tok, e_col) + __ldg(p.tq_b + 16 * rank + e_col)) * (0.25f * 1.4426950408889634f);
+    if (tid < 64) {
+      float4 v = ks_sum4(0, 8);
+      const float4 bz = *reinterpret_cast<const float4*>(&s.prm[P_TQ + e_cg]);
+      const float sc = 0.25f * 1.4426950408889634f;
+      *reinterpret_cast<float4*>(&s.tqs[e_tok][e_cg]) = make_float4((v.x + bz.x) * sc, (v.y + bz.y) * sc, (v.z + bz.z) * sc, (v.w + bz.w) * sc);
+    }
     __syncthreads();
     DT_TRACE(8);
     {
-      // A fragments of Q (hi / lo): rows g, g + 8; physical channels 4t .. 4t+3
-      uint32_t qh[4], ql[4];
+      // Flash attention with the KEYS as the M dimension: S^T[16 keys][8 tokens] = K_h Q_h^T (one MMA per 16 keys and token
+      // tile, + one for the lo half of q), P^T = exp2(S^T - max) transposed in registers (movmatrix) into the B fragment of
+      // O^T[16 channels][8 tokens] += V_h^T P^T, whose A fragment is V transposed the same way.  Channels are permuted:
+      // thread t loads physical channels 4t..4t+3 of a key (one 8-byte load).
+      // B fragments of Q^T (hi / lo): token n = g (+ 8 per token tile), physical channels 4t .. 4t+3
+      uint32_t qh[NT8][2], ql[NT8][2];
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int row = g + 8 * rr;
+      for (int nt = 0; nt < NT8; ++nt) {
+        const int row = nt * 8 + g;
         bf16 h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_bf16((row < Nt) ? s.tqs[row][4 * t + j] : 0.f, h[j], l[j]);
-        qh[rr] = uint32_t(bf16_bits(h[0])) | (uint32_t(bf16_bits(h[1])) << 16);
-        qh[rr + 2] = uint32_t(bf16_bits(h[2])) | (uint32_t(bf16_bits(h[3])) << 16);
-        ql[rr] = uint32_t(bf16_bits(l[0])) | (uint32_t(bf16_bits(l[1])) << 16);
-        ql[rr + 2] = uint32_t(bf16_bits(l[2])) | (uint32_t(bf16_bits(l[3])) << 16);
+        qh[nt][0] = uint32_t(bf16_bits(h[0])) | (uint32_t(bf16_bits(h[1])) << 16);
+        qh[nt][1] = uint32_t(bf16_bits(h[2])) | (uint32_t(bf16_bits(h[3])) << 16);
+        ql[nt][0] = uint32_t(bf16_bits(l[0])) | (uint32_t(bf16_bits(l[1])) << 16);
+        ql[nt][1] = uint32_t(bf16_bits(l[2])) | (uint32_t(bf16_bits(l[3])) << 16);
       }
-      float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-      float o[2][4];
+      // per thread: tokens 8 nt + 2t, 8 nt + 2t + 1 (columns of S^T and O^T)
+      float m[NT8][2], l[NT8][2], o[NT8][4];
 #pragma unroll
-      for (int c = 0; c < 2; ++c)
+      for (int nt = 0; nt < NT8; ++nt) {
+        m[nt][0] = m[nt][1] = -INFINITY;
+        l[nt][0] = l[nt][1] = 0.f;
+        o[nt][0] = o[nt][1] = o[nt][2] = o[nt][3] = 0.f;
+      }
+      auto attn_compute = [&](const KV2& buf) {
+        float sc[2][NT8][4];   // [key tile][token tile]: (key g, tok 2t) (key g, tok 2t+1) (key g+8, tok 2t) (key g+8, tok 2t+1)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) o[c][e] = 0.f;
-      auto attn_compute = [&](const KV4& buf) {
-        float sc[4][4];
-        float mx0 = -INFINITY, mx1 = -INFINITY;
+        for (int kt = 0; kt < 2; ++kt)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-          mma_bf16(sc[j], qh[0], qh[1], qh[2], qh[3], buf.k[j].x, buf.k[j].y);
-          mma_bf16(sc[j], ql[0], ql[1], ql[2], ql[3], buf.k[j].x, buf.k[j].y);
-        }
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          mx0 = fmaxf(mx0, fmaxf(sc[j][0], sc[j][1]));
-          if (NT8 == 2) mx1 = fmaxf(mx1, fmaxf(sc[j][2], sc[j][3]));
-        }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        const float mn0 = fmaxf(m[0], mx0);
-        const float corr0 = ex2_approx(m[0] - mn0);
-        m[0] = mn0;
-        l[0] *= corr0;
-        o[0][0] *= corr0; o[0][1] *= corr0; o[1][0] *= corr0; o[1][1] *= corr0;
-        if (NT8 == 2) {
-          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-          const float mn1 = fmaxf(m[1], mx1);
-          const float corr1 = ex2_approx(m[1] - mn1);
-          m[1] = mn1;
-          l[1] *= corr1;
-          o[0][2] *= corr1; o[0][3] *= corr1; o[1][2] *= corr1; o[1][3] *= corr1;
-        }
-#pragma unroll
-        for (int st = 0; st < 2; ++st) {
-          const int ja = 2 * st, jb = 2 * st + 1;
-          const float pa0 = ex2_approx(sc[ja][0] - m[0]), pa1 = ex2_approx(sc[ja][1] - m[0]);
-          const float pb0 = ex2_approx(sc[jb][0] - m[0]), pb1 = ex2_approx(sc[jb][1] - m[0]);
-          l[0] += (pa0 + pa1) + (pb0 + pb1);
-          float pa2 = 0.f, pa3 = 0.f, pb2 = 0.f, pb3 = 0.f;
-          if (NT8 == 2) {
-            pa2 = ex2_approx(sc[ja][2] - m[1]); pa3 = ex2_approx(sc[ja][3] - m[1]);
-            pb2 = ex2_approx(sc[jb][2] - m[1]); pb3 = ex2_approx(sc[jb][3] - m[1]);
-            l[1] += (pa2 + pa3) + (pb2 + pb3);
+          for (int nt = 0; nt < NT8; ++nt) {
+            sc[kt][nt][0] = sc[kt][nt][1] = sc[kt][nt][2] = sc[kt][nt][3] = 0.f;
+            mma_bf16(sc[kt][nt], buf.k[2 * kt].x, buf.k[2 * kt + 1].x, buf.k[2 * kt].y, buf.k[2 * kt + 1].y, qh[nt][0], qh[nt][1]);
+            mma_bf16(sc[kt][nt], buf.k[2 * kt].x, buf.k[2 * kt + 1].x, buf.k[2 * kt].y, buf.k[2 * kt + 1].y, ql[nt][0], ql[nt][1]);
           }
-          const uint32_t a0 = pack_bf16x2(pa0, pa1), a1 = pack_bf16x2(pa2, pa3);
-          const uint32_t a2 = pack_bf16x2(pb0, pb1), a3 = pack_bf16x2(pb2, pb3);
-          mma_bf16(o[0], a0, a1, a2, a3, movmatrix_trans(buf.v[ja].x), movmatrix_trans(buf.v[jb].x));
-          mma_bf16(o[1], a0, a1, a2, a3, movmatrix_trans(buf.v[ja].y), movmatrix_trans(buf.v[jb].y));
+#pragma unroll
+        for (int nt = 0; nt < NT8; ++nt) {
+          float mx0 = fmaxf(fmaxf(sc[0][nt][0], sc[0][nt][2]), fmaxf(sc[1][nt][0], sc[1][nt][2]));
+          float mx1 = fmaxf(fmaxf(sc[0][nt][1], sc[0][nt][3]), fmaxf(sc[1][nt][1], sc[1][nt][3]));
+#pragma unroll
+          for (int sh = 4; sh < 32; sh <<= 1) {   // over the 8 key lanes g
+            mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, sh));
+            mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, sh));
+          }
+          const float mn0 = fmaxf(m[nt][0], mx0), mn1 = fmaxf(m[nt][1], mx1);
+          const float cr0 = ex2_approx(m[nt][0] - mn0), cr1 = ex2_approx(m[nt][1] - mn1);
+          m[nt][0] = mn0; m[nt][1] = mn1;
+          l[nt][0] *= cr0; l[nt][1] *= cr1;
+          o[nt][0] *= cr0; o[nt][1] *= cr1; o[nt][2] *= cr0; o[nt][3] *= cr1;
+        }
+#pragma unroll
+        for (int kt = 0; kt < 2; ++kt) {
+          // A = V^T: (channel g, keys 2t, 2t+1) (channel g + 8, ...) (channel g, keys 2t + 8, 2t + 9) (channel g + 8, ...)
+          const uint32_t a0 = movmatrix_trans(buf.v[2 * kt].x), a1 = movmatrix_trans(buf.v[2 * kt].y);
+          const uint32_t a2 = movmatrix_trans(buf.v[2 * kt + 1].x), a3 = movmatrix_trans(buf.v[2 * kt + 1].y);
+#pragma unroll
+          for (int nt = 0; nt < NT8; ++nt) {
+            const float p0 = ex2_approx(sc[kt][nt][0] - m[nt][0]), p1 = ex2_approx(sc[kt][nt][1] - m[nt][1]);
+            const float p2 = ex2_approx(sc[kt][nt][2] - m[nt][0]), p3 = ex2_approx(sc[kt][nt][3] - m[nt][1]);
+            l[nt][0] += p0 + p2;
+            l[nt][1] += p1 + p3;
+            mma_bf16(o[nt], a0, a1, a2, a3, movmatrix_trans(pack_bf16x2(p0, p1)), movmatrix_trans(pack_bf16x2(p2, p3)));
+          }
         }
       };
 #pragma unroll 1
@@ -483,25 +543,31 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
           attn_compute(kv1);
         }
       }
-      // per-warp partial -> shared memory.  o[c][0..1]: row g, channels 4t + 2c + {0, 1}; o[c][2..3]: row g + 8
+      // per-warp partial -> shared memory.  O^T rows: virtual channel g -> physical 4 (g >> 1) + (g & 1), g + 8 -> that + 2
 #pragma unroll
-      for (int rr = 0; rr < NT8; ++rr) {
-        float lr = l[rr];
-        lr += __shfl_xor_sync(0xffffffffu, lr, 1);
-        lr += __shfl_xor_sync(0xffffffffu, lr, 2);
-        const int row = g + 8 * rr;
-        *reinterpret_cast<float4*>(&s.tpart[warp][row][4 * t]) = make_float4(o[0][2 * rr], o[0][2 * rr + 1], o[1][2 * rr], o[1][2 * rr + 1]);
-        if (t == 0) { s.tpart[warp][row][16] = m[rr]; s.tpart[warp][row][17] = lr; }
+      for (int nt = 0; nt < NT8; ++nt) {
+        float l0 = l[nt][0], l1 = l[nt][1];
+#pragma unroll
+        for (int sh = 4; sh < 32; sh <<= 1) {
+          l0 += __shfl_xor_sync(0xffffffffu, l0, sh);
+          l1 += __shfl_xor_sync(0xffffffffu, l1, sh);
+        }
+        const int ch = 4 * (g >> 1) + (g & 1), tok = nt * 8 + 2 * t;
+        s.tpart[warp][tok][ch] = o[nt][0];
+        s.tpart[warp][tok + 1][ch] = o[nt][1];
+        s.tpart[warp][tok][ch + 2] = o[nt][2];
+        s.tpart[warp][tok + 1][ch + 2] = o[nt][3];
+        if (g == 0) {
+          s.tpart[warp][tok][16] = m[nt][0]; s.tpart[warp][tok][17] = l0;
+          s.tpart[warp][tok + 1][16] = m[nt][1]; s.tpart[warp][tok + 1][17] = l1;
+        }
       }
     }
     __syncthreads();
     DT_TRACE(9);
-    wait_cluster_start();
-    {   // merge the 16 warps' partials; thread = (row, channel) for tid < 256
+    if (tid < 256) {   // merge the 16 warps' partials; thread = (row, channel)
       const int row = tid >> 4, ch = tid & 15;
-      float val = 0.f;
-      const bool act = tid < 256 && row < Nt;
-      if (act) {
+      if (row < Nt) {
         float M = -INFINITY;
 #pragma unroll
         for (int w = 0; w < DT_WARPS; ++w) M = fmaxf(M, s.tpart[w][row][16]);
@@ -512,24 +578,29 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
           num += s.tpart[w][row][ch] * f;
           den += s.tpart[w][row][17] * f;
         }
-        val = num / den;
+        s.tqs[row][ch] = num / den;
       }
-      if (tid < 256) bcast_op_pair(s.opC, act ? row : 0, 16 * (int)rank + ch, val, act);
     }
     if (flags & DEC_TOK_MLP) load_w<256>(wt, p.m1_w + (long long)(256 * (int)rank + 16 * warp) * 256, 256, g, t);   // mlp1 tile of this warp
+    __syncthreads();
+    wait_cluster_start();
+    if (tid < 2 * Nt) {
+      const int row = tid >> 1, c8 = (tid & 1) * 8;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = s.tqs[row][c8 + j];
+      bcast_op8(s.opC, row, 16 * (int)rank + c8, v);
+    }
     DT_TRACE(10);
     cluster_sync_all();
     DT_TRACE(11);
     if (warp < 8) ks_mma(s.opC, warp & 3);   // output projection (K = 128): 2 tiles x 4 k-slices
     __syncthreads();
-    if (e_tok < Nt) {
-      const int col = 32 * (int)rank + 16 * e_tile + e_col;
-      bcast_f32(&s.ybuf[e_tok][col], ks_sum(e_tile, 4, e_tok, e_col) + __ldg(p.to_b + col) + s.xs[e_tok][col]);
-    }
+    ks_bcast_rows(4, P_TO, true);
     DT_TRACE(12);
     cluster_sync_all();
     DT_TRACE(13);
-    layer_norm(p.n2_w, p.n2_b, (flags & DEC_TOK_MLP) != 0, !(flags & DEC_TOK_MLP));
+    layer_norm(P_N2W, P_N2B, (flags & DEC_TOK_MLP) != 0, !(flags & DEC_TOK_MLP));
     __syncthreads();
     DT_TRACE(14);
   }
@@ -537,10 +608,9 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
   // ================================================================== token MLP (:200-203) + i2t k / v projections (:205-208)
   if (flags & DEC_TOK_MLP) {
     {   // hidden units [256 r + 16 w, + 16)
-      const int h0 = 256 * (int)rank + 16 * warp;
-      const float bz0 = __ldg(p.m1_b + h0 + g), bz1 = __ldg(p.m1_b + h0 + g + 8);
+      const float bz0 = s.prm[P_M1 + 16 * warp + g], bz1 = s.prm[P_M1 + 16 * warp + g + 8];
       float o[NT8][4];
-      mma_w<256, NT8>(wt, s.opB, 0, o, g, t);
+      mma_w<256, NT8, true>(wt, s.opB, 0, o, g, t);
       // second GEMM over this CTA's hidden slice: output columns [16 w, 16 w + 16), requested while the hidden units are stored
       load_w<256>(wt, p.m2_w + (long long)(16 * warp) * 2048 + 256 * (int)rank, 2048, g, t);
 #pragma unroll
@@ -548,50 +618,56 @@ __global__ void __cluster_dims__(CLD, 1, 1) __launch_bounds__(DT_THREADS, 1) dec
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = g + 8 * (e >> 1), tok = nt * 8 + 2 * t + (e & 1);
-          bf16 hi, lo;
-          split_bf16(tok < Nt ? fmaxf(o[nt][e] + ((e >> 1) ? bz1 : bz0), 0.f) : 0.f, hi, lo);
-          s.opH[0][tok][16 * warp + col] = hi;
-          s.opH[1][tok][16 * warp + col] = lo;
+          s.opH[0][tok][16 * warp + col] = __float2bfloat16_rn(tok < Nt ? fmaxf(o[nt][e] + ((e >> 1) ? bz1 : bz0), 0.f) : 0.f);
         }
     }
     __syncthreads();
     DT_TRACE(15);
-    {   // partial sums -> owner CTA w / 2
+    {   // partial sums of all 256 output columns (hidden activations bf16: no lo half) -> local staging -> owner CTAs
       float o[NT8][4];
-      mma_w<256, NT8>(wt, s.opH, 0, o, g, t);
+      mma_w<256, NT8, false>(wt, s.opH, 0, o, g, t);
 #pragma unroll
       for (int nt = 0; nt < NT8; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int col = 16 * (warp & 1) + g + 8 * (e >> 1), tok = nt * 8 + 2 * t + (e & 1);
-          if (tok < Nt) st_cluster_f32(mapa_u32(smem_u32(&s.part[rank][tok][col]), (uint32_t)(warp >> 1)), o[nt][e]);
-        }
+        for (int e = 0; e < 4; ++e) s.ybuf[nt * 8 + 2 * t + (e & 1)][16 * warp + g + 8 * (e >> 1)] = o[nt][e];
     }
     // image->token attention k (x + pe) and v (x) columns [16 r, 16 r + 16): 2 tiles x 8 k-slices
     load_w<32>(ws, (warp < 8 ? p.ik_w : p.iv_w) + (long long)(16 * rank) * 256 + 32 * (warp & 7), 256, g, t);
+    __syncthreads();
+#pragma unroll
+    for (int i = tid; i < 8 * Nt * 8; i += DT_THREADS) {   // (token, owner, 4 columns): 16 bytes each to the owner's `part`
+      const int cg = (i & 7) * 4, owner = (i >> 3) & 7, tok = i >> 6;
+      const uint4 v = *reinterpret_cast<const uint4*>(&s.ybuf[tok][32 * owner + cg]);
+      st_cluster_v4(mapa_u32(smem_u32(&s.part[rank][tok][cg]), (uint32_t)owner), v);
+    }
     DT_TRACE(16);
     cluster_sync_all();
     DT_TRACE(17);
-    {   // reduce this CTA's 32 columns in fixed source order, + bias + residual, all-gather
-      const int tok = tid >> 5, col = tid & 31, cg = 32 * (int)rank + col;
-      if (tok < Nt) {
-        float v = s.part[0][tok][col];
+    if (tid < 8 * Nt) {   // reduce this CTA's 32 columns in fixed source order, + bias + residual, all-gather
+      const int tok = tid >> 3, cg = (tid & 7) * 4, col = 32 * (int)rank + cg;
+      float4 v = *reinterpret_cast<const float4*>(&s.part[0][tok][cg]);
 #pragma unroll
-        for (int r = 1; r < CLD; ++r) v += s.part[r][tok][col];
-        bcast_f32(&s.ybuf[tok][cg], v + __ldg(p.m2_b + cg) + s.xs[tok][cg]);
+      for (int r = 1; r < CLD; ++r) {
+        const float4 u = *reinterpret_cast<const float4*>(&s.part[r][tok][cg]);
+        v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
       }
+      const float4 bz = *reinterpret_cast<const float4*>(&s.prm[P_M2 + cg]);
+      const float4 xr = *reinterpret_cast<const float4*>(&s.xs[tok][col]);
+      v.x += bz.x + xr.x; v.y += bz.y + xr.y; v.z += bz.z + xr.z; v.w += bz.w + xr.w;
+      bcast_v4(&s.ybuf[tok][col], make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
     }
     DT_TRACE(18);
     cluster_sync_all();
     DT_TRACE(19);
-    layer_norm(p.n3_w, p.n3_b, true, true);
+    layer_norm(P_N3W, P_N3B, true, true);
     __syncthreads();
     ks_mma(warp < 8 ? s.opA : s.opB, warp & 7);
     __syncthreads();
-    if (e_tok < Nt) {
-      const float* bias = (e_tile == 0 ? p.ik_b : p.iv_b) + 16 * rank;
+    if (tid < 128 && e_tok < Nt) {
+      const float4 v = ks_sum4(e_tile, 8);
+      const float4 bz = *reinterpret_cast<const float4*>(&s.prm[(e_tile == 0 ? P_IK : P_IV) + e_cg]);
       float* dst = (e_tile == 0 ? p.kt : p.vt) + (long long)b * Nt * 128 + 16 * rank;
-      dst[e_tok * 128 + e_col] = ks_sum(e_tile, 8, e_tok, e_col) + __ldg(bias + e_col);
+      *reinterpret_cast<float4*>(dst + e_tok * 128 + e_cg) = make_float4(v.x + bz.x, v.y + bz.y, v.z + bz.z, v.w + bz.w);
     }
     DT_TRACE(20);
   }
