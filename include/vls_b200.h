@@ -51,6 +51,8 @@ void vls_launch_count_add(long long n);
  * "dec_fused": 1 (default) = the token side of the mask decoder's two-way layers (<= 16 token rows, image tokens a
  * multiple of 64) runs as thread-block-cluster kernels (dec_tok.cu) over head-major image projections; 0 = as the chain
  * of small kernels.
+ * "up2_tc": 1 (default) = the mask decoder's second ConvTranspose + hyper-network product runs as a tcgen05 GEMM with a
+ * fused epilogue (f32 skip features, width a multiple of 32); 0 = on the FP32 pipe.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -240,6 +242,7 @@ typedef struct vls_mask_decoder_weights {
   const void* up1_w; const float* up1_b;   /* bf16 [(dy*2+dx)*64+co][ci], f32 [256] (bias tiled x4) */
   const float *up_ln_w, *up_ln_b;          /* [64] */
   const float* up2_w; const float* up2_b;  /* f32 [4 pos][64 ci][32 co], [32] */
+  const void* up2_wh;                      /* bf16 [2 (hi, lo)][(dy*2+dx)*32+co][64 ci]: up2_w = hi + lo, for the tensor-core path */
   const void* hyper_w[3]; const float* hyper_b[3]; /* 4 MLPs batched: [4][256][256] x2, [4][32][256] */
   const void* iou_w[3];   const float* iou_b[3];   /* [256,256] x2, [4,256] */
   const void* obj_w[3];   const float* obj_b[3];   /* [256,256] x2, [1,256] */

@@ -105,6 +105,39 @@ def test_mask_decoder_video_and_llava(env):
     assert _stats(got16[0][:, :, ::4, ::4], torch.from_numpy(gold["dec_llava_masks_s4"]))[0] < 3e-2
 
 
+def test_mask_decoder_fused_paths_match_kernel_chain(env):
+    """The cluster-kernel token side (dec_tok.cu) and the tcgen05 ConvT#2 (up2_masks_tc) against the chain of small kernels
+    they replace (vls_set_tuning dec_fused / up2_tc = 0): same math, different summation order / operand rounding."""
+    from video_llava_seg_b200 import _lib
+
+    dev, sd, inp = env["dev"], env["sd"], env["inp"]
+    B = env["build"]
+    dec = B.load_prefixed(B.build_mask_decoder(), sd, "sam_mask_decoder.").to(dev).eval()
+    pe_mod = B.load_prefixed(B.build_prompt_encoder(), sd, "sam_prompt_encoder.").to(dev).eval()
+    pe = pe_mod.get_dense_pe()
+    emb, s0, s1 = inp["emb"].to(dev), inp["s0"].to(dev), inp["s1"].to(dev)
+    g = torch.Generator().manual_seed(3)
+    lib = _lib.lib()
+    try:
+        for ns in (2, 3, 9):   # 8, 9 (two token tiles) and 15 token rows
+            sparse = torch.randn(2, ns, 256, generator=g).to(dev)
+            dense = pe_mod.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(2, -1, 64, 64)
+            outs = []
+            for fused in (1, 0):
+                lib.vls_set_tuning(b"dec_fused", fused)
+                lib.vls_set_tuning(b"up2_tc", fused)
+                outs.append([o.float().clone() for o in dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse,
+                                                           dense_prompt_embeddings=dense, multimask_output=True,
+                                                           repeat_image=False, high_res_features=[s0, s1])])
+            for n, a, r in zip(("masks", "iou", "tokens", "obj"), *outs):
+                mx, mean = _stats(a, r)
+                print(f"fused vs chain, {6 + ns} tokens, {n}: max {mx:.3e} mean {mean:.3e}")
+                assert mx < 5e-3, (ns, n, mx)
+    finally:
+        lib.vls_set_tuning(b"dec_fused", 1)
+        lib.vls_set_tuning(b"up2_tc", 1)
+
+
 def test_memory_encoder(env):
     from oracle import sam2_path as O
 

@@ -41,7 +41,7 @@ class DecLayer(ctypes.Structure):
 class MaskDecoderWeights(ctypes.Structure):
     _fields_ = [("layers", DecLayer * 2), ("final_t2i", AttnW)] + _fields(
         "final_img_w", "final_img_b", "final_pe_add", "nf_w", "nf_b", "out_tokens", "up1_w", "up1_b", "up_ln_w",
-        "up_ln_b", "up2_w", "up2_b") + [("hyper_w", c_void_p * 3), ("hyper_b", c_void_p * 3), ("iou_w", c_void_p * 3),
+        "up_ln_b", "up2_w", "up2_b", "up2_wh") + [("hyper_w", c_void_p * 3), ("hyper_b", c_void_p * 3), ("iou_w", c_void_p * 3),
                                         ("iou_b", c_void_p * 3), ("obj_w", c_void_p * 3), ("obj_b", c_void_p * 3),
                                         ("iou_sigmoid", c_int)]
 
@@ -213,6 +213,9 @@ def pack_mask_decoder(sd, prefix, device, image_pe, iou_sigmoid=True):
     w2 = sd[up + "3.weight"]  # [64 ci, 32 co, 2, 2] -> [pos][ci][co]
     w.up2_w = k.f(w2.permute(2, 3, 0, 1).reshape(4, 64, 32))
     w.up2_b = k.f(sd[up + "3.bias"])
+    w2g = w2.permute(2, 3, 1, 0).reshape(4 * 32, 64).float()   # [(dy*2+dx)*32 + co][ci]
+    w2hi = w2g.to(torch.bfloat16)
+    w.up2_wh = k.h(torch.cat([w2hi.float(), w2g - w2hi.float()], 0))
     hp = prefix + "output_hypernetworks_mlps."
     for j in range(3):
         w.hyper_w[j] = k.h(torch.stack([sd[f"{hp}{m}.layers.{j}.weight"] for m in range(4)], 0))

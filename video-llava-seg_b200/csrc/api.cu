@@ -48,6 +48,10 @@ int vls_set_tuning(const char* key, int value) {
     g_dec_fused = value != 0;
     return 0;
   }
+  if (std::string(key) == "up2_tc") {   // mask decoder ConvT#2 + hyper product: 1 = tcgen05 GEMM, 0 = FP32-pipe kernel
+    g_up2_tc = value != 0;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

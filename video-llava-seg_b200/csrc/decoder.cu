@@ -311,6 +311,112 @@ up2_masks_kernel(const bf16* __restrict__ u, const float* __restrict__ w2t, cons
   }
 }
 
+// ------------------------------------------------------------------ upscaling stage 2 + hyper-network product, tensor cores
+// Same result as up2_masks_kernel; the ConvTranspose2d(64 -> 32, k2, s2) is a tcgen05 GEMM: a CTA owns 128 consecutive
+// input pixels (one row of the 128 x 128 stage-1 map), D[128 pixels][128 = (dy, dx, co)] = U[128][64] . W^T in tensor
+// memory.  The weights stay f32-exact: W = Wh + Wl (two bf16 matrices), 4 + 4 MMAs of K = 16 into the same accumulator.
+// Epilogue: thread = pixel reads its 4 x 32 accumulators, adds bias and the feat_s0 skip (two 8-byte loads per (dy, co),
+// 256 contiguous bytes per warp), GELU, dots the 32 channels with the M hyper-network vectors and stores 2 x M x 8 bytes.
+// The r1 kernel did the 134 MFMA of the convolution on the FP32 pipe (21.9 us = 12 TFLOP/s).
+constexpr int UP2_THREADS = 288;   // warps 0-7: epilogue (thread = (pixel = TMEM lane, dy)), warp 8: TMA + MMA
+constexpr int UP2_SMEM = 3 * 128 * 64 * 2 + 1024 + 256 + (4 * 32 + 32) * 4 + 64;
+
+template <int M>
+__global__ void __launch_bounds__(UP2_THREADS, 1)
+up2_masks_tc_kernel(const __grid_constant__ CUtensorMap tmU, const __grid_constant__ CUtensorMap tmW, const float* __restrict__ bias,
+                    const float* __restrict__ feat, long long feat_sb, const float* __restrict__ hyper, int h2, int w2,
+                    float* __restrict__ masks) {
+  extern __shared__ uint8_t up2_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(up2_smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sU = smem;                       // [128 pixels][64 ci] bf16, SW128
+  uint8_t* sW = smem + 128 * 64 * 2;        // [2][128 (pos, co)][64 ci]
+  float* sh = reinterpret_cast<float*>(smem + 3 * 128 * 64 * 2);   // [32 co][M] hyper (transposed), then [32] bias
+  float* sb = sh + 32 * M;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sb + 32);
+  uint64_t* done = full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, m0 = blockIdx.x * 128;
+  if (threadIdx.x == 0) {
+    mbar_init(full, 1);
+    mbar_init(done, 1);
+    fence_barrier_init();
+    tma_prefetch_desc(&tmU);
+    tma_prefetch_desc(&tmW);
+  }
+  if (warp == 8) {
+    tmem_alloc(tmem_slot, 128);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  pdl_enter();
+  if (warp == 8) {
+    if (elect_one()) {
+      mbar_expect_tx(full, 3 * 128 * 64 * 2);
+      tma_load_3d(sU, &tmU, full, 0, m0, b);
+      tma_load_3d(sW, &tmW, full, 0, 0, 0);
+      tma_load_3d(sW + 128 * 64 * 2, &tmW, full, 0, 128, 0);
+      mbar_wait(full, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(128, 128);
+      const uint64_t ad = make_desc_sw128(smem_u32(sU));
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const uint64_t bd = make_desc_sw128(smem_u32(sW + h * 128 * 64 * 2));
+#pragma unroll
+        for (int k = 0; k < 4; ++k) umma_ss(tmem, ad + 2 * k, bd + 2 * k, idesc, (h | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(done);
+    }
+  } else {
+    for (int i = threadIdx.x; i < 32 * M; i += 256) sh[i] = hyper[(long long)b * M * 32 + (i % M) * 32 + i / M];   // sh[co][m]
+    if (threadIdx.x < 32) sb[threadIdx.x] = bias[threadIdx.x];
+    const int q = warp & 3, dy = warp >> 2;   // TMEM lane quarter, output row parity
+    const int pix = m0 + q * 32 + lane;
+    const bool ok = pix < h2 * w2;
+    const int y = ok ? pix / w2 : 0, x = ok ? pix % w2 : 0;
+    const int H4 = 2 * h2, W4 = 2 * w2;
+    const float* fbase = feat + (long long)b * feat_sb + (long long)(2 * y + dy) * W4 + 2 * x;
+    float2 f[32];   // requested before the accumulator is ready
+#pragma unroll
+    for (int co = 0; co < 32; ++co)
+      f[co] = ok ? __ldg(reinterpret_cast<const float2*>(fbase + (long long)co * H4 * W4)) : make_float2(0.f, 0.f);
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // hyper / bias staged (epilogue warps only)
+    mbar_wait(done, 0);
+    tc_fence_after();
+    const uint32_t lane_off = uint32_t(q * 32) << 16;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+      uint32_t r[32];
+      tmem_ld32(tmem + lane_off + (dy * 2 + dx) * 32, r);
+      tc_wait_ld();
+      float mk[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) mk[m] = 0.f;
+#pragma unroll
+      for (int co = 0; co < 32; ++co) {
+        const float a = gelu_fast(__uint_as_float(r[co]) + sb[co] + (dx ? f[co].y : f[co].x));
+#pragma unroll
+        for (int m = 0; m < M; ++m) mk[m] += sh[co * M + m] * a;
+      }
+      if (dx == 0) {
+#pragma unroll
+        for (int m = 0; m < M; ++m) f[m].x = mk[m];   // park the dx = 0 results: one 8-byte store per m
+      } else if (ok) {
+#pragma unroll
+        for (int m = 0; m < M; ++m)
+          *reinterpret_cast<float2*>(masks + (((long long)b * M + m) * H4 + 2 * y + dy) * W4 + 2 * x) = make_float2(f[m].x, mk[m]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, 128);
+}
+
 // ------------------------------------------------------------------ best-IoU / object-gate selection
 // sam2_base.py:359-390: gate = obj_logit > 0; multimask -> argmax over iou[:,1:]; low_res = gate ? mask : -1024
 __global__ void select_best_kernel(const float* __restrict__ masks, const float* __restrict__ iou,
@@ -399,6 +505,27 @@ int launch_up2_masks(const void* u, const float* w2t, const float* bias, const v
     VLS_CUDA(cudaFuncSetAttribute(up2_masks_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   VLS_CUDA(launch_k(up2_masks_kernel<4>, dim3(dim3((w2 + 31) / 32, h2, B)), dim3(128), smem, stream, reinterpret_cast<const bf16*>(u), w2t, bias, feat, feat_bf16, feat_sb, hyper, h2, w2, masks));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+int g_up2_tc = 1;   // vls_set_tuning("up2_tc")
+// tensor-core path of the fused ConvT#2 + hyper product: f32 skip features, w2 a multiple of 32; wh = bf16 [2][128][64]
+int launch_up2_masks_tc(const void* u, const void* wh, const float* bias, const float* feat, long long feat_sb,
+                        const float* hyper, int B, int M, int h2, int w2, float* masks, cudaStream_t stream) {
+  VLS_REQUIRE((M == 1 || M == 4) && w2 % 32 == 0, "up2_masks_tc: M must be 1 or 4 and the width a multiple of 32");
+  CUtensorMap tmU, tmW;
+  VLS_TRY(make_tmap_bf16(&tmU, u, 64, (uint64_t)h2 * w2, B, 64, (long long)h2 * w2 * 64, 128));
+  VLS_TRY(make_tmap_bf16(&tmW, wh, 64, 256, 1, 64, 256 * 64, 128));
+  static unsigned long long attr1 = 0, attr4 = 0;
+  const dim3 grid((h2 * w2 + 127) / 128, B);
+  if (M == 4) {
+    if (first_use_on_device(&attr4)) VLS_CUDA(cudaFuncSetAttribute(up2_masks_tc_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+    VLS_CUDA(launch_k(up2_masks_tc_kernel<4>, grid, dim3(UP2_THREADS), UP2_SMEM, stream, tmU, tmW, bias, feat, feat_sb, hyper, h2, w2, masks));
+  } else {
+    if (first_use_on_device(&attr1)) VLS_CUDA(cudaFuncSetAttribute(up2_masks_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, UP2_SMEM));
+    VLS_CUDA(launch_k(up2_masks_tc_kernel<1>, grid, dim3(UP2_THREADS), UP2_SMEM, stream, tmU, tmW, bias, feat, feat_sb, hyper, h2, w2, masks));
+  }
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -153,6 +153,9 @@ int launch_up1_post(const void* g, const void* feat, int feat_bf16, long long fe
 int launch_up2_masks(const void* u, const float* w2t, const float* bias, const void* feat, int feat_bf16,
                      long long feat_sb, const float* hyper, int B, int M, int h2, int w2, float* masks,
                      cudaStream_t stream);
+int launch_up2_masks_tc(const void* u, const void* wh, const float* bias, const float* feat, long long feat_sb,
+                        const float* hyper, int B, int M, int h2, int w2, float* masks, cudaStream_t stream);
+extern int g_up2_tc;
 int launch_select_best(const float* masks, const float* iou, const float* tokens, const float* obj_logits, int B, int M,
                        int multimask, int HW, float* low_res, float* tok_sel, int* best_idx, float* is_obj,
                        float* occluded, cudaStream_t stream);

@@ -443,7 +443,11 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
   }
   // -- ConvT(64->32) + feat_s0 + GELU + (hyper @ upscaled) fused (mask_decoder.py:225,234): needs both branches
   VLS_TRY(fork_join(1, st));
-  VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, st));
+  if (w->up2_wh && s0_dtype == VLS_F32 && (2 * W) % 32 == 0 && g_up2_tc)   // tcgen05 path (decoder.cu)
+    VLS_TRY(launch_up2_masks_tc(up1, w->up2_wh, w->up2_b, reinterpret_cast<const float*>(feat_s0), s0_bstride, hyper, B, 4, 2 * H,
+                                2 * W, masks, st));
+  else
+    VLS_TRY(launch_up2_masks(up1, w->up2_w, w->up2_b, feat_s0, s0_dtype, s0_bstride, hyper, B, 4, 2 * H, 2 * W, masks, st));
   // -- mask tokens out
   return launch_gather_rows(queries + 2 * 256, (long long)Nt * 256, 256, B, 4, 256, tokens_out, st);
 }
