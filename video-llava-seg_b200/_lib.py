@@ -141,6 +141,9 @@ def lib():
         _declare(handle)
         _declare_modules(handle)
         _lib = handle
+        for kv in filter(None, os.environ.get("VLS_TUNING", "").split(",")):   # dev aid: VLS_TUNING="dec_fused=0,up2_tc=0"
+            k, v = kv.split("=")
+            check(handle.vls_set_tuning(k.strip().encode(), int(v)), f"vls_set_tuning({kv})")
     return _lib
 
 

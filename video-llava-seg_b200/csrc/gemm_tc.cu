@@ -295,6 +295,8 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
 
 }  // namespace
 
+int g_gemm_bn64_below = 296;   // vls_set_tuning("gemm_bn64_below")
+
 int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   GemmArgs a = a_in;
   VLS_REQUIRE(a.A && a.W && a.C, "gemm: null operand");
@@ -312,7 +314,9 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   if (a.a_div <= 0) a.a_div = 1;
   if (a.w_div <= 0) a.w_div = 1;
   const long long tiles128 = (long long)((a.M + 127) / 128) * ((a.N + 127) / 128) * a.batch;
-  if (tiles128 < 120 || a.N <= 64) return launch_bn<64>(a, stream);
+  // up to two waves of 128-wide tiles (M = 4096 projections): 64-wide tiles put 2-3 CTAs on every SM, so one CTA's
+  // epilogue runs under the others' loads and MMAs (the q/k projection + RoPE: 14.9 -> see DESIGN)
+  if (tiles128 < g_gemm_bn64_below || a.N <= 64) return launch_bn<64>(a, stream);
   return launch_bn<128>(a, stream);
 }
 

@@ -138,10 +138,11 @@ class FrameGraph:
 
 
 class SteadyStateGraph:
-    ARENA_FRAMES = 64     # frames of retained outputs allocated at once
+    ARENA_FRAMES = 64     # frames of retained outputs allocated at once (at least)
+    ARENA_MAX_FRAMES = 512  # ... and at most: the first arena covers the rest of the clip up to this many frames
 
     def __init__(self, model, state, frame_idx, batch_size, owner=None):
-        self._arena, self._arena_pos = None, 0
+        self._arena, self._arena_pos, self._arena_len = None, 0, 0
         self._owner = weakref.ref(owner) if owner is not None else None
         self.model, self.B = model, batch_size
         self.dev = state["device"]
@@ -225,7 +226,7 @@ class SteadyStateGraph:
         for d in range(1, self.n_ptr):
             self.bank_pos[self.ptr_off + d * self.k: self.ptr_off + (d + 1) * self.k] = self.ptr_pos_table[d]
         self._pos_src = None
-        self._arena, self._arena_pos = None, 0      # retained outputs of the previous clip stay with that clip
+        self._arena, self._arena_pos, self._arena_len = None, 0, 0      # retained outputs of the previous clip stay with that clip
         self.next_frame = frame_idx
 
     # ------------------------------------------------------------------ reuse across clips
@@ -333,8 +334,12 @@ class SteadyStateGraph:
         # each a potential multi-millisecond host stall); the yielded video-resolution tensor is a normal allocation
         # that the caching allocator recycles as soon as the consumer drops it.
         keep = [nchw, rows, pred, obj_ptr, obj_logits]
-        if self._arena is None or self._arena_pos == self.ARENA_FRAMES:
-            self._arena = [torch.empty((self.ARENA_FRAMES,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in keep]
+        if self._arena is None or self._arena_pos == self._arena_len:
+            # sized for the rest of the clip: an 80 MB arena every 64 frames was one cudaMalloc of 4 - 90 ms on a fresh box
+            # (bench.py's end-to-end windows showed it as a single 92 ms step)
+            left = int(state.get("num_frames", 0)) - frame_idx
+            self._arena_len = max(self.ARENA_FRAMES, min(self.ARENA_MAX_FRAMES, left))
+            self._arena = [torch.empty((self._arena_len,) + tuple(t.shape), dtype=t.dtype, device=t.device) for t in keep]
             self._arena_pos = 0
         dst = [a[self._arena_pos] for a in self._arena] + [torch.empty_like(video)]
         self._arena_pos += 1
