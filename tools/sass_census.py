@@ -1,5 +1,5 @@
 """Per-kernel census of the Blackwell-specific SASS in libvls_b200.so (cuobjdump -sass): tcgen05 MMAs (UTCHMMA), tensor-memory
-loads / stores (LDTM / STTM), TMA loads / stores (UTMALDG / UTMASTG), tcgen05 commits (UTCBAR), mbarrier ops (SYNCS), SFU
+loads / stores (LDTM / STTM), TMA loads / stores (UTMALDG / UTMASTG), tcgen05 commits (UTCBAR), warp-level mma.sync / movmatrix of the decoder's token-side cluster kernel (HMMA / MOVM), mbarrier ops (SYNCS), SFU
 exponentials (MUFU.EX2), packed FP32 (FFMA2 / FADD2) and the ELECT + BRA.U.ANY loops the compiler emits around uniform-datapath
 instructions in divergent code (must be 0).  usage: python tools/sass_census.py > profiles/sass_census.txt"""
 import collections, os, re, subprocess, sys
@@ -9,8 +9,8 @@ so = os.path.join(ROOT, "video-llava-seg_b200", "libvls_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 demangle = lambda n: subprocess.run(["c++filt", n], capture_output=True, text=True).stdout.strip() or n
 PAT = collections.OrderedDict([("UTCHMMA", r"\bUTCHMMA\b"), ("LDTM", r"\bLDTM\b"), ("STTM", r"\bSTTM\b"), ("UTMALDG", r"\bUTMALDG\b"),
-                               ("UTMASTG", r"\bUTMASTG\b"), ("UTCBAR", r"\bUTCBAR\b"), ("SYNCS", r"\bSYNCS\b"), ("MUFU.EX2", r"MUFU\.EX2"),
-                               ("FFMA2", r"\bFFMA2\b"), ("FADD2", r"\bFADD2\b"), ("BRA.U.ANY", r"BRA\.U\.ANY"), ("instr", r"^\s+/\*[0-9a-f]{4}\*/")])
+                               ("UTMASTG", r"\bUTMASTG\b"), ("UTCBAR", r"\bUTCBAR\b"), ("HMMA", r"\bHMMA\b"), ("MOVM", r"\bMOVM\b"), ("SYNCS", r"\bSYNCS\b"), ("MUFU.EX2", r"MUFU\.EX2"),
+                               ("FFMA2", r"\bFFMA2\b"), ("FADD2", r"\bFADD2\b"), ("BRA.U.ANY", r"BRA\.U\.ANY"), ("instr", r"^\s+/\*[0-9a-f]{4,6}\*/")])
 counts, name = collections.OrderedDict(), None
 for line in out.splitlines():
     m = re.search(r"Function : (\S+)", line)
