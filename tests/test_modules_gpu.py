@@ -65,6 +65,32 @@ def test_memory_attention_full_size_bf16_io(env):
     assert mx < 5e-2 and mean < 4e-3
 
 
+def test_memory_attention_mid_fused_matches_kernel_chain(env):
+    """mid_fused.cu (self-attention out-proj + residual, LayerNorm2, cross-attention q-proj + RoPE in one cluster kernel)
+    against the GEMM / LayerNorm / GEMM chain it replaces, at a ragged query count (2 objects, Nq = 4096) and the small shape."""
+    from video_llava_seg_b200 import _lib
+
+    dev, sd, inp = env["dev"], env["sd"], env["inp"]
+    m = env["build"].load_prefixed(env["build"].build_memory_attention(), sd, "memory_attention.").to(dev).eval()
+    g = torch.Generator().manual_seed(5)
+    nq, nk, b = 4096, 2 * 4096 + 16, 2
+    big = (torch.randn(nq, b, 256, generator=g) * 0.5, (torch.randn(nk, b, 64, generator=g) * 0.5).bfloat16(),
+           torch.randn(nq, b, 256, generator=g) * 0.5, torch.randn(nk, b, 64, generator=g) * 0.5, 16)
+    small = (inp["curr"], inp["mem"], inp["curr_pos"], inp["mem_pos"], inp["n_ptr_tokens"])
+    lib = _lib.lib()
+    try:
+        for name, (curr, mem, cpos, mpos, nptr) in (("small", small), ("big", big)):
+            outs = []
+            for fused in (1, 0):
+                lib.vls_set_tuning(b"mid_fused", fused)
+                outs.append(m(curr.to(dev), mem.to(dev), cpos.to(dev), mpos.to(dev), nptr).float().clone())
+            mx, mean = _stats(outs[0], outs[1])
+            print(f"mid_fused vs chain ({name}): max {mx:.3e} mean {mean:.3e}")
+            assert mx < 2e-2 and mean < 1e-3, (name, mx, mean)
+    finally:
+        lib.vls_set_tuning(b"mid_fused", 1)
+
+
 def test_mask_decoder_video_and_llava(env):
     from oracle import sam2_path as O
 

@@ -56,6 +56,10 @@ int vls_set_tuning(const char* key, int value) {
     g_gemm_bn64_below = value;
     return 0;
   }
+  if (std::string(key) == "mid_fused") {   // memory attention: self-attn out-proj + LN2 + cross-attn q-proj as one launch
+    g_mid_fused = value != 0;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

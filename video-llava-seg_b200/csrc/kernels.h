@@ -96,6 +96,21 @@ struct LayerTailArgs {
 };
 int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream);
 
+// x += ao Wo^T + bo;  q = RoPE(LayerNorm(x) Wq^T + bq)  -- the middle of a memory-attention layer in one cluster kernel
+// (mid_fused.cu): self-attention output projection + residual, LayerNorm2, cross-attention query projection + axial RoPE
+struct MidArgs {
+  const void* ao = nullptr;                                  // bf16 [B][M][256]
+  const void* wo = nullptr; const float* bo = nullptr;       // [256][256], [256]
+  const float* ln_w = nullptr; const float* ln_b = nullptr; float ln_eps = 1e-5f;
+  const void* wq = nullptr; const float* bq = nullptr;
+  float* x = nullptr;                                        // f32 [B][M][256], in place
+  const float* rope_cos = nullptr; const float* rope_sin = nullptr; int rope_period = 0;
+  void* q = nullptr; long long ldq = 256, q_bstride = 0;      // bf16 rows
+  int B = 1, M = 0;
+};
+int launch_mid_fused(const MidArgs& a, cudaStream_t stream);
+extern int g_mid_fused;
+
 // ---------------------------------------------------------------- connected components (cc.cu)
 size_t cc_workspace_bytes(int n, int h, int w, bool fill);
 int launch_cc_label(const uint8_t* img, int n, int h, int w, int32_t* labels, int32_t* counts, void* ws,

@@ -158,6 +158,15 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(fork_join(2, st));
     }
     VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, (long long)C * ldvs, C, 0, Nq, s_self));
+    if (g_mid_fused) {
+      // ---- self-attention output projection + residual, LayerNorm2 and the cross-attention query projection (+ RoPE) in
+      //      ONE cluster kernel (mid_fused.cu)
+      MidArgs a;
+      a.ao = ao; a.wo = Lw.sa_o_w; a.bo = Lw.sa_o_b; a.ln_w = Lw.n2_w; a.ln_b = Lw.n2_b; a.ln_eps = LN_EPS;
+      a.wq = Lw.ca_q_w; a.bq = Lw.ca_q_b; a.x = x; a.rope_cos = w->rope_cos; a.rope_sin = w->rope_sin; a.rope_period = Nq;
+      a.q = qk; a.ldq = 2 * C; a.q_bstride = (long long)Nq * 2 * C; a.B = B; a.M = Nq;
+      VLS_TRY(launch_mid_fused(a, st));
+    } else {
     {
       GemmArgs g = lin(ao, C, (long long)Nq * C, Lw.sa_o_w, Nq, C, C, B, Lw.sa_o_b, x, 0, C, (long long)Nq * C);
       g.residual = x; g.ld_res = C; g.res_bstride = (long long)Nq * C;
@@ -169,6 +178,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.ca_q_w, Nq, C, C, B, Lw.ca_q_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
       g.rope_cos = w->rope_cos; g.rope_sin = w->rope_sin; g.rope_period = Nq; g.rope_rows = Nq;
       VLS_TRY(launch_gemm(g, st));
+    }
     }
     if (!joined) {
       VLS_TRY(fork_join(0, st));
