@@ -202,7 +202,8 @@ def run_ours(args):
     config = make_config(args.workload, world)
     config["execution"] = "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay"
     config["e2e_path"] = ("pinned host features -> double-buffered H2D -> propagate_in_video(output_mode='binary': fused "
-                          "resize+threshold) -> uint8 mask D2H into pinned memory every step, consumer pipelined by one frame")
+                          "resize+threshold) -> uint8 mask D2H into pinned memory every step on a copy stream; step i's events close over the "
+                          "read-back of step i-1 (K steps = K complete read-backs), consumer pipelined by one frame")
     line = {"metric": wl["metric"], "unit": UNIT, "n_gpus": world, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic backbone features + seeded random-init weights",
             "config": config}
@@ -234,10 +235,20 @@ def run_ours(args):
         host = [torch.empty((B, 1, 1024, 1024), dtype=torch.uint8).pin_memory() for _ in range(2)] if d2h else None
         done = [torch.cuda.Event(), torch.cuda.Event()]
         checksum = 0
+        main = torch.cuda.current_stream(dev)
+        d2h_stream = torch.cuda.Stream(device=dev) if d2h else None
 
         def read_back(m, slot):   # with d2h the predictor runs in output_mode "binary": m is already the uint8 mask
-            host[slot].copy_(m, non_blocking=True)
-            done[slot].record()
+            # the copy engine reads the mask back on its own stream while the next frame is tracked (as a streaming client
+            # would); step i's timed region ends with a wait for step i-1's copy, so every window of K steps contains K
+            # complete read-backs
+            ready = torch.cuda.Event()
+            ready.record(main)
+            d2h_stream.wait_event(ready)
+            with torch.cuda.stream(d2h_stream):
+                host[slot].copy_(m, non_blocking=True)
+                done[slot].record(d2h_stream)
+            m.record_stream(d2h_stream)
 
         predictor.output_mode = "binary" if d2h else "logits"
         with sampler as clocks:
@@ -265,8 +276,9 @@ def run_ours(args):
                 starts[i].record()
                 _, _, m = next(gen)
                 if d2h:
-                    read_back(m, i % 2)                      # result of step i -> pinned host memory, inside its events
+                    read_back(m, i % 2)                      # result of step i -> pinned host memory (copy stream)
                     out_bytes = host[i % 2].numel()
+                    main.wait_event(done[(i - 1) % 2])       # ... and the previous step's read-back ends inside this step
                 stops[i].record()
                 if d2h and i > 0:
                     done[(i - 1) % 2].synchronize()          # consume step i-1's mask on the host
