@@ -55,6 +55,8 @@ void vls_launch_count_add(long long n);
  * fused epilogue (f32 skip features, width a multiple of 32); 0 = on the FP32 pipe.
  * "mid_fused": 1 (default) = self-attention output projection + residual, LayerNorm2 and the cross-attention query
  * projection (+ RoPE) of a memory-attention layer run as one cluster kernel; 0 = GEMM, LayerNorm, GEMM.
+ * "dec_img_fused": 1 (default, needs dec_fused) = image->token attention, its output projection, LayerNorm4 and the next
+ * image-side projections of the mask decoder run as one cluster kernel per layer (dec_img.cu); 0 = as four launches.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */

@@ -132,7 +132,7 @@ def test_mask_decoder_video_and_llava(env):
 
 
 def test_mask_decoder_fused_paths_match_kernel_chain(env):
-    """The cluster-kernel token side (dec_tok.cu) and the tcgen05 ConvT#2 (up2_masks_tc) against the chain of small kernels
+    """The cluster-kernel token side (dec_tok.cu) and image side (dec_img.cu) and the tcgen05 ConvT#2 (up2_masks_tc) against the chain of small kernels
     they replace (vls_set_tuning dec_fused / up2_tc = 0): same math, different summation order / operand rounding."""
     from video_llava_seg_b200 import _lib
 
@@ -151,6 +151,7 @@ def test_mask_decoder_fused_paths_match_kernel_chain(env):
             outs = []
             for fused in (1, 0):
                 lib.vls_set_tuning(b"dec_fused", fused)
+                lib.vls_set_tuning(b"dec_img_fused", fused)
                 lib.vls_set_tuning(b"up2_tc", fused)
                 outs.append([o.float().clone() for o in dec(image_embeddings=emb, image_pe=pe, sparse_prompt_embeddings=sparse,
                                                            dense_prompt_embeddings=dense, multimask_output=True,
@@ -161,6 +162,7 @@ def test_mask_decoder_fused_paths_match_kernel_chain(env):
                 assert mx < 5e-3, (ns, n, mx)
     finally:
         lib.vls_set_tuning(b"dec_fused", 1)
+        lib.vls_set_tuning(b"dec_img_fused", 1)
         lib.vls_set_tuning(b"up2_tc", 1)
 
 

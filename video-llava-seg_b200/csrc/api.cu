@@ -60,6 +60,10 @@ int vls_set_tuning(const char* key, int value) {
     g_mid_fused = value != 0;
     return 0;
   }
+  if (std::string(key) == "dec_img_fused") {   // mask decoder image side of a layer: 1 = one cluster kernel, 0 = i2t + GEMM + LN + GEMM
+    g_dec_img_fused = value != 0;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

@@ -86,6 +86,17 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// TMA store: a box in shared memory (the layout a TMA load of the same map would have produced) -> global memory.  The
+// source must have been made visible to the async proxy (fence.proxy.async) by its writers; the issuing thread commits the
+// group and waits for the READ of the source before the buffer is reused or the CTA exits.
+__device__ __forceinline__ void tma_store_3d(const void* smem_src, const CUtensorMap* m, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // multicast variant: the box lands at the same CTA-relative smem offset in every CTA of `cta_mask`, and each
 // destination CTA's mbarrier (same offset) receives the complete_tx for the bytes written into it
 __device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,

@@ -201,6 +201,25 @@ extern long long* g_dec_trace;
 bool dec_tok_supported(int Nt, int T);
 int launch_dec_tok(const DecTokArgs& a, cudaStream_t stream);
 
+// ---------------------------------------------------------------- mask decoder, image side of a layer (dec_img.cu)
+// image->token attention + output projection + residual + LayerNorm4 (keys f32 in place, bf16 copy) and the NEXT image-side
+// projections ([K_t2i | V_t2i | Q_i2t] of the following layer: 384 columns, or the final attention's [K | V]: 256) written
+// as head planes -- one 4-CTA cluster kernel per 128 image tokens.
+struct DecImgArgs {
+  int B = 1, T = 0, Nt = 0;
+  const void* planes_in = nullptr; long long planes_in_bstride = 0; int qplane = 16;   // q of head h = plane qplane + h
+  const float* kt = nullptr; const float* vt = nullptr;                                  // f32 [B][Nt][128]
+  const void* wo = nullptr; const float* bo = nullptr;                                   // i2t out-proj [256][128]
+  const float* ln_w = nullptr; const float* ln_b = nullptr; float ln_eps = 1e-5f;
+  float* keys = nullptr; void* keys_h = nullptr;                                         // f32 in place / bf16 [B][T][256]
+  int n_next = 0;                                                                        // 384, 256 or 0 (no projection)
+  const void* wn = nullptr; const float* bn = nullptr; const float* pe_add = nullptr;    // [n_next][256], [n_next], f32 [T][n_next]
+  void* planes_out = nullptr; long long planes_out_bstride = 0;
+};
+extern int g_dec_img_fused;
+bool dec_img_supported(int Nt, int T);
+int launch_dec_img(const DecImgArgs& a, cudaStream_t stream);
+
 // ---------------------------------------------------------------- memory encoder kernels (memenc.cu)
 int launch_mds1(const float* src, int mode, int B, int H, int W, int factor, float scale, float bias_v, const float* wgt,
                 const float* cb, const float* lnw, const float* lnb, float eps, void* out, cudaStream_t stream);

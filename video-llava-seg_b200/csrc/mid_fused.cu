@@ -63,7 +63,8 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
 
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
-                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmX, const MidParams p) {
+                 const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmX,
+                 const __grid_constant__ CUtensorMap tmQ, const MidParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;                          // ao tile, then the t tile (all-gathered)
@@ -96,6 +97,7 @@ mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmW0);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmX);
+    tma_prefetch_desc(&tmQ);
   }
   if (warp == 1) {
     tmem_alloc(tmem_slot, 128);
@@ -159,12 +161,11 @@ mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     MID_TRACE(2);
     float sum = 0.f, ss = 0.f;
-    float* xrow = p.x + (long long)bz * p.x_bstride + (long long)row * C + n0;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       uint32_t r[32];
       tmem_ld32(tmem + lane_off + TM_Y0 + k * 32, r);
-      const uint8_t* xs = sX + k * (BM * 128) + rl * 128;
+      uint8_t* xs = sX + k * (BM * 128) + rl * 128;
       float4 xv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + ((i ^ (rl & 7)) << 4));
@@ -178,8 +179,17 @@ mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         sum += (m.x + m.y) + (m.z + m.w);
         ss += (m.x * m.x + m.y * m.y) + (m.z * m.z + m.w * m.w);
         xm[k * 32 + 4 * i] = m.x; xm[k * 32 + 4 * i + 1] = m.y; xm[k * 32 + 4 * i + 2] = m.z; xm[k * 32 + 4 * i + 3] = m.w;
-        if (row_ok) *reinterpret_cast<float4*>(xrow + k * 32 + 4 * i) = m;
+        // the new residual row goes back into the staging tile (same swizzled slot) and out through a TMA store: thread = row
+        // global stores touch 32 cache lines per warp instruction (2.8 k cycles for this epilogue)
+        *reinterpret_cast<float4*>(xs + ((i ^ (rl & 7)) << 4)) = m;
       }
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) tma_store_3d(sX + k * (BM * 128), &tmX, n0 + 32 * k, m0, bz);
+      tma_store_commit();
     }
     const uint32_t dst = smem_u32(&stats[rank * BM + rl]);
 #pragma unroll
@@ -257,7 +267,9 @@ mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_wait(d1_full, 0);
     tc_fence_after();
     MID_TRACE(7);
-    bf16* qrow = p.q + (long long)bz * p.q_bstride + (long long)row * p.ldq + n0;
+    // q rows are staged in a dead panel of the t tile (a peer's panel: consumed by this CTA's MMAs, never read remotely) in
+    // the 128B-swizzled layout of a TMA box and stored by the TMA engine
+    uint8_t* qrow = sA + ((rank + 1) & 3) * (BM * 128) + rl * 128;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       uint32_t r[32];
@@ -275,11 +287,16 @@ mid_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         o[2 * i] = pack_bf16x2(a0 * c0 - b0 * s0, a0 * s0 + b0 * c0);
         o[2 * i + 1] = pack_bf16x2(a1 * c1 - b1 * s1, a1 * s1 + b1 * c1);
       }
-      if (row_ok) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          *reinterpret_cast<uint4*>(qrow + k * 32 + 8 * i) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-      }
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(qrow + (((4 * k + i) ^ (rl & 7)) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    }
+    fence_proxy_async();
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    if (threadIdx.x == 64) {
+      tma_store_3d(sA + ((rank + 1) & 3) * (BM * 128), &tmQ, n0, m0, bz);
+      tma_store_commit();
+      tma_store_wait_read();   // both store groups have read their shared-memory sources
     }
   }
   MID_TRACE(8);
@@ -299,11 +316,12 @@ int launch_mid_fused(const MidArgs& a, cudaStream_t stream) {
   VLS_REQUIRE(a.ao && a.wo && a.bo && a.ln_w && a.ln_b && a.wq && a.bq && a.x && a.q && a.rope_cos && a.rope_sin && a.B > 0 && a.M > 0 &&
               a.rope_period > 0, "mid_fused: bad arguments");
   VLS_REQUIRE(a.ldq % 8 == 0 && a.q_bstride % 8 == 0, "mid_fused: q strides must be multiples of 8");
-  CUtensorMap tmA, tmW0, tmW1, tmX;
+  CUtensorMap tmA, tmW0, tmW1, tmX, tmQ;
   VLS_TRY(make_tmap_bf16(&tmA, a.ao, C, a.M, a.B, C, (long long)a.M * C, BM));
   VLS_TRY(make_tmap_bf16(&tmW0, a.wo, C, C, 1, C, (long long)C * C, NS));
   VLS_TRY(make_tmap_bf16(&tmW1, a.wq, C, C, 1, C, (long long)C * C, NS));
   VLS_TRY(make_tmap_f32(&tmX, a.x, C, a.M, a.B, C, (long long)a.M * C, BM));
+  VLS_TRY(make_tmap_bf16(&tmQ, a.q, C, a.M, a.B, a.ldq, a.q_bstride, BM));
   MidParams p = {};
   p.M = a.M; p.b0 = a.bo; p.ln_w = a.ln_w; p.ln_b = a.ln_b; p.ln_eps = a.ln_eps; p.b1 = a.bq;
   p.x = a.x; p.x_bstride = (long long)a.M * C;
@@ -312,7 +330,7 @@ int launch_mid_fused(const MidArgs& a, cudaStream_t stream) {
   p.trace = g_ffn_trace;
   static unsigned long long attr_set = 0;
   if (first_use_on_device(&attr_set)) VLS_CUDA(cudaFuncSetAttribute(mid_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  VLS_CUDA(launch_k(mid_fused_kernel, dim3(CL, (a.M + BM - 1) / BM, a.B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmX, p));
+  VLS_CUDA(launch_k(mid_fused_kernel, dim3(CL, (a.M + BM - 1) / BM, a.B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmX, tmQ, p));
   VLS_POST_LAUNCH(1);
   return 0;
 }

@@ -341,7 +341,46 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     return launch_dec_tok(d, s_);
   };
 
-  for (int l = 0; l < 2; ++l) {
+  const bool img_fused = fused && dec_img_supported(Nt, T);
+  if (img_fused) {
+    // ---- both layers as cluster kernels: token side (dec_tok.cu) and image side (dec_img.cu).  Only layer 0's image-side
+    //      projection is a stand-alone GEMM (next to the token self-attention); every later one is produced by dec_img.
+    {
+      cudaStream_t side;
+      VLS_TRY(fork_begin(1, st, &side));
+      GemmArgs g = lin(keys_h, C, (long long)T * C, w->layers[0].img_w, T, 384, C, B, w->layers[0].img_b, kvq, 1, 384, (long long)T * 384);
+      g.residual = w->layers[0].img_pe_add; g.ld_res = 384; g.res_bstride = 0;
+      planes_out(g);
+      VLS_TRY(launch_gemm(g, side));
+      VLS_TRY(dec_tok(DEC_TOK_SELF | DEC_TOK_FIRST, &w->layers[0], nullptr, nullptr, nullptr, 0, st));
+      VLS_TRY(fork_join(1, st));
+    }
+    for (int l = 0; l < 2; ++l) {
+      const vls_dec_layer& L = w->layers[l];
+      VLS_TRY(dec_tok(DEC_TOK_CROSS | DEC_TOK_MLP, &L, &L.t2i, L.n2_w, L.n2_b, (long long)T * 384, st));
+      cudaStream_t side = st;
+      if (l == 0) {   // the next layer's token self-attention only needs the token rows: next to the image side
+        VLS_TRY(fork_begin(1, st, &side));
+        VLS_TRY(dec_tok(DEC_TOK_SELF, &w->layers[1], nullptr, nullptr, nullptr, 0, side));
+      }
+      DecImgArgs d;
+      d.B = B; d.T = T; d.Nt = Nt;
+      d.planes_in = kvq; d.planes_in_bstride = (long long)T * 384; d.qplane = 16;
+      d.kt = kt; d.vt = vt; d.wo = L.i2t.o_w; d.bo = L.i2t.o_b; d.ln_w = L.n4_w; d.ln_b = L.n4_b; d.ln_eps = LN_EPS;
+      d.keys = keys; d.keys_h = keys_h;
+      d.planes_out = kvq;   // in place: a cluster reads its rows' q planes before its first barrier and writes after it
+      if (l == 0) {
+        d.n_next = 384; d.wn = w->layers[1].img_w; d.bn = w->layers[1].img_b; d.pe_add = w->layers[1].img_pe_add;
+        d.planes_out_bstride = (long long)T * 384;
+      } else {
+        d.n_next = 256; d.wn = w->final_img_w; d.bn = w->final_img_b; d.pe_add = w->final_pe_add;
+        d.planes_out_bstride = (long long)T * 256;
+      }
+      VLS_TRY(launch_dec_img(d, st));
+      if (l == 0) VLS_TRY(fork_join(1, st));
+    }
+  }
+  for (int l = 0; l < 2 && !img_fused; ++l) {
     const vls_dec_layer& L = w->layers[l];
     // -- token self attention (sam/transformer.py:183-191); layer 0 drops the PE and the residual
     const float* pe = l == 0 ? nullptr : tokens0;
@@ -403,7 +442,7 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
   }
   VLS_TRY(launch_up1_post(scratch, feat_s1, s1_dtype, s1_bstride, B, H, W, w->up_ln_w, w->up_ln_b, LN2D_EPS, up1, up_side));
   // -- final tokens -> image attention (sam/transformer.py:127-132)
-  {
+  if (!img_fused) {
     GemmArgs g = lin(keys_h, C, (long long)T * C, w->final_img_w, T, 256, C, B, w->final_img_b, kvq, 1, 256, (long long)T * 256);
     g.residual = w->final_pe_add; g.ld_res = 256; g.res_bstride = 0;
     planes_out(g);
