@@ -57,6 +57,8 @@ void vls_launch_count_add(long long n);
  * projection (+ RoPE) of a memory-attention layer run as one cluster kernel; 0 = GEMM, LayerNorm, GEMM.
  * "dec_img_fused": 1 (default, needs dec_fused) = image->token attention, its output projection, LayerNorm4 and the next
  * image-side projections of the mask decoder run as one cluster kernel per layer (dec_img.cu); 0 = as four launches.
+ * "mds3_tc": 1 (default) = stage 3 of the mask down-sampler (16 -> 64 channels) runs as im2col + tcgen05 GEMM + LayerNorm2d/GELU;
+ * 0 = on the FP32 pipe.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
  * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
@@ -296,6 +298,7 @@ typedef struct vls_mem_encoder_weights {
   const float *c1_w, *c1_b, *ln1_w, *ln1_b;   /* f32 [4][9] */
   const float *c2_w, *c2_b, *ln2_w, *ln2_b;   /* f32 [9][4][16] */
   const float *c3_w, *c3_b, *ln3_w, *ln3_b;   /* f32 [9][16][64] */
+  const void* c3_wh;                          /* bf16 [64][(ky*3+kx)*16+ci]: the same weights for the tensor-core path (may be NULL) */
   const void* c4_w; const float *c4_b, *ln4_w, *ln4_b;  /* bf16 [256][9*64] (tap-major), f32 */
   const void* c5_w; const float* c5_b;        /* bf16 [256][256] */
   const void* pix_w; const float* pix_b;      /* bf16 [256][256] */

@@ -56,7 +56,7 @@ class CxBlock(ctypes.Structure):
 
 class MemEncoderWeights(ctypes.Structure):
     _fields_ = _fields("c1_w", "c1_b", "ln1_w", "ln1_b", "c2_w", "c2_b", "ln2_w", "ln2_b", "c3_w", "c3_b", "ln3_w",
-                       "ln3_b", "c4_w", "c4_b", "ln4_w", "ln4_b", "c5_w", "c5_b", "pix_w", "pix_b") + [
+                       "ln3_b", "c3_wh", "c4_w", "c4_b", "ln4_w", "ln4_b", "c5_w", "c5_b", "pix_w", "pix_b") + [
                            ("cx", CxBlock * 2)] + _fields("out_w", "out_b", "no_obj_embed")
 
 
@@ -251,6 +251,7 @@ def pack_mem_encoder(sd, prefix, device, no_obj_embed=None):
     w.c2_b, w.ln2_w, w.ln2_b = k.f(sd[e + "3.bias"]), k.f(sd[e + "4.weight"]), k.f(sd[e + "4.bias"])
     w.c3_w = k.f(sd[e + "6.weight"].permute(2, 3, 1, 0).reshape(9, 16, 64))
     w.c3_b, w.ln3_w, w.ln3_b = k.f(sd[e + "6.bias"]), k.f(sd[e + "7.weight"]), k.f(sd[e + "7.bias"])
+    w.c3_wh = k.h(sd[e + "6.weight"].permute(0, 2, 3, 1).reshape(64, 9 * 16))  # [co][(ky*3+kx)*16+ci]
     w.c4_w = k.h(sd[e + "9.weight"].permute(0, 2, 3, 1).reshape(256, 9 * 64))  # [co][(ky*3+kx)*64+ci]
     w.c4_b, w.ln4_w, w.ln4_b = k.f(sd[e + "9.bias"]), k.f(sd[e + "10.weight"]), k.f(sd[e + "10.bias"])
     w.c5_w, w.c5_b = k.h(sd[e + "12.weight"].reshape(256, 256)), k.f(sd[e + "12.bias"])

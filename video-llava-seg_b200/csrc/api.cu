@@ -64,6 +64,10 @@ int vls_set_tuning(const char* key, int value) {
     g_dec_img_fused = value != 0;
     return 0;
   }
+  if (std::string(key) == "mds3_tc") {   // mask down-sampler stage 3: 1 = im2col + tcgen05 GEMM + LN/GELU, 0 = FP32-pipe kernel
+    g_mds3_tc = value != 0;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

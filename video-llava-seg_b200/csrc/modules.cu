@@ -602,7 +602,15 @@ int vls_mem_encoder_forward(const vls_mem_encoder_weights* w, const void* pix_fe
   VLS_TRY(launch_mds1(mask, mask_mode, B, 16 * H, 16 * W, (mask_mode == 2 || mask_mode == 3) ? 4 : 1, sig_scale, sig_bias, w->c1_w, w->c1_b,
                       w->ln1_w, w->ln1_b, LN2D_EPS, m1, st));
   VLS_TRY(launch_mds2(m1, B, 8 * H, 8 * W, w->c2_w, w->c2_b, w->ln2_w, w->ln2_b, LN2D_EPS, m2, st));
-  VLS_TRY(launch_mds3(m2, B, 4 * H, 4 * W, w->c3_w, w->c3_b, w->ln3_w, w->ln3_b, LN2D_EPS, m3, st));
+  if (w->c3_wh && g_mds3_tc) {
+    // stage 3 (16 -> 64 channels) on tensor cores: im2col [4T][144] + tcgen05 GEMM (K = 144, zero-filled to 192 by TMA) + LN2d(64)
+    // + GELU; `col` and `scratch` are free until stage 4 (same sizes: 4T x 144 = T x 576, 4T x 64 = T x 256)
+    VLS_TRY(launch_im2col3x3s2(m2, B, 4 * H, 4 * W, 16, col, st));
+    VLS_TRY(launch_gemm(lin(col, 144, (long long)4 * T * 144, w->c3_wh, 4 * T, 64, 144, B, w->c3_b, scratch, 0, 64, (long long)4 * T * 64), st));
+    VLS_TRY(launch_ln64_gelu(scratch, (long long)B * 4 * T, w->ln3_w, w->ln3_b, LN2D_EPS, m3, st));
+  } else {
+    VLS_TRY(launch_mds3(m2, B, 4 * H, 4 * W, w->c3_w, w->c3_b, w->ln3_w, w->ln3_b, LN2D_EPS, m3, st));
+  }
   VLS_TRY(launch_im2col3x3s2(m3, B, 2 * H, 2 * W, 64, col, st));
   VLS_TRY(launch_gemm(lin(col, 576, (long long)T * 576, w->c4_w, T, C, 576, B, w->c4_b, scratch, 0, C, (long long)T * C), st));
   VLS_TRY(launch_ln256(scratch, B, T, w->ln4_w, w->ln4_b, LN2D_EPS, 1, nullptr, 0, 0, t, (long long)T * C, C, st));

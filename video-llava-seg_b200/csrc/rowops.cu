@@ -80,6 +80,31 @@ __global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long lo
   if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
+// ------------------------------------------------------------------ LayerNorm2d over 64 channels + GELU (mask down-sampler)
+// x: f32 rows [rows][64]; half a warp per row, lane owns 4 channels; out bf16 rows.
+__global__ void ln64_gelu_kernel(const float* __restrict__ x, long long rows, const float* __restrict__ w,
+                                 const float* __restrict__ bsh, float eps, bf16* __restrict__ out) {
+  pdl_enter();
+  const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+  const int c = (threadIdx.x & 15) * 4;
+  const bool ok = row < rows;
+  float4 v = ok ? *reinterpret_cast<const float4*>(x + row * 64 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float s = (v.x + v.y) + (v.z + v.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 64.0f);
+  v.x -= mean; v.y -= mean; v.z -= mean; v.w -= mean;
+  float q = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / 64.0f) + eps);
+  const float4 g = *reinterpret_cast<const float4*>(w + c), b = *reinterpret_cast<const float4*>(bsh + c);
+  if (ok)
+    *reinterpret_cast<uint2*>(out + row * 64 + c) =
+        make_uint2(pack_bf16x2(gelu_erf(v.x * rstd * g.x + b.x), gelu_erf(v.y * rstd * g.y + b.y)),
+                   pack_bf16x2(gelu_erf(v.z * rstd * g.z + b.z), gelu_erf(v.w * rstd * g.w + b.w)));
+}
+
 // ------------------------------------------------------------------ NCHW (+ optional addend) -> token rows
 // in element (b, c, y, x) at b*sb + c*sc + y*sh + x*sw (any of them may be 0 for expanded views).
 struct Strides4 { long long sb, sc, sh, sw; };
@@ -111,6 +136,39 @@ __global__ void nchw_to_rows_kernel(const void* __restrict__ in, int in_bf16, St
       if (out_bf16) out_bf16[o] = __float2bfloat16_rn(v);
     }
   }
+}
+
+// Channel-contiguous input (sc == 1: the "NCHW" tensor is a permuted view of token rows, which is how the memory attention
+// hands pix_feat_with_mem to the decoder): no transpose, a thread moves 4 channels of one token.  The generic kernel above
+// reads such a view with 4 useful bytes per 32-byte sector (7.6 us for 4 MB).
+__global__ void chlast_to_rows_kernel(const void* __restrict__ in, int in_bf16, Strides4 si, const void* __restrict__ add,
+                                      int add_bf16, Strides4 sa, int C, int H, int W, float* __restrict__ out_f32,
+                                      bf16* __restrict__ out_bf16, long long total4) {
+  pdl_enter();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = C >> 2, T = H * W;
+  const int c = (int)(i % c4) * 4;
+  const int t = (int)((i / c4) % T), b = (int)(i / ((long long)c4 * T));
+  const int y = t / W, x = t % W;
+  const long long ib = b * si.sb + y * si.sh + x * si.sw + c;
+  float v[4];
+  if (in_bf16) {
+    const uint2 r = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(in) + ib);
+    const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&r.x), d = *reinterpret_cast<const __nv_bfloat162*>(&r.y);
+    v[0] = __low2float(a); v[1] = __high2float(a); v[2] = __low2float(d); v[3] = __high2float(d);
+  } else {
+    const float4 r = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(in) + ib);
+    v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+  }
+  if (add) {
+    const long long ab = b * sa.sb + y * sa.sh + x * sa.sw;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += ld_any(add, ab + (c + k) * sa.sc, add_bf16);
+  }
+  const long long o = ((long long)b * T + t) * C + c;
+  if (out_f32) *reinterpret_cast<float4*>(out_f32 + o) = make_float4(v[0], v[1], v[2], v[3]);
+  if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + o) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
 // ------------------------------------------------------------------ token rows -> NCHW f32/bf16 (+ gated channel vector)
@@ -437,8 +495,27 @@ int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], cons
   Strides4 s1{si[0], si[1], si[2], si[3]};
   Strides4 s2{0, 0, 0, 0};
   if (add) s2 = Strides4{sa[0], sa[1], sa[2], sa[3]};
+  const int esz = in_bf16 ? 2 : 4;
+  const bool chlast = si[1] == 1 && C % 4 == 0 && si[0] % 4 == 0 && si[2] % 4 == 0 && si[3] % 4 == 0 &&
+                      (reinterpret_cast<uintptr_t>(in) % (4 * esz)) == 0;
+  if (chlast) {   // channel-contiguous view of token rows: plain vectorised copy (+ addend)
+    const long long total4 = (long long)B * H * W * (C / 4);
+    VLS_CUDA(launch_k(chlast_to_rows_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream, in, in_bf16, s1, add,
+                      add_bf16, s2, C, H, W, out_f32, reinterpret_cast<bf16*>(out_bf16), total4));
+    VLS_POST_LAUNCH(1);
+    return 0;
+  }
   dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), blk(32, 8);
   VLS_CUDA(launch_k(nchw_to_rows_kernel, dim3(grid), dim3(blk), 0, stream, in, in_bf16, s1, add, add_bf16, s2, C, H, W, out_f32, reinterpret_cast<bf16*>(out_bf16)));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
+int g_mds3_tc = 1;   // mask down-sampler stage 3 as im2col + tcgen05 GEMM (vls_set_tuning "mds3_tc")
+
+int launch_ln64_gelu(const float* x, long long rows, const float* w, const float* b, float eps, void* out, cudaStream_t stream) {
+  VLS_CUDA(launch_k(ln64_gelu_kernel, dim3((unsigned)((rows * 16 + 255) / 256)), dim3(256), 0, stream, x, rows, w, b, eps,
+                    reinterpret_cast<bf16*>(out)));
   VLS_POST_LAUNCH(1);
   return 0;
 }
