@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x -s --no-header -p no:cacheprovider -k "memory_encoder" 2>&1 | tail -12 | tee gpurun_out/r_tests1.log
+timeout 600 python -m pytest tests -m gpu -q -x -s --no-header -p no:cacheprovider -k "decoder" 2>&1 | tail -22 | tee gpurun_out/r_tests1.log
 timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider 2>&1 | tail -5 | tee gpurun_out/r_tests.log
 timeout 300 python tools/timeline_frame.py > gpurun_out/r_timeline.txt 2>&1
-grep -E "frame span|chlast|ln64|im2col" gpurun_out/r_timeline.txt | head -7
+grep -E "frame span" gpurun_out/r_timeline.txt | head -7
 timeout 900 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-pixels 2>gpurun_out/r_bench.err | tail -1 > gpurun_out/r_bench.json
 python - <<'PY'
 import json

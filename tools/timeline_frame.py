@@ -40,3 +40,4 @@ for s, d, n in rows[a:b]:
     print(f"{s - base:9.1f} {d:7.1f}  {n}")
     tot += d
 print("frame span us", rows[b][0] - base, "sum of kernel durations", tot)
+gen.close()   # (a generator finalised at interpreter exit prints a traceback from torch.no_grad's context manager)
