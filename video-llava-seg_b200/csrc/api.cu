@@ -68,6 +68,10 @@ int vls_set_tuning(const char* key, int value) {
     g_mds3_tc = value != 0;
     return 0;
   }
+  if (std::string(key) == "attn_bal_min_tiles") {   // balanced attention mode only for at least this many 128-key tiles
+    g_attn_bal_min_tiles = value;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

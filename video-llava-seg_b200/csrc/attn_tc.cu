@@ -582,6 +582,8 @@ size_t attn_part_ml_offset(int B, int Nq, int splits, int dv) {   // byte offset
   return align256((size_t)B * splits * Nq * dv * 4);
 }
 
+int g_attn_bal_min_tiles = 64;   // balanced mode only for at least this many key tiles (vls_set_tuning "attn_bal_min_tiles")
+
 int attn_pick_splits(int B, int Nq, int Nk) {
   const int qtiles = (Nq + BM - 1) / BM;
   const int ntiles = (Nk + BN - 1) / BN;
@@ -593,7 +595,7 @@ int attn_pick_splits(int B, int Nq, int Nk) {
   // 1.73 waves): deal the (query tile, key tile) units out evenly instead.
   // Only where the fixed path needs KV splits (and therefore partials + a combine) anyway: with many query tiles
   // (s == 1) it writes bf16 outputs directly, and trading that for f32 partials cost 17 % at B=8 (measured).
-  if (g_attn_balanced && s >= 2 && ntiles >= 64 && bal_ok(qtiles * B, ntiles)) {
+  if (g_attn_balanced && s >= 2 && ntiles >= g_attn_bal_min_tiles && bal_ok(qtiles * B, ntiles)) {
     const long long ctas = (long long)qtiles * B * s;
     const long long waves = (ctas + BAL_CTAS - 1) / BAL_CTAS;
     if (ctas * 100 < waves * BAL_CTAS * 94) return 0;     // the fixed split would leave > 6 % of the SM-waves idle

@@ -58,6 +58,7 @@ struct AttnArgs {
 };
 extern int g_attn_cluster;
 extern int g_attn_balanced;
+extern int g_attn_bal_min_tiles;
 extern int g_attn_v_rows;
 extern long long* g_attn_trace;
 size_t attn_workspace_bytes(int B, int Nq, int splits, int dv = 256);
