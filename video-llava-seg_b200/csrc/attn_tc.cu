@@ -91,7 +91,7 @@ struct Seg {
 template <int CL, bool BAL, int DV, bool VMN>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const AttnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in both CTAs of the pair, so this alignment is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -419,6 +419,31 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     } else {
       // partial row: balanced mode -> [slot][row in tile]; fixed splits -> [batch][split][query row]
       const long long prow = BAL ? (long long)S.slot * BM + rl : ((long long)bz * p.splits + blockIdx.y) * p.Nq + row;
+      if (!BAL && CL == 1) {
+        // fixed splits: the f32 partial tile leaves through the TMA engine.  thread = row stores to global memory touch 32
+        // cache lines per warp instruction (8 k wavefronts for this 128 KB tile); here each thread drops its row into the dead
+        // Q / K buffers in the layout of [128 rows x 32 floats] 128B-swizzled boxes and one thread issues DV / 32 tensor stores
+        // (every MMA of the CTA has completed -- o_done -- and every TMA load has been consumed by one)
+#pragma unroll 1
+        for (int c = 0; c < OC / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem + lane_off + TM_O + half * OC + c * 32, o);
+          uint8_t* st = smem + (half * (OC / 32) + c) * (BM * 128) + rl * 128;
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(st + ((i ^ (rl & 7)) << 4)) =
+                make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+        }
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 64) {
+#pragma unroll 1
+          for (int bx = 0; bx < DV / 32; ++bx) tma_store_3d(smem + bx * (BM * 128), &tmP, bx * 32, S.q0, bz * p.splits + (int)blockIdx.y);
+          tma_store_commit();
+          tma_store_wait_read();
+        }
+      } else {
       float* po = p.part_o + prow * DV + half * OC;
 #pragma unroll 1
       for (int c = 0; c < OC / 32; ++c) {
@@ -432,6 +457,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             o4[i] = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
                                 __uint_as_float(o[4 * i + 3]));
         }
+      }
       }
       if (row_ok && half == 0) {
         p.part_ml[prow * 2] = m_used;
@@ -621,6 +647,9 @@ int launch_variant(const AttnArgs& a, const AttnParams& p, int qtiles, cudaStrea
   } else {
     VLS_TRY(make_tmap_bf16(&tmV, a.Vt, a.Nk, DV, a.B, a.ldvt, a.vt_bstride, CL > 1 ? DV / 2 : DV));   // V^T [DV][Nk]
   }
+  CUtensorMap tmP = tmQ;   // fixed splits: partial tiles f32 [B * splits][Nq][DV], stored by TMA (rows beyond Nq are clipped)
+  if (!BAL && CL == 1 && a.splits > 1)
+    VLS_TRY(make_tmap_f32(&tmP, a.part_o, DV, a.Nq, (uint64_t)a.B * a.splits, DV, (long long)a.Nq * DV, BM));
   static unsigned long long attr_set = 0;   // one flag word per instantiation
   if (first_use_on_device(&attr_set)) {
     auto kern = attn_fwd_kernel<CL, BAL, DV, VMN>;
@@ -638,7 +667,7 @@ int launch_variant(const AttnArgs& a, const AttnParams& p, int qtiles, cudaStrea
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
   auto kern = attn_fwd_kernel<CL, BAL, DV, VMN>;
-  VLS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, p));
+  VLS_CUDA(cudaLaunchKernelEx(&cfg, kern, tmQ, tmK, tmV, tmP, p));
   VLS_POST_LAUNCH(1);
   return 0;
 }

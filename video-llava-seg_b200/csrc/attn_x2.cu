@@ -117,7 +117,7 @@ __device__ __forceinline__ float2 exp2_poly2(float2 x) {
 template <int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-               const __grid_constant__ CUtensorMap tmV, const X2Params p) {
+               const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const X2Params p) {
   extern __shared__ uint8_t smem_raw[];
   float* xchg = reinterpret_cast<float*>(smem_raw);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + XCHG_BYTES);
@@ -410,13 +410,28 @@ attn_x2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                                  pack_bf16x2(__uint_as_float(o[8 * i + 6]) * inv, __uint_as_float(o[8 * i + 7]) * inv));
           } else {
             const long long prow = ((long long)bz * p.splits + split) * p.Nq + row;
-            float4* o4 = reinterpret_cast<float4*>(p.part_o + prow * DV + half * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              o4[i] = make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]),
-                                  __uint_as_float(o[4 * i + 3]));
             if (half == 0) *reinterpret_cast<float2*>(p.part_ml + prow * 2) = make_float2(m_used[g], lt);
           }
+        }
+        if (p.splits > 1) {
+          // the f32 partial tile leaves through the TMA engine: box (tile g, half) = [128 rows x 32 floats], 128B-swizzled, in
+          // the dead Q_B / K buffers (thread = row stores to global memory touch 32 cache lines per warp instruction)
+          uint8_t* st = smem + (g * 2 + half) * (BM * 128) + rl * 128;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(st + ((i ^ (rl & 7)) << 4)) =
+                make_float4(__uint_as_float(o[4 * i]), __uint_as_float(o[4 * i + 1]), __uint_as_float(o[4 * i + 2]), __uint_as_float(o[4 * i + 3]));
+        }
+      }
+      if (p.splits > 1) {
+        fence_proxy_async();
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 128) {   // first softmax thread
+#pragma unroll 1
+          for (int bx = 0; bx < 4; ++bx)
+            tma_store_3d(smem + bx * (BM * 128), &tmP, (bx & 1) * 32, q0 + (bx >> 1) * BM, bz * p.splits + split);
+          tma_store_commit();
+          tma_store_wait_read();
         }
       }
     }
@@ -503,6 +518,8 @@ int launch_attention_x2(const AttnArgs& a, cudaStream_t stream) {
   VLS_TRY(make_tmap_bf16(&tmQ, a.Q, D, a.Nq, a.B, a.ldq, a.q_bstride, BM));
   VLS_TRY(make_tmap_bf16(&tmK, a.K, D, a.Nk, a.B, a.ldk, a.k_bstride, BN));
   VLS_TRY(make_tmap_bf16(&tmV, a.Vt, DV, a.Nk, a.B, a.ldvt, a.vt_bstride, BN));
+  CUtensorMap tmP = tmQ;   // split partials f32 [B * splits][Nq][64], stored by TMA (rows beyond Nq are clipped)
+  if (a.splits > 1) VLS_TRY(make_tmap_f32(&tmP, a.part_o, DV, a.Nq, (uint64_t)a.B * a.splits, DV, (long long)a.Nq * DV, BM));
   static unsigned long long attr_set = 0;
   if (first_use_on_device(&attr_set)) {
     VLS_CUDA(cudaFuncSetAttribute(attn_x2_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -520,10 +537,10 @@ int launch_attention_x2(const AttnArgs& a, cudaStream_t stream) {
   const int pairs = (a.Nq + 2 * BM - 1) / (2 * BM);
   const dim3 grid(pairs, a.splits, a.B);
   switch (g_attn_x2_poly) {
-    case 0: VLS_CUDA(launch_k(attn_x2_kernel<0>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, p)); break;
-    case 1: VLS_CUDA(launch_k(attn_x2_kernel<1>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, p)); break;
-    case 3: VLS_CUDA(launch_k(attn_x2_kernel<3>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, p)); break;
-    default: VLS_CUDA(launch_k(attn_x2_kernel<2>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, p)); break;
+    case 0: VLS_CUDA(launch_k(attn_x2_kernel<0>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, tmP, p)); break;
+    case 1: VLS_CUDA(launch_k(attn_x2_kernel<1>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, tmP, p)); break;
+    case 3: VLS_CUDA(launch_k(attn_x2_kernel<3>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, tmP, p)); break;
+    default: VLS_CUDA(launch_k(attn_x2_kernel<2>, grid, dim3(THREADS), SMEM, stream, tmQ, tmK, tmV, tmP, p)); break;
   }
   VLS_POST_LAUNCH(1);
   if (a.splits > 1) {
