@@ -386,6 +386,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   }
   FFN_TRACE(11);
+  // residual rows of the reduce below: requested BEFORE the barrier (the loads were batched four at a time behind it: four
+  // L2 round trips of the 5.7 k-cycle reduce phase)
+  float4 xin_all[16];
+  if (warp >= 2) {
+    const int et = threadIdx.x - 64;
+    const int cg = et & 15, rsub = et >> 4;
+    const float* xres = (FRONT ? p.x_out : p.x_in) + (long long)bz * p.x_bstride + rank * 64 + cg * 4;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int rl = rsub + 8 * j;
+      xin_all[j] = (m0 + rl) < p.M ? *reinterpret_cast<const float4*>(xres + (long long)(m0 + rl) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   tc_fence_before();
   cluster_sync_all();            // all four partial slices of this CTA's 64 columns are in ITS shared memory
   FFN_TRACE(12);
@@ -397,7 +410,6 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 64;
     const int cg = et & 15, rsub = et >> 4;
     const long long xbase = (long long)bz * p.x_bstride + rank * 64 + cg * 4;
-    const float* xres = (FRONT ? p.x_out : p.x_in) + xbase;   // FRONT: the x_mid slice parked in x_out by the prologue
     float* xr = p.x_out + xbase;
     const float4 bb = __ldg(reinterpret_cast<const float4*>(p.b2 + rank * 64 + cg * 4));
 #pragma unroll
@@ -406,7 +418,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int rl = rsub + 8 * (j0 + i);
-        xin[i] = (m0 + rl) < p.M ? *reinterpret_cast<const float4*>(xres + (long long)(m0 + rl) * C) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xin[i] = xin_all[j0 + i];
 #pragma unroll
         for (int r = 0; r < CL; ++r) v[i][r] = *reinterpret_cast<const float4*>(smem + r * SL_BYTES + cg * SL_PITCH + rl * 16);
       }
