@@ -83,12 +83,14 @@ def test_memory_attention_mid_fused_matches_kernel_chain(env):
             outs = []
             for fused in (1, 0):
                 lib.vls_set_tuning(b"mid_fused", fused)
+                lib.vls_set_tuning(b"tail_quarter", fused)   # layer-tail prologue by column quarters vs full width per CTA
                 outs.append(m(curr.to(dev), mem.to(dev), cpos.to(dev), mpos.to(dev), nptr).float().clone())
             mx, mean = _stats(outs[0], outs[1])
             print(f"mid_fused vs chain ({name}): max {mx:.3e} mean {mean:.3e}")
             assert mx < 2e-2 and mean < 1e-3, (name, mx, mean)
     finally:
         lib.vls_set_tuning(b"mid_fused", 1)
+        lib.vls_set_tuning(b"tail_quarter", 1)
 
 
 def test_mask_decoder_video_and_llava(env):

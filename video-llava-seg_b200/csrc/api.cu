@@ -72,6 +72,10 @@ int vls_set_tuning(const char* key, int value) {
     g_attn_bal_min_tiles = value;
     return 0;
   }
+  if (std::string(key) == "tail_quarter") {   // layer-tail prologue by column quarters (1) or full width in every CTA (0)
+    g_tail_quarter = value != 0;
+    return 0;
+  }
   if (std::string(key) == "tail_fused") {  // memory-attention layer tail (out-proj + LN3 + FFN + next LN) as one launch
     g_tail_fused = value != 0;
     return 0;

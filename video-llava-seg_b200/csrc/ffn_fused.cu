@@ -97,12 +97,19 @@ __device__ __forceinline__ float2 ld_dsmem_f2(uint32_t cluster_addr) {
   return v;
 }
 
-// FRONT: tmA = ao [B][M][64] (box 128 x 64), tmW0 = folded out-proj weight [256][64] (box 256 x 64); else tmA = t [B][M][256]
-template <bool FRONT, bool BACK, int NCH, bool GELU>
+// FRONT != 0: tmA = ao [B][M][64] (box 128 x 64), tmW0 = folded out-proj weight [256][64] (box 256 x 64, or 64 x 64 for
+// FRONT == 2); else tmA = t [B][M][256].
+// FRONT == 1: every CTA computes the full-width x_mid and LayerNorm3 itself (13.6 k cycles: 128 KB residual tile per CTA, two
+//             passes over 256 TMEM columns per thread, thread = row global stores of the parked slice).
+// FRONT == 2: the column-quarter pattern of mid_fused.cu: CTA r computes x_mid columns [64 r, 64 r + 64) (4 MMAs, N = 64), the
+//             per-row statistics go over DSMEM, its normalised 64 columns are one K panel of the t operand and are
+//             all-gathered with bulk shared -> shared::cluster copies; the new residual slice leaves through a TMA store.
+//             The FRONT operands live in the (still idle) W2 ring, so the W1 ring streams from the first cycle.
+template <int FRONT, bool BACK, int NCH, bool GELU>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(THREADS, 1)
 ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW0,
                  const __grid_constant__ CUtensorMap tmW1, const __grid_constant__ CUtensorMap tmW2,
-                 const __grid_constant__ CUtensorMap tmX, const FfnParams p) {
+                 const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmXo, const FfnParams p) {
   extern __shared__ uint8_t smem_raw[];
   // the dynamic smem base has the same offset in every CTA of the cluster, so this alignment is identical too
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -122,8 +129,9 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* g0_done = g0_full + 1;         // FRONT: the out-proj MMAs have completed (x_mid partial in TMEM, W2 ring free)
   uint64_t* a_ready = g0_done + 1;         // FRONT: 128 epilogue threads have written t = LN(x_mid) into sA
   uint64_t* x_full = a_ready + 1;          // FRONT: the f32 residual tile has landed in its staging area (sA + 4 W1 slots)
-  uint64_t* x_free = x_full + 1;           // FRONT: ... and has been consumed: the W1 ring may be filled
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(x_free + 1);
+  uint64_t* x_free = x_full + 1;           // FRONT: ... and has been consumed: the W1 ring (FRONT == 2: the W2 ring) may be filled
+  uint64_t* t_full = x_free + 1;           // FRONT == 2: the three remote panels of the t tile have landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -144,9 +152,12 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(a_ready, 128);
     mbar_init(x_full, 1);
     mbar_init(x_free, 1);
+    mbar_init(t_full, 1);
+    if (FRONT == 2) mbar_expect_tx(t_full, (CL - 1) * BM * 128);   // armed before any peer can send
     fence_barrier_init();
     tma_prefetch_desc(&tmW0);
     if (FRONT) tma_prefetch_desc(&tmX);
+    if (FRONT == 2) tma_prefetch_desc(&tmXo);
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmW1);
     tma_prefetch_desc(&tmW2);
@@ -162,9 +173,19 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   pdl_enter();   // global memory from here on
   FFN_TRACE(0);
 
+  // FRONT == 2 has a cluster barrier in the middle of the epilogue warps' prologue: the producer / MMA warps arrive here and
+  // consume the phase right before the next cluster barrier
+  if (FRONT == 2 && warp < 2) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   if (warp == 0) {
     if (elect_one()) {   // elect.sync: a lane test makes the compiler wrap every TMA / tcgen05 instruction in an ELECT + BRA.U.ANY loop
-      if (FRONT) {   // staged in the (still idle) W2 ring: slot 0 = folded out-proj weight [256 x 64], slot 1 = ao tile [128 x 64]
+      if (FRONT == 2) {  // W2 ring slot 0: [W0 slice 64 x 64 | ao tile 128 x 64 | statistics | parameters], slot 1: residual slice f32
+        mbar_expect_tx(g0_full, 64 * 128 + BM * 128);
+        tma_load_3d(sW2, &tmW0, g0_full, 0, (int)rank * 64, 0);
+        tma_load_3d(sW2 + 64 * 128, &tmA, g0_full, 0, m0, bz);
+        mbar_expect_tx(x_full, BM * 64 * 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) tma_load_3d(sW2 + W2_SLOT_BYTES + k * (BM * 128), &tmX, x_full, (int)rank * 64 + 32 * k, m0, bz);
+      } else if (FRONT) {   // staged in the (still idle) W2 ring: slot 0 = folded out-proj weight [256 x 64], slot 1 = ao tile [128 x 64]
         mbar_expect_tx(g0_full, W2_SLOT_BYTES + BM * 128);
         tma_load_3d(sW2, &tmW0, g0_full, 0, 0, 0);
         tma_load_3d(sW2 + W2_SLOT_BYTES, &tmA, g0_full, 0, m0, bz);
@@ -180,7 +201,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       // panel streams in consumption order: chunk 0 W1 panels, [chunk c+1 W1 panels, chunk c W2 panels] ...
       int i1 = 0, i2 = 0;
-      if (FRONT) mbar_wait(x_free, 0);
+      if (FRONT == 1) mbar_wait(x_free, 0);
       auto load_w1 = [&](int c) {
 #pragma unroll 1
         for (int kp = 0; kp < 4; ++kp, ++i1) {
@@ -202,7 +223,8 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       load_w1(0);
       for (int c = 0; c < NCH; ++c) {
         if (c + 1 < NCH) load_w1(c + 1);
-        if (FRONT && c == 0) mbar_wait(g0_done, 0);   // the out-proj operands have been consumed: the W2 ring is free
+        if (FRONT == 1 && c == 0) mbar_wait(g0_done, 0);   // the out-proj operands have been consumed: the W2 ring is free
+        if (FRONT == 2 && c == 0) mbar_wait(x_free, 0);    // ... and so have the statistics, parameters and the residual slice
         load_w2(c);
       }
     }
@@ -242,7 +264,17 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(&w2_empty[s]);
         }
       };
-      if (FRONT) {
+      if (FRONT == 2) {
+        mbar_wait(g0_full, 0);
+        tc_fence_after();
+        constexpr uint32_t idesc0 = make_idesc_bf16(BM, 64);
+        const uint64_t ad = make_desc_sw128(smem_u32(sW2 + 64 * 128)), bd = make_desc_sw128(smem_u32(sW2));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_ss(tmem + TM_Y, ad + 2 * kk, bd + 2 * kk, idesc0, kk != 0 ? 1u : 0u);
+        umma_commit(g0_done);
+        mbar_wait(a_ready, 0);     // own panel of t = LN(x_mid) written ...
+        mbar_wait(t_full, 0);      // ... and the three remote ones have landed
+      } else if (FRONT) {
         mbar_wait(g0_full, 0);
         tc_fence_after();
         const uint64_t ad = make_desc_sw128(smem_u32(sW2 + W2_SLOT_BYTES)), bd = make_desc_sw128(smem_u32(sW2));
@@ -266,7 +298,99 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int rl = q * 32 + lane;
     const uint32_t lane_off = uint32_t(q * 32) << 16;
-    if (FRONT) {
+    if (FRONT == 2) {
+      // ---- column quarter: x_mid[:, 64 r : 64 r + 64] = x_in + ao (Wo Wv)_r^T + b0
+      float* prm = reinterpret_cast<float*>(sW2 + 64 * 128 + BM * 128 + CL * BM * 8);   // [b0 | ln_w | ln_b] slices
+      float2* stats = reinterpret_cast<float2*>(sW2 + 64 * 128 + BM * 128);             // [source rank][row]
+      uint8_t* sXq = sW2 + W2_SLOT_BYTES;                                                // residual slice: 2 boxes [128 x 32 f32]
+      const int n0 = (int)rank * 64;
+      {
+        const int i = threadIdx.x - 64;   // 0..127: 192 floats as 96 float2
+        if (i < 96) {
+          const int which = i >> 5, c2 = (i & 31) * 2;
+          const float* src = which == 0 ? p.b0 : which == 1 ? p.ln_w : p.ln_b;
+          *reinterpret_cast<float2*>(&prm[which * 64 + c2]) = __ldg(reinterpret_cast<const float2*>(src + n0 + c2));
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      mbar_wait(g0_done, 0);
+      mbar_wait(x_full, 0);
+      tc_fence_after();
+      FFN_TRACE(1);
+      float xm[64];
+      float sum = 0.f, ss = 0.f;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        uint32_t r[32];
+        tmem_ld32(tmem + lane_off + TM_Y + k * 32, r);
+        uint8_t* xs = sXq + k * (BM * 128) + rl * 128;
+        float4 xv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xv[i] = *reinterpret_cast<const float4*>(xs + ((i ^ (rl & 7)) << 4));
+        tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 bb = *reinterpret_cast<const float4*>(&prm[k * 32 + 4 * i]);
+          float4 m;
+          m.x = __uint_as_float(r[4 * i]) + bb.x + xv[i].x; m.y = __uint_as_float(r[4 * i + 1]) + bb.y + xv[i].y;
+          m.z = __uint_as_float(r[4 * i + 2]) + bb.z + xv[i].z; m.w = __uint_as_float(r[4 * i + 3]) + bb.w + xv[i].w;
+          sum += (m.x + m.y) + (m.z + m.w);
+          ss += (m.x * m.x + m.y * m.y) + (m.z * m.z + m.w * m.w);
+          xm[k * 32 + 4 * i] = m.x; xm[k * 32 + 4 * i + 1] = m.y; xm[k * 32 + 4 * i + 2] = m.z; xm[k * 32 + 4 * i + 3] = m.w;
+          *reinterpret_cast<float4*>(xs + ((i ^ (rl & 7)) << 4)) = m;   // parked slice of x_mid: out through a TMA store
+        }
+      }
+      fence_proxy_async();
+      {
+        const uint32_t dst = smem_u32(&stats[rank * BM + rl]);
+#pragma unroll
+        for (int r = 0; r < CL; ++r)
+          asm volatile("st.shared::cluster.v2.f32 [%0], {%1,%2};" ::"r"(mapa_u32(dst, (uint32_t)r)), "f"(sum), "f"(ss) : "memory");
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) tma_store_3d(sXq + k * (BM * 128), &tmXo, n0 + 32 * k, m0, bz);
+        tma_store_commit();
+      }
+      FFN_TRACE(2);
+      tc_fence_before();
+      cluster_sync_all();   // statistics of the four column quarters are here (warps 0 / 1 arrived at kernel start)
+      {
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int r = 0; r < CL; ++r) { const float2 q2 = stats[r * BM + rl]; s1 += q2.x; s2 += q2.y; }   // same order everywhere
+        const float mean = s1 * (1.0f / C);
+        const float rstd = rsqrtf(fmaxf(s2 * (1.0f / C) - mean * mean, 0.f) + p.ln_eps);
+        uint8_t* prow = sA + rank * (BM * 128) + rl * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 wa = *reinterpret_cast<const float4*>(&prm[64 + 8 * j]), wb = *reinterpret_cast<const float4*>(&prm[64 + 8 * j + 4]);
+          const float4 ba = *reinterpret_cast<const float4*>(&prm[128 + 8 * j]), bb = *reinterpret_cast<const float4*>(&prm[128 + 8 * j + 4]);
+          const uint32_t p0 = pack_bf16x2((xm[8 * j] - mean) * rstd * wa.x + ba.x, (xm[8 * j + 1] - mean) * rstd * wa.y + ba.y);
+          const uint32_t p1 = pack_bf16x2((xm[8 * j + 2] - mean) * rstd * wa.z + ba.z, (xm[8 * j + 3] - mean) * rstd * wa.w + ba.w);
+          const uint32_t p2 = pack_bf16x2((xm[8 * j + 4] - mean) * rstd * wb.x + bb.x, (xm[8 * j + 5] - mean) * rstd * wb.y + bb.y);
+          const uint32_t p3 = pack_bf16x2((xm[8 * j + 6] - mean) * rstd * wb.z + bb.z, (xm[8 * j + 7] - mean) * rstd * wb.w + bb.w);
+          *reinterpret_cast<uint4*>(prow + ((j ^ (rl & 7)) << 4)) = make_uint4(p0, p1, p2, p3);
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(a_ready);
+      asm volatile("bar.sync 1, 128;" ::: "memory");   // panel complete; statistics and parameters no longer needed
+      if (threadIdx.x == 64) {
+        const uint32_t src = smem_u32(sA + rank * (BM * 128)), bar = smem_u32(t_full);
+#pragma unroll
+        for (int d = 1; d < CL; ++d) {
+          const uint32_t peer = (rank + d) % CL;
+          asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                       ::"r"(mapa_u32(src, peer)), "r"(src), "r"(BM * 128), "r"(mapa_u32(bar, peer)) : "memory");
+        }
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // the parked slice has been written (the reduce re-reads it)
+        mbar_arrive(x_free);                                         // the W2 ring is free
+      }
+      FFN_TRACE(3);
+    } else if (FRONT) {
       // x_mid = x_in + ao (Wo Wv)^T + b0;  t = LN3(x_mid) -> sA (bf16, 128B-swizzled K-major panels)
       const int row = m0 + rl;
       const bool row_ok = row < p.M;
@@ -366,6 +490,7 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tc_fence_after();
     FFN_TRACE(9);
   }
+  if (FRONT == 2 && warp < 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   cluster_sync_all();            // ... and of every peer: their t tiles / W1 rings (the landing zone) are dead too
   FFN_TRACE(10);
   if (warp >= 2) {
@@ -491,17 +616,18 @@ ffn_fused_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 int g_ffn_fused = 1;   // memory attention: 1 = this kernel, 0 = two GEMM launches (vls_set_tuning "ffn_fused")
 long long* g_ffn_trace = nullptr;   // dev-only: 16 int64 clock64 stamps (tools/trace_ffn.py)
+int g_tail_quarter = 1;   // layer tail prologue: 1 = column quarters + all-gather (FRONT == 2), 0 = full width in every CTA
 int g_tail_fused = 1;  // memory attention: 1 = out-proj + LN3 + FFN + next LN in one launch (needs ffn_fused), 0 = separate
 
 namespace {
 
-template <bool FRONT, bool BACK, int NCH, bool GELU>
+template <int FRONT, bool BACK, int NCH, bool GELU>
 int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmW0, const CUtensorMap& tmW1, const CUtensorMap& tmW2,
-                   const CUtensorMap& tmX, const FfnParams& p, int B, cudaStream_t stream) {
+                   const CUtensorMap& tmX, const CUtensorMap& tmXo, const FfnParams& p, int B, cudaStream_t stream) {
   static unsigned long long attr_set = 0;   // one flag word per instantiation
   auto kern = ffn_fused_kernel<FRONT, BACK, NCH, GELU>;
   if (first_use_on_device(&attr_set)) VLS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-  VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, tmX, p));
+  VLS_CUDA(launch_k(kern, dim3(CL, (p.M + BM - 1) / BM, B), dim3(THREADS), SMEM_BYTES, stream, tmA, tmW0, tmW1, tmW2, tmX, tmXo, p));
   VLS_POST_LAUNCH(1);
   return 0;
 }
@@ -523,8 +649,8 @@ int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const vo
   FfnParams p = {};
   p.M = M; p.b1 = b1; p.b2 = b2; p.x_in = x; p.x_out = x; p.x_bstride = x_bstride;
   p.trace = g_ffn_trace;
-  if (gelu) return launch_variant<false, false, 2, true>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
-  return launch_variant<false, false, 4, false>(tmA, tmA, tmW1, tmW2, tmA, p, B, stream);
+  if (gelu) return launch_variant<0, false, 2, true>(tmA, tmA, tmW1, tmW2, tmA, tmA, p, B, stream);
+  return launch_variant<0, false, 4, false>(tmA, tmA, tmW1, tmW2, tmA, tmA, p, B, stream);
 }
 
 // The tail of a memory-attention layer in one launch (see the file header):
@@ -535,10 +661,12 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
               a.ln2_b && a.t_out && a.B > 0 && a.M > 0, "layer_tail: bad arguments");
   VLS_REQUIRE(a.x_in != a.x_out, "layer_tail: x_in and x_out must be different buffers");
   VLS_REQUIRE(a.t_out_st % 4 == 0 && a.t_out_sb % 4 == 0, "layer_tail: output strides must be multiples of 4");
-  CUtensorMap tmA, tmW0, tmW1, tmW2, tmX;
+  CUtensorMap tmA, tmW0, tmW1, tmW2, tmX, tmXo;
+  const bool quarter = g_tail_quarter != 0;
   VLS_TRY(make_tmap_f32(&tmX, a.x_in, C, a.M, a.B, C, (long long)a.M * C, BM));
+  VLS_TRY(make_tmap_f32(&tmXo, a.x_out, C, a.M, a.B, C, (long long)a.M * C, BM));
   VLS_TRY(make_tmap_bf16(&tmA, a.ao, 64, a.M, a.B, 64, (long long)a.M * 64, BM));
-  VLS_TRY(make_tmap_bf16(&tmW0, a.w0, 64, C, 1, 64, (long long)C * 64, C));
+  VLS_TRY(make_tmap_bf16(&tmW0, a.w0, 64, C, 1, 64, (long long)C * 64, quarter ? 64 : C));
   constexpr int FF = 2048;
   VLS_TRY(make_tmap_bf16(&tmW1, a.w1, C, FF, 1, C, (long long)FF * C, HC));
   VLS_TRY(make_tmap_bf16(&tmW2, a.w2, FF, C, 1, FF, (long long)FF * C, C));
@@ -548,7 +676,8 @@ int launch_layer_tail(const LayerTailArgs& a, cudaStream_t stream) {
   p.ln2_w = a.ln2_w; p.ln2_b = a.ln2_b; p.ln2_eps = a.ln2_eps;
   p.t_out = a.t_out; p.t_out_bf16 = a.t_out_bf16; p.t_out_st = a.t_out_st; p.t_out_sb = a.t_out_sb;
   p.trace = g_ffn_trace;
-  return launch_variant<true, true, 4, false>(tmA, tmW0, tmW1, tmW2, tmX, p, a.B, stream);
+  if (quarter) return launch_variant<2, true, 4, false>(tmA, tmW0, tmW1, tmW2, tmX, tmXo, p, a.B, stream);
+  return launch_variant<1, true, 4, false>(tmA, tmW0, tmW1, tmW2, tmX, tmXo, p, a.B, stream);
 }
 
 }  // namespace vls

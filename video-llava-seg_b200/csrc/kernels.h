@@ -81,6 +81,7 @@ int launch_ffn_fused(const void* t, long long ldt, long long t_bstride, const vo
                      int gelu = 0);
 extern int g_ffn_fused;
 extern int g_tail_fused;
+extern int g_tail_quarter;
 extern long long* g_ffn_trace;
 // x_mid = x_in + ao W0^T + b0;  x_out = x_mid + FFN(LN(x_mid));  t_out = LN2(x_out)   -- one cluster kernel
 struct LayerTailArgs {
