@@ -311,11 +311,23 @@ def test_resize_binarize_matches_interpolate(dev, shape, size):
         assert torch.equal(bits.cpu(), torch.from_numpy(np.packbits(u8.cpu().numpy(), axis=-1)))
 
 
-@pytest.mark.parametrize("B,H,W", [(1, 64, 64), (2, 20, 12), (24, 64, 64), (40, 30, 22)])
-def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W):
+@pytest.mark.parametrize("B,H,W,variant", [(1, 64, 64, 1), (2, 20, 12, 1), (24, 64, 64, 1), (24, 64, 64, 2), (24, 64, 64, 0),
+                                             (40, 30, 22, 1), (40, 30, 22, 2), (40, 30, 22, 0), (64, 10, 66, 1)])
+def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W, variant):
     """CXBlock head (memory_encoder.py:86-93): depth-wise 7x7 conv (pad 3) + LayerNorm2d(eps 1e-6) on NHWC rows, f32 in,
-    bf16 out.  Small batches take the per-row kernel, large ones the FFMA2 column-strip kernel (odd sizes exercise the
-    halo / ragged strips of both)."""
+    bf16 out.  Small batches take the per-row kernel, large ones the FFMA2 column-strip kernels (variant 1 / 2: input rows
+    staged by TMA with the halo zero-filled by the tensor map, 3 / 4 CTAs per SM; 0: the global-load kernel); odd sizes
+    exercise the halo / ragged strips / partial last row pieces of all of them."""
+    from video_llava_seg_b200._lib import check, ptr, stream
+
+    check(vls_lib.vls_set_tuning(b"dwconv_tma", variant))
+    try:
+        _dwconv7_case(dev, vls_lib, B, H, W)
+    finally:
+        check(vls_lib.vls_set_tuning(b"dwconv_tma", 1))
+
+
+def _dwconv7_case(dev, vls_lib, B, H, W):
     from video_llava_seg_b200._lib import check, ptr, stream
 
     x = _rand((B, H * W, 256), dev, 3)

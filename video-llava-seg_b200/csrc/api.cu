@@ -68,6 +68,10 @@ int vls_set_tuning(const char* key, int value) {
     g_mds3_tc = value != 0;
     return 0;
   }
+  if (std::string(key) == "dwconv_tma") {   // CXBlock depth-wise 7x7 strip kernel: 1 = input rows staged by TMA, 0 = global loads
+    g_dwconv_tma = value;   // 2: the variant capped at 128 registers (4 CTAs per SM)
+    return 0;
+  }
   if (std::string(key) == "attn_bal_min_tiles") {   // balanced attention mode only for at least this many 128-key tiles
     g_attn_bal_min_tiles = value;
     return 0;

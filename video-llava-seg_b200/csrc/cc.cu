@@ -169,6 +169,16 @@ __device__ __forceinline__ RowOcc row_occ(const uint8_t* occ, int BW, int by, in
 // the whole CTA (nthreads = blockDim.x, a multiple of 32).  `occ` must be complete (followed by __syncthreads) on
 // entry; on return (after the caller's __syncthreads) every occupied block's word is a NAME block index, every name's
 // word its root, and a root's word root | area << 14.
+#ifdef CC_TRACE
+__device__ long long g_cc_tr[8];
+__device__ int g_cc_cnt[4];
+#define CC_RMARK(i)                                            \
+  do {                                                         \
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_cc_tr[i] = clock64(); \
+  } while (0)
+#else
+#define CC_RMARK(i)
+#endif
 __device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, int BW, uint16_t* name_list,
                                                 int* name_count, int name_cap) {
   const int nthreads = blockDim.x;
@@ -259,6 +269,18 @@ __device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, 
           if (is_head && label != n0) atomicAdd(lab + label, area << CC_IDX_BITS);
         }
       }
+#ifdef CC_TRACE
+      if (blockIdx.x == 0 && warp == 0) {
+        const uint32_t un = __ballot_sync(0xffffffffu, (ca != INF && ca != runmin) || (cb != INF && cb != runmin && cb != ca) ||
+                                                           (cc != INF && cc != runmin && cc != ca && cc != cb));
+        if (lane == 0) {
+          g_cc_cnt[0] += un != 0;
+          g_cc_cnt[1] += __popc(un);
+          g_cc_cnt[2] += !(mx == -1 || mx == mn);
+          g_cc_cnt[3] += 1;
+        }
+      }
+#endif
       // rare: a run joining differently named components (every candidate of every lane, not just the lane's minimum)
       if (ca != INF && ca != runmin) ufa_union(lab, ca, runmin);
       if (cb != INF && cb != runmin && cb != ca) ufa_union(lab, cb, runmin);
@@ -269,7 +291,9 @@ __device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, 
     __syncwarp();
     if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
   }
+  CC_RMARK(0);
   __syncthreads();
+  CC_RMARK(1);
   // C. seams between regions (generic lock-free unions; every region is already labelled)
   //    C1: the first row of each band against the last row of the band above, inside the strip
   if (t_begin < t_end) {
@@ -314,6 +338,7 @@ __device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, 
     }
   }
   __syncthreads();
+  CC_RMARK(2);
   // D. every parent pointer written so far targets a NAME block (a run that started a new label): flatten the names
   //    (the only loop-y finds left) and hand the area parked on a name to its root.  Afterwards block -> name -> root is
   //    two plain loads and a root's word is root | area << 14.  Names are a few % of the blocks, so they are first
@@ -353,10 +378,12 @@ __device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, 
       if (occ[bi] & CC_NAME) push(bi);
   }
   __syncthreads();
+  CC_RMARK(3);
   {
     const int cnt = min(*name_count, name_cap);
     for (int i = threadIdx.x; i < cnt; i += nthreads) flatten(name_list[i]);
   }
+  CC_RMARK(4);
 }
 
 // FILL=false: img uint8 -> labels/counts int32.   FILL=true: scores f32 updated in place.
@@ -491,6 +518,14 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
     printf("cc_small<%d> cta %d: A %lld  B-D (region labeller) %lld  E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
            tr[4] - tr[1], tr[5] - tr[4]);
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    printf("   cta 0 thread 0: B (own band) %lld  wait for the other bands %lld  C %lld  D scan %lld  D flatten %lld  names %d\n",
+           g_cc_tr[0] - tr[1], g_cc_tr[1] - g_cc_tr[0], g_cc_tr[2] - g_cc_tr[1], g_cc_tr[3] - g_cc_tr[2],
+           g_cc_tr[4] - g_cc_tr[3], *name_count);
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    printf("   warp 0: %d rows, %d with a union (%d lanes), %d through the segmented scan\n", g_cc_cnt[3], g_cc_cnt[0], g_cc_cnt[1], g_cc_cnt[2]);
+    g_cc_cnt[0] = g_cc_cnt[1] = g_cc_cnt[2] = g_cc_cnt[3] = 0;
+  }
 #endif
 }
 

@@ -183,4 +183,21 @@ int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t ro
   return 0;
 }
 
+int make_tmap_f32_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_w,
+                       uint32_t box_h) {
+  std::call_once(g_encode_once, resolve_encode);
+  VLS_REQUIRE(g_encode != nullptr, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+  VLS_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
+  VLS_REQUIRE(C >= 4 && C <= 256 && C % 4 == 0 && box_w >= 1 && box_w <= 256 && box_h >= 1 && box_h <= 256, "TMA box out of range");
+  cuuint64_t gdim[4] = {C, W, H, B < 1 ? 1 : B};
+  cuuint64_t gstr[3] = {C * 4, W * C * 4, H * W * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)C, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(base), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VLS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(f32 nhwc) failed with CUresult %d", (int)r);
+  return 0;
+}
+
 }  // namespace vls

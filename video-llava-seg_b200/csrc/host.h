@@ -100,6 +100,11 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, uint64_t cols, uint64_t r
 int make_tmap_f32(CUtensorMap* out, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t row_stride,
                   uint64_t batch_stride, uint32_t box_rows);
 
+// 4-D f32 tensor map over a channel-last image batch [B][H][W][C] (C <= 256): box = (C, box_w, box_h, 1), no swizzle,
+// zero fill out of bounds (coordinates may be negative: the halo of a convolution).
+int make_tmap_f32_nhwc(CUtensorMap* out, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_w,
+                       uint32_t box_h);
+
 struct Workspace {  // bump allocator over a caller-owned device buffer
   char* base;
   size_t size, off;

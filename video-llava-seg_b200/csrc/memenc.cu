@@ -8,6 +8,8 @@
 
 namespace vls {
 
+int g_dwconv_tma = 1;   // vls_set_tuning("dwconv_tma")
+
 namespace {
 
 // bilinear sample of a low-res map at high-res pixel (Y, X), align_corners=False, integer factor F
@@ -491,16 +493,211 @@ dwconv7_ln_strip_kernel(const float* __restrict__ x, int H, int W, int R, const 
   }
 }
 
+// ---- v3: the strip kernel with its input rows staged by TMA.
+// What the ncu capture of v2 showed (profiles/r1_dwconv_strip_ncu_full_summary.txt): 100 M of its 170 M warp instructions were
+// not FFMA2 -- per two input rows 20 predicated LDG.64 with their zero fills, halo masks and 64-bit address arithmetic -- and the
+// issue slots were only half busy because every k-step began with 20 loads whose values the first FFMA2 needs.  Here a 4-D
+// tensor map over x [B][H][W][256] delivers each k-step's box (2 rows x 10 columns x 256 channels = 20 KB) into a two-stage
+// shared-memory ring: the halo is zero-filled by the TMA unit (coordinates may be negative / beyond the image), the box
+// of k-step s+2 is requested as soon as k-step s has been consumed, and a thread reads its channel pair with immediate-offset
+// LDS.64.  The depth-wise weights (50 KB) are read through L1 (ld.global.nc, 256 B per warp instruction): one copy per SM
+// instead of one per CTA, which leaves 40 KB of shared memory per CTA.  LayerNorm epilogue in packed f32x2 arithmetic.
+constexpr int DW_NST = 2;
+constexpr int DW_STAGE_FLOATS = 2 * (DW_TX + 6) * 256;
+constexpr size_t DW_TMA_SMEM = (size_t)DW_NST * DW_STAGE_FLOATS * 4 + 2 * 4 * 16 * 4 + DW_NST * 8;
+
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+}
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+dwconv7_ln_tma_kernel(const __grid_constant__ CUtensorMap tmX, int H, int W, int R, const float* __restrict__ wgt,
+                      const float* __restrict__ cb, const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                      bf16* __restrict__ out) {
+  pdl_enter();
+  extern __shared__ __align__(128) unsigned char dwt_smem[];
+  float* ring = reinterpret_cast<float*>(dwt_smem);                              // [DW_NST][2 rows][10 columns][256]
+  float* red = ring + DW_NST * DW_STAGE_FLOATS;                                  // [2 parity][4 warps][16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + 2 * 4 * 16);                // [DW_NST]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.z, y0 = blockIdx.y * R, x0 = blockIdx.x * DW_TX;
+  const int y_last = min(y0 + R, H) - 1;                   // last output row of this CTA
+  const int nsteps = (y_last - y0 + 8) >> 1;               // k-steps: input rows y0 - 3 + 2s and the next one, up to y_last + 3
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < DW_NST; ++s) mbar_init(&full[s], 1);
+    fence_barrier_init();
+#pragma unroll
+    for (int s = 0; s < DW_NST; ++s)
+      if (s < nsteps) {
+        mbar_expect_tx(&full[s], DW_STAGE_FLOATS * 4);
+        tma_load_4d(ring + s * DW_STAGE_FLOATS, &tmX, &full[s], 0, x0 - 3, y0 - 3 + 2 * s, b);
+      }
+  }
+  const float2 bias = *reinterpret_cast<const float2*>(cb + 2 * tid);
+  const float2 g = *reinterpret_cast<const float2*>(lnw + 2 * tid), be = *reinterpret_cast<const float2*>(lnb + 2 * tid);
+  const float2* w2p = reinterpret_cast<const float2*>(wgt) + tid;                // tap t: w2p[t * 128]
+  bf16* ob = out + (long long)b * H * W * 256 + 2 * tid;
+  __syncthreads();
+  float2 acc[8][DW_TX];   // eight partial output rows (slot = output row mod 8 relative to the strip); slots are started by tap (0, 0)
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+#pragma unroll
+    for (int j = 0; j < DW_TX; ++j) acc[s][j] = bias;
+  int parity = 0, step = 0;
+  for (int base = y0 - 3; base <= y_last + 3; base += 8) {
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const int yi = base + k;                     // input rows yi, yi + 1
+      if (yi > y_last + 3) break;
+      const int stage = (k >> 1) % DW_NST;         // base advances by 4 k-steps, DW_NST divides 4
+      mbar_wait(&full[stage], (uint32_t)(step / DW_NST) & 1u);
+      const float2* rs = reinterpret_cast<const float2*>(ring + stage * DW_STAGE_FLOATS) + tid;
+      float2 row[2][DW_TX + 6];
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int i = 0; i < DW_TX + 6; ++i) row[r][i] = rs[(r * (DW_TX + 6) + i) * 128];
+#pragma unroll
+      for (int dy = 0; dy < 7; ++dy) {             // input row yi+r, tap row dy -> output row yi + r + 3 - dy
+#pragma unroll
+        for (int dx = 0; dx < 7; ++dx) {
+          const float2 w2 = __ldg(w2p + (dy * 7 + dx) * 128);
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const int slot = (k + r + 3 - dy + 8) % 8;
+#pragma unroll
+            for (int j = 0; j < DW_TX; ++j)   // tap (0, 0) is the first contribution to its output row: it starts from the bias
+              acc[slot][j] = ffma2(w2, row[r][j + dx], (dy == 0 && dx == 0) ? bias : acc[slot][j]);
+          }
+        }
+      }
+      // output rows yi - 3 and yi - 2 are complete: slots (k + 5) % 8 and (k + 6) % 8
+      const int yo = yi - 3;
+      const int sa = (k + 5) % 8, sb = (k + 6) % 8;
+      const bool do_ln = yo + 1 >= y0 && yo <= y_last;
+      if (do_ln) {
+        // LayerNorm over the 256 channels of 2 rows x 4 pixels: 16 quantities, butterfly transpose-reduce (16 shuffles)
+        float q[16];
+#pragma unroll
+        for (int j = 0; j < DW_TX; ++j) {
+          const float2 v = acc[sa][j], u = acc[sb][j];
+          const float2 vv = fmul2(v, v), uu = fmul2(u, u);
+          q[j] = v.x + v.y;
+          q[4 + j] = vv.x + vv.y;
+          q[8 + j] = u.x + u.y;
+          q[12 + j] = uu.x + uu.y;
+        }
+#pragma unroll
+        for (int half = 8, bit = 16; half >= 1; half >>= 1, bit >>= 1) {
+          const bool hi = lane & bit;
+#pragma unroll
+          for (int i = 0; i < half; ++i) {
+            const float send = hi ? q[i] : q[i + half], keep = hi ? q[i + half] : q[i];
+            q[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+        q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+        if ((lane & 1) == 0) red[(parity * 4 + warp) * 16 + (lane >> 1)] = q[0];
+      }
+      __syncthreads();                             // the stage is consumed by everyone; the partial sums are visible
+      if (tid == 0 && step + DW_NST < nsteps) {
+        mbar_expect_tx(&full[stage], DW_STAGE_FLOATS * 4);
+        tma_load_4d(ring + stage * DW_STAGE_FLOATS, &tmX, &full[stage], 0, x0 - 3, y0 - 3 + 2 * (step + DW_NST), b);
+      }
+      if (do_ln) {
+        const float4* rp = reinterpret_cast<const float4*>(red + parity * 64);
+        float2 t[8];                               // t[2c], t[2c+1] = float4 number c of the 16 totals
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 a = rp[c];
+          t[2 * c] = make_float2(a.x, a.y);
+          t[2 * c + 1] = make_float2(a.z, a.w);
+        }
+#pragma unroll
+        for (int w = 1; w < 4; ++w)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float4 a = rp[4 * w + c];
+            t[2 * c] = fadd2(t[2 * c], make_float2(a.x, a.y));
+            t[2 * c + 1] = fadd2(t[2 * c + 1], make_float2(a.z, a.w));
+          }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int yr = yo + r;
+          if (yr < y0 || yr > y_last) continue;
+          const float sum[4] = {t[4 * r].x, t[4 * r].y, t[4 * r + 1].x, t[4 * r + 1].y};
+          const float sq[4] = {t[4 * r + 2].x, t[4 * r + 2].y, t[4 * r + 3].x, t[4 * r + 3].y};
+          bf16* orow = ob + ((long long)yr * W + x0) * 256;
+#pragma unroll
+          for (int j = 0; j < DW_TX; ++j) {
+            const float mean = sum[j] * (1.f / 256.f);
+            const float var = fmaxf(sq[j] * (1.f / 256.f) - mean * mean, 0.f);
+            const float rstd = rsqrtf(var + eps);
+            if (x0 + j < W) {
+              const float2 v = r == 0 ? acc[sa][j] : acc[sb][j];
+              const float2 a2 = fmul2(g, make_float2(rstd, rstd));
+              const float2 b2 = ffma2(make_float2(-mean, -mean), a2, be);
+              const float2 o = ffma2(v, a2, b2);
+              *reinterpret_cast<uint32_t*>(orow + j * 256) = pack_bf16x2(o.x, o.y);
+            }
+          }
+        }
+        parity ^= 1;
+      }
+      ++step;
+    }
+  }
+}
+
 int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
                       const float* lnb, float eps, void* out, cudaStream_t stream) {
   // few images: one CTA per 8 pixels of a row (512 CTAs at B=1, latency matters); many images: the FFMA2 column-strip
-  // kernel, strips of R rows chosen so that the grid is at least ~4 waves of 148 SMs x 4 CTAs
+  // kernels.  A strip is cut into n pieces of R = ceil(H / n) rows; every piece recomputes 6 halo rows and the grid runs in
+  // whole waves of 148 SMs x 3 CTAs, so n minimises (R + 6) / R x (waves rounded up / waves).
   const long long strips = (long long)((W + DW_TX - 1) / DW_TX) * B;
   if (strips * ((H + 15) / 16) < 1184) {
     VLS_CUDA(launch_k(dwconv7_ln_kernel, dim3((W + 7) / 8, H, B), dim3(256), 0, stream, x, H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
+    VLS_POST_LAUNCH(1);
+    return 0;
+  }
+  int R = H;
+  {
+    double best = 1e30;
+    for (int n = 1; n <= 8; ++n) {
+      const int r = (H + n - 1) / n;
+      if (r < 8) break;
+      const double waves = (double)strips * ((H + r - 1) / r) / (148.0 * 3.0);
+      const double cost = (r + 6.0) / r * ceil(waves) / waves;
+      if (cost < best - 1e-9) best = cost, R = r;
+    }
+  }
+  const int tma = g_dwconv_tma;
+  if (tma && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    CUtensorMap tm;
+    VLS_TRY(make_tmap_f32_nhwc(&tm, x, 256, W, H, B, DW_TX + 6, 2));
+    static unsigned long long attr = 0;
+    if (first_use_on_device(&attr)) {
+      VLS_CUDA(cudaFuncSetAttribute(dwconv7_ln_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_TMA_SMEM));
+      VLS_CUDA(cudaFuncSetAttribute(dwconv7_ln_tma_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DW_TMA_SMEM));
+    }
+    auto kern = tma == 2 ? dwconv7_ln_tma_kernel<4> : dwconv7_ln_tma_kernel<3>;
+    VLS_CUDA(launch_k(kern, dim3((W + DW_TX - 1) / DW_TX, (H + R - 1) / R, B), dim3(128), DW_TMA_SMEM, stream, tm, H, W, R, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
   } else {
-    int R = H;
-    while (R > 16 && strips * ((H + R - 1) / R) < 2368) R = (R + 1) / 2;
     const size_t smem = 49 * 128 * sizeof(float2) + 2 * 4 * 16 * sizeof(float);
     static unsigned long long attr = 0;
     if (first_use_on_device(&attr)) {
