@@ -7,17 +7,15 @@
 // always the minimum index, so   label(pixel) = 1 + min over its component of ((r&~1)*W + (c&~1))
 // and count(pixel) = component area; background pixels get 0 / 0.
 //
-// Small path (one CTA of 512 threads per image, (H/2)*(W/2) <= 16384 blocks, two CTAs per SM): everything lives in
-// 5 bytes of shared memory per block (a union-find word that doubles as the area counter + an occupancy byte).
+// Small path (one CTA of 512 threads per image, (H/2)*(W/2) <= 16384 blocks, two CTAs per SM): everything lives in shared
+// memory (a union-find word per block that doubles as the area counter, an occupancy byte per block, four 32-bit
+// occupancy planes per chunk-row of 32 blocks).
 //   A. occupancy of every 2x2 block straight from global memory with 128-bit loads (16 pixels x 2 rows per thread)
-//   B. region labelling: a warp walks its band of rows of one 32-block column strip top-down, keeping the previous
-//      row's labels in registers; a horizontal run (found with __ballot_sync) inherits the smallest label of the upper
-//      blocks it touches (warp reductions / segmented min-scan) or starts a new label.  No atomics unless a run joins
-//      two differently named components.  Run areas are summed per label in registers and parked on the label's word.
-//   C. seams between regions (band seams inside a strip, strip seams one lane per row) with lock-free atomicMin
-//      min-root unions + path compression; area parked on a node travels with the link
-//   D. the few blocks that ever started a label are flattened onto their roots (the only loop-y finds)
-//   E. block -> label -> root -> area with plain loads; 128-bit streaming stores of labels and areas
+//   P. occupancy planes (one warp per chunk-row, four ballots); every occupied block's word := its run's head block
+//   U. run-based unions, ONE THREAD per chunk-row: horizontal runs, the upper runs they touch and the seams to the
+//      neighbouring chunks are bit operations on the planes; one lock-free atomicMin min-root union per (run, upper run)
+//   F. every run head is re-parented to its root and adds its run's pixel count to the root's word
+//   E. block -> head -> root -> area with plain loads; 128-bit streaming stores of labels and areas
 //      (or, for hole filling, sparse in-place stores of 0.1)
 // Larger images: 64 x 128 pixel tiles labelled in shared memory by the same region labeller; the global state is one
 // forest word (parent << 4 | occupancy) and one area word per 2x2 block plus a list of the tile-local roots that touch
@@ -33,8 +31,7 @@ constexpr int CC_THREADS = 512;
 constexpr int CC_MAX_BLOCKS = 16384;
 constexpr int CC_IDX_BITS = 14;                       // block index < 16384; bits 14.. of a ROOT's word hold its area
 constexpr int CC_IDX_MASK = (1 << CC_IDX_BITS) - 1;
-constexpr int CC_NAME_CAP = 4096;                     // entries of the shared-memory list of NAME blocks (phase D)
-constexpr uint32_t CC_NAME = 0x10u;                   // occupancy byte, bit 4: the block started a new label in phase B
+constexpr int CC_MAX_CHUNK_ROWS = 1024;               // chunk-rows (32 blocks of one block row) per image on the small path
 
 __device__ __forceinline__ int uf_find(const volatile int* s, int n) {
   int p = s[n];
@@ -45,8 +42,11 @@ __device__ __forceinline__ int uf_find(const volatile int* s, int n) {
   return n;
 }
 
-// Every node on the path n -> ... -> r gets parent r.  r is an ancestor of n and parents are always smaller than
-// their children, so the walk ends at r; atomicMin keeps "parent only ever moves to a smaller member of the set".
+// Every node on the path n -> ... -> r gets parent r.  Only valid while every path stays inside its own set: links are made
+// with compare-and-swap on ROOTS (uf_union).  The r1 labeller linked with atomicMin, which re-parents a node that has just
+// stopped being a root (and repairs that by uniting its former parent as well); for a moment the path of a node then leads
+// into a set it is not yet united with, a concurrent compression lowers the parents of THAT set's nodes and cuts real links
+// (found with tools/debug_cc.py: one launch in ~50 split a component).
 __device__ __forceinline__ void uf_compress(int* s, int n, int r) {
   while (n > r) {
     const int p = reinterpret_cast<const volatile int*>(s)[n];
@@ -56,28 +56,47 @@ __device__ __forceinline__ void uf_compress(int* s, int n, int r) {
   }
 }
 
-// min-root union (lock-free, atomicMin on roots) followed by path compression of both sides
+// min-root union (lock-free: a root is linked below the other set's root by compare-and-swap, so a word only changes from
+// "root" to "child" once and paths never leave their set).  The two finds advance together (two independent loads per
+// step); paths are compressed only when one of them was longer than a hop (a fresh head joining a flat tree needs nothing).
+template <bool COMPRESS = true>
 __device__ __forceinline__ void uf_union(int* s, int a, int b) {
-  int ra = uf_find(s, a), rb = uf_find(s, b);
+  const volatile int* v = s;
+  int ra = a, rb = b, pa = v[a], pb = v[b], hops = 0;
+  while (pa != ra || pb != rb) {
+    ra = pa;
+    rb = pb;
+    pa = v[ra];
+    pb = v[rb];
+    ++hops;
+  }
   while (ra != rb) {
     if (ra < rb) {
       const int t = ra;
       ra = rb;
       rb = t;
     }
-    const int old = atomicMin(s + ra, rb);  // ra > rb
+    const int old = atomicCAS(s + ra, ra, rb);  // ra > rb
     if (old == ra) break;
-    ra = uf_find(s, old);                   // ra had been linked meanwhile: carry on from its parent
-    rb = uf_find(s, rb);
+    ra = old;                                   // ra had been linked meanwhile: carry on from its parent
+    pa = v[ra];
+    pb = v[rb];
+    while (pa != ra || pb != rb) {
+      ra = pa;
+      rb = pb;
+      pa = v[ra];
+      pb = v[rb];
+    }
+    hops = 2;
   }
-  const int r = ra < rb ? ra : rb;
-  uf_compress(s, a, r);
-  uf_compress(s, b, r);
+  if (COMPRESS && hops > 1) {
+    const int r = ra < rb ? ra : rb;
+    uf_compress(s, a, r);
+    uf_compress(s, b, r);
+  }
 }
 
-// ---- area-carrying variant for the shared-memory kernel: a word is parent | area << 14.  Areas are parked on NAME
-// blocks (phase B) and travel with the links: atomicMin returns the old word, whose area part is re-added to the new
-// parent.  Area left on a name that is no longer a root is collected when the names are flattened (phase D).
+// find on words parent | area << 14 (a ROOT's word carries its component's area once the areas are accumulated)
 __device__ __forceinline__ int ufa_find(const volatile int* s, int n) {
   int p = s[n] & CC_IDX_MASK;
   while (p != n) {
@@ -85,36 +104,6 @@ __device__ __forceinline__ int ufa_find(const volatile int* s, int n) {
     p = s[n] & CC_IDX_MASK;
   }
   return n;
-}
-__device__ __forceinline__ void ufa_move_area(int* s, int old_word, int to) {
-  const uint32_t a = (uint32_t)old_word >> CC_IDX_BITS;
-  if (a) atomicAdd(s + to, (int)(a << CC_IDX_BITS));
-}
-__device__ __forceinline__ void ufa_compress(int* s, int n, int r) {
-  while (n > r) {
-    const int p = reinterpret_cast<const volatile int*>(s)[n] & CC_IDX_MASK;
-    if (p == n) break;
-    if (p > r) ufa_move_area(s, atomicMin(s + n, r), r);
-    n = p;
-  }
-}
-__device__ __forceinline__ void ufa_union(int* s, int a, int b) {
-  int ra = ufa_find(s, a), rb = ufa_find(s, b);
-  while (ra != rb) {
-    if (ra < rb) {
-      const int t = ra;
-      ra = rb;
-      rb = t;
-    }
-    const int old = atomicMin(s + ra, rb);  // ra > rb: the word becomes rb (any area bits made it larger than rb)
-    ufa_move_area(s, old, rb);
-    if ((old & CC_IDX_MASK) == ra) break;
-    ra = ufa_find(s, old & CC_IDX_MASK);
-    rb = ufa_find(s, rb);
-  }
-  const int r = ra < rb ? ra : rb;
-  ufa_compress(s, a, r);
-  ufa_compress(s, b, r);
 }
 
 // occupancy bits: 0 = top-left, 1 = top-right, 2 = bottom-left, 3 = bottom-right
@@ -145,262 +134,265 @@ __device__ __forceinline__ uint32_t occ2_from_u8(uint32_t top, uint32_t bot) {
   return a | (b << 8);
 }
 
-// One warp-row = 32 consecutive blocks of one block row.  Neighbour occupancies come from two byte loads per lane
-// plus shuffles; only the edge lanes read the adjacent chunk.
-struct RowOcc {
-  uint32_t me, left, up, ul, ur;
-};
-__device__ __forceinline__ RowOcc row_occ(const uint8_t* occ, int BW, int by, int bx, int bi, bool in, int lane) {
-  RowOcc o;
-  o.me = in ? occ[bi] : 0u;
-  o.up = (in && by > 0) ? occ[bi - BW] : 0u;
-  o.left = __shfl_up_sync(0xffffffffu, o.me, 1);
-  o.ul = __shfl_up_sync(0xffffffffu, o.up, 1);
-  o.ur = __shfl_down_sync(0xffffffffu, o.up, 1);
-  if (lane == 0) {
-    o.left = (in && bx > 0) ? occ[bi - 1] : 0u;
-    o.ul = (in && bx > 0 && by > 0) ? occ[bi - BW - 1] : 0u;
-  }
-  if (lane == 31) o.ur = (in && bx + 1 < BW && by > 0) ? occ[bi - BW + 1] : 0u;
-  return o;
+// ---- run-based region labeller (r2).
+// A CHUNK-ROW = 32 consecutive blocks of one block row, held as four 32-bit occupancy planes (uint4: x = top-left, y =
+// top-right, z = bottom-left, w = bottom-right pixels).  On planes, connectivity is a handful of bit operations for 32
+// blocks at once, so ONE THREAD owns a chunk-row (the r1 labeller spent ~300 warp instructions on it: a warp walked its
+// band of rows top-down with shuffles / ballots / warp reductions per row and was instruction-issue bound):
+//   hm    = (x|z) & ((y|w) << 1)         block i joins block i-1;  run heads = occupied & ~hm
+//   up    : (x|y) & (u.z|u.w)            block i touches the upper block i
+//   up-l  : x & (u.w << 1)               ... the upper block i-1;    up-r: y & (u.z >> 1) the upper block i+1
+// A run is named after its head block; only heads are union-find nodes.
+//   U1  hooks: for every upper run a run touches (clz / ffs on the head masks, each upper run once) and for the seams to the
+//       neighbouring chunks ONE atomicMin(word[head], other head) -- no find.  When the head already had another parent, the
+//       pair (old parent, new one) still has to be united: it goes to a list.  Every row hooks at the same time, so a tall
+//       component is now a parent chain as long as it is tall -- finds on it are what made the first version of this
+//       labeller slow (45 k cycles of unions, 41-67 k of flattening) --
+//   J   which pointer jumping (word[h] = word[word[h]], all heads in parallel, until nothing changes: log2(height) rounds)
+//       collapses;
+//   U2  the listed pairs are united on the now flat trees (lock-free min-root unions), a thread each;
+//   F   every head is re-parented to its root and adds its run's pixel count to the root's word; the largest run of every
+//       chunk-row goes through a warp-level reduction by root first (one big component would otherwise receive an atomic
+//       from every chunk-row it covers).
+__device__ __forceinline__ uint32_t cc_hm(uint4 p) { return (p.x | p.z) & ((p.y | p.w) << 1); }
+__device__ __forceinline__ uint32_t cc_heads(uint4 p) { return (p.x | p.y | p.z | p.w) & ~cc_hm(p); }
+// the run that starts at head bit s: bits s .. e-1, e = first bit above s whose block does not join its left neighbour
+__device__ __forceinline__ uint32_t cc_run_mask(uint32_t hm, int s) {
+  const uint32_t stop = ~hm & ~((2u << s) - 1u);
+  const uint32_t below_e = stop ? ((stop & (0u - stop)) - 1u) : 0xffffffffu;
+  return below_e & ~((1u << s) - 1u);
 }
+// head (bit index) of the run that contains the occupied block `bit`
+__device__ __forceinline__ int cc_head_of(uint32_t heads, int bit) { return 31 - __clz(heads & (0xffffffffu >> (31 - bit))); }
 
-// Phases B-D of the shared-memory labeller on a BH x BW block region held in `lab` / `occ` (row pitch BW), executed by
-// the whole CTA (nthreads = blockDim.x, a multiple of 32).  `occ` must be complete (followed by __syncthreads) on
-// entry; on return (after the caller's __syncthreads) every occupied block's word is a NAME block index, every name's
-// word its root, and a root's word root | area << 14.
+constexpr int CC_ROWS_PER_THREAD = 2;   // chunk-rows per thread at most: CC_MAX_CHUNK_ROWS / CC_THREADS (small path), 64 / 256 (tiles)
+static_assert(CC_MAX_CHUNK_ROWS <= CC_ROWS_PER_THREAD * CC_THREADS, "a thread holds the heads of its chunk-rows in registers");
+constexpr int CC_PAIR_CAP = 2048;   // deferred unions (two 16-bit block indices per entry)
+
 #ifdef CC_TRACE
 __device__ long long g_cc_tr[8];
-__device__ int g_cc_cnt[4];
-#define CC_RMARK(i)                                            \
-  do {                                                         \
+#define CC_RMARK(i)                                                  \
+  do {                                                               \
     if (threadIdx.x == 0 && blockIdx.x == 0) g_cc_tr[i] = clock64(); \
   } while (0)
 #else
 #define CC_RMARK(i)
 #endif
-__device__ __forceinline__ void cc_label_region(int* lab, uint8_t* occ, int BH, int BW, uint16_t* name_list,
-                                                int* name_count, int name_cap) {
-  const int nthreads = blockDim.x;
-  const int nb = BH * BW;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = nthreads >> 5;
-  const int chunks = (BW + 31) >> 5;
-  // warp-row tasks in column-strip-major order; each warp owns a contiguous band of rows of one strip and walks it
-  // top-down, which (with path compression) keeps the union-find chains a few hops long
-  const int ntask = BH * chunks, per = (ntask + nwarps - 1) / nwarps;
-  const int t_begin = warp * per, t_end = min(ntask, t_begin + per);
-  // B. region labelling.  A region = this warp's band of rows within one 32-block column strip, walked top-down with
-  //    the previous row's labels kept in REGISTERS: a run takes the smallest label among the upper blocks it touches
-  //    (segmented min-scan over the run's lanes) or becomes a new root; shared memory sees one store per block.
-  //    Only a run that touches two differently named upper components costs a union-find operation.
-  {
-    constexpr int INF = 0x7fffffff;
-    uint32_t up_me = 0u;
-    int up_lab = INF, acc_name = -1, acc_sum = 0;
-    int chunk = t_begin / BH, by = t_begin - chunk * BH;
-    for (int t = t_begin; t < t_end; ++t, ++by) {
-      if (by == BH) {
-        by = 0;
-        ++chunk;
-      }
-      if (by == 0) {
-        up_me = 0u;
-        up_lab = INF;
-      }
-      const int c0 = chunk << 5, bx = c0 + lane;
-      const bool in = bx < BW;
-      const int bi = by * BW + bx;
-      const uint32_t me = in ? occ[bi] : 0u;
-      uint32_t left = __shfl_up_sync(0xffffffffu, me, 1);
-      uint32_t ulo = __shfl_up_sync(0xffffffffu, up_me, 1), uro = __shfl_down_sync(0xffffffffu, up_me, 1);
-      const int ull = __shfl_up_sync(0xffffffffu, up_lab, 1), url = __shfl_down_sync(0xffffffffu, up_lab, 1);
-      if (lane == 0) left = 0u, ulo = 0u;
-      if (lane == 31) uro = 0u;
-      const int ca = conn_up(me, up_me) ? up_lab : INF, cb = conn_upleft(me, ulo) ? ull : INF,
-                cc = conn_upright(me, uro) ? url : INF;
-      const int cand = min(ca, min(cb, cc));
-      const uint32_t hm = __ballot_sync(0xffffffffu, conn_left(me, left));
-      const uint32_t stops = ~hm | 1u;
-      const int head = 31 - __clz(stops & (0xffffffffu >> (31 - lane)));
-      const uint32_t above = stops & ~(0xffffffffu >> (31 - lane));
-      // smallest candidate of the run.  Usually every candidate in the 32-block row carries the same name (one
-      // component passes through): two warp reductions + a ballot.  Otherwise a segmented min-scan over the runs.
-      const int mn = __reduce_min_sync(0xffffffffu, cand);
-      const int mx = __reduce_max_sync(0xffffffffu, cand == INF ? -1 : cand);
-      int runmin;
-      if (mx == -1 || mx == mn) {
-        const uint32_t run = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << head) - 1u);
-        runmin = (__ballot_sync(0xffffffffu, cand != INF) & run) ? mn : INF;
-      } else {
-        int x = cand;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-          const int v = __shfl_up_sync(0xffffffffu, x, d);
-          if (lane - d >= head) x = min(x, v);
+
+// Occupancy planes of every chunk-row from the occupancy bytes (one warp per chunk-row, four ballots): the generic way;
+// the 128-bit uint8 path of the small kernel writes the planes directly while it loads the image.
+__device__ __forceinline__ void cc_planes_from_occ(const uint8_t* occ, int BH, int BW, uint4* planes) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int chunks = (BW + 31) >> 5, nrows = BH * chunks;
+  const uint32_t magic = chunks > 1 ? (uint32_t)((0x100000000ull + chunks - 1) / chunks) : 0u;
+#pragma unroll 2
+  for (int r = warp; r < nrows; r += nwarps) {
+    const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
+    const int bx = (ch << 5) + lane;
+    const uint32_t o = bx < BW ? occ[by * BW + bx] : 0u;
+    uint4 p;
+    p.x = __ballot_sync(0xffffffffu, o & 1u);
+    p.y = __ballot_sync(0xffffffffu, o & 2u);
+    p.z = __ballot_sync(0xffffffffu, o & 4u);
+    p.w = __ballot_sync(0xffffffffu, o & 8u);
+    if (lane == 0) planes[r] = p;
+  }
+}
+
+// Labels the BH x BW block region described by `planes` (BH * ceil(BW / 32) chunk-row records, complete and followed by
+// __syncthreads on entry), executed by the whole CTA (blockDim.x a multiple of 32).  `lab` has one word per block (row pitch
+// BW); only the words of run heads are used.  On return (after the caller's __syncthreads): every head's word is its root
+// (the smallest block index of the component) and a root's word is root | area << 14.  cc_root_of() maps a block to its root.
+__device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, int BH, int BW, uint32_t* pairs, int* pair_count) {
+  const int nthreads = blockDim.x, lane = threadIdx.x & 31;
+  const int chunks = (BW + 31) >> 5, nrows = BH * chunks, nb = BH * BW;
+  const uint32_t magic = chunks > 1 ? (uint32_t)((0x100000000ull + chunks - 1) / chunks) : 0u;   // r / chunks, exact for r < 2^16
+  // I. every word its own root
+  if ((nb & 3) == 0 && (reinterpret_cast<uintptr_t>(lab) & 15) == 0) {
+    for (int i = threadIdx.x * 4; i < nb; i += nthreads * 4) *reinterpret_cast<int4*>(lab + i) = make_int4(i, i + 1, i + 2, i + 3);
+  } else {
+    for (int i = threadIdx.x; i < nb; i += nthreads) lab[i] = i;
+  }
+  if (threadIdx.x == 0) *pair_count = 0;
+  __syncthreads();
+  CC_RMARK(0);
+  // a > b.  old == a: a was a root and now hangs below b.  Otherwise a already had the parent `old`: the smaller of the two
+  // is its parent now and the pair (old, b) is still to be united.
+  auto hook = [&](int a, int b) {
+    const int old = atomicMin(lab + a, b);
+    if (old != a && old != b) {
+      const int slot = atomicAdd(pair_count, 1);
+      if (slot < CC_PAIR_CAP) pairs[slot] = (uint32_t)old | ((uint32_t)b << 16);
+      else uf_union<false>(lab, old, b);   // list full: unite now (hooks still re-parent heads, so without compression)
+    }
+  };
+  // U1. hooks, one thread per chunk-row
+  for (int r = threadIdx.x; r < nrows; r += nthreads) {
+    const uint4 m = planes[r];
+    const uint32_t occm = m.x | m.y | m.z | m.w;
+    if (!occm) continue;
+    const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
+    const uint32_t hm = cc_hm(m), heads = occm & ~hm;
+    const int base = by * BW + (ch << 5);
+    if (ch > 0 && ((m.x | m.z) & 1u)) {           // block 0 joins the last block of the chunk to the left
+      const uint4 l = planes[r - 1];
+      if ((l.y | l.w) >> 31) hook(base, base - 32 + (31 - __clz(cc_heads(l))));
+    }
+    if (by == 0) continue;
+    const uint4 u = planes[r - chunks];
+    const int ubase = base - BW;
+    const uint32_t tu = (m.x | m.y) & (u.z | u.w), tul = m.x & (u.w << 1), tur = m.y & (u.z >> 1);
+    if (tu | tul | tur) {
+      const uint32_t hmu = cc_hm(u), uheads = (u.x | u.y | u.z | u.w) & ~hmu;
+      uint32_t hh = heads;
+      while (hh) {
+        const int s = __ffs(hh) - 1;
+        hh &= hh - 1;
+        const uint32_t run = cc_run_mask(hm, s);
+        uint32_t upm = (tu & run) | ((tul & run) >> 1) | ((tur & run) << 1);   // upper blocks this run touches
+        while (upm) {
+          const int hj = cc_head_of(uheads, __ffs(upm) - 1);                    // the upper run that contains the lowest of them
+          upm &= ~cc_run_mask(hmu, hj);
+          hook(base + s, ubase + hj);
         }
-        runmin = __shfl_sync(0xffffffffu, x, above ? __ffs(above) - 2 : 31);
       }
-      int label = INF;
-      if (me) {
-        label = (runmin == INF) ? (by * BW + c0 + head) : runmin;
-        lab[bi] = label;
-        if (runmin == INF && head == lane) occ[bi] = (uint8_t)(me | CC_NAME);   // this block is a NAME: a tree node others point to
+    }
+    if (ch > 0 && (m.x & 1u)) {                   // top-left pixel of block 0 against the bottom-right pixel of the upper-left chunk
+      const uint4 ul = planes[r - chunks - 1];
+      if (ul.w >> 31) hook(base, ubase - 32 + (31 - __clz(cc_heads(ul))));
+    }
+    if (ch + 1 < chunks && (m.y >> 31)) {         // top-right pixel of block 31 against the bottom-left pixel of the upper-right chunk
+      const uint4 ur = planes[r - chunks + 1];
+      if (ur.z & 1u) hook(base + (31 - __clz(heads)), ubase + 32);
+    }
+  }
+  __syncthreads();
+  CC_RMARK(1);
+  // J. pointer jumping over the heads until every head points at a root of the hook forest.  A thread keeps the still
+  //    unresolved heads of its (at most CC_ROWS_PER_THREAD) chunk-rows as bit masks in registers: after the first rounds only
+  //    the heads of tall components are left.
+  {
+    const volatile int* v = lab;
+    uint32_t pend[CC_ROWS_PER_THREAD];
+    int pbase[CC_ROWS_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < CC_ROWS_PER_THREAD; ++k) {
+      const int r = threadIdx.x + k * nthreads;
+      pend[k] = 0u;
+      pbase[k] = 0;
+      if (r < nrows) {
+        const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
+        pend[k] = cc_heads(planes[r]);
+        pbase[k] = by * BW + (ch << 5);
       }
-      // area of every run goes to its label's word; the runs of this row that share the first run's label are summed
-      // with one warp reduction and carried in registers from row to row (one atomic per label change, not per run)
-      {
-        const uint32_t run = (above ? ((1u << (__ffs(above) - 1)) - 1u) : 0xffffffffu) & ~((1u << lane) - 1u);
-        const uint32_t b0 = __ballot_sync(0xffffffffu, me & 1u), b1 = __ballot_sync(0xffffffffu, me & 2u);
-        const uint32_t b2 = __ballot_sync(0xffffffffu, me & 4u), b3 = __ballot_sync(0xffffffffu, me & 8u);
-        const bool is_head = me && head == lane;
-        const int area = __popc(b0 & run) + __popc(b1 & run) + __popc(b2 & run) + __popc(b3 & run);
-        const uint32_t heads = __ballot_sync(0xffffffffu, is_head);
-        if (heads) {
-          const int n0 = __shfl_sync(0xffffffffu, label, __ffs(heads) - 1);
-          const int total = __reduce_add_sync(0xffffffffu, (is_head && label == n0) ? area : 0);
-          if (n0 == acc_name) {
-            acc_sum += total;
+    }
+    int changed;
+#ifdef CC_TRACE
+    int rounds = 0;
+#endif
+    do {
+      changed = 0;
+#pragma unroll
+      for (int k = 0; k < CC_ROWS_PER_THREAD; ++k) {
+        uint32_t hh = pend[k];
+        while (hh) {
+          const int bit = __ffs(hh) - 1;
+          hh &= hh - 1;
+          const int h = pbase[k] + bit;
+          const int p = v[h];
+          const int gp = v[p];
+          if (gp == p) {
+            pend[k] &= ~(1u << bit);               // the parent is a root (or h itself is): done
           } else {
-            __syncwarp();
-            if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
-            acc_name = n0;
-            acc_sum = total;
+            lab[h] = v[gp];                        // up to three levels per round (every ancestor is a valid parent)
+            changed = 1;
           }
-          if (is_head && label != n0) atomicAdd(lab + label, area << CC_IDX_BITS);
         }
       }
 #ifdef CC_TRACE
-      if (blockIdx.x == 0 && warp == 0) {
-        const uint32_t un = __ballot_sync(0xffffffffu, (ca != INF && ca != runmin) || (cb != INF && cb != runmin && cb != ca) ||
-                                                           (cc != INF && cc != runmin && cc != ca && cc != cb));
-        if (lane == 0) {
-          g_cc_cnt[0] += un != 0;
-          g_cc_cnt[1] += __popc(un);
-          g_cc_cnt[2] += !(mx == -1 || mx == mn);
-          g_cc_cnt[3] += 1;
-        }
-      }
+      ++rounds;
 #endif
-      // rare: a run joining differently named components (every candidate of every lane, not just the lane's minimum)
-      if (ca != INF && ca != runmin) ufa_union(lab, ca, runmin);
-      if (cb != INF && cb != runmin && cb != ca) ufa_union(lab, cb, runmin);
-      if (cc != INF && cc != runmin && cc != ca && cc != cb) ufa_union(lab, cc, runmin);
-      up_me = me;
-      up_lab = label;
-    }
-    __syncwarp();
-    if (acc_sum && lane == 0) atomicAdd(lab + acc_name, acc_sum << CC_IDX_BITS);
+    } while (__syncthreads_or(changed));
+#ifdef CC_TRACE
+    if (threadIdx.x == 0 && blockIdx.x == 0) g_cc_tr[7] = rounds;
+#endif
   }
-  CC_RMARK(0);
-  __syncthreads();
-  CC_RMARK(1);
-  // C. seams between regions (generic lock-free unions; every region is already labelled)
-  //    C1: the first row of each band against the last row of the band above, inside the strip
-  if (t_begin < t_end) {
-    const int chunk = t_begin / BH, by = t_begin - chunk * BH;
-    if (by > 0) {
-      const int c0 = chunk << 5, bx = c0 + lane;
-      const bool in = bx < BW;
-      const int bi = by * BW + bx;
-      const uint32_t me = in ? occ[bi] : 0u, up = in ? occ[bi - BW] : 0u;
-      uint32_t left = __shfl_up_sync(0xffffffffu, me, 1);
-      uint32_t ul = __shfl_up_sync(0xffffffffu, up, 1), ur = __shfl_down_sync(0xffffffffu, up, 1);
-      if (lane == 0) left = 0u, ul = 0u;
-      if (lane == 31) ur = 0u;
-      const bool h = conn_left(me, left);
-      const bool cu = conn_up(me, up);
-      const bool cul = conn_upleft(me, ul) && !(cu && conn_left(up, ul));
-      const bool cur = conn_upright(me, ur) && !(cu && conn_left(ur, up));
-      const bool cu_prev = __shfl_up_sync(0xffffffffu, cu, 1);
-      const bool cu_redundant = lane > 0 && h && cu_prev && conn_left(up, ul);
-      if (cu && !cu_redundant) ufa_union(lab, bi, bi - BW);
-      if (cul) ufa_union(lab, bi, bi - BW - 1);
-      if (cur) ufa_union(lab, bi, bi - BW + 1);
-    }
-  }
-  //    C2: strip seams, one lane per row: left edge block of a strip with its left / upper-left neighbour, and the right
-  //    edge block of the strip before it with its upper-right neighbour
-  {
-    const int rg = (BH + 31) >> 5, ns = (chunks - 1) * rg;
-    for (int u = warp; u < ns; u += nwarps) {
-      const int sb = 1 + u / rg, by = ((u - (sb - 1) * rg) << 5) + lane;
-      if (by < BH) {
-        const int bi = by * BW + (sb << 5);
-        const uint32_t me = occ[bi], lf = occ[bi - 1];
-        if (conn_left(me, lf)) ufa_union(lab, bi, bi - 1);
-        if (by > 0) {
-          const uint32_t up = occ[bi - BW], ul = occ[bi - BW - 1];
-          const bool across = conn_left(up, ul);
-          if (conn_upleft(me, ul) && !(conn_up(me, up) && across)) ufa_union(lab, bi, bi - BW - 1);
-          if (conn_upright(lf, up) && !(conn_up(lf, ul) && across)) ufa_union(lab, bi - 1, bi - BW);
-        }
-      }
-    }
-  }
-  __syncthreads();
   CC_RMARK(2);
-  // D. every parent pointer written so far targets a NAME block (a run that started a new label): flatten the names
-  //    (the only loop-y finds left) and hand the area parked on a name to its root.  Afterwards block -> name -> root is
-  //    two plain loads and a root's word is root | area << 14.  Names are a few % of the blocks, so they are first
-  //    gathered into a list (128-bit scan of the occupancy bytes) and then handled one per thread with full warps;
-  //    a scan that overflows the list flattens the surplus names in place.
-  auto flatten = [&](int bi) {
-    const int root = ufa_find(lab, bi);
-    if (root != bi) {
-      ufa_move_area(lab, lab[bi], root);
-      lab[bi] = root;
-    }
-  };
-  if (threadIdx.x == 0) *name_count = 0;
-  __syncthreads();
+  // U2. the deferred pairs
   {
-    auto push = [&](int bi) {
-      const int slot = atomicAdd(name_count, 1);
-      if (slot < name_cap) name_list[slot] = (uint16_t)bi;
-      else flatten(bi);
-    };
-    const int nvec = (nb & 3) == 0 ? nb >> 4 : 0;     // the occupancy array starts 4*nb bytes into shared memory
-    const uint4* occ4 = reinterpret_cast<const uint4*>(occ);
-    for (int v = threadIdx.x; v < nvec; v += nthreads) {
-      const uint4 o = occ4[v];
-      const uint32_t wds[4] = {o.x, o.y, o.z, o.w};
-#pragma unroll
-      for (int wi = 0; wi < 4; ++wi) {
-        uint32_t m = wds[wi] & 0x10101010u;
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          m &= m - 1;
-          push((v << 4) + (wi << 2) + (bit >> 3));
-        }
-      }
-    }
-    for (int bi = (nvec << 4) + threadIdx.x; bi < nb; bi += nthreads)
-      if (occ[bi] & CC_NAME) push(bi);
+    const int n = min(*pair_count, CC_PAIR_CAP);
+    for (int i = threadIdx.x; i < n; i += nthreads) uf_union(lab, (int)(pairs[i] & 0xffffu), (int)(pairs[i] >> 16));
   }
   __syncthreads();
   CC_RMARK(3);
-  {
-    const int cnt = min(*name_count, name_cap);
-    for (int i = threadIdx.x; i < cnt; i += nthreads) flatten(name_list[i]);
+  // F. every head: parent -> root, and its run's pixel count onto the root's word (finds ignore the area bits; only roots
+  //    receive area, only non-roots are re-parented, so the plain stores and the atomic adds never touch the same word)
+  for (int r0 = threadIdx.x - lane; r0 < nrows; r0 += nthreads) {   // whole warps: the reduction below needs all 32 lanes
+    const int r = r0 + lane;
+    int best_root = -1, best_area = 0;
+    if (r < nrows) {
+      const uint4 m = planes[r];
+      const uint32_t occm = m.x | m.y | m.z | m.w;
+      if (occm) {
+        const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
+        const uint32_t hm = cc_hm(m);
+        const int base = by * BW + (ch << 5);
+        uint32_t hh = occm & ~hm;
+        while (hh) {
+          const int s = __ffs(hh) - 1;
+          hh &= hh - 1;
+          const uint32_t run = cc_run_mask(hm, s);
+          int area = __popc(m.x & run) + __popc(m.y & run) + __popc(m.z & run) + __popc(m.w & run);
+          const int idx = base + s;
+          int root = ufa_find(lab, idx);
+          if (root != idx) lab[idx] = root;
+          if (root == best_root) {
+            best_area += area;
+          } else {
+            if (area > best_area) {                // keep the largest run for the warp-level reduction
+              const int tr = root, ta = area;
+              root = best_root;
+              area = best_area;
+              best_root = tr;
+              best_area = ta;
+            }
+            if (area) atomicAdd(lab + root, area << CC_IDX_BITS);
+          }
+        }
+      }
+    }
+    __syncwarp();
+    const uint32_t grp = __match_any_sync(0xffffffffu, best_area ? best_root : -1 - lane);
+    const int total = __reduce_add_sync(grp, best_area);
+    if (best_area && lane == __ffs(grp) - 1) atomicAdd(lab + best_root, total << CC_IDX_BITS);
   }
   CC_RMARK(4);
 }
 
+// root of the component of the occupied block (by, bx) after cc_label_region (+ __syncthreads)
+__device__ __forceinline__ int cc_root_of(const int* lab, const uint4* planes, int BW, int by, int bx) {
+  const int chunks = (BW + 31) >> 5;
+  const uint4 p = planes[by * chunks + (bx >> 5)];
+  return lab[by * BW + (bx & ~31) + cc_head_of(cc_heads(p), bx & 31)] & CC_IDX_MASK;
+}
+
 // FILL=false: img uint8 -> labels/counts int32.   FILL=true: scores f32 updated in place.
-// Shared memory: one int32 per block (union-find parent; a root's word additionally carries area << 14 once the
-// areas are accumulated) + one occupancy byte per block = 5 B/block, 80 KB at 256 x 256 -> two CTAs per SM, so one
-// image's loads/stores overlap the other's union-find.
+// Shared memory: four plane words per chunk-row, one int32 per block (union-find parent of a run head; a root's word
+// additionally carries area << 14), the deferred-pair list, and (generic paths only) one occupancy byte per block:
+// 96 KB at 256 x 256 -> two CTAs per SM, so one image's loads / stores overlap the other's labelling.
 template <bool FILL>
 __global__ void __launch_bounds__(CC_THREADS, 2)
 cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t* counts_all, float* scores_all,
                 int max_area, float fill_value, int vec) {
   pdl_enter();
-  extern __shared__ int cc_smem[];
+  extern __shared__ __align__(16) int cc_smem[];
   const int BH = H >> 1, BW = W >> 1, nb = BH * BW;
-  int* lab = cc_smem;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(cc_smem + nb);
-  uint16_t* name_list = reinterpret_cast<uint16_t*>(occ + ((nb + 15) & ~15));
-  int* name_count = reinterpret_cast<int*>(name_list + CC_NAME_CAP);
+  const int chunks = (BW + 31) >> 5, nrows = BH * chunks;
+  uint4* planes = reinterpret_cast<uint4*>(cc_smem);              // [nrows] (first: 16-byte aligned for any nb)
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(cc_smem + 4 * nrows);
+  int* pair_count = cc_smem + 4 * nrows + CC_PAIR_CAP;
+  int* lab = pair_count + 4;
+  uint8_t* occ = reinterpret_cast<uint8_t*>(lab + nb);
   const size_t img_off = (size_t)blockIdx.x * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
@@ -414,8 +406,33 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
 #define CC_MARK(i)
 #endif
   // A. occupancy
-  if (vec) {
-    if (FILL) {  // 2 x float4 -> 2 blocks
+  if (vec && !FILL) {
+    // 2 x 16 pixels -> 8 blocks -> one byte of each of the chunk-row's four planes, written in place (no occupancy bytes,
+    // no ballot pass).  Units beyond the image (the last chunk of a row when BW % 32 != 0) write zeros.
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
+    const int upr = chunks << 2, units = BH * upr;
+    uint8_t* pb = reinterpret_cast<uint8_t*>(planes);
+#pragma unroll 2
+    for (int u = threadIdx.x; u < units; u += CC_THREADS) {
+      const int by = u / upr, k = u - by * upr;
+      uint32_t ox = 0u, oy = 0u;
+      if (8 * k < BW) {   // W % 16 == 0: a unit is inside the image or completely outside
+        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 16 * k);
+        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 16 * k);
+        ox = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);   // one occupancy nibble per byte, blocks 0-3
+        oy = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);   // blocks 4-7
+      }
+      uint8_t* dst = pb + (size_t)(by * chunks + (k >> 2)) * 16 + (k & 3);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // bit j of bytes 0..3 -> bits 24..27 (0x01020408 = 2^24 + 2^17 + 2^10 + 2^3: byte i lands on bit 24 + i, no carries)
+        const uint32_t lo = (((ox >> j) & 0x01010101u) * 0x01020408u) >> 24;
+        const uint32_t hi = (((oy >> j) & 0x01010101u) * 0x01020408u) >> 24;
+        dst[4 * j] = (uint8_t)(lo | (hi << 4));
+      }
+    }
+  } else {
+    if (vec) {   // FILL: 2 x float4 -> 2 blocks
       const float* f = reinterpret_cast<const float*>(img);
       const int upr = W >> 2, units = BH * upr;
 #pragma unroll 4
@@ -427,84 +444,100 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
         const uint32_t o1 = (t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u);
         *reinterpret_cast<uint16_t*>(occ + by * BW + 2 * k) = (uint16_t)(o0 | (o1 << 8));
       }
-    } else {     // 2 x 16 pixels -> 8 blocks
-      const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
-      const int upr = W >> 4, units = BH * upr;
-#pragma unroll 2
-      for (int u = threadIdx.x; u < units; u += CC_THREADS) {
-        const int by = u / upr, k = u - by * upr;
-        const uint4 t = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by) * W + 16 * k);
-        const uint4 b = *reinterpret_cast<const uint4*>(p + (size_t)(2 * by + 1) * W + 16 * k);
-        uint2 o;
-        o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
-        o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
-        *reinterpret_cast<uint2*>(occ + by * BW + 8 * k) = o;
-      }
+    } else {
+      for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
     }
-  } else {
-    for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) occ[bi] = (uint8_t)load_occ<FILL>(img, H, W, bi / BW, bi % BW, 0.f);
+    __syncthreads();
+    cc_planes_from_occ(occ, BH, BW, planes);
   }
   __syncthreads();
   CC_MARK(1);
-  cc_label_region(lab, occ, BH, BW, name_list, name_count, CC_NAME_CAP);
+  cc_label_region(lab, planes, BH, BW, pairs, pair_count);
   __syncthreads();
   CC_MARK(4);
   // E. outputs
   if (FILL) {
+    // one thread per chunk-row: a run whose component is small enough is written pixel by pixel (holes are rare and tiny)
     float* sc = scores_all + img_off;
-    for (int bi = threadIdx.x; bi < nb; bi += CC_THREADS) {
-      const uint32_t me = occ[bi];
-      if (!me) continue;
-      const int rt = lab[lab[bi] & CC_IDX_MASK] & CC_IDX_MASK;
-      if ((int)((uint32_t)lab[rt] >> CC_IDX_BITS) > max_area) continue;
-      const int r = 2 * (bi / BW), c = 2 * (bi % BW);
-      if (me & 1u) sc[(size_t)r * W + c] = fill_value;
-      if (me & 2u) sc[(size_t)r * W + c + 1] = fill_value;
-      if (me & 4u) sc[(size_t)(r + 1) * W + c] = fill_value;
-      if (me & 8u) sc[(size_t)(r + 1) * W + c + 1] = fill_value;
+    const uint32_t cmagic = chunks > 1 ? (uint32_t)((0x100000000ull + chunks - 1) / chunks) : 0u;
+    for (int r = threadIdx.x; r < nrows; r += CC_THREADS) {
+      const uint4 m = planes[r];
+      const uint32_t occm = m.x | m.y | m.z | m.w;
+      if (!occm) continue;
+      const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, cmagic) : r, ch = r - by * chunks;
+      const uint32_t hm = cc_hm(m);
+      const int base = by * BW + (ch << 5);
+      uint32_t hh = occm & ~hm;
+      while (hh) {
+        const int s = __ffs(hh) - 1;
+        hh &= hh - 1;
+        const int rt = lab[base + s] & CC_IDX_MASK;
+        if ((int)((uint32_t)lab[rt] >> CC_IDX_BITS) > max_area) continue;
+        uint32_t run = cc_run_mask(hm, s);
+        while (run) {
+          const int i = __ffs(run) - 1;
+          run &= run - 1;
+          float* px = sc + (size_t)(2 * by) * W + 2 * ((ch << 5) + i);
+          if ((m.x >> i) & 1u) px[0] = fill_value;
+          if ((m.y >> i) & 1u) px[1] = fill_value;
+          if ((m.z >> i) & 1u) px[W] = fill_value;
+          if ((m.w >> i) & 1u) px[W + 1] = fill_value;
+        }
+      }
     }
   } else {
     int32_t* labels = labels_all + img_off;
     int32_t* counts = counts_all + img_off;
+    // root block index -> label value needs root / BW: multiply-high by ceil(2^32 / BW) is exact for root < 2^14
+    const uint32_t magic = BW > 1 ? (uint32_t)((0x100000000ull + BW - 1) / BW) : 0u;
     if ((W & 3) == 0) {
-      // root block index -> label value needs root / BW: multiply-high by ceil(2^32 / BW) is exact for root < 2^14
-      const uint32_t magic = BW > 1 ? (uint32_t)((0x100000000ull + BW - 1) / BW) : 0u;
+      // a thread writes 4 pixels of one pixel row = its half of two blocks; block -> run head (bit tricks on the chunk-row's
+      // planes, one broadcast load) -> root -> area
       const int segs = (W + 127) >> 7;
-#pragma unroll 2
+#pragma unroll 4
       for (int task = warp; task < H * segs; task += nwarps) {
         const int r = task / segs, c = ((task - r * segs) << 7) + (lane << 2);
         if (c >= W) continue;
-        const int b0 = (r >> 1) * BW + (c >> 1);
-        const int sh = (r & 1) << 1;
-        const uint32_t oo = *reinterpret_cast<const uint16_t*>(occ + b0);
-        const uint32_t o0 = (oo & 0xFFu) >> sh, o1 = (oo >> 8) >> sh;
+        const int by = r >> 1, i0 = (c >> 1) & 31;
+        const uint4 p = planes[by * chunks + (c >> 6)];
+        const uint32_t pl = (r & 1) ? p.z : p.x, pr = (r & 1) ? p.w : p.y;
+        const uint32_t hm = cc_hm(p), heads = (p.x | p.y | p.z | p.w) & ~hm;
+        const int rowbase = by * BW + ((c >> 6) << 5);
+        const uint32_t a0 = (pl >> i0) & 1u, a1 = (pr >> i0) & 1u, a2 = (pl >> (i0 + 1)) & 1u, a3 = (pr >> (i0 + 1)) & 1u;
         int l0 = 0, l1 = 0, n0 = 0, n1 = 0;
-        if (o0 & 3u) {
-          const int rt = lab[lab[b0] & CC_IDX_MASK] & CC_IDX_MASK;
+        if (a0 | a1) {
+          const int rt = lab[rowbase + cc_head_of(heads, i0)] & CC_IDX_MASK;
           const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
           l0 = q * 2 * W + (rt - q * BW) * 2 + 1;
           n0 = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
         }
-        if (o1 & 3u) {
-          const int rt = lab[lab[b0 + 1] & CC_IDX_MASK] & CC_IDX_MASK;
-          const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
-          l1 = q * 2 * W + (rt - q * BW) * 2 + 1;
-          n1 = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
+        if (a2 | a3) {
+          if ((a0 | a1) && ((hm >> (i0 + 1)) & 1u)) {   // the same run
+            l1 = l0;
+            n1 = n0;
+          } else {
+            const int rt = lab[rowbase + cc_head_of(heads, i0 + 1)] & CC_IDX_MASK;
+            const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
+            l1 = q * 2 * W + (rt - q * BW) * 2 + 1;
+            n1 = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
+          }
         }
-        const int4 lv = make_int4((o0 & 1u) ? l0 : 0, (o0 & 2u) ? l0 : 0, (o1 & 1u) ? l1 : 0, (o1 & 2u) ? l1 : 0);
-        const int4 cv = make_int4((o0 & 1u) ? n0 : 0, (o0 & 2u) ? n0 : 0, (o1 & 1u) ? n1 : 0, (o1 & 2u) ? n1 : 0);
+        const int4 lv = make_int4(a0 ? l0 : 0, a1 ? l0 : 0, a2 ? l1 : 0, a3 ? l1 : 0);
+        const int4 cv = make_int4(a0 ? n0 : 0, a1 ? n0 : 0, a2 ? n1 : 0, a3 ? n1 : 0);
         __stcs(reinterpret_cast<int4*>(labels + (size_t)r * W + c), lv);
         __stcs(reinterpret_cast<int4*>(counts + (size_t)r * W + c), cv);
       }
     } else {
       for (int px = threadIdx.x; px < H * W; px += CC_THREADS) {
         const int r = px / W, c = px % W;
-        const int b0 = (r >> 1) * BW + (c >> 1);
-        const bool fg = (occ[b0] >> (((r & 1) << 1) | (c & 1))) & 1u;
+        const int by = r >> 1, bx = c >> 1;
+        const uint4 p = planes[by * chunks + (bx >> 5)];
+        const uint32_t pl = (r & 1) ? ((c & 1) ? p.w : p.z) : ((c & 1) ? p.y : p.x);
         int l = 0, n = 0;
-        if (fg) {
-          const int rt = lab[lab[b0] & CC_IDX_MASK] & CC_IDX_MASK;
-          l = (rt / BW) * 2 * W + (rt % BW) * 2 + 1;
+        if ((pl >> (bx & 31)) & 1u) {
+          const int rt = cc_root_of(lab, planes, BW, by, bx);
+          const int q = BW > 1 ? (int)__umulhi((uint32_t)rt, magic) : rt;
+          l = q * 2 * W + (rt - q * BW) * 2 + 1;
           n = (int)((uint32_t)lab[rt] >> CC_IDX_BITS);
         }
         labels[px] = l;
@@ -516,16 +549,11 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   __syncthreads();
   CC_MARK(5);
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
-    printf("cc_small<%d> cta %d: A %lld  B-D (region labeller) %lld  E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
+    printf("cc_small<%d> cta %d: A %lld  region labeller %lld  E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
            tr[4] - tr[1], tr[5] - tr[4]);
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("   cta 0 thread 0: B (own band) %lld  wait for the other bands %lld  C %lld  D scan %lld  D flatten %lld  names %d\n",
-           g_cc_tr[0] - tr[1], g_cc_tr[1] - g_cc_tr[0], g_cc_tr[2] - g_cc_tr[1], g_cc_tr[3] - g_cc_tr[2],
-           g_cc_tr[4] - g_cc_tr[3], *name_count);
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    printf("   warp 0: %d rows, %d with a union (%d lanes), %d through the segmented scan\n", g_cc_cnt[3], g_cc_cnt[0], g_cc_cnt[1], g_cc_cnt[2]);
-    g_cc_cnt[0] = g_cc_cnt[1] = g_cc_cnt[2] = g_cc_cnt[3] = 0;
-  }
+    printf("   cta 0 thread 0: I (init) %lld  U1 (hooks) %lld  J (pointer jumping) %lld  U2 (%d deferred pairs) %lld  F (flatten + areas) %lld cycles, %d jumping rounds\n",
+           g_cc_tr[0] - tr[1], g_cc_tr[1] - g_cc_tr[0], g_cc_tr[2] - g_cc_tr[1], *pair_count, g_cc_tr[3] - g_cc_tr[2], g_cc_tr[4] - g_cc_tr[3], (int)g_cc_tr[7]);
 #endif
 }
 
@@ -541,7 +569,7 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
 //   cc_t_final  : block -> root (usually one hop), 8-byte stores of labels / areas (or sparse fill of small holes)
 // DRAM traffic ~11 B/pixel for 9 algorithmic (the first version scattered the forest into the labels array, kept separate
 // occupancy and area arrays and cleared one of them: ~23 B/pixel).
-constexpr int TBH = 32, TBW = 64, T_THREADS = 256, T_NAME_CAP = 512;
+constexpr int TBH = 32, TBW = 64, T_THREADS = 256;
 constexpr int T_BORDER = 2 * (TBH + TBW);   // open-root list entries per tile (one per border block at most)
 
 __device__ __forceinline__ int gfind(const volatile uint32_t* f, int n) {
@@ -552,8 +580,9 @@ __device__ __forceinline__ int gfind(const volatile uint32_t* f, int n) {
   }
   return n;
 }
-// min-root union on words parent << 4 | occupancy: the nibble of a node never changes, so comparing whole words orders
-// by parent
+// min-root union on words parent << 4 | occupancy (the nibble of a node never changes).  Roots are linked with
+// compare-and-swap (see uf_union: linking with atomicMin lets paths leave their set for a moment, and the compression
+// below would then cut links of the other set).
 __device__ __forceinline__ void gunion(uint32_t* f, int a, int b) {
   int ra = gfind(f, a), rb = gfind(f, b);
   while (ra != rb) {
@@ -563,7 +592,7 @@ __device__ __forceinline__ void gunion(uint32_t* f, int a, int b) {
       rb = t;
     }
     const uint32_t nib = reinterpret_cast<const volatile uint32_t*>(f)[ra] & 15u;
-    const uint32_t old = atomicMin(f + ra, ((uint32_t)rb << 4) | nib);
+    const uint32_t old = atomicCAS(f + ra, ((uint32_t)ra << 4) | nib, ((uint32_t)rb << 4) | nib);
     if ((int)(old >> 4) == ra) break;
     ra = gfind(f, (int)(old >> 4));
     rb = gfind(f, rb);
@@ -590,8 +619,9 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
   pdl_enter();
   __shared__ int lab[TBH * TBW];
   __shared__ __align__(16) uint8_t occ[TBH * TBW];
-  __shared__ uint16_t names[T_NAME_CAP];
-  __shared__ int name_count;
+  __shared__ uint4 planes[TBH * (TBW / 32)];
+  __shared__ uint32_t pairs[CC_PAIR_CAP];
+  __shared__ int pair_count;
   const int BHg = H >> 1, BWg = W >> 1;
   const int z = blockIdx.z;
   const size_t off = (size_t)z * H * W;
@@ -635,7 +665,9 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
     }
   }
   __syncthreads();
-  cc_label_region(lab, occ, TBH, TBW, names, &name_count, T_NAME_CAP);
+  cc_planes_from_occ(occ, TBH, TBW, planes);
+  __syncthreads();
+  cc_label_region(lab, planes, TBH, TBW, pairs, &pair_count);
   __syncthreads();
   // roots that reach the tile border (bit 5 of the root's occupancy byte; every writer stores the same bit)
   for (int k = threadIdx.x; k < T_BORDER; k += T_THREADS) {
@@ -646,7 +678,7 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
     else { ly = k - 2 * TBW - TBH; lx = TBW - 1; }
     const int i = ly * TBW + lx;
     if (occ[i] & 0xFu) {
-      const int root = lab[lab[i] & CC_IDX_MASK] & CC_IDX_MASK;
+      const int root = cc_root_of(lab, planes, TBW, ly, lx);
       occ[root] = (uint8_t)(occ[root] | 0x20u);
     }
   }
@@ -659,7 +691,7 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
     const uint32_t o = occ[i];
     const int gb = by * BWg + bx;
     if (o & 0xFu) {
-      const int root = lab[lab[i] & CC_IDX_MASK] & CC_IDX_MASK;
+      const int root = cc_root_of(lab, planes, TBW, ly, lx);
       const int groot = (by0 + root / TBW) * BWg + bx0 + root % TBW;
       forest[gb] = ((uint32_t)groot << 4) | (o & 0xFu);
       if (root == i) {
@@ -789,11 +821,13 @@ __global__ void cc_t_final(int H, int W, const uint32_t* __restrict__ forest_all
   }
 }
 
-bool small_ok(int h, int w) { return (h / 2) * (w / 2) <= CC_MAX_BLOCKS; }
+size_t chunk_rows(int h, int w) { return (size_t)(h / 2) * ((w / 2 + 31) / 32); }
+bool small_ok(int h, int w) { return (h / 2) * (w / 2) <= CC_MAX_BLOCKS && chunk_rows(h, w) <= CC_MAX_CHUNK_ROWS; }
 size_t small_smem(int h, int w) {
   const size_t nb = (size_t)(h / 2) * (w / 2);
-  return nb * 4 + ((nb + 15) & ~(size_t)15) + CC_NAME_CAP * 2 + 16;
+  return chunk_rows(h, w) * 16 + CC_PAIR_CAP * 4 + 16 + nb * 4 + ((nb + 15) & ~(size_t)15) + 16;
 }
+constexpr size_t CC_SMALL_SMEM_MAX = (size_t)CC_MAX_CHUNK_ROWS * 16 + CC_PAIR_CAP * 4 + 32 + (size_t)CC_MAX_BLOCKS * 5 + 16;
 
 template <bool FILL>
 int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, int32_t* counts, int max_area,
@@ -805,8 +839,7 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   if (small_ok(h, w)) {
     static unsigned long long attr[2] = {0, 0};
     if (first_use_on_device(&attr[FILL])) {
-      VLS_CUDA(cudaFuncSetAttribute(cc_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)small_smem(256, 256)));
+      VLS_CUDA(cudaFuncSetAttribute(cc_small_kernel<FILL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CC_SMALL_SMEM_MAX));
     }
     // 128-bit loads need 16-byte aligned rows: W % 16 (uint8) / W % 4 (f32) and an aligned base
     const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0)
