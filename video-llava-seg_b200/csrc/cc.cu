@@ -33,15 +33,6 @@ constexpr int CC_IDX_BITS = 14;                       // block index < 16384; bi
 constexpr int CC_IDX_MASK = (1 << CC_IDX_BITS) - 1;
 constexpr int CC_MAX_CHUNK_ROWS = 1024;               // chunk-rows (32 blocks of one block row) per image on the small path
 
-__device__ __forceinline__ int uf_find(const volatile int* s, int n) {
-  int p = s[n];
-  while (p != n) {
-    n = p;
-    p = s[n];
-  }
-  return n;
-}
-
 // Every node on the path n -> ... -> r gets parent r.  Only valid while every path stays inside its own set: links are made
 // with compare-and-swap on ROOTS (uf_union).  The r1 labeller linked with atomicMin, which re-parents a node that has just
 // stopped being a root (and repairs that by uniting its former parent as well); for a moment the path of a node then leads
@@ -145,12 +136,12 @@ __device__ __forceinline__ uint32_t occ2_from_u8(uint32_t top, uint32_t bot) {
 // A run is named after its head block; only heads are union-find nodes.
 //   U1  hooks: for every upper run a run touches (clz / ffs on the head masks, each upper run once) and for the seams to the
 //       neighbouring chunks ONE atomicMin(word[head], other head) -- no find.  When the head already had another parent, the
-//       pair (old parent, new one) still has to be united: it goes to a list.  Every row hooks at the same time, so a tall
+//       pair (old parent, new one) still has to be united: the thread keeps it (registers) for phase U2.  Every row hooks at the same time, so a tall
 //       component is now a parent chain as long as it is tall -- finds on it are what made the first version of this
 //       labeller slow (45 k cycles of unions, 41-67 k of flattening) --
 //   J   which pointer jumping (word[h] = word[word[h]], all heads in parallel, until nothing changes: log2(height) rounds)
 //       collapses;
-//   U2  the listed pairs are united on the now flat trees (lock-free min-root unions), a thread each;
+//   U2  the deferred pairs are united on the now flat trees (lock-free min-root unions);
 //   F   every head is re-parented to its root and adds its run's pixel count to the root's word; the largest run of every
 //       chunk-row goes through a warp-level reduction by root first (one big component would otherwise receive an atomic
 //       from every chunk-row it covers).
@@ -162,12 +153,11 @@ __device__ __forceinline__ uint32_t cc_run_mask(uint32_t hm, int s) {
   const uint32_t below_e = stop ? ((stop & (0u - stop)) - 1u) : 0xffffffffu;
   return below_e & ~((1u << s) - 1u);
 }
+constexpr int CC_PAIR_CAP = 2048;   // deferred unions (two 16-bit block indices per entry)
+
 // head (bit index) of the run that contains the occupied block `bit`
 __device__ __forceinline__ int cc_head_of(uint32_t heads, int bit) { return 31 - __clz(heads & (0xffffffffu >> (31 - bit))); }
 
-constexpr int CC_ROWS_PER_THREAD = 2;   // chunk-rows per thread at most: CC_MAX_CHUNK_ROWS / CC_THREADS (small path), 64 / 256 (tiles)
-static_assert(CC_MAX_CHUNK_ROWS <= CC_ROWS_PER_THREAD * CC_THREADS, "a thread holds the heads of its chunk-rows in registers");
-constexpr int CC_PAIR_CAP = 2048;   // deferred unions (two 16-bit block indices per entry)
 
 #ifdef CC_TRACE
 __device__ long long g_cc_tr[8];
@@ -201,23 +191,57 @@ __device__ __forceinline__ void cc_planes_from_occ(const uint8_t* occ, int BH, i
 
 // Labels the BH x BW block region described by `planes` (BH * ceil(BW / 32) chunk-row records, complete and followed by
 // __syncthreads on entry), executed by the whole CTA (blockDim.x a multiple of 32).  `lab` has one word per block (row pitch
-// BW); only the words of run heads are used.  On return (after the caller's __syncthreads): every head's word is its root
-// (the smallest block index of the component) and a root's word is root | area << 14.  cc_root_of() maps a block to its root.
-__device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, int BH, int BW, uint32_t* pairs, int* pair_count) {
+// BW); only the words of run heads are used.  `list` receives the block indices of all run heads (up to BH * BW
+// entries: blocks that hold only left-column pixels are all heads): phases U1 / J / F run ONE HEAD PER THREAD over that list, so a chunk-row full of speckle (16 runs) does not hold up a
+// warp whose other lanes own one run each.  `ctl` = two counters; `pairs` = CC_PAIR_CAP words.  On return (after the caller's __syncthreads): every head's
+// word is its root (the smallest block index of the component) and a root's word is root | area << 14.  cc_root_of() maps
+// a block to its root.
+__device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, int BH, int BW, uint32_t* pairs, int* ctl,
+                                                uint16_t* list) {
   const int nthreads = blockDim.x, lane = threadIdx.x & 31;
   const int chunks = (BW + 31) >> 5, nrows = BH * chunks, nb = BH * BW;
   const uint32_t magic = chunks > 1 ? (uint32_t)((0x100000000ull + chunks - 1) / chunks) : 0u;   // r / chunks, exact for r < 2^16
+  const uint32_t bw_magic = BW > 1 ? (uint32_t)((0x100000000ull + BW - 1) / BW) : 0u;             // idx / BW, exact for idx < 2^14
+  int* head_count = ctl;
+  int* pair_count = ctl + 1;
   // I. every word its own root
   if ((nb & 3) == 0 && (reinterpret_cast<uintptr_t>(lab) & 15) == 0) {
     for (int i = threadIdx.x * 4; i < nb; i += nthreads * 4) *reinterpret_cast<int4*>(lab + i) = make_int4(i, i + 1, i + 2, i + 3);
   } else {
     for (int i = threadIdx.x; i < nb; i += nthreads) lab[i] = i;
   }
-  if (threadIdx.x == 0) *pair_count = 0;
+  if (threadIdx.x < 2) ctl[threadIdx.x] = 0;
+  __syncthreads();
+  // L. list of the run heads (thread per chunk-row; one atomic per warp)
+  for (int r0 = threadIdx.x - lane; r0 < nrows; r0 += nthreads) {
+    const int r = r0 + lane;
+    uint32_t hh = 0u;
+    int base = 0;
+    if (r < nrows) {
+      const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
+      hh = cc_heads(planes[r]);
+      base = by * BW + (ch << 5);
+    }
+    const int cnt = __popc(hh);
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    int wbase = 0;
+    if (lane == 31 && incl) wbase = atomicAdd(head_count, incl);
+    int pos = __shfl_sync(0xffffffffu, wbase, 31) + incl - cnt;
+    while (hh) {
+      list[pos++] = (uint16_t)(base + __ffs(hh) - 1);
+      hh &= hh - 1;
+    }
+  }
   __syncthreads();
   CC_RMARK(0);
+  const int nheads = *head_count;
   // a > b.  old == a: a was a root and now hangs below b.  Otherwise a already had the parent `old`: the smaller of the two
-  // is its parent now and the pair (old, b) is still to be united.
+  // is its parent now and the pair (old, b) is still to be united (phase U2).
   auto hook = [&](int a, int b) {
     const int old = atomicMin(lab + a, b);
     if (old != a && old != b) {
@@ -226,87 +250,74 @@ __device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, i
       else uf_union<false>(lab, old, b);   // list full: unite now (hooks still re-parent heads, so without compression)
     }
   };
-  // U1. hooks, one thread per chunk-row
-  for (int r = threadIdx.x; r < nrows; r += nthreads) {
+  // U1. hooks of every run (all hooks of a head come from its one thread, in sequence)
+  for (int e = threadIdx.x; e < nheads; e += nthreads) {
+    const int idx = list[e];
+    const int by = BW > 1 ? (int)__umulhi((uint32_t)idx, bw_magic) : idx, col = idx - by * BW;
+    const int ch = col >> 5, s = col & 31, r = by * chunks + ch, base = idx - s;
     const uint4 m = planes[r];
-    const uint32_t occm = m.x | m.y | m.z | m.w;
-    if (!occm) continue;
-    const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
-    const uint32_t hm = cc_hm(m), heads = occm & ~hm;
-    const int base = by * BW + (ch << 5);
-    if (ch > 0 && ((m.x | m.z) & 1u)) {           // block 0 joins the last block of the chunk to the left
+    const uint32_t hm = cc_hm(m), run = cc_run_mask(hm, s);
+    if (s == 0 && ch > 0 && ((m.x | m.z) & 1u)) {   // block 0 joins the last block of the chunk to the left
       const uint4 l = planes[r - 1];
-      if ((l.y | l.w) >> 31) hook(base, base - 32 + (31 - __clz(cc_heads(l))));
+      if ((l.y | l.w) >> 31) hook(idx, base - 32 + (31 - __clz(cc_heads(l))));
     }
     if (by == 0) continue;
     const uint4 u = planes[r - chunks];
     const int ubase = base - BW;
-    const uint32_t tu = (m.x | m.y) & (u.z | u.w), tul = m.x & (u.w << 1), tur = m.y & (u.z >> 1);
-    if (tu | tul | tur) {
+    uint32_t upm = (((m.x | m.y) & (u.z | u.w)) & run) | (((m.x & (u.w << 1)) & run) >> 1) | (((m.y & (u.z >> 1)) & run) << 1);
+    if (upm) {                                      // upper blocks this run touches
       const uint32_t hmu = cc_hm(u), uheads = (u.x | u.y | u.z | u.w) & ~hmu;
-      uint32_t hh = heads;
-      while (hh) {
-        const int s = __ffs(hh) - 1;
-        hh &= hh - 1;
-        const uint32_t run = cc_run_mask(hm, s);
-        uint32_t upm = (tu & run) | ((tul & run) >> 1) | ((tur & run) << 1);   // upper blocks this run touches
-        while (upm) {
-          const int hj = cc_head_of(uheads, __ffs(upm) - 1);                    // the upper run that contains the lowest of them
-          upm &= ~cc_run_mask(hmu, hj);
-          hook(base + s, ubase + hj);
-        }
-      }
+      do {
+        const int hj = cc_head_of(uheads, __ffs(upm) - 1);   // the upper run that contains the lowest of them
+        upm &= ~cc_run_mask(hmu, hj);
+        hook(idx, ubase + hj);
+      } while (upm);
     }
-    if (ch > 0 && (m.x & 1u)) {                   // top-left pixel of block 0 against the bottom-right pixel of the upper-left chunk
+    if (s == 0 && ch > 0 && (m.x & 1u)) {           // top-left pixel of block 0 against the bottom-right pixel of the upper-left chunk
       const uint4 ul = planes[r - chunks - 1];
-      if (ul.w >> 31) hook(base, ubase - 32 + (31 - __clz(cc_heads(ul))));
+      if (ul.w >> 31) hook(idx, ubase - 32 + (31 - __clz(cc_heads(ul))));
     }
-    if (ch + 1 < chunks && (m.y >> 31)) {         // top-right pixel of block 31 against the bottom-left pixel of the upper-right chunk
+    if ((run >> 31) && ch + 1 < chunks && (m.y >> 31)) {   // top-right pixel of block 31 against the bottom-left pixel of the upper-right chunk
       const uint4 ur = planes[r - chunks + 1];
-      if (ur.z & 1u) hook(base + (31 - __clz(heads)), ubase + 32);
+      if (ur.z & 1u) hook(idx, ubase + 32);
     }
   }
   __syncthreads();
   CC_RMARK(1);
   // J. pointer jumping over the heads until every head points at a root of the hook forest.  A thread keeps the still
-  //    unresolved heads of its (at most CC_ROWS_PER_THREAD) chunk-rows as bit masks in registers: after the first rounds only
+  //    unresolved ones of its list entries (e = thread + k * nthreads, k < 32) as a bit mask: after the first rounds only
   //    the heads of tall components are left.
   {
     const volatile int* v = lab;
-    uint32_t pend[CC_ROWS_PER_THREAD];
-    int pbase[CC_ROWS_PER_THREAD];
-#pragma unroll
-    for (int k = 0; k < CC_ROWS_PER_THREAD; ++k) {
-      const int r = threadIdx.x + k * nthreads;
-      pend[k] = 0u;
-      pbase[k] = 0;
-      if (r < nrows) {
-        const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
-        pend[k] = cc_heads(planes[r]);
-        pbase[k] = by * BW + (ch << 5);
-      }
-    }
+    uint32_t pend = 0u;
+    for (int k = 0, e = threadIdx.x; e < nheads && k < 32; ++k, e += nthreads) pend |= 1u << k;
     int changed;
 #ifdef CC_TRACE
     int rounds = 0;
 #endif
     do {
       changed = 0;
-#pragma unroll
-      for (int k = 0; k < CC_ROWS_PER_THREAD; ++k) {
-        uint32_t hh = pend[k];
-        while (hh) {
-          const int bit = __ffs(hh) - 1;
-          hh &= hh - 1;
-          const int h = pbase[k] + bit;
-          const int p = v[h];
-          const int gp = v[p];
-          if (gp == p) {
-            pend[k] &= ~(1u << bit);               // the parent is a root (or h itself is): done
-          } else {
-            lab[h] = v[gp];                        // up to three levels per round (every ancestor is a valid parent)
-            changed = 1;
-          }
+      uint32_t pp = pend;
+      while (pp) {
+        const int k = __ffs(pp) - 1;
+        pp &= pp - 1;
+        const int h = list[threadIdx.x + k * nthreads];
+        const int p = v[h];
+        const int gp = v[p];
+        if (gp == p) {
+          pend &= ~(1u << k);                      // the parent is a root (or h itself is): done
+        } else {
+          lab[h] = v[gp];                          // up to three levels per round (every ancestor is a valid parent)
+          changed = 1;
+        }
+      }
+      for (int e = threadIdx.x + 32 * nthreads; e < nheads; e += nthreads) {   // (more than 32 heads per thread: never on the paths in use)
+        const int hh = list[e];
+        const int pp = v[hh];
+        const int gg = v[pp];
+        if (gg != pp) {
+          lab[hh] = v[gg];
+          changed = 1;
         }
       }
 #ifdef CC_TRACE
@@ -318,7 +329,7 @@ __device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, i
 #endif
   }
   CC_RMARK(2);
-  // U2. the deferred pairs
+  // U2. the deferred pairs, on the now flat trees
   {
     const int n = min(*pair_count, CC_PAIR_CAP);
     for (int i = threadIdx.x; i < n; i += nthreads) uf_union(lab, (int)(pairs[i] & 0xffffu), (int)(pairs[i] >> 16));
@@ -326,45 +337,25 @@ __device__ __forceinline__ void cc_label_region(int* lab, const uint4* planes, i
   __syncthreads();
   CC_RMARK(3);
   // F. every head: parent -> root, and its run's pixel count onto the root's word (finds ignore the area bits; only roots
-  //    receive area, only non-roots are re-parented, so the plain stores and the atomic adds never touch the same word)
-  for (int r0 = threadIdx.x - lane; r0 < nrows; r0 += nthreads) {   // whole warps: the reduction below needs all 32 lanes
-    const int r = r0 + lane;
-    int best_root = -1, best_area = 0;
-    if (r < nrows) {
-      const uint4 m = planes[r];
-      const uint32_t occm = m.x | m.y | m.z | m.w;
-      if (occm) {
-        const int by = chunks > 1 ? (int)__umulhi((uint32_t)r, magic) : r, ch = r - by * chunks;
-        const uint32_t hm = cc_hm(m);
-        const int base = by * BW + (ch << 5);
-        uint32_t hh = occm & ~hm;
-        while (hh) {
-          const int s = __ffs(hh) - 1;
-          hh &= hh - 1;
-          const uint32_t run = cc_run_mask(hm, s);
-          int area = __popc(m.x & run) + __popc(m.y & run) + __popc(m.z & run) + __popc(m.w & run);
-          const int idx = base + s;
-          int root = ufa_find(lab, idx);
-          if (root != idx) lab[idx] = root;
-          if (root == best_root) {
-            best_area += area;
-          } else {
-            if (area > best_area) {                // keep the largest run for the warp-level reduction
-              const int tr = root, ta = area;
-              root = best_root;
-              area = best_area;
-              best_root = tr;
-              best_area = ta;
-            }
-            if (area) atomicAdd(lab + root, area << CC_IDX_BITS);
-          }
-        }
-      }
+  //    receive area, only non-roots are re-parented, so the plain stores and the atomic adds never touch the same word).
+  //    Neighbouring list entries are neighbouring runs, mostly of one big component: the areas are first summed per root
+  //    inside the warp, one atomic per distinct root.
+  for (int e0 = threadIdx.x - lane; e0 < nheads; e0 += nthreads) {
+    const int e = e0 + lane;
+    int root = -1 - lane, area = 0;
+    if (e < nheads) {
+      const int idx = list[e];
+      const int by = BW > 1 ? (int)__umulhi((uint32_t)idx, bw_magic) : idx, col = idx - by * BW;
+      const uint4 m = planes[by * chunks + (col >> 5)];
+      const uint32_t run = cc_run_mask(cc_hm(m), col & 31);
+      area = __popc(m.x & run) + __popc(m.y & run) + __popc(m.z & run) + __popc(m.w & run);
+      root = ufa_find(lab, idx);
+      if (root != idx) lab[idx] = root;
     }
     __syncwarp();
-    const uint32_t grp = __match_any_sync(0xffffffffu, best_area ? best_root : -1 - lane);
-    const int total = __reduce_add_sync(grp, best_area);
-    if (best_area && lane == __ffs(grp) - 1) atomicAdd(lab + best_root, total << CC_IDX_BITS);
+    const uint32_t grp = __match_any_sync(0xffffffffu, root);
+    const int total = __reduce_add_sync(grp, area);
+    if (area && lane == __ffs(grp) - 1) atomicAdd(lab + root, total << CC_IDX_BITS);
   }
   CC_RMARK(4);
 }
@@ -390,9 +381,10 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   const int chunks = (BW + 31) >> 5, nrows = BH * chunks;
   uint4* planes = reinterpret_cast<uint4*>(cc_smem);              // [nrows] (first: 16-byte aligned for any nb)
   uint32_t* pairs = reinterpret_cast<uint32_t*>(cc_smem + 4 * nrows);
-  int* pair_count = cc_smem + 4 * nrows + CC_PAIR_CAP;
-  int* lab = pair_count + 4;
-  uint8_t* occ = reinterpret_cast<uint8_t*>(lab + nb);
+  int* ctl = cc_smem + 4 * nrows + CC_PAIR_CAP;                  // head / pair counters
+  int* lab = ctl + 4;
+  uint8_t* occ = reinterpret_cast<uint8_t*>(lab + nb);            // occupancy bytes of the generic paths, then the head list
+  uint16_t* list = reinterpret_cast<uint16_t*>(occ);              // [nb]
   const size_t img_off = (size_t)blockIdx.x * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + img_off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + img_off);
@@ -452,7 +444,7 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
   }
   __syncthreads();
   CC_MARK(1);
-  cc_label_region(lab, planes, BH, BW, pairs, pair_count);
+  cc_label_region(lab, planes, BH, BW, pairs, ctl, list);
   __syncthreads();
   CC_MARK(4);
   // E. outputs
@@ -552,8 +544,8 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
     printf("cc_small<%d> cta %d: A %lld  region labeller %lld  E %lld cycles\n", (int)FILL, blockIdx.x, tr[1] - tr[0],
            tr[4] - tr[1], tr[5] - tr[4]);
   if (threadIdx.x == 0 && blockIdx.x == 0)
-    printf("   cta 0 thread 0: I (init) %lld  U1 (hooks) %lld  J (pointer jumping) %lld  U2 (%d deferred pairs) %lld  F (flatten + areas) %lld cycles, %d jumping rounds\n",
-           g_cc_tr[0] - tr[1], g_cc_tr[1] - g_cc_tr[0], g_cc_tr[2] - g_cc_tr[1], *pair_count, g_cc_tr[3] - g_cc_tr[2], g_cc_tr[4] - g_cc_tr[3], (int)g_cc_tr[7]);
+    printf("   cta 0 thread 0: I + L (init, %d heads listed) %lld  U1 (hooks) %lld  J (pointer jumping) %lld  U2 (%d deferred pairs) %lld  F (flatten + areas) %lld cycles, %d jumping rounds\n",
+           ctl[0], g_cc_tr[0] - tr[1], g_cc_tr[1] - g_cc_tr[0], g_cc_tr[2] - g_cc_tr[1], ctl[1], g_cc_tr[3] - g_cc_tr[2], g_cc_tr[4] - g_cc_tr[3], (int)g_cc_tr[7]);
 #endif
 }
 
@@ -620,8 +612,9 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
   __shared__ int lab[TBH * TBW];
   __shared__ __align__(16) uint8_t occ[TBH * TBW];
   __shared__ uint4 planes[TBH * (TBW / 32)];
+  __shared__ uint16_t heads[TBH * TBW];
   __shared__ uint32_t pairs[CC_PAIR_CAP];
-  __shared__ int pair_count;
+  __shared__ int ctl[2];
   const int BHg = H >> 1, BWg = W >> 1;
   const int z = blockIdx.z;
   const size_t off = (size_t)z * H * W;
@@ -667,7 +660,7 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
   __syncthreads();
   cc_planes_from_occ(occ, TBH, TBW, planes);
   __syncthreads();
-  cc_label_region(lab, planes, TBH, TBW, pairs, &pair_count);
+  cc_label_region(lab, planes, TBH, TBW, pairs, ctl, heads);
   __syncthreads();
   // roots that reach the tile border (bit 5 of the root's occupancy byte; every writer stores the same bit)
   for (int k = threadIdx.x; k < T_BORDER; k += T_THREADS) {
@@ -825,9 +818,10 @@ size_t chunk_rows(int h, int w) { return (size_t)(h / 2) * ((w / 2 + 31) / 32); 
 bool small_ok(int h, int w) { return (h / 2) * (w / 2) <= CC_MAX_BLOCKS && chunk_rows(h, w) <= CC_MAX_CHUNK_ROWS; }
 size_t small_smem(int h, int w) {
   const size_t nb = (size_t)(h / 2) * (w / 2);
-  return chunk_rows(h, w) * 16 + CC_PAIR_CAP * 4 + 16 + nb * 4 + ((nb + 15) & ~(size_t)15) + 16;
+  // planes | deferred pairs | counters | words | occupancy bytes, re-used as the list of run heads (16 bits per block)
+  return chunk_rows(h, w) * 16 + CC_PAIR_CAP * 4 + 16 + nb * 4 + ((nb * 2 + 15) & ~(size_t)15) + 16;
 }
-constexpr size_t CC_SMALL_SMEM_MAX = (size_t)CC_MAX_CHUNK_ROWS * 16 + CC_PAIR_CAP * 4 + 32 + (size_t)CC_MAX_BLOCKS * 5 + 16;
+constexpr size_t CC_SMALL_SMEM_MAX = (size_t)CC_MAX_CHUNK_ROWS * 16 + CC_PAIR_CAP * 4 + 32 + (size_t)CC_MAX_BLOCKS * 6 + 16;
 
 template <bool FILL>
 int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, int32_t* counts, int max_area,
