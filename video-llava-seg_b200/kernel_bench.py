@@ -18,7 +18,9 @@ def cases(dev, quick=True):
     shape, CC stress shape, fuser dwconv) + LayerNorm; otherwise also noise input / hole filling."""
     lib = _lib.lib()
     g = torch.Generator().manual_seed(0)
-    shapes = [(512, 256, 256, "blobby"), (64, 1024, 1024, "blobby")] + ([] if quick else [(64, 1024, 1024, "noise")])
+    # 592 = 148 SMs x 2 resident CTAs x 2: whole waves of the one-CTA-per-image kernel (512 images are 1.73 waves)
+    shapes = [(512, 256, 256, "blobby"), (592, 256, 256, "blobby"), (64, 1024, 1024, "blobby")] + \
+        ([] if quick else [(64, 1024, 1024, "noise")])
     for (n, h, w, kind) in shapes:
         m = (_blobby(g, n, h, w) if kind == "blobby" else torch.rand(n, 1, h, w, generator=g) < 0.55).to(dev).to(torch.uint8)
         nb = lib.vls_cc_workspace_bytes(n, h, w)
