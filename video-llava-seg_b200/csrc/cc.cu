@@ -565,8 +565,9 @@ cc_small_kernel(const void* img_all, int H, int W, int32_t* labels_all, int32_t*
 //   cc_t_final  : block -> root (usually one hop), 8-byte stores of labels / areas (or sparse fill of small holes)
 // DRAM traffic ~11 B/pixel for 9 algorithmic (the first version scattered the forest into the labels array, kept separate
 // occupancy and area arrays and cleared one of them: ~23 B/pixel).
-constexpr int TBH = 32, TBW = 64, T_THREADS = 256;
-constexpr int T_BORDER = 2 * (TBH + TBW);   // open-root list entries per tile (one per border block at most)
+constexpr int TBH = 32, TBW = 64, T_THREADS = 256;   // small tiles
+constexpr int BTH = 128, BTW = 128;                   // big tiles (CC_THREADS threads)
+constexpr int T_BORDER = 2 * (TBH + TBW);   // open-root list entries per small tile (one per border block at most)
 
 __device__ __forceinline__ int gfind(const volatile uint32_t* f, int n) {
   uint32_t w = f[n];
@@ -608,28 +609,39 @@ __device__ __forceinline__ void gunion(uint32_t* f, int a, int b) {
   }
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(T_THREADS)
+template <int TH, int TW>
+constexpr size_t cc_tile_smem() {   // planes | deferred pairs | counters | words | occupancy bytes, then the head list
+  return (size_t)TH * (TW / 32) * 16 + CC_PAIR_CAP * 4 + 16 + (size_t)TH * TW * 4 + (size_t)TH * TW * 2;
+}
+
+// Tile = TH x TW blocks (32 x 64 for images smaller than 256 pixels in a dimension, else 128 x 128 = the small path's
+// 256 x 256 pixels: the labeller's phases are latency chains of about the same length whatever the tile size, and a tile's
+// border work grows with its perimeter).
+template <bool FILL, int TH, int TW, int THREADS>
+__global__ void __launch_bounds__(THREADS)
 cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, uint32_t* forest_all, int32_t* area_all,
            int* list_count, int2* list) {
   pdl_enter();
-  __shared__ int lab[TBH * TBW];
-  __shared__ __align__(16) uint8_t occ[TBH * TBW];
-  __shared__ uint4 planes[TBH * (TBW / 32)];
-  __shared__ uint16_t heads[TBH * TBW];
-  __shared__ uint32_t pairs[CC_PAIR_CAP];
-  __shared__ int ctl[2];
+  extern __shared__ __align__(16) int cc_tile_smem_base[];
+  constexpr int CHT = TW / 32;
+  uint4* planes = reinterpret_cast<uint4*>(cc_tile_smem_base);          // [TH * CHT]
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(cc_tile_smem_base + 4 * TH * CHT);
+  int* ctl = cc_tile_smem_base + 4 * TH * CHT + CC_PAIR_CAP;
+  int* lab = ctl + 4;                                                    // [TH * TW]
+  uint8_t* occ = reinterpret_cast<uint8_t*>(lab + TH * TW);             // [TH * TW] bytes, then the head list (2 bytes per block)
+  uint16_t* heads = reinterpret_cast<uint16_t*>(occ);
   const int BHg = H >> 1, BWg = W >> 1;
   const int z = blockIdx.z;
   const size_t off = (size_t)z * H * W;
   const void* img = FILL ? static_cast<const void*>(scores_all + off)
                          : static_cast<const void*>(reinterpret_cast<const uint8_t*>(img_all) + off);
-  const int by0 = blockIdx.y * TBH, bx0 = blockIdx.x * TBW;
+  const int by0 = blockIdx.y * TH, bx0 = blockIdx.x * TW;
   // A. occupancy of the tile (blocks outside the image are empty)
-  if (vec && !FILL) {   // 2 x 16 pixels -> 8 blocks per thread: exactly one unit per thread
+  if (vec && !FILL) {   // 2 x 16 pixels -> 8 blocks per thread
     const uint8_t* p = reinterpret_cast<const uint8_t*>(img);
-    for (int u = threadIdx.x; u < TBH * (TBW / 8); u += T_THREADS) {
-      const int ly = u / (TBW / 8), k = u % (TBW / 8);
+#pragma unroll 2
+    for (int u = threadIdx.x; u < TH * (TW / 8); u += THREADS) {
+      const int ly = u / (TW / 8), k = u % (TW / 8);
       const int by = by0 + ly, bx = bx0 + 8 * k;
       uint2 o = make_uint2(0u, 0u);
       if (by < BHg && bx < BWg) {   // W % 16 == 0: a unit is inside the image or completely outside
@@ -638,13 +650,13 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
         o.x = occ2_from_u8(t.x, b.x) | (occ2_from_u8(t.y, b.y) << 16);
         o.y = occ2_from_u8(t.z, b.z) | (occ2_from_u8(t.w, b.w) << 16);
       }
-      *reinterpret_cast<uint2*>(occ + ly * TBW + 8 * k) = o;
+      *reinterpret_cast<uint2*>(occ + ly * TW + 8 * k) = o;
     }
   } else if (vec && FILL) {   // 2 x float4 -> 2 blocks
     const float* f = reinterpret_cast<const float*>(img);
 #pragma unroll 4
-    for (int u = threadIdx.x; u < TBH * (TBW / 2); u += T_THREADS) {
-      const int ly = u / (TBW / 2), k = u % (TBW / 2);
+    for (int u = threadIdx.x; u < TH * (TW / 2); u += THREADS) {
+      const int ly = u / (TW / 2), k = u % (TW / 2);
       const int by = by0 + ly, bx = bx0 + 2 * k;
       uint32_t o = 0;
       if (by < BHg && bx < BWg) {   // W % 4 == 0
@@ -653,47 +665,48 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
         o = (t.x <= 0.f ? 1u : 0u) | (t.y <= 0.f ? 2u : 0u) | (b.x <= 0.f ? 4u : 0u) | (b.y <= 0.f ? 8u : 0u);
         o |= ((t.z <= 0.f ? 1u : 0u) | (t.w <= 0.f ? 2u : 0u) | (b.z <= 0.f ? 4u : 0u) | (b.w <= 0.f ? 8u : 0u)) << 8;
       }
-      *reinterpret_cast<uint16_t*>(occ + ly * TBW + 2 * k) = (uint16_t)o;
+      *reinterpret_cast<uint16_t*>(occ + ly * TW + 2 * k) = (uint16_t)o;
     }
   } else {
-    for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
-      const int by = by0 + i / TBW, bx = bx0 + i % TBW;
+    for (int i = threadIdx.x; i < TH * TW; i += THREADS) {
+      const int by = by0 + i / TW, bx = bx0 + i % TW;
       occ[i] = (by < BHg && bx < BWg) ? (uint8_t)load_occ<FILL>(img, H, W, by, bx, 0.f) : (uint8_t)0;
     }
   }
   __syncthreads();
-  cc_planes_from_occ(occ, TBH, TBW, planes);
+  cc_planes_from_occ(occ, TH, TW, planes);
   __syncthreads();
-  cc_label_region(lab, planes, TBH, TBW, pairs, ctl, heads);
+  cc_label_region(lab, planes, TH, TW, pairs, ctl, heads);   // (the occupancy bytes are gone: their memory is the head list now)
   __syncthreads();
-  // roots that reach the tile border (bit 5 of the root's occupancy byte; every writer stores the same bit)
-  for (int k = threadIdx.x; k < T_BORDER; k += T_THREADS) {
+  // roots that reach the tile border: the sign bit of the root's word (area needs 17 bits above the 14 index bits)
+  constexpr int NBORDER = 2 * (TH + TW);
+  for (int k = threadIdx.x; k < NBORDER; k += THREADS) {
     int ly, lx;
-    if (k < TBW) { ly = 0; lx = k; }
-    else if (k < 2 * TBW) { ly = TBH - 1; lx = k - TBW; }
-    else if (k < 2 * TBW + TBH) { ly = k - 2 * TBW; lx = 0; }
-    else { ly = k - 2 * TBW - TBH; lx = TBW - 1; }
-    const int i = ly * TBW + lx;
-    if (occ[i] & 0xFu) {
-      const int root = cc_root_of(lab, planes, TBW, ly, lx);
-      occ[root] = (uint8_t)(occ[root] | 0x20u);
-    }
+    if (k < TW) { ly = 0; lx = k; }
+    else if (k < 2 * TW) { ly = TH - 1; lx = k - TW; }
+    else if (k < 2 * TW + TH) { ly = k - 2 * TW; lx = 0; }
+    else { ly = k - 2 * TW - TH; lx = TW - 1; }
+    const uint4 p = planes[ly * CHT + (lx >> 5)];
+    if (((p.x | p.y | p.z | p.w) >> (lx & 31)) & 1u) atomicOr(lab + cc_root_of(lab, planes, TW, ly, lx), (int)0x80000000);
   }
   __syncthreads();
   uint32_t* forest = forest_all + (size_t)z * BHg * BWg;
   int32_t* area = area_all + (size_t)z * BHg * BWg;
-  for (int i = threadIdx.x; i < TBH * TBW; i += T_THREADS) {
-    const int ly = i / TBW, lx = i % TBW, by = by0 + ly, bx = bx0 + lx;
+  for (int i = threadIdx.x; i < TH * TW; i += THREADS) {
+    const int ly = i / TW, lx = i % TW, by = by0 + ly, bx = bx0 + lx;
     if (by >= BHg || bx >= BWg) continue;
-    const uint32_t o = occ[i];
+    const uint4 p = planes[ly * CHT + (lx >> 5)];
+    const int bit = lx & 31;
+    const uint32_t o = ((p.x >> bit) & 1u) | (((p.y >> bit) & 1u) << 1) | (((p.z >> bit) & 1u) << 2) | (((p.w >> bit) & 1u) << 3);
     const int gb = by * BWg + bx;
-    if (o & 0xFu) {
-      const int root = cc_root_of(lab, planes, TBW, ly, lx);
-      const int groot = (by0 + root / TBW) * BWg + bx0 + root % TBW;
-      forest[gb] = ((uint32_t)groot << 4) | (o & 0xFu);
+    if (o) {
+      const int root = lab[ly * TW + (lx & ~31) + cc_head_of(cc_heads(p), bit)] & CC_IDX_MASK;
+      const int groot = (by0 + root / TW) * BWg + bx0 + root % TW;
+      forest[gb] = ((uint32_t)groot << 4) | o;
       if (root == i) {
-        area[gb] = (int)((uint32_t)lab[i] >> CC_IDX_BITS);
-        if (o & 0x20u) list[atomicAdd(list_count, 1)] = make_int2(z, gb);
+        const int word = lab[i];
+        area[gb] = (int)(((uint32_t)word & 0x7fffffffu) >> CC_IDX_BITS);
+        if (word < 0) list[atomicAdd(list_count, 1)] = make_int2(z, gb);
       }
     } else {
       forest[gb] = (uint32_t)gb << 4;
@@ -701,30 +714,32 @@ cc_t_label(const void* img_all, const float* scores_all, int H, int W, int vec, 
   }
 }
 
-// One warp per tile edge piece: the two 32-block halves of the top row (lanes = consecutive blocks: coalesced loads,
+// One warp per tile edge piece: the 32-block pieces of the top row (lanes = consecutive blocks: coalesced loads,
 // neighbours by shuffle, and the same pruning as inside a tile -- a run that crosses the border costs ONE union, not one
-// per block), the left column and the right column (lanes = rows).
+// per block), of the left column and of the right column (lanes = rows).
+template <int TH, int TW>
 __global__ void cc_t_border(int H, int W, uint32_t* forest_all) {
   pdl_enter();
+  constexpr int PT = TW / 32, PC = TH / 32, PIECES = PT + 2 * PC;
   const int BH = H >> 1, BW = W >> 1;
-  const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
+  const int tiles_x = (BW + TW - 1) / TW, tiles_y = (BH + TH - 1) / TH;
   const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (gw >= tiles_x * tiles_y * 4) return;
-  const int tile = gw >> 2, piece = gw & 3;
+  if (gw >= tiles_x * tiles_y * PIECES) return;
+  const int tile = gw / PIECES, piece = gw - tile * PIECES;
   const int ty = tile / tiles_x, tx = tile - ty * tiles_x;
-  const int by0 = ty * TBH, bx0 = tx * TBW;
+  const int by0 = ty * TH, bx0 = tx * TW;
   uint32_t* forest = forest_all + (size_t)blockIdx.z * BH * BW;
   auto nib = [&](int y, int x) -> uint32_t {
     return (y >= 0 && y < BH && x >= 0 && x < BW) ? (forest[y * BW + x] & 15u) : 0u;   // a word's nibble never changes
   };
-  if (piece < 2) {   // top row, blocks bx0 + 32*piece + lane
+  if (piece < PT) {   // top row, blocks bx0 + 32*piece + lane
     const int by = by0, bx = bx0 + 32 * piece + lane;
     if (by == 0 || by >= BH) return;
     const uint32_t me = nib(by, bx), up = nib(by - 1, bx);
     uint32_t left = __shfl_up_sync(0xffffffffu, me, 1), ul = __shfl_up_sync(0xffffffffu, up, 1);
     uint32_t ur = __shfl_down_sync(0xffffffffu, up, 1);
     if (lane == 0) {
-      left = piece == 1 ? nib(by, bx - 1) : 0u;   // the block before the tile's first one belongs to another tile
+      left = piece > 0 ? nib(by, bx - 1) : 0u;   // the block before the tile's first one belongs to another tile
       ul = nib(by - 1, bx - 1);
     }
     if (lane == 31) ur = nib(by - 1, bx + 1);
@@ -738,21 +753,21 @@ __global__ void cc_t_border(int H, int W, uint32_t* forest_all) {
     if (cu && !cu_redundant) gunion(forest, idx, idx - BW);
     if (cul) gunion(forest, idx, idx - BW - 1);
     if (cur) gunion(forest, idx, idx - BW + 1);
-  } else if (piece == 2) {   // left column, rows by0 + lane
-    const int by = by0 + lane, bx = bx0;
+  } else if (piece < PT + PC) {   // left column, rows by0 + 32*(piece - PT) + lane
+    const int ly = 32 * (piece - PT) + lane, by = by0 + ly, bx = bx0;
     if (bx == 0 || by >= BH) return;
     const uint32_t me = nib(by, bx);
     if (!me) return;
     const uint32_t lf = nib(by, bx - 1);
     const int idx = by * BW + bx;
     if (conn_left(me, lf)) gunion(forest, idx, idx - 1);
-    if (lane > 0) {          // the tile's first row is the top-row piece's business
+    if (ly > 0) {            // the tile's first row is the top-row piece's business
       const uint32_t up = nib(by - 1, bx), ul = nib(by - 1, bx - 1);
       if (conn_upleft(me, ul) && !(conn_up(me, up) && conn_left(up, ul))) gunion(forest, idx, idx - BW - 1);
     }
   } else {   // right column
-    const int by = by0 + lane, bx = bx0 + TBW - 1;
-    if (lane == 0 || bx + 1 >= BW || by >= BH) return;
+    const int ly = 32 * (piece - PT - PC) + lane, by = by0 + ly, bx = bx0 + TW - 1;
+    if (ly == 0 || bx + 1 >= BW || by >= BH) return;
     const uint32_t me = nib(by, bx);
     if (!me) return;
     const uint32_t up = nib(by - 1, bx), ur = nib(by - 1, bx + 1);
@@ -851,14 +866,24 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
   VLS_REQUIRE(((uintptr_t)ws % 16) == 0, "cc: workspace must be 16-byte aligned");
   const int BH = h / 2, BW = w / 2;
   const size_t nblk1 = (size_t)BH * BW;                       // blocks per image
-  const int tiles_x = (BW + TBW - 1) / TBW, tiles_y = (BH + TBH - 1) / TBH;
+  // 64 x 128-pixel tiles.  256 x 256-pixel ones (the kernels are templates on the tile size) were measured on 64 x 1024^2:
+  // border unions 39 -> 24 us per half, but labelling 79 -> 96 us (512 CTAs per half on 296 slots = 1.7 waves of a CTA that
+  // takes 90 k cycles; noise input 630 vs 400 us in total), so they stay off.
+  const bool big = false;
+  const int th = big ? BTH : TBH, tw = big ? BTW : TBW;
+  const int tiles_x = (BW + tw - 1) / tw, tiles_y = (BH + th - 1) / th;
   uint32_t* forest = reinterpret_cast<uint32_t*>(ws);
   int32_t* area = reinterpret_cast<int32_t*>(forest + nblk1 * n);
   int* list_count = reinterpret_cast<int*>(area + nblk1 * n);   // one counter per slice, 16 bytes reserved
   int2* list = reinterpret_cast<int2*>(list_count + 4);
-  const size_t list_per_image = (size_t)tiles_x * tiles_y * T_BORDER;
+  const size_t list_per_image = (size_t)tiles_x * tiles_y * 2 * (th + tw);   // one entry per border block of a tile at most
   VLS_CUDA(cudaMemsetAsync(list_count, 0, 16, stream));
   const int vec = FILL ? ((w % 4) == 0 && ((uintptr_t)scores % 16) == 0) : ((w % 16) == 0 && ((uintptr_t)img % 16) == 0);
+  static unsigned long long attr[2] = {0, 0};
+  if (first_use_on_device(&attr[FILL])) {
+    VLS_CUDA(cudaFuncSetAttribute(cc_t_label<FILL, BTH, BTW, CC_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)cc_tile_smem<BTH, BTW>()));
+  }
   // The labelling kernel is latency / issue bound and the final pass store bound, so a large batch is cut into slices
   // of work (two from 8 images on); odd slices run on a forked stream, so one slice's output pass
   // (store bound) overlaps the next slice's labelling (latency / issue bound).
@@ -875,10 +900,16 @@ int run(const void* img, float* scores, int n, int h, int w, int32_t* labels, in
     int32_t* a_h = area + nblk1 * i0;
     int2* l_h = list + list_per_image * i0;
     const long long list_cap = (long long)cnt * list_per_image;
-    VLS_CUDA(launch_k(cc_t_label<FILL>, dim3(tiles_x, tiles_y, cnt), dim3(T_THREADS), 0, st, img_h, sc_h, h, w, vec, f_h, a_h,
-                      list_count + sl, l_h));
-    const long long border = (long long)tiles_x * tiles_y * 4 * 32;   // four warps per tile
-    VLS_CUDA(launch_k(cc_t_border, dim3((unsigned)((border + 255) / 256), 1, cnt), dim3(256), 0, st, h, w, f_h));
+    const long long border = (long long)tiles_x * tiles_y * (tw / 32 + 2 * (th / 32)) * 32;   // one warp per edge piece
+    if (big) {
+      VLS_CUDA(launch_k(cc_t_label<FILL, BTH, BTW, CC_THREADS>, dim3(tiles_x, tiles_y, cnt), dim3(CC_THREADS), cc_tile_smem<BTH, BTW>(),
+                        st, img_h, sc_h, h, w, vec, f_h, a_h, list_count + sl, l_h));
+      VLS_CUDA(launch_k(cc_t_border<BTH, BTW>, dim3((unsigned)((border + 255) / 256), 1, cnt), dim3(256), 0, st, h, w, f_h));
+    } else {
+      VLS_CUDA(launch_k(cc_t_label<FILL, TBH, TBW, T_THREADS>, dim3(tiles_x, tiles_y, cnt), dim3(T_THREADS), cc_tile_smem<TBH, TBW>(),
+                        st, img_h, sc_h, h, w, vec, f_h, a_h, list_count + sl, l_h));
+      VLS_CUDA(launch_k(cc_t_border<TBH, TBW>, dim3((unsigned)((border + 255) / 256), 1, cnt), dim3(256), 0, st, h, w, f_h));
+    }
     VLS_CUDA(launch_k(cc_t_areas, dim3((unsigned)((list_cap + 255) / 256)), dim3(256), 0, st, h, w, f_h, a_h, list_count + sl, l_h));
     dim3 blk(128, 1, 1), grd((BW + 127) / 128, BH, cnt);
     VLS_CUDA(launch_k(cc_t_final<FILL>, grd, blk, 0, st, h, w, f_h, a_h, FILL ? nullptr : labels + px0, FILL ? nullptr : counts + px0,
