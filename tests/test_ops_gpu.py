@@ -232,6 +232,28 @@ def _blobby(n, h, w, seed, thr=0.0):
     return (z + 0.15 * torch.randn(n, 1, h, w, generator=g)) > thr
 
 
+def test_cc_lockfree_unions_stress(dev):
+    """The union phase is lock-free; a wrong protocol shows up as ONE split component in one launch out of ~50 (found in
+    r2: linking roots with atomicMin instead of compare-and-swap lets a path leave its set for a moment, and a concurrent
+    path compression then cuts a link of the neighbouring set).  Many launches on mask-like inputs, with the L2 disturbed
+    in between, compared on the device against the C oracle."""
+    from oracle import cc as cc_oracle
+    from video_llava_seg_b200.utils.misc import get_connected_components
+
+    junk = torch.empty(64 << 20, dtype=torch.uint8, device=dev)
+    for shape, seed, iters in (((32, 1, 256, 256), 256, 150), ((2, 1, 512, 768), 11, 40)):
+        m = _blobby(shape[0], shape[2], shape[3], seed)
+        rl, rc = cc_oracle.cc_label(m)
+        md, rld, rcd = m.to(dev), rl.to(dev), rc.to(dev)
+        bad = torch.zeros((), dtype=torch.int64, device=dev)
+        for it in range(iters):
+            if it % 3 == 0:
+                junk.zero_()
+            labels, counts = get_connected_components(md)
+            bad += (labels != rld).sum() + (counts != rcd).sum()
+        assert int(bad.item()) == 0, f"{shape}: {int(bad.item())} wrong pixels over {iters} launches"
+
+
 @pytest.mark.parametrize("shape", [(32, 1, 256, 256), (6, 1, 32, 1024), (5, 1, 1024, 32), (3, 1, 128, 512), (2, 1, 48, 80)])
 def test_cc_blobby_large_components(dev, shape):
     """Mask-like inputs (few large components with ragged borders + speckle): long union-find chains, many
