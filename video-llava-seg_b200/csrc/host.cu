@@ -1,4 +1,5 @@
 #include "host.h"
+#include <algorithm>
 
 #include <cudaTypedefs.h>
 
@@ -89,6 +90,7 @@ int prof_collect(int slot, int* count, double* total_ms) {
 struct Fork {
   cudaStream_t side = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_step[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 bool overlap_enabled() {
   static const bool on = !(getenv("VLS_NO_SIDE_STREAM") && getenv("VLS_NO_SIDE_STREAM")[0] == '1');
@@ -102,7 +104,16 @@ int fork_get(int idx, Fork** out) {
   VLS_REQUIRE(dev >= 0 && dev < 16, "device index %d out of range", dev);
   Fork& f = forks[dev][idx];
   if (!f.side) {
-    VLS_CUDA(cudaStreamCreateWithFlags(&f.side, cudaStreamNonBlocking));
+    // Fork 2 (self-attention value projection) sits on the frame's critical path: its stream gets the high priority the frame
+    // graph's main chain is captured with (graphed.py), the other forks (0: memory K projections = 450 CTAs per layer, 1: decoder
+    // helpers, 3: hole filling / output stage, 4: object-pointer MLP) the default, lowest one.  With every fork at the
+    // default priority the value projection of layer 0 queued behind the K projection's CTAs and the first self-attention
+    // started ~26 us late (warm timeline: 68 us into the frame instead of ~43); fork 1 at high priority let the image-side
+    // GEMM take the SMs the decoder's 8-CTA cluster kernels need (decoder +16 us).
+    int least = 0, greatest = 0;
+    VLS_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    const int prio = idx == 2 ? std::max(greatest, -1) : least;
+    VLS_CUDA(cudaStreamCreateWithPriority(&f.side, cudaStreamNonBlocking, prio));
     VLS_CUDA(cudaEventCreateWithFlags(&f.ev_fork, cudaEventDisableTiming));
     VLS_CUDA(cudaEventCreateWithFlags(&f.ev_join, cudaEventDisableTiming));
   }
@@ -118,6 +129,26 @@ int fork_begin(int idx, cudaStream_t main, cudaStream_t* side) {
   VLS_CUDA(cudaEventRecord(f->ev_fork, main));
   VLS_CUDA(cudaStreamWaitEvent(f->side, f->ev_fork, 0));
   *side = f->side;
+  return 0;
+}
+// milestones inside a forked chain: fork_mark records milestone k on the side stream, fork_wait makes `main` wait for it
+// (the memory K projections of the four layers run as one forked chain, and layer l only needs the l-th of them)
+int fork_mark(int idx, int k) {
+  if (!overlap_enabled()) return 0;
+  VLS_REQUIRE(k >= 0 && k < 8, "fork_mark: milestone %d out of range", k);
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  if (!f->ev_step[k]) VLS_CUDA(cudaEventCreateWithFlags(&f->ev_step[k], cudaEventDisableTiming));
+  VLS_CUDA(cudaEventRecord(f->ev_step[k], f->side));
+  return 0;
+}
+int fork_wait(int idx, int k, cudaStream_t main) {
+  if (!overlap_enabled()) return 0;
+  VLS_REQUIRE(k >= 0 && k < 8, "fork_wait: milestone %d out of range", k);
+  Fork* f;
+  VLS_TRY(fork_get(idx, &f));
+  VLS_REQUIRE(f->ev_step[k] != nullptr, "fork_wait: milestone %d was never marked", k);
+  VLS_CUDA(cudaStreamWaitEvent(main, f->ev_step[k], 0));
   return 0;
 }
 int fork_join(int idx, cudaStream_t main) {

@@ -64,6 +64,9 @@ inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, siz
 // independent side streams.
 int fork_begin(int idx, cudaStream_t main, cudaStream_t* side);
 int fork_join(int idx, cudaStream_t main);
+// milestones inside a forked chain: fork_mark(idx, k) records milestone k on the side stream, fork_wait makes `main` wait for it
+int fork_mark(int idx, int k);
+int fork_wait(int idx, int k, cudaStream_t main);
 
 // One-time per-DEVICE initialisation (cudaFuncSetAttribute is a per-device setting): returns true the first time it is
 // called with this flag word on the current device.  Thread-safe.

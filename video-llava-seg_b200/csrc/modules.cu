@@ -105,19 +105,37 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   // output projection at packing time (memory_attention.py:66-81, sam/transformer.py:311-360).
   // The K launch runs on a forked side stream (event fork/join, capturable into CUDA graphs) so that it overlaps layer
   // 0's LayerNorm -> q/k/v projection -> self-attention -> out-projection chain, whose kernels fill < 1 wave of SMs.
-  cudaStream_t side;
-  VLS_TRY(fork_begin(0, st, &side));
-  {
+  // One launch per layer with a milestone after each: layer l's cross-attention waits for ITS keys only.  Layer 0's keys are
+  // projected on the fork at once, layer l+1's when layer l's cross-attention has finished -- in the background of the layer
+  // tail and the next self-attention chain, whose kernels leave SMs idle.  (As one batched launch of L x B problems the first
+  // cross-attention waited for all four layers' keys: the 54 us of projection work and layer 0's self-attention chain, which
+  // needs the SMs as well, added up to ~104 us before it started; all four launched at the start slowed layer 0's kernels.)
+  const bool k_per_layer = L <= 8;
+  auto project_keys = [&](int l) -> int {     // l < 0: all layers in one launch
+    cudaStream_t side;
+    VLS_TRY(fork_begin(0, st, &side));
     GemmArgs k;
     k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
-    k.W = w->ca_k_w_all; k.ldw = CM; k.w_bstride = (long long)C * CM; k.w_batches = L; k.w_div = B;
-    k.M = Nk; k.N = C; k.K = CM; k.batch = L * B;
-    k.bias = w->ca_k_b_all; k.bias_mode = 1; k.bias_bstride = C; k.bias_batches = L; k.bias_div = B;
+    k.ldw = CM; k.w_bstride = (long long)C * CM; k.w_div = B;
+    k.M = Nk; k.N = C; k.K = CM;
+    k.bias_mode = 1; k.bias_bstride = C; k.bias_div = B;
     k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
-    k.C = kc_all; k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
+    k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
+    if (l >= 0) {
+      k.W = static_cast<const char*>(w->ca_k_w_all) + (size_t)l * C * CM * 2; k.w_batches = 1;
+      k.bias = w->ca_k_b_all + (size_t)l * C; k.bias_batches = 1;
+      k.C = kc_all + (size_t)l * B * Nk * C * 2; k.batch = B;
+    } else {
+      k.W = w->ca_k_w_all; k.w_batches = L;
+      k.bias = w->ca_k_b_all; k.bias_batches = L;
+      k.C = kc_all; k.batch = L * B;
+    }
     VLS_TRY(launch_gemm(k, side));
-    if (!g_attn_v_rows) VLS_TRY(launch_transpose_rows64(mem, B, Nk, memT, ldv, side));
-  }
+    if (l <= 0 && !g_attn_v_rows) VLS_TRY(launch_transpose_rows64(mem, B, Nk, memT, ldv, side));
+    if (l >= 0) VLS_TRY(fork_mark(0, l));
+    return 0;
+  };
+  VLS_TRY(project_keys(k_per_layer ? 0 : -1));
   bool joined = false;
 
   // dv = 256: V^T [256][ldvt]; dv = 64: the memory itself, as rows [Nk][64] (v_rows) or transposed [64][ldvt]
@@ -180,7 +198,9 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g, st));
     }
     }
-    if (!joined) {
+    if (k_per_layer) {
+      VLS_TRY(fork_wait(0, l, st));
+    } else if (!joined) {
       VLS_TRY(fork_join(0, st));
       joined = true;
     }
@@ -188,6 +208,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, mem, CM, (long long)Nk * CM, CM, 1, Nk, s_cross));
     else
       VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, memT, ldv, (long long)CM * ldv, CM, 0, Nk, s_cross));
+    if (k_per_layer && l + 1 < L) VLS_TRY(project_keys(l + 1));
     if (tail_fused) {
       // ---- the rest of the layer in ONE cluster kernel (ffn_fused.cu): folded out-projection + residual, LayerNorm3, FFN
       //      + residual, and the LayerNorm that follows (next layer's norm1, or the final norm straight into `out`)
