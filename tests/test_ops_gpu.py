@@ -333,7 +333,8 @@ def test_resize_binarize_matches_interpolate(dev, shape, size):
         assert torch.equal(bits.cpu(), torch.from_numpy(np.packbits(u8.cpu().numpy(), axis=-1)))
 
 
-@pytest.mark.parametrize("B,H,W,variant", [(1, 64, 64, 1), (2, 20, 12, 1), (24, 64, 64, 1), (24, 64, 64, 2), (24, 64, 64, 0),
+@pytest.mark.parametrize("B,H,W,variant", [(1, 64, 64, 1), (1, 64, 64, 3), (2, 20, 12, 1), (2, 20, 12, 3), (3, 7, 5, 1), (8, 64, 64, 1),
+                                             (24, 64, 64, 1), (24, 64, 64, 2), (24, 64, 64, 0),
                                              (40, 30, 22, 1), (40, 30, 22, 2), (40, 30, 22, 0), (64, 10, 66, 1)])
 def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W, variant):
     """CXBlock head (memory_encoder.py:86-93): depth-wise 7x7 conv (pad 3) + LayerNorm2d(eps 1e-6) on NHWC rows, f32 in,
@@ -342,11 +343,13 @@ def test_dwconv7_layernorm2d(dev, vls_lib, B, H, W, variant):
     exercise the halo / ragged strips / partial last row pieces of all of them."""
     from video_llava_seg_b200._lib import check, ptr, stream
 
-    check(vls_lib.vls_set_tuning(b"dwconv_tma", variant))
+    check(vls_lib.vls_set_tuning(b"dwconv_tma", 1 if variant == 3 else variant))
+    check(vls_lib.vls_set_tuning(b"dwconv_small", int(variant == 3)))     # 3: the one-CTA-per-8-pixels kernel of small batches (the default)
     try:
         _dwconv7_case(dev, vls_lib, B, H, W)
     finally:
         check(vls_lib.vls_set_tuning(b"dwconv_tma", 1))
+        check(vls_lib.vls_set_tuning(b"dwconv_small", 1))
 
 
 def _dwconv7_case(dev, vls_lib, B, H, W):

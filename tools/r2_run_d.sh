@@ -1,6 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -m gpu -q -x -k "ffn_fused" --no-header -p no:cacheprovider 2>&1 | tail -20 | tee gpurun_out/d_tests_ffn.log
-timeout 900 python -m pytest tests -m gpu -q -k "memory_attention or (propagation_matches and not b8_t20) or cuda_graph_steady" --no-header -p no:cacheprovider 2>&1 | tail -20 | tee gpurun_out/d_tests_parity.log
-timeout 300 python tools/timeline_frame.py > gpurun_out/d_timeline.txt 2>&1
-timeout 900 python bench.py --steps 40 --warmup 5 2>&1 | tail -5 | tee gpurun_out/d_bench.log
+timeout 600 python -m pytest tests -m gpu -x -q -k "dwconv7 or memory_encoder" --no-header -p no:cacheprovider 2>&1 | tail -3
+for v in 0 1; do echo "== dwconv_small=$v"; VLS_TUNING="dwconv_small=$v" timeout 600 python bench.py --no-cpu-baseline --no-pixels 2>gpurun_out/d_bench.err | tail -1 > gpurun_out/d_bench_$v.json
+python - $v <<'PY'
+import json,sys
+d=json.load(open(f'gpurun_out/d_bench_{sys.argv[1]}.json'))
+print({k:d.get(k) for k in ('value','ms_per_step','windows_ms_per_step')}, d['e2e']['value'])
+PY
+done

@@ -68,6 +68,10 @@ int vls_set_tuning(const char* key, int value) {
     g_mds3_tc = value != 0;
     return 0;
   }
+  if (std::string(key) == "dwconv_small") {   // CXBlock depth-wise 7x7 at small batches: 1 = per-row kernel, 0 = TMA strip kernel
+    g_dwconv_small = value != 0;
+    return 0;
+  }
   if (std::string(key) == "dwconv_tma") {   // CXBlock depth-wise 7x7 strip kernel: 1 = input rows staged by TMA, 0 = global loads
     g_dwconv_tma = value;   // 2: the variant capped at 128 registers (4 CTAs per SM)
     return 0;

@@ -151,6 +151,7 @@ int launch_ln256_small(const float* x, long long x_sr, int rows, const float* w,
 
 int launch_ln64_gelu(const float* x, long long rows, const float* w, const float* b, float eps, void* out, cudaStream_t stream);
 extern int g_mds3_tc;
+extern int g_dwconv_small; // 1 = small batches take the one-CTA-per-8-pixels kernel instead of the TMA strip kernel
 extern int g_dwconv_tma;   // depth-wise 7x7 strip kernel: 1 = input rows staged by TMA, 0 = the r1 kernel (global loads)
 int launch_build_tokens(const float* out_tokens, int n_out, const float* sparse, int Ns, int B, float* tok_a, float* tok_b,
                         cudaStream_t stream);

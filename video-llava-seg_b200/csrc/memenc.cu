@@ -9,6 +9,7 @@
 namespace vls {
 
 int g_dwconv_tma = 1;   // vls_set_tuning("dwconv_tma")
+int g_dwconv_small = 1; // vls_set_tuning("dwconv_small"): 1 = small batches take the one-CTA-per-8-pixels kernel (default), 0 = the strip kernel
 
 namespace {
 
@@ -666,11 +667,15 @@ dwconv7_ln_tma_kernel(const __grid_constant__ CUtensorMap tmX, int H, int W, int
 
 int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, const float* cb, const float* lnw,
                       const float* lnb, float eps, void* out, cudaStream_t stream) {
-  // few images: one CTA per 8 pixels of a row (512 CTAs at B=1, latency matters); many images: the FFMA2 column-strip
-  // kernels.  A strip is cut into n pieces of R = ceil(H / n) rows; every piece recomputes 6 halo rows and the grid runs in
-  // whole waves of 148 SMs x 3 CTAs, so n minimises (R + 6) / R x (waves rounded up / waves).
+  // Column-strip kernels (FFMA2): a strip of 4 pixel columns is cut into n pieces of R = ceil(H / n) rows; every piece
+  // recomputes 6 halo rows and the grid runs in whole waves of 148 SMs x 3 CTAs, so n minimises
+  // (R + 6) / R x (waves rounded up / waves): 2 pieces of 32 rows at B = 64, 16 pieces of 4 rows (256 CTAs) at B = 1.
+  // Few images (the production frame): one CTA per 8 pixels of a row (512 CTAs at B = 1); the strip kernel at B = 1
+  // (vls_set_tuning("dwconv_small", 0)) was measured at the same frame time (0.9437 vs 0.9431 ms), so the default stays.
   const long long strips = (long long)((W + DW_TX - 1) / DW_TX) * B;
-  if (strips * ((H + 15) / 16) < 1184) {
+  const int tma = g_dwconv_tma;
+  const bool tma_ok = tma && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  if (strips * ((H + 15) / 16) < 1184 && (g_dwconv_small || !tma_ok)) {
     VLS_CUDA(launch_k(dwconv7_ln_kernel, dim3((W + 7) / 8, H, B), dim3(256), 0, stream, x, H, W, wgt, cb, lnw, lnb, eps, reinterpret_cast<bf16*>(out)));
     VLS_POST_LAUNCH(1);
     return 0;
@@ -678,16 +683,15 @@ int launch_dwconv7_ln(const float* x, int B, int H, int W, const float* wgt, con
   int R = H;
   {
     double best = 1e30;
-    for (int n = 1; n <= 8; ++n) {
+    for (int n = 1; n <= 16; ++n) {
       const int r = (H + n - 1) / n;
-      if (r < 8) break;
+      if (r < 4) break;
       const double waves = (double)strips * ((H + r - 1) / r) / (148.0 * 3.0);
       const double cost = (r + 6.0) / r * ceil(waves) / waves;
       if (cost < best - 1e-9) best = cost, R = r;
     }
   }
-  const int tma = g_dwconv_tma;
-  if (tma && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if (tma_ok) {
     CUtensorMap tm;
     VLS_TRY(make_tmap_f32_nhwc(&tm, x, 256, W, H, B, DW_TX + 6, 2));
     static unsigned long long attr = 0;
