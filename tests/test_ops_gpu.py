@@ -369,7 +369,7 @@ def _dwconv7_case(dev, vls_lib, B, H, W):
     assert (out.float() - ref).abs().mean().item() < 3e-3
 
 
-@pytest.mark.parametrize("B,HW,n_mem,n_ptr,k", [(1, 4096, 7, 16, 4), (3, 64, 7, 16, 4), (2, 8, 3, 2, 4)])
+@pytest.mark.parametrize("B,HW,n_mem,n_ptr,k", [(1, 4096, 7, 16, 4), (3, 64, 7, 16, 4), (2, 8, 3, 2, 4), (2, 16, 4, 21, 4), (1, 8, 2, 17, 2)])
 def test_bank_shift_and_clone_many(dev, B, HW, n_mem, n_ptr, k):
     """Device memory bank: the one-launch in-place age shift equals the slice copies it replaces (exact, bf16 moves +
     one f32->bf16 rounding of the new pointer), and clone_many equals Tensor.clone()."""
