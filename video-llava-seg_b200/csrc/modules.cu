@@ -94,9 +94,12 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
   VLS_TRY(launch_axpy_rows(curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, 0.1f, B, Nq, C, x,
                            nullptr, st));
-  VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, st));
-  VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
-                           memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, st));
+  // The two memory-side conversions feed the K projection and the cross-attention only: they run on the K projection's fork
+  // (they were 8.7 us at the head of the main chain).  A bank that already is contiguous bf16 rows [B][Nk][64] -- the device
+  // bank of the graph path -- is attended over in place.
+  const bool mem_alias = mem_dtype == VLS_BF16 && mem_st == CM && (B == 1 || mem_sb == (long long)Nk * CM) &&
+                         (reinterpret_cast<uintptr_t>(memory) & 15) == 0;
+  const void* memr = mem_alias ? memory : mem;
 
   // memory K projections of ALL layers in one launch (they do not depend on x): batch index z = l*B + b.
   //   K_l = RoPE((mem + pos) Wk_l^T + bk_l)  (pointer tokens un-rotated)
@@ -114,6 +117,11 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   auto project_keys = [&](int l) -> int {     // l < 0: all layers in one launch
     cudaStream_t side;
     VLS_TRY(fork_begin(0, st, &side));
+    if (l <= 0) {
+      if (!mem_alias) VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, side));
+      VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
+                               memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, side));
+    }
     GemmArgs k;
     k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
     k.ldw = CM; k.w_bstride = (long long)C * CM; k.w_div = B;
@@ -131,7 +139,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       k.C = kc_all; k.batch = L * B;
     }
     VLS_TRY(launch_gemm(k, side));
-    if (l <= 0 && !g_attn_v_rows) VLS_TRY(launch_transpose_rows64(mem, B, Nk, memT, ldv, side));
+    if (l <= 0 && !g_attn_v_rows) VLS_TRY(launch_transpose_rows64(memr, B, Nk, memT, ldv, side));
     if (l >= 0) VLS_TRY(fork_mark(0, l));
     return 0;
   };
@@ -205,7 +213,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       joined = true;
     }
     if (g_attn_v_rows)
-      VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, mem, CM, (long long)Nk * CM, CM, 1, Nk, s_cross));
+      VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, memr, CM, (long long)Nk * CM, CM, 1, Nk, s_cross));
     else
       VLS_TRY(attention(kc_all + (size_t)l * B * Nk * C * 2, C, (long long)Nk * C, memT, ldv, (long long)CM * ldv, CM, 0, Nk, s_cross));
     if (k_per_layer && l + 1 < L) VLS_TRY(project_keys(l + 1));
