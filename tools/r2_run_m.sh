@@ -1,10 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 1500 python -m pytest tests -m gpu -q -x --no-header -p no:cacheprovider 2>&1 | tail -8 | tee gpurun_out/m_tests.log
-timeout 900 python bench.py --steps 40 --warmup 5 --no-cpu-baseline 2>gpurun_out/m_bench.err | tail -1 > gpurun_out/m_bench.json
-tail -5 gpurun_out/m_bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/m_bench.json'))
-print({k:d.get(k) for k in ('value','ms_per_step','windows_ms_per_step','e2e','e2e_from_pixels','whole_clip')})
-PY
+ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:'mds1|mds2|dwconv7_ln_kernel|axpy_rows|im2col|rows_to_nchw|chlast' -c 14 -o gpurun_out/r2_memenc_small -f python tools/profile_frame.py 1 > gpurun_out/m_ncu.log 2>&1; tail -2 gpurun_out/m_ncu.log
+python tools/ncu_full_summary.py gpurun_out/r2_memenc_small.ncu-rep > gpurun_out/r2_memenc_small_summary.txt
+grep -E "^==|duration|inst_executed.sum|issue_active|warps_active|long_scoreboard|registers|grid_size|dram__bytes_read" gpurun_out/r2_memenc_small_summary.txt

@@ -324,9 +324,13 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
 
   // tokens = [obj_score, iou, mask x4, sparse...] (mask_decoder.py:179-197); queries = tokens
   VLS_TRY(launch_build_tokens(w->out_tokens, 6, sparse, Ns, B, tokens0, queries, st));
-  // keys = image_embeddings (+ repeat) + dense, NCHW -> token rows (mask_decoder.py:200-205)
+  // keys = image_embeddings (+ repeat) + dense, NCHW -> token rows (mask_decoder.py:200-205).  With the cluster kernels the
+  // conversion runs on the fork that carries the image-side projection, next to the token chain (tokens -> self-attention).
+  const bool keys_on_fork = dec_tok_supported(Nt, T) && dec_img_supported(Nt, T);
+  cudaStream_t keys_stream = st;
+  if (keys_on_fork) VLS_TRY(fork_begin(1, st, &keys_stream));
   VLS_TRY(launch_nchw_to_rows(image_embeddings, emb_dtype, emb_strides, dense, dense_dtype, dense_strides, B, C, H, W, keys,
-                              keys_h, st));
+                              keys_h, keys_stream));
 
   auto tok_args = [&](const float* x, const float* xadd, int K, const void* Wt, const float* bias, int N, int act,
                       const float* res, float* out) {
@@ -375,8 +379,7 @@ int vls_mask_decoder_forward(const vls_mask_decoder_weights* w, const void* imag
     // ---- both layers as cluster kernels: token side (dec_tok.cu) and image side (dec_img.cu).  Only layer 0's image-side
     //      projection is a stand-alone GEMM (next to the token self-attention); every later one is produced by dec_img.
     {
-      cudaStream_t side;
-      VLS_TRY(fork_begin(1, st, &side));
+      cudaStream_t side = keys_stream;   // forked above, before the key conversion
       GemmArgs g = lin(keys_h, C, (long long)T * C, w->layers[0].img_w, T, 384, C, B, w->layers[0].img_b, kvq, 1, 384, (long long)T * 384);
       g.residual = w->layers[0].img_pe_add; g.ld_res = 384; g.res_bstride = 0;
       planes_out(g);

@@ -224,7 +224,10 @@ class SAM2Base(nn.Module):
             # no prompt on propagated frames: two `not_a_point` tokens + `no_mask` dense embedding are
             # weight constants (prompt_encoder.py:87-96,178-180) -- skip the per-frame prompt-encoder ops
             pe = self.sam_prompt_encoder
-            sparse = pe.not_a_point_embed.weight.reshape(1, 1, -1).expand(B, 2, -1)
+            cache = self._constants().setdefault("no_prompt_sparse", {})
+            if B not in cache:       # materialised once per weight set: expand().contiguous() was a 2 us copy kernel per frame
+                cache[B] = pe.not_a_point_embed.weight.detach().float().reshape(1, 1, -1).expand(B, 2, -1).contiguous()
+            sparse = cache[B]
             dense = pe.no_mask_embed.weight.reshape(1, -1, 1, 1).expand(B, -1, *pe.image_embedding_size)
         else:
             sparse, dense = self.sam_prompt_encoder(points=(coords, labels), boxes=None, masks=mask_prompt)
