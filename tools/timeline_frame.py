@@ -28,11 +28,9 @@ print("cuda events:", len(ev))
 # split into frames by large gaps
 t0 = ev[0].time_range.start
 rows = [(e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:60]) for e in ev]
-# take the 3rd frame: find graph boundaries by the axpy_rows kernel that starts memory attention
-starts = [i for i, r in enumerate(rows) if "axpy_rows" in r[2]]
-print("axpy indices", starts[:20])
-# frames begin at every 5th axpy? print the window between the 2nd-to-last and last frame start
-firsts = [i for k, i in enumerate(starts) if k % 5 == 0]
+# a frame's graph replay begins with the first axpy_rows kernel after the staging copies (multi_copy / memcpy) of the host loop
+firsts = [i for i, r in enumerate(rows) if "axpy_rows" in r[2] and i > 0 and ("multi_copy" in rows[i - 1][2] or "emcpy" in rows[i - 1][2])]
+print("frame starts", firsts[:8])
 a, b = firsts[-2], firsts[-1]
 base = rows[a][0]
 tot = 0.0
