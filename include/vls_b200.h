@@ -154,8 +154,9 @@ int vls_resize_bilinear(const float* in, int n, int h, int w, float* out, int H,
  * 2..n_ptr-1 <- 1..n_ptr-2, slot 1 <- new_ptr (f32 [B][tokens_per_ptr*64]).  Slot 0 of both (conditioning frame) stays. */
 int vls_bank_shift(void* bank, int B, int HW, int n_mem, int n_ptr, int tokens_per_ptr, const void* new_rows,
                    const float* new_ptr, vls_stream_t stream);
-/* n <= 8 device-to-device copies in one launch (src[i] -> dst[i], bytes[i] % 16 == 0, 16-byte aligned): the per-frame
- * snapshots of the outputs a replayed CUDA graph leaves in its static buffers. */
+/* n <= 8 device-to-device copies in one launch (src[i] -> dst[i]; in 16-byte vectors when size and addresses are multiples
+ * of 16, else -- at most 4096 bytes -- byte by byte): the per-frame snapshots of the outputs a replayed CUDA graph leaves
+ * in its static buffers. */
 int vls_multi_copy(const void* const* src, void* const* dst, const size_t* bytes, int n, vls_stream_t stream);
 
 /* Fused output stage: the same bilinear resize followed by `> thresh`, without materialising the f32 [H,W] logits

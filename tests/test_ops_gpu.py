@@ -390,6 +390,15 @@ def test_bank_shift_and_clone_many(dev, B, HW, n_mem, n_ptr, k):
     src = [rows, new_ptr, bank[:, :HW], torch.arange(5, device=dev), _rand((B, 1, 16, 16), dev, 24)]
     out = ops.clone_many(src)
     assert all(torch.equal(a, b) and a.data_ptr() != b.data_ptr() for a, b in zip(src, out))
+    # copy_many: small unaligned tensors (bytes) and pairs of equally laid out dense views (channel-last) share the launch
+    chl = _rand((1, 8, 8, 32), dev, 25).permute(0, 3, 1, 2)              # [1,32,8,8] view of NHWC memory
+    tiny, odd = _rand((B, 1), dev, 26), _rand((7,), dev, 27)[1:]          # 4*B bytes; a 4-byte aligned, 24-byte tensor
+    dsts = [torch.empty_like(chl), torch.empty_like(tiny), torch.empty_like(odd)]
+    assert dsts[0].stride() == chl.stride()
+    before = ops.lib().vls_launch_count()
+    ops.copy_many([chl, tiny, odd], dsts)
+    assert ops.lib().vls_launch_count() - before == 1, "one multi-copy launch, no fallback"
+    assert all(torch.equal(a, b) for a, b in zip([chl, tiny, odd], dsts))
 
 
 def test_cc_matches_reference_kernel(dev):

@@ -374,12 +374,15 @@ __global__ void bank_shift_kernel(bf16* __restrict__ bank, int B, int HW, int n_
   }
 }
 
-// up to 8 device-to-device copies in one launch (per-frame snapshots of the graph's static outputs)
+// up to 8 device-to-device copies in one launch (per-frame snapshots of the graph's static outputs).  A copy is done in
+// 16-byte vectors, or -- small tensors whose size / address is not a multiple of 16, e.g. the [B,1] object scores -- in
+// bytes (unit = 1): such a tensor used to fall back to a cudaMemcpy of its own between two graph replays.
 struct MultiCopy {
-  const uint4* src[8];
-  uint4* dst[8];
-  long long vecs[8];     // 16-byte vectors per copy
-  long long first[9];    // prefix sums of vecs
+  const char* src[8];
+  char* dst[8];
+  long long items[8];    // work items per copy: 16-byte vectors or bytes
+  int unit[8];           // 16 or 1
+  long long first[9];    // prefix sums of items
 };
 __global__ void multi_copy_kernel(const MultiCopy m, int n) {
   pdl_enter();
@@ -388,7 +391,9 @@ __global__ void multi_copy_kernel(const MultiCopy m, int n) {
   int c = 0;
 #pragma unroll
   for (int i = 1; i < 8; ++i) c += (i < n && id >= m.first[i]) ? 1 : 0;
-  m.dst[c][id - m.first[c]] = m.src[c][id - m.first[c]];
+  const long long k = id - m.first[c];
+  if (m.unit[c] == 16) reinterpret_cast<uint4*>(m.dst[c])[k] = reinterpret_cast<const uint4*>(m.src[c])[k];
+  else m.dst[c][k] = m.src[c][k];
 }
 
 }  // namespace
@@ -437,15 +442,17 @@ int launch_multi_copy(const void* const* src, void* const* dst, const size_t* by
   MultiCopy m;
   m.first[0] = 0;
   for (int i = 0; i < 8; ++i) {
-    m.src[i] = nullptr; m.dst[i] = nullptr; m.vecs[i] = 0;
+    m.src[i] = nullptr; m.dst[i] = nullptr; m.items[i] = 0; m.unit[i] = 16;
     if (i < n) {
-      VLS_REQUIRE(src[i] && dst[i] && bytes[i] % 16 == 0 && ((uintptr_t)src[i] % 16) == 0 && ((uintptr_t)dst[i] % 16) == 0,
-                  "multi_copy: copy %d must be 16-byte aligned and a multiple of 16 bytes", i);
-      m.src[i] = reinterpret_cast<const uint4*>(src[i]);
-      m.dst[i] = reinterpret_cast<uint4*>(dst[i]);
-      m.vecs[i] = (long long)(bytes[i] / 16);
+      VLS_REQUIRE(src[i] && dst[i], "multi_copy: copy %d has a null pointer", i);
+      const bool vec = bytes[i] % 16 == 0 && ((uintptr_t)src[i] % 16) == 0 && ((uintptr_t)dst[i] % 16) == 0;
+      VLS_REQUIRE(vec || bytes[i] <= 4096, "multi_copy: copy %d must be 16-byte aligned and a multiple of 16 bytes (or at most 4096 bytes)", i);
+      m.src[i] = reinterpret_cast<const char*>(src[i]);
+      m.dst[i] = reinterpret_cast<char*>(dst[i]);
+      m.unit[i] = vec ? 16 : 1;
+      m.items[i] = vec ? (long long)(bytes[i] / 16) : (long long)bytes[i];
     }
-    m.first[i + 1] = m.first[i] + m.vecs[i];
+    m.first[i + 1] = m.first[i] + m.items[i];
   }
   if (m.first[n] == 0) return 0;
   VLS_CUDA(launch_k(multi_copy_kernel, dim3((unsigned)((m.first[n] + 255) / 256)), dim3(256), 0, stream, m, n));

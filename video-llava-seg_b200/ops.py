@@ -134,16 +134,30 @@ def bank_shift(bank, hw, n_mem, n_ptr, tokens_per_ptr, new_rows, new_ptr):
                                stream()), "vls_bank_shift")
 
 
+def _same_dense_layout(a, b):
+    """Both tensors cover their memory without holes in the same (possibly permuted) order: a flat byte copy is dst.copy_(src)."""
+    if a.shape != b.shape or a.stride() != b.stride():
+        return False
+    expect = 1
+    for st, sz in sorted((st, sz) for st, sz in zip(a.stride(), a.shape) if sz > 1):
+        if st != expect:
+            return False
+        expect *= sz
+    return True
+
+
 def copy_many(srcs, dsts):
-    """dst.copy_(src) for every pair with ONE kernel launch per 8 pairs (vls_multi_copy) when both sides are contiguous
-    CUDA tensors of equal byte size that is a multiple of 16 (16-byte aligned); other pairs fall back to Tensor.copy_."""
+    """dst.copy_(src) for every pair with ONE kernel launch per 8 pairs (vls_multi_copy) when both sides are CUDA tensors of
+    one dtype with the same dense memory layout (contiguous, or e.g. both channel-last views) -- in 16-byte vectors, small
+    unaligned tensors (<= 4 KB) in bytes; other pairs fall back to Tensor.copy_ (a memcpy / kernel of their own)."""
     import ctypes
 
     fast = []
     for i, (a, b) in enumerate(zip(srcs, dsts)):
         nb = a.numel() * a.element_size()
-        if (a.is_cuda and b.is_cuda and a.is_contiguous() and b.is_contiguous() and a.dtype == b.dtype and nb > 0
-                and nb == b.numel() * b.element_size() and nb % 16 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0):
+        vec = nb % 16 == 0 and a.data_ptr() % 16 == 0 and b.data_ptr() % 16 == 0
+        if (a.is_cuda and b.is_cuda and a.dtype == b.dtype and nb > 0 and (vec or nb <= 4096)
+                and ((a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()) or _same_dense_layout(a, b))):
             fast.append(i)
         else:
             b.copy_(a)
