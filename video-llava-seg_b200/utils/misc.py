@@ -7,6 +7,21 @@ from .. import _lib
 from .._lib import check, lib, ptr, stream
 
 
+_WS = {}
+
+
+def _workspace(nbytes, device):
+    """Scratch buffer of the tiled path, kept per (device, stream) and grown on demand (r1 allocated one per call)."""
+    if torch.cuda.is_current_stream_capturing():      # a captured graph keeps its own allocation alive (private pool)
+        return torch.empty(max(nbytes, 1), device=device, dtype=torch.uint8)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < max(nbytes, 1):
+        ws = torch.empty(max(nbytes, 256), device=device, dtype=torch.uint8)
+        _WS[key] = ws
+    return ws
+
+
 def get_connected_components(mask):
     """(N,1,H,W) binary mask -> (labels int32, counts int32), 8-connectivity.
     Same contract as `sam2._C.get_connected_componnets` (connected_components.cu:213-282)."""
@@ -19,7 +34,7 @@ def get_connected_components(mask):
     labels = torch.empty((n, 1, h, w), device=m.device, dtype=torch.int32)
     counts = torch.empty((n, 1, h, w), device=m.device, dtype=torch.int32)
     nbytes = lib().vls_cc_workspace_bytes(n, h, w)
-    ws = torch.empty(max(nbytes, 1), device=m.device, dtype=torch.uint8)
+    ws = _workspace(nbytes, m.device)
     check(lib().vls_cc_label(ptr(m), n, h, w, ptr(labels), ptr(counts), ptr(ws), nbytes, stream()), "vls_cc_label")
     return labels, counts
 
@@ -34,7 +49,7 @@ def fill_holes_in_mask_scores(mask, max_area):
     n, c, h, w = out.shape
     assert c == 1
     nbytes = lib().vls_fill_holes_workspace_bytes(n, h, w)
-    ws = torch.empty(max(nbytes, 1), device=out.device, dtype=torch.uint8)
+    ws = _workspace(nbytes, out.device)
     check(lib().vls_fill_holes(ptr(out), n, h, w, int(max_area), 0.1, ptr(ws), nbytes, stream()), "vls_fill_holes")
     return out
 
