@@ -317,6 +317,9 @@ int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   // up to two waves of 128-wide tiles (M = 4096 projections): 64-wide tiles put 2-3 CTAs on every SM, so one CTA's
   // epilogue runs under the others' loads and MMAs (the q/k projection + RoPE: 14.9 -> see DESIGN)
   if (tiles128 < g_gemm_bn64_below || a.N <= 64) return launch_bn<64>(a, stream);
+  // (The memory K projection -- M = 28736, N = 256, K = 64 -- is 450 tiles on 148 SMs x 3 resident CTAs = 1.01 waves
+  // (ncu: launch__waves_per_multiprocessor), i.e. the time of two.  900 tiles of 128 x 64 at 4 CTAs per SM = 1.52 half-size
+  // waves were measured as well: the frame got 7 us SLOWER (0.9205 vs 0.913 ms, A/B on one box), so the rule stays.)
   return launch_bn<128>(a, stream);
 }
 
