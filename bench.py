@@ -272,6 +272,8 @@ def run_ours(args):
             gc.collect()
             gc.disable()          # a generation-2 collection inside a 2 ms step is host noise, not the path
             clocks.mark_start()
+            host_wait = 0.0                                  # seconds the host spent blocked on the device (debug)
+            t_loop = time.perf_counter()
             for i in range(n):
                 flush.zero_()
                 starts[i].record()
@@ -282,8 +284,11 @@ def run_ours(args):
                     main.wait_event(done[(i - 1) % 2])       # ... and the previous step's read-back ends inside this step
                 stops[i].record()
                 if d2h and i > 0:
+                    t_w = time.perf_counter()
                     done[(i - 1) % 2].synchronize()          # consume step i-1's mask on the host
+                    host_wait += time.perf_counter() - t_w
                     checksum += int(host[(i - 1) % 2][0, 0, 0, 0])
+            t_loop = time.perf_counter() - t_loop
             torch.cuda.synchronize()
             clocks.mark_stop()
             gc.enable()
@@ -292,6 +297,8 @@ def run_ours(args):
         per_step = [s.elapsed_time(e) for s, e in zip(starts, stops)]
         if os.environ.get("VLS_BENCH_DEBUG"):
             print(f"[bench debug] d2h={d2h} per-step ms: {[round(x, 3) for x in per_step]}", file=sys.stderr, flush=True)
+            print(f"[bench debug] d2h={d2h} host: {1e3 * t_loop / n:.3f} ms per iteration enqueued, of which "
+                  f"{1e3 * host_wait / n:.3f} ms blocked on the device", file=sys.stderr, flush=True)
         if world > 1:
             dist.barrier()
         windows = []

@@ -224,6 +224,21 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
                          int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
                          int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
                          void* workspace, size_t workspace_bytes, vls_stream_t stream);
+/* The same call in two halves, for callers that software-pipeline consecutive frames (the reference runs
+ * MemoryAttention.forward, memory_attention.py:119-169, as one call per frame; nothing in it before layer 0's
+ * cross-attention, :66-81, reads the memory):
+ *   phase 1 (head): x = curr + 0.1 curr_pos, layer 0's norm1 / self-attention / norm2 / cross-attention query projection;
+ *                   x and the rotated queries stay in `workspace`; memory, memory_pos and out are not touched (may be NULL)
+ *   phase 2 (rest): everything from layer 0's key projection and cross-attention on, for the head that was run LAST on the
+ *                   same workspace with the same B, Nq, Nk; curr / curr_pos are not read (may be NULL)
+ *   phase 0       : both, = vls_mem_attn_forward.
+ * Head + rest launch exactly the kernels of the whole call, in the same order per stream: results are bit-identical. */
+int vls_mem_attn_forward_phase(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+                               long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
+                               const void* memory, int mem_dtype, long long mem_st, long long mem_sb,
+                               const void* memory_pos, int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq,
+                               int Nk, int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
+                               void* workspace, size_t workspace_bytes, vls_stream_t stream, int phase);
 
 /* Mask decoder (sam/mask_decoder.py:110-245 + sam/transformer.py:90-286). */
 typedef struct vls_attn_w {

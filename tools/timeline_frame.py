@@ -9,11 +9,13 @@ from video_llava_seg_b200.features import FeatureClip
 dev = torch.device("cuda:0")
 predictor = build_sam.build_sam2_video_predictor(None, synth.init_state_dict(0), dev)
 T = 30
+B = int(os.environ.get("VLS_TL_OBJECTS", "1"))     # objects tracked jointly (BASELINE configs[2]: 8)
 clip = synth.SyntheticClip(100, T)
 frames = [clip.frame(t, 1) for t in range(T)]
 src = FeatureClip(lambda t: frames[t], T, resident_device=dev)
 state = predictor.init_state(src)
-predictor.add_new_points_or_box(state, 0, 1, points=clip.point_prompt(1)["point_coords"][0].tolist(), labels=[1])
+for o, pt in enumerate(clip.point_prompt(B)["point_coords"]):
+    predictor.add_new_points_or_box(state, 0, o + 1, points=pt.tolist(), labels=[1])
 gen = predictor.propagate_in_video(state)
 for _ in range(22):
     next(gen)

@@ -56,6 +56,10 @@ int vls_set_tuning(const char* key, int value) {
     g_gemm_bn64_below = value;
     return 0;
   }
+  if (std::string(key) == "mem_attn_head_short") {   // pipelined frames: head = projections only (1) or through the query projection (0)
+    g_mem_attn_head_short = value != 0;
+    return 0;
+  }
   if (std::string(key) == "mid_fused") {   // memory attention: self-attn out-proj + LN2 + cross-attn q-proj as one launch
     g_mid_fused = value != 0;
     return 0;

@@ -55,14 +55,28 @@ static size_t mem_attn_ws(int B, int Nq, int Nk, int L) {
 
 size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) { return mem_attn_ws(B, Nq, Nk, 8); }
 
-int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+}  // extern "C"
+// vls_set_tuning("mem_attn_head_short"): 1 = the head (phase 1) ends after layer 0's q/k/v projections, and the self-attention
+// + out-projection / LayerNorm2 / query projection open the rest next to the key projection; 0 = the head runs through the
+// cross-attention query projection (default).  Measured (A/B on one box, frame ms): no pipelining 0.911, full head 0.894, short
+// head 0.920 -- with the short head the self-attention (128 CTAs, high-priority chain) opens the frame and the key projection
+// on its fork only gets SMs ~17 us later, so the first cross-attention starts 54 us into the frame instead of 33.
+namespace vls { int g_mem_attn_head_short = 0; }
+extern "C" {
+// phase 0: the whole stack.  phase 1 (HEAD): only what depends on `curr` alone -- x = curr + 0.1 pos, layer 0's LayerNorm1,
+// q/k/v projections, self-attention, out-projection + LayerNorm2 + cross-attention query projection -- leaving x and the
+// rotated queries in the workspace.  phase 2 (REST): everything else, starting at layer 0's memory K projection and
+// cross-attention, on a workspace whose head has been run.  The graph path runs frame t+1's head next to frame t's mask
+// decoder and memory encoder (graphed.py), so a frame starts at its first cross-attention.
+static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
                          long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
                          const void* memory, int mem_dtype, long long mem_st, long long mem_sb, const void* memory_pos,
                          int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
                          int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
-                         void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+                         void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase) {
   cudaStream_t st = (cudaStream_t)stream_;
-  VLS_REQUIRE(w && curr && memory && out, "mem_attn: null argument");
+  VLS_REQUIRE(phase >= 0 && phase <= 2, "mem_attn: phase must be 0 (whole), 1 (head) or 2 (rest)");
+  VLS_REQUIRE(w && (curr || phase == 2) && (memory || phase == 1) && (out || phase == 1), "mem_attn: null argument");
   VLS_REQUIRE(w->num_layers >= 1 && w->num_layers <= 8, "mem_attn: num_layers out of range");
   VLS_REQUIRE(B >= 1 && Nq >= 1 && Nk >= 1, "mem_attn: bad shape");
   VLS_REQUIRE(num_obj_ptr_tokens >= 0 && num_obj_ptr_tokens <= Nk, "mem_attn: bad num_obj_ptr_tokens");
@@ -92,8 +106,9 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
               "mem_attn: workspace carve failed");
 
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
-  VLS_TRY(launch_axpy_rows(curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, 0.1f, B, Nq, C, x,
-                           nullptr, st));
+  if (phase != 2)
+    VLS_TRY(launch_axpy_rows(curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, 0.1f, B, Nq, C, x,
+                             nullptr, st));
   // The two memory-side conversions feed the K projection and the cross-attention only: they run on the K projection's fork
   // (they were 8.7 us at the head of the main chain).  A bank that already is contiguous bf16 rows [B][Nk][64] -- the device
   // bank of the graph path -- is attended over in place.
@@ -143,7 +158,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
     if (l >= 0) VLS_TRY(fork_mark(0, l));
     return 0;
   };
-  VLS_TRY(project_keys(k_per_layer ? 0 : -1));
+  if (phase != 1) VLS_TRY(project_keys(k_per_layer ? 0 : -1));
   bool joined = false;
 
   // dv = 256: V^T [256][ldvt]; dv = 64: the memory itself, as rows [Nk][64] (v_rows) or transposed [64][ldvt]
@@ -167,6 +182,8 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   for (int l = 0; l < L; ++l) {
     const vls_mem_attn_layer& Lw = w->layers[l];
     // ---- self attention (memory_attention.py:58-64): q = k = v = LN1(x); RoPE on q and k
+    const bool first_rest = phase == 2 && l == 0;   // phase 2: layer 0's chain up to the head's end was run ahead
+    if (!first_rest) {
     if (!have_t) VLS_TRY(launch_ln256(x, B, Nq, Lw.n1_w, Lw.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.sa_qk_w, Nq, 2 * C, C, B, Lw.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
@@ -183,6 +200,9 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g, st));
       VLS_TRY(fork_join(2, st));
     }
+    }
+    if (phase == 1 && g_mem_attn_head_short) return 0;   // short head: the projections only (kernels of < 10 us)
+    if (!(first_rest && !g_mem_attn_head_short)) {
     VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, (long long)C * ldvs, C, 0, Nq, s_self));
     if (g_mid_fused) {
       // ---- self-attention output projection + residual, LayerNorm2 and the cross-attention query projection (+ RoPE) in
@@ -206,6 +226,8 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
       VLS_TRY(launch_gemm(g, st));
     }
     }
+    }
+    if (phase == 1) return 0;
     if (k_per_layer) {
       VLS_TRY(fork_wait(0, l, st));
     } else if (!joined) {
@@ -260,6 +282,28 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
   if (out_dtype == VLS_BF16)
     return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, nullptr, 0, 0, out, out_sb, out_st, st);
   return launch_ln256(x, B, Nq, w->norm_w, w->norm_b, LN_EPS, 0, (float*)out, out_sb, out_st, nullptr, 0, 0, st);
+}
+
+int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+                         long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
+                         const void* memory, int mem_dtype, long long mem_st, long long mem_sb, const void* memory_pos,
+                         int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
+                         int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
+                         void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
+  return mem_attn_forward_impl(w, curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, memory, mem_dtype,
+                               mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb, B, Nq, Nk, num_obj_ptr_tokens, out,
+                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, 0);
+}
+
+int vls_mem_attn_forward_phase(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
+                               long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
+                               const void* memory, int mem_dtype, long long mem_st, long long mem_sb,
+                               const void* memory_pos, int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq,
+                               int Nk, int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
+                               void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase) {
+  return mem_attn_forward_impl(w, curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, memory, mem_dtype,
+                               mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb, B, Nq, Nk, num_obj_ptr_tokens, out,
+                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, phase);
 }
 
 // ================================================================== mask decoder

@@ -6,9 +6,12 @@ import torch
 class FeatureClip:
     """Wraps `frame(t) -> {"vision_feat" [HW,1,256], "vision_pos" [HW,1,256], "feat_s0" [1,32,4H,4W],
     "feat_s1" [1,64,2H,2W]}` (e.g. synth.SyntheticClip.frame).  With `pinned=True` frames are staged in pinned
-    host memory and copied to the device inside `frame_features`, double-buffered on a copy stream so that frame
+    host memory and copied to the device inside `frame_features`, on a copy stream with three staging sets so that frame
     t+1 crosses PCIe while frame t is tracked (the end-to-end path of bench.py); otherwise they are uploaded once
-    and stay resident in HBM."""
+    and stay resident in HBM.  Three sets, not two: the pipelined graph path (graphed.py) asks for frame t+1 while it still
+    reads frame t's high-resolution features, so a set is only recycled two requests after its own."""
+
+    SETS = 3
 
     def __init__(self, frame_fn, num_frames, video_height=1024, video_width=1024, feat=64, resident_device=None,
                  pinned=False, period=None):
@@ -36,13 +39,13 @@ class FeatureClip:
             self.h2d_bytes_per_frame = sum(v.numel() * v.element_size() for v in self._frames[0].values())
 
     def _issue_h2d(self, t, device):
-        """Enqueue the host->device copy of frame t on the copy stream into staging set t % 2."""
+        """Enqueue the host->device copy of frame t on the copy stream into staging set t % SETS."""
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=device)
-            self._staging = [None, None]
-            self._ready = [None, None]
-            self._consumed = [None, None]
-        s = t % 2
+            self._staging = [None] * self.SETS
+            self._ready = [None] * self.SETS
+            self._consumed = [None] * self.SETS
+        s = t % self.SETS
         src = self._frames[t % self._period]
         if self._staging[s] is None:
             self._staging[s] = {k: torch.empty(v.shape, dtype=v.dtype, device=device) for k, v in src.items()}
@@ -58,19 +61,20 @@ class FeatureClip:
 
     def frame_features(self, t, device):
         if self._pinned:
-            # double-buffered prefetch: frame t+1 crosses PCIe on a copy stream while frame t is being tracked
+            # prefetch: frame t+1 crosses PCIe on a copy stream while frame t is being tracked
             main = torch.cuda.current_stream(device)
-            if self._copy_stream is None or self._ready[t % 2] is None or self._ready[t % 2][0] != t:
+            cur = t % self.SETS
+            if self._copy_stream is None or self._ready[cur] is None or self._ready[cur][0] != t:
                 self._issue_h2d(t, device)
-            prev = (t - 1) % 2
-            if self._consumed is not None and self._staging[prev] is not None:
+            old = (t - 2) % self.SETS                    # = the set frame t+1 is about to land in
+            if self._consumed is not None and self._staging[old] is not None:
                 ev = torch.cuda.Event()
-                ev.record(main)                          # everything that read the other set has been enqueued by now
-                self._consumed[prev] = ev
-            main.wait_event(self._ready[t % 2][1])
+                ev.record(main)                          # everything that read frame t-2's set has been enqueued by now
+                self._consumed[old] = ev
+            main.wait_event(self._ready[cur][1])
             if t + 1 < self.num_frames:
                 self._issue_h2d(t + 1, device)
-            d = dict(self._staging[t % 2])
+            d = dict(self._staging[cur])
         else:
             d = {k: v.to(device, non_blocking=True) for k, v in self._frames[t % self._period].items()}
         if self._pos.device != torch.device(device):

@@ -36,15 +36,30 @@ from .modeling.sam2_utils import get_1d_sine_pe
 from .utils.misc import fill_holes_in_mask_scores
 
 
-def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw, side_stream):
+def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw, side_stream, head=None):
     """memory attention -> mask decoder -> SAM-heads glue -> {hole filling + output stage || memory encoder} of one
-    tracked frame on static buffers: what both kinds of captured graph replay."""
+    tracked frame on static buffers: what both kinds of captured graph replay.
+    head = (next frame's features, stream): software-pipelined frames.  This frame's memory attention starts at layer 0's
+    cross-attention (its head -- everything that depends on the frame's features alone -- was run ahead), and the NEXT
+    frame's head runs on `stream` next to this frame's mask decoder and memory encoder, whose small kernels leave most
+    SMs idle.  Same kernels, same operands, same order per buffer: results are bit-identical to the unpipelined frame."""
     dev = in_feat.device
     s = m.sam_image_embedding_size
+    main = torch.cuda.current_stream(dev)
     vf = in_feat.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
     vp = in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
-    pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=mem.transpose(0, 1),
-                             memory_pos=pos[None].expand(B, -1, -1).transpose(0, 1), num_obj_ptr_tokens=n_ptr_tokens)
+    mem_t, pos_t = mem.transpose(0, 1), pos[None].expand(B, -1, -1).transpose(0, 1)
+    pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=mem_t, memory_pos=pos_t, num_obj_ptr_tokens=n_ptr_tokens,
+                             phase=0 if head is None else 2)
+    if head is not None:
+        # right behind this frame's stack: measured against starting it after the mask decoder (0.912 vs 0.900 ms per frame --
+        # it then collides with the memory encoder's full-width kernels) and against a head that stops before the
+        # self-attention (0.920: see g_mem_attn_head_short in csrc/modules.cu)
+        nxt, head_stream = head
+        head_stream.wait_stream(main)      # the module's workspace is free again once this frame's stack has run
+        with torch.cuda.stream(head_stream):
+            m.memory_attention(curr=[nxt.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)], curr_pos=[vp], memory=mem_t,
+                               memory_pos=pos_t, num_obj_ptr_tokens=n_ptr_tokens, phase=1)
     pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
     high = [in_s0.expand(B, -1, -1, -1), in_s1.expand(B, -1, -1, -1)]
     _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
@@ -52,7 +67,6 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
         defer_obj_ptr=True)        # obj_ptr MLP on a forked stream, joined below: nothing before the bank update needs it
     # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
     # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
-    main = torch.cuda.current_stream(dev)
     side = side_stream if os.environ.get("VLS_NO_SIDE_STREAM", "0") != "1" else main
     side.wait_stream(main)
     with torch.cuda.stream(side):
@@ -61,7 +75,15 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     nchw, rows, _ = m._encode_new_memory_low_res([vf], low, obj_logits, False)
     _lib.check(_lib.lib().vls_sam_heads_join(_lib.stream()), "vls_sam_heads_join")
     main.wait_stream(side)
+    if head is not None:
+        main.wait_stream(head[1])
     return pred, obj_ptr, obj_logits, nchw, rows, video
+
+
+def pipelined_frames(m):
+    """Software pipelining of consecutive steady-state frames (see _frame_body); `predictor.pipeline_frames = False` or
+    VLS_NO_PIPELINE=1 turn it off."""
+    return bool(getattr(m, "pipeline_frames", True)) and os.environ.get("VLS_NO_PIPELINE", "0") != "1"
 
 
 def baked_settings(m):
@@ -69,7 +91,8 @@ def baked_settings(m):
     every frame, so a capture is only valid (and only shared between sessions) while they are unchanged."""
     return (m.output_mode, m.fill_hole_area, float(m.sigmoid_scale_for_mem_enc), float(m.sigmoid_bias_for_mem_enc),
             bool(m._use_multimask(False, None)), bool(m.use_multimask_token_for_obj_ptr),
-            m.no_obj_embed_spatial is not None, bool(m.non_overlap_masks), bool(m.non_overlap_masks_for_mem_enc))
+            m.no_obj_embed_spatial is not None, bool(m.non_overlap_masks), bool(m.non_overlap_masks_for_mem_enc),
+            pipelined_frames(m))
 
 
 def _signature_objects(m):
@@ -132,6 +155,7 @@ class FrameGraph:
         if self.graph is None:
             self._capture()
         self.graph.replay()
+        self.model.memory_attention.ws_epoch += 1      # the replay ran on the module's workspace
         _lib.lib().vls_launch_count_add(self.launches_per_replay)
         pred, obj_ptr, obj_logits, nchw, rows, video = ops.clone_many(list(self.outputs))
         return pred, obj_ptr, obj_logits, nchw, rows, video
@@ -158,6 +182,8 @@ class SteadyStateGraph:
         self.graph = None
         self.next_frame = None
         self._side = torch.cuda.Stream(device=self.dev)
+        self.pipelined = pipelined_frames(model)
+        self._head_stream = torch.cuda.Stream(device=self.dev)     # default (lowest) priority: the head fills idle SMs
         self._build_static(state, frame_idx)
 
     # ------------------------------------------------------------------ eligibility
@@ -196,6 +222,7 @@ class SteadyStateGraph:
         fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
         self.in_s0, self.in_s1, self.in_feat = (torch.empty_like(x) for x in fpn[-3:])
         self.in_pos = torch.empty_like(pe[-1])
+        self.in_feat_next = torch.empty_like(self.in_feat)     # pipelined: the features the next frame's head runs on
         self._fill_static(state, frame_idx)
 
     def _fill_static(self, state, frame_idx):
@@ -226,6 +253,7 @@ class SteadyStateGraph:
         for d in range(1, self.n_ptr):
             self.bank_pos[self.ptr_off + d * self.k: self.ptr_off + (d + 1) * self.k] = self.ptr_pos_table[d]
         self._pos_src = None
+        self._head_frame, self._head_epoch, self._lookahead = None, -1, None   # no head has been run ahead for this clip
         self._arena, self._arena_pos, self._arena_len = None, 0, 0      # retained outputs of the previous clip stay with that clip
         self.next_frame = frame_idx
 
@@ -259,11 +287,25 @@ class SteadyStateGraph:
         self._owner = weakref.ref(owner)
         self._fill_static(state, frame_idx)
 
-    def _load_inputs(self, state, frame_idx):
-        _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx, 1)
-        fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
+    def _load_inputs(self, state, frame_idx, load_feat=True):
+        """Stage the frame's inputs.  Pipelined: the frame's own low-resolution features are already in `in_feat` (the
+        previous replay moved them there) unless load_feat, and the NEXT frame's are fetched one frame ahead for its head."""
+        if self._lookahead is not None and self._lookahead[0] == frame_idx:
+            fpn, pe = self._lookahead[1:]
+        else:
+            _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx, 1)
+            fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
         # one launch for all the staging copies (five Tensor.copy_ calls were ~20 us of launch gaps per frame)
-        srcs, dsts = [fpn[-3], fpn[-2], fpn[-1]], [self.in_s0, self.in_s1, self.in_feat]
+        srcs, dsts = [fpn[-3], fpn[-2]], [self.in_s0, self.in_s1]
+        if load_feat:
+            srcs.append(fpn[-1])
+            dsts.append(self.in_feat)
+        self._lookahead = None
+        if self.pipelined and frame_idx + 1 < self.num_frames:
+            _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx + 1, 1)
+            self._lookahead = (frame_idx + 1, bo["backbone_fpn"], bo["vision_pos_enc"])
+            srcs.append(self._lookahead[1][-1])
+            dsts.append(self.in_feat_next)
         if self._pos_src is None or self._pos_src != (pe[-1].data_ptr(), pe[-1].shape):
             srcs.append(pe[-1])                            # the neck's sine encoding is normally one constant tensor
             dsts.append(self.in_pos)
@@ -277,13 +319,28 @@ class SteadyStateGraph:
     def _step(self):
         pred, obj_ptr, obj_logits, nchw, rows, video = _frame_body(
             self.model, self.B, self.in_feat, self.in_pos, self.in_s0, self.in_s1, self.bank_mem, self.bank_pos,
-            self.n_ptr * self.k, self.hw, self._side)
+            self.n_ptr * self.k, self.hw, self._side, (self.in_feat_next, self._head_stream) if self.pipelined else None)
+        if self.pipelined:
+            # the next frame's features become the current ones (memory encoder and head have both read theirs by now)
+            ops.copy_many([self.in_feat_next], [self.in_feat])
         # bank shift for the next frame (one launch, in place): memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
         ops.bank_shift(self.bank_mem, self.HW, self.n_mem, self.n_ptr, self.k, rows.contiguous(), obj_ptr.float().contiguous())
         return pred, obj_ptr, obj_logits, nchw, rows, video
 
+    def _run_head(self):
+        """Head of the frame whose features are in `in_feat`, eagerly: the first steady-state frame of a clip, and whenever
+        something else has used the memory-attention workspace since the head was run ahead."""
+        B = self.B
+        vf = self.in_feat.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+        vp = self.in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
+        self.model.memory_attention(curr=[vf], curr_pos=[vp], memory=self.bank_mem.transpose(0, 1),
+                                    memory_pos=self.bank_pos[None].expand(B, -1, -1).transpose(0, 1),
+                                    num_obj_ptr_tokens=self.n_ptr * self.k, phase=1)
+
     def _capture(self):
         keep = (self.bank_mem.clone(), self.bank_pos.clone())
+        if self.pipelined:
+            self._run_head()                                # the warm-up frames below start at a cross-attention
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream(self.dev))
         with torch.cuda.stream(side):
@@ -320,11 +377,20 @@ class SteadyStateGraph:
         """One propagated frame.  Returns the compact state entry and the video-resolution logits."""
         assert frame_idx == self.next_frame, "graphed propagation must advance frame by frame"
         assert self.owned_by(state.get("graph_owner")), "the captured graph (and its memory bank) belongs to another session"
-        self._load_inputs(state, frame_idx)
+        ma = self.model.memory_attention
+        need_head = self.pipelined and not (self._head_frame == frame_idx and self._head_epoch == ma.ws_epoch)
+        self._load_inputs(state, frame_idx, load_feat=need_head or not self.pipelined)
         if self.graph is None:
             self._capture()
             self._load_inputs(state, frame_idx)
+            need_head = self.pipelined
+        if need_head:
+            self._run_head()
         self.graph.replay()
+        ma.ws_epoch += 1                                    # the replay ran on the module's workspace
+        if self.pipelined:                                  # ... and left the next frame's head in it
+            self._head_frame = frame_idx + 1 if frame_idx + 1 < self.num_frames else None
+            self._head_epoch = ma.ws_epoch
         _lib.lib().vls_launch_count_add(self.launches_per_replay)
         pred, obj_ptr, obj_logits, nchw, rows, video = self.outputs
         self.next_frame = frame_idx + 1

@@ -44,14 +44,19 @@ class MemoryAttention(PackedModule):
         self.pos_enc_at_input = pos_enc_at_input
         self.batch_first = batch_first
         self._rope = {}
+        # bumped by everything that runs on the module's workspace (eager calls and graph replays): a head computed ahead of
+        # its frame (phase 1) is only valid while nobody else has used the workspace since
+        self.ws_epoch = 0
 
     def _apply(self, fn, *a, **kw):
         self._rope = {}
         return super()._apply(fn, *a, **kw)
 
-    def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0):
+    def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0, phase=0):
         """curr / curr_pos: [Nq,B,256] (or 1-element lists of it); memory / memory_pos: [Nk,B,64];
-        returns [Nq,B,256] in curr's dtype.  Same contract as memory_attention.py:119-169."""
+        returns [Nq,B,256] in curr's dtype.  Same contract as memory_attention.py:119-169.
+        phase (not in the reference): 1 = only the part that depends on `curr` alone (layer 0 up to its cross-attention
+        queries, left in the workspace; returns None), 2 = the rest for the head run last, 0 = both (vls_b200.h)."""
         if isinstance(curr, list):
             assert isinstance(curr_pos, list) and len(curr) == len(curr_pos) == 1
             curr, curr_pos = curr[0], curr_pos[0]
@@ -77,13 +82,14 @@ class MemoryAttention(PackedModule):
 
         cu, cpos = rows(curr), rows(curr_pos if self.pos_enc_at_input else None)
         me, mpos = rows(memory), rows(memory_pos)
-        out = torch.empty((nq, b, c), device=dev, dtype=curr.dtype)
+        out = torch.empty((nq, b, c), device=dev, dtype=curr.dtype) if phase != 1 else None
         nbytes = lib().vls_mem_attn_workspace_bytes(b, nq, nk)
         ws = self._workspace(nbytes, dev)
-        check(lib().vls_mem_attn_forward(
+        self.ws_epoch += 1
+        check(lib().vls_mem_attn_forward_phase(
             ctypes_ref(w), ptr(cu[0]), cu[1], cu[2], cu[3], ptr(cpos[0]), cpos[1], cpos[2], cpos[3],
             ptr(me[0]), me[1], me[2], me[3], ptr(mpos[0]), mpos[1], mpos[2], mpos[3], b, nq, nk,
-            int(num_obj_ptr_tokens), ptr(out), dtype_code(out), out.stride(0), out.stride(1), ptr(ws), ws.numel(),
-            stream()), "vls_mem_attn_forward")
+            int(num_obj_ptr_tokens), ptr(out), 0 if out is None else dtype_code(out), 0 if out is None else out.stride(0),
+            0 if out is None else out.stride(1), ptr(ws), ws.numel(), stream(), int(phase)), "vls_mem_attn_forward_phase")
         return out
 
