@@ -232,13 +232,19 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
  *   phase 2 (rest): everything from layer 0's key projection and cross-attention on, for the head that was run LAST on the
  *                   same workspace with the same B, Nq, Nk; curr / curr_pos are not read (may be NULL)
  *   phase 0       : both, = vls_mem_attn_forward.
- * Head + rest launch exactly the kernels of the whole call, in the same order per stream: results are bit-identical. */
+ * ahead_rows > 0 (a multiple of Nq, same value in both phases): the head also projects layer 0's keys of memory rows
+ * [0, ahead_rows) -- which requires memory / memory_pos in phase 1 -- and the rest only those of rows [ahead_rows, Nk).
+ * In phase 1 the memory rows of [ahead_shift_from, ahead_rows) are read ahead_shift rows further on: a caller whose bank is
+ * a sliding window calls the head BEFORE it shifts the window by ahead_shift rows (sam2_base.py:533-568: the six most recent
+ * memories move down one slot per frame, the conditioning memory stays).
+ * Head + rest compute exactly what the whole call computes, element by element: results are bit-identical. */
 int vls_mem_attn_forward_phase(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
                                long long curr_sb, const void* curr_pos, int pos_dtype, long long pos_st, long long pos_sb,
                                const void* memory, int mem_dtype, long long mem_st, long long mem_sb,
                                const void* memory_pos, int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq,
                                int Nk, int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
-                               void* workspace, size_t workspace_bytes, vls_stream_t stream, int phase);
+                               void* workspace, size_t workspace_bytes, vls_stream_t stream, int phase, int ahead_rows,
+                               int ahead_shift_from, int ahead_shift);
 
 /* Mask decoder (sam/mask_decoder.py:110-245 + sam/transformer.py:90-286). */
 typedef struct vls_attn_w {

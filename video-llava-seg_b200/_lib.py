@@ -109,7 +109,7 @@ def _declare_modules(lib):
                                          c_int, c_ll, c_ll, c_void_p, c_int, c_ll, c_ll, c_int, c_int, c_int, c_int,
                                          c_void_p, c_int, c_ll, c_ll, c_void_p, c_size_t, c_void_p]
     lib.vls_mem_attn_forward_phase.restype = c_int
-    lib.vls_mem_attn_forward_phase.argtypes = lib.vls_mem_attn_forward.argtypes + [c_int]
+    lib.vls_mem_attn_forward_phase.argtypes = lib.vls_mem_attn_forward.argtypes + [c_int, c_int, c_int, c_int]
     lib.vls_mask_decoder_workspace_bytes.restype = c_size_t
     lib.vls_mask_decoder_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int]
     lib.vls_mask_decoder_forward.restype = c_int

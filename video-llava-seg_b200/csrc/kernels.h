@@ -112,7 +112,7 @@ struct MidArgs {
 };
 int launch_mid_fused(const MidArgs& a, cudaStream_t stream);
 extern int g_mid_fused;
-extern int g_mem_attn_head_short;   // modules.cu
+extern int g_mem_attn_head_short, g_mem_attn_keys0_inline;   // modules.cu
 
 // ---------------------------------------------------------------- connected components (cc.cu)
 size_t cc_workspace_bytes(int n, int h, int w, bool fill);
@@ -129,6 +129,10 @@ int launch_ln256(const float* x, int B, int T, const float* w, const float* b, f
 int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
                      long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
                      cudaStream_t stream);
+// ... with the output rows a slice of a taller [B][rows][C] matrix (batch stride out_sb elements)
+int launch_axpy_rows_strided(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
+                             long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
+                             long long out_sb, cudaStream_t stream);
 // NCHW view (strides sb,sc,sh,sw; zeros allowed) (+ addend) -> rows [B][H*W][C] f32 and/or bf16.
 int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], const void* add, int add_bf16,
                         const long long sa[4], int B, int C, int H, int W, float* out_f32, void* out_bf16,

@@ -61,7 +61,7 @@ size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) { return mem_attn_ws(
 // cross-attention query projection (default).  Measured (A/B on one box, frame ms): no pipelining 0.911, full head 0.894, short
 // head 0.920 -- with the short head the self-attention (128 CTAs, high-priority chain) opens the frame and the key projection
 // on its fork only gets SMs ~17 us later, so the first cross-attention starts 54 us into the frame instead of 33.
-namespace vls { int g_mem_attn_head_short = 0; }
+namespace vls { int g_mem_attn_head_short = 0; int g_mem_attn_keys0_inline = 1; }
 extern "C" {
 // phase 0: the whole stack.  phase 1 (HEAD): only what depends on `curr` alone -- x = curr + 0.1 pos, layer 0's LayerNorm1,
 // q/k/v projections, self-attention, out-projection + LayerNorm2 + cross-attention query projection -- leaving x and the
@@ -73,9 +73,16 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
                          const void* memory, int mem_dtype, long long mem_st, long long mem_sb, const void* memory_pos,
                          int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq, int Nk,
                          int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
-                         void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase) {
+                         void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase, int ahead_rows,
+                         int ahead_shift_from, int ahead_shift) {
   cudaStream_t st = (cudaStream_t)stream_;
   VLS_REQUIRE(phase >= 0 && phase <= 2, "mem_attn: phase must be 0 (whole), 1 (head) or 2 (rest)");
+  if (phase == 0) ahead_rows = 0;
+  VLS_REQUIRE(ahead_rows >= 0 && ahead_rows <= Nk - num_obj_ptr_tokens && ahead_rows % Nq == 0,
+              "mem_attn: keys projected ahead (%d rows) must be whole rotated blocks of Nq = %d keys", ahead_rows, Nq);
+  VLS_REQUIRE(ahead_rows == 0 || (ahead_shift_from >= 0 && ahead_shift_from <= ahead_rows && ahead_shift >= 0 &&
+                                  ahead_rows + ahead_shift <= Nk),
+              "mem_attn: bad shift of the keys projected ahead (from %d by %d of %d)", ahead_shift_from, ahead_shift, ahead_rows);
   VLS_REQUIRE(w && (curr || phase == 2) && (memory || phase == 1) && (out || phase == 1), "mem_attn: null argument");
   VLS_REQUIRE(w->num_layers >= 1 && w->num_layers <= 8, "mem_attn: num_layers out of range");
   VLS_REQUIRE(B >= 1 && Nq >= 1 && Nk >= 1, "mem_attn: bad shape");
@@ -128,34 +135,60 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
   // tail and the next self-attention chain, whose kernels leave SMs idle.  (As one batched launch of L x B problems the first
   // cross-attention waited for all four layers' keys: the 54 us of projection work and layer 0's self-attention chain, which
   // needs the SMs as well, added up to ~104 us before it started; all four launched at the start slowed layer 0's kernels.)
-  const bool k_per_layer = L <= 8;
-  auto project_keys = [&](int l) -> int {     // l < 0: all layers in one launch
-    cudaStream_t side;
-    VLS_TRY(fork_begin(0, st, &side));
-    if (l <= 0) {
-      if (!mem_alias) VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, side));
-      VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb,
-                               memory_pos ? 1.0f : 0.f, B, Nk, CM, nullptr, mempos, side));
-    }
+  const bool k_per_layer = L <= 8 || ahead_rows > 0;
+  // memory + positional rows [r0, r1) of the bank -> bf16 operand rows; src_shift: the memory rows are read that many rows
+  // further on (a device bank that has not been shifted yet: see ahead_rows below)
+  auto convert_rows = [&](int r0, int r1, int src_shift, cudaStream_t s_) -> int {
+    if (r1 <= r0) return 0;
+    const size_t mel = mem_dtype == VLS_BF16 ? 2 : 4, pel = mpos_dtype == VLS_BF16 ? 2 : 4;
+    const char* msrc = static_cast<const char*>(memory) + (size_t)(r0 + src_shift) * mem_st * mel;
+    const char* psrc = memory_pos ? static_cast<const char*>(memory_pos) + (size_t)r0 * mpos_st * pel : nullptr;
+    return launch_axpy_rows_strided(msrc, mem_dtype, mem_st, mem_sb, psrc, mpos_dtype, mpos_st, mpos_sb, memory_pos ? 1.0f : 0.f,
+                                    B, r1 - r0, CM, nullptr, static_cast<char*>(mempos) + (size_t)r0 * CM * 2,
+                                    (long long)Nk * CM, s_);
+  };
+  // K_l rows [r0, r1) (r0 a multiple of Nq, so the RoPE phase of a row is its index inside the launch); l < 0: all layers
+  auto gemm_keys = [&](int l, int r0, int r1, cudaStream_t s_) -> int {
+    if (r1 <= r0) return 0;
     GemmArgs k;
-    k.A = mempos; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
+    k.A = static_cast<char*>(mempos) + (size_t)r0 * CM * 2; k.lda = CM; k.a_bstride = (long long)Nk * CM; k.a_batches = B; k.a_div = 1;
     k.ldw = CM; k.w_bstride = (long long)C * CM; k.w_div = B;
-    k.M = Nk; k.N = C; k.K = CM;
+    k.M = r1 - r0; k.N = C; k.K = CM;
     k.bias_mode = 1; k.bias_bstride = C; k.bias_div = B;
-    k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = Nk - num_obj_ptr_tokens;
+    const int rot = Nk - num_obj_ptr_tokens;
+    k.rope_cos = w->rope_cos; k.rope_sin = w->rope_sin; k.rope_period = Nq; k.rope_rows = (r1 < rot ? r1 : rot) - r0;
+    if (k.rope_rows < 0) k.rope_rows = 0;
     k.c_bf16 = 1; k.ldc = C; k.c_bstride = (long long)Nk * C;
     if (l >= 0) {
       k.W = static_cast<const char*>(w->ca_k_w_all) + (size_t)l * C * CM * 2; k.w_batches = 1;
       k.bias = w->ca_k_b_all + (size_t)l * C; k.bias_batches = 1;
-      k.C = kc_all + (size_t)l * B * Nk * C * 2; k.batch = B;
+      k.C = kc_all + ((size_t)l * B * Nk + r0) * C * 2; k.batch = B;
     } else {
       k.W = w->ca_k_w_all; k.w_batches = L;
       k.bias = w->ca_k_b_all; k.bias_batches = L;
-      k.C = kc_all; k.batch = L * B;
+      k.C = kc_all + (size_t)r0 * C * 2; k.batch = L * B;
     }
-    VLS_TRY(launch_gemm(k, side));
+    return launch_gemm(k, s_);
+  };
+  // ahead_rows > 0 (phases 1 and 2 only): layer 0's keys of the first ahead_rows bank rows are projected by the HEAD -- one frame
+  // ahead, next to the previous frame's mask decoder -- and the rest projects only the rows behind them at the start of the
+  // frame (the newest memory and the object pointers: 1/7 of the bank).  With ahead_shift the head reads the memory rows of
+  // [ahead_shift_from, ahead_rows) that many rows further on: the caller's bank has not been shifted yet.
+  // phase 2 behind a full head: nothing runs on the main stream before layer 0's cross-attention, so its keys are projected
+  // there instead of on the fork (the cross-stream edge at the root of a captured graph cost ~8 us before the GEMM started)
+  const bool keys0_inline = phase == 2 && !g_mem_attn_head_short && k_per_layer && g_mem_attn_keys0_inline;
+  auto project_keys = [&](int l) -> int {     // l < 0: all layers in one launch
+    cudaStream_t side = st;
+    const bool inl = keys0_inline && l == 0;
+    if (!inl) VLS_TRY(fork_begin(0, st, &side));
+    const int r0 = (l == 0 && phase == 2) ? ahead_rows : 0;
+    if (l <= 0) {
+      if (!mem_alias) VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, side));
+      VLS_TRY(convert_rows(r0, Nk, 0, side));
+    }
+    VLS_TRY(gemm_keys(l, r0, Nk, side));
     if (l <= 0 && !g_attn_v_rows) VLS_TRY(launch_transpose_rows64(memr, B, Nk, memT, ldv, side));
-    if (l >= 0) VLS_TRY(fork_mark(0, l));
+    if (l >= 0 && !inl) VLS_TRY(fork_mark(0, l));
     return 0;
   };
   if (phase != 1) VLS_TRY(project_keys(k_per_layer ? 0 : -1));
@@ -227,9 +260,16 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     }
     }
     }
-    if (phase == 1) return 0;
+    if (phase == 1) {
+      if (ahead_rows > 0) {   // behind the head, on its stream: nothing in this call waits for them
+        VLS_TRY(convert_rows(0, ahead_shift_from, 0, st));
+        VLS_TRY(convert_rows(ahead_shift_from, ahead_rows, ahead_shift, st));
+        VLS_TRY(gemm_keys(0, 0, ahead_rows, st));
+      }
+      return 0;
+    }
     if (k_per_layer) {
-      VLS_TRY(fork_wait(0, l, st));
+      if (!(keys0_inline && l == 0)) VLS_TRY(fork_wait(0, l, st));
     } else if (!joined) {
       VLS_TRY(fork_join(0, st));
       joined = true;
@@ -292,7 +332,7 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
                          void* workspace, size_t workspace_bytes, vls_stream_t stream_) {
   return mem_attn_forward_impl(w, curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, memory, mem_dtype,
                                mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb, B, Nq, Nk, num_obj_ptr_tokens, out,
-                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, 0);
+                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, 0, 0, 0, 0);
 }
 
 int vls_mem_attn_forward_phase(const vls_mem_attn_weights* w, const void* curr, int curr_dtype, long long curr_st,
@@ -300,10 +340,12 @@ int vls_mem_attn_forward_phase(const vls_mem_attn_weights* w, const void* curr, 
                                const void* memory, int mem_dtype, long long mem_st, long long mem_sb,
                                const void* memory_pos, int mpos_dtype, long long mpos_st, long long mpos_sb, int B, int Nq,
                                int Nk, int num_obj_ptr_tokens, void* out, int out_dtype, long long out_st, long long out_sb,
-                               void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase) {
+                               void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase, int ahead_rows,
+                               int ahead_shift_from, int ahead_shift) {
   return mem_attn_forward_impl(w, curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, memory, mem_dtype,
                                mem_st, mem_sb, memory_pos, mpos_dtype, mpos_st, mpos_sb, B, Nq, Nk, num_obj_ptr_tokens, out,
-                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, phase);
+                               out_dtype, out_st, out_sb, workspace, workspace_bytes, stream_, phase, ahead_rows,
+                               ahead_shift_from, ahead_shift);
 }
 
 // ================================================================== mask decoder

@@ -61,15 +61,17 @@ __global__ void ln256_kernel(const float* __restrict__ x, int B, int T, const fl
 // a, p: element (t, b, c) at  t*s_t + b*s_b + c  (f32 or bf16); C % 4 == 0.  out rows contiguous.
 __global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long long a_st, long long a_sb,
                                  const void* __restrict__ p, int p_bf16, long long p_st, long long p_sb, float alpha,
-                                 int B, int T, int C, float* __restrict__ out_f32, bf16* __restrict__ out_bf16) {
+                                 int B, int T, int C, float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
+                                 long long out_sb) {
   pdl_enter();
   const long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total4 = (long long)B * T * C / 4;
   if (i4 >= total4) return;
-  const long long e = i4 * 4;
-  const int c = (int)(e % C);
-  const long long bt = e / C;
+  const long long e_in = i4 * 4;
+  const int c = (int)(e_in % C);
+  const long long bt = e_in / C;
   const int t = (int)(bt % T), b = (int)(bt / T);
+  const long long e = (long long)b * out_sb + (long long)t * C + c;   // out_sb = T * C unless the rows are a slice of a taller matrix
   float v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -494,15 +496,22 @@ int launch_ln256(const float* x, int B, int T, const float* w, const float* b, f
   return 0;
 }
 
+int launch_axpy_rows_strided(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
+                             long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
+                             long long out_sb, cudaStream_t stream) {
+  VLS_REQUIRE(C % 4 == 0 && out_sb % 4 == 0, "axpy_rows: C and the output batch stride must be multiples of 4");
+  const long long total4 = (long long)B * T * C / 4;
+  if (total4 == 0) return 0;
+  VLS_CUDA(launch_k(axpy_rows_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,  a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16), out_sb));
+  VLS_POST_LAUNCH(1);
+  return 0;
+}
+
 int launch_axpy_rows(const void* a, int a_bf16, long long a_st, long long a_sb, const void* p, int p_bf16,
                      long long p_st, long long p_sb, float alpha, int B, int T, int C, float* out_f32, void* out_bf16,
                      cudaStream_t stream) {
-  VLS_REQUIRE(C % 4 == 0, "axpy_rows: C must be a multiple of 4");
-  const long long total4 = (long long)B * T * C / 4;
-  if (total4 == 0) return 0;
-  VLS_CUDA(launch_k(axpy_rows_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,  a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16)));
-  VLS_POST_LAUNCH(1);
-  return 0;
+  return launch_axpy_rows_strided(a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, out_bf16,
+                                  (long long)T * C, stream);
 }
 
 int launch_nchw_to_rows(const void* in, int in_bf16, const long long si[4], const void* add, int add_bf16,

@@ -36,13 +36,16 @@ from .modeling.sam2_utils import get_1d_sine_pe
 from .utils.misc import fill_holes_in_mask_scores
 
 
-def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw, side_stream, head=None):
+def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw, side_stream, head=None, keys_ahead=(0, 0, 0)):
     """memory attention -> mask decoder -> SAM-heads glue -> {hole filling + output stage || memory encoder} of one
     tracked frame on static buffers: what both kinds of captured graph replay.
     head = (next frame's features, stream): software-pipelined frames.  This frame's memory attention starts at layer 0's
     cross-attention (its head -- everything that depends on the frame's features alone -- was run ahead), and the NEXT
     frame's head runs on `stream` next to this frame's mask decoder and memory encoder, whose small kernels leave most
-    SMs idle.  Same kernels, same operands, same order per buffer: results are bit-identical to the unpipelined frame."""
+    SMs idle.  keys_ahead = (rows, shift_from, shift): the head also projects layer 0's keys of the bank rows that are
+    already known -- the conditioning memory and, read one slot further on because the bank is shifted at the end of the
+    frame, the memories that stay in the window -- so this frame projects only the newest memory and the pointers before its
+    first cross-attention.  Same arithmetic on the same operands: results are bit-identical to the unpipelined frame."""
     dev = in_feat.device
     s = m.sam_image_embedding_size
     main = torch.cuda.current_stream(dev)
@@ -50,7 +53,7 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     vp = in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
     mem_t, pos_t = mem.transpose(0, 1), pos[None].expand(B, -1, -1).transpose(0, 1)
     pix = m.memory_attention(curr=[vf], curr_pos=[vp], memory=mem_t, memory_pos=pos_t, num_obj_ptr_tokens=n_ptr_tokens,
-                             phase=0 if head is None else 2)
+                             phase=0 if head is None else 2, keys_ahead=(keys_ahead[0], 0, 0))
     if head is not None:
         # right behind this frame's stack: measured against starting it after the mask decoder (0.912 vs 0.900 ms per frame --
         # it then collides with the memory encoder's full-width kernels) and against a head that stops before the
@@ -59,7 +62,7 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
         head_stream.wait_stream(main)      # the module's workspace is free again once this frame's stack has run
         with torch.cuda.stream(head_stream):
             m.memory_attention(curr=[nxt.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)], curr_pos=[vp], memory=mem_t,
-                               memory_pos=pos_t, num_obj_ptr_tokens=n_ptr_tokens, phase=1)
+                               memory_pos=pos_t, num_obj_ptr_tokens=n_ptr_tokens, phase=1, keys_ahead=keys_ahead)
     pix = pix.permute(1, 2, 0).reshape(B, m.hidden_dim, s, s)
     high = [in_s0.expand(B, -1, -1, -1), in_s1.expand(B, -1, -1, -1)]
     _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
@@ -183,6 +186,8 @@ class SteadyStateGraph:
         self.next_frame = None
         self._side = torch.cuda.Stream(device=self.dev)
         self.pipelined = pipelined_frames(model)
+        # layer 0's keys of the conditioning memory and of the five memories that stay in the window: projected by the head
+        self.keys_ahead = (self.n_mem - 1) * self.HW if self.pipelined and os.environ.get("VLS_NO_KEYS_AHEAD", "0") != "1" else 0
         self._head_stream = torch.cuda.Stream(device=self.dev)     # default (lowest) priority: the head fills idle SMs
         self._build_static(state, frame_idx)
 
@@ -319,7 +324,8 @@ class SteadyStateGraph:
     def _step(self):
         pred, obj_ptr, obj_logits, nchw, rows, video = _frame_body(
             self.model, self.B, self.in_feat, self.in_pos, self.in_s0, self.in_s1, self.bank_mem, self.bank_pos,
-            self.n_ptr * self.k, self.hw, self._side, (self.in_feat_next, self._head_stream) if self.pipelined else None)
+            self.n_ptr * self.k, self.hw, self._side, (self.in_feat_next, self._head_stream) if self.pipelined else None,
+            (self.keys_ahead, self.HW, self.HW))     # the bank is shifted by one memory (HW rows) after the frame
         if self.pipelined:
             # the next frame's features become the current ones (memory encoder and head have both read theirs by now)
             ops.copy_many([self.in_feat_next], [self.in_feat])
@@ -335,7 +341,8 @@ class SteadyStateGraph:
         vp = self.in_pos.expand(B, -1, -1, -1).flatten(2).permute(2, 0, 1)
         self.model.memory_attention(curr=[vf], curr_pos=[vp], memory=self.bank_mem.transpose(0, 1),
                                     memory_pos=self.bank_pos[None].expand(B, -1, -1).transpose(0, 1),
-                                    num_obj_ptr_tokens=self.n_ptr * self.k, phase=1)
+                                    num_obj_ptr_tokens=self.n_ptr * self.k, phase=1,
+                                    keys_ahead=(self.keys_ahead, self.keys_ahead, 0))   # the bank is this frame's: no shift
 
     def _capture(self):
         keep = (self.bank_mem.clone(), self.bank_pos.clone())

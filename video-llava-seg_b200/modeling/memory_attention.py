@@ -52,11 +52,12 @@ class MemoryAttention(PackedModule):
         self._rope = {}
         return super()._apply(fn, *a, **kw)
 
-    def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0, phase=0):
+    def forward(self, curr, memory, curr_pos=None, memory_pos=None, num_obj_ptr_tokens=0, phase=0, keys_ahead=(0, 0, 0)):
         """curr / curr_pos: [Nq,B,256] (or 1-element lists of it); memory / memory_pos: [Nk,B,64];
         returns [Nq,B,256] in curr's dtype.  Same contract as memory_attention.py:119-169.
         phase (not in the reference): 1 = only the part that depends on `curr` alone (layer 0 up to its cross-attention
-        queries, left in the workspace; returns None), 2 = the rest for the head run last, 0 = both (vls_b200.h)."""
+        queries, left in the workspace; returns None), 2 = the rest for the head run last, 0 = both (vls_b200.h).
+        keys_ahead = (rows, shift_from, shift): the head also projects layer 0's keys of the first `rows` memory rows."""
         if isinstance(curr, list):
             assert isinstance(curr_pos, list) and len(curr) == len(curr_pos) == 1
             curr, curr_pos = curr[0], curr_pos[0]
@@ -90,6 +91,7 @@ class MemoryAttention(PackedModule):
             ctypes_ref(w), ptr(cu[0]), cu[1], cu[2], cu[3], ptr(cpos[0]), cpos[1], cpos[2], cpos[3],
             ptr(me[0]), me[1], me[2], me[3], ptr(mpos[0]), mpos[1], mpos[2], mpos[3], b, nq, nk,
             int(num_obj_ptr_tokens), ptr(out), 0 if out is None else dtype_code(out), 0 if out is None else out.stride(0),
-            0 if out is None else out.stride(1), ptr(ws), ws.numel(), stream(), int(phase)), "vls_mem_attn_forward_phase")
+            0 if out is None else out.stride(1), ptr(ws), ws.numel(), stream(), int(phase), int(keys_ahead[0]),
+            int(keys_ahead[1]), int(keys_ahead[2])), "vls_mem_attn_forward_phase")
         return out
 
