@@ -60,6 +60,10 @@ int vls_set_tuning(const char* key, int value) {
     g_mem_attn_head_short = value != 0;
     return 0;
   }
+  if (std::string(key) == "mem_attn_keys_ahead_all") {   // pipelined frames: the head projects every layer's known keys (1) or layer 0's (0)
+    g_mem_attn_keys_ahead_all = value != 0;
+    return 0;
+  }
   if (std::string(key) == "mem_attn_keys0_inline") {   // pipelined frames: layer 0's keys on the main stream (1) or on the fork (0)
     g_mem_attn_keys0_inline = value != 0;
     return 0;

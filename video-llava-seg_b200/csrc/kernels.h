@@ -112,7 +112,7 @@ struct MidArgs {
 };
 int launch_mid_fused(const MidArgs& a, cudaStream_t stream);
 extern int g_mid_fused;
-extern int g_mem_attn_head_short, g_mem_attn_keys0_inline;   // modules.cu
+extern int g_mem_attn_head_short, g_mem_attn_keys0_inline, g_mem_attn_keys_ahead_all;   // modules.cu
 
 // ---------------------------------------------------------------- connected components (cc.cu)
 size_t cc_workspace_bytes(int n, int h, int w, bool fill);

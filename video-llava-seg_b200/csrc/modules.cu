@@ -61,7 +61,7 @@ size_t vls_mem_attn_workspace_bytes(int B, int Nq, int Nk) { return mem_attn_ws(
 // cross-attention query projection (default).  Measured (A/B on one box, frame ms): no pipelining 0.911, full head 0.894, short
 // head 0.920 -- with the short head the self-attention (128 CTAs, high-priority chain) opens the frame and the key projection
 // on its fork only gets SMs ~17 us later, so the first cross-attention starts 54 us into the frame instead of 33.
-namespace vls { int g_mem_attn_head_short = 0; int g_mem_attn_keys0_inline = 1; }
+namespace vls { int g_mem_attn_head_short = 0; int g_mem_attn_keys0_inline = 1; int g_mem_attn_keys_ahead_all = 0; }
 extern "C" {
 // phase 0: the whole stack.  phase 1 (HEAD): only what depends on `curr` alone -- x = curr + 0.1 pos, layer 0's LayerNorm1,
 // q/k/v projections, self-attention, out-projection + LayerNorm2 + cross-attention query projection -- leaving x and the
@@ -181,7 +181,10 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     cudaStream_t side = st;
     const bool inl = keys0_inline && l == 0;
     if (!inl) VLS_TRY(fork_begin(0, st, &side));
-    const int r0 = (l == 0 && phase == 2) ? ahead_rows : 0;
+    // keys projected ahead: layer 0's, or (keys_ahead_all) every layer's -- then no full-bank projection runs in the
+    // background of the frame's own attention kernels at all; measured 0.8748 vs 0.8733 ms per frame (A/B on one box): the
+    // extra 44 MB the head then writes next to the mask decoder cost more than the quieter attention phase gained, so off
+    const int r0 = (phase == 2 && (l == 0 || g_mem_attn_keys_ahead_all)) ? ahead_rows : 0;
     if (l <= 0) {
       if (!mem_alias) VLS_TRY(launch_axpy_rows(memory, mem_dtype, mem_st, mem_sb, nullptr, 0, 0, 0, 0.f, B, Nk, CM, nullptr, mem, side));
       VLS_TRY(convert_rows(r0, Nk, 0, side));
@@ -264,7 +267,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
       if (ahead_rows > 0) {   // behind the head, on its stream: nothing in this call waits for them
         VLS_TRY(convert_rows(0, ahead_shift_from, 0, st));
         VLS_TRY(convert_rows(ahead_shift_from, ahead_rows, ahead_shift, st));
-        VLS_TRY(gemm_keys(0, 0, ahead_rows, st));
+        VLS_TRY(gemm_keys(g_mem_attn_keys_ahead_all ? -1 : 0, 0, ahead_rows, st));
       }
       return 0;
     }

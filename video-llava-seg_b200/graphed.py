@@ -292,19 +292,17 @@ class SteadyStateGraph:
         self._owner = weakref.ref(owner)
         self._fill_static(state, frame_idx)
 
-    def _load_inputs(self, state, frame_idx, load_feat=True):
-        """Stage the frame's inputs.  Pipelined: the frame's own low-resolution features are already in `in_feat` (the
-        previous replay moved them there) unless load_feat, and the NEXT frame's are fetched one frame ahead for its head."""
+    def _load_inputs(self, state, frame_idx):
+        """Stage the frame's inputs.  Pipelined: the NEXT frame's low-resolution features are fetched one frame ahead for
+        its head; the frame's own (the memory encoder reads them) are staged again from the look-ahead kept for a frame --
+        4 MB more in this launch, against a copy kernel of its own inside the frame."""
         if self._lookahead is not None and self._lookahead[0] == frame_idx:
             fpn, pe = self._lookahead[1:]
         else:
             _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx, 1)
             fpn, pe = bo["backbone_fpn"], bo["vision_pos_enc"]
         # one launch for all the staging copies (five Tensor.copy_ calls were ~20 us of launch gaps per frame)
-        srcs, dsts = [fpn[-3], fpn[-2]], [self.in_s0, self.in_s1]
-        if load_feat:
-            srcs.append(fpn[-1])
-            dsts.append(self.in_feat)
+        srcs, dsts = [fpn[-3], fpn[-2], fpn[-1]], [self.in_s0, self.in_s1, self.in_feat]
         self._lookahead = None
         if self.pipelined and frame_idx + 1 < self.num_frames:
             _, bo, _, _, _ = self.model._get_image_feature(state, frame_idx + 1, 1)
@@ -326,9 +324,6 @@ class SteadyStateGraph:
             self.model, self.B, self.in_feat, self.in_pos, self.in_s0, self.in_s1, self.bank_mem, self.bank_pos,
             self.n_ptr * self.k, self.hw, self._side, (self.in_feat_next, self._head_stream) if self.pipelined else None,
             (self.keys_ahead, self.HW, self.HW))     # the bank is shifted by one memory (HW rows) after the frame
-        if self.pipelined:
-            # the next frame's features become the current ones (memory encoder and head have both read theirs by now)
-            ops.copy_many([self.in_feat_next], [self.in_feat])
         # bank shift for the next frame (one launch, in place): memories t-6..t-1 <- t-5..t, pointers t-1..t-15 <- t..t-14
         ops.bank_shift(self.bank_mem, self.HW, self.n_mem, self.n_ptr, self.k, rows.contiguous(), obj_ptr.float().contiguous())
         return pred, obj_ptr, obj_logits, nchw, rows, video
@@ -386,7 +381,7 @@ class SteadyStateGraph:
         assert self.owned_by(state.get("graph_owner")), "the captured graph (and its memory bank) belongs to another session"
         ma = self.model.memory_attention
         need_head = self.pipelined and not (self._head_frame == frame_idx and self._head_epoch == ma.ws_epoch)
-        self._load_inputs(state, frame_idx, load_feat=need_head or not self.pipelined)
+        self._load_inputs(state, frame_idx)
         if self.graph is None:
             self._capture()
             self._load_inputs(state, frame_idx)
