@@ -202,7 +202,7 @@ def run_ours(args):
     config = make_config(args.workload, world)
     method = {}   # how this arm runs and times the workload: kept OUT of `config`, which both arms must share verbatim
     method["execution"] = "steady-state frames replay one CUDA graph (graphed.py); gpu_launches counts the library kernels inside each replay"
-    method["e2e_path"] = ("pinned host features -> double-buffered H2D -> propagate_in_video(output_mode='binary': fused "
+    method["e2e_path"] = ("pinned host features -> H2D one frame ahead on a copy stream (3 staging sets) -> propagate_in_video(output_mode='binary': fused "
                           "resize+threshold) -> uint8 mask D2H into pinned memory every step on a copy stream; step i's events close over the "
                           "read-back of step i-1 (K steps = K complete read-backs), consumer pipelined by one frame")
     line = {"metric": wl["metric"], "unit": UNIT, "n_gpus": world, "higher_is_better": True, "scaling": "weak",
