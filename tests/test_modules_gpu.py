@@ -93,6 +93,50 @@ def test_memory_attention_mid_fused_matches_kernel_chain(env):
         lib.vls_set_tuning(b"tail_quarter", 1)
 
 
+def test_memory_attention_head_and_rest_are_bit_identical_to_one_call(env):
+    """vls_mem_attn_forward_phase: head (phase 1) + rest (phase 2) against the one-call form, bit for bit -- plain split, layer 0's
+    keys of the first memories projected by the head, and the head run on a sliding-window bank BEFORE its shift (what the
+    pipelined steady-state graph does: graphed._frame_body), for every tuning of the head, at 1 and 2 objects."""
+    from video_llava_seg_b200 import _lib
+
+    dev, sd = env["dev"], env["sd"]
+    m = env["build"].load_prefixed(env["build"].build_memory_attention(), sd, "memory_attention.").to(dev).eval()
+    lib = _lib.lib()
+    g = torch.Generator().manual_seed(11)
+    nq, slots, nptr = 1024, 4, 16                       # 32 x 32 tokens, 4 memories + 4 pointers of 4 tokens
+    nk = slots * nq + nptr
+    try:
+        for b in (1, 2):
+            curr = (torch.randn(nq, b, 256, generator=g) * 0.5).to(dev)
+            cpos = (torch.randn(nq, b, 256, generator=g) * 0.5).to(dev)
+            mpos = (torch.randn(nk, 1, 64, generator=g) * 0.5).expand(nk, b, 64).contiguous().to(dev)
+            window = (torch.randn(nk + nq, b, 64, generator=g) * 0.5).bfloat16().to(dev)   # one memory more than the bank
+            # the bank before the shift: [cond | m1 m2 m3 | ptrs];  after: [cond | m2 m3 m4 | ptrs']
+            before = torch.cat([window[:slots * nq], window[(slots + 1) * nq:]]).contiguous()
+            after = torch.cat([window[:nq], window[2 * nq:(slots + 1) * nq], window[(slots + 1) * nq:].flip(0)]).contiguous()
+            whole = m(curr, after, cpos, mpos, nptr).clone()
+            r0 = (slots - 1) * nq
+            for short, inline, ahead_all in ((0, 1, 0), (1, 1, 0), (0, 0, 0), (0, 1, 1)):
+                lib.vls_set_tuning(b"mem_attn_head_short", short)
+                lib.vls_set_tuning(b"mem_attn_keys0_inline", inline)
+                lib.vls_set_tuning(b"mem_attn_keys_ahead_all", ahead_all)
+                # (a) plain split on the final bank, (b) keys ahead on the final bank, (c) keys ahead on the unshifted bank
+                for name, head_mem, head_keys, rest_keys in (("split", after, (0, 0, 0), (0, 0, 0)),
+                                                             ("keys ahead", after, (r0, r0, 0), (r0, 0, 0)),
+                                                             ("keys ahead, shifted", before, (r0, nq, nq), (r0, 0, 0))):
+                    m._ws.zero_()                      # nothing of the one-call run may survive in the workspace
+                    assert m(curr, head_mem, cpos, mpos, nptr, phase=1, keys_ahead=head_keys) is None
+                    out = m(torch.zeros_like(curr), after, cpos, mpos, nptr, phase=2, keys_ahead=rest_keys)
+                    assert torch.equal(out, whole), (b, short, inline, ahead_all, name, (out - whole).abs().max().item())
+        import pytest
+        with pytest.raises(RuntimeError):               # keys ahead must be whole rotated blocks
+            m(curr, after, cpos, mpos, nptr, phase=1, keys_ahead=(nq // 2, 0, 0))
+    finally:
+        lib.vls_set_tuning(b"mem_attn_head_short", 0)
+        lib.vls_set_tuning(b"mem_attn_keys0_inline", 1)
+        lib.vls_set_tuning(b"mem_attn_keys_ahead_all", 0)
+
+
 def test_mask_decoder_video_and_llava(env):
     from oracle import sam2_path as O
 

@@ -406,6 +406,49 @@ def test_cuda_graph_steady_state_matches_eager(predictor):
             assert torch.equal(eager[t][0], graphed[t][0]), "ramp frames take the same eager path"
 
 
+def test_pipelined_frames_are_bit_identical_and_survive_interference(predictor):
+    """Steady-state frames software-pipelined across replays (graphed._frame_body: frame t+1's memory-attention head and the
+    known keys run next to frame t's decoder / memory encoder) against the unpipelined graph: identical bits.  Halfway
+    through, something else uses the memory-attention workspace between two frames (an eager forward), so the head that was
+    run ahead is stale and must be recomputed; pinned host features exercise the one-frame look-ahead of FeatureClip."""
+    from video_llava_seg_b200 import synth
+    from video_llava_seg_b200.features import FeatureClip
+
+    T = 26
+    clip = synth.SyntheticClip(23, T)
+    prompt = clip.point_prompt(1)
+
+    def run(pipelined, pinned, disturb_at=None):
+        predictor.pipeline_frames = pipelined
+        src = FeatureClip(lambda t: clip.frame(t, 1), T, pinned=True) if pinned else \
+            FeatureClip(lambda t: clip.frame(t, 1), T, resident_device="cuda:0")
+        st = predictor.init_state(src)
+        predictor.add_new_points_or_box(st, 0, 1, points=prompt["point_coords"][0].tolist(), labels=[1])
+        outs = []
+        for f, ids, video in predictor.propagate_in_video(st):
+            o = st["output_dict"]["cond_frame_outputs" if f == 0 else "non_cond_frame_outputs"][f]
+            outs.append((o["pred_masks"].clone(), o["obj_ptr"].clone(), o["maskmem_features"].clone(), video.clone()))
+            if f == disturb_at:
+                ma = predictor.memory_attention
+                g = torch.Generator().manual_seed(3)
+                ma(torch.randn(4096, 1, 256, generator=g).cuda(), torch.randn(4096 + 16, 1, 64, generator=g).cuda(),
+                   torch.randn(4096, 1, 256, generator=g).cuda(), torch.randn(4096 + 16, 1, 64, generator=g).cuda(), 16)
+        return outs, st
+
+    try:
+        plain, st0 = run(False, False)
+        assert st0["steady_graph"] is not None and not st0["steady_graph"].pipelined
+        for pinned, disturb in ((False, None), (False, 20), (True, 21)):
+            piped, st = run(True, pinned, disturb)
+            g = st["steady_graph"]
+            assert g is not None and g.graph is not None and g.pipelined and g.keys_ahead == 6 * 4096
+            for t in range(T):
+                for a, b, name in zip(plain[t], piped[t], ("pred_masks", "obj_ptr", "maskmem", "video_res")):
+                    assert torch.equal(a, b), (pinned, disturb, t, name, (a.float() - b.float()).abs().max().item())
+    finally:
+        predictor.pipeline_frames = True
+
+
 @pytest.mark.parametrize("mode", ["binary", "bits"])
 def test_fused_binary_output_stage(predictor, mode):
     """f-3: output_mode 'binary' / 'bits' (fused up-sampling + threshold, f32 video-resolution logits never written)

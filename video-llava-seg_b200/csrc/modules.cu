@@ -213,6 +213,12 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     return launch_attention(a, st);
   };
 
+  auto keys_ahead = [&]() -> int {   // behind the head, on its stream: nothing in this call waits for them
+    if (ahead_rows <= 0) return 0;
+    VLS_TRY(convert_rows(0, ahead_shift_from, 0, st));
+    VLS_TRY(convert_rows(ahead_shift_from, ahead_rows, ahead_shift, st));
+    return gemm_keys(g_mem_attn_keys_ahead_all ? -1 : 0, 0, ahead_rows, st);
+  };
   const bool tail_fused = g_ffn_fused && g_tail_fused;
   bool have_t = false, out_done = false;   // tail_fused: the previous layer's tail kernel already produced t = LN1(x) / the output
   for (int l = 0; l < L; ++l) {
@@ -237,7 +243,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
       VLS_TRY(fork_join(2, st));
     }
     }
-    if (phase == 1 && g_mem_attn_head_short) return 0;   // short head: the projections only (kernels of < 10 us)
+    if (phase == 1 && g_mem_attn_head_short) return keys_ahead();   // short head: the projections only (kernels of < 10 us)
     if (!(first_rest && !g_mem_attn_head_short)) {
     VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, (long long)C * ldvs, C, 0, Nq, s_self));
     if (g_mid_fused) {
@@ -263,14 +269,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     }
     }
     }
-    if (phase == 1) {
-      if (ahead_rows > 0) {   // behind the head, on its stream: nothing in this call waits for them
-        VLS_TRY(convert_rows(0, ahead_shift_from, 0, st));
-        VLS_TRY(convert_rows(ahead_shift_from, ahead_rows, ahead_shift, st));
-        VLS_TRY(gemm_keys(g_mem_attn_keys_ahead_all ? -1 : 0, 0, ahead_rows, st));
-      }
-      return 0;
-    }
+    if (phase == 1) return keys_ahead();
     if (k_per_layer) {
       if (!(keys0_inline && l == 0)) VLS_TRY(fork_wait(0, l, st));
     } else if (!joined) {
