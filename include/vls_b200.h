@@ -232,6 +232,8 @@ int vls_mem_attn_forward(const vls_mem_attn_weights* w, const void* curr, int cu
  *   phase 2 (rest): everything from layer 0's key projection and cross-attention on, for the head that was run LAST on the
  *                   same workspace with the same B, Nq, Nk; curr / curr_pos are not read (may be NULL)
  *   phase 0       : both, = vls_mem_attn_forward.
+ *   phase 3, 4    : the head in two halves (3: x, norm1 and layer 0's q/k/v projections; 4: self-attention ... query projection
+ *                   and the keys projected ahead), for callers that place the halves differently; 3 then 4 = 1.
  * ahead_rows > 0 (a multiple of Nq, same value in both phases): the head also projects layer 0's keys of memory rows
  * [0, ahead_rows) -- which requires memory / memory_pos in phase 1 -- and the rest only those of rows [ahead_rows, Nk).
  * In phase 1 the memory rows of [ahead_shift_from, ahead_rows) are read ahead_shift rows further on: a caller whose bank is

@@ -76,14 +76,17 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
                          void* workspace, size_t workspace_bytes, vls_stream_t stream_, int phase, int ahead_rows,
                          int ahead_shift_from, int ahead_shift) {
   cudaStream_t st = (cudaStream_t)stream_;
-  VLS_REQUIRE(phase >= 0 && phase <= 2, "mem_attn: phase must be 0 (whole), 1 (head) or 2 (rest)");
+  VLS_REQUIRE(phase >= 0 && phase <= 4, "mem_attn: phase must be 0 (whole), 1 (head), 2 (rest), 3 (head front) or 4 (head back)");
+  // phase 3 + phase 4 = phase 1: front = x and layer 0's q/k/v projections, back = self-attention ... query projection + the
+  // keys projected ahead.  The graph path runs the back half behind the mask decoder (graphed._frame_body).
+  const bool is_head = phase == 1 || phase == 3 || phase == 4;
   if (phase == 0) ahead_rows = 0;
   VLS_REQUIRE(ahead_rows >= 0 && ahead_rows <= Nk - num_obj_ptr_tokens && ahead_rows % Nq == 0,
               "mem_attn: keys projected ahead (%d rows) must be whole rotated blocks of Nq = %d keys", ahead_rows, Nq);
   VLS_REQUIRE(ahead_rows == 0 || (ahead_shift_from >= 0 && ahead_shift_from <= ahead_rows && ahead_shift >= 0 &&
                                   ahead_rows + ahead_shift <= Nk),
               "mem_attn: bad shift of the keys projected ahead (from %d by %d of %d)", ahead_shift_from, ahead_shift, ahead_rows);
-  VLS_REQUIRE(w && (curr || phase == 2) && (memory || phase == 1) && (out || phase == 1), "mem_attn: null argument");
+  VLS_REQUIRE(w && (curr || phase == 2 || phase == 4) && (memory || is_head) && (out || is_head), "mem_attn: null argument");
   VLS_REQUIRE(w->num_layers >= 1 && w->num_layers <= 8, "mem_attn: num_layers out of range");
   VLS_REQUIRE(B >= 1 && Nq >= 1 && Nk >= 1, "mem_attn: bad shape");
   VLS_REQUIRE(num_obj_ptr_tokens >= 0 && num_obj_ptr_tokens <= Nk, "mem_attn: bad num_obj_ptr_tokens");
@@ -113,7 +116,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
               "mem_attn: workspace carve failed");
 
   // x = curr + 0.1 * curr_pos (memory_attention.py:141); memory -> bf16; memory + pos -> bf16 (:76)
-  if (phase != 2)
+  if (phase != 2 && phase != 4)
     VLS_TRY(launch_axpy_rows(curr, curr_dtype, curr_st, curr_sb, curr_pos, pos_dtype, pos_st, pos_sb, 0.1f, B, Nq, C, x,
                              nullptr, st));
   // The two memory-side conversions feed the K projection and the cross-attention only: they run on the K projection's fork
@@ -194,7 +197,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     if (l >= 0 && !inl) VLS_TRY(fork_mark(0, l));
     return 0;
   };
-  if (phase != 1) VLS_TRY(project_keys(k_per_layer ? 0 : -1));
+  if (!is_head) VLS_TRY(project_keys(k_per_layer ? 0 : -1));
   bool joined = false;
 
   // dv = 256: V^T [256][ldvt]; dv = 64: the memory itself, as rows [Nk][64] (v_rows) or transposed [64][ldvt]
@@ -225,7 +228,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     const vls_mem_attn_layer& Lw = w->layers[l];
     // ---- self attention (memory_attention.py:58-64): q = k = v = LN1(x); RoPE on q and k
     const bool first_rest = phase == 2 && l == 0;   // phase 2: layer 0's chain up to the head's end was run ahead
-    if (!first_rest) {
+    if (!first_rest && phase != 4) {
     if (!have_t) VLS_TRY(launch_ln256(x, B, Nq, Lw.n1_w, Lw.n1_b, LN_EPS, 0, nullptr, 0, 0, t, (long long)Nq * C, C, st));
     {
       GemmArgs g = lin(t, C, (long long)Nq * C, Lw.sa_qk_w, Nq, 2 * C, C, B, Lw.sa_qk_b, qk, 1, 2 * C, (long long)Nq * 2 * C);
@@ -243,7 +246,8 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
       VLS_TRY(fork_join(2, st));
     }
     }
-    if (phase == 1 && g_mem_attn_head_short) return keys_ahead();   // short head: the projections only (kernels of < 10 us)
+    if (phase == 3) return 0;
+    if (is_head && g_mem_attn_head_short) return keys_ahead();   // short head: the projections only (kernels of < 10 us)
     if (!(first_rest && !g_mem_attn_head_short)) {
     VLS_TRY(attention(qk + (size_t)C * 2, 2 * C, (long long)Nq * 2 * C, vts, ldvs, (long long)C * ldvs, C, 0, Nq, s_self));
     if (g_mid_fused) {
@@ -269,7 +273,7 @@ static int mem_attn_forward_impl(const vls_mem_attn_weights* w, const void* curr
     }
     }
     }
-    if (phase == 1) return keys_ahead();
+    if (is_head) return keys_ahead();
     if (k_per_layer) {
       if (!(keys0_inline && l == 0)) VLS_TRY(fork_wait(0, l, st));
     } else if (!joined) {

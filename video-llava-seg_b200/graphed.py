@@ -57,7 +57,8 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     if head is not None:
         # right behind this frame's stack: measured against starting it after the mask decoder (0.912 vs 0.900 ms per frame --
         # it then collides with the memory encoder's full-width kernels) and against a head that stops before the
-        # self-attention (0.920: see g_mem_attn_head_short in csrc/modules.cu)
+        # self-attention (0.920: see g_mem_attn_head_short in csrc/modules.cu), and against the head in two halves (phases 3
+        # and 4), the grid-wide self-attention half behind the decoder's cluster kernels: 0.903 vs 0.881
         nxt, head_stream = head
         head_stream.wait_stream(main)      # the module's workspace is free again once this frame's stack has run
         with torch.cuda.stream(head_stream):
@@ -68,6 +69,7 @@ def _frame_body(m, B, in_feat, in_pos, in_s0, in_s1, mem, pos, n_ptr_tokens, hw,
     _, _, _, low, _, obj_ptr, obj_logits = m._forward_sam_heads(
         pix, high_res_features=high, multimask_output=m._use_multimask(False, None), need_high_res=False,
         defer_obj_ptr=True)        # obj_ptr MLP on a forked stream, joined below: nothing before the bank update needs it
+
     # the output branch (hole filling = one CTA per object, + video-resolution resize) does not feed the memory
     # encoder, so it is captured on a forked stream and overlaps the encoder's small kernels
     side = side_stream if os.environ.get("VLS_NO_SIDE_STREAM", "0") != "1" else main

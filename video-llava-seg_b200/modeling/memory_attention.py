@@ -83,7 +83,7 @@ class MemoryAttention(PackedModule):
 
         cu, cpos = rows(curr), rows(curr_pos if self.pos_enc_at_input else None)
         me, mpos = rows(memory), rows(memory_pos)
-        out = torch.empty((nq, b, c), device=dev, dtype=curr.dtype) if phase != 1 else None
+        out = torch.empty((nq, b, c), device=dev, dtype=curr.dtype) if phase in (0, 2) else None   # 1, 3, 4: head only
         nbytes = lib().vls_mem_attn_workspace_bytes(b, nq, nk)
         ws = self._workspace(nbytes, dev)
         self.ws_epoch += 1
