@@ -61,7 +61,12 @@ void vls_launch_count_add(long long n);
  * 0 = on the FP32 pipe.
  * "pdl": 1 = kernels are launched with programmatic stream serialisation (they all begin with griddepcontrol.wait), so
  * launch latency overlaps the previous kernel's tail; default 0 (also settable with the environment variable VLS_PDL=1):
- * inside the CUDA-graph replay of the steady-state frame it measured no gain. */
+ * inside the CUDA-graph replay of the steady-state frame it measured no gain.
+ * vls_mem_attn_forward_phase only: "mem_attn_head_short": 0 (default) = the head runs through the cross-attention query
+ * projection, 1 = it stops after layer 0's q/k/v projections (set it identically for head and rest);
+ * "mem_attn_keys0_inline": 1 (default) = behind a full head, the rest projects layer 0's remaining keys on the caller's
+ * stream, 0 = on the internal fork; "mem_attn_keys_ahead_all": 0 (default) = ahead_rows applies to layer 0's keys, 1 = to
+ * every layer's (identically for head and rest). */
 int vls_set_tuning(const char* key, int value);
 /* Developer aid: when non-NULL, CTA (0,0,0) of every attention launch writes clock64() stamps of its producer /
  * MMA / softmax roles for the first 64 key tiles into this device buffer of 3*64*8 int64 (tools/trace_attention.py). */
