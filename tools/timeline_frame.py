@@ -31,7 +31,7 @@ print("cuda events:", len(ev))
 t0 = ev[0].time_range.start
 rows = [(e.time_range.start - t0, e.time_range.end - e.time_range.start, e.name[:60]) for e in ev]
 # a frame's graph replay begins with the first axpy_rows kernel after the staging copies (multi_copy / memcpy) of the host loop
-firsts = [i for i, r in enumerate(rows) if "axpy_rows" in r[2] and i > 0 and ("multi_copy" in rows[i - 1][2] or "emcpy" in rows[i - 1][2])]
+firsts = [i for i, r in enumerate(rows) if "axpy_rows" in r[2] and i > 0 and ("multi_copy" in rows[i - 1][2] or "Memcpy" in rows[i - 1][2])]
 print("frame starts", firsts[:8])
 a, b = firsts[-2], firsts[-1]
 base = rows[a][0]

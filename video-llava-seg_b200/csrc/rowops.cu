@@ -59,6 +59,26 @@ __global__ void ln256_kernel(const float* __restrict__ x, int B, int T, const fl
 
 // ------------------------------------------------------------------ out[b][t][c] = a + alpha * p
 // a, p: element (t, b, c) at  t*s_t + b*s_b + c  (f32 or bf16); C % 4 == 0.  out rows contiguous.
+// four consecutive channels at once (VEC: 8- / 16-byte aligned bases, strides multiples of 4 elements)
+template <bool VEC>
+__device__ __forceinline__ void ld4_any(const void* p, long long i, int is_bf16, float v[4]) {
+  if (VEC) {
+    if (is_bf16) {
+      const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const bf16*>(p) + i);
+      const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+      const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+      v[0] = lo.x; v[1] = lo.y; v[2] = hi.x; v[3] = hi.y;
+    } else {
+      const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p) + i);
+      v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = ld_any(p, i + k, is_bf16);
+  }
+}
+
+template <bool VEC>
 __global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long long a_st, long long a_sb,
                                  const void* __restrict__ p, int p_bf16, long long p_st, long long p_sb, float alpha,
                                  int B, int T, int C, float* __restrict__ out_f32, bf16* __restrict__ out_bf16,
@@ -73,10 +93,12 @@ __global__ void axpy_rows_kernel(const void* __restrict__ a, int a_bf16, long lo
   const int t = (int)(bt % T), b = (int)(bt / T);
   const long long e = (long long)b * out_sb + (long long)t * C + c;   // out_sb = T * C unless the rows are a slice of a taller matrix
   float v[4];
+  ld4_any<VEC>(a, t * a_st + b * a_sb + c, a_bf16, v);
+  if (p) {
+    float q[4];
+    ld4_any<VEC>(p, t * p_st + b * p_sb + c, p_bf16, q);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    v[i] = ld_any(a, t * a_st + b * a_sb + c + i, a_bf16);
-    if (p) v[i] += alpha * ld_any(p, t * p_st + b * p_sb + c + i, p_bf16);
+    for (int i = 0; i < 4; ++i) v[i] += alpha * q[i];
   }
   if (out_f32) *reinterpret_cast<float4*>(out_f32 + e) = make_float4(v[0], v[1], v[2], v[3]);
   if (out_bf16) *reinterpret_cast<uint2*>(out_bf16 + e) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
@@ -502,7 +524,12 @@ int launch_axpy_rows_strided(const void* a, int a_bf16, long long a_st, long lon
   VLS_REQUIRE(C % 4 == 0 && out_sb % 4 == 0, "axpy_rows: C and the output batch stride must be multiples of 4");
   const long long total4 = (long long)B * T * C / 4;
   if (total4 == 0) return 0;
-  VLS_CUDA(launch_k(axpy_rows_kernel, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,  a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16), out_sb));
+  auto vec_ok = [](const void* q, int is_bf16, long long st, long long sb) {
+    return q == nullptr || ((reinterpret_cast<uintptr_t>(q) % (is_bf16 ? 8 : 16)) == 0 && st % 4 == 0 && sb % 4 == 0);
+  };
+  // a + alpha * p is evaluated identically on both paths (same operations in the same order per element)
+  auto kern = (vec_ok(a, a_bf16, a_st, a_sb) && vec_ok(p, p_bf16, p_st, p_sb)) ? axpy_rows_kernel<true> : axpy_rows_kernel<false>;
+  VLS_CUDA(launch_k(kern, dim3((unsigned)((total4 + 255) / 256)), dim3(256), 0, stream,  a, a_bf16, a_st, a_sb, p, p_bf16, p_st, p_sb, alpha, B, T, C, out_f32, reinterpret_cast<bf16*>(out_bf16), out_sb));
   VLS_POST_LAUNCH(1);
   return 0;
 }
