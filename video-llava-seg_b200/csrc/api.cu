@@ -52,6 +52,10 @@ int vls_set_tuning(const char* key, int value) {
     g_up2_tc = value != 0;
     return 0;
   }
+  if (std::string(key) == "gemm_ring2_above") {   // GEMMs with K <= 256 and more CTAs than this stream operands through a 2-stage ring
+    g_gemm_ring2_above = value;
+    return 0;
+  }
   if (std::string(key) == "gemm_bn64_below") {   // GEMMs with fewer 128x128 tiles than this run with 128x64 tiles
     g_gemm_bn64_below = value;
     return 0;

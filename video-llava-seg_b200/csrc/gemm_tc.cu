@@ -17,6 +17,8 @@
 
 namespace vls {
 
+extern int g_gemm_ring2_above;
+
 namespace {
 
 constexpr int BM = 128;
@@ -287,8 +289,9 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
   const int kblocks = (a.K + BK - 1) / BK;
   const long long ctas = (long long)((a.M + BM - 1) / BM) * ((a.N + BN - 1) / BN) * a.batch;
   if (kblocks <= 1) return launch_cfg<BN, 1>(a, stream);
-  // multi-wave grids with short K are epilogue-bound: a 2-stage ring keeps 3 CTAs resident per SM
-  if (kblocks <= 2 || (kblocks <= 4 && ctas > 2 * 148)) return launch_cfg<BN, 2>(a, stream);
+  // short K: a 2-stage ring keeps 3-4 CTAs resident per SM and lets a CTA start in the shared memory one retiring CTA of a
+  // co-running launch frees (g_gemm_ring2_above)
+  if (kblocks <= 2 || (kblocks <= 4 && ctas > g_gemm_ring2_above)) return launch_cfg<BN, 2>(a, stream);
   if (kblocks <= 4) return launch_cfg<BN, 4>(a, stream);
   return launch_cfg<BN, BN == 64 ? 8 : 6>(a, stream);
 }
@@ -296,6 +299,11 @@ int launch_bn(const GemmArgs& a, cudaStream_t stream) {
 }  // namespace
 
 int g_gemm_bn64_below = 296;   // vls_set_tuning("gemm_bn64_below")
+// vls_set_tuning("gemm_ring2_above"): K <= 256 GEMMs with more CTAs than this use a 2-stage operand ring.  Was 2 x 148 (only
+// multi-wave grids); 0 since the pipelined frame: the M = 4096 projections of the memory attention run next to the background key
+// projection, whose three resident 69 KB CTAs per SM leave no room for a 97 KB four-stage CTA until two of them retire -- a 50 KB
+// two-stage CTA starts when one does.  Frame 0.8865 -> 0.8752 ms (three runs each on one box; 100: 0.8763, 130: 0.8915).
+int g_gemm_ring2_above = 0;
 
 int launch_gemm(const GemmArgs& a_in, cudaStream_t stream) {
   GemmArgs a = a_in;

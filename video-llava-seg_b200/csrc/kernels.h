@@ -37,6 +37,7 @@ struct GemmArgs {
   int c_colblock = 0; long long c_colblock_stride = 0;
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t stream);
+extern int g_gemm_ring2_above;  // K <= 256 GEMMs with more CTAs than this use a 2-stage operand ring (more CTAs resident per SM)
 extern int g_gemm_bn64_below;   // GEMMs with fewer 128 x 128 tiles than this use 128 x 64 tiles
 
 // ---------------------------------------------------------------- tcgen05 flash attention (attn_tc.cu)
